@@ -1,0 +1,174 @@
+/*
+ * kge_b200.h — C-ABI of the B200-native KGE scoring engine (libkge_b200.so).
+ *
+ * The reference (Sujit-O/pykg2vec) has NO native interface: its hot path is the
+ * duck-typed Python surface `model.forward(h, r, t)` / `model.loss(...)` /
+ * `Evaluator.test_*_rank` executed as chains of ATen ops.  Each entry point
+ * below replaces one such chain; the comment above it cites the reference
+ * lines (relative to /root/reference/) whose behaviour it reproduces.
+ *
+ * Conventions
+ *   - plain `extern "C"`, POD arguments, raw DEVICE pointers unless the name
+ *     says `host`; no torch / C++ types cross this boundary.
+ *   - every function returns 0 on success, a negative KGE_E* code otherwise and
+ *     never throws; `kge_last_error()` returns a thread-local message.
+ *   - nothing is allocated or retained: all buffers are borrowed for the call,
+ *     outputs and workspaces are pre-allocated by the caller.
+ *   - `stream` is a `cudaStream_t` passed as `void*` (0 = legacy default
+ *     stream).  All work is enqueued asynchronously on it.
+ *   - no CUDA state is touched at load time (fork-safe: pykg2vec forks sampler
+ *     processes after CUDA init, pykg2vec/data/generator.py:292-312).
+ *   - ids are int64 (torch.LongTensor, pykg2vec/utils/trainer.py:275-293),
+ *     tables are fp32 row-major [rows, dim] (nn.Embedding weights,
+ *     pykg2vec/models/Domain.py:8-17), scores are fp32.
+ *
+ * Canonical arithmetic ("RSUM order") is specified in DESIGN.md §3; the CPU
+ * oracle (oracle/kge_oracle.c) restates it independently and the two agree
+ * bit-for-bit on scores and therefore exactly on ranks.
+ */
+#ifndef KGE_B200_H
+#define KGE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KGE_ABI_VERSION 1
+#define KGE_MAX_TABLES 6
+
+/* status codes */
+#define KGE_OK 0
+#define KGE_EINVAL -1   /* bad argument (null pointer, unsupported dim, ...) */
+#define KGE_ENOTSUP -2  /* model / mode not implemented by this entry point */
+#define KGE_ECUDA -3    /* CUDA runtime error, see kge_last_error() */
+#define KGE_EWORKSPACE -4 /* workspace too small */
+
+/* model ids.  Table order in kge_model_t.tables[] is given per model.
+ * (file:line = the reference forward()/embed() being replaced) */
+enum kge_model_id {
+  KGE_TRANSE = 0,   /* [ent, rel]                       pairwise.py:56-93   */
+  KGE_TRANSH = 1,   /* [ent, rel, w]                    pairwise.py:143-182 */
+  KGE_TRANSD = 2,   /* [ent, rel, ent_map, rel_map]     pairwise.py:229-278 */
+  KGE_TRANSR = 3,   /* [ent, rel, rel_matrix]           pairwise.py:405-470 */
+  KGE_ROTATE = 4,   /* [ent_re, ent_im, rel]            pairwise.py:765-791 */
+  KGE_HOLE = 5,     /* [ent, rel]                       pairwise.py:1119-1125 */
+  KGE_DISTMULT = 6, /* [ent, rel]                       pointwise.py:444-446 */
+  KGE_COMPLEX = 7,  /* [ent_re, ent_im, rel_re, rel_im] pointwise.py:163-188 */
+  KGE_CP = 8,       /* [sub, rel, obj]                  pointwise.py:374-376 */
+  KGE_SIMPLE = 9,   /* [ent_h, ent_t, rel, rel_inv]     pointwise.py:522-526 */
+  KGE_TRANSM = 10,  /* [ent, rel, theta(R x 1)]         pairwise.py:325-347 */
+  KGE_NUM_MODELS = 11
+};
+
+/* Which two operands are combined first.  TAIL: (h,r) are the
+ * query side and t is the candidate — this is also the order forward() uses,
+ * matching the reference's left-to-right `h + r - t` / `h*r*t`.  HEAD: (r,t)
+ * are the query side and h is the candidate (Evaluator.test_head_rank,
+ * pykg2vec/utils/evaluator.py:262-273). */
+enum kge_grouping { KGE_GROUP_TAIL = 0, KGE_GROUP_HEAD = 1 };
+
+typedef struct kge_model {
+  int32_t model;        /* enum kge_model_id */
+  int32_t dim;          /* entity embedding width d (hidden_size / ent_hidden_size) */
+  int32_t rel_dim;      /* relation width (TransR rel_hidden_size); else == dim */
+  int32_t l1_flag;      /* TransE-family: 1 -> L1 norm, 0 -> L2 norm (pairwise.py:73-76) */
+  float margin;         /* RotatE margin (pairwise.py:791) */
+  float phase_scale;    /* RotatE: (float)(pi / embedding_range) (pairwise.py:776-782) */
+  int64_t num_ent;      /* rows in the entity tables passed here (a shard may pass fewer) */
+  int64_t num_rel;
+  const float* tables[KGE_MAX_TABLES];
+} kge_model_t;
+
+/* ---- library info ------------------------------------------------------- */
+int kge_abi_version(void);
+const char* kge_version(void);
+const char* kge_last_error(void);
+
+/* ---- batch scoring: replaces model.forward(h, r, t) ---------------------
+ * (pykg2vec/utils/trainer.py:147-180 callers; per-model lines in kge_model_id)
+ * scores[i] = f_model(tables, h[i], r[i], t[i]), i < n.  Lower = more plausible
+ * for every model (the reference negates similarity models). */
+int kge_score_fwd(const kge_model_t* m, int grouping, const int64_t* h, const int64_t* r,
+                  const int64_t* t, int64_t n, float* scores, void* stream);
+
+/* Backward of forward() (autograd through the ATen chain, trainer.py:298).
+ * grad_tables[k] is a dense fp32 buffer shaped like tables[k] (nn.Embedding
+ * dense-gradient semantics, Domain.py:8-17); row gradients are ACCUMULATED
+ * into it (caller zeroes).  grad_tables[k] may be NULL to skip a table. */
+int kge_score_bwd(const kge_model_t* m, const int64_t* h, const int64_t* r, const int64_t* t,
+                  int64_t n, const float* grad_scores, float* const* grad_tables, void* stream);
+
+/* ---- losses: replace pykg2vec/utils/criterion.py ------------------------
+ * Each call writes the scalar loss to loss_out[0] and, when the grad pointers
+ * are non-NULL, d loss / d score (so autograd needs no second pass). */
+/* Criterion.pairwise_hinge, criterion.py:26-29: sum_i max(pos_i + margin - neg_i, 0) */
+int kge_loss_pairwise_hinge(const float* pos, const float* neg, int64_t n, float margin,
+                            float* loss_out, float* grad_pos, float* grad_neg, void* stream);
+/* Criterion.pointwise_logistic, criterion.py:32-34: mean_i softplus(target_i * preds_i) */
+int kge_loss_pointwise_logistic(const float* preds, const float* target, int64_t n,
+                                float* loss_out, float* grad_preds, void* stream);
+/* Criterion.pariwise_logistic (sic), criterion.py:14-23: RotatE self-adversarial loss;
+ * neg is [B * neg_rate] with the negatives of positive i contiguous. */
+int kge_loss_selfadv(const float* pos, const float* neg, int64_t B, int32_t neg_rate, float alpha,
+                     float* loss_out, float* grad_pos, float* grad_neg, void* stream);
+
+/* get_reg() of DistMult / Complex / ComplexN3 (pointwise.py:448-458,190-202,224-238):
+ * reg_out[0] = lmbda * mean_i sum_{gathered rows} sum_j g(x_j); g = x^2 (reg_type 0, "F2"),
+ * x^3 signed (1, DistMult/Complex "N3"), |x|^3 (2, ComplexN3 "N3").  When grad_tables
+ * is non-NULL the gradient scaled by grad_scale is accumulated into it. */
+int kge_reg_fwd_bwd(const kge_model_t* m, int reg_type, float lmbda, const int64_t* h,
+                    const int64_t* r, const int64_t* t, int64_t n, float* reg_out,
+                    float grad_scale, float* const* grad_tables, void* stream);
+
+/* ---- fused training steps (trainer.py:147-157 + :298-299 in one pass) ----
+ * pos/neg forward + hinge + backward + SGD update of the touched rows.
+ * Equivalent to optim.SGD on dense nn.Embedding gradients (rows with zero
+ * gradient do not move).  loss_out[0] receives the batch loss.  neg ids are
+ * [n * neg_rate]; hinge requires neg_rate == 1 as in the reference (the
+ * shapes only broadcast then, criterion.py:26-29). */
+int kge_train_pairwise_hinge_sgd(const kge_model_t* m, float* const* tables_rw,
+                                 const int64_t* pos_h, const int64_t* pos_r, const int64_t* pos_t,
+                                 const int64_t* neg_h, const int64_t* neg_r, const int64_t* neg_t,
+                                 int64_t n, float margin, float lr, float* loss_out, void* stream);
+
+/* ---- 1-vs-all link-prediction ranks: replaces Evaluator.test ------------
+ * (pykg2vec/utils/evaluator.py:309-334 + MetricCalculator.get_*_rank :70-123)
+ *
+ * For query i = (qh[i], qr[i], qt[i]) and candidate entity rows
+ * [row_lo, row_hi) of the tables in `m` (m->num_ent == row_hi - row_lo rows are
+ * addressable, local row k is global entity row_lo + k):
+ *   counts[i*4+0] += #{e : score(qh,qr,e) <  score(qh,qr,qt)}            (tail, raw)
+ *   counts[i*4+1] += the same minus #{e in filt_t[i], e != qt : ...}      (tail, filtered)
+ *   counts[i*4+2], counts[i*4+3]: likewise for heads with filt_h (tr_h).
+ * i.e. the 0-based ranks MetricCalculator computes when scores are tie-free.
+ * Query-side rows are read from `mq` (normally == m; for a row-sharded table a
+ * compact table of gathered query rows with qh/qt re-indexed into it, while
+ * tgt_h/tgt_t keep GLOBAL entity ids used only for id comparisons and filters).
+ * Filters are CSR over queries with GLOBAL entity ids (hr_t / tr_h of
+ * pykg2vec/data/kgcontroller.py:410-428); pointers may be NULL (raw only).
+ * counts is ACCUMULATED (caller zeroes), int32 [Q,4]; partial counts of
+ * different row shards add up to the global rank (one all-reduce).
+ * workspace: >= kge_rank_workspace_bytes(m, Q) bytes of device memory. */
+int64_t kge_rank_workspace_bytes(const kge_model_t* m, int64_t Q);
+int kge_rank_1vsall(const kge_model_t* m, const kge_model_t* mq, int64_t row_lo, int64_t row_hi,
+                    const int64_t* qh, const int64_t* qr, const int64_t* qt,
+                    const int64_t* tgt_h, const int64_t* tgt_t, int64_t Q,
+                    const int64_t* filt_t_ptr, const int64_t* filt_t_idx,
+                    const int64_t* filt_h_ptr, const int64_t* filt_h_idx,
+                    int32_t* counts, void* workspace, int64_t workspace_bytes, int flags,
+                    void* stream);
+/* flags for kge_rank_1vsall */
+#define KGE_RANK_FORCE_GATHER 1 /* use the untiled gather sweep even where a tiled kernel exists */
+#define KGE_RANK_TAIL_ONLY 2
+#define KGE_RANK_HEAD_ONLY 4
+
+/* Number of kernels this library has launched since load (all streams); used
+ * by bench.py for its gpu_launches claim. */
+int64_t kge_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KGE_B200_H */

@@ -1,0 +1,172 @@
+"""CPU oracle — TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this package.  ``pykg2vec_b200`` never does.
+
+Two pieces:
+
+* ``kge_oracle.c`` (this module binds it with ctypes): scalar C restatement of the
+  reference's score functions and of the 1-vs-all rank computation in the
+  canonical arithmetic of DESIGN.md §3.  Bit-exact contract with the CUDA path.
+* ``ref_port.py``: torch restatement of the reference's ATen op chains (used as
+  the fp64 gradient oracle and as the timed CPU baseline).
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SRC = os.path.join(_HERE, "kge_oracle.c")
+_OUT_DIR = os.path.join(_HERE, "_build")
+_SO = os.path.join(_OUT_DIR, "libkge_oracle.so")
+
+MODEL_IDS = {
+    "transe": 0, "transh": 1, "transd": 2, "transr": 3, "rotate": 4, "hole": 5,
+    "distmult": 6, "complex": 7, "cp": 8, "simple": 9, "transm": 10,
+}
+GROUP_TAIL, GROUP_HEAD = 0, 1
+MAX_TABLES = 6
+
+
+class KgeModel(ctypes.Structure):
+    _fields_ = [
+        ("model", ctypes.c_int32), ("dim", ctypes.c_int32), ("rel_dim", ctypes.c_int32),
+        ("l1_flag", ctypes.c_int32), ("margin", ctypes.c_float), ("phase_scale", ctypes.c_float),
+        ("num_ent", ctypes.c_int64), ("num_rel", ctypes.c_int64),
+        ("tables", ctypes.c_void_p * MAX_TABLES),
+    ]
+
+
+def build(force=False):
+    """gcc -O2 -ffp-contract=off (no FMA contraction: fmaf() is explicit) + OpenMP."""
+    if not force and os.path.exists(_SO) and os.path.getmtime(_SO) >= os.path.getmtime(_SRC):
+        return _SO
+    os.makedirs(_OUT_DIR, exist_ok=True)
+    cmd = ["gcc", "-O2", "-std=c11", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
+           "-fopenmp", "-mfma", "-o", _SO + ".tmp", _SRC, "-lm"]
+    subprocess.run(cmd, check=True)
+    os.replace(_SO + ".tmp", _SO)
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build())
+        _lib.kgeo_sincosf.argtypes = [ctypes.c_float, ctypes.POINTER(ctypes.c_float),
+                                      ctypes.POINTER(ctypes.c_float)]
+    return _lib
+
+
+def _f32(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+class Model:
+    """Host-side model description: name + list of fp32 numpy tables in C-ABI order."""
+
+    def __init__(self, name, tables, dim, rel_dim=None, l1_flag=False, margin=0.0,
+                 embedding_range=None):
+        self.name = name.lower()
+        self.tables = [_f32(t) for t in tables]
+        self.dim = int(dim)
+        self.rel_dim = int(rel_dim if rel_dim is not None else dim)
+        self.l1_flag = bool(l1_flag)
+        self.margin = float(margin)
+        # RotatE: theta = r / (embedding_range / pi)  (pairwise.py:748,776-782)
+        self.phase_scale = float(np.float32(np.pi / embedding_range)) if embedding_range else 0.0
+        self.num_ent = self.tables[0].shape[0]
+        rel_index = {"rotate": 2, "complex": 2}.get(self.name, 1)
+        self.num_rel = self.tables[rel_index].shape[0]
+
+    def c_struct(self):
+        m = KgeModel()
+        m.model = MODEL_IDS[self.name]
+        m.dim, m.rel_dim, m.l1_flag = self.dim, self.rel_dim, int(self.l1_flag)
+        m.margin, m.phase_scale = self.margin, self.phase_scale
+        m.num_ent, m.num_rel = self.num_ent, self.num_rel
+        for k, t in enumerate(self.tables):
+            m.tables[k] = t.ctypes.data
+        return m
+
+
+def score_fwd(model, h, r, t, grouping=GROUP_TAIL):
+    h, r, t = _i64(h), _i64(r), _i64(t)
+    out = np.empty(h.shape[0], dtype=np.float32)
+    m = model.c_struct()
+    rc = lib().kgeo_score_fwd(ctypes.byref(m), int(grouping), _ptr(h), _ptr(r), _ptr(t),
+                              ctypes.c_int64(h.shape[0]), _ptr(out))
+    assert rc == 0
+    return out
+
+
+def sweep_scores(model, grouping, h, r, t, row_lo=0, row_hi=None):
+    row_hi = model.num_ent if row_hi is None else row_hi
+    out = np.empty(row_hi - row_lo, dtype=np.float32)
+    m = model.c_struct()
+    rc = lib().kgeo_sweep_scores(ctypes.byref(m), int(grouping), ctypes.c_int64(h), ctypes.c_int64(r),
+                                 ctypes.c_int64(t), ctypes.c_int64(row_lo), ctypes.c_int64(row_hi),
+                                 _ptr(out))
+    assert rc == 0
+    return out
+
+
+def rank_1vsall(model, qh, qr, qt, filt_t=None, filt_h=None, row_lo=0, row_hi=None):
+    """filt_* = (ptr[Q+1], idx[nnz]) CSR of known positives per query, or None."""
+    qh, qr, qt = _i64(qh), _i64(qr), _i64(qt)
+    Q = qh.shape[0]
+    row_hi = model.num_ent if row_hi is None else row_hi
+    counts = np.zeros((Q, 4), dtype=np.int32)
+    ft = (None, None) if filt_t is None else (_i64(filt_t[0]), _i64(filt_t[1]))
+    fh = (None, None) if filt_h is None else (_i64(filt_h[0]), _i64(filt_h[1]))
+    m = model.c_struct()
+    rc = lib().kgeo_rank_1vsall(ctypes.byref(m), ctypes.c_int64(row_lo), ctypes.c_int64(row_hi),
+                                _ptr(qh), _ptr(qr), _ptr(qt), ctypes.c_int64(Q),
+                                _ptr(ft[0]), _ptr(ft[1]), _ptr(fh[0]), _ptr(fh[1]), _ptr(counts))
+    assert rc == 0
+    return counts
+
+
+def loss_pairwise_hinge(pos, neg, margin):
+    pos, neg = _f32(pos), _f32(neg)
+    out = np.zeros(1, dtype=np.float32)
+    terms = np.empty(pos.shape[0], dtype=np.float32)
+    lib().kgeo_loss_pairwise_hinge(_ptr(pos), _ptr(neg), ctypes.c_int64(pos.shape[0]),
+                                   ctypes.c_float(margin), _ptr(out), _ptr(terms))
+    return float(out[0]), terms
+
+
+def loss_pointwise_logistic(preds, target):
+    preds, target = _f32(preds), _f32(target)
+    out = np.zeros(1, dtype=np.float32)
+    lib().kgeo_loss_pointwise_logistic(_ptr(preds), _ptr(target), ctypes.c_int64(preds.shape[0]),
+                                       _ptr(out))
+    return float(out[0])
+
+
+def loss_selfadv(pos, neg, neg_rate, alpha):
+    pos, neg = _f32(pos), _f32(neg)
+    out = np.zeros(1, dtype=np.float32)
+    lib().kgeo_loss_selfadv(_ptr(pos), _ptr(neg), ctypes.c_int64(pos.shape[0]),
+                            ctypes.c_int32(neg_rate), ctypes.c_float(alpha), _ptr(out))
+    return float(out[0])
+
+
+def sincosf(x):
+    s, c = ctypes.c_float(), ctypes.c_float()
+    lib().kgeo_sincosf(ctypes.c_float(x), ctypes.byref(s), ctypes.byref(c))
+    return s.value, c.value

@@ -1,0 +1,196 @@
+"""Torch restatement of the reference's ATen op chains — TEST INFRASTRUCTURE ONLY.
+
+Purpose (see oracle/__init__.py for the access rules):
+  * fp64 autograd through these formulas is the GRADIENT oracle for the CUDA
+    backward kernels (tests/);
+  * fp32 on CPU with all host threads, it is the timed ``cpu_baseline`` /
+    ``--impl reference`` arm of bench.py ("port": the real reference cannot travel
+    to the GPU box).  It executes the same op sequence the reference does —
+    gather, F.normalize, elementwise chain, reduction, full ``topk`` sort, D2H, and
+    the per-triple Python rank walk — so its timing is representative of
+    pykg2vec's own CPU path.
+
+Every function cites the reference lines it follows (relative to /root/reference/).
+It is pinned against the real reference by tests/test_oracle_golden.py.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+def _norm_dist(h, r, t, l1):
+    """pairwise.py:69-76 — normalise the three operands, then p-norm of h + r - t."""
+    x = F.normalize(h, p=2, dim=-1) + F.normalize(r, p=2, dim=-1) - F.normalize(t, p=2, dim=-1)
+    return torch.norm(x, p=1 if l1 else 2, dim=-1)
+
+
+def score(name, tables, h, r, t, l1_flag=False, margin=0.0, embedding_range=None, rel_dim=None):
+    """model.forward(h, r, t) for the in-scope models.  tables in C-ABI order
+    (include/kge_b200.h, enum kge_model_id)."""
+    name = name.lower()
+    if name == "transe":  # pairwise.py:56-93
+        ent, rel = tables
+        return _norm_dist(ent[h], rel[r], ent[t], l1_flag)
+    if name == "transm":  # pairwise.py:325-347
+        ent, rel, theta = tables
+        return theta[r] * _norm_dist(ent[h], rel[r], ent[t], l1_flag)
+    if name == "transh":  # pairwise.py:143-182
+        ent, rel, w = tables
+        wn = F.normalize(w[r], p=2, dim=-1)
+        eh, et = ent[h], ent[t]
+        eh = eh - (eh * wn).sum(-1, keepdim=True) * wn
+        et = et - (et * wn).sum(-1, keepdim=True) * wn
+        return _norm_dist(eh, rel[r], et, l1_flag)
+    if name == "transd":  # pairwise.py:229-278
+        ent, rel, emap, rmap = tables
+        eh, et, rm = ent[h], ent[t], rmap[r]
+        eh = eh + (eh * emap[h]).sum(-1, keepdim=True) * rm
+        et = et + (et * emap[t]).sum(-1, keepdim=True) * rm
+        return _norm_dist(eh, rel[r], et, l1_flag)
+    if name == "transr":  # pairwise.py:405-470
+        ent, rel, mat = tables
+        d = ent.shape[1]
+        dr = rel.shape[1] if rel_dim is None else rel_dim
+        eh = F.normalize(ent[h], p=2, dim=-1)
+        er = F.normalize(rel[r], p=2, dim=-1)
+        et = F.normalize(ent[t], p=2, dim=-1)
+        m = mat[r].view(-1, d, dr)
+        eh = torch.matmul(eh.unsqueeze(1), m).squeeze(1)
+        et = torch.matmul(et.unsqueeze(1), m).squeeze(1)
+        return _norm_dist(eh, er, et, l1_flag)
+    if name == "rotate":  # pairwise.py:765-791
+        ent_re, ent_im, rel = tables
+        phase = rel[r] / (embedding_range / 3.14159265358979323846)
+        re, im = torch.cos(phase), torch.sin(phase)
+        hr, hi, tr, ti = ent_re[h], ent_im[h], ent_re[t], ent_im[t]
+        sr = hr * re - hi * im - tr
+        si = hr * im + hi * re - ti
+        return -(margin - torch.sum(sr ** 2 + si ** 2, dim=-1))
+    if name == "distmult":  # pointwise.py:444-446
+        ent, rel = tables
+        return -torch.sum(ent[h] * rel[r] * ent[t], -1)
+    if name == "cp":  # pointwise.py:374-376
+        sub, rel, obj = tables
+        return -torch.sum(sub[h] * rel[r] * obj[t], -1)
+    if name == "complex":  # pointwise.py:163-188
+        ere, eim, rre, rim = tables
+        hr, hi, tr, ti, rr, ri = ere[h], eim[h], ere[t], eim[t], rre[r], rim[r]
+        return -torch.sum(hr * tr * rr + hi * ti * rr + hr * ti * ri - hi * tr * ri, -1)
+    raise NotImplementedError(name)
+
+
+def gathered_rows(name, tables, h, r, t):
+    """The rows get_reg() re-gathers (pointwise.py:448-458, 190-202, 377-388)."""
+    name = name.lower()
+    if name == "distmult":
+        ent, rel = tables
+        return [ent[h], rel[r], ent[t]]
+    if name == "cp":
+        sub, rel, obj = tables
+        return [sub[h], rel[r], obj[t]]
+    if name == "complex":
+        ere, eim, rre, rim = tables
+        return [ere[h], eim[h], rre[r], rim[r], ere[t], eim[t]]
+    raise NotImplementedError(name)
+
+
+def reg(name, tables, h, r, t, lmbda, reg_type):
+    """reg_type 0: F2 (x**2); 1: signed N3 (x**3, Complex/DistMult 'n3');
+    2: |x|**3 (ComplexN3.get_reg, pointwise.py:224-238)."""
+    rows = gathered_rows(name, tables, h, r, t)
+    if reg_type == 0:
+        per = sum(torch.sum(x ** 2, -1) for x in rows)
+    elif reg_type == 1:
+        per = sum(torch.sum(x ** 3, -1) for x in rows)
+    else:
+        per = sum(torch.sum(x.abs() ** 3, -1) for x in rows)
+    return lmbda * torch.mean(per)
+
+
+# ---- losses (pykg2vec/utils/criterion.py) -------------------------------------
+def pairwise_hinge(pos, neg, margin):  # criterion.py:26-29
+    v = pos + margin - neg
+    return torch.max(v, torch.zeros_like(v)).sum()
+
+
+def pointwise_logistic(preds, target):  # criterion.py:32-34
+    return F.softplus(target * preds).mean()
+
+
+def selfadv(pos, neg, neg_rate, alpha):  # criterion.py:14-23
+    p = F.logsigmoid(-pos)
+    n = (-neg).view(-1, neg_rate)
+    w = torch.softmax(n * alpha, dim=1).detach()
+    n = torch.sum(w * F.logsigmoid(-n), dim=-1)
+    return -n.mean() - p.mean()
+
+
+# ---- evaluation (pykg2vec/utils/evaluator.py) ---------------------------------
+def _walk(order, target, known):
+    """MetricCalculator.get_tail_rank / get_head_rank, evaluator.py:70-123:
+    read the descending-sorted id list from its END (best first) until the target."""
+    rank = frank = 0
+    for j in range(len(order)):
+        e = order[-j - 1]
+        if e == target:
+            break
+        rank += 1
+        frank += 1
+        if e in known:
+            frank -= 1
+    return rank, frank
+
+
+def evaluate(score_fn, num_ent, triples, hr_t, tr_h, python_walk=True):
+    """Evaluator.test, evaluator.py:309-334: per test triple two 1-vs-all forwards,
+    a full topk(k=N) sort each, transfer to numpy, then the Python walk.
+    score_fn(h, r, t) -> [b] scores for LongTensors.  Returns list of
+    (trank, ftrank, hrank, fhrank) 0-based."""
+    out = []
+    ents = torch.arange(num_ent, dtype=torch.long)
+    for (h, r, t) in triples:
+        hb = torch.full((num_ent,), h, dtype=torch.long)
+        rb = torch.full((num_ent,), r, dtype=torch.long)
+        tb = torch.full((num_ent,), t, dtype=torch.long)
+        _, head_order = torch.topk(score_fn(ents, rb, tb), k=num_ent)  # evaluator.py:262-273
+        _, tail_order = torch.topk(score_fn(hb, rb, ents), k=num_ent)  # evaluator.py:249-260
+        head_order = head_order.detach().cpu().numpy()
+        tail_order = tail_order.detach().cpu().numpy()
+        if python_walk:
+            tr, ftr = _walk(tail_order, t, hr_t.get((h, r), ()))
+            hrk, fhr = _walk(head_order, h, tr_h.get((t, r), ()))
+            out.append((tr, ftr, hrk, fhr))
+        else:
+            out.append((int(tail_order[-1]), 0, int(head_order[-1]), 0))
+    return out
+
+
+def settle(ranks0, hits=(1, 3, 5, 10)):
+    """MetricCalculator.settle, evaluator.py:125-141.  ranks0: [Q,4] 0-based
+    (trank, ftrank, hrank, fhrank)."""
+    import numpy as np
+    a = np.asarray(ranks0)
+    head = a[:, 2].astype(np.float32) + 1
+    tail = a[:, 0].astype(np.float32) + 1
+    fhead = a[:, 3].astype(np.float32) + 1
+    ftail = a[:, 1].astype(np.float32) + 1
+    ranks = np.concatenate((head, tail))
+    franks = np.concatenate((fhead, ftail))
+    res = {"mr": np.mean(ranks), "mrr": np.mean(np.reciprocal(ranks)),
+           "fmr": np.mean(franks), "fmrr": np.mean(np.reciprocal(franks))}
+    for k in hits:
+        res["hit%d" % k] = np.mean(ranks <= k, dtype=np.float32)
+        res["fhit%d" % k] = np.mean(franks <= k, dtype=np.float32)
+    return res
+
+
+def embedding_range(margin, dim):
+    """RotatE.__init__, pairwise.py:748."""
+    return (margin + 2.0) / dim
+
+
+def xavier_uniform(rows, cols, gen):
+    """nn.init.xavier_uniform_ on a [rows, cols] table (pairwise.py:46-47)."""
+    a = math.sqrt(6.0 / (rows + cols))
+    return (torch.rand(rows, cols, generator=gen, dtype=torch.float32) * 2 - 1) * a

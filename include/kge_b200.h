@@ -147,7 +147,9 @@ int kge_train_pairwise_hinge_sgd(const kge_model_t* m, float* const* tables_rw,
  * compact table of gathered query rows with qh/qt re-indexed into it, while
  * tgt_h/tgt_t keep GLOBAL entity ids used only for id comparisons and filters).
  * Filters are CSR over queries with GLOBAL entity ids (hr_t / tr_h of
- * pykg2vec/data/kgcontroller.py:410-428); pointers may be NULL (raw only).
+ * pykg2vec/data/kgcontroller.py:410-428): ptr[Q+1], idx[nnz]; nnz is passed
+ * explicitly (it lives in device memory as ptr[Q]).  Pointers may be NULL /
+ * nnz 0 (then filtered == raw).  Q <= 65535 per call (batch larger test sets).
  * counts is ACCUMULATED (caller zeroes), int32 [Q,4]; partial counts of
  * different row shards add up to the global rank (one all-reduce).
  * workspace: >= kge_rank_workspace_bytes(m, Q) bytes of device memory. */
@@ -155,8 +157,8 @@ int64_t kge_rank_workspace_bytes(const kge_model_t* m, int64_t Q);
 int kge_rank_1vsall(const kge_model_t* m, const kge_model_t* mq, int64_t row_lo, int64_t row_hi,
                     const int64_t* qh, const int64_t* qr, const int64_t* qt,
                     const int64_t* tgt_h, const int64_t* tgt_t, int64_t Q,
-                    const int64_t* filt_t_ptr, const int64_t* filt_t_idx,
-                    const int64_t* filt_h_ptr, const int64_t* filt_h_idx,
+                    const int64_t* filt_t_ptr, const int64_t* filt_t_idx, int64_t filt_t_nnz,
+                    const int64_t* filt_h_ptr, const int64_t* filt_h_idx, int64_t filt_h_nnz,
                     int32_t* counts, void* workspace, int64_t workspace_bytes, int flags,
                     void* stream);
 /* flags for kge_rank_1vsall */

@@ -1,0 +1,245 @@
+"""ctypes binding of libkge_b200.so (the C-ABI declared in include/kge_b200.h).
+
+There is no fallback: if the library is missing or a call fails this module raises.
+torch is used only for device memory, streams and tensor metadata.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_build", "libkge_b200.so")
+MAX_TABLES = 6
+ABI_VERSION = 1
+
+MODEL_IDS = {
+    "transe": 0, "transh": 1, "transd": 2, "transr": 3, "rotate": 4, "hole": 5,
+    "distmult": 6, "complex": 7, "cp": 8, "simple": 9, "transm": 10,
+}
+GROUP_TAIL, GROUP_HEAD = 0, 1
+RANK_FORCE_GATHER, RANK_TAIL_ONLY, RANK_HEAD_ONLY = 1, 2, 4
+
+# every symbol include/kge_b200.h declares (tests check they are all exported)
+EXPORTS = [
+    "kge_abi_version", "kge_version", "kge_last_error", "kge_launch_count",
+    "kge_score_fwd", "kge_score_bwd",
+    "kge_loss_pairwise_hinge", "kge_loss_pointwise_logistic", "kge_loss_selfadv", "kge_reg_fwd_bwd",
+    "kge_train_pairwise_hinge_sgd",
+    "kge_rank_workspace_bytes", "kge_rank_1vsall",
+]
+
+
+class KgeModel(ctypes.Structure):
+    _fields_ = [
+        ("model", ctypes.c_int32), ("dim", ctypes.c_int32), ("rel_dim", ctypes.c_int32),
+        ("l1_flag", ctypes.c_int32), ("margin", ctypes.c_float), ("phase_scale", ctypes.c_float),
+        ("num_ent", ctypes.c_int64), ("num_rel", ctypes.c_int64),
+        ("tables", ctypes.c_void_p * MAX_TABLES),
+    ]
+
+
+class KgeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load the shared library (once).  Raises if it has not been built: the product
+    path never falls back to a CPU or PyTorch implementation."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise KgeError("libkge_b200.so not found at %s — run `python -m pykg2vec_b200.build` "
+                       "(or __graft_entry__.build())" % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    L.kge_version.restype = ctypes.c_char_p
+    L.kge_last_error.restype = ctypes.c_char_p
+    L.kge_launch_count.restype = ctypes.c_int64
+    L.kge_rank_workspace_bytes.restype = ctypes.c_int64
+    if L.kge_abi_version() != ABI_VERSION:
+        raise KgeError("libkge_b200.so ABI %d != binding ABI %d" % (L.kge_abi_version(), ABI_VERSION))
+    _lib = L
+    return L
+
+
+def check(rc, what):
+    if rc != 0:
+        raise KgeError("%s failed (%d): %s" % (what, rc, lib().kge_last_error().decode()))
+
+
+def _ptr(t):
+    if t is None:
+        return ctypes.c_void_p(0)
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev_i64(t, name):
+    if t.dtype != torch.int64 or not t.is_cuda or not t.is_contiguous():
+        raise KgeError("%s must be a contiguous CUDA int64 tensor" % name)
+    return t
+
+
+def _dev_f32(t, name):
+    if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+        raise KgeError("%s must be a contiguous CUDA float32 tensor" % name)
+    return t
+
+
+class ModelDesc:
+    """Host description of a model: C-ABI name + device tables in C-ABI order."""
+
+    def __init__(self, name, tables, dim, rel_dim=None, l1_flag=False, margin=0.0, phase_scale=0.0,
+                 num_ent=None, num_rel=None):
+        self.name = name.lower()
+        if self.name not in MODEL_IDS:
+            raise KgeError("unknown model %r" % name)
+        self.tables = [_dev_f32(t, "table") for t in tables]
+        self.dim = int(dim)
+        self.rel_dim = int(rel_dim if rel_dim is not None else dim)
+        self.l1_flag = bool(l1_flag)
+        self.margin = float(margin)
+        self.phase_scale = float(phase_scale)
+        rel_index = {"rotate": 2, "complex": 2}.get(self.name, 1)
+        self.num_ent = int(num_ent if num_ent is not None else self.tables[0].shape[0])
+        self.num_rel = int(num_rel if num_rel is not None else self.tables[rel_index].shape[0])
+
+    def c_struct(self, tables=None):
+        m = KgeModel()
+        m.model = MODEL_IDS[self.name]
+        m.dim, m.rel_dim, m.l1_flag = self.dim, self.rel_dim, int(self.l1_flag)
+        m.margin, m.phase_scale = self.margin, self.phase_scale
+        m.num_ent, m.num_rel = self.num_ent, self.num_rel
+        for k, t in enumerate(tables if tables is not None else self.tables):
+            m.tables[k] = t.data_ptr()
+        return m
+
+
+def _table_ptr_array(tensors):
+    arr = (ctypes.c_void_p * MAX_TABLES)()
+    for k, t in enumerate(tensors):
+        arr[k] = t.data_ptr() if t is not None else None
+    return arr
+
+
+def score_fwd(desc, h, r, t, grouping=GROUP_TAIL, out=None):
+    h, r, t = _dev_i64(h, "h"), _dev_i64(r, "r"), _dev_i64(t, "t")
+    n = h.numel()
+    if r.numel() != n or t.numel() != n:
+        raise KgeError("h, r, t must have equal length")
+    if out is None:
+        out = torch.empty(n, dtype=torch.float32, device=h.device)
+    m = desc.c_struct()
+    check(lib().kge_score_fwd(ctypes.byref(m), int(grouping), _ptr(h), _ptr(r), _ptr(t),
+                              ctypes.c_int64(n), _ptr(out), _stream()), "kge_score_fwd")
+    return out
+
+
+def score_bwd(desc, h, r, t, grad_scores, grad_tables):
+    m = desc.c_struct()
+    arr = _table_ptr_array(grad_tables)
+    check(lib().kge_score_bwd(ctypes.byref(m), _ptr(h), _ptr(r), _ptr(t), ctypes.c_int64(h.numel()),
+                              _ptr(_dev_f32(grad_scores, "grad_scores")), arr, _stream()), "kge_score_bwd")
+
+
+def loss_pairwise_hinge(pos, neg, margin, want_grad=True):
+    pos, neg = _dev_f32(pos, "pos"), _dev_f32(neg, "neg")
+    loss = torch.empty(1, dtype=torch.float32, device=pos.device)
+    gp = torch.empty_like(pos) if want_grad else None
+    gn = torch.empty_like(neg) if want_grad else None
+    check(lib().kge_loss_pairwise_hinge(_ptr(pos), _ptr(neg), ctypes.c_int64(pos.numel()),
+                                        ctypes.c_float(margin), _ptr(loss), _ptr(gp), _ptr(gn), _stream()),
+          "kge_loss_pairwise_hinge")
+    return loss, gp, gn
+
+
+def loss_pointwise_logistic(preds, target, want_grad=True):
+    preds, target = _dev_f32(preds, "preds"), _dev_f32(target, "target")
+    loss = torch.empty(1, dtype=torch.float32, device=preds.device)
+    g = torch.empty_like(preds) if want_grad else None
+    check(lib().kge_loss_pointwise_logistic(_ptr(preds), _ptr(target), ctypes.c_int64(preds.numel()),
+                                            _ptr(loss), _ptr(g), _stream()), "kge_loss_pointwise_logistic")
+    return loss, g
+
+
+def loss_selfadv(pos, neg, neg_rate, alpha, want_grad=True):
+    pos, neg = _dev_f32(pos, "pos"), _dev_f32(neg, "neg")
+    if neg.numel() != pos.numel() * neg_rate:
+        raise KgeError("neg must hold neg_rate scores per positive")
+    loss = torch.empty(1, dtype=torch.float32, device=pos.device)
+    gp = torch.empty_like(pos) if want_grad else None
+    gn = torch.empty_like(neg) if want_grad else None
+    check(lib().kge_loss_selfadv(_ptr(pos), _ptr(neg), ctypes.c_int64(pos.numel()), ctypes.c_int32(neg_rate),
+                                 ctypes.c_float(alpha), _ptr(loss), _ptr(gp), _ptr(gn), _stream()),
+          "kge_loss_selfadv")
+    return loss, gp, gn
+
+
+def reg_fwd_bwd(desc, reg_type, lmbda, h, r, t, grad_scale=0.0, grad_tables=None):
+    out = torch.empty(1, dtype=torch.float32, device=h.device)
+    m = desc.c_struct()
+    arr = _table_ptr_array(grad_tables) if grad_tables is not None else None
+    check(lib().kge_reg_fwd_bwd(ctypes.byref(m), int(reg_type), ctypes.c_float(lmbda), _ptr(h), _ptr(r),
+                                _ptr(t), ctypes.c_int64(h.numel()), _ptr(out), ctypes.c_float(grad_scale),
+                                arr, _stream()), "kge_reg_fwd_bwd")
+    return out
+
+
+def train_pairwise_hinge_sgd(desc, grad_scratch, ph, pr, pt, nh, nr, nt, margin, lr, loss_out=None):
+    """In-place fused step on desc.tables; grad_scratch: zero-filled dense buffers shaped
+    like the tables (left zero-filled on return)."""
+    if loss_out is None:
+        loss_out = torch.empty(1, dtype=torch.float32, device=ph.device)
+    m = desc.c_struct()
+    rw = _table_ptr_array(desc.tables)
+    gs = _table_ptr_array(grad_scratch)
+    check(lib().kge_train_pairwise_hinge_sgd(ctypes.byref(m), rw, gs, _ptr(ph), _ptr(pr), _ptr(pt), _ptr(nh),
+                                             _ptr(nr), _ptr(nt), ctypes.c_int64(ph.numel()),
+                                             ctypes.c_float(margin), ctypes.c_float(lr), _ptr(loss_out),
+                                             _stream()), "kge_train_pairwise_hinge_sgd")
+    return loss_out
+
+
+def rank_workspace_bytes(desc, Q):
+    m = desc.c_struct()
+    return int(lib().kge_rank_workspace_bytes(ctypes.byref(m), ctypes.c_int64(Q)))
+
+
+def rank_1vsall(desc, qh, qr, qt, filt_t=None, filt_h=None, counts=None, row_lo=0, row_hi=None,
+                query_desc=None, tgt_h=None, tgt_t=None, flags=0, workspace=None):
+    """Accumulate 0-based (tail raw, tail filtered, head raw, head filtered) rank counts of the
+    queries over candidate rows [row_lo, row_hi) into counts [Q,4] int32.
+    filt_* = (ptr[Q+1] int64 cuda, idx[nnz] int64 cuda) or None."""
+    qh, qr, qt = _dev_i64(qh, "qh"), _dev_i64(qr, "qr"), _dev_i64(qt, "qt")
+    Q = qh.numel()
+    if row_hi is None:
+        row_hi = row_lo + desc.num_ent
+    if counts is None:
+        counts = torch.zeros((Q, 4), dtype=torch.int32, device=qh.device)
+    nbytes = rank_workspace_bytes(desc, Q)
+    if workspace is None or workspace.numel() < nbytes:
+        workspace = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=qh.device)
+    m = desc.c_struct()
+    mq = query_desc.c_struct() if query_desc is not None else None
+    ft_ptr, ft_idx = filt_t if filt_t is not None else (None, None)
+    fh_ptr, fh_idx = filt_h if filt_h is not None else (None, None)
+    check(lib().kge_rank_1vsall(
+        ctypes.byref(m), ctypes.byref(mq) if mq is not None else None,
+        ctypes.c_int64(row_lo), ctypes.c_int64(row_hi), _ptr(qh), _ptr(qr), _ptr(qt),
+        _ptr(tgt_h), _ptr(tgt_t), ctypes.c_int64(Q),
+        _ptr(ft_ptr), _ptr(ft_idx), ctypes.c_int64(ft_idx.numel() if ft_idx is not None else 0),
+        _ptr(fh_ptr), _ptr(fh_idx), ctypes.c_int64(fh_idx.numel() if fh_idx is not None else 0),
+        _ptr(counts), _ptr(workspace), ctypes.c_int64(workspace.numel()), ctypes.c_int(flags), _stream()),
+        "kge_rank_1vsall")
+    return counts
+
+
+def launch_count():
+    return int(lib().kge_launch_count())

@@ -1,0 +1,296 @@
+// kge_models.cuh — per-model score functions evaluated by an 8-lane group.
+//
+// Each function restates one reference forward() (file:line cited, relative to
+// /root/reference/) in the canonical arithmetic of DESIGN.md §3.  All 8 lanes of
+// the group call it with the same row pointers and all return the same score.
+// GROUPING (kge_grouping): TAIL combines (h,r) first, HEAD combines (r,t) first.
+#pragma once
+#include "kge_common.cuh"
+
+namespace kge {
+
+struct TripleRows {
+  const float* h[2];  // head-side rows   (ent / ent_re, ent_map / ent_im)
+  const float* t[2];  // tail-side rows
+  const float* r[3];  // relation-side rows (rel / rel_re, w / rel_map / rel_im / M_r / theta)
+};
+
+// Row pointers of triple (h, r, t).  htab/ttab/rtab: the table sets the head-side,
+// tail-side and relation-side rows are read from (they differ only in 1-vs-all
+// sweeps over a row shard, where the candidate side is the local shard).
+template <int MODEL>
+KGE_DEV void resolve_rows(TripleRows& R, const ModelParams& P, const float* const* htab,
+                          const float* const* ttab, const float* const* rtab, int64_t h, int64_t r,
+                          int64_t t) {
+  const size_t d = (size_t)P.d, dr = (size_t)P.dr;
+  R.h[1] = R.t[1] = R.r[1] = R.r[2] = nullptr;
+  if (MODEL == KGE_TRANSE || MODEL == KGE_DISTMULT) {
+    R.h[0] = htab[0] + h * d; R.t[0] = ttab[0] + t * d; R.r[0] = rtab[1] + r * d;
+  } else if (MODEL == KGE_TRANSM) {
+    R.h[0] = htab[0] + h * d; R.t[0] = ttab[0] + t * d; R.r[0] = rtab[1] + r * d;
+    R.r[1] = rtab[2] + r;  // theta[r]
+  } else if (MODEL == KGE_CP) {
+    R.h[0] = htab[0] + h * d; R.t[0] = ttab[2] + t * d; R.r[0] = rtab[1] + r * d;
+  } else if (MODEL == KGE_TRANSH) {
+    R.h[0] = htab[0] + h * d; R.t[0] = ttab[0] + t * d; R.r[0] = rtab[1] + r * d;
+    R.r[1] = rtab[2] + r * d;
+  } else if (MODEL == KGE_TRANSD) {
+    R.h[0] = htab[0] + h * d; R.t[0] = ttab[0] + t * d; R.r[0] = rtab[1] + r * d;
+    R.h[1] = htab[2] + h * d; R.t[1] = ttab[2] + t * d; R.r[1] = rtab[3] + r * d;
+  } else if (MODEL == KGE_TRANSR) {
+    R.h[0] = htab[0] + h * d; R.t[0] = ttab[0] + t * d; R.r[0] = rtab[1] + r * dr;
+    R.r[1] = rtab[2] + r * d * dr;
+  } else if (MODEL == KGE_ROTATE) {
+    R.h[0] = htab[0] + h * d; R.h[1] = htab[1] + h * d;
+    R.t[0] = ttab[0] + t * d; R.t[1] = ttab[1] + t * d;
+    R.r[0] = rtab[2] + r * d;
+  } else if (MODEL == KGE_COMPLEX) {
+    R.h[0] = htab[0] + h * d; R.h[1] = htab[1] + h * d;
+    R.t[0] = ttab[0] + t * d; R.t[1] = ttab[1] + t * d;
+    R.r[0] = rtab[2] + r * d; R.r[1] = rtab[3] + r * d;
+  }
+}
+
+// Shared tail of TransE/H/D/R/M forward(): L2-normalise h', r', t' and return
+// ||h^ + r^ - t^||_p  (pairwise.py:69-76, :146-153, :266-273, :463-470).
+// fh/fr/ft(c) return chunk c (4 elements, zero beyond the width) of each operand.
+template <int GROUPING, class FH, class FR, class FT>
+KGE_DEV float trans_distance(FH fh, FR fr, FT ft, int nch, int lane, int l1) {
+  float sh = 0.f, sr = 0.f, st = 0.f;
+#pragma unroll 2
+  for (int c = lane; c < nch; c += 8) {
+    const float4 a = fh(c), b = fr(c), cc = ft(c);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      sh = ffma(f4_get(a, e), f4_get(a, e), sh);
+      sr = ffma(f4_get(b, e), f4_get(b, e), sr);
+      st = ffma(f4_get(cc, e), f4_get(cc, e), st);
+    }
+  }
+  const float ih = inv_norm_from_sumsq(group_sum(sh));
+  const float ir = inv_norm_from_sumsq(group_sum(sr));
+  const float it = inv_norm_from_sumsq(group_sum(st));
+  float acc = 0.f;
+#pragma unroll 2
+  for (int c = lane; c < nch; c += 8) {
+    const float4 a = fh(c), b = fr(c), cc = ft(c);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float hn = fmul(f4_get(a, e), ih), rn = fmul(f4_get(b, e), ir), tn = fmul(f4_get(cc, e), it);
+      float x;
+      if (GROUPING == KGE_GROUP_TAIL) x = fsub(fadd(hn, rn), tn);
+      else x = fadd(hn, fsub(rn, tn));
+      if (l1) acc = fadd(acc, fabsf(x)); else acc = ffma(x, x, acc);
+    }
+  }
+  acc = group_sum(acc);
+  return l1 ? acc : __fsqrt_rn(acc);
+}
+
+template <int VEC>
+KGE_DEV float group_dot(const float* __restrict__ a, const float* __restrict__ b, int d, int nch, int lane) {
+  float s = 0.f;
+#pragma unroll 2
+  for (int c = lane; c < nch; c += 8) {
+    const float4 x = ld_chunk<VEC>(a, c, d), y = ld_chunk<VEC>(b, c, d);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) s = ffma(f4_get(x, e), f4_get(y, e), s);
+  }
+  return group_sum(s);
+}
+
+// `scratch`: per-group shared memory, only used by TransR (2 * dr_pad floats).
+template <int MODEL, int VEC, int GROUPING>
+KGE_DEV float score_group(const TripleRows& R, const ModelParams& P, int lane, float* scratch) {
+  const int d = P.d;
+  const int nch = (d + 3) >> 2;
+  if (MODEL == KGE_TRANSE || MODEL == KGE_TRANSM) {
+    // TransE.forward pairwise.py:56-93; TransM.forward pairwise.py:325-347
+    const float dist = trans_distance<GROUPING>(
+        [&](int c) { return ld_chunk<VEC>(R.h[0], c, d); },
+        [&](int c) { return ld_chunk<VEC>(R.r[0], c, d); },
+        [&](int c) { return ld_chunk<VEC>(R.t[0], c, d); }, nch, lane, P.l1);
+    if (MODEL == KGE_TRANSM) return fmul(__ldg(R.r[1]), dist);
+    return dist;
+  } else if (MODEL == KGE_TRANSH) {
+    // TransH.embed/_projection pairwise.py:166-182: e_perp = e - (e . w~) w~
+    float sw = 0.f;
+    for (int c = lane; c < nch; c += 8) {
+      const float4 w = ld_chunk<VEC>(R.r[1], c, d);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sw = ffma(f4_get(w, e), f4_get(w, e), sw);
+    }
+    const float iw = inv_norm_from_sumsq(group_sum(sw));
+    float ah = 0.f, at = 0.f;
+    for (int c = lane; c < nch; c += 8) {
+      const float4 w = ld_chunk<VEC>(R.r[1], c, d), a = ld_chunk<VEC>(R.h[0], c, d),
+                   b = ld_chunk<VEC>(R.t[0], c, d);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float wn = fmul(f4_get(w, e), iw);
+        ah = ffma(f4_get(a, e), wn, ah);
+        at = ffma(f4_get(b, e), wn, at);
+      }
+    }
+    ah = group_sum(ah); at = group_sum(at);
+    auto proj = [&](const float* row, float a, int c) {
+      const float4 w = ld_chunk<VEC>(R.r[1], c, d), x = ld_chunk<VEC>(row, c, d);
+      float4 o;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) f4_at(o, e) = ffma(-a, fmul(f4_get(w, e), iw), f4_get(x, e));
+      return o;
+    };
+    return trans_distance<GROUPING>([&](int c) { return proj(R.h[0], ah, c); },
+                                    [&](int c) { return ld_chunk<VEC>(R.r[0], c, d); },
+                                    [&](int c) { return proj(R.t[0], at, c); }, nch, lane, P.l1);
+  } else if (MODEL == KGE_TRANSD) {
+    // TransD.embed/_projection pairwise.py:240-249,275-278: e' = e + (e . e_m) r_m
+    const float ah = group_dot<VEC>(R.h[0], R.h[1], d, nch, lane);
+    const float at = group_dot<VEC>(R.t[0], R.t[1], d, nch, lane);
+    auto proj = [&](const float* row, float a, int c) {
+      const float4 rm = ld_chunk<VEC>(R.r[1], c, d), x = ld_chunk<VEC>(row, c, d);
+      float4 o;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) f4_at(o, e) = ffma(a, f4_get(rm, e), f4_get(x, e));
+      return o;
+    };
+    return trans_distance<GROUPING>([&](int c) { return proj(R.h[0], ah, c); },
+                                    [&](int c) { return ld_chunk<VEC>(R.r[0], c, d); },
+                                    [&](int c) { return proj(R.t[0], at, c); }, nch, lane, P.l1);
+  } else if (MODEL == KGE_TRANSR) {
+    // TransR.embed/transform pairwise.py:405-442 then forward :463-470
+    const int dr = P.dr, nchr = (dr + 3) >> 2, drp = nchr * 4;
+    float sh = 0.f, st = 0.f, sr = 0.f;
+    for (int c = lane; c < nch; c += 8) {
+      const float4 a = ld_chunk<VEC>(R.h[0], c, d), b = ld_chunk<VEC>(R.t[0], c, d);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { sh = ffma(f4_get(a, e), f4_get(a, e), sh); st = ffma(f4_get(b, e), f4_get(b, e), st); }
+    }
+    for (int c = lane; c < nchr; c += 8) {
+      const float4 b = ld_chunk<VEC>(R.r[0], c, dr);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sr = ffma(f4_get(b, e), f4_get(b, e), sr);
+    }
+    const float ih = inv_norm_from_sumsq(group_sum(sh));
+    const float it = inv_norm_from_sumsq(group_sum(st));
+    const float ir = inv_norm_from_sumsq(group_sum(sr));
+    float* hp = scratch;        // [drp]
+    float* tp = scratch + drp;  // [drp]
+    // h'_k = sum_j h^_j M[j,k], sequential in j (single accumulator per output element);
+    // lane l owns the output chunks c = l, l+8, ...
+    for (int c = lane; c < nchr; c += 8) {
+      float4 ah = make_float4(0.f, 0.f, 0.f, 0.f), at = ah;
+      for (int j = 0; j < d; ++j) {
+        const float hn = fmul(__ldg(R.h[0] + j), ih), tn = fmul(__ldg(R.t[0] + j), it);
+        const float4 mrow = ld_chunk<VEC>(R.r[1] + (size_t)j * dr, c, dr);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          f4_at(ah, e) = ffma(hn, f4_get(mrow, e), f4_get(ah, e));
+          f4_at(at, e) = ffma(tn, f4_get(mrow, e), f4_get(at, e));
+        }
+      }
+      *reinterpret_cast<float4*>(hp + 4 * c) = ah;
+      *reinterpret_cast<float4*>(tp + 4 * c) = at;
+    }
+    __syncwarp();
+    return trans_distance<GROUPING>(
+        [&](int c) { return *reinterpret_cast<const float4*>(hp + 4 * c); },
+        [&](int c) {
+          const float4 b = ld_chunk<VEC>(R.r[0], c, dr);
+          return make_float4(fmul(b.x, ir), fmul(b.y, ir), fmul(b.z, ir), fmul(b.w, ir));
+        },
+        [&](int c) { return *reinterpret_cast<const float4*>(tp + 4 * c); }, nchr, lane, P.l1);
+  } else if (MODEL == KGE_ROTATE) {
+    // RotatE.embed/forward pairwise.py:765-791
+    float acc = 0.f;
+#pragma unroll 2
+    for (int c = lane; c < nch; c += 8) {
+      const float4 hr = ld_chunk<VEC>(R.h[0], c, d), hi = ld_chunk<VEC>(R.h[1], c, d),
+                   rr = ld_chunk<VEC>(R.r[0], c, d), tr = ld_chunk<VEC>(R.t[0], c, d),
+                   ti = ld_chunk<VEC>(R.t[1], c, d);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float im, re;
+        sincos_canon(fmul(f4_get(rr, e), P.phase), im, re);
+        const float u = fmul(f4_get(hi, e), im);
+        const float sr0 = ffma(f4_get(hr, e), re, -u);
+        const float v = fmul(f4_get(hi, e), re);
+        const float si0 = ffma(f4_get(hr, e), im, v);
+        const float sr = fsub(sr0, f4_get(tr, e)), si = fsub(si0, f4_get(ti, e));
+        acc = ffma(sr, sr, acc);
+        acc = ffma(si, si, acc);
+      }
+    }
+    return fsub(group_sum(acc), P.margin);
+  } else if (MODEL == KGE_DISTMULT || MODEL == KGE_CP) {
+    // DistMult.forward pointwise.py:444-446; CP.forward pointwise.py:374-376
+    float acc = 0.f;
+#pragma unroll 2
+    for (int c = lane; c < nch; c += 8) {
+      const float4 a = ld_chunk<VEC>(R.h[0], c, d), b = ld_chunk<VEC>(R.r[0], c, d),
+                   cc = ld_chunk<VEC>(R.t[0], c, d);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (GROUPING == KGE_GROUP_TAIL) acc = ffma(fmul(f4_get(a, e), f4_get(b, e)), f4_get(cc, e), acc);
+        else acc = ffma(f4_get(a, e), fmul(f4_get(b, e), f4_get(cc, e)), acc);
+      }
+    }
+    return -group_sum(acc);
+  } else if (MODEL == KGE_COMPLEX) {
+    // Complex.forward pointwise.py:163-188
+    float acc = 0.f;
+#pragma unroll 2
+    for (int c = lane; c < nch; c += 8) {
+      const float4 hr = ld_chunk<VEC>(R.h[0], c, d), hi = ld_chunk<VEC>(R.h[1], c, d),
+                   rr = ld_chunk<VEC>(R.r[0], c, d), ri = ld_chunk<VEC>(R.r[1], c, d),
+                   tr = ld_chunk<VEC>(R.t[0], c, d), ti = ld_chunk<VEC>(R.t[1], c, d);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (GROUPING == KGE_GROUP_TAIL) {
+          const float qr = ffma(f4_get(hr, e), f4_get(rr, e), -fmul(f4_get(hi, e), f4_get(ri, e)));
+          const float qi = ffma(f4_get(hi, e), f4_get(rr, e), fmul(f4_get(hr, e), f4_get(ri, e)));
+          acc = ffma(qr, f4_get(tr, e), acc);
+          acc = ffma(qi, f4_get(ti, e), acc);
+        } else {
+          const float qr = ffma(f4_get(tr, e), f4_get(rr, e), fmul(f4_get(ti, e), f4_get(ri, e)));
+          const float qi = ffma(f4_get(ti, e), f4_get(rr, e), -fmul(f4_get(tr, e), f4_get(ri, e)));
+          acc = ffma(f4_get(hr, e), qr, acc);
+          acc = ffma(f4_get(hi, e), qi, acc);
+        }
+      }
+    }
+    return -group_sum(acc);
+  }
+  return 0.f;
+}
+
+// shared-memory floats one 8-lane group needs (TransR only)
+inline size_t group_scratch_floats(const kge_model_t* m) {
+  if (m->model != KGE_TRANSR) return 0;
+  return (size_t)2 * (size_t)(((m->rel_dim + 3) >> 2) * 4);
+}
+
+// Dispatch helper: calls F.template run<MODEL, VEC>() for the runtime (model, vec).
+#define KGE_DISPATCH_MODEL_VEC(model, vec, CALL)                                   \
+  do {                                                                             \
+    switch (model) {                                                               \
+      case KGE_TRANSE: KGE_DISPATCH_VEC(KGE_TRANSE, vec, CALL); break;             \
+      case KGE_TRANSH: KGE_DISPATCH_VEC(KGE_TRANSH, vec, CALL); break;             \
+      case KGE_TRANSD: KGE_DISPATCH_VEC(KGE_TRANSD, vec, CALL); break;             \
+      case KGE_TRANSR: KGE_DISPATCH_VEC(KGE_TRANSR, vec, CALL); break;             \
+      case KGE_ROTATE: KGE_DISPATCH_VEC(KGE_ROTATE, vec, CALL); break;             \
+      case KGE_DISTMULT: KGE_DISPATCH_VEC(KGE_DISTMULT, vec, CALL); break;         \
+      case KGE_COMPLEX: KGE_DISPATCH_VEC(KGE_COMPLEX, vec, CALL); break;           \
+      case KGE_CP: KGE_DISPATCH_VEC(KGE_CP, vec, CALL); break;                     \
+      case KGE_TRANSM: KGE_DISPATCH_VEC(KGE_TRANSM, vec, CALL); break;             \
+      default: ::kge::set_error("model id %d not supported", (int)(model)); return KGE_ENOTSUP; \
+    }                                                                              \
+  } while (0)
+#define KGE_DISPATCH_VEC(M, vec, CALL)          \
+  do {                                          \
+    if ((vec) == 4) { CALL(M, 4); }             \
+    else if ((vec) == 2) { CALL(M, 2); }        \
+    else { CALL(M, 1); }                        \
+  } while (0)
+
+}  // namespace kge

@@ -1,0 +1,223 @@
+// kge_rank.cu — 1-vs-all link-prediction rank counts: replaces Evaluator.test
+// (pykg2vec/utils/evaluator.py:309-334) together with the Python rank walk of
+// MetricCalculator.get_tail_rank/get_head_rank (evaluator.py:70-123).
+//
+// Instead of materialising N scores, sorting them (topk k=N), copying the ids to
+// the host and walking the list, each query's rank is COUNTED on the device:
+//   raw      = #{e in [row_lo,row_hi) : score_e < score_target}
+//   filtered = raw - #{e in filter(q), e != target : score_e < score_target}
+// Scores use exactly the arithmetic of kge_score_fwd, so counts of
+// disjoint row shards add up to the global rank.
+//
+// Two sweep implementations:
+//   * gather sweep (all models): the fused gather+score group function evaluated
+//     over (query, candidate) pairs; one CTA = one query x 512 consecutive candidates.
+//   * tiled sweep (kge_rank_tiled.cu; TransE/TransM, DistMult/CP, ComplEx, RotatE):
+//     query vectors and candidate rows staged in shared memory by bulk-async copies,
+//     register-tiled pair evaluation, FMA-pipe bound.
+#include "kge_models.cuh"
+#include "kge_rank.cuh"
+
+namespace kge {
+
+constexpr int kThreads = 256;
+constexpr int kGroupsPerCta = kThreads / 8;
+constexpr int kSweepIters = 16;
+constexpr int kCandsPerCta = kGroupsPerCta * kSweepIters;
+
+template <int MODEL, int VEC, int GROUPING>
+__global__ void __launch_bounds__(kThreads)
+sweep_gather_kernel(ModelParams P, const int64_t* __restrict__ qh, const int64_t* __restrict__ qr,
+                    const int64_t* __restrict__ qt, const float* __restrict__ thr, int64_t nc,
+                    int32_t* __restrict__ counts, int col, int scratch_floats) {
+  extern __shared__ float4 smem_f4[];
+  __shared__ int block_cnt;
+  float* scratch = reinterpret_cast<float*>(smem_f4) + (size_t)(threadIdx.x >> 3) * scratch_floats;
+  const int lane = threadIdx.x & 7, grp = threadIdx.x >> 3;
+  const int64_t q = blockIdx.y;
+  const int64_t h = __ldg(qh + q), r = __ldg(qr + q), t = __ldg(qt + q);
+  const float th = __ldg(thr + q);
+  if (threadIdx.x == 0) block_cnt = 0;
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * kCandsPerCta;
+  int cnt = 0;
+  for (int it = 0; it < kSweepIters; ++it) {
+    const int64_t e = base + it * kGroupsPerCta + grp;
+    const bool valid = e < nc;
+    const int64_t ei = valid ? e : nc - 1;
+    TripleRows R;
+    if (GROUPING == KGE_GROUP_TAIL) resolve_rows<MODEL>(R, P, P.qtab, P.tab, P.qtab, h, r, ei);
+    else resolve_rows<MODEL>(R, P, P.tab, P.qtab, P.qtab, ei, r, t);
+    const float s = score_group<MODEL, VEC, GROUPING>(R, P, lane, scratch);
+    cnt += (valid && s < th) ? 1 : 0;
+  }
+  if (lane == 0 && cnt) atomicAdd(&block_cnt, cnt);
+  __syncthreads();
+  if (threadIdx.x == 0 && block_cnt) {
+    atomicAdd(counts + q * 4 + col, block_cnt);
+    atomicAdd(counts + q * 4 + col + 1, block_cnt);
+  }
+}
+
+// One group per filter entry (q, e): subtract it from the filtered count when it
+// outranks the target.  Entries equal to the target or outside the row shard are skipped.
+template <int MODEL, int VEC, int GROUPING>
+__global__ void __launch_bounds__(kThreads)
+filter_correct_kernel(ModelParams P, const int64_t* __restrict__ qh, const int64_t* __restrict__ qr,
+                      const int64_t* __restrict__ qt, const int64_t* __restrict__ tgt,
+                      const float* __restrict__ thr, const int64_t* __restrict__ ptr,
+                      const int64_t* __restrict__ idx, int64_t Q, int64_t nnz, int64_t row_lo,
+                      int64_t row_hi, int32_t* __restrict__ counts, int col, int scratch_floats) {
+  extern __shared__ float4 smem_f4[];
+  float* scratch = reinterpret_cast<float*>(smem_f4) + (size_t)(threadIdx.x >> 3) * scratch_floats;
+  const int lane = threadIdx.x & 7;
+  const int64_t k = (int64_t)blockIdx.x * kGroupsPerCta + (threadIdx.x >> 3);
+  const bool valid = k < nnz;
+  const int64_t kk = valid ? k : nnz - 1;
+  int64_t lo = 0, hi = Q;  // largest q with ptr[q] <= kk
+  while (hi - lo > 1) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (__ldg(ptr + mid) <= kk) lo = mid; else hi = mid;
+  }
+  const int64_t q = lo;
+  const int64_t e = __ldg(idx + kk);
+  const bool skip = (e == __ldg(tgt + q)) || e < row_lo || e >= row_hi;
+  const int64_t el = skip ? 0 : e - row_lo;
+  TripleRows R;
+  if (GROUPING == KGE_GROUP_TAIL)
+    resolve_rows<MODEL>(R, P, P.qtab, P.tab, P.qtab, __ldg(qh + q), __ldg(qr + q), el);
+  else
+    resolve_rows<MODEL>(R, P, P.tab, P.qtab, P.qtab, el, __ldg(qr + q), __ldg(qt + q));
+  const float s = score_group<MODEL, VEC, GROUPING>(R, P, lane, scratch);
+  if (valid && !skip && lane == 0 && s < __ldg(thr + q)) atomicSub(counts + q * 4 + col + 1, 1);
+}
+
+// thresholds: the target's own score, evaluated on the query-side tables
+template <int MODEL, int VEC, int GROUPING>
+__global__ void __launch_bounds__(kThreads)
+threshold_kernel(ModelParams P, const int64_t* __restrict__ qh, const int64_t* __restrict__ qr,
+                 const int64_t* __restrict__ qt, int64_t Q, float* __restrict__ thr, int scratch_floats) {
+  extern __shared__ float4 smem_f4[];
+  float* scratch = reinterpret_cast<float*>(smem_f4) + (size_t)(threadIdx.x >> 3) * scratch_floats;
+  const int lane = threadIdx.x & 7;
+  const int64_t g = (int64_t)blockIdx.x * kGroupsPerCta + (threadIdx.x >> 3);
+  const bool valid = g < Q;
+  const int64_t gi = valid ? g : Q - 1;
+  TripleRows R;
+  resolve_rows<MODEL>(R, P, P.qtab, P.qtab, P.qtab, __ldg(qh + gi), __ldg(qr + gi), __ldg(qt + gi));
+  const float s = score_group<MODEL, VEC, GROUPING>(R, P, lane, scratch);
+  if (valid && lane == 0) thr[g] = s;
+}
+
+int check_model(const kge_model_t* m);
+int model_vec(const kge_model_t* m);
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace kge
+
+using namespace kge;
+
+extern "C" int64_t kge_rank_workspace_bytes(const kge_model_t* m, int64_t Q) {
+  if (!m || Q < 0) return 0;
+  size_t bytes = align_up((size_t)2 * (size_t)Q * sizeof(float), 256);
+  bytes += tiled_workspace_bytes(m, Q);
+  return (int64_t)bytes;
+}
+
+extern "C" int kge_rank_1vsall(const kge_model_t* m, const kge_model_t* mq, int64_t row_lo,
+                               int64_t row_hi, const int64_t* qh, const int64_t* qr,
+                               const int64_t* qt, const int64_t* tgt_h, const int64_t* tgt_t,
+                               int64_t Q, const int64_t* filt_t_ptr, const int64_t* filt_t_idx,
+                               int64_t filt_t_nnz, const int64_t* filt_h_ptr,
+                               const int64_t* filt_h_idx, int64_t filt_h_nnz, int32_t* counts,
+                               void* workspace, int64_t workspace_bytes, int flags, void* stream) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  if (!mq) mq = m;
+  rc = check_model(mq);
+  if (rc) return rc;
+  if (mq->model != m->model || mq->dim != m->dim || mq->rel_dim != m->rel_dim) {
+    set_error("kge_rank_1vsall: m and mq describe different models"); return KGE_EINVAL;
+  }
+  if (Q == 0) return KGE_OK;
+  if (Q < 0 || !qh || !qr || !qt || !counts || !workspace || row_lo < 0 || row_hi <= row_lo ||
+      row_hi - row_lo > m->num_ent) {
+    set_error("kge_rank_1vsall: bad arguments"); return KGE_EINVAL;
+  }
+  if (Q > 65535) { set_error("kge_rank_1vsall: Q=%lld > 65535, batch the queries", (long long)Q); return KGE_EINVAL; }
+  if (workspace_bytes < kge_rank_workspace_bytes(m, Q)) { set_error("workspace too small"); return KGE_EWORKSPACE; }
+  if (!tgt_h) tgt_h = qh;
+  if (!tgt_t) tgt_t = qt;
+  const int64_t nc = row_hi - row_lo;
+  cudaStream_t st = (cudaStream_t)stream;
+  const ModelParams P = make_params(m, mq);
+  int vec = model_vec(m);
+  const int vq = model_vec(mq);
+  if (vq < vec) vec = vq;
+  const int sf = (int)group_scratch_floats(m);
+  const size_t smem = (size_t)sf * kGroupsPerCta * sizeof(float);
+  float* thr_t = reinterpret_cast<float*>(workspace);
+  float* thr_h = thr_t + Q;
+  void* tiled_ws = reinterpret_cast<char*>(workspace) + align_up((size_t)2 * (size_t)Q * sizeof(float), 256);
+  const unsigned qgrid = (unsigned)((Q + kGroupsPerCta - 1) / kGroupsPerCta);
+  const dim3 sgrid((unsigned)((nc + kCandsPerCta - 1) / kCandsPerCta), (unsigned)Q);
+  const bool use_tiled = !(flags & KGE_RANK_FORCE_GATHER) && tiled_supported(m);
+
+  for (int dir = 0; dir < 2; ++dir) {
+    if (dir == 0 && (flags & KGE_RANK_HEAD_ONLY)) continue;
+    if (dir == 1 && (flags & KGE_RANK_TAIL_ONLY)) continue;
+    float* thr = dir == 0 ? thr_t : thr_h;
+    const int col = dir == 0 ? 0 : 2;
+    const int64_t* fptr = dir == 0 ? filt_t_ptr : filt_h_ptr;
+    const int64_t* fidx = dir == 0 ? filt_t_idx : filt_h_idx;
+    const int64_t nnz = dir == 0 ? filt_t_nnz : filt_h_nnz;
+    const int64_t* tgt = dir == 0 ? tgt_t : tgt_h;
+#define SET_SMEM(K)                                                                          \
+  if (smem > 48 * 1024)                                                                      \
+    KGE_CUDA_OK(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#define CALL_THR(M, V)                                                                         \
+  do {                                                                                         \
+    if (dir == 0) { SET_SMEM((threshold_kernel<M, V, KGE_GROUP_TAIL>));                        \
+      threshold_kernel<M, V, KGE_GROUP_TAIL><<<qgrid, kThreads, smem, st>>>(P, qh, qr, qt, Q, thr, sf); } \
+    else { SET_SMEM((threshold_kernel<M, V, KGE_GROUP_HEAD>));                                 \
+      threshold_kernel<M, V, KGE_GROUP_HEAD><<<qgrid, kThreads, smem, st>>>(P, qh, qr, qt, Q, thr, sf); } \
+  } while (0)
+    KGE_DISPATCH_MODEL_VEC(m->model, vec, CALL_THR);
+#undef CALL_THR
+    KGE_CHECK_LAUNCH("threshold_kernel");
+
+    if (use_tiled) {
+      rc = tiled_sweep(m, mq, dir, qh, qr, qt, thr, Q, nc, counts, col, tiled_ws, st);
+      if (rc) return rc;
+    } else {
+#define CALL_SWEEP(M, V)                                                                       \
+  do {                                                                                         \
+    if (dir == 0) { SET_SMEM((sweep_gather_kernel<M, V, KGE_GROUP_TAIL>));                     \
+      sweep_gather_kernel<M, V, KGE_GROUP_TAIL><<<sgrid, kThreads, smem, st>>>(P, qh, qr, qt, thr, nc, counts, col, sf); } \
+    else { SET_SMEM((sweep_gather_kernel<M, V, KGE_GROUP_HEAD>));                              \
+      sweep_gather_kernel<M, V, KGE_GROUP_HEAD><<<sgrid, kThreads, smem, st>>>(P, qh, qr, qt, thr, nc, counts, col, sf); } \
+  } while (0)
+      KGE_DISPATCH_MODEL_VEC(m->model, vec, CALL_SWEEP);
+#undef CALL_SWEEP
+      KGE_CHECK_LAUNCH("sweep_gather_kernel");
+    }
+
+    if (fptr && fidx && nnz > 0) {
+      const unsigned fgrid = (unsigned)((nnz + kGroupsPerCta - 1) / kGroupsPerCta);
+#define CALL_FILT(M, V)                                                                        \
+  do {                                                                                         \
+    if (dir == 0) { SET_SMEM((filter_correct_kernel<M, V, KGE_GROUP_TAIL>));                   \
+      filter_correct_kernel<M, V, KGE_GROUP_TAIL><<<fgrid, kThreads, smem, st>>>(              \
+          P, qh, qr, qt, tgt, thr, fptr, fidx, Q, nnz, row_lo, row_hi, counts, col, sf); }     \
+    else { SET_SMEM((filter_correct_kernel<M, V, KGE_GROUP_HEAD>));                            \
+      filter_correct_kernel<M, V, KGE_GROUP_HEAD><<<fgrid, kThreads, smem, st>>>(              \
+          P, qh, qr, qt, tgt, thr, fptr, fidx, Q, nnz, row_lo, row_hi, counts, col, sf); }     \
+  } while (0)
+      KGE_DISPATCH_MODEL_VEC(m->model, vec, CALL_FILT);
+#undef CALL_FILT
+      KGE_CHECK_LAUNCH("filter_correct_kernel");
+    }
+  }
+  return KGE_OK;
+}

@@ -1,0 +1,88 @@
+// kge_score.cu — fused gather + score forward:  replaces model.forward(h, r, t)
+// (pykg2vec/models/pairwise.py, pointwise.py; callers pykg2vec/utils/trainer.py:147-180).
+//
+// Mapping: one 8-lane group per triple (4 triples per warp, 32 per 256-thread CTA).
+// Lane l reads the 16-byte chunks l, l+8, ... of every gathered row, so the 8 lanes
+// of a group cover 128 contiguous bytes of a row per load instruction (one full
+// cache line when the row is line-aligned), and a warp has 4 x (rows per triple)
+// independent row streams in flight.  HBM-bound: rows*d*4 + 28 bytes per triple.
+#include "kge_models.cuh"
+
+namespace kge {
+
+constexpr int kThreads = 256;
+constexpr int kGroupsPerCta = kThreads / 8;
+
+template <int MODEL, int VEC>
+__global__ void __launch_bounds__(kThreads)
+score_fwd_kernel(ModelParams P, int grouping, const int64_t* __restrict__ h,
+                 const int64_t* __restrict__ r, const int64_t* __restrict__ t, int64_t n,
+                 float* __restrict__ out, int scratch_floats) {
+  extern __shared__ float4 smem_f4[];
+  float* scratch = reinterpret_cast<float*>(smem_f4) + (size_t)(threadIdx.x >> 3) * scratch_floats;
+  const int lane = threadIdx.x & 7;
+  const int64_t g = (int64_t)blockIdx.x * kGroupsPerCta + (threadIdx.x >> 3);
+  const bool valid = g < n;
+  const int64_t gi = valid ? g : n - 1;  // idle groups shadow the last triple (shuffles stay full-warp)
+  TripleRows R;
+  resolve_rows<MODEL>(R, P, P.tab, P.tab, P.tab, __ldg(h + gi), __ldg(r + gi), __ldg(t + gi));
+  float s;
+  if (grouping == KGE_GROUP_TAIL) s = score_group<MODEL, VEC, KGE_GROUP_TAIL>(R, P, lane, scratch);
+  else s = score_group<MODEL, VEC, KGE_GROUP_HEAD>(R, P, lane, scratch);
+  if (valid && lane == 0) out[g] = s;
+}
+
+int check_model(const kge_model_t* m) {
+  if (!m) { set_error("model is NULL"); return KGE_EINVAL; }
+  const int nt = num_tables(m->model);
+  if (nt == 0) { set_error("unknown model id %d", m->model); return KGE_ENOTSUP; }
+  if (m->dim <= 0 || m->rel_dim <= 0 || m->num_ent <= 0 || m->num_rel <= 0) {
+    set_error("bad model geometry dim=%d rel_dim=%d num_ent=%lld num_rel=%lld", m->dim, m->rel_dim,
+              (long long)m->num_ent, (long long)m->num_rel);
+    return KGE_EINVAL;
+  }
+  for (int k = 0; k < nt; ++k)
+    if (!m->tables[k]) { set_error("tables[%d] is NULL", k); return KGE_EINVAL; }
+  if (m->model != KGE_TRANSR && m->rel_dim != m->dim) {
+    // TransD as written only broadcasts when ent_hidden_size == rel_hidden_size (pairwise.py:275-278)
+    set_error("rel_dim (%d) must equal dim (%d) for this model", m->rel_dim, m->dim);
+    return KGE_EINVAL;
+  }
+  return KGE_OK;
+}
+
+int model_vec(const kge_model_t* m) {
+  const int nt = num_tables(m->model);
+  if (m->model == KGE_TRANSM) return pick_vec(m, 2, m->dim);  // theta is a [R] vector, read as scalars
+  return pick_vec(m, nt, m->dim, m->model == KGE_TRANSR ? m->rel_dim : 0);
+}
+
+}  // namespace kge
+
+using namespace kge;
+
+extern "C" int kge_score_fwd(const kge_model_t* m, int grouping, const int64_t* h, const int64_t* r,
+                             const int64_t* t, int64_t n, float* scores, void* stream) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  if (n == 0) return KGE_OK;
+  if (n < 0 || !h || !r || !t || !scores) { set_error("kge_score_fwd: bad arguments"); return KGE_EINVAL; }
+  if (grouping != KGE_GROUP_TAIL && grouping != KGE_GROUP_HEAD) { set_error("bad grouping"); return KGE_EINVAL; }
+  const ModelParams P = make_params(m, nullptr);
+  const int vec = model_vec(m);
+  const int sf = (int)group_scratch_floats(m);
+  const size_t smem = (size_t)sf * kGroupsPerCta * sizeof(float);
+  const unsigned grid = (unsigned)((n + kGroupsPerCta - 1) / kGroupsPerCta);
+  cudaStream_t st = (cudaStream_t)stream;
+#define CALL(M, V)                                                                              \
+  do {                                                                                          \
+    if (smem > 48 * 1024)                                                                       \
+      KGE_CUDA_OK(cudaFuncSetAttribute(score_fwd_kernel<M, V>,                                  \
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    score_fwd_kernel<M, V><<<grid, kThreads, smem, st>>>(P, grouping, h, r, t, n, scores, sf);  \
+  } while (0)
+  KGE_DISPATCH_MODEL_VEC(m->model, vec, CALL);
+#undef CALL
+  KGE_CHECK_LAUNCH("score_fwd_kernel");
+  return KGE_OK;
+}

@@ -1,0 +1,135 @@
+"""-m gpu parity tests: CUDA path (through the C-ABI) vs the CPU oracle, bit-exact on
+scores and exact on rank counts; and vs the golden outputs of the reference itself
+(scores within 1e-4 relative, ranks exact)."""
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+import gpu_util as gpu
+
+pytestmark = pytest.mark.gpu
+CASES = gu.case_names()
+
+
+def _lib():
+    from pykg2vec_b200 import _lib
+    return _lib
+
+
+def _cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_score_fwd_golden(name):
+    import oracle
+    L = _lib()
+    g = gu.load(name)
+    desc = gpu.desc_from_golden(g)
+    om = gu.oracle_model(g)
+    h, r, t = _cuda(g["h"]), _cuda(g["r"]), _cuda(g["t"])
+    for grouping in (L.GROUP_TAIL, L.GROUP_HEAD):
+        s = L.score_fwd(desc, h, r, t, grouping).cpu().numpy()
+        so = oracle.score_fwd(om, g["h"], g["r"], g["t"], grouping)
+        np.testing.assert_array_equal(gpu.bits(s), gpu.bits(so), err_msg="%s grouping %d: kernel != oracle bitwise" % (name, grouping))
+        ref = g["scores"]
+        floor = 1e-3 * np.abs(ref).max()
+        err = np.abs(s.astype(np.float64) - ref) / np.maximum(np.abs(ref), floor)
+        assert err.max() < 1e-4, (name, err.max())
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("flags", [0, 1])
+def test_rank_golden(name, flags):
+    L = _lib()
+    g = gu.load(name)
+    desc = gpu.desc_from_golden(g)
+    Q = g["ranks"].shape[0]
+    counts = L.rank_1vsall(desc, _cuda(g["h"][:Q]), _cuda(g["r"][:Q]), _cuda(g["t"][:Q]),
+                           (_cuda(g["filt_t_ptr"]), _cuda(g["filt_t_idx"])),
+                           (_cuda(g["filt_h_ptr"]), _cuda(g["filt_h_idx"])), flags=flags)
+    np.testing.assert_array_equal(counts.cpu().numpy(), g["ranks"])
+
+
+SYN = [
+    # name, N, R, d, dr, l1, margin
+    ("transe", 1500, 13, 200, None, False, 0.0),
+    ("transe", 1500, 13, 50, None, True, 0.0),
+    ("transe", 700, 5, 37, None, True, 0.0),
+    ("transm", 900, 7, 64, None, False, 0.0),
+    ("transh", 900, 7, 100, None, False, 0.0),
+    ("transd", 900, 7, 50, None, True, 0.0),
+    ("transr", 400, 5, 40, 24, False, 0.0),
+    ("rotate", 800, 9, 1000, None, False, 24.0),
+    ("rotate", 800, 9, 50, None, False, 6.0),
+    ("distmult", 1500, 11, 200, None, False, 0.0),
+    ("cp", 900, 11, 30, None, False, 0.0),
+    ("complex", 1500, 11, 200, None, False, 0.0),
+    ("complex", 1200, 11, 500, None, False, 0.0),
+]
+
+
+@pytest.mark.parametrize("spec", SYN, ids=lambda s: "%s-N%d-d%d" % (s[0], s[1], s[3]))
+def test_score_and_rank_synthetic_bitexact(spec):
+    import oracle
+    L = _lib()
+    name, N, R, d, dr, l1, margin = spec
+    om, _ = gpu.synthetic_case(name, N, R, d, seed=hash(spec) % 10007, dr=dr, l1=l1, margin=margin)
+    desc = gpu.desc_from_oracle_model(om)
+    rng = np.random.RandomState(5)
+    for n in (1, 31, 257, 1000):
+        h, r, t = rng.randint(N, size=n), rng.randint(R, size=n), rng.randint(N, size=n)
+        for grouping in (0, 1):
+            s = L.score_fwd(desc, _cuda(h), _cuda(r), _cuda(t), grouping).cpu().numpy()
+            so = oracle.score_fwd(om, h, r, t, grouping)
+            np.testing.assert_array_equal(gpu.bits(s), gpu.bits(so))
+    Q = 5
+    qh, qr, qt = rng.randint(N, size=Q), rng.randint(R, size=Q), rng.randint(N, size=Q)
+    ft, fh = gpu.random_filters_csr(rng, N, qh, qr, qt)
+    want = oracle.rank_1vsall(om, qh, qr, qt, ft, fh)
+    for flags in (0, 1):
+        got = L.rank_1vsall(desc, _cuda(qh), _cuda(qr), _cuda(qt), (_cuda(ft[0]), _cuda(ft[1])),
+                            (_cuda(fh[0]), _cuda(fh[1])), flags=flags).cpu().numpy()
+        np.testing.assert_array_equal(got, want)
+
+
+def test_empty_and_argument_errors():
+    L = _lib()
+    g = gu.load("transe_l1_d50")
+    desc = gpu.desc_from_golden(g)
+    e = torch.empty(0, dtype=torch.int64, device="cuda")
+    assert L.score_fwd(desc, e, e, e).numel() == 0
+    with pytest.raises(L.KgeError):
+        L.score_fwd(desc, _cuda(g["h"]), _cuda(g["r"][:5]), _cuda(g["t"]))
+    with pytest.raises(L.KgeError):
+        L.score_fwd(desc, _cuda(g["h"]).int(), _cuda(g["r"]), _cuda(g["t"]))
+
+
+def test_rank_row_shards_add_up():
+    """partial counts over disjoint row shards (separate shard tables + compact query table)
+    add up to the replicated result — the row-sharded multi-GPU formulation on one GPU."""
+    L = _lib()
+    import oracle
+    om, tabs = gpu.synthetic_case("complex", 1000, 7, 100, seed=3)
+    rng = np.random.RandomState(9)
+    Q = 7
+    qh, qr, qt = rng.randint(1000, size=Q), rng.randint(7, size=Q), rng.randint(1000, size=Q)
+    ft, fh = gpu.random_filters_csr(rng, 1000, qh, qr, qt)
+    want = oracle.rank_1vsall(om, qh, qr, qt, ft, fh)
+    # compact query table: rows of all query heads and tails, queries re-indexed into it
+    uniq = np.unique(np.concatenate([qh, qt]))
+    remap = {int(e): i for i, e in enumerate(uniq)}
+    qtabs = [torch.from_numpy(tabs[0][uniq]).cuda(), torch.from_numpy(tabs[1][uniq]).cuda(),
+             torch.from_numpy(tabs[2]).cuda(), torch.from_numpy(tabs[3]).cuda()]
+    qdesc = L.ModelDesc("complex", qtabs, 100)
+    qh2 = np.asarray([remap[int(e)] for e in qh]); qt2 = np.asarray([remap[int(e)] for e in qt])
+    counts = torch.zeros((Q, 4), dtype=torch.int32, device="cuda")
+    for lo, hi in ((0, 300), (300, 301), (301, 1000)):
+        stabs = [torch.from_numpy(np.ascontiguousarray(tabs[0][lo:hi])).cuda(),
+                 torch.from_numpy(np.ascontiguousarray(tabs[1][lo:hi])).cuda(), qtabs[2], qtabs[3]]
+        sdesc = L.ModelDesc("complex", stabs, 100)
+        L.rank_1vsall(sdesc, _cuda(qh2), _cuda(qr), _cuda(qt2), (_cuda(ft[0]), _cuda(ft[1])),
+                      (_cuda(fh[0]), _cuda(fh[1])), counts=counts, row_lo=lo, row_hi=hi, query_desc=qdesc,
+                      tgt_h=_cuda(qh), tgt_t=_cuda(qt))
+    np.testing.assert_array_equal(counts.cpu().numpy(), want)

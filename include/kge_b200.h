@@ -122,16 +122,31 @@ int kge_reg_fwd_bwd(const kge_model_t* m, int reg_type, float lmbda, const int64
                     const int64_t* r, const int64_t* t, int64_t n, float* reg_out,
                     float grad_scale, float* const* grad_tables, void* stream);
 
-/* ---- fused training steps (trainer.py:147-157 + :298-299 in one pass) ----
- * pos/neg forward + hinge + backward + SGD update of the touched rows.
- * Equivalent to optim.SGD on dense nn.Embedding gradients (rows with zero
- * gradient do not move).  loss_out[0] receives the batch loss.  neg ids are
- * [n * neg_rate]; hinge requires neg_rate == 1 as in the reference (the
- * shapes only broadcast then, criterion.py:26-29). */
+/* ---- fused training step + sparse optimizer (trainer.py:147-157 + :298-299) ----
+ * kge_train_pairwise_hinge_sgd: pos/neg forward + Criterion.pairwise_hinge + backward
+ * + optim.SGD in two kernels.  tables_rw must alias m->tables (they are updated in
+ * place); grad_scratch[k] is a ZERO-FILLED dense buffer shaped like tables[k] and is
+ * zero-filled again on return.  Equivalent to optim.SGD on dense nn.Embedding
+ * gradients: rows with zero gradient do not move.  loss_out[0] receives the batch
+ * loss (sum over pairs).  n pairs, one negative per positive as in the reference
+ * (the hinge shapes only broadcast for neg_rate == 1, criterion.py:26-29). */
 int kge_train_pairwise_hinge_sgd(const kge_model_t* m, float* const* tables_rw,
+                                 float* const* grad_scratch,
                                  const int64_t* pos_h, const int64_t* pos_r, const int64_t* pos_t,
                                  const int64_t* neg_h, const int64_t* neg_r, const int64_t* neg_t,
                                  int64_t n, float margin, float lr, float* loss_out, void* stream);
+
+/* Sparse optimizer.step() for the rows touched by the triples (h[i], r[i], t[i]):
+ * takes the accumulated row gradients out of grad_scratch (as filled by
+ * kge_score_bwd / kge_reg_fwd_bwd; left zero-filled) and applies
+ *   optimizer 0: torch.optim.SGD      w -= lr * g                     (trainer.py:117-121)
+ *   optimizer 1: torch.optim.Adagrad  s += g*g; w -= lr*g/(sqrt(s)+eps) (trainer.py:122-126)
+ * state[k] (Adagrad) is shaped like tables[k].  For both optimizers rows with zero
+ * gradient are left untouched by the dense reference optimizers too, so the result
+ * equals the dense step. */
+int kge_optim_apply_rows(const kge_model_t* m, float* const* tables_rw, float* const* grad_scratch,
+                         float* const* state, int optimizer, const int64_t* h, const int64_t* r,
+                         const int64_t* t, int64_t n, float lr, float eps, void* stream);
 
 /* ---- 1-vs-all link-prediction ranks: replaces Evaluator.test ------------
  * (pykg2vec/utils/evaluator.py:309-334 + MetricCalculator.get_*_rank :70-123)

@@ -25,7 +25,7 @@ EXPORTS = [
     "kge_abi_version", "kge_version", "kge_last_error", "kge_launch_count",
     "kge_score_fwd", "kge_score_bwd",
     "kge_loss_pairwise_hinge", "kge_loss_pointwise_logistic", "kge_loss_selfadv", "kge_reg_fwd_bwd",
-    "kge_train_pairwise_hinge_sgd",
+    "kge_train_pairwise_hinge_sgd", "kge_optim_apply_rows",
     "kge_rank_workspace_bytes", "kge_rank_1vsall",
 ]
 
@@ -205,6 +205,17 @@ def train_pairwise_hinge_sgd(desc, grad_scratch, ph, pr, pt, nh, nr, nt, margin,
                                              ctypes.c_float(margin), ctypes.c_float(lr), _ptr(loss_out),
                                              _stream()), "kge_train_pairwise_hinge_sgd")
     return loss_out
+
+
+def optim_apply_rows(desc, grad_scratch, state, optimizer, h, r, t, lr, eps=1e-10):
+    """optimizer: 0 SGD, 1 Adagrad.  Consumes (and re-zeroes) grad_scratch for the touched rows."""
+    m = desc.c_struct()
+    rw = _table_ptr_array(desc.tables)
+    gs = _table_ptr_array(grad_scratch)
+    stt = _table_ptr_array(state) if state is not None else None
+    check(lib().kge_optim_apply_rows(ctypes.byref(m), rw, gs, stt, ctypes.c_int(optimizer), _ptr(h), _ptr(r),
+                                     _ptr(t), ctypes.c_int64(h.numel()), ctypes.c_float(lr),
+                                     ctypes.c_float(eps), _stream()), "kge_optim_apply_rows")
 
 
 def rank_workspace_bytes(desc, Q):

@@ -54,11 +54,14 @@ KGE_DEV float fadd(float a, float b) { return __fadd_rn(a, b); }
 KGE_DEV float fsub(float a, float b) { return __fsub_rn(a, b); }
 KGE_DEV float ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 
-// RSUM butterfly across the 8 lanes of a group (all 32 lanes of the warp must call).
+// RSUM butterfly across the 8 lanes of a group.  The shuffle mask names only the
+// group's own lanes, so different groups of a warp may diverge freely.
+KGE_DEV unsigned group_mask() { return 0xFFu << (threadIdx.x & 24); }
 KGE_DEV float group_sum(float v) {
-  v = fadd(v, __shfl_xor_sync(0xffffffffu, v, 4));
-  v = fadd(v, __shfl_xor_sync(0xffffffffu, v, 2));
-  v = fadd(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  const unsigned m = group_mask();
+  v = fadd(v, __shfl_xor_sync(m, v, 4));
+  v = fadd(v, __shfl_xor_sync(m, v, 2));
+  v = fadd(v, __shfl_xor_sync(m, v, 1));
   return v;
 }
 

@@ -1,0 +1,455 @@
+// kge_grads.cuh — per-model backward of the score functions, evaluated by an 8-lane
+// group; replaces autograd through the reference's ATen chains (loss.backward(),
+// pykg2vec/utils/trainer.py:298).  Intermediates are recomputed (nothing is saved
+// by the forward), row gradients are accumulated with red.global.add (v4 when the
+// row is 16-byte aligned) into dense gradient tables (nn.Embedding dense-grad
+// semantics, pykg2vec/models/Domain.py:8-17).
+//
+// The backward differentiates forward() (TAIL grouping).  It is a floating-point
+// path checked against the fp64 autograd oracle with a tolerance; it does not
+// use the canonical-order intrinsics except where it recomputes forward values.
+#pragma once
+#include "kge_models.cuh"
+
+namespace kge {
+
+struct GradRows {
+  float* h[2];
+  float* t[2];
+  float* r[3];
+};
+
+template <int MODEL>
+KGE_DEV void resolve_grad_rows(GradRows& G, const ModelParams& P, float* const* gt, int64_t h,
+                               int64_t r, int64_t t) {
+  const size_t d = (size_t)P.d, dr = (size_t)P.dr;
+  G.h[0] = G.h[1] = G.t[0] = G.t[1] = G.r[0] = G.r[1] = G.r[2] = nullptr;
+  auto at = [&](int k, size_t off) -> float* { return gt[k] ? gt[k] + off : nullptr; };
+  if (MODEL == KGE_TRANSE || MODEL == KGE_DISTMULT || MODEL == KGE_TRANSM) {
+    G.h[0] = at(0, h * d); G.t[0] = at(0, t * d); G.r[0] = at(1, r * d);
+  } else if (MODEL == KGE_CP) {
+    G.h[0] = at(0, h * d); G.t[0] = at(2, t * d); G.r[0] = at(1, r * d);
+  } else if (MODEL == KGE_TRANSH) {
+    G.h[0] = at(0, h * d); G.t[0] = at(0, t * d); G.r[0] = at(1, r * d); G.r[1] = at(2, r * d);
+  } else if (MODEL == KGE_TRANSD) {
+    G.h[0] = at(0, h * d); G.t[0] = at(0, t * d); G.r[0] = at(1, r * d);
+    G.h[1] = at(2, h * d); G.t[1] = at(2, t * d); G.r[1] = at(3, r * d);
+  } else if (MODEL == KGE_TRANSR) {
+    G.h[0] = at(0, h * d); G.t[0] = at(0, t * d); G.r[0] = at(1, r * dr); G.r[1] = at(2, r * d * dr);
+  } else if (MODEL == KGE_ROTATE) {
+    G.h[0] = at(0, h * d); G.h[1] = at(1, h * d); G.t[0] = at(0, t * d); G.t[1] = at(1, t * d);
+    G.r[0] = at(2, r * d);
+  } else if (MODEL == KGE_COMPLEX) {
+    G.h[0] = at(0, h * d); G.h[1] = at(1, h * d); G.t[0] = at(0, t * d); G.t[1] = at(1, t * d);
+    G.r[0] = at(2, r * d); G.r[1] = at(3, r * d);
+  }
+}
+
+template <int VEC>
+KGE_DEV void red_row_chunk(float* row, int c, int d, float4 g) {
+  if (row) red_chunk<VEC>(row, c, d, g);
+}
+
+KGE_DEV float sgnf(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
+
+// Backward through  s = || h^ + r^ - t^ ||_p  with  v^ = v * inv_norm(v)   (F.normalize).
+// fh/fr/ft(c): chunk c of the (already projected) operands.  gs = dL/ds.
+struct DistCtx {
+  float ih, ir, it;     // inverse norms
+  float ch, cr, ct;     // coef * <v^, u>  per operand (projection term of normalize backward)
+  float coef;           // gs (L1) or gs / s (L2)
+  int l1;
+};
+
+template <class FH, class FR, class FT>
+KGE_DEV DistCtx dist_prepare(FH fh, FR fr, FT ft, int nch, int lane, int l1, float gs) {
+  DistCtx X;
+  float sh = 0.f, sr = 0.f, st = 0.f;
+  for (int c = lane; c < nch; c += 8) {
+    const float4 a = fh(c), b = fr(c), cc = ft(c);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      sh = ffma(f4_get(a, e), f4_get(a, e), sh);
+      sr = ffma(f4_get(b, e), f4_get(b, e), sr);
+      st = ffma(f4_get(cc, e), f4_get(cc, e), st);
+    }
+  }
+  sh = group_sum(sh); sr = group_sum(sr); st = group_sum(st);
+  X.ih = inv_norm_from_sumsq(sh); X.ir = inv_norm_from_sumsq(sr); X.it = inv_norm_from_sumsq(st);
+  // norm below eps: F.normalize divides by the constant eps (clamp_min has zero gradient there)
+  const bool clamp_h = __fsqrt_rn(sh) < 1e-12f, clamp_r = __fsqrt_rn(sr) < 1e-12f,
+             clamp_t = __fsqrt_rn(st) < 1e-12f;
+  X.l1 = l1;
+  float S = 0.f, ah = 0.f, ar = 0.f, at = 0.f;
+  for (int c = lane; c < nch; c += 8) {
+    const float4 a = fh(c), b = fr(c), cc = ft(c);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float hn = f4_get(a, e) * X.ih, rn = f4_get(b, e) * X.ir, tn = f4_get(cc, e) * X.it;
+      const float x = (hn + rn) - tn;
+      const float u = l1 ? sgnf(x) : x;
+      S += x * x; ah += hn * u; ar += rn * u; at += tn * u;
+    }
+  }
+  S = group_sum(S); ah = group_sum(ah); ar = group_sum(ar); at = group_sum(at);
+  const float s = sqrtf(S);
+  X.coef = l1 ? gs : ((s > 0.f) ? gs / s : 0.f);
+  X.ch = clamp_h ? 0.f : X.coef * ah;
+  X.cr = clamp_r ? 0.f : X.coef * ar;
+  X.ct = clamp_t ? 0.f : X.coef * at;
+  return X;
+}
+
+// gradient w.r.t. one element of each operand given its raw values
+KGE_DEV void dist_elem(const DistCtx& X, float hv, float rv, float tv, float& dh, float& dr, float& dt) {
+  const float hn = hv * X.ih, rn = rv * X.ir, tn = tv * X.it;
+  const float x = (hn + rn) - tn;
+  const float dx = X.coef * (X.l1 ? sgnf(x) : x);
+  dh = (dx - hn * X.ch) * X.ih;
+  dr = (dx - rn * X.cr) * X.ir;
+  dt = -(dx - tn * X.ct) * X.it;
+}
+
+// Accumulate gs * d score / d rows into G.  All 8 lanes call; `scratch` per group
+// (group_scratch_floats_bwd floats, TransR only).
+template <int MODEL, int VEC>
+KGE_DEV void grad_group(const TripleRows& R, const GradRows& G, const ModelParams& P, int lane,
+                        float gs, float* scratch) {
+  const int d = P.d;
+  const int nch = (d + 3) >> 2;
+  if (MODEL == KGE_TRANSE || MODEL == KGE_TRANSM) {
+    if (MODEL == KGE_TRANSM) gs *= __ldg(R.r[1]);
+    auto fh = [&](int c) { return ld_chunk<VEC>(R.h[0], c, d); };
+    auto fr = [&](int c) { return ld_chunk<VEC>(R.r[0], c, d); };
+    auto ft = [&](int c) { return ld_chunk<VEC>(R.t[0], c, d); };
+    const DistCtx X = dist_prepare(fh, fr, ft, nch, lane, P.l1, gs);
+    for (int c = lane; c < nch; c += 8) {
+      const float4 a = fh(c), b = fr(c), cc = ft(c);
+      float4 dh, dr, dt;
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        dist_elem(X, f4_get(a, e), f4_get(b, e), f4_get(cc, e), f4_at(dh, e), f4_at(dr, e), f4_at(dt, e));
+      red_row_chunk<VEC>(G.h[0], c, d, dh);
+      red_row_chunk<VEC>(G.r[0], c, d, dr);
+      red_row_chunk<VEC>(G.t[0], c, d, dt);
+    }
+  } else if (MODEL == KGE_TRANSH) {
+    float sw = 0.f;
+    for (int c = lane; c < nch; c += 8) {
+      const float4 w = ld_chunk<VEC>(R.r[1], c, d);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sw = ffma(f4_get(w, e), f4_get(w, e), sw);
+    }
+    sw = group_sum(sw);
+    const float iw = inv_norm_from_sumsq(sw);
+    const bool clamp_w = __fsqrt_rn(sw) < 1e-12f;
+    float ah = 0.f, at = 0.f;
+    for (int c = lane; c < nch; c += 8) {
+      const float4 w = ld_chunk<VEC>(R.r[1], c, d), a = ld_chunk<VEC>(R.h[0], c, d), b = ld_chunk<VEC>(R.t[0], c, d);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float wn = fmul(f4_get(w, e), iw);
+        ah = ffma(f4_get(a, e), wn, ah);
+        at = ffma(f4_get(b, e), wn, at);
+      }
+    }
+    ah = group_sum(ah); at = group_sum(at);
+    auto wn4 = [&](int c) {
+      const float4 w = ld_chunk<VEC>(R.r[1], c, d);
+      return make_float4(fmul(w.x, iw), fmul(w.y, iw), fmul(w.z, iw), fmul(w.w, iw));
+    };
+    auto proj = [&](const float* row, float a, int c) {
+      const float4 w = wn4(c), x = ld_chunk<VEC>(row, c, d);
+      float4 o;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) f4_at(o, e) = ffma(-a, f4_get(w, e), f4_get(x, e));
+      return o;
+    };
+    auto fh = [&](int c) { return proj(R.h[0], ah, c); };
+    auto fr = [&](int c) { return ld_chunk<VEC>(R.r[0], c, d); };
+    auto ft = [&](int c) { return proj(R.t[0], at, c); };
+    const DistCtx X = dist_prepare(fh, fr, ft, nch, lane, P.l1, gs);
+    // bh = <w~, dh_perp>, bt = <w~, dt_perp>
+    float bh = 0.f, bt = 0.f;
+    for (int c = lane; c < nch; c += 8) {
+      const float4 a = fh(c), b = fr(c), cc = ft(c), w = wn4(c);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float dh, dr, dt;
+        dist_elem(X, f4_get(a, e), f4_get(b, e), f4_get(cc, e), dh, dr, dt);
+        bh += f4_get(w, e) * dh; bt += f4_get(w, e) * dt;
+      }
+    }
+    bh = group_sum(bh); bt = group_sum(bt);
+    // cw = <w~, dw~>,  dw~_k = -h_k bh - ah dh_perp_k - t_k bt - at dt_perp_k
+    float cw = 0.f;
+    for (int c = lane; c < nch; c += 8) {
+      const float4 a = fh(c), b = fr(c), cc = ft(c), w = wn4(c);
+      const float4 hv = ld_chunk<VEC>(R.h[0], c, d), tv = ld_chunk<VEC>(R.t[0], c, d);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float dh, dr, dt;
+        dist_elem(X, f4_get(a, e), f4_get(b, e), f4_get(cc, e), dh, dr, dt);
+        const float dwn = -f4_get(hv, e) * bh - ah * dh - f4_get(tv, e) * bt - at * dt;
+        cw += f4_get(w, e) * dwn;
+      }
+    }
+    cw = group_sum(cw);
+    if (clamp_w) cw = 0.f;
+    for (int c = lane; c < nch; c += 8) {
+      const float4 a = fh(c), b = fr(c), cc = ft(c), w = wn4(c);
+      const float4 hv = ld_chunk<VEC>(R.h[0], c, d), tv = ld_chunk<VEC>(R.t[0], c, d);
+      float4 gh, gr, gtt, gw;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float dh, dr, dt;
+        dist_elem(X, f4_get(a, e), f4_get(b, e), f4_get(cc, e), dh, dr, dt);
+        const float dwn = -f4_get(hv, e) * bh - ah * dh - f4_get(tv, e) * bt - at * dt;
+        f4_at(gh, e) = dh - f4_get(w, e) * bh;
+        f4_at(gtt, e) = dt - f4_get(w, e) * bt;
+        f4_at(gr, e) = dr;
+        f4_at(gw, e) = (dwn - f4_get(w, e) * cw) * iw;
+      }
+      red_row_chunk<VEC>(G.h[0], c, d, gh);
+      red_row_chunk<VEC>(G.t[0], c, d, gtt);
+      red_row_chunk<VEC>(G.r[0], c, d, gr);
+      red_row_chunk<VEC>(G.r[1], c, d, gw);
+    }
+  } else if (MODEL == KGE_TRANSD) {
+    const float ah = group_dot<VEC>(R.h[0], R.h[1], d, nch, lane);
+    const float at = group_dot<VEC>(R.t[0], R.t[1], d, nch, lane);
+    auto proj = [&](const float* row, float a, int c) {
+      const float4 rm = ld_chunk<VEC>(R.r[1], c, d), x = ld_chunk<VEC>(row, c, d);
+      float4 o;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) f4_at(o, e) = ffma(a, f4_get(rm, e), f4_get(x, e));
+      return o;
+    };
+    auto fh = [&](int c) { return proj(R.h[0], ah, c); };
+    auto fr = [&](int c) { return ld_chunk<VEC>(R.r[0], c, d); };
+    auto ft = [&](int c) { return proj(R.t[0], at, c); };
+    const DistCtx X = dist_prepare(fh, fr, ft, nch, lane, P.l1, gs);
+    float bh = 0.f, bt = 0.f;  // <r_m, dh'>, <r_m, dt'>
+    for (int c = lane; c < nch; c += 8) {
+      const float4 a = fh(c), b = fr(c), cc = ft(c), rm = ld_chunk<VEC>(R.r[1], c, d);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float dh, dr, dt;
+        dist_elem(X, f4_get(a, e), f4_get(b, e), f4_get(cc, e), dh, dr, dt);
+        bh += f4_get(rm, e) * dh; bt += f4_get(rm, e) * dt;
+      }
+    }
+    bh = group_sum(bh); bt = group_sum(bt);
+    for (int c = lane; c < nch; c += 8) {
+      const float4 a = fh(c), b = fr(c), cc = ft(c);
+      const float4 hv = ld_chunk<VEC>(R.h[0], c, d), tv = ld_chunk<VEC>(R.t[0], c, d),
+                   hm = ld_chunk<VEC>(R.h[1], c, d), tm = ld_chunk<VEC>(R.t[1], c, d);
+      float4 gh, gr, gtt, ghm, gtm, grm;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float dh, dr, dt;
+        dist_elem(X, f4_get(a, e), f4_get(b, e), f4_get(cc, e), dh, dr, dt);
+        f4_at(gh, e) = dh + f4_get(hm, e) * bh;
+        f4_at(gtt, e) = dt + f4_get(tm, e) * bt;
+        f4_at(ghm, e) = f4_get(hv, e) * bh;
+        f4_at(gtm, e) = f4_get(tv, e) * bt;
+        f4_at(gr, e) = dr;
+        f4_at(grm, e) = ah * dh + at * dt;
+      }
+      red_row_chunk<VEC>(G.h[0], c, d, gh);
+      red_row_chunk<VEC>(G.t[0], c, d, gtt);
+      red_row_chunk<VEC>(G.h[1], c, d, ghm);
+      red_row_chunk<VEC>(G.t[1], c, d, gtm);
+      red_row_chunk<VEC>(G.r[0], c, d, gr);
+      red_row_chunk<VEC>(G.r[1], c, d, grm);
+    }
+  } else if (MODEL == KGE_ROTATE) {
+    const float g2 = 2.f * gs;
+    for (int c = lane; c < nch; c += 8) {
+      const float4 hr = ld_chunk<VEC>(R.h[0], c, d), hi = ld_chunk<VEC>(R.h[1], c, d),
+                   rr = ld_chunk<VEC>(R.r[0], c, d), tr = ld_chunk<VEC>(R.t[0], c, d),
+                   ti = ld_chunk<VEC>(R.t[1], c, d);
+      float4 ghr, ghi, gtr, gti, grr;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float im, re;
+        sincos_canon(fmul(f4_get(rr, e), P.phase), im, re);
+        const float sr = f4_get(hr, e) * re - f4_get(hi, e) * im - f4_get(tr, e);
+        const float si = f4_get(hr, e) * im + f4_get(hi, e) * re - f4_get(ti, e);
+        const float dsr = g2 * sr, dsi = g2 * si;
+        f4_at(ghr, e) = dsr * re + dsi * im;
+        f4_at(ghi, e) = -dsr * im + dsi * re;
+        f4_at(gtr, e) = -dsr;
+        f4_at(gti, e) = -dsi;
+        const float dre = dsr * f4_get(hr, e) + dsi * f4_get(hi, e);
+        const float dim = -dsr * f4_get(hi, e) + dsi * f4_get(hr, e);
+        f4_at(grr, e) = (-dre * im + dim * re) * P.phase;
+      }
+      red_row_chunk<VEC>(G.h[0], c, d, ghr);
+      red_row_chunk<VEC>(G.h[1], c, d, ghi);
+      red_row_chunk<VEC>(G.t[0], c, d, gtr);
+      red_row_chunk<VEC>(G.t[1], c, d, gti);
+      red_row_chunk<VEC>(G.r[0], c, d, grr);
+    }
+  } else if (MODEL == KGE_DISTMULT || MODEL == KGE_CP) {
+    const float ng = -gs;
+    for (int c = lane; c < nch; c += 8) {
+      const float4 a = ld_chunk<VEC>(R.h[0], c, d), b = ld_chunk<VEC>(R.r[0], c, d), cc = ld_chunk<VEC>(R.t[0], c, d);
+      float4 gh, gr, gtt;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        f4_at(gh, e) = ng * f4_get(b, e) * f4_get(cc, e);
+        f4_at(gr, e) = ng * f4_get(a, e) * f4_get(cc, e);
+        f4_at(gtt, e) = ng * f4_get(a, e) * f4_get(b, e);
+      }
+      red_row_chunk<VEC>(G.h[0], c, d, gh);
+      red_row_chunk<VEC>(G.r[0], c, d, gr);
+      red_row_chunk<VEC>(G.t[0], c, d, gtt);
+    }
+  } else if (MODEL == KGE_COMPLEX) {
+    const float ng = -gs;
+    for (int c = lane; c < nch; c += 8) {
+      const float4 hr = ld_chunk<VEC>(R.h[0], c, d), hi = ld_chunk<VEC>(R.h[1], c, d),
+                   rr = ld_chunk<VEC>(R.r[0], c, d), ri = ld_chunk<VEC>(R.r[1], c, d),
+                   tr = ld_chunk<VEC>(R.t[0], c, d), ti = ld_chunk<VEC>(R.t[1], c, d);
+      float4 ghr, ghi, grr, gri, gtr, gti;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float a = f4_get(hr, e), b = f4_get(hi, e), p = f4_get(rr, e), q = f4_get(ri, e),
+                    x = f4_get(tr, e), y = f4_get(ti, e);
+        f4_at(ghr, e) = ng * (x * p + y * q);
+        f4_at(ghi, e) = ng * (y * p - x * q);
+        f4_at(gtr, e) = ng * (a * p - b * q);
+        f4_at(gti, e) = ng * (b * p + a * q);
+        f4_at(grr, e) = ng * (a * x + b * y);
+        f4_at(gri, e) = ng * (a * y - b * x);
+      }
+      red_row_chunk<VEC>(G.h[0], c, d, ghr);
+      red_row_chunk<VEC>(G.h[1], c, d, ghi);
+      red_row_chunk<VEC>(G.r[0], c, d, grr);
+      red_row_chunk<VEC>(G.r[1], c, d, gri);
+      red_row_chunk<VEC>(G.t[0], c, d, gtr);
+      red_row_chunk<VEC>(G.t[1], c, d, gti);
+    }
+  } else if (MODEL == KGE_TRANSR) {
+    // h^ = h*ih; h'_k = sum_j h^_j M_jk; h'^ = normalise(h'); r^ = normalise(r) (then normalised
+    // again inside the distance); x = h'^ + r^^ - t'^.   scratch: hp, tp, dhp, dtp [drp each],
+    // dhn, dtn [dp each]  (see group_scratch_floats_bwd).
+    const int dr = P.dr, nchr = (dr + 3) >> 2, drp = nchr * 4, dp = nch * 4;
+    float sh = 0.f, st = 0.f, sr = 0.f;
+    for (int c = lane; c < nch; c += 8) {
+      const float4 a = ld_chunk<VEC>(R.h[0], c, d), b = ld_chunk<VEC>(R.t[0], c, d);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { sh = ffma(f4_get(a, e), f4_get(a, e), sh); st = ffma(f4_get(b, e), f4_get(b, e), st); }
+    }
+    for (int c = lane; c < nchr; c += 8) {
+      const float4 b = ld_chunk<VEC>(R.r[0], c, dr);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sr = ffma(f4_get(b, e), f4_get(b, e), sr);
+    }
+    sh = group_sum(sh); st = group_sum(st); sr = group_sum(sr);
+    const float ih = inv_norm_from_sumsq(sh), it = inv_norm_from_sumsq(st), ir = inv_norm_from_sumsq(sr);
+    const bool clamp_h0 = __fsqrt_rn(sh) < 1e-12f, clamp_t0 = __fsqrt_rn(st) < 1e-12f,
+               clamp_r0 = __fsqrt_rn(sr) < 1e-12f;
+    float* hp = scratch;
+    float* tp = hp + drp;
+    float* dhp = tp + drp;
+    float* dtp = dhp + drp;
+    float* dhn = dtp + drp;  // [dp] gradient w.r.t. normalised head
+    float* dtn = dhn + dp;
+    for (int c = lane; c < nchr; c += 8) {
+      float4 ah = make_float4(0.f, 0.f, 0.f, 0.f), at = ah;
+      for (int j = 0; j < d; ++j) {
+        const float hn = fmul(__ldg(R.h[0] + j), ih), tn = fmul(__ldg(R.t[0] + j), it);
+        const float4 mrow = ld_chunk<VEC>(R.r[1] + (size_t)j * dr, c, dr);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          f4_at(ah, e) = ffma(hn, f4_get(mrow, e), f4_get(ah, e));
+          f4_at(at, e) = ffma(tn, f4_get(mrow, e), f4_get(at, e));
+        }
+      }
+      *reinterpret_cast<float4*>(hp + 4 * c) = ah;
+      *reinterpret_cast<float4*>(tp + 4 * c) = at;
+    }
+    auto fh = [&](int c) { return *reinterpret_cast<const float4*>(hp + 4 * c); };
+    auto fr = [&](int c) {
+      const float4 b = ld_chunk<VEC>(R.r[0], c, dr);
+      return make_float4(fmul(b.x, ir), fmul(b.y, ir), fmul(b.z, ir), fmul(b.w, ir));
+    };
+    auto ft = [&](int c) { return *reinterpret_cast<const float4*>(tp + 4 * c); };
+    const DistCtx X = dist_prepare(fh, fr, ft, nchr, lane, P.l1, gs);
+    float rdot = 0.f;  // <r^, dr^>
+    for (int c = lane; c < nchr; c += 8) {
+      const float4 a = fh(c), b = fr(c), cc = ft(c);
+      float4 dh, drn, dt;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        dist_elem(X, f4_get(a, e), f4_get(b, e), f4_get(cc, e), f4_at(dh, e), f4_at(drn, e), f4_at(dt, e));
+        rdot += f4_get(b, e) * f4_get(drn, e);
+      }
+      *reinterpret_cast<float4*>(dhp + 4 * c) = dh;
+      *reinterpret_cast<float4*>(dtp + 4 * c) = dt;
+    }
+    rdot = group_sum(rdot);
+    if (clamp_r0) rdot = 0.f;
+    for (int c = lane; c < nchr; c += 8) {
+      const float4 a = fh(c), b = fr(c), cc = ft(c);
+      float4 gr;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float dh, drn, dt;
+        dist_elem(X, f4_get(a, e), f4_get(b, e), f4_get(cc, e), dh, drn, dt);
+        f4_at(gr, e) = (drn - f4_get(b, e) * rdot) * ir;
+      }
+      red_row_chunk<VEC>(G.r[0], c, dr, gr);
+    }
+    // dh^_j = sum_k M_jk dh'_k ; dM_jk = h^_j dh'_k + t^_j dt'_k
+    float hdot = 0.f, tdot = 0.f;
+    for (int j = 0; j < d; ++j) {
+      const float hn = fmul(__ldg(R.h[0] + j), ih), tn = fmul(__ldg(R.t[0] + j), it);
+      float ph = 0.f, pt = 0.f;
+      for (int c = lane; c < nchr; c += 8) {
+        const float4 mrow = ld_chunk<VEC>(R.r[1] + (size_t)j * dr, c, dr);
+        const float4 dh = *reinterpret_cast<const float4*>(dhp + 4 * c);
+        const float4 dt = *reinterpret_cast<const float4*>(dtp + 4 * c);
+        float4 gm;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          ph += f4_get(mrow, e) * f4_get(dh, e);
+          pt += f4_get(mrow, e) * f4_get(dt, e);
+          f4_at(gm, e) = hn * f4_get(dh, e) + tn * f4_get(dt, e);
+        }
+        if (G.r[1]) red_chunk<VEC>(G.r[1] + (size_t)j * dr, c, dr, gm);
+      }
+      ph = group_sum(ph); pt = group_sum(pt);
+      hdot += hn * ph; tdot += tn * pt;
+      if (lane == 0) { dhn[j] = ph; dtn[j] = pt; }
+    }
+    if (clamp_h0) hdot = 0.f;
+    if (clamp_t0) tdot = 0.f;
+    __syncwarp();
+    for (int c = lane; c < nch; c += 8) {
+      const float4 hv = ld_chunk<VEC>(R.h[0], c, d), tv = ld_chunk<VEC>(R.t[0], c, d);
+      float4 gh, gtt;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = 4 * c + e;
+        const float a = (j < d) ? dhn[j] : 0.f, b = (j < d) ? dtn[j] : 0.f;
+        f4_at(gh, e) = (a - f4_get(hv, e) * ih * hdot) * ih;
+        f4_at(gtt, e) = (b - f4_get(tv, e) * it * tdot) * it;
+      }
+      red_row_chunk<VEC>(G.h[0], c, d, gh);
+      red_row_chunk<VEC>(G.t[0], c, d, gtt);
+    }
+    (void)dp;
+  }
+}
+
+// shared-memory floats one 8-lane group needs in the backward kernels
+inline size_t group_scratch_floats_bwd(const kge_model_t* m) {
+  if (m->model != KGE_TRANSR) return 0;
+  const size_t drp = (size_t)(((m->rel_dim + 3) >> 2) * 4), dp = (size_t)(((m->dim + 3) >> 2) * 4);
+  return 4 * drp + 2 * dp;
+}
+
+}  // namespace kge

@@ -1,0 +1,234 @@
+// kge_train.cu — fused training step for the pairwise (margin) models and the sparse
+// optimizer application:  replaces, per batch, Trainer.train_step_pairwise
+// (pykg2vec/utils/trainer.py:147-157: two forward passes + Criterion.pairwise_hinge),
+// loss.backward() (:298) and optimizer.step() (:299) for optim.SGD / optim.Adagrad
+// over dense nn.Embedding gradients.
+//
+//   kernel A (train_hinge_kernel): one 8-lane group per (positive, negative) pair:
+//     both scores (canonical arithmetic, == forward()), hinge term, and for active
+//     pairs the row gradients of both triples scattered into a zero-filled dense
+//     gradient scratch G.
+//   kernel B (apply_rows_kernel): for every (table, id) the batch touched, take the
+//     accumulated row gradient out of G with atomicExch(.,0) — duplicates of a row see
+//     zeros — and apply the optimizer to that row.  G is zero again afterwards, and
+//     rows the batch did not touch are neither read nor written, which for SGD and
+//     Adagrad is exactly what the dense optimizers do to zero-gradient rows.
+#include "kge_grads.cuh"
+
+namespace kge {
+
+constexpr int kThreads = 256;
+constexpr int kGroupsPerCta = kThreads / 8;
+
+struct GradTablesT { float* t[KGE_MAX_TABLES]; };
+
+template <int MODEL, int VEC>
+__global__ void __launch_bounds__(kThreads)
+train_hinge_kernel(ModelParams P, GradTablesT GT, const int64_t* __restrict__ ph,
+                   const int64_t* __restrict__ pr, const int64_t* __restrict__ pt,
+                   const int64_t* __restrict__ nh, const int64_t* __restrict__ nr,
+                   const int64_t* __restrict__ nt, int64_t n, float margin,
+                   float* __restrict__ loss, int scratch_floats) {
+  extern __shared__ float4 smem_f4[];
+  __shared__ float red[kThreads / 32];
+  float* scratch = reinterpret_cast<float*>(smem_f4) + (size_t)(threadIdx.x >> 3) * scratch_floats;
+  const int lane = threadIdx.x & 7;
+  const int64_t g = (int64_t)blockIdx.x * kGroupsPerCta + (threadIdx.x >> 3);
+  float v = 0.f;
+  if (g < n) {
+    const int64_t a = __ldg(ph + g), b = __ldg(pr + g), c = __ldg(pt + g);
+    const int64_t x = __ldg(nh + g), y = __ldg(nr + g), z = __ldg(nt + g);
+    TripleRows Rp, Rn;
+    resolve_rows<MODEL>(Rp, P, P.tab, P.tab, P.tab, a, b, c);
+    resolve_rows<MODEL>(Rn, P, P.tab, P.tab, P.tab, x, y, z);
+    const float sp = score_group<MODEL, VEC, KGE_GROUP_TAIL>(Rp, P, lane, scratch);
+    const float sn = score_group<MODEL, VEC, KGE_GROUP_TAIL>(Rn, P, lane, scratch);
+    v = fmaxf(fsub(fadd(sp, margin), sn), 0.f);  // Criterion.pairwise_hinge, criterion.py:26-29
+    if (v > 0.f) {
+      GradRows Gp, Gn;
+      resolve_grad_rows<MODEL>(Gp, P, GT.t, a, b, c);
+      resolve_grad_rows<MODEL>(Gn, P, GT.t, x, y, z);
+      grad_group<MODEL, VEC>(Rp, Gp, P, lane, 1.f, scratch);
+      grad_group<MODEL, VEC>(Rn, Gn, P, lane, -1.f, scratch);
+    }
+    if (lane != 0) v = 0.f;
+  }
+  // batch loss: block tree + one atomic per CTA
+#pragma unroll
+  for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) s += red[w];
+    if (s != 0.f) atomicAdd(loss, s);
+  }
+}
+
+// ---- sparse optimizer application ---------------------------------------------
+constexpr int kMaxTasks = 12;
+struct ApplyTasks {
+  int ntasks;
+  float* w[kMaxTasks];      // table to update
+  float* g[kMaxTasks];      // its gradient scratch
+  float* state[kMaxTasks];  // Adagrad: sum of squared gradients (same shape); SGD: unused
+  int width[kMaxTasks];
+  const int64_t* ids[kMaxTasks];
+};
+
+// optimizer 0: SGD  (w -= lr * g)                       torch.optim.SGD, trainer.py:117-121
+// optimizer 1: Adagrad (s += g*g; w -= lr * g / (sqrt(s) + eps))  torch.optim.Adagrad, trainer.py:122-126
+template <int OPT>
+__global__ void __launch_bounds__(kThreads)
+apply_rows_kernel(ApplyTasks T, int64_t n, float lr, float eps) {
+  const int task = blockIdx.y;
+  const int lane = threadIdx.x & 7;
+  const int64_t i = (int64_t)blockIdx.x * kGroupsPerCta + (threadIdx.x >> 3);
+  if (i >= n) return;
+  const int width = T.width[task];
+  const size_t off = (size_t)__ldg(T.ids[task] + i) * (size_t)width;
+  float* __restrict__ w = T.w[task] + off;
+  float* __restrict__ g = T.g[task] + off;
+  float* __restrict__ s = (OPT == 1) ? T.state[task] + off : nullptr;
+  for (int j = lane; j < width; j += 8) {
+    const float gv = atomicExch(g + j, 0.f);
+    if (gv != 0.f) {
+      if (OPT == 0) {
+        w[j] -= lr * gv;
+      } else {
+        const float sv = s[j] + gv * gv;
+        s[j] = sv;
+        w[j] -= lr * gv / (sqrtf(sv) + eps);
+      }
+    }
+  }
+}
+
+int check_model(const kge_model_t* m);
+int model_vec(const kge_model_t* m);
+
+// which tables a head / relation / tail id touches, per model
+static int roles(int model, int which /*0 h, 1 r, 2 t*/, int out[2]) {
+  switch (model) {
+    case KGE_TRANSE: case KGE_DISTMULT: case KGE_TRANSM:
+      out[0] = which == 1 ? 1 : 0; return 1;
+    case KGE_CP: out[0] = which; return 1;  // sub, rel, obj
+    case KGE_TRANSH: if (which == 1) { out[0] = 1; out[1] = 2; return 2; } out[0] = 0; return 1;
+    case KGE_TRANSR: if (which == 1) { out[0] = 1; out[1] = 2; return 2; } out[0] = 0; return 1;
+    case KGE_TRANSD: if (which == 1) { out[0] = 1; out[1] = 3; return 2; } out[0] = 0; out[1] = 2; return 2;
+    case KGE_ROTATE: if (which == 1) { out[0] = 2; return 1; } out[0] = 0; out[1] = 1; return 2;
+    case KGE_COMPLEX: if (which == 1) { out[0] = 2; out[1] = 3; return 2; } out[0] = 0; out[1] = 1; return 2;
+    default: return 0;
+  }
+}
+static int table_width(const kge_model_t* m, int k) {
+  switch (m->model) {
+    case KGE_TRANSR: return k == 0 ? m->dim : (k == 1 ? m->rel_dim : m->dim * m->rel_dim);
+    default: return m->dim;
+  }
+}
+
+int launch_apply(const kge_model_t* m, float* const* tables_rw, float* const* grad_scratch,
+                 float* const* state, int optimizer, const int64_t* const* hs, const int64_t* const* rs,
+                 const int64_t* const* ts, int nsets, int64_t n, float lr, float eps, cudaStream_t st) {
+  ApplyTasks T;
+  T.ntasks = 0;
+  for (int s = 0; s < nsets; ++s) {
+    const int64_t* idarr[3] = {hs[s], rs[s], ts[s]};
+    for (int which = 0; which < 3; ++which) {
+      int tabs[2];
+      const int nt = roles(m->model, which, tabs);
+      for (int q = 0; q < nt; ++q) {
+        const int k = tabs[q];
+        if (!grad_scratch[k] || !tables_rw[k]) continue;
+        if (T.ntasks >= kMaxTasks) { set_error("too many apply tasks"); return KGE_EINVAL; }
+        T.w[T.ntasks] = tables_rw[k];
+        T.g[T.ntasks] = grad_scratch[k];
+        T.state[T.ntasks] = state ? state[k] : nullptr;
+        if (optimizer == 1 && !T.state[T.ntasks]) { set_error("Adagrad needs a state table for table %d", k); return KGE_EINVAL; }
+        T.width[T.ntasks] = table_width(m, k);
+        T.ids[T.ntasks] = idarr[which];
+        ++T.ntasks;
+      }
+    }
+  }
+  if (T.ntasks == 0) return KGE_OK;
+  const dim3 grid((unsigned)((n + kGroupsPerCta - 1) / kGroupsPerCta), (unsigned)T.ntasks);
+  if (optimizer == 0) apply_rows_kernel<0><<<grid, kThreads, 0, st>>>(T, n, lr, eps);
+  else apply_rows_kernel<1><<<grid, kThreads, 0, st>>>(T, n, lr, eps);
+  KGE_CHECK_LAUNCH("apply_rows_kernel");
+  return KGE_OK;
+}
+
+}  // namespace kge
+
+using namespace kge;
+
+extern "C" int kge_train_pairwise_hinge_sgd(const kge_model_t* m, float* const* tables_rw,
+                                            float* const* grad_scratch, const int64_t* pos_h,
+                                            const int64_t* pos_r, const int64_t* pos_t,
+                                            const int64_t* neg_h, const int64_t* neg_r,
+                                            const int64_t* neg_t, int64_t n, float margin, float lr,
+                                            float* loss_out, void* stream) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  if (n <= 0 || !tables_rw || !grad_scratch || !pos_h || !pos_r || !pos_t || !neg_h || !neg_r || !neg_t || !loss_out) {
+    set_error("kge_train_pairwise_hinge_sgd: bad arguments"); return KGE_EINVAL;
+  }
+  const int nt = num_tables(m->model);
+  const ModelParams P = make_params(m, nullptr);
+  GradTablesT GT;
+  int vec = model_vec(m);
+  for (int k = 0; k < KGE_MAX_TABLES; ++k) {
+    GT.t[k] = (k < nt) ? grad_scratch[k] : nullptr;
+    if (k < nt && m->model == KGE_TRANSM && k == 2) GT.t[k] = nullptr;
+    if (GT.t[k]) {
+      if ((const float*)tables_rw[k] != m->tables[k]) { set_error("tables_rw[%d] must alias m->tables[%d]", k, k); return KGE_EINVAL; }
+      const uintptr_t a = (uintptr_t)GT.t[k];
+      if (vec == 4 && (a & 15)) vec = 2;
+      if (vec == 2 && (a & 7)) vec = 1;
+    }
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  KGE_CUDA_OK(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
+  const int sf = (int)group_scratch_floats_bwd(m);
+  const size_t smem = (size_t)sf * kGroupsPerCta * sizeof(float);
+  const unsigned grid = (unsigned)((n + kGroupsPerCta - 1) / kGroupsPerCta);
+#define CALL(M, V)                                                                               \
+  do {                                                                                           \
+    if (smem > 48 * 1024)                                                                        \
+      KGE_CUDA_OK(cudaFuncSetAttribute(train_hinge_kernel<M, V>,                                 \
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    train_hinge_kernel<M, V><<<grid, kThreads, smem, st>>>(P, GT, pos_h, pos_r, pos_t, neg_h, neg_r, \
+                                                          neg_t, n, margin, loss_out, sf);       \
+  } while (0)
+  KGE_DISPATCH_MODEL_VEC(m->model, vec, CALL);
+#undef CALL
+  KGE_CHECK_LAUNCH("train_hinge_kernel");
+  const int64_t* hs[2] = {pos_h, neg_h};
+  const int64_t* rs[2] = {pos_r, neg_r};
+  const int64_t* ts[2] = {pos_t, neg_t};
+  float* gs[KGE_MAX_TABLES];
+  for (int k = 0; k < KGE_MAX_TABLES; ++k) gs[k] = GT.t[k];
+  return launch_apply(m, tables_rw, gs, nullptr, 0, hs, rs, ts, 2, n, lr, 0.f, st);
+}
+
+extern "C" int kge_optim_apply_rows(const kge_model_t* m, float* const* tables_rw,
+                                    float* const* grad_scratch, float* const* state, int optimizer,
+                                    const int64_t* h, const int64_t* r, const int64_t* t, int64_t n,
+                                    float lr, float eps, void* stream) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  if (n <= 0 || !tables_rw || !grad_scratch || !h || !r || !t || (optimizer != 0 && optimizer != 1)) {
+    set_error("kge_optim_apply_rows: bad arguments"); return KGE_EINVAL;
+  }
+  float* gs[KGE_MAX_TABLES];
+  const int nt = num_tables(m->model);
+  for (int k = 0; k < KGE_MAX_TABLES; ++k) gs[k] = (k < nt) ? grad_scratch[k] : nullptr;
+  if (m->model == KGE_TRANSM) gs[2] = nullptr;
+  const int64_t* hs[1] = {h};
+  const int64_t* rs[1] = {r};
+  const int64_t* ts[1] = {t};
+  return launch_apply(m, tables_rw, gs, state, optimizer, hs, rs, ts, 1, n, lr, eps, (cudaStream_t)stream);
+}

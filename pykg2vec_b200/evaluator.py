@@ -1,0 +1,285 @@
+"""Evaluator / MetricCalculator — mirror of pykg2vec/utils/evaluator.py.
+
+Same constructor, `test_tail_rank / test_head_rank / test_rel_rank`, `mini_test`,
+`full_test`, `test` entry points and the same MetricCalculator metric dictionaries, but
+`test()` no longer walks one triple at a time (evaluator.py:313-326: two forwards over
+all N entities, a full topk sort, a D2H copy of N ids and a Python loop per triple):
+queries are ranked in batches by the 1-vs-all counting kernel (kge_rank_1vsall) and only
+Q x 4 int32 ranks come back to the host.
+"""
+import os
+import timeit
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class MetricCalculator:
+    """Mirror of evaluator.py:14-230 (metric bookkeeping is host logic and stays Python)."""
+
+    def __init__(self, config):
+        self.config = config
+        self.hr_t = config.knowledge_graph.read_cache_data('hr_t')
+        self.tr_h = config.knowledge_graph.read_cache_data('tr_h')
+        self.mr, self.fmr, self.mrr, self.fmrr, self.hit, self.fhit = {}, {}, {}, {}, {}, {}
+        self.epoch = None
+        self.reset()
+
+    def reset(self):
+        self.rank_head, self.rank_tail, self.f_rank_head, self.f_rank_tail = [], [], [], []
+        self.epoch = None
+        self.start_time = timeit.default_timer()
+
+    # -- reference-compatible slow path: sorted candidate lists (evaluator.py:54-123) --------
+    def append_result(self, result):
+        predict_tail, predict_head = result[0], result[1]
+        h, r, t = result[2], result[3], result[4]
+        self.epoch = result[5]
+        t_rank, f_t_rank = self.get_tail_rank(predict_tail, h, r, t)
+        h_rank, f_h_rank = self.get_head_rank(predict_head, h, r, t)
+        self.rank_head.append(h_rank)
+        self.rank_tail.append(t_rank)
+        self.f_rank_head.append(f_h_rank)
+        self.f_rank_tail.append(f_t_rank)
+
+    def get_tail_rank(self, tail_candidate, h, r, t):
+        trank = ftrank = 0
+        known = self.hr_t[(h, r)]
+        for j in range(len(tail_candidate)):
+            val = tail_candidate[-j - 1]
+            if val == t:
+                break
+            trank += 1
+            ftrank += 1
+            if val in known:
+                ftrank -= 1
+        return trank, ftrank
+
+    def get_head_rank(self, head_candidate, h, r, t):
+        hrank = fhrank = 0
+        known = self.tr_h[(t, r)]
+        for j in range(len(head_candidate)):
+            val = head_candidate[-j - 1]
+            if val == h:
+                break
+            hrank += 1
+            fhrank += 1
+            if val in known:
+                fhrank -= 1
+        return hrank, fhrank
+
+    # -- fast path: ranks counted on the device ---------------------------------------------
+    def append_ranks(self, counts, epoch):
+        """counts: [Q,4] int array of 0-based (trank, ftrank, hrank, fhrank)."""
+        c = np.asarray(counts)
+        self.epoch = epoch
+        self.rank_tail.extend(c[:, 0].tolist())
+        self.f_rank_tail.extend(c[:, 1].tolist())
+        self.rank_head.extend(c[:, 2].tolist())
+        self.f_rank_head.extend(c[:, 3].tolist())
+
+    def settle(self):
+        """evaluator.py:125-141."""
+        head_ranks = np.asarray(self.rank_head, dtype=np.float32) + 1
+        tail_ranks = np.asarray(self.rank_tail, dtype=np.float32) + 1
+        head_franks = np.asarray(self.f_rank_head, dtype=np.float32) + 1
+        tail_franks = np.asarray(self.f_rank_tail, dtype=np.float32) + 1
+        ranks = np.concatenate((head_ranks, tail_ranks))
+        franks = np.concatenate((head_franks, tail_franks))
+        self.mr[self.epoch] = np.mean(ranks)
+        self.mrr[self.epoch] = np.mean(np.reciprocal(ranks))
+        self.fmr[self.epoch] = np.mean(franks)
+        self.fmrr[self.epoch] = np.mean(np.reciprocal(franks))
+        for hit in self.config.hits:
+            self.hit[(self.epoch, hit)] = np.mean(ranks <= hit, dtype=np.float32)
+            self.fhit[(self.epoch, hit)] = np.mean(franks <= hit, dtype=np.float32)
+
+    def get_curr_scores(self):
+        return {'mr': self.mr[self.epoch], 'fmr': self.fmr[self.epoch],
+                'mrr': self.mrr[self.epoch], 'fmrr': self.fmrr[self.epoch]}
+
+    def save_test_summary(self, model_name):
+        """evaluator.py:151-206 (summary txt + per-epoch CSV)."""
+        import pandas as pd
+        files = os.listdir(str(self.config.path_result))
+        l = len([f for f in files if model_name in f if 'Testing' in f])
+        with open(str(self.config.path_result / (model_name + '_summary_' + str(l) + '.txt')), 'w') as fh:
+            fh.write('----------------SUMMARY----------------\n')
+            for key, val in self.config.__dict__.items():
+                if 'gpu' in key or 'knowledge_graph' in key:
+                    continue
+                if isinstance(val, list):
+                    val = '[' + ','.join(str(v) for v in val) + ']'
+                fh.write(key + ':' + str(val) + '\n')
+            fh.write('-----------------------------------------\n')
+        columns = ['Epoch', 'Mean Rank', 'Filtered Mean Rank', 'Mean Reciprocal Rank',
+                   'Filtered Mean Reciprocal Rank']
+        for hit in self.config.hits:
+            columns += ['Hit-%d Ratio' % hit, 'Filtered Hit-%d Ratio' % hit]
+        results = []
+        for epoch in self.mr:
+            row = [epoch, self.mr[epoch], self.fmr[epoch], self.mrr[epoch], self.fmrr[epoch]]
+            for hit in self.config.hits:
+                row += [self.hit[(epoch, hit)], self.fhit[(epoch, hit)]]
+            results.append(row)
+        with open(str(self.config.path_result / (model_name + '_Testing_results_' + str(l) + '.csv')), 'a') as fh:
+            pd.DataFrame(results, columns=columns).to_csv(fh)
+
+    def display_summary(self):
+        stop_time = timeit.default_timer()
+        lines = ['', "------Test Results for %s: Epoch: %s --- time: %.2f------------"
+                 % (getattr(self.config, 'dataset_name', '?'), str(self.epoch), stop_time - self.start_time),
+                 '--# of entities, # of relations: %d, %d' % (self.config.tot_entity, self.config.tot_relation),
+                 '--mr,  filtered mr             : %.4f, %.4f' % (self.mr[self.epoch], self.fmr[self.epoch]),
+                 '--mrr, filtered mrr            : %.4f, %.4f' % (self.mrr[self.epoch], self.fmrr[self.epoch])]
+        for hit in self.config.hits:
+            lines.append('--hits%d                        : %.4f ' % (hit, self.hit[(self.epoch, hit)]))
+            lines.append('--filtered hits%d               : %.4f ' % (hit, self.fhit[(self.epoch, hit)]))
+        lines += ["---------------------------------------------------------", '']
+        if getattr(self.config, 'verbose', False):
+            print("\n".join(lines))
+        return "\n".join(lines)
+
+
+def build_filter_csr(keys, dct):
+    """CSR (ptr[Q+1], idx[nnz]) int64 numpy of the known-positive sets dct[key] per query."""
+    ptr = np.zeros(len(keys) + 1, dtype=np.int64)
+    chunks = []
+    for i, k in enumerate(keys):
+        s = dct.get(k, ())
+        ptr[i + 1] = ptr[i] + len(s)
+        if len(s):
+            chunks.append(np.fromiter(s, dtype=np.int64, count=len(s)))
+    idx = np.concatenate(chunks) if chunks else np.zeros(0, dtype=np.int64)
+    return ptr, idx
+
+
+class Evaluator:
+    """Mirror of evaluator.py:233-334."""
+
+    QUERY_BATCH = 8192  # queries per kge_rank_1vsall call (<= 65535)
+
+    def __init__(self, model, config, tuning=False):
+        self.model = model
+        self.config = config
+        self.tuning = tuning
+        self.test_data = self.config.knowledge_graph.read_cache_data('triplets_test')
+        self.eval_data = self.config.knowledge_graph.read_cache_data('triplets_valid')
+        self.metric_calculator = MetricCalculator(self.config)
+        self._workspace = None
+        self._filter_cache = {}
+
+    # ---- single-query API used by Trainer.infer_* (trainer.py:330-386) ---------------------
+    def _dev(self):
+        return torch.device(self.config.device)
+
+    def test_tail_rank(self, h, r, topk=-1):
+        """ids in DESCENDING score order, length topk (evaluator.py:249-260; worst first for
+        distance models — the caller reads the list from its end)."""
+        if hasattr(self.model, 'predict_tail_rank'):
+            return self.model.predict_tail_rank(torch.LongTensor([h]).to(self._dev()),
+                                                torch.LongTensor([r]).to(self._dev()), topk=topk).squeeze(0)
+        n = self.config.tot_entity
+        dev = self._dev()
+        h_batch = torch.full((n,), int(h), dtype=torch.long, device=dev)
+        r_batch = torch.full((n,), int(r), dtype=torch.long, device=dev)
+        entity_array = torch.arange(n, dtype=torch.long, device=dev)
+        preds = self.model.forward(h_batch, r_batch, entity_array)
+        _, rank = torch.topk(preds, k=topk)
+        return rank
+
+    def test_head_rank(self, r, t, topk=-1):
+        if hasattr(self.model, 'predict_head_rank'):
+            return self.model.predict_head_rank(torch.LongTensor([t]).to(self._dev()),
+                                                torch.LongTensor([r]).to(self._dev()), topk=topk).squeeze(0)
+        n = self.config.tot_entity
+        dev = self._dev()
+        entity_array = torch.arange(n, dtype=torch.long, device=dev)
+        r_batch = torch.full((n,), int(r), dtype=torch.long, device=dev)
+        t_batch = torch.full((n,), int(t), dtype=torch.long, device=dev)
+        preds = self.model.forward(entity_array, r_batch, t_batch)
+        _, rank = torch.topk(preds, k=topk)
+        return rank
+
+    def test_rel_rank(self, h, t, topk=-1):
+        if hasattr(self.model, 'predict_rel_rank'):
+            return self.model.predict_rel_rank(h.to(self._dev()), t.to(self._dev()), topk=topk).squeeze(0)
+        n = self.config.tot_relation
+        dev = self._dev()
+        h_batch = torch.full((n,), int(h), dtype=torch.long, device=dev)
+        rel_array = torch.arange(n, dtype=torch.long, device=dev)
+        t_batch = torch.full((n,), int(t), dtype=torch.long, device=dev)
+        preds = self.model.forward(h_batch, rel_array, t_batch)
+        _, rank = torch.topk(preds, k=topk)
+        return rank
+
+    # ---- batched ranking ---------------------------------------------------------------------
+    def rank_triples(self, hs, rs, ts, filt_t=None, filt_h=None):
+        """0-based (trank, ftrank, hrank, fhrank) for host id arrays -> numpy int32 [Q,4].
+        Host buffers in, host ranks out: this is the end-to-end call bench.py times."""
+        hs = np.ascontiguousarray(hs, dtype=np.int64)
+        rs = np.ascontiguousarray(rs, dtype=np.int64)
+        ts = np.ascontiguousarray(ts, dtype=np.int64)
+        Q = hs.shape[0]
+        dev = self._dev()
+        desc = self.model.kge_desc()
+        out = np.empty((Q, 4), dtype=np.int32)
+        for lo in range(0, Q, self.QUERY_BATCH):
+            hi = min(Q, lo + self.QUERY_BATCH)
+            q = hi - lo
+            ids = torch.from_numpy(np.stack([hs[lo:hi], rs[lo:hi], ts[lo:hi]])).to(dev, non_blocking=True)
+            ft = fh = None
+            if filt_t is not None:
+                p, i = filt_t
+                sub_p = p[lo:hi + 1] - p[lo]
+                ft = (torch.from_numpy(sub_p).to(dev), torch.from_numpy(i[p[lo]:p[hi]]).to(dev))
+                p, i = filt_h
+                sub_p = p[lo:hi + 1] - p[lo]
+                fh = (torch.from_numpy(sub_p).to(dev), torch.from_numpy(i[p[lo]:p[hi]]).to(dev))
+            need = _lib.rank_workspace_bytes(desc, q)
+            if self._workspace is None or self._workspace.numel() < need:
+                self._workspace = torch.empty(max(need, 16), dtype=torch.uint8, device=dev)
+            counts = _lib.rank_1vsall(desc, ids[0], ids[1], ids[2], ft, fh, workspace=self._workspace)
+            out[lo:hi] = counts.cpu().numpy()
+        return out
+
+    def _filters_for(self, data, num):
+        key = (id(data), num)
+        if key not in self._filter_cache:
+            mc = self.metric_calculator
+            tr = [(data[i].h, data[i].r, data[i].t) for i in range(num)]
+            ft = build_filter_csr([(h, r) for h, r, t in tr], mc.hr_t)
+            fh = build_filter_csr([(t, r) for h, r, t in tr], mc.tr_h)
+            arr = np.asarray(tr, dtype=np.int64).reshape(-1, 3)
+            self._filter_cache[key] = (arr, ft, fh)
+        return self._filter_cache[key]
+
+    def mini_test(self, epoch=None):
+        if self.config.test_num == 0:
+            tot_valid_to_test = len(self.eval_data)
+        else:
+            tot_valid_to_test = min(self.config.test_num, len(self.eval_data))
+        if getattr(self.config, 'debug', False):
+            tot_valid_to_test = 10
+        return self.test(self.eval_data, tot_valid_to_test, epoch=epoch)
+
+    def full_test(self, epoch=None):
+        tot_valid_to_test = len(self.test_data)
+        if getattr(self.config, 'debug', False):
+            tot_valid_to_test = 10
+        return self.test(self.test_data, tot_valid_to_test, epoch=epoch)
+
+    def test(self, data, num_of_test, epoch=None):
+        self.metric_calculator.reset()
+        arr, ft, fh = self._filters_for(data, num_of_test)
+        with torch.no_grad():
+            counts = self.rank_triples(arr[:, 0], arr[:, 1], arr[:, 2], ft, fh)
+        self.metric_calculator.append_ranks(counts, epoch)
+        self.metric_calculator.settle()
+        self.metric_calculator.display_summary()
+        if epoch is not None and hasattr(self.config, 'epochs') and hasattr(self.config, 'path_result') \
+                and self.metric_calculator.epoch >= self.config.epochs - 1:
+            self.metric_calculator.save_test_summary(self.model.model_name)
+        return self.metric_calculator.get_curr_scores()

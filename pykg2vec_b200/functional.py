@@ -1,0 +1,110 @@
+"""torch.autograd.Function wrappers around the C-ABI kernels.
+
+These are what make the CUDA path a drop-in behind `loss.backward()` of the
+reference's Trainer (pykg2vec/utils/trainer.py:298): forward() returns an fp32 [b]
+tensor whose backward scatters DENSE gradients into the nn.Embedding weights, exactly
+the autograd contract of the reference models.  No CPU / eager fallback exists: CPU
+tensors raise.
+"""
+import torch
+
+from . import _lib
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if not t.is_cuda:
+            raise _lib.KgeError(
+                "pykg2vec_b200 runs on CUDA (sm_100a) only: got a %s tensor. There is no CPU "
+                "fallback — move the model and ids to a CUDA device." % t.device)
+
+
+class ScoreFunction(torch.autograd.Function):
+    """model.forward(h, r, t) -> scores [b].  `spec` is the model's static description
+    (name, dim, ...), tables are passed explicitly so autograd tracks them."""
+
+    @staticmethod
+    def forward(ctx, spec, h, r, t, *tables):
+        _require_cuda(h, r, t, *tables)
+        h, r, t = h.contiguous(), r.contiguous(), t.contiguous()
+        desc = spec.desc([tb.detach() for tb in tables])
+        out = _lib.score_fwd(desc, h, r, t, _lib.GROUP_TAIL)
+        ctx.spec = spec
+        ctx.save_for_backward(h, r, t, *tables)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        h, r, t, *tables = ctx.saved_tensors
+        desc = ctx.spec.desc([tb.detach() for tb in tables])
+        grads = []
+        for k, tb in enumerate(tables):
+            need = ctx.needs_input_grad[4 + k]
+            grads.append(torch.zeros_like(tb) if need else None)
+        _lib.score_bwd(desc, h, r, t, gout.contiguous(), grads)
+        return (None, None, None, None, *grads)
+
+
+class RegFunction(torch.autograd.Function):
+    """get_reg(h, r, t): lmbda * mean_b sum_rows g(x)  (pointwise.py:448-458,190-202,224-238)."""
+
+    @staticmethod
+    def forward(ctx, spec, reg_type, lmbda, h, r, t, *tables):
+        _require_cuda(h, r, t, *tables)
+        desc = spec.desc([tb.detach() for tb in tables])
+        out = _lib.reg_fwd_bwd(desc, reg_type, lmbda, h.contiguous(), r.contiguous(), t.contiguous())
+        ctx.spec, ctx.reg_type, ctx.lmbda = spec, reg_type, lmbda
+        ctx.save_for_backward(h, r, t, *tables)
+        return out.reshape(())
+
+    @staticmethod
+    def backward(ctx, gout):
+        h, r, t, *tables = ctx.saved_tensors
+        desc = ctx.spec.desc([tb.detach() for tb in tables])
+        grads = [torch.zeros_like(tb) for tb in tables]
+        # d(reg)/d(table) scaled by the upstream scalar (read on the host: one tiny sync, as
+        # loss.item() already is in the reference loop, trainer.py:300)
+        _lib.reg_fwd_bwd(desc, ctx.reg_type, ctx.lmbda, h, r, t, grad_scale=float(gout), grad_tables=grads)
+        return (None, None, None, None, None, None, *grads)
+
+
+class HingeFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pos, neg, margin):
+        _require_cuda(pos, neg)
+        loss, gp, gn = _lib.loss_pairwise_hinge(pos.contiguous(), neg.contiguous(), float(margin))
+        ctx.save_for_backward(gp, gn)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        gp, gn = ctx.saved_tensors
+        return gp * g, gn * g, None
+
+
+class LogisticFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, preds, target):
+        _require_cuda(preds, target)
+        loss, gpreds = _lib.loss_pointwise_logistic(preds.contiguous(), target.contiguous().float())
+        ctx.save_for_backward(gpreds)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (gpreds,) = ctx.saved_tensors
+        return gpreds * g, None
+
+
+class SelfAdvFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pos, neg, neg_rate, alpha):
+        _require_cuda(pos, neg)
+        loss, gp, gn = _lib.loss_selfadv(pos.contiguous(), neg.contiguous(), int(neg_rate), float(alpha))
+        ctx.save_for_backward(gp, gn)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        gp, gn = ctx.saved_tensors
+        return gp * g, gn * g, None, None

@@ -1,0 +1,246 @@
+"""Pairwise (margin-based) models — same constructor kwargs, attribute names,
+state_dict keys, parameter_list and loss bindings as pykg2vec/models/pairwise.py; the
+batch score forward() is the fused gather+score CUDA kernel (kge_score_fwd), its
+backward the scatter kernel (kge_score_bwd).
+
+embed() is not on the hot path (it serves export / visualisation,
+pykg2vec/utils/trainer.py:462-471, visualization.py:91) and stays plain tensor code.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+from .criterion import Criterion
+from .Domain import NamedEmbedding
+from .functional import ScoreFunction
+from .KGMeta import PairwiseModel
+
+
+class ModelSpec:
+    """Static description handed to the autograd functions."""
+
+    def __init__(self, name, dim, rel_dim=None, l1_flag=False, margin=0.0, phase_scale=0.0):
+        self.name, self.dim, self.rel_dim = name, dim, rel_dim if rel_dim is not None else dim
+        self.l1_flag, self.margin, self.phase_scale = l1_flag, margin, phase_scale
+
+    def desc(self, tables):
+        return _lib.ModelDesc(self.name, tables, self.dim, rel_dim=self.rel_dim, l1_flag=self.l1_flag,
+                              margin=self.margin, phase_scale=self.phase_scale)
+
+
+class _KernelScored:
+    """Mixin: forward() through the CUDA kernel; kge_tables() gives the weights in C-ABI order."""
+
+    def kge_tables(self):
+        raise NotImplementedError
+
+    def kge_spec(self):
+        raise NotImplementedError
+
+    def kge_desc(self):
+        """ModelDesc over the live weights (no copy) for the rank / fused-train entry points."""
+        return self.kge_spec().desc([w.detach() for w in self.kge_tables()])
+
+    def forward(self, h, r, t):
+        return ScoreFunction.apply(self.kge_spec(), h, r, t, *self.kge_tables())
+
+
+class TransE(_KernelScored, PairwiseModel):
+    """pykg2vec/models/pairwise.py:12-93."""
+
+    def __init__(self, **kwargs):
+        super(TransE, self).__init__(self.__class__.__name__.lower())
+        param_list = ["tot_entity", "tot_relation", "hidden_size", "l1_flag"]
+        param_dict = self.load_params(param_list, kwargs)
+        self.__dict__.update(param_dict)
+        self.ent_embeddings = NamedEmbedding("ent_embedding", self.tot_entity, self.hidden_size)
+        self.rel_embeddings = NamedEmbedding("rel_embedding", self.tot_relation, self.hidden_size)
+        nn.init.xavier_uniform_(self.ent_embeddings.weight)
+        nn.init.xavier_uniform_(self.rel_embeddings.weight)
+        self.parameter_list = [self.ent_embeddings, self.rel_embeddings]
+        self.loss = Criterion.pairwise_hinge
+
+    def kge_tables(self):
+        return [self.ent_embeddings.weight, self.rel_embeddings.weight]
+
+    def kge_spec(self):
+        return ModelSpec("transe", self.hidden_size, l1_flag=bool(self.l1_flag))
+
+    def embed(self, h, r, t):
+        return self.ent_embeddings(h), self.rel_embeddings(r), self.ent_embeddings(t)
+
+
+class TransH(_KernelScored, PairwiseModel):
+    """pykg2vec/models/pairwise.py:96-182."""
+
+    def __init__(self, **kwargs):
+        super(TransH, self).__init__(self.__class__.__name__.lower())
+        param_list = ["tot_entity", "tot_relation", "hidden_size", "l1_flag"]
+        param_dict = self.load_params(param_list, kwargs)
+        self.__dict__.update(param_dict)
+        self.ent_embeddings = NamedEmbedding("ent_embedding", self.tot_entity, self.hidden_size)
+        self.rel_embeddings = NamedEmbedding("rel_embedding", self.tot_relation, self.hidden_size)
+        self.w = NamedEmbedding("w", self.tot_relation, self.hidden_size)
+        nn.init.xavier_uniform_(self.ent_embeddings.weight)
+        nn.init.xavier_uniform_(self.rel_embeddings.weight)
+        nn.init.xavier_uniform_(self.w.weight)
+        self.parameter_list = [self.ent_embeddings, self.rel_embeddings, self.w]
+        self.loss = Criterion.pairwise_hinge
+
+    def kge_tables(self):
+        return [self.ent_embeddings.weight, self.rel_embeddings.weight, self.w.weight]
+
+    def kge_spec(self):
+        return ModelSpec("transh", self.hidden_size, l1_flag=bool(self.l1_flag))
+
+    def embed(self, h, r, t):
+        emb_h, emb_r, emb_t = self.ent_embeddings(h), self.rel_embeddings(r), self.ent_embeddings(t)
+        proj_vec = self.w(r)
+        return self._projection(emb_h, proj_vec), emb_r, self._projection(emb_t, proj_vec)
+
+    @staticmethod
+    def _projection(emb_e, proj_vec):
+        proj_vec = F.normalize(proj_vec, p=2, dim=-1)
+        return emb_e - torch.sum(emb_e * proj_vec, dim=-1, keepdim=True) * proj_vec
+
+
+class TransD(_KernelScored, PairwiseModel):
+    """pykg2vec/models/pairwise.py:185-278 (valid only for ent_hidden_size == rel_hidden_size,
+    like the reference whose _projection broadcast fails otherwise)."""
+
+    def __init__(self, **kwargs):
+        super(TransD, self).__init__(self.__class__.__name__.lower())
+        param_list = ["tot_entity", "tot_relation", "rel_hidden_size", "ent_hidden_size", "l1_flag"]
+        param_dict = self.load_params(param_list, kwargs)
+        self.__dict__.update(param_dict)
+        self.ent_embeddings = NamedEmbedding("ent_embedding", self.tot_entity, self.ent_hidden_size)
+        self.rel_embeddings = NamedEmbedding("rel_embedding", self.tot_relation, self.rel_hidden_size)
+        self.ent_mappings = NamedEmbedding("ent_mappings", self.tot_entity, self.ent_hidden_size)
+        self.rel_mappings = NamedEmbedding("rel_mappings", self.tot_relation, self.rel_hidden_size)
+        for e in (self.ent_embeddings, self.rel_embeddings, self.ent_mappings, self.rel_mappings):
+            nn.init.xavier_uniform_(e.weight)
+        self.parameter_list = [self.ent_embeddings, self.rel_embeddings, self.ent_mappings, self.rel_mappings]
+        self.loss = Criterion.pairwise_hinge
+
+    def kge_tables(self):
+        return [self.ent_embeddings.weight, self.rel_embeddings.weight, self.ent_mappings.weight,
+                self.rel_mappings.weight]
+
+    def kge_spec(self):
+        if self.ent_hidden_size != self.rel_hidden_size:
+            raise RuntimeError("TransD requires ent_hidden_size == rel_hidden_size (the reference's "
+                               "_projection broadcast, pairwise.py:275-278)")
+        return ModelSpec("transd", self.ent_hidden_size, l1_flag=bool(self.l1_flag))
+
+    def embed(self, h, r, t):
+        emb_h, emb_r, emb_t = self.ent_embeddings(h), self.rel_embeddings(r), self.ent_embeddings(t)
+        h_m, r_m, t_m = self.ent_mappings(h), self.rel_mappings(r), self.ent_mappings(t)
+        return self._projection(emb_h, h_m, r_m), emb_r, self._projection(emb_t, t_m, r_m)
+
+    @staticmethod
+    def _projection(emb_e, emb_m, proj_vec):
+        return emb_e + torch.sum(emb_e * emb_m, dim=-1, keepdim=True) * proj_vec
+
+
+class TransM(_KernelScored, PairwiseModel):
+    """pykg2vec/models/pairwise.py:281-364.  theta is a per-relation constant computed from
+    the training triples at construction (pairwise.py:304-314)."""
+
+    def __init__(self, **kwargs):
+        super(TransM, self).__init__(self.__class__.__name__.lower())
+        param_list = ["tot_entity", "tot_relation", "hidden_size", "l1_flag"]
+        param_dict = self.load_params(param_list, kwargs)
+        self.__dict__.update(param_dict)
+        self.ent_embeddings = NamedEmbedding("ent_embedding", self.tot_entity, self.hidden_size)
+        self.rel_embeddings = NamedEmbedding("rel_embedding", self.tot_relation, self.hidden_size)
+        rel_head = {x: [] for x in range(self.tot_relation)}
+        rel_tail = {x: [] for x in range(self.tot_relation)}
+        rel_counts = {x: 0 for x in range(self.tot_relation)}
+        for tr in kwargs["knowledge_graph"].read_cache_data('triplets_train'):
+            rel_head[tr.r].append(tr.h)
+            rel_tail[tr.r].append(tr.t)
+            rel_counts[tr.r] += 1
+        theta = [1 / np.log(2 + rel_counts[x] / (1 + len(rel_tail[x])) + rel_counts[x] / (1 + len(rel_head[x])))
+                 for x in range(self.tot_relation)]
+        self.theta = torch.from_numpy(np.asarray(theta, dtype=np.float32)).to(kwargs["device"])
+        nn.init.xavier_uniform_(self.ent_embeddings.weight)
+        nn.init.xavier_uniform_(self.rel_embeddings.weight)
+        self.parameter_list = [self.ent_embeddings, self.rel_embeddings]
+        self.loss = Criterion.pairwise_hinge
+
+    def kge_tables(self):
+        return [self.ent_embeddings.weight, self.rel_embeddings.weight, self.theta]
+
+    def kge_spec(self):
+        return ModelSpec("transm", self.hidden_size, l1_flag=bool(self.l1_flag))
+
+    def embed(self, h, r, t):
+        return self.ent_embeddings(h), self.rel_embeddings(r), self.ent_embeddings(t)
+
+
+class TransR(_KernelScored, PairwiseModel):
+    """pykg2vec/models/pairwise.py:367-470."""
+
+    def __init__(self, **kwargs):
+        super(TransR, self).__init__(self.__class__.__name__.lower())
+        param_list = ["tot_entity", "tot_relation", "rel_hidden_size", "ent_hidden_size", "l1_flag"]
+        param_dict = self.load_params(param_list, kwargs)
+        self.__dict__.update(param_dict)
+        self.ent_embeddings = NamedEmbedding("ent_embedding", self.tot_entity, self.ent_hidden_size)
+        self.rel_embeddings = NamedEmbedding("rel_embedding", self.tot_relation, self.rel_hidden_size)
+        self.rel_matrix = NamedEmbedding("rel_matrix", self.tot_relation, self.ent_hidden_size * self.rel_hidden_size)
+        nn.init.xavier_uniform_(self.ent_embeddings.weight)
+        nn.init.xavier_uniform_(self.rel_embeddings.weight)
+        nn.init.xavier_uniform_(self.rel_matrix.weight)
+        self.parameter_list = [self.ent_embeddings, self.rel_embeddings, self.rel_matrix]
+        self.loss = Criterion.pairwise_hinge
+
+    def kge_tables(self):
+        return [self.ent_embeddings.weight, self.rel_embeddings.weight, self.rel_matrix.weight]
+
+    def kge_spec(self):
+        return ModelSpec("transr", self.ent_hidden_size, rel_dim=self.rel_hidden_size, l1_flag=bool(self.l1_flag))
+
+    def embed(self, h, r, t):
+        h_e = F.normalize(self.ent_embeddings(h), p=2, dim=-1)
+        r_e = F.normalize(self.rel_embeddings(r), p=2, dim=-1)
+        t_e = F.normalize(self.ent_embeddings(t), p=2, dim=-1)
+        m = self.rel_matrix(r).view(-1, self.ent_hidden_size, self.rel_hidden_size)
+        return torch.matmul(h_e.unsqueeze(1), m).squeeze(1), r_e, torch.matmul(t_e.unsqueeze(1), m).squeeze(1)
+
+
+class RotatE(_KernelScored, PairwiseModel):
+    """pykg2vec/models/pairwise.py:727-791."""
+
+    def __init__(self, **kwargs):
+        super(RotatE, self).__init__(self.__class__.__name__.lower())
+        param_list = ["tot_entity", "tot_relation", "hidden_size", "margin"]
+        param_dict = self.load_params(param_list, kwargs)
+        self.__dict__.update(param_dict)
+        self.embedding_range = (self.margin + 2.0) / self.hidden_size
+        self.ent_embeddings = NamedEmbedding("ent_embeddings_real", self.tot_entity, self.hidden_size)
+        self.ent_embeddings_imag = NamedEmbedding("ent_embeddings_imag", self.tot_entity, self.hidden_size)
+        self.rel_embeddings = NamedEmbedding("rel_embeddings_real", self.tot_relation, self.hidden_size)
+        nn.init.uniform_(self.ent_embeddings.weight, -self.embedding_range, self.embedding_range)
+        nn.init.uniform_(self.ent_embeddings_imag.weight, -self.embedding_range, self.embedding_range)
+        nn.init.uniform_(self.rel_embeddings.weight, -self.embedding_range, self.embedding_range)
+        self.parameter_list = [self.ent_embeddings, self.ent_embeddings_imag, self.rel_embeddings]
+        self.loss = Criterion.pariwise_logistic
+
+    def kge_tables(self):
+        return [self.ent_embeddings.weight, self.ent_embeddings_imag.weight, self.rel_embeddings.weight]
+
+    def kge_spec(self):
+        # theta = r / (embedding_range / pi)  (pairwise.py:776-782) as one fp32 multiplier
+        phase = float(np.float32(math.pi / self.embedding_range))
+        return ModelSpec("rotate", self.hidden_size, margin=float(self.margin), phase_scale=phase)
+
+    def embed(self, h, r, t):
+        pi = 3.14159265358979323846
+        r_e_r = self.rel_embeddings(r) / (self.embedding_range / pi)
+        return (self.ent_embeddings(h), self.ent_embeddings_imag(h), torch.cos(r_e_r), torch.sin(r_e_r),
+                self.ent_embeddings(t), self.ent_embeddings_imag(t))

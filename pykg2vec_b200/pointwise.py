@@ -1,0 +1,130 @@
+"""Pointwise (logistic) models — same surface as pykg2vec/models/pointwise.py; forward()
+and get_reg() are CUDA kernels (kge_score_fwd / kge_reg_fwd_bwd)."""
+import torch.nn as nn
+
+from .criterion import Criterion
+from .Domain import NamedEmbedding
+from .functional import RegFunction
+from .KGMeta import PointwiseModel
+from .pairwise import ModelSpec, _KernelScored
+
+_REG_TYPES = {"f2": 0, "n3": 1}
+
+
+class _RowRegularised(_KernelScored):
+    _abs_n3 = False
+
+    def _reg(self, h, r, t, reg_type):
+        key = reg_type.lower()
+        if key not in _REG_TYPES:
+            raise NotImplementedError('Unknown regularizer type: %s' % reg_type)
+        code = _REG_TYPES[key]
+        if code == 1 and self._abs_n3:
+            code = 2  # ComplexN3: |x|**3 (pointwise.py:224-238); |x|**2 == x**2 for its "f2"
+        return RegFunction.apply(self.kge_spec(), code, float(self.lmbda), h, r, t, *self.kge_tables())
+
+
+class DistMult(_RowRegularised, PointwiseModel):
+    """pykg2vec/models/pointwise.py:391-458."""
+
+    def __init__(self, **kwargs):
+        super(DistMult, self).__init__(self.__class__.__name__.lower())
+        param_list = ["tot_entity", "tot_relation", "hidden_size", "lmbda"]
+        param_dict = self.load_params(param_list, kwargs)
+        self.__dict__.update(param_dict)
+        self.ent_embeddings = NamedEmbedding("ent_embedding", self.tot_entity, self.hidden_size)
+        self.rel_embeddings = NamedEmbedding("rel_embedding", self.tot_relation, self.hidden_size)
+        nn.init.xavier_uniform_(self.ent_embeddings.weight)
+        nn.init.xavier_uniform_(self.rel_embeddings.weight)
+        self.parameter_list = [self.ent_embeddings, self.rel_embeddings]
+        self.loss = Criterion.pointwise_logistic
+
+    def kge_tables(self):
+        return [self.ent_embeddings.weight, self.rel_embeddings.weight]
+
+    def kge_spec(self):
+        return ModelSpec("distmult", self.hidden_size)
+
+    def embed(self, h, r, t):
+        return self.ent_embeddings(h), self.rel_embeddings(r), self.ent_embeddings(t)
+
+    def get_reg(self, h, r, t, reg_type="F2"):
+        return self._reg(h, r, t, reg_type)
+
+
+class CP(_RowRegularised, PointwiseModel):
+    """pykg2vec/models/pointwise.py:321-388."""
+
+    def __init__(self, **kwargs):
+        super(CP, self).__init__(self.__class__.__name__.lower())
+        param_list = ["tot_entity", "tot_relation", "hidden_size", "lmbda"]
+        param_dict = self.load_params(param_list, kwargs)
+        self.__dict__.update(param_dict)
+        self.sub_embeddings = NamedEmbedding("sub_embedding", self.tot_entity, self.hidden_size)
+        self.rel_embeddings = NamedEmbedding("rel_embedding", self.tot_relation, self.hidden_size)
+        self.obj_embeddings = NamedEmbedding("obj_embedding", self.tot_entity, self.hidden_size)
+        nn.init.xavier_uniform_(self.sub_embeddings.weight)
+        nn.init.xavier_uniform_(self.rel_embeddings.weight)
+        nn.init.xavier_uniform_(self.obj_embeddings.weight)
+        self.parameter_list = [self.sub_embeddings, self.rel_embeddings, self.obj_embeddings]
+        self.loss = Criterion.pointwise_logistic
+
+    def kge_tables(self):
+        return [self.sub_embeddings.weight, self.rel_embeddings.weight, self.obj_embeddings.weight]
+
+    def kge_spec(self):
+        return ModelSpec("cp", self.hidden_size)
+
+    def embed(self, h, r, t):
+        return self.sub_embeddings(h), self.rel_embeddings(r), self.obj_embeddings(t)
+
+    def get_reg(self, h, r, t, reg_type='N3'):
+        return self._reg(h, r, t, reg_type)
+
+
+class Complex(_RowRegularised, PointwiseModel):
+    """pykg2vec/models/pointwise.py:122-202."""
+
+    def __init__(self, **kwargs):
+        super(Complex, self).__init__(self.__class__.__name__.lower())
+        param_list = ["tot_entity", "tot_relation", "hidden_size", "lmbda"]
+        param_dict = self.load_params(param_list, kwargs)
+        self.__dict__.update(param_dict)
+        k = self.hidden_size
+        self.ent_embeddings_real = NamedEmbedding("emb_e_real", self.tot_entity, k)
+        self.ent_embeddings_img = NamedEmbedding("emb_e_img", self.tot_entity, k)
+        self.rel_embeddings_real = NamedEmbedding("emb_rel_real", self.tot_relation, k)
+        self.rel_embeddings_img = NamedEmbedding("emb_rel_img", self.tot_relation, k)
+        for e in (self.ent_embeddings_real, self.ent_embeddings_img, self.rel_embeddings_real,
+                  self.rel_embeddings_img):
+            nn.init.xavier_uniform_(e.weight)
+        self.parameter_list = [self.ent_embeddings_real, self.ent_embeddings_img, self.rel_embeddings_real,
+                               self.rel_embeddings_img]
+        self.loss = Criterion.pointwise_logistic
+
+    def kge_tables(self):
+        return [self.ent_embeddings_real.weight, self.ent_embeddings_img.weight,
+                self.rel_embeddings_real.weight, self.rel_embeddings_img.weight]
+
+    def kge_spec(self):
+        return ModelSpec("complex", self.hidden_size)
+
+    def embed(self, h, r, t):
+        return (self.ent_embeddings_real(h), self.ent_embeddings_img(h), self.rel_embeddings_real(r),
+                self.rel_embeddings_img(r), self.ent_embeddings_real(t), self.ent_embeddings_img(t))
+
+    def get_reg(self, h, r, t, reg_type="F2"):
+        return self._reg(h, r, t, reg_type)
+
+
+class ComplexN3(Complex):
+    """pykg2vec/models/pointwise.py:205-238."""
+    _abs_n3 = True
+
+    def __init__(self, **kwargs):
+        super(ComplexN3, self).__init__(**kwargs)
+        self.model_name = 'complexn3'
+        self.loss = Criterion.pointwise_logistic
+
+    def get_reg(self, h, r, t, reg_type="N3"):
+        return self._reg(h, r, t, reg_type)

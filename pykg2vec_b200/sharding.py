@@ -1,0 +1,153 @@
+"""Multi-GPU partitioning of the hot path (one process per GPU, torch.distributed).
+
+The reference is single-process/single-device; what is added here is the
+minimum the path needs:
+
+* 1-vs-all evaluation with replicated tables: test triples are independent
+  (pykg2vec/utils/evaluator.py:313) -> contiguous query shards, NO collective in the data
+  path, one final all-gather of the Q x 4 int32 ranks.
+* 1-vs-all evaluation with ROW-SHARDED entity tables (tables that outgrow one GPU): every
+  rank sweeps its rows for all queries; the only exchanges are (1) an all-reduce that
+  assembles the compact table of query rows (each row contributed by its owner, zeros
+  elsewhere: x + 0 is exact) and (2) ONE all-reduce-sum of the partial rank counts.
+* data-parallel training with replicated tables: a step's batch is tiny (24 KB of ids for
+  B=512), so ranks all-gather their batch ids and every rank applies the identical global
+  update — no gradient exchange at all.
+
+Everything here is host logic over torch.distributed and runs unchanged on the gloo
+backend (tests/test_sharding_gloo.py, world_size 2, CPU) — the per-shard counting itself is
+injected (`count_fn`) so those tests can plug the oracle in; the product always passes the
+CUDA kernel (`cuda_count_fn`).
+"""
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def init_distributed(backend=None):
+    """Initialise from the torchrun environment (RANK / WORLD_SIZE / MASTER_*)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1:
+        return 0, 1
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        dist.init_process_group(backend=backend)
+    return dist.get_rank(), dist.get_world_size()
+
+
+def shard_range(total, world, rank):
+    """Contiguous balanced partition of range(total): sizes differ by at most one."""
+    base, rem = divmod(int(total), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def allgather_batch_ids(ids):
+    """ids: [k, B] int64 on the rank's device -> [k, world*B]: the global batch every rank
+    trains on (replicated update)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return ids
+    world = dist.get_world_size()
+    out = torch.empty((world,) + tuple(ids.shape), dtype=ids.dtype, device=ids.device)
+    dist.all_gather_into_tensor(out, ids.contiguous())
+    return out.permute(1, 0, 2).reshape(ids.shape[0], world * ids.shape[1]).contiguous()
+
+
+def gather_query_shards(local_counts, total):
+    """local_counts: [q_local, 4] int32 of this rank's query shard (shard_range order) ->
+    [total, 4] on every rank.  The single collective of replicated-table evaluation."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return local_counts
+    world, rank = dist.get_world_size(), dist.get_rank()
+    cap = -(-int(total) // world)
+    buf = torch.zeros((cap, 4), dtype=local_counts.dtype, device=local_counts.device)
+    buf[:local_counts.shape[0]] = local_counts
+    out = torch.empty((world, cap, 4), dtype=local_counts.dtype, device=local_counts.device)
+    dist.all_gather_into_tensor(out, buf)
+    parts = []
+    for r in range(world):
+        lo, hi = shard_range(total, world, r)
+        parts.append(out[r, :hi - lo])
+    return torch.cat(parts, dim=0)
+
+
+def cuda_count_fn(name, dim, **spec_kw):
+    """The product's per-shard counting: kge_rank_1vsall on the local row shard."""
+    from . import _lib
+
+    def fn(shard_tables, query_tables, row_lo, row_hi, qh_c, qr, qt_c, tgt_h, tgt_t, filt_t, filt_h):
+        desc = _lib.ModelDesc(name, shard_tables, dim, **spec_kw)
+        qdesc = _lib.ModelDesc(name, query_tables, dim, **spec_kw)
+        return _lib.rank_1vsall(desc, qh_c, qr, qt_c, filt_t, filt_h, row_lo=row_lo, row_hi=row_hi,
+                                query_desc=qdesc, tgt_h=tgt_h, tgt_t=tgt_t)
+    return fn
+
+
+class RowShardedRanker:
+    """1-vs-all ranks over entity tables partitioned by rows across the ranks.
+
+    entity_tables_local: this rank's rows [row_lo, row_hi) of every ENTITY table (list, in
+    the model's C-ABI order restricted to entity tables); relation tables are replicated.
+    ent_slots / rel_slots: positions of entity / relation tables in the C-ABI table list
+    (e.g. ComplEx: ent_slots=(0,1), rel_slots=(2,3))."""
+
+    def __init__(self, count_fn, num_ent, entity_tables_local, relation_tables, ent_slots, rel_slots,
+                 rank=None, world=None):
+        self.count_fn = count_fn
+        self.num_ent = int(num_ent)
+        self.rank = dist.get_rank() if rank is None else rank
+        self.world = dist.get_world_size() if world is None else world
+        self.row_lo, self.row_hi = shard_range(num_ent, self.world, self.rank)
+        self.ent_local = list(entity_tables_local)
+        self.rel = list(relation_tables)
+        self.ent_slots, self.rel_slots = tuple(ent_slots), tuple(rel_slots)
+        for t in self.ent_local:
+            assert t.shape[0] == self.row_hi - self.row_lo, "local shard has the wrong row count"
+
+    def _assemble(self, ent_tables):
+        n = len(self.ent_slots) + len(self.rel_slots)
+        out = [None] * n
+        for s, t in zip(self.ent_slots, ent_tables):
+            out[s] = t
+        for s, t in zip(self.rel_slots, self.rel):
+            out[s] = t
+        return out
+
+    def exchange_query_rows(self, uniq):
+        """Compact table of the rows `uniq` (sorted global ids) of every entity table,
+        identical on all ranks: owner contributes its rows, everyone else zeros, one
+        all-reduce-sum per table."""
+        dev = self.ent_local[0].device
+        uniq_t = torch.as_tensor(uniq, dtype=torch.long, device=dev)
+        mine = (uniq_t >= self.row_lo) & (uniq_t < self.row_hi)
+        compact = []
+        for t in self.ent_local:
+            buf = torch.zeros((uniq_t.numel(), t.shape[1]), dtype=t.dtype, device=dev)
+            buf[mine] = t[uniq_t[mine] - self.row_lo]
+            if self.world > 1:
+                dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+            compact.append(buf)
+        return compact
+
+    def rank_queries(self, qh, qr, qt, filt_t=None, filt_h=None):
+        """qh/qr/qt: numpy int64 global ids (identical on all ranks).  filt_*: CSR numpy
+        (ptr, idx) with global ids or None.  Returns [Q,4] int32 global ranks on every rank."""
+        dev = self.ent_local[0].device
+        qh = np.ascontiguousarray(qh, dtype=np.int64)
+        qt = np.ascontiguousarray(qt, dtype=np.int64)
+        uniq = np.unique(np.concatenate([qh, qt]))
+        compact_ent = self.exchange_query_rows(uniq)
+        qh_c = torch.from_numpy(np.searchsorted(uniq, qh)).to(dev)
+        qt_c = torch.from_numpy(np.searchsorted(uniq, qt)).to(dev)
+        to = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int64)).to(dev)
+        ft = (to(filt_t[0]), to(filt_t[1])) if filt_t is not None else None
+        fh = (to(filt_h[0]), to(filt_h[1])) if filt_h is not None else None
+        counts = self.count_fn(self._assemble(self.ent_local), self._assemble(compact_ent), self.row_lo,
+                               self.row_hi, qh_c, to(qr), qt_c, to(qh), to(qt), ft, fh)
+        if self.world > 1:
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM)  # the single exchange of partial rank counts
+        return counts

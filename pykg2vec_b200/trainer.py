@@ -1,0 +1,160 @@
+"""Trainer hot loop — mirror of the per-batch part of pykg2vec/utils/trainer.py
+(build_model optimizer selection :103-144, train_step_pairwise :147-157,
+train_step_pointwise :176-180, and the batch body of train_model_epoch :269-300).
+
+Two execution modes for the same step semantics:
+  * autograd mode (any torch optimizer, e.g. adam): model(...) / model.loss(...) /
+    loss.backward() / optimizer.step() exactly as the reference Trainer drives them — the
+    CUDA kernels sit behind forward()/loss()/backward().  This is also what runs when the
+    unmodified reference Trainer is handed these model classes.
+  * fused mode (optimizer sgd or adagrad, config.fused_step not False): the step is issued
+    as a few kernels with no dense [N,d] gradient or dense optimizer sweep:
+      pairwise hinge + SGD : kge_train_pairwise_hinge_sgd (2 kernels)
+      otherwise            : score_fwd -> loss kernel -> score_bwd (+ reg) -> kge_optim_apply_rows
+    Results equal the dense optimizers' (zero-gradient rows do not move under SGD/Adagrad).
+
+The sampler processes, epoch loop, early stopping, checkpointing and export of the
+reference Trainer are out of scope here; batches are handed in as
+host id arrays, which is what Generator yields (pykg2vec/data/generator.py:97,158).
+"""
+import numpy as np
+import torch
+import torch.optim as optim
+
+from . import _lib
+from .evaluator import Evaluator
+from .KGMeta import TrainingStrategy
+
+
+class Trainer:
+    def __init__(self, model, config):
+        self.model = model
+        self.config = config
+        self.evaluator = None
+        self.optimizer = None
+        self._fused = False
+        self._grad_scratch = None
+        self._state = None
+        self._pinned = None
+        self._loss_buf = None
+
+    def build_model(self):
+        """trainer.py:103-144 (optimizer selection; unknown names raise NotImplementedError)."""
+        self.evaluator = Evaluator(self.model, self.config)
+        self.model.to(self.config.device)
+        name = self.config.optimizer
+        lr = self.config.learning_rate
+        if name == "adam":
+            self.optimizer = optim.Adam(self.model.parameters(), lr=lr)
+        elif name == "sgd":
+            self.optimizer = optim.SGD(self.model.parameters(), lr=lr)
+        elif name == "adagrad":
+            self.optimizer = optim.Adagrad(self.model.parameters(), lr=lr)
+        elif name == "rms":
+            self.optimizer = optim.RMSprop(self.model.parameters(), lr=lr)
+        else:
+            raise NotImplementedError("No support for %s optimizer" % name)
+        self._fused = name in ("sgd", "adagrad") and getattr(self.config, "fused_step", True) and \
+            hasattr(self.model, "kge_desc")
+        if self._fused:
+            tabs = self.model.kge_tables()
+            self._grad_scratch = [torch.zeros_like(t) if t.requires_grad else None for t in tabs]
+            if name == "adagrad":  # optim.Adagrad: state_sum starts at initial_accumulator_value = 0
+                self._state = [torch.zeros_like(t) if t.requires_grad else None for t in tabs]
+        self._loss_buf = torch.zeros(1, dtype=torch.float32, device=self.config.device)
+
+    # ---- reference-signature steps (autograd mode) --------------------------------------------
+    def train_step_pairwise(self, pos_h, pos_r, pos_t, neg_h, neg_r, neg_t):
+        pos_preds = self.model(pos_h, pos_r, pos_t)
+        neg_preds = self.model(neg_h, neg_r, neg_t)
+        if self.model.model_name.lower() == "rotate":
+            loss = self.model.loss(pos_preds, neg_preds, self.config.neg_rate, self.config.alpha)
+        else:
+            loss = self.model.loss(pos_preds, neg_preds, self.config.margin)
+        loss = loss + self.model.get_reg(None, None, None)
+        return loss
+
+    def train_step_pointwise(self, h, r, t, target):
+        preds = self.model(h, r, t)
+        loss = self.model.loss(preds, target.type(preds.type()))
+        loss = loss + self.model.get_reg(h, r, t)
+        return loss
+
+    # ---- fused steps --------------------------------------------------------------------------
+    def _opt_code(self):
+        return 0 if self.config.optimizer == "sgd" else 1
+
+    def _fused_pairwise(self, ids):
+        desc = self.model.kge_desc()
+        ph, pr, pt, nh, nr, nt = ids
+        lr = float(self.config.learning_rate)
+        if self.model.model_name.lower() != "rotate" and self.config.optimizer == "sgd":
+            _lib.train_pairwise_hinge_sgd(desc, self._grad_scratch, ph, pr, pt, nh, nr, nt,
+                                          float(self.config.margin), lr, self._loss_buf)
+            return self._loss_buf
+        pos = _lib.score_fwd(desc, ph, pr, pt)
+        neg = _lib.score_fwd(desc, nh, nr, nt)
+        if self.model.model_name.lower() == "rotate":
+            loss, gp, gn = _lib.loss_selfadv(pos, neg, int(self.config.neg_rate), float(self.config.alpha))
+        else:
+            loss, gp, gn = _lib.loss_pairwise_hinge(pos, neg, float(self.config.margin))
+        _lib.score_bwd(desc, ph, pr, pt, gp, self._grad_scratch)
+        _lib.score_bwd(desc, nh, nr, nt, gn, self._grad_scratch)
+        _lib.optim_apply_rows(desc, self._grad_scratch, self._state, self._opt_code(), ph, pr, pt, lr)
+        _lib.optim_apply_rows(desc, self._grad_scratch, self._state, self._opt_code(), nh, nr, nt, lr)
+        return loss
+
+    def _fused_pointwise(self, ids):
+        desc = self.model.kge_desc()
+        h, r, t, y = ids
+        lr = float(self.config.learning_rate)
+        preds = _lib.score_fwd(desc, h, r, t)
+        loss, g = _lib.loss_pointwise_logistic(preds, y.to(torch.float32))
+        _lib.score_bwd(desc, h, r, t, g, self._grad_scratch)
+        reg_type = 2 if getattr(self.model, "_abs_n3", False) else (1 if self.model.model_name == "cp" else 0)
+        reg = _lib.reg_fwd_bwd(desc, reg_type, float(self.model.lmbda), h, r, t, grad_scale=1.0,
+                               grad_tables=self._grad_scratch)
+        _lib.optim_apply_rows(desc, self._grad_scratch, self._state, self._opt_code(), h, r, t, lr)
+        return loss + reg
+
+    # ---- one batch, host ids in, host loss out (trainer.py:269-300) -----------------------------
+    def _to_device(self, arrays):
+        """Pack the batch's id arrays into one pinned staging buffer and issue ONE H2D copy
+        (the reference issues one pageable copy per array, trainer.py:288-293)."""
+        k = len(arrays)
+        n = max(len(a) for a in arrays)
+        if self._pinned is None or self._pinned.shape[0] < k or self._pinned.shape[1] < n:
+            self._pinned = torch.empty((k, n), dtype=torch.int64).pin_memory()
+        lens = []
+        for i, a in enumerate(arrays):
+            a = np.asarray(a, dtype=np.int64)
+            self._pinned[i, :len(a)] = torch.from_numpy(a)
+            lens.append(len(a))
+        dev = self._pinned[:k, :n].to(self.config.device, non_blocking=True)
+        return [dev[i, :lens[i]] for i in range(k)], k * n * 8
+
+    def train_batch(self, data):
+        """data: the list Generator yields — 6 id arrays (pairwise) or 4 (pointwise)."""
+        self.model.train()
+        ids, nbytes = self._to_device(list(data))
+        self.last_h2d_bytes = nbytes
+        strategy = self.model.training_strategy
+        if self._fused:
+            with torch.no_grad():
+                if strategy == TrainingStrategy.PAIRWISE_BASED:
+                    loss = self._fused_pairwise(ids)
+                elif strategy == TrainingStrategy.POINTWISE_BASED:
+                    loss = self._fused_pointwise(ids)
+                else:
+                    raise NotImplementedError("Unknown training strategy: %s" % strategy)
+            return float(loss.item())  # D2H sync, as acc_loss += loss.item() (trainer.py:300)
+        self.optimizer.zero_grad()
+        if strategy == TrainingStrategy.PAIRWISE_BASED:
+            loss = self.train_step_pairwise(*ids)
+        elif strategy == TrainingStrategy.POINTWISE_BASED:
+            loss = self.train_step_pointwise(*ids)
+        else:
+            raise NotImplementedError("Unknown training strategy: %s" % strategy)
+        loss.backward()
+        self.optimizer.step()
+        return float(loss.item())

@@ -1,0 +1,254 @@
+"""-m gpu tests of the training-side kernels: backward vs the fp64 autograd oracle
+(oracle/ref_port.py) and vs gradients produced by the reference itself (golden), losses,
+regularisers, the model classes through autograd, and the fused sparse training steps vs
+dense torch optimizers on the oracle formulas."""
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+import gpu_util as gpu
+
+pytestmark = pytest.mark.gpu
+CASES = [n for n in gu.case_names() if "pretrained" not in n]
+GRAD_TOL = 2e-4  # relative to the largest |gradient| of the table
+
+
+def _L():
+    from pykg2vec_b200 import _lib
+    return _lib
+
+
+def _cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _check_grads(got, want, tol=GRAD_TOL, what=""):
+    for k, (g, w) in enumerate(zip(got, want)):
+        if w is None:
+            continue
+        w = np.asarray(w, dtype=np.float64)
+        scale = max(np.abs(w).max(), 1e-12)
+        err = np.abs(g.astype(np.float64) - w).max() / scale
+        assert err < tol, "%s table %d: rel err %.3g" % (what, k, err)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_score_bwd_vs_reference_autograd(name):
+    L = _L()
+    g = gu.load(name)
+    desc = gpu.desc_from_golden(g)
+    grads = [torch.zeros_like(t) for t in desc.tables]
+    L.score_bwd(desc, _cuda(g["h"]), _cuda(g["r"]), _cuda(g["t"]), _cuda(g["upstream"]), grads)
+    want = [g["grad%d" % k] for k in range(len(grads))]
+    _check_grads([x.cpu().numpy() for x in grads], want, what=name)
+
+
+@pytest.mark.parametrize("spec", [
+    ("transe", 300, 7, 200, None, False, 0.0), ("transe", 300, 7, 50, None, True, 0.0),
+    ("transh", 300, 7, 100, None, True, 0.0), ("transd", 300, 7, 64, None, False, 0.0),
+    ("transr", 120, 5, 40, 24, False, 0.0), ("transm", 300, 7, 36, None, False, 0.0),
+    ("rotate", 300, 7, 100, None, False, 12.0), ("distmult", 300, 7, 200, None, False, 0.0),
+    ("cp", 300, 7, 30, None, False, 0.0), ("complex", 300, 7, 200, None, False, 0.0),
+], ids=lambda s: "%s-d%d" % (s[0], s[3]))
+def test_score_bwd_vs_fp64_oracle(spec):
+    """duplicates in the batch (few entities) exercise the atomic scatter."""
+    from oracle import ref_port
+    L = _L()
+    name, N, R, d, dr, l1, margin = spec
+    om, tabs = gpu.synthetic_case(name, N, R, d, seed=11, dr=dr, l1=l1, margin=margin, scale=0.3)
+    desc = gpu.desc_from_oracle_model(om)
+    rng = np.random.RandomState(1)
+    n = 777
+    h, r, t = rng.randint(N, size=n), rng.randint(R, size=n), rng.randint(N, size=n)
+    up = rng.standard_normal(n).astype(np.float32)
+    grads = [torch.zeros_like(x) for x in desc.tables]
+    L.score_bwd(desc, _cuda(h), _cuda(r), _cuda(t), _cuda(up), grads)
+    t64 = [torch.from_numpy(x.astype(np.float64)).requires_grad_(name != "transm" or i < 2)
+           for i, x in enumerate(tabs)]
+    s = ref_port.score(name, t64, torch.from_numpy(h), torch.from_numpy(r), torch.from_numpy(t),
+                       l1_flag=l1, margin=margin, embedding_range=((margin + 2.0) / d if name == "rotate" else None),
+                       rel_dim=dr)
+    (s * torch.from_numpy(up.astype(np.float64))).sum().backward()
+    want = [x.grad.numpy() if x.grad is not None else None for x in t64]
+    _check_grads([x.cpu().numpy() for x in grads], want, tol=5e-5, what=name)
+
+
+def test_losses_vs_golden_and_oracle():
+    import oracle
+    L = _L()
+    g = gu.load("losses")
+    loss, gp, gn = L.loss_pairwise_hinge(_cuda(g["pos"]), _cuda(g["neg"]), float(g["margin"]))
+    assert abs(loss.item() - g["hinge"]) <= 1e-5 * abs(g["hinge"])
+    np.testing.assert_array_equal(gp.cpu().numpy(), g["hinge_gpos"])
+    np.testing.assert_array_equal(gn.cpu().numpy(), g["hinge_gneg"])
+    loss, gg = L.loss_pointwise_logistic(_cuda(g["preds"]), _cuda(g["target"]))
+    assert abs(loss.item() - g["logistic"]) <= 1e-5 * abs(g["logistic"])
+    np.testing.assert_allclose(gg.cpu().numpy(), g["logistic_g"], rtol=1e-4, atol=1e-8)
+    for tag, alpha in (("a1", 1.0), ("a01", 0.1)):
+        loss, gp, gn = L.loss_selfadv(_cuda(g["sa_pos"]), _cuda(g["sa_neg"]), int(g["sa_neg_rate"]), alpha)
+        assert abs(loss.item() - g["sa_" + tag]) <= 2e-5 * abs(g["sa_" + tag])
+        np.testing.assert_allclose(gp.cpu().numpy(), g["sa_%s_gpos" % tag], rtol=1e-4, atol=1e-8)
+        np.testing.assert_allclose(gn.cpu().numpy(), g["sa_%s_gneg" % tag], rtol=1e-4, atol=1e-8)
+    # larger, seeded: vs the C oracle
+    rng = np.random.RandomState(3)
+    pos = (rng.standard_normal(5000) * 2).astype(np.float32)
+    neg = (rng.standard_normal(5000) * 2).astype(np.float32)
+    want, _ = oracle.loss_pairwise_hinge(pos, neg, 1.5)
+    got, _, _ = L.loss_pairwise_hinge(_cuda(pos), _cuda(neg), 1.5)
+    assert abs(got.item() - want) <= 1e-5 * abs(want)
+    neg2 = (rng.standard_normal(5000 * 16) * 3).astype(np.float32)
+    want = oracle.loss_selfadv(pos, neg2, 16, 0.5)
+    got, _, _ = L.loss_selfadv(_cuda(pos), _cuda(neg2), 16, 0.5)
+    assert abs(got.item() - want) <= 2e-5 * abs(want)
+
+
+@pytest.mark.parametrize("name", [n for n in CASES if n.split("_")[0] in ("distmult", "complex", "cp")])
+def test_regulariser_vs_golden_and_autograd(name):
+    from oracle import ref_port
+    L = _L()
+    g = gu.load(name)
+    desc = gpu.desc_from_golden(g)
+    h, r, t = _cuda(g["h"]), _cuda(g["r"]), _cuda(g["t"])
+    lm = float(g["kw_lmbda"])
+    for code, key in ((0, "reg_f2"), (1, "reg_n3"), (2, "reg_absn3")):
+        if key not in g:
+            continue
+        grads = [torch.zeros_like(x) for x in desc.tables]
+        out = L.reg_fwd_bwd(desc, code, lm, h, r, t, grad_scale=1.0, grad_tables=grads)
+        assert abs(out.item() - g[key]) <= 1e-4 * abs(g[key]) + 1e-9, (name, key)
+        t64 = [torch.from_numpy(x.astype(np.float64)).requires_grad_() for x in gu.tables_of(g)]
+        ref_port.reg(str(g["model"]), t64, torch.from_numpy(g["h"]), torch.from_numpy(g["r"]),
+                     torch.from_numpy(g["t"]), lm, code).backward()
+        _check_grads([x.cpu().numpy() for x in grads], [x.grad.numpy() for x in t64], tol=5e-5, what=name + key)
+
+
+def _make_model(g, device="cuda"):
+    """the pykg2vec_b200 model class for a golden case, loaded with the golden tables through
+    the reference's state_dict keys."""
+    import pykg2vec_b200
+    kw = {k[3:]: (g[k].item() if g[k].ndim == 0 else g[k]) for k in g if k.startswith("kw_")}
+    cls = pykg2vec_b200.import_model(str(g["model"]))
+    m = cls(tot_entity=int(g["N"]), tot_relation=int(g["R"]), **kw)
+    sd = {str(k) + ".weight": torch.from_numpy(g["table%d" % i]) for i, k in enumerate(g["table_keys"])}
+    m.load_state_dict(sd)
+    return m.to(device)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_model_classes_forward_backward_like_reference(name):
+    """Drop-in surface: state_dict keys load, forward() scores and .backward() dense grads
+    match what the reference classes produced."""
+    g = gu.load(name)
+    if str(g["model"]) == "transm":
+        pytest.skip("needs a knowledge graph")
+    m = _make_model(g)
+    h, r, t = _cuda(g["h"]), _cuda(g["r"]), _cuda(g["t"])
+    s = m(h, r, t)
+    ref = g["scores"]
+    floor = 1e-3 * np.abs(ref).max()
+    err = np.abs(s.detach().cpu().numpy().astype(np.float64) - ref) / np.maximum(np.abs(ref), floor)
+    assert err.max() < 1e-4
+    (s * _cuda(g["upstream"])).sum().backward()
+    got = [getattr(m, str(k)).weight.grad.cpu().numpy() for k in g["table_keys"]]
+    _check_grads(got, [g["grad%d" % i] for i in range(len(got))], what=name)
+    embs = m.embed(h, r, t)
+    assert all(e.shape[0] == h.numel() for e in embs)
+
+
+def test_fused_hinge_sgd_matches_dense_sgd():
+    """kge_train_pairwise_hinge_sgd == (oracle formulas + torch autograd + optim.SGD)."""
+    from oracle import ref_port
+    L = _L()
+    for name, d, l1 in (("transe", 200, False), ("transe", 50, True), ("transh", 48, False), ("transd", 40, True)):
+        N, R, B = 500, 9, 512
+        om, tabs = gpu.synthetic_case(name, N, R, d, seed=21, l1=l1, scale=0.4)
+        desc = gpu.desc_from_oracle_model(om)
+        scratch = [torch.zeros_like(x) for x in desc.tables]
+        ref = [torch.from_numpy(x.astype(np.float64)).requires_grad_() for x in tabs]
+        opt = torch.optim.SGD(ref, lr=0.05)
+        rng = np.random.RandomState(4)
+        for step in range(3):
+            ids = [rng.randint(N if k % 3 != 1 else R, size=B) for k in range(6)]
+            loss = L.train_pairwise_hinge_sgd(desc, scratch, *[_cuda(x) for x in ids], margin=0.7, lr=0.05)
+            opt.zero_grad()
+            tid = [torch.from_numpy(x) for x in ids]
+            pos = ref_port.score(name, ref, tid[0], tid[1], tid[2], l1_flag=l1)
+            neg = ref_port.score(name, ref, tid[3], tid[4], tid[5], l1_flag=l1)
+            want = ref_port.pairwise_hinge(pos, neg, 0.7)
+            want.backward()
+            opt.step()
+            assert abs(loss.item() - want.item()) <= 2e-4 * abs(want.item()), (name, step)
+            for a, b in zip(desc.tables, ref):
+                np.testing.assert_allclose(a.cpu().numpy(), b.detach().numpy(), rtol=0, atol=3e-5)
+            assert all(float(s.abs().max()) == 0.0 for s in scratch), "gradient scratch must be left zeroed"
+
+
+def _trainer_for(model_name, kg, **cfgkw):
+    import pykg2vec_b200
+    from pykg2vec_b200.synthetic import SyntheticConfig
+    from pykg2vec_b200.trainer import Trainer
+    cfg = SyntheticConfig(kg, **cfgkw)
+    torch.manual_seed(0)
+    model = pykg2vec_b200.import_model(model_name)(**cfg.__dict__)
+    tr = Trainer(model, cfg)
+    tr.build_model()
+    return tr
+
+
+@pytest.mark.parametrize("model_name,opt", [("transe", "sgd"), ("transe", "adagrad"), ("distmult", "sgd"),
+                                            ("complex", "adagrad"), ("rotate", "adagrad")])
+def test_trainer_fused_equals_autograd_mode(model_name, opt):
+    """Trainer.train_batch in fused mode follows the same weight trajectory as the autograd
+    mode (reference step order) with the dense torch optimizer."""
+    from pykg2vec_b200.synthetic import SyntheticKnowledgeGraph
+    kg = SyntheticKnowledgeGraph(400, 6, 2000, 50, 50, seed=1)
+    kw = dict(optimizer=opt, learning_rate=0.05, hidden_size=64, margin=1.0 if model_name != "rotate" else 6.0,
+              l1_flag=False, lmbda=0.01, neg_rate=4 if model_name == "rotate" else 1, alpha=0.5)
+    a = _trainer_for(model_name, kg, fused_step=True, **kw)
+    b = _trainer_for(model_name, kg, fused_step=False, **kw)
+    b.model.load_state_dict(a.model.state_dict())
+    assert a._fused and not b._fused
+    rng = np.random.RandomState(2)
+    B = 256
+    for step in range(3):
+        if a.model.training_strategy.name == "PAIRWISE_BASED":
+            nr = kw["neg_rate"]
+            data = [rng.randint(400, size=B), rng.randint(6, size=B), rng.randint(400, size=B),
+                    rng.randint(400, size=B * nr), rng.randint(6, size=B * nr), rng.randint(400, size=B * nr)]
+        else:
+            data = [rng.randint(400, size=B), rng.randint(6, size=B), rng.randint(400, size=B),
+                    np.where(np.arange(B) % 2 == 0, 1, -1)]
+        la, lb = a.train_batch(data), b.train_batch(data)
+        assert abs(la - lb) <= 1e-4 * max(abs(lb), 1e-6), (step, la, lb)
+        for (ka, va), (kb, vb) in zip(a.model.state_dict().items(), b.model.state_dict().items()):
+            np.testing.assert_allclose(va.cpu().numpy(), vb.cpu().numpy(), rtol=0, atol=2e-5, err_msg=ka)
+
+
+def test_evaluator_matches_oracle_and_reference_metrics():
+    """Evaluator.test (batched rank kernel) == oracle rank counts; settle() metrics follow."""
+    import oracle
+    from oracle import ref_port
+    from pykg2vec_b200.synthetic import SyntheticKnowledgeGraph
+    kg = SyntheticKnowledgeGraph(600, 5, 3000, 40, 30, seed=5)
+    tr = _trainer_for("complex", kg, hidden_size=32, lmbda=0.1)
+    ev = tr.evaluator
+    res = ev.full_test(epoch=0)
+    tabs = [w.detach().cpu().numpy() for w in tr.model.kge_tables()]
+    om = oracle.Model("complex", tabs, 32)
+    test = kg.arrays["test"]
+    from pykg2vec_b200.evaluator import build_filter_csr
+    hr_t, tr_h = kg.read_cache_data("hr_t"), kg.read_cache_data("tr_h")
+    ft = build_filter_csr([(int(h), int(r)) for h, r, t in test], hr_t)
+    fh = build_filter_csr([(int(t), int(r)) for h, r, t in test], tr_h)
+    want = oracle.rank_1vsall(om, test[:, 0], test[:, 1], test[:, 2], ft, fh)
+    mc = ev.metric_calculator
+    got = np.stack([mc.rank_tail, mc.f_rank_tail, mc.rank_head, mc.f_rank_head], axis=1)
+    np.testing.assert_array_equal(got, want)
+    ref = ref_port.settle(want)
+    assert res["mr"] == pytest.approx(ref["mr"]) and res["fmrr"] == pytest.approx(ref["fmrr"])
+    # infer-style single query API: descending score order, length topk (evaluator.py:249-260)
+    top = ev.test_tail_rank(int(test[0, 0]), int(test[0, 1]), topk=5)
+    assert top.shape == (5,)
+    full = oracle.sweep_scores(om, oracle.GROUP_TAIL, int(test[0, 0]), int(test[0, 1]), 0)
+    assert set(top.cpu().tolist()) == set(np.argsort(-full, kind="stable")[:5].tolist())

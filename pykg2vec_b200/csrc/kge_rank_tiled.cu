@@ -1,11 +1,588 @@
-// kge_rank_tiled.cu — shared-memory tiled 1-vs-all sweep (placeholder until implemented).
+// kge_rank_tiled.cu — shared-memory tiled 1-vs-all sweep (the dominant kernel of evaluation).
+//
+// For a block of QBLK queries and a run of candidate rows, every (query, candidate) score is
+// evaluated from on-chip operands and compared with the query's threshold (its target's
+// score); only per-query counts leave the SM.  The arithmetic per pair is exactly the
+// canonical order of DESIGN.md §3 — an 8-lane group owns a register tile of TQ x TC pairs,
+// lane l accumulates the chunks l, l+8, ... of the embedding axis, and the cross-lane
+// butterfly (4,2,1) is done as a reduce-scatter so that each lane finishes a different pair —
+// hence bit-identical to kge_score_fwd / the gather sweep / the CPU oracle.
+//
+// Data movement (B200): operands are staged in shared memory by bulk-async copies
+// (cp.async.bulk global->shared, completion on an mbarrier; UBLKCP in SASS), double
+// buffered.  Query vectors are prepared once per call (prep_query_kernel) into a compact
+// [Q][KQ][dp] buffer; candidates come straight from the model tables (or from a
+// normalised / padded scratch copy).  Two modes, chosen on the host from the shared-memory
+// budget: "full rows" (query block resident for the whole CTA, one bulk copy per candidate
+// tile) and "slabs" of DS elements of the embedding axis for wide models (d = 500, 1000).
+//
+// Bound: fp32 pipe (2-8 instructions per element pair), not HBM: a candidate row is read from
+// L2 once per query BLOCK instead of once per query.
+#include "kge_models.cuh"
 #include "kge_rank.cuh"
+
 namespace kge {
-bool tiled_supported(const kge_model_t*) { return false; }
-size_t tiled_workspace_bytes(const kge_model_t*, int64_t) { return 0; }
-int tiled_sweep(const kge_model_t*, const kge_model_t*, int, const int64_t*, const int64_t*,
-                const int64_t*, const float*, int64_t, int64_t, int32_t*, int, void*, cudaStream_t) {
-  set_error("tiled sweep not built");
-  return KGE_ENOTSUP;
+
+constexpr int kTThreads = 256;
+constexpr int kTGroups = kTThreads / 8;  // 32
+constexpr int kGQ = 16;                  // query sub-blocks per CTA
+constexpr int kGC = kTGroups / kGQ;      // 2 candidate group columns
+constexpr int kNT = 4;                   // register tiles (candidate sub-blocks) per group
+constexpr int kTC = 4;                   // candidates per register tile
+constexpr int kCBLK = kGC * kNT * kTC;   // 32 candidates per tile
+
+enum { OP_TRANS_T = 0, OP_TRANS_H = 1, OP_DOT1 = 2, OP_DOT2 = 3, OP_ROT_T = 4, OP_ROT_H = 5 };
+
+template <int OP> struct OpTraits { static constexpr int KQ = 1, KC = 1, TQ = 4; };
+template <> struct OpTraits<OP_DOT2> { static constexpr int KQ = 2, KC = 2, TQ = 4; };
+template <> struct OpTraits<OP_ROT_T> { static constexpr int KQ = 2, KC = 2, TQ = 4; };
+template <> struct OpTraits<OP_ROT_H> { static constexpr int KQ = 4, KC = 2, TQ = 2; };
+
+struct TiledParams {
+  const float* qvec;      // [Q][KQ][dp]
+  const float* cand[2];   // KC candidate arrays, row pitch cand_pitch floats
+  int64_t cand_pitch;
+  const float* thr;       // [Q]
+  const float* qscale;    // [Q] (TransM theta[r]) or nullptr
+  int64_t Q, nc;
+  int dp, DS, nslabs, full_rows;
+  int tiles_per_cta, ntiles;
+  int32_t* counts;
+  int col, l1;
+  float margin;
+};
+
+// ---- mbarrier / bulk-copy primitives ------------------------------------------------------
+KGE_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+KGE_DEV void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+KGE_DEV void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+KGE_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+KGE_DEV void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ---- per-element pair operations (canonical arithmetic) ---------------------------------------
+template <int OP, bool L1>
+KGE_DEV void pair_op(float& acc, const float4* q, const float4* c) {
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    if (OP == OP_TRANS_T || OP == OP_TRANS_H) {
+      const float x = (OP == OP_TRANS_T) ? fsub(f4_get(q[0], e), f4_get(c[0], e))
+                                         : fadd(f4_get(c[0], e), f4_get(q[0], e));
+      if (L1) acc = fadd(acc, fabsf(x)); else acc = ffma(x, x, acc);
+    } else if (OP == OP_DOT1) {
+      acc = ffma(f4_get(q[0], e), f4_get(c[0], e), acc);
+    } else if (OP == OP_DOT2) {
+      acc = ffma(f4_get(q[0], e), f4_get(c[0], e), acc);
+      acc = ffma(f4_get(q[1], e), f4_get(c[1], e), acc);
+    } else if (OP == OP_ROT_T) {
+      const float sr = fsub(f4_get(q[0], e), f4_get(c[0], e));
+      const float si = fsub(f4_get(q[1], e), f4_get(c[1], e));
+      acc = ffma(sr, sr, acc);
+      acc = ffma(si, si, acc);
+    } else {  // OP_ROT_H: q = (re, im, t_re, t_im), c = (h_re, h_im)
+      const float re = f4_get(q[0], e), im = f4_get(q[1], e);
+      const float u = fmul(f4_get(c[1], e), im);
+      const float sr0 = ffma(f4_get(c[0], e), re, -u);
+      const float v = fmul(f4_get(c[1], e), re);
+      const float si0 = ffma(f4_get(c[0], e), im, v);
+      const float sr = fsub(sr0, f4_get(q[2], e)), si = fsub(si0, f4_get(q[3], e));
+      acc = ffma(sr, sr, acc);
+      acc = ffma(si, si, acc);
+    }
+  }
+}
+
+template <int OP, bool L1>
+KGE_DEV float finalize(float sum, float qscale, float margin, bool has_scale) {
+  if (OP == OP_TRANS_T || OP == OP_TRANS_H) {
+    const float dist = L1 ? sum : __fsqrt_rn(sum);
+    return has_scale ? fmul(qscale, dist) : dist;
+  }
+  if (OP == OP_DOT1 || OP == OP_DOT2) return -sum;
+  return fsub(sum, margin);
+}
+
+// Butterfly 4,2,1 over the group's 8 lanes as a reduce-scatter: on return v[0 .. NV/8) hold
+// complete sums of the pairs  orig = b4*NV/2 + b2*NV/4 + b1*NV/8 + i  (b* = lane bits 2,1,0).
+template <int NV>
+KGE_DEV void reduce_scatter(float (&v)[NV], int lane) {
+  const unsigned m = group_mask();
+  {
+    const bool hi = lane & 4;
+#pragma unroll
+    for (int i = 0; i < NV / 2; ++i) {
+      const float send = hi ? v[i] : v[i + NV / 2];
+      const float keep = hi ? v[i + NV / 2] : v[i];
+      v[i] = fadd(keep, __shfl_xor_sync(m, send, 4));
+    }
+  }
+  {
+    const bool hi = lane & 2;
+#pragma unroll
+    for (int i = 0; i < NV / 4; ++i) {
+      const float send = hi ? v[i] : v[i + NV / 4];
+      const float keep = hi ? v[i + NV / 4] : v[i];
+      v[i] = fadd(keep, __shfl_xor_sync(m, send, 2));
+    }
+  }
+  {
+    const bool hi = lane & 1;
+#pragma unroll
+    for (int i = 0; i < NV / 8; ++i) {
+      const float send = hi ? v[i] : v[i + NV / 8];
+      const float keep = hi ? v[i + NV / 8] : v[i];
+      v[i] = fadd(keep, __shfl_xor_sync(m, send, 1));
+    }
+  }
+}
+
+template <int OP, bool L1>
+__global__ void __launch_bounds__(kTThreads)
+sweep_tiled_kernel(TiledParams P) {
+  constexpr int KQ = OpTraits<OP>::KQ, KC = OpTraits<OP>::KC, TQ = OpTraits<OP>::TQ;
+  constexpr int QBLK = kGQ * TQ;
+  constexpr int NV = TQ * kTC;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // layout: [2 mbarriers][thr QBLK][qs QBLK][cnt QBLK] | q stages | c stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  float* s_thr = reinterpret_cast<float*>(smem_raw + 16);
+  float* s_qs = s_thr + QBLK;
+  int* s_cnt = reinterpret_cast<int*>(s_qs + QBLK);
+  const int hdr = ((16 + 3 * QBLK * 4) + 127) / 128 * 128;
+  const int DS = P.DS;
+  const int qstages = P.nslabs > 1 ? 2 : 1;
+  float* qbuf = reinterpret_cast<float*>(smem_raw + hdr);                      // [qstages][QBLK][KQ][DS]
+  float* cbuf = qbuf + (size_t)qstages * QBLK * KQ * DS;                        // [2][KC][CBLK][DS]
+  const int tid = threadIdx.x, lane = tid & 7, grp = tid >> 3;
+  const int gq = grp / kGC, gc = grp % kGC;
+  const int64_t q0 = (int64_t)blockIdx.y * QBLK;
+  const int qrows = (int)min((int64_t)QBLK, P.Q - q0);
+  const int t0 = blockIdx.x * P.tiles_per_cta;
+  const int ntile_local = min(P.tiles_per_cta, P.ntiles - t0);
+  if (ntile_local <= 0) return;
+  const int T = ntile_local * P.nslabs;
+
+  if (tid < QBLK) {
+    const bool ok = tid < qrows;
+    s_thr[tid] = ok ? __ldg(P.thr + q0 + tid) : 0.f;
+    s_qs[tid] = (ok && P.qscale) ? __ldg(P.qscale + q0 + tid) : 1.f;
+    s_cnt[tid] = 0;
+  }
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  // producer: warp 0 issues the bulk copies of iteration `it` into stage it&1
+  auto issue = [&](int it) {
+    if (tid >= 32) return;
+    const int stage = it & 1;
+    const int tile = t0 + it / P.nslabs, slab = it % P.nslabs;
+    const int slab_len = min(DS, P.dp - slab * DS);
+    const int64_t cbase = (int64_t)tile * kCBLK;
+    const int crows = (int)min((int64_t)kCBLK, P.nc - cbase);
+    const bool load_q = (P.nslabs > 1) || (it == 0);
+    float* qdst = qbuf + (size_t)(P.nslabs > 1 ? stage : 0) * QBLK * KQ * DS;
+    float* cdst = cbuf + (size_t)stage * KC * kCBLK * DS;
+    uint32_t total;
+    if (P.full_rows) total = (uint32_t)(KC * crows * P.dp * 4) + (load_q ? (uint32_t)(qrows * KQ * P.dp * 4) : 0u);
+    else total = (uint32_t)((KC * crows + (load_q ? qrows * KQ : 0)) * slab_len * 4);
+    if (tid == 0) mbar_arrive_expect_tx(&bars[stage], total);
+    __syncwarp();
+    if (P.full_rows) {
+      if (tid < KC) bulk_g2s(cdst + (size_t)tid * kCBLK * DS, P.cand[tid] + cbase * P.cand_pitch,
+                             (uint32_t)(crows * P.dp * 4), &bars[stage]);
+      if (load_q && tid == KC) bulk_g2s(qdst, P.qvec + q0 * KQ * P.dp, (uint32_t)(qrows * KQ * P.dp * 4), &bars[stage]);
+    } else {
+      for (int i = tid; i < KC * crows; i += 32) {
+        const int k = i / crows, row = i % crows;
+        bulk_g2s(cdst + ((size_t)k * kCBLK + row) * DS, P.cand[k] + (cbase + row) * P.cand_pitch + (size_t)slab * DS,
+                 (uint32_t)(slab_len * 4), &bars[stage]);
+      }
+      if (load_q)
+        for (int i = tid; i < qrows * KQ; i += 32)
+          bulk_g2s(qdst + (size_t)i * DS, P.qvec + (q0 * KQ + i) * P.dp + (size_t)slab * DS,
+                   (uint32_t)(slab_len * 4), &bars[stage]);
+    }
+  };
+
+  // which pair(s) this lane finishes after the reduce-scatter, and its (fixed) query row
+  const int b4 = (lane >> 2) & 1, b2 = (lane >> 1) & 1, b1 = lane & 1;
+  const int orig0 = b4 * (NV / 2) + b2 * (NV / 4) + b1 * (NV / 8);
+  const int my_iq = orig0 / kTC;                 // same for all of the lane's results
+  const int qrow = gq * TQ + my_iq;
+  const bool qvalid = qrow < qrows;
+  const float th = s_thr[qrow], qsc = s_qs[qrow];
+  const bool has_scale = P.qscale != nullptr;
+  int cnt = 0;
+
+  float acc[kNT][NV];
+  issue(0);
+  for (int it = 0; it < T; ++it) {
+    const int stage = it & 1;
+    const int tile = t0 + it / P.nslabs, slab = it % P.nslabs;
+    if (it + 1 < T) issue(it + 1);
+    if (slab == 0) {
+#pragma unroll
+      for (int nt = 0; nt < kNT; ++nt)
+#pragma unroll
+        for (int i = 0; i < NV; ++i) acc[nt][i] = 0.f;
+    }
+    mbar_wait(&bars[stage], (uint32_t)((it >> 1) & 1));
+    const int slab_len = min(DS, P.dp - slab * DS);
+    const int nch = slab_len >> 2;
+    const float* qs = qbuf + (size_t)(P.nslabs > 1 ? stage : 0) * QBLK * KQ * DS + (size_t)(gq * TQ) * KQ * DS;
+    const float* cs = cbuf + (size_t)stage * KC * kCBLK * DS;
+    for (int c = lane; c < nch; c += 8) {
+      float4 q4[TQ][KQ];
+#pragma unroll
+      for (int i = 0; i < TQ; ++i)
+#pragma unroll
+        for (int k = 0; k < KQ; ++k)
+          q4[i][k] = *reinterpret_cast<const float4*>(qs + ((size_t)i * KQ + k) * DS + 4 * c);
+#pragma unroll
+      for (int nt = 0; nt < kNT; ++nt) {
+        float4 c4[kTC][KC];
+        const int crow0 = (gc + kGC * nt) * kTC;
+#pragma unroll
+        for (int j = 0; j < kTC; ++j)
+#pragma unroll
+          for (int k = 0; k < KC; ++k)
+            c4[j][k] = *reinterpret_cast<const float4*>(cs + ((size_t)k * kCBLK + crow0 + j) * DS + 4 * c);
+#pragma unroll
+        for (int i = 0; i < TQ; ++i)
+#pragma unroll
+          for (int j = 0; j < kTC; ++j) pair_op<OP, L1>(acc[nt][i * kTC + j], q4[i], c4[j]);
+      }
+    }
+    if (slab == P.nslabs - 1) {
+      const int64_t cbase = (int64_t)tile * kCBLK;
+#pragma unroll
+      for (int nt = 0; nt < kNT; ++nt) {
+        reduce_scatter<NV>(acc[nt], lane);
+#pragma unroll
+        for (int i = 0; i < NV / 8; ++i) {
+          const int jc = (orig0 + i) % kTC;
+          const int64_t cand = cbase + (gc + kGC * nt) * kTC + jc;
+          const float s = finalize<OP, L1>(acc[nt][i], qsc, P.margin, has_scale);
+          cnt += (qvalid && cand < P.nc && s < th) ? 1 : 0;
+        }
+      }
+    }
+    __syncthreads();  // everyone is done with stage `stage` before it is refilled at it+2
+  }
+  if (cnt) atomicAdd(&s_cnt[qrow], cnt);
+  __syncthreads();
+  if (tid < qrows && s_cnt[tid]) {
+    atomicAdd(P.counts + (q0 + tid) * 4 + P.col, s_cnt[tid]);
+    atomicAdd(P.counts + (q0 + tid) * 4 + P.col + 1, s_cnt[tid]);
+  }
+}
+
+// ---- preparation kernels -------------------------------------------------------------------------
+// query vectors [Q][KQ][dp] (zero padded) + qscale; one 8-lane group per query
+template <int MODEL, int VEC, int DIR>
+__global__ void __launch_bounds__(256)
+prep_query_kernel(ModelParams P, const int64_t* __restrict__ qh, const int64_t* __restrict__ qr,
+                  const int64_t* __restrict__ qt, int64_t Q, int dp, float* __restrict__ qvec,
+                  float* __restrict__ qscale) {
+  const int lane = threadIdx.x & 7;
+  const int64_t q = (int64_t)blockIdx.x * 32 + (threadIdx.x >> 3);
+  if (q >= Q) return;
+  const int d = P.d, nch = (d + 3) >> 2, nchp = dp >> 2;
+  TripleRows R;
+  resolve_rows<MODEL>(R, P, P.qtab, P.qtab, P.qtab, __ldg(qh + q), __ldg(qr + q), __ldg(qt + q));
+  constexpr int KQ = (MODEL == KGE_COMPLEX) ? 2 : (MODEL == KGE_ROTATE ? (DIR == 0 ? 2 : 4) : 1);
+  float* out = qvec + (size_t)q * KQ * dp;
+  auto st = [&](int k, int c, float4 v) { *reinterpret_cast<float4*>(out + (size_t)k * dp + 4 * c) = v; };
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (MODEL == KGE_TRANSE || MODEL == KGE_TRANSM) {
+    const float* a = (DIR == 0) ? R.h[0] : R.r[0];   // TAIL: h^ + r^ ; HEAD: r^ - t^
+    const float* b = (DIR == 0) ? R.r[0] : R.t[0];
+    float sa = 0.f, sb = 0.f;
+    for (int c = lane; c < nch; c += 8) {
+      const float4 x = ld_chunk<VEC>(a, c, d), y = ld_chunk<VEC>(b, c, d);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { sa = ffma(f4_get(x, e), f4_get(x, e), sa); sb = ffma(f4_get(y, e), f4_get(y, e), sb); }
+    }
+    const float ia = inv_norm_from_sumsq(group_sum(sa)), ib = inv_norm_from_sumsq(group_sum(sb));
+    for (int c = lane; c < nchp; c += 8) {
+      float4 o = zero;
+      if (c < nch) {
+        const float4 x = ld_chunk<VEC>(a, c, d), y = ld_chunk<VEC>(b, c, d);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float xn = fmul(f4_get(x, e), ia), yn = fmul(f4_get(y, e), ib);
+          f4_at(o, e) = (DIR == 0) ? fadd(xn, yn) : fsub(xn, yn);
+        }
+      }
+      st(0, c, o);
+    }
+    if (MODEL == KGE_TRANSM && lane == 0) qscale[q] = __ldg(R.r[1]);
+  } else if (MODEL == KGE_DISTMULT || MODEL == KGE_CP) {
+    const float* a = (DIR == 0) ? R.h[0] : R.r[0];   // TAIL: h*r ; HEAD: r*t
+    const float* b = (DIR == 0) ? R.r[0] : R.t[0];
+    for (int c = lane; c < nchp; c += 8) {
+      float4 o = zero;
+      if (c < nch) {
+        const float4 x = ld_chunk<VEC>(a, c, d), y = ld_chunk<VEC>(b, c, d);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) f4_at(o, e) = fmul(f4_get(x, e), f4_get(y, e));
+      }
+      st(0, c, o);
+    }
+  } else if (MODEL == KGE_COMPLEX) {
+    const float* er = (DIR == 0) ? R.h[0] : R.t[0];
+    const float* ei = (DIR == 0) ? R.h[1] : R.t[1];
+    for (int c = lane; c < nchp; c += 8) {
+      float4 o0 = zero, o1 = zero;
+      if (c < nch) {
+        const float4 xr = ld_chunk<VEC>(er, c, d), xi = ld_chunk<VEC>(ei, c, d),
+                     rr = ld_chunk<VEC>(R.r[0], c, d), ri = ld_chunk<VEC>(R.r[1], c, d);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (DIR == 0) {
+            f4_at(o0, e) = ffma(f4_get(xr, e), f4_get(rr, e), -fmul(f4_get(xi, e), f4_get(ri, e)));
+            f4_at(o1, e) = ffma(f4_get(xi, e), f4_get(rr, e), fmul(f4_get(xr, e), f4_get(ri, e)));
+          } else {
+            f4_at(o0, e) = ffma(f4_get(xr, e), f4_get(rr, e), fmul(f4_get(xi, e), f4_get(ri, e)));
+            f4_at(o1, e) = ffma(f4_get(xi, e), f4_get(rr, e), -fmul(f4_get(xr, e), f4_get(ri, e)));
+          }
+        }
+      }
+      st(0, c, o0); st(1, c, o1);
+    }
+  } else if (MODEL == KGE_ROTATE) {
+    for (int c = lane; c < nchp; c += 8) {
+      float4 o0 = zero, o1 = zero, o2 = zero, o3 = zero;
+      if (c < nch) {
+        const float4 rr = ld_chunk<VEC>(R.r[0], c, d);
+        float4 re, im;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sincos_canon(fmul(f4_get(rr, e), P.phase), f4_at(im, e), f4_at(re, e));
+        if (DIR == 0) {
+          const float4 hr = ld_chunk<VEC>(R.h[0], c, d), hi = ld_chunk<VEC>(R.h[1], c, d);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float u = fmul(f4_get(hi, e), f4_get(im, e));
+            f4_at(o0, e) = ffma(f4_get(hr, e), f4_get(re, e), -u);
+            const float v = fmul(f4_get(hi, e), f4_get(re, e));
+            f4_at(o1, e) = ffma(f4_get(hr, e), f4_get(im, e), v);
+          }
+        } else {
+          o0 = re; o1 = im; o2 = ld_chunk<VEC>(R.t[0], c, d); o3 = ld_chunk<VEC>(R.t[1], c, d);
+        }
+      }
+      st(0, c, o0); st(1, c, o1);
+      if (DIR == 1) { st(2, c, o2); st(3, c, o3); }
+    }
+  }
+}
+
+// candidate scratch: row e -> (normalised | copied) and zero padded to dp
+template <int VEC, bool NORMALISE>
+__global__ void __launch_bounds__(256)
+prep_cand_kernel(const float* __restrict__ table, int64_t nc, int d, int dp, float* __restrict__ out) {
+  const int lane = threadIdx.x & 7;
+  const int64_t e = (int64_t)blockIdx.x * 32 + (threadIdx.x >> 3);
+  if (e >= nc) return;
+  const float* row = table + (size_t)e * d;
+  const int nch = (d + 3) >> 2, nchp = dp >> 2;
+  float inv = 1.f;
+  if (NORMALISE) {
+    float s = 0.f;
+    for (int c = lane; c < nch; c += 8) {
+      const float4 x = ld_chunk<VEC>(row, c, d);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s = ffma(f4_get(x, k), f4_get(x, k), s);
+    }
+    inv = inv_norm_from_sumsq(group_sum(s));
+  }
+  for (int c = lane; c < nchp; c += 8) {
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < nch) {
+      o = ld_chunk<VEC>(row, c, d);
+      if (NORMALISE) { o.x = fmul(o.x, inv); o.y = fmul(o.y, inv); o.z = fmul(o.z, inv); o.w = fmul(o.w, inv); }
+    }
+    *reinterpret_cast<float4*>(out + (size_t)e * dp + 4 * c) = o;
+  }
+}
+
+int model_vec(const kge_model_t* m);
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static int dp_of(const kge_model_t* m) { return ((m->dim + 3) / 4) * 4; }
+static int max_kq(int model) { return model == KGE_ROTATE ? 4 : (model == KGE_COMPLEX ? 2 : 1); }
+static int num_cand_tables(int model) { return (model == KGE_ROTATE || model == KGE_COMPLEX) ? 2 : 1; }
+static bool cand_needs_scratch(const kge_model_t* m) {
+  if (m->model == KGE_TRANSE || m->model == KGE_TRANSM) return true;  // normalised copy
+  if (m->dim % 4 != 0) return true;
+  const int slots[3] = {0, 1, 2};
+  for (int k = 0; k < 3; ++k)
+    if (m->tables[slots[k]] && ((uintptr_t)m->tables[slots[k]] & 15)) return true;
+  return false;
+}
+
+bool tiled_supported(const kge_model_t* m) {
+  switch (m->model) {
+    case KGE_TRANSE: case KGE_TRANSM: case KGE_DISTMULT: case KGE_CP: case KGE_COMPLEX: case KGE_ROTATE:
+      return true;
+    default: return false;
+  }
+}
+
+size_t tiled_workspace_bytes(const kge_model_t* m, int64_t Q) {
+  if (!tiled_supported(m)) return 0;
+  const size_t dp = (size_t)dp_of(m);
+  size_t bytes = align_up((size_t)Q * max_kq(m->model) * dp * sizeof(float), 256);  // qvec
+  bytes += align_up((size_t)Q * sizeof(float), 256);                                  // qscale
+  // candidate scratch (always reserved: alignment of the tables is only known at call time);
+  // CP sweeps the object table for tails and the subject table for heads -> one table at a time
+  bytes += align_up((size_t)num_cand_tables(m->model) * (size_t)m->num_ent * dp * sizeof(float), 256);
+  return bytes;
+}
+
+template <int OP, bool L1>
+static int launch_sweep(const TiledParams& P, int QBLK, size_t smem, cudaStream_t st, int splits, int qblocks) {
+  KGE_CUDA_OK(cudaFuncSetAttribute(sweep_tiled_kernel<OP, L1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  sweep_tiled_kernel<OP, L1><<<dim3((unsigned)splits, (unsigned)qblocks), kTThreads, smem, st>>>(P);
+  KGE_CHECK_LAUNCH("sweep_tiled_kernel");
+  (void)QBLK;
+  return KGE_OK;
+}
+
+int tiled_sweep(const kge_model_t* m, const kge_model_t* mq, int dir, const int64_t* qh,
+                const int64_t* qr, const int64_t* qt, const float* thr, int64_t Q, int64_t nc,
+                int32_t* counts, int col, void* ws, cudaStream_t st) {
+  const int model = m->model;
+  const int d = m->dim, dp = dp_of(m);
+  const int op = (model == KGE_TRANSE || model == KGE_TRANSM) ? (dir == 0 ? OP_TRANS_T : OP_TRANS_H)
+               : (model == KGE_DISTMULT || model == KGE_CP) ? OP_DOT1
+               : (model == KGE_COMPLEX) ? OP_DOT2 : (dir == 0 ? OP_ROT_T : OP_ROT_H);
+  const int KQ = (op == OP_DOT2 || op == OP_ROT_T) ? 2 : (op == OP_ROT_H ? 4 : 1);
+  const int KC = num_cand_tables(model);
+  const int TQ = (op == OP_ROT_H) ? 2 : 4;
+  const int QBLK = kGQ * TQ;
+  // workspace carve-up
+  char* w = reinterpret_cast<char*>(ws);
+  float* qvec = reinterpret_cast<float*>(w);
+  w += align_up((size_t)Q * max_kq(model) * dp * sizeof(float), 256);
+  float* qscale = reinterpret_cast<float*>(w);
+  w += align_up((size_t)Q * sizeof(float), 256);
+  float* cscratch = reinterpret_cast<float*>(w);
+
+  // 1. query vectors (query-side tables)
+  const ModelParams PQ = make_params(mq, mq);
+  const int vq = model_vec(mq);
+  const unsigned qgrid = (unsigned)((Q + 31) / 32);
+#define PREP(M, V)                                                                                   \
+  do {                                                                                               \
+    if (dir == 0) prep_query_kernel<M, V, 0><<<qgrid, 256, 0, st>>>(PQ, qh, qr, qt, Q, dp, qvec, qscale); \
+    else prep_query_kernel<M, V, 1><<<qgrid, 256, 0, st>>>(PQ, qh, qr, qt, Q, dp, qvec, qscale);     \
+  } while (0)
+  switch (model) {
+    case KGE_TRANSE: KGE_DISPATCH_VEC(KGE_TRANSE, vq, PREP); break;
+    case KGE_TRANSM: KGE_DISPATCH_VEC(KGE_TRANSM, vq, PREP); break;
+    case KGE_DISTMULT: KGE_DISPATCH_VEC(KGE_DISTMULT, vq, PREP); break;
+    case KGE_CP: KGE_DISPATCH_VEC(KGE_CP, vq, PREP); break;
+    case KGE_COMPLEX: KGE_DISPATCH_VEC(KGE_COMPLEX, vq, PREP); break;
+    default: KGE_DISPATCH_VEC(KGE_ROTATE, vq, PREP); break;
+  }
+#undef PREP
+  KGE_CHECK_LAUNCH("prep_query_kernel");
+
+  // 2. candidate arrays
+  TiledParams P;
+  const float* src[2] = {nullptr, nullptr};
+  if (model == KGE_CP) src[0] = m->tables[dir == 0 ? 2 : 0];
+  else { src[0] = m->tables[0]; if (KC == 2) src[1] = m->tables[1]; }
+  const bool normalise = (model == KGE_TRANSE || model == KGE_TRANSM);
+  bool scratch = normalise || (d % 4 != 0);
+  for (int k = 0; k < KC; ++k) if ((uintptr_t)src[k] & 15) scratch = true;
+  if (scratch) {
+    int vc = (d % 4 == 0) ? 4 : (d % 2 == 0 ? 2 : 1);
+    for (int k = 0; k < KC; ++k) {
+      const uintptr_t a = (uintptr_t)src[k];
+      if (vc == 4 && (a & 15)) vc = 2;
+      if (vc == 2 && (a & 7)) vc = 1;
+    }
+    const unsigned cgrid = (unsigned)((nc + 31) / 32);
+    for (int k = 0; k < KC; ++k) {
+      float* dst = cscratch + (size_t)k * (size_t)nc * dp;
+      // head and tail sweeps of one call share the normalised copy (same table): recompute is cheap
+      if (normalise) {
+        if (vc == 4) prep_cand_kernel<4, true><<<cgrid, 256, 0, st>>>(src[k], nc, d, dp, dst);
+        else if (vc == 2) prep_cand_kernel<2, true><<<cgrid, 256, 0, st>>>(src[k], nc, d, dp, dst);
+        else prep_cand_kernel<1, true><<<cgrid, 256, 0, st>>>(src[k], nc, d, dp, dst);
+      } else {
+        if (vc == 4) prep_cand_kernel<4, false><<<cgrid, 256, 0, st>>>(src[k], nc, d, dp, dst);
+        else if (vc == 2) prep_cand_kernel<2, false><<<cgrid, 256, 0, st>>>(src[k], nc, d, dp, dst);
+        else prep_cand_kernel<1, false><<<cgrid, 256, 0, st>>>(src[k], nc, d, dp, dst);
+      }
+      KGE_CHECK_LAUNCH("prep_cand_kernel");
+      P.cand[k] = dst;
+    }
+    if (KC == 1) P.cand[1] = nullptr;
+    P.cand_pitch = dp;
+  } else {
+    P.cand[0] = src[0]; P.cand[1] = src[1]; P.cand_pitch = d;
+  }
+
+  // 3. shared-memory plan: full rows when they fit in ~110 KB (2 CTAs/SM), else slabs of DS elements
+  const size_t budget = 110 * 1024;
+  const size_t hdr = align_up(16 + 3 * (size_t)QBLK * 4, 128);
+  auto bytes_for = [&](int DS, int qstages) {
+    return hdr + ((size_t)QBLK * KQ * qstages + (size_t)kCBLK * KC * 2) * (size_t)DS * sizeof(float);
+  };
+  int DS, nslabs, full;
+  if (bytes_for(dp, 1) <= budget) { DS = dp; nslabs = 1; full = 1; }
+  else {
+    DS = 32;
+    while (DS + 32 <= dp && bytes_for(DS + 32, 2) <= budget) DS += 32;
+    nslabs = (dp + DS - 1) / DS; full = 0;
+    if (nslabs == 1) { full = 1; DS = dp; }
+  }
+  const size_t smem = bytes_for(DS, nslabs > 1 ? 2 : 1);
+  P.qvec = qvec; P.thr = thr; P.qscale = (model == KGE_TRANSM) ? qscale : nullptr;
+  P.Q = Q; P.nc = nc; P.dp = dp; P.DS = DS; P.nslabs = nslabs; P.full_rows = full;
+  P.ntiles = (int)((nc + kCBLK - 1) / kCBLK);
+  const int qblocks = (int)((Q + QBLK - 1) / QBLK);
+  const int ctas_per_sm = smem * 2 + 2048 <= 227 * 1024 ? 2 : 1;
+  int splits = (sm_count() * ctas_per_sm + qblocks - 1) / qblocks;
+  if (splits < 1) splits = 1;
+  if (splits > P.ntiles) splits = P.ntiles;
+  P.tiles_per_cta = (P.ntiles + splits - 1) / splits;
+  splits = (P.ntiles + P.tiles_per_cta - 1) / P.tiles_per_cta;
+  P.counts = counts; P.col = col; P.l1 = m->l1_flag; P.margin = m->margin;
+
+  switch (op) {
+    case OP_TRANS_T: return m->l1_flag ? launch_sweep<OP_TRANS_T, true>(P, QBLK, smem, st, splits, qblocks)
+                                       : launch_sweep<OP_TRANS_T, false>(P, QBLK, smem, st, splits, qblocks);
+    case OP_TRANS_H: return m->l1_flag ? launch_sweep<OP_TRANS_H, true>(P, QBLK, smem, st, splits, qblocks)
+                                       : launch_sweep<OP_TRANS_H, false>(P, QBLK, smem, st, splits, qblocks);
+    case OP_DOT1: return launch_sweep<OP_DOT1, false>(P, QBLK, smem, st, splits, qblocks);
+    case OP_DOT2: return launch_sweep<OP_DOT2, false>(P, QBLK, smem, st, splits, qblocks);
+    case OP_ROT_T: return launch_sweep<OP_ROT_T, false>(P, QBLK, smem, st, splits, qblocks);
+    default: return launch_sweep<OP_ROT_H, false>(P, QBLK, smem, st, splits, qblocks);
+  }
+}
+
 }  // namespace kge

@@ -220,14 +220,26 @@ def run_cuda(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for i in range(args.warmup):
         resident_step(i)
         if not args.lite:
             e2e_step(i)
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    # sustained run (~1.5 s of back-to-back steps) so that nvidia-smi samples clocks UNDER LOAD
+    t_end = time.perf_counter() + (0.3 if args.lite else 1.5)
+    sustained_steps = 0
+    torch.cuda.synchronize()
+    t_s0 = time.perf_counter()
+    while time.perf_counter() < t_end:
+        for i in range(args.warmup, total):
+            resident_step(i)
+        torch.cuda.synchronize()
+        sustained_steps += args.steps
+    ms_sustained = (time.perf_counter() - t_s0) * 1e3 / max(sustained_steps, 1)
+    barrier()
     launches0 = _lib.launch_count()
     ms_res = max_over_ranks(timed(resident_step, args.warmup, args.steps, True))
     launches = _lib.launch_count() - launches0
@@ -282,6 +294,7 @@ def run_cuda(args):
                          "otherwise stay L2-resident",
                    "parallelism": "dp%d: batch ids all-gathered, replicated update; test triples sharded" % world},
         "ms_per_step_warm_l2": ms_warm / args.steps,
+        "ms_per_step_sustained": ms_sustained,
         "e2e": {"value": scored_per_step * args.steps / (ms_e2e * 1e-3), "unit": "triples/s",
                 "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(6 * w["B"] * 8 + 3 * w["Q"] * 8 +
@@ -304,6 +317,19 @@ def run_cuda(args):
 
 
 # ------------------------------------------------------------------ CPU reference arm ----
+def usable_cores():
+    """cores this process may actually use: affinity mask capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return n
+
+
 class CpuArm:
     """The torch port of the reference's CPU path (oracle/ref_port.py: the same ATen op chain,
     dense autograd + dense optim.SGD, forward over N + topk(N) + Python rank walk) on the host
@@ -314,7 +340,7 @@ class CpuArm:
         from oracle import ref_port
         w = WORKLOAD
         self.torch, self.rp = torch, ref_port
-        self.cores = os.cpu_count() or 1
+        self.cores = usable_cores()
         torch.set_num_threads(self.cores)
         self.kg = make_graph()
         gen = torch.Generator().manual_seed(2)
@@ -352,9 +378,31 @@ class CpuArm:
             return (time.perf_counter() - t0) / n
 
 
+def tune_threads(arm):
+    """Give the CPU arm its best shot: intra-op thread counts up to the usable cores are
+    probed on one train step + one test triple and the fastest is kept (torch CPU kernels
+    on small tensors often run faster on fewer threads than cores)."""
+    w = WORKLOAD
+    cands = sorted({c for c in (arm.cores, 64, 32, 16, 8, 4) if c <= arm.cores}, reverse=True)
+    best, best_t = cands[0], float("inf")
+    for c in cands:
+        arm.torch.set_num_threads(c)
+        arm.train_steps(1)
+        t0 = time.perf_counter()
+        t = arm.train_steps(1) + w["Q"] * arm.eval_queries(1)
+        if t < best_t:
+            best, best_t = c, t
+        if time.perf_counter() - t0 > 20:
+            break
+    arm.torch.set_num_threads(best)
+    arm.cores = best
+    return best
+
+
 def cpu_measure(n_train, n_queries, arm=None):
     """(seconds per train step, seconds per test triple, cores) after a short warm-up."""
     arm = arm or CpuArm()
+    tune_threads(arm)
     arm.train_steps(2)
     arm.eval_queries(1)
     return arm.train_steps(n_train), arm.eval_queries(n_queries), arm.cores
@@ -385,7 +433,7 @@ def run_reference(args):
     per_step_queries = 2
     tt, tq = [], []
     arm = CpuArm()
-    cores = arm.cores
+    cores = tune_threads(arm)
     for s in range(args.warmup + args.steps):
         a, b = arm.train_steps(1), arm.eval_queries(per_step_queries)
         if s >= args.warmup:

@@ -72,8 +72,12 @@ filter_correct_kernel(ModelParams P, const int64_t* __restrict__ qh, const int64
   float* scratch = reinterpret_cast<float*>(smem_f4) + (size_t)(threadIdx.x >> 3) * scratch_floats;
   const int lane = threadIdx.x & 7;
   const int64_t k = (int64_t)blockIdx.x * kGroupsPerCta + (threadIdx.x >> 3);
-  const bool valid = k < nnz;
-  const int64_t kk = valid ? k : nnz - 1;
+  // the true entry count lives in device memory (ptr[Q]); the host may pass a capacity
+  // (upper bound) as nnz so that the launch shape can stay fixed inside a CUDA graph
+  const int64_t nnz_true = min(nnz, __ldg(ptr + Q));
+  if (nnz_true <= 0) return;
+  const bool valid = k < nnz_true;
+  const int64_t kk = valid ? k : nnz_true - 1;
   int64_t lo = 0, hi = Q;  // largest q with ptr[q] <= kk
   while (hi - lo > 1) {
     const int64_t mid = (lo + hi) >> 1;
@@ -163,6 +167,10 @@ extern "C" int kge_rank_1vsall(const kge_model_t* m, const kge_model_t* mq, int6
   const unsigned qgrid = (unsigned)((Q + kGroupsPerCta - 1) / kGroupsPerCta);
   const dim3 sgrid((unsigned)((nc + kCandsPerCta - 1) / kCandsPerCta), (unsigned)Q);
   const bool use_tiled = !(flags & KGE_RANK_FORCE_GATHER) && tiled_supported(m);
+  if (use_tiled) {
+    rc = tiled_prepare_candidates(m, nc, tiled_ws, Q, st);
+    if (rc) return rc;
+  }
 
   for (int dir = 0; dir < 2; ++dir) {
     if (dir == 0 && (flags & KGE_RANK_HEAD_ONLY)) continue;
@@ -183,9 +191,11 @@ extern "C" int kge_rank_1vsall(const kge_model_t* m, const kge_model_t* mq, int6
     else { SET_SMEM((threshold_kernel<M, V, KGE_GROUP_HEAD>));                                 \
       threshold_kernel<M, V, KGE_GROUP_HEAD><<<qgrid, kThreads, smem, st>>>(P, qh, qr, qt, Q, thr, sf); } \
   } while (0)
-    KGE_DISPATCH_MODEL_VEC(m->model, vec, CALL_THR);
+    if (!use_tiled) {  // the tiled path computes the thresholds inside its query-prep kernel
+      KGE_DISPATCH_MODEL_VEC(m->model, vec, CALL_THR);
+      KGE_CHECK_LAUNCH("threshold_kernel");
+    }
 #undef CALL_THR
-    KGE_CHECK_LAUNCH("threshold_kernel");
 
     if (use_tiled) {
       rc = tiled_sweep(m, mq, dir, qh, qr, qt, thr, Q, nc, counts, col, tiled_ws, st);

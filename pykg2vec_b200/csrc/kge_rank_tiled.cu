@@ -303,13 +303,17 @@ template <int MODEL, int VEC, int DIR>
 __global__ void __launch_bounds__(256)
 prep_query_kernel(ModelParams P, const int64_t* __restrict__ qh, const int64_t* __restrict__ qr,
                   const int64_t* __restrict__ qt, int64_t Q, int dp, float* __restrict__ qvec,
-                  float* __restrict__ qscale) {
+                  float* __restrict__ qscale, float* __restrict__ thr) {
   const int lane = threadIdx.x & 7;
   const int64_t q = (int64_t)blockIdx.x * 32 + (threadIdx.x >> 3);
   if (q >= Q) return;
   const int d = P.d, nch = (d + 3) >> 2, nchp = dp >> 2;
   TripleRows R;
   resolve_rows<MODEL>(R, P, P.qtab, P.qtab, P.qtab, __ldg(qh + q), __ldg(qr + q), __ldg(qt + q));
+  {  // threshold = the target's own score in this direction's grouping (== kge_score_fwd)
+    const float s = score_group<MODEL, VEC, DIR == 0 ? KGE_GROUP_TAIL : KGE_GROUP_HEAD>(R, P, lane, nullptr);
+    if (lane == 0) thr[q] = s;
+  }
   constexpr int KQ = (MODEL == KGE_COMPLEX) ? 2 : (MODEL == KGE_ROTATE ? (DIR == 0 ? 2 : 4) : 1);
   float* out = qvec + (size_t)q * KQ * dp;
   auto st = [&](int k, int c, float4 v) { *reinterpret_cast<float4*>(out + (size_t)k * dp + 4 * c) = v; };
@@ -441,6 +445,59 @@ static bool cand_needs_scratch(const kge_model_t* m) {
   return false;
 }
 
+// candidate source tables of a sweep direction; returns true when a scratch copy is needed
+// (normalised rows for TransE/TransM, padding for d % 4 != 0, unaligned tables)
+static bool cand_sources(const kge_model_t* m, int dir, const float* src[2]) {
+  const int KC = num_cand_tables(m->model);
+  src[0] = src[1] = nullptr;
+  if (m->model == KGE_CP) src[0] = m->tables[dir == 0 ? 2 : 0];
+  else { src[0] = m->tables[0]; if (KC == 2) src[1] = m->tables[1]; }
+  bool scratch = (m->model == KGE_TRANSE || m->model == KGE_TRANSM) || (m->dim % 4 != 0);
+  for (int k = 0; k < KC; ++k) if ((uintptr_t)src[k] & 15) scratch = true;
+  return scratch;
+}
+
+static int fill_cand_scratch(const kge_model_t* m, const float* const src[2], int KC, int64_t nc,
+                             float* cscratch, cudaStream_t st) {
+  const int d = m->dim, dp = dp_of(m);
+  const bool normalise = (m->model == KGE_TRANSE || m->model == KGE_TRANSM);
+  int vc = (d % 4 == 0) ? 4 : (d % 2 == 0 ? 2 : 1);
+  for (int k = 0; k < KC; ++k) {
+    const uintptr_t a = (uintptr_t)src[k];
+    if (vc == 4 && (a & 15)) vc = 2;
+    if (vc == 2 && (a & 7)) vc = 1;
+  }
+  const unsigned cgrid = (unsigned)((nc + 31) / 32);
+  for (int k = 0; k < KC; ++k) {
+    float* dst = cscratch + (size_t)k * (size_t)nc * dp;
+    if (normalise) {
+      if (vc == 4) prep_cand_kernel<4, true><<<cgrid, 256, 0, st>>>(src[k], nc, d, dp, dst);
+      else if (vc == 2) prep_cand_kernel<2, true><<<cgrid, 256, 0, st>>>(src[k], nc, d, dp, dst);
+      else prep_cand_kernel<1, true><<<cgrid, 256, 0, st>>>(src[k], nc, d, dp, dst);
+    } else {
+      if (vc == 4) prep_cand_kernel<4, false><<<cgrid, 256, 0, st>>>(src[k], nc, d, dp, dst);
+      else if (vc == 2) prep_cand_kernel<2, false><<<cgrid, 256, 0, st>>>(src[k], nc, d, dp, dst);
+      else prep_cand_kernel<1, false><<<cgrid, 256, 0, st>>>(src[k], nc, d, dp, dst);
+    }
+    KGE_CHECK_LAUNCH("prep_cand_kernel");
+  }
+  return KGE_OK;
+}
+
+static float* cand_scratch_ptr(const kge_model_t* m, void* ws, int64_t Q) {
+  char* w = reinterpret_cast<char*>(ws);
+  w += align_up((size_t)Q * max_kq(m->model) * dp_of(m) * sizeof(float), 256);
+  w += align_up((size_t)Q * sizeof(float), 256);
+  return reinterpret_cast<float*>(w);
+}
+
+int tiled_prepare_candidates(const kge_model_t* m, int64_t nc, void* ws, int64_t Q, cudaStream_t st) {
+  if (m->model == KGE_CP) return KGE_OK;  // per direction, see tiled_sweep
+  const float* src[2];
+  if (!cand_sources(m, 0, src)) return KGE_OK;
+  return fill_cand_scratch(m, src, num_cand_tables(m->model), nc, cand_scratch_ptr(m, ws, Q), st);
+}
+
 bool tiled_supported(const kge_model_t* m) {
   switch (m->model) {
     case KGE_TRANSE: case KGE_TRANSM: case KGE_DISTMULT: case KGE_CP: case KGE_COMPLEX: case KGE_ROTATE:
@@ -470,7 +527,7 @@ static int launch_sweep(const TiledParams& P, int QBLK, size_t smem, cudaStream_
 }
 
 int tiled_sweep(const kge_model_t* m, const kge_model_t* mq, int dir, const int64_t* qh,
-                const int64_t* qr, const int64_t* qt, const float* thr, int64_t Q, int64_t nc,
+                const int64_t* qr, const int64_t* qt, float* thr, int64_t Q, int64_t nc,
                 int32_t* counts, int col, void* ws, cudaStream_t st) {
   const int model = m->model;
   const int d = m->dim, dp = dp_of(m);
@@ -495,8 +552,8 @@ int tiled_sweep(const kge_model_t* m, const kge_model_t* mq, int dir, const int6
   const unsigned qgrid = (unsigned)((Q + 31) / 32);
 #define PREP(M, V)                                                                                   \
   do {                                                                                               \
-    if (dir == 0) prep_query_kernel<M, V, 0><<<qgrid, 256, 0, st>>>(PQ, qh, qr, qt, Q, dp, qvec, qscale); \
-    else prep_query_kernel<M, V, 1><<<qgrid, 256, 0, st>>>(PQ, qh, qr, qt, Q, dp, qvec, qscale);     \
+    if (dir == 0) prep_query_kernel<M, V, 0><<<qgrid, 256, 0, st>>>(PQ, qh, qr, qt, Q, dp, qvec, qscale, thr); \
+    else prep_query_kernel<M, V, 1><<<qgrid, 256, 0, st>>>(PQ, qh, qr, qt, Q, dp, qvec, qscale, thr); \
   } while (0)
   switch (model) {
     case KGE_TRANSE: KGE_DISPATCH_VEC(KGE_TRANSE, vq, PREP); break;
@@ -509,41 +566,22 @@ int tiled_sweep(const kge_model_t* m, const kge_model_t* mq, int dir, const int6
 #undef PREP
   KGE_CHECK_LAUNCH("prep_query_kernel");
 
-  // 2. candidate arrays
+  // 2. candidate arrays (scratch copies were produced by tiled_prepare_candidates)
   TiledParams P;
-  const float* src[2] = {nullptr, nullptr};
-  if (model == KGE_CP) src[0] = m->tables[dir == 0 ? 2 : 0];
-  else { src[0] = m->tables[0]; if (KC == 2) src[1] = m->tables[1]; }
-  const bool normalise = (model == KGE_TRANSE || model == KGE_TRANSM);
-  bool scratch = normalise || (d % 4 != 0);
-  for (int k = 0; k < KC; ++k) if ((uintptr_t)src[k] & 15) scratch = true;
-  if (scratch) {
-    int vc = (d % 4 == 0) ? 4 : (d % 2 == 0 ? 2 : 1);
-    for (int k = 0; k < KC; ++k) {
-      const uintptr_t a = (uintptr_t)src[k];
-      if (vc == 4 && (a & 15)) vc = 2;
-      if (vc == 2 && (a & 7)) vc = 1;
-    }
-    const unsigned cgrid = (unsigned)((nc + 31) / 32);
-    for (int k = 0; k < KC; ++k) {
-      float* dst = cscratch + (size_t)k * (size_t)nc * dp;
-      // head and tail sweeps of one call share the normalised copy (same table): recompute is cheap
-      if (normalise) {
-        if (vc == 4) prep_cand_kernel<4, true><<<cgrid, 256, 0, st>>>(src[k], nc, d, dp, dst);
-        else if (vc == 2) prep_cand_kernel<2, true><<<cgrid, 256, 0, st>>>(src[k], nc, d, dp, dst);
-        else prep_cand_kernel<1, true><<<cgrid, 256, 0, st>>>(src[k], nc, d, dp, dst);
-      } else {
-        if (vc == 4) prep_cand_kernel<4, false><<<cgrid, 256, 0, st>>>(src[k], nc, d, dp, dst);
-        else if (vc == 2) prep_cand_kernel<2, false><<<cgrid, 256, 0, st>>>(src[k], nc, d, dp, dst);
-        else prep_cand_kernel<1, false><<<cgrid, 256, 0, st>>>(src[k], nc, d, dp, dst);
+  {
+    const float* src[2] = {nullptr, nullptr};
+    const bool scratch = cand_sources(m, dir, src);
+    if (scratch) {
+      for (int k = 0; k < KC; ++k) P.cand[k] = cscratch + (size_t)k * (size_t)nc * dp;
+      if (KC == 1) P.cand[1] = nullptr;
+      P.cand_pitch = dp;
+      if (model == KGE_CP) {  // subject and object tables differ per direction: (re)fill now
+        int rc = fill_cand_scratch(m, src, KC, nc, cscratch, st);
+        if (rc) return rc;
       }
-      KGE_CHECK_LAUNCH("prep_cand_kernel");
-      P.cand[k] = dst;
+    } else {
+      P.cand[0] = src[0]; P.cand[1] = src[1]; P.cand_pitch = d;
     }
-    if (KC == 1) P.cand[1] = nullptr;
-    P.cand_pitch = dp;
-  } else {
-    P.cand[0] = src[0]; P.cand[1] = src[1]; P.cand_pitch = d;
   }
 
   // 3. shared-memory plan: full rows when they fit in ~110 KB (2 CTAs/SM), else slabs of DS elements

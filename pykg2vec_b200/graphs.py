@@ -1,0 +1,47 @@
+"""CUDA-graph staging of a host-in / host-out call.
+
+The hot loop issues a handful of short kernels per batch (train step: 2 kernels + a
+memset; evaluation batch: ~8), so launch latency and per-call host work dominate the
+end-to-end time.  StagedGraph captures the whole round trip — ONE H2D copy from a pinned
+staging buffer, the kernels, ONE D2H copy into a pinned result buffer — as a single CUDA
+graph that is replayed per batch (Guideline: capture launch-bound inner loops in graphs).
+The C-ABI entry points are capture-safe: they only enqueue work on the given stream.
+"""
+import torch
+
+
+class StagedGraph:
+    def __init__(self, device, in_words, out_like, body, in_dtype=torch.int64):
+        """body(d_in) must enqueue the kernels on the current stream and return a device tensor
+        shaped like `out_like` (a CPU tensor prototype) that it fully overwrites."""
+        self.device = torch.device(device)
+        self.h_in = torch.empty(in_words, dtype=in_dtype).pin_memory()
+        self.d_in = torch.zeros(in_words, dtype=in_dtype, device=self.device)
+        self.h_out = torch.empty_like(out_like).pin_memory()
+        self.body = body
+        self.graph = None
+
+    def _run_eager(self):
+        self.d_in.copy_(self.h_in, non_blocking=True)
+        d_out = self.body(self.d_in)
+        self.h_out.copy_(d_out, non_blocking=True)
+
+    def capture(self):
+        cur = torch.cuda.current_stream(self.device)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            self._run_eager()  # warm-up outside capture (sets kernel attributes, sizes workspaces)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._run_eager()
+        self.graph = g
+        return self
+
+    def __call__(self):
+        """h_in must already hold the inputs.  Returns the pinned result (valid until next call)."""
+        self.graph.replay()
+        torch.cuda.current_stream(self.device).synchronize()
+        return self.h_out

@@ -52,9 +52,10 @@ def allgather_batch_ids(ids):
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return ids
     world = dist.get_world_size()
-    out = torch.empty((world,) + tuple(ids.shape), dtype=ids.dtype, device=ids.device)
+    k, b = ids.shape
+    out = torch.empty((world * k, b), dtype=ids.dtype, device=ids.device)  # concatenated along dim 0
     dist.all_gather_into_tensor(out, ids.contiguous())
-    return out.permute(1, 0, 2).reshape(ids.shape[0], world * ids.shape[1]).contiguous()
+    return out.view(world, k, b).permute(1, 0, 2).reshape(k, world * b).contiguous()
 
 
 def gather_query_shards(local_counts, total):
@@ -66,8 +67,9 @@ def gather_query_shards(local_counts, total):
     cap = -(-int(total) // world)
     buf = torch.zeros((cap, 4), dtype=local_counts.dtype, device=local_counts.device)
     buf[:local_counts.shape[0]] = local_counts
-    out = torch.empty((world, cap, 4), dtype=local_counts.dtype, device=local_counts.device)
+    out = torch.empty((world * cap, 4), dtype=local_counts.dtype, device=local_counts.device)
     dist.all_gather_into_tensor(out, buf)
+    out = out.view(world, cap, 4)
     parts = []
     for r in range(world):
         lo, hi = shard_range(total, world, r)

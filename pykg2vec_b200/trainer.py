@@ -37,6 +37,7 @@ class Trainer:
         self._state = None
         self._pinned = None
         self._loss_buf = None
+        self._graphs = {}
 
     def build_model(self):
         """trainer.py:103-144 (optimizer selection; unknown names raise NotImplementedError)."""
@@ -133,9 +134,42 @@ class Trainer:
         dev = self._pinned[:k, :n].to(self.config.device, non_blocking=True)
         return [dev[i, :lens[i]] for i in range(k)], k * n * 8
 
+    def _graphed_hinge_step(self, data):
+        """Pairwise hinge + SGD as ONE CUDA graph: H2D of the packed [6,B] ids from a pinned
+        buffer, the two training kernels, D2H of the loss."""
+        from .graphs import StagedGraph
+        B = len(data[0])
+        tables = self.model.kge_tables()
+        key = (B, tuple(int(w.data_ptr()) for w in tables))
+        call = self._graphs.get(key)
+        if call is None:
+            desc = self.model.kge_desc()
+            loss = torch.zeros(1, dtype=torch.float32, device=self.config.device)
+            margin, lr = float(self.config.margin), float(self.config.learning_rate)
+
+            def body(d_in):
+                ids = d_in.view(6, B)
+                _lib.train_pairwise_hinge_sgd(desc, self._grad_scratch, ids[0], ids[1], ids[2], ids[3],
+                                              ids[4], ids[5], margin, lr, loss)
+                return loss
+
+            call = StagedGraph(self.config.device, 6 * B, torch.empty(1, dtype=torch.float32), body).capture()
+            self._graphs[key] = call
+        buf = call.h_in.numpy().reshape(6, B)
+        for i, a in enumerate(data):
+            buf[i] = a
+        self.last_h2d_bytes = 6 * B * 8
+        return float(call()[0])
+
     def train_batch(self, data):
         """data: the list Generator yields — 6 id arrays (pairwise) or 4 (pointwise)."""
         self.model.train()
+        data = list(data)
+        if (self._fused and getattr(self.config, "cuda_graph", True)
+                and self.model.training_strategy == TrainingStrategy.PAIRWISE_BASED
+                and self.model.model_name.lower() != "rotate" and self.config.optimizer == "sgd"
+                and len(data) == 6 and all(len(a) == len(data[0]) for a in data)):
+            return self._graphed_hinge_step(data)
         ids, nbytes = self._to_device(list(data))
         self.last_h2d_bytes = nbytes
         strategy = self.model.training_strategy

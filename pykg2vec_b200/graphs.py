@@ -11,19 +11,22 @@ import torch
 
 
 class StagedGraph:
-    def __init__(self, device, in_words, out_like, body, in_dtype=torch.int64):
+    def __init__(self, device, in_words, out_like, body, in_dtype=torch.int64, warm_body=None):
         """body(d_in) must enqueue the kernels on the current stream and return a device tensor
-        shaped like `out_like` (a CPU tensor prototype) that it fully overwrites."""
+        shaped like `out_like` (a CPU tensor prototype) that it fully overwrites.  The staging
+        buffer starts zero-filled (id 0 is always valid) and the un-captured warm-up run uses
+        `warm_body` when the real body has side effects (a training step)."""
         self.device = torch.device(device)
-        self.h_in = torch.empty(in_words, dtype=in_dtype).pin_memory()
+        self.h_in = torch.zeros(in_words, dtype=in_dtype).pin_memory()
+        self.warm_body = warm_body
         self.d_in = torch.zeros(in_words, dtype=in_dtype, device=self.device)
         self.h_out = torch.empty_like(out_like).pin_memory()
         self.body = body
         self.graph = None
 
-    def _run_eager(self):
+    def _run_eager(self, body=None):
         self.d_in.copy_(self.h_in, non_blocking=True)
-        d_out = self.body(self.d_in)
+        d_out = (body or self.body)(self.d_in)
         self.h_out.copy_(d_out, non_blocking=True)
 
     def capture(self):
@@ -31,7 +34,7 @@ class StagedGraph:
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(cur)
         with torch.cuda.stream(side):
-            self._run_eager()  # warm-up outside capture (sets kernel attributes, sizes workspaces)
+            self._run_eager(self.warm_body)  # warm-up outside capture (loads kernels, sets attributes)
         cur.wait_stream(side)
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()

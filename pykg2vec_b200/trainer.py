@@ -147,13 +147,17 @@ class Trainer:
             loss = torch.zeros(1, dtype=torch.float32, device=self.config.device)
             margin, lr = float(self.config.margin), float(self.config.learning_rate)
 
-            def body(d_in):
-                ids = d_in.view(6, B)
-                _lib.train_pairwise_hinge_sgd(desc, self._grad_scratch, ids[0], ids[1], ids[2], ids[3],
-                                              ids[4], ids[5], margin, lr, loss)
-                return loss
+            def make_body(step_lr):
+                def body(d_in):
+                    ids = d_in.view(6, B)
+                    _lib.train_pairwise_hinge_sgd(desc, self._grad_scratch, ids[0], ids[1], ids[2], ids[3],
+                                                  ids[4], ids[5], margin, step_lr, loss)
+                    return loss
+                return body
 
-            call = StagedGraph(self.config.device, 6 * B, torch.empty(1, dtype=torch.float32), body).capture()
+            # the warm-up run before capture uses lr = 0: the tables are left exactly unchanged
+            call = StagedGraph(self.config.device, 6 * B, torch.empty(1, dtype=torch.float32), make_body(lr),
+                               warm_body=make_body(0.0)).capture()
             self._graphs[key] = call
         buf = call.h_in.numpy().reshape(6, B)
         for i, a in enumerate(data):

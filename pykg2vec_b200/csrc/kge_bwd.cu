@@ -11,7 +11,7 @@ constexpr int kGroupsPerCta = kThreads / 8;
 
 struct GradTables { float* t[KGE_MAX_TABLES]; };
 
-template <int MODEL, int VEC>
+template <int MODEL, int VEC, int CHSEL>
 __global__ void __launch_bounds__(kThreads)
 score_bwd_kernel(ModelParams P, GradTables GT, const int64_t* __restrict__ h,
                  const int64_t* __restrict__ r, const int64_t* __restrict__ t, int64_t n,
@@ -30,7 +30,7 @@ score_bwd_kernel(ModelParams P, GradTables GT, const int64_t* __restrict__ h,
   if (!valid) {  // idle groups run the math (full-warp shuffles) but scatter nothing
     G.h[0] = G.h[1] = G.t[0] = G.t[1] = G.r[0] = G.r[1] = G.r[2] = nullptr;
   }
-  grad_group<MODEL, VEC>(R, G, P, lane, __ldg(gout + gi), scratch);
+  grad_group<MODEL, VEC, CHSEL>(R, G, P, lane, __ldg(gout + gi), scratch);
 }
 
 int check_model(const kge_model_t* m);
@@ -64,15 +64,25 @@ extern "C" int kge_score_bwd(const kge_model_t* m, const int64_t* h, const int64
   const size_t smem = (size_t)sf * kGroupsPerCta * sizeof(float);
   const unsigned grid = (unsigned)((n + kGroupsPerCta - 1) / kGroupsPerCta);
   cudaStream_t st = (cudaStream_t)stream;
-#define CALL(M, V)                                                                              \
-  do {                                                                                          \
-    if (smem > 48 * 1024)                                                                       \
-      KGE_CUDA_OK(cudaFuncSetAttribute(score_bwd_kernel<M, V>,                                  \
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    score_bwd_kernel<M, V><<<grid, kThreads, smem, st>>>(P, GT, h, r, t, n, grad_scores, sf);   \
+  const int chsel = (m->model == KGE_TRANSE || m->model == KGE_TRANSM) ? ch_select(m->dim) : 0;
+#define LAUNCH(M, V, C)                                                                            \
+  do {                                                                                             \
+    if (smem > 48 * 1024)                                                                          \
+      KGE_CUDA_OK(cudaFuncSetAttribute(score_bwd_kernel<M, V, C>,                                  \
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    score_bwd_kernel<M, V, C><<<grid, kThreads, smem, st>>>(P, GT, h, r, t, n, grad_scores, sf);   \
+  } while (0)
+#define CALL(M, V)                                                       \
+  do {                                                                   \
+    if (!(M == KGE_TRANSE || M == KGE_TRANSM)) { LAUNCH(M, V, 0); }      \
+    else if (chsel == 2) { LAUNCH(M, V, 2); }                            \
+    else if (chsel == 4) { LAUNCH(M, V, 4); }                            \
+    else if (chsel == 8) { LAUNCH(M, V, 8); }                            \
+    else { LAUNCH(M, V, 0); }                                            \
   } while (0)
   KGE_DISPATCH_MODEL_VEC(m->model, vec, CALL);
 #undef CALL
+#undef LAUNCH
   KGE_CHECK_LAUNCH("score_bwd_kernel");
   return KGE_OK;
 }

@@ -110,15 +110,78 @@ KGE_DEV void dist_elem(const DistCtx& X, float hv, float rv, float tv, float& dh
   dt = -(dx - tn * X.ct) * X.it;
 }
 
+// TransE / TransM backward with the three rows held in registers (CH chunks per lane):
+// one trip to memory for the operands, then norms, projections and the scatter from registers.
+template <int CH, int VEC>
+KGE_DEV void grad_trans_cached(const TripleRows& R, const GradRows& G, int d, int nch, int lane, int l1,
+                               float gs) {
+  float4 A[CH], B[CH], C[CH];
+#pragma unroll
+  for (int k = 0; k < CH; ++k) {
+    const int c = lane + 8 * k;
+    if (c < nch) { A[k] = ld_chunk<VEC>(R.h[0], c, d); B[k] = ld_chunk<VEC>(R.r[0], c, d); C[k] = ld_chunk<VEC>(R.t[0], c, d); }
+    else { A[k] = B[k] = C[k] = make_float4(0.f, 0.f, 0.f, 0.f); }
+  }
+  DistCtx X;
+  float sh = 0.f, sr = 0.f, st = 0.f;
+#pragma unroll
+  for (int k = 0; k < CH; ++k)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      sh = ffma(f4_get(A[k], e), f4_get(A[k], e), sh);
+      sr = ffma(f4_get(B[k], e), f4_get(B[k], e), sr);
+      st = ffma(f4_get(C[k], e), f4_get(C[k], e), st);
+    }
+  sh = group_sum(sh); sr = group_sum(sr); st = group_sum(st);
+  X.ih = inv_norm_from_sumsq(sh); X.ir = inv_norm_from_sumsq(sr); X.it = inv_norm_from_sumsq(st);
+  const bool clamp_h = __fsqrt_rn(sh) < 1e-12f, clamp_r = __fsqrt_rn(sr) < 1e-12f, clamp_t = __fsqrt_rn(st) < 1e-12f;
+  X.l1 = l1;
+  float S = 0.f, ah = 0.f, ar = 0.f, at = 0.f;
+#pragma unroll
+  for (int k = 0; k < CH; ++k)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float hn = f4_get(A[k], e) * X.ih, rn = f4_get(B[k], e) * X.ir, tn = f4_get(C[k], e) * X.it;
+      const float x = (hn + rn) - tn;
+      const float u = l1 ? sgnf(x) : x;
+      S += x * x; ah += hn * u; ar += rn * u; at += tn * u;
+    }
+  S = group_sum(S); ah = group_sum(ah); ar = group_sum(ar); at = group_sum(at);
+  const float s = sqrtf(S);
+  X.coef = l1 ? gs : ((s > 0.f) ? gs / s : 0.f);
+  X.ch = clamp_h ? 0.f : X.coef * ah;
+  X.cr = clamp_r ? 0.f : X.coef * ar;
+  X.ct = clamp_t ? 0.f : X.coef * at;
+#pragma unroll
+  for (int k = 0; k < CH; ++k) {
+    const int c = lane + 8 * k;
+    if (c < nch) {
+      float4 dh, dr, dt;
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        dist_elem(X, f4_get(A[k], e), f4_get(B[k], e), f4_get(C[k], e), f4_at(dh, e), f4_at(dr, e), f4_at(dt, e));
+      red_row_chunk<VEC>(G.h[0], c, d, dh);
+      red_row_chunk<VEC>(G.r[0], c, d, dr);
+      red_row_chunk<VEC>(G.t[0], c, d, dt);
+    }
+  }
+}
+
 // Accumulate gs * d score / d rows into G.  All 8 lanes call; `scratch` per group
 // (group_scratch_floats_bwd floats, TransR only).
-template <int MODEL, int VEC>
+template <int MODEL, int VEC, int CHSEL = -1>
 KGE_DEV void grad_group(const TripleRows& R, const GradRows& G, const ModelParams& P, int lane,
                         float gs, float* scratch) {
   const int d = P.d;
   const int nch = (d + 3) >> 2;
   if (MODEL == KGE_TRANSE || MODEL == KGE_TRANSM) {
     if (MODEL == KGE_TRANSM) gs *= __ldg(R.r[1]);
+    if (CHSEL > 0) { grad_trans_cached<(CHSEL > 0 ? CHSEL : 1), VEC>(R, G, d, nch, lane, P.l1, gs); return; }
+    if (CHSEL < 0) {
+      if (nch <= 16) { grad_trans_cached<2, VEC>(R, G, d, nch, lane, P.l1, gs); return; }
+      if (nch <= 32) { grad_trans_cached<4, VEC>(R, G, d, nch, lane, P.l1, gs); return; }
+      if (nch <= 64) { grad_trans_cached<8, VEC>(R, G, d, nch, lane, P.l1, gs); return; }
+    }
     auto fh = [&](int c) { return ld_chunk<VEC>(R.h[0], c, d); };
     auto fr = [&](int c) { return ld_chunk<VEC>(R.r[0], c, d); };
     auto ft = [&](int c) { return ld_chunk<VEC>(R.t[0], c, d); };

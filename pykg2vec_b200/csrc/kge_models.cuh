@@ -54,26 +54,47 @@ KGE_DEV void resolve_rows(TripleRows& R, const ModelParams& P, const float* cons
 // Shared tail of TransE/H/D/R/M forward(): L2-normalise h', r', t' and return
 // ||h^ + r^ - t^||_p  (pairwise.py:69-76, :146-153, :266-273, :463-470).
 // fh/fr/ft(c) return chunk c (4 elements, zero beyond the width) of each operand.
-template <int GROUPING, class FH, class FR, class FT>
-KGE_DEV float trans_distance(FH fh, FR fr, FT ft, int nch, int lane, int l1) {
-  float sh = 0.f, sr = 0.f, st = 0.f;
-#pragma unroll 2
-  for (int c = lane; c < nch; c += 8) {
-    const float4 a = fh(c), b = fr(c), cc = ft(c);
+// CH > 0: the lane's chunks (c = lane + 8k, k < CH) are fetched ONCE into registers and both
+// passes (norms, then distance) run from registers — one trip to memory instead of two.
+template <int GROUPING, int CH, class FH, class FR, class FT>
+KGE_DEV float trans_distance_impl(FH fh, FR fr, FT ft, int nch, int lane, int l1) {
+  float4 A[CH > 0 ? CH : 1], B[CH > 0 ? CH : 1], C[CH > 0 ? CH : 1];
+  if (CH > 0) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      sh = ffma(f4_get(a, e), f4_get(a, e), sh);
-      sr = ffma(f4_get(b, e), f4_get(b, e), sr);
-      st = ffma(f4_get(cc, e), f4_get(cc, e), st);
+    for (int k = 0; k < CH; ++k) {
+      const int c = lane + 8 * k;
+      if (c < nch) { A[k] = fh(c); B[k] = fr(c); C[k] = ft(c); }
+      else { A[k] = B[k] = C[k] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    }
+  }
+  float sh = 0.f, sr = 0.f, st = 0.f;
+  if (CH > 0) {
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        sh = ffma(f4_get(A[k], e), f4_get(A[k], e), sh);
+        sr = ffma(f4_get(B[k], e), f4_get(B[k], e), sr);
+        st = ffma(f4_get(C[k], e), f4_get(C[k], e), st);
+      }
+    }
+  } else {
+#pragma unroll 2
+    for (int c = lane; c < nch; c += 8) {
+      const float4 a = fh(c), b = fr(c), cc = ft(c);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        sh = ffma(f4_get(a, e), f4_get(a, e), sh);
+        sr = ffma(f4_get(b, e), f4_get(b, e), sr);
+        st = ffma(f4_get(cc, e), f4_get(cc, e), st);
+      }
     }
   }
   const float ih = inv_norm_from_sumsq(group_sum(sh));
   const float ir = inv_norm_from_sumsq(group_sum(sr));
   const float it = inv_norm_from_sumsq(group_sum(st));
   float acc = 0.f;
-#pragma unroll 2
-  for (int c = lane; c < nch; c += 8) {
-    const float4 a = fh(c), b = fr(c), cc = ft(c);
+  auto step = [&](const float4& a, const float4& b, const float4& cc) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float hn = fmul(f4_get(a, e), ih), rn = fmul(f4_get(b, e), ir), tn = fmul(f4_get(cc, e), it);
@@ -82,9 +103,29 @@ KGE_DEV float trans_distance(FH fh, FR fr, FT ft, int nch, int lane, int l1) {
       else x = fadd(hn, fsub(rn, tn));
       if (l1) acc = fadd(acc, fabsf(x)); else acc = ffma(x, x, acc);
     }
+  };
+  if (CH > 0) {
+    // zero-filled slots beyond the row add exact zeros: same bits as skipping them
+#pragma unroll
+    for (int k = 0; k < CH; ++k) step(A[k], B[k], C[k]);
+  } else {
+#pragma unroll 2
+    for (int c = lane; c < nch; c += 8) step(fh(c), fr(c), ft(c));
   }
   acc = group_sum(acc);
   return l1 ? acc : __fsqrt_rn(acc);
+}
+
+// CHSEL >= 0: the register-cache depth is fixed at compile time (kernels whose host launcher
+// picks it from d, so that narrow models keep a small register footprint / high occupancy);
+// CHSEL < 0: chosen at run time.
+template <int GROUPING, int CHSEL = -1, class FH, class FR, class FT>
+KGE_DEV float trans_distance(FH fh, FR fr, FT ft, int nch, int lane, int l1) {
+  if (CHSEL >= 0) return trans_distance_impl<GROUPING, (CHSEL >= 0 ? CHSEL : 0)>(fh, fr, ft, nch, lane, l1);
+  if (nch <= 16) return trans_distance_impl<GROUPING, 2>(fh, fr, ft, nch, lane, l1);   // d <= 64
+  if (nch <= 32) return trans_distance_impl<GROUPING, 4>(fh, fr, ft, nch, lane, l1);   // d <= 128
+  if (nch <= 64) return trans_distance_impl<GROUPING, 8>(fh, fr, ft, nch, lane, l1);   // d <= 256
+  return trans_distance_impl<GROUPING, 0>(fh, fr, ft, nch, lane, l1);
 }
 
 template <int VEC>
@@ -100,13 +141,13 @@ KGE_DEV float group_dot(const float* __restrict__ a, const float* __restrict__ b
 }
 
 // `scratch`: per-group shared memory, only used by TransR (2 * dr_pad floats).
-template <int MODEL, int VEC, int GROUPING>
+template <int MODEL, int VEC, int GROUPING, int CHSEL = -1>
 KGE_DEV float score_group(const TripleRows& R, const ModelParams& P, int lane, float* scratch) {
   const int d = P.d;
   const int nch = (d + 3) >> 2;
   if (MODEL == KGE_TRANSE || MODEL == KGE_TRANSM) {
     // TransE.forward pairwise.py:56-93; TransM.forward pairwise.py:325-347
-    const float dist = trans_distance<GROUPING>(
+    const float dist = trans_distance<GROUPING, CHSEL>(
         [&](int c) { return ld_chunk<VEC>(R.h[0], c, d); },
         [&](int c) { return ld_chunk<VEC>(R.r[0], c, d); },
         [&](int c) { return ld_chunk<VEC>(R.t[0], c, d); }, nch, lane, P.l1);
@@ -140,7 +181,7 @@ KGE_DEV float score_group(const TripleRows& R, const ModelParams& P, int lane, f
       for (int e = 0; e < 4; ++e) f4_at(o, e) = ffma(-a, fmul(f4_get(w, e), iw), f4_get(x, e));
       return o;
     };
-    return trans_distance<GROUPING>([&](int c) { return proj(R.h[0], ah, c); },
+    return trans_distance<GROUPING, CHSEL>([&](int c) { return proj(R.h[0], ah, c); },
                                     [&](int c) { return ld_chunk<VEC>(R.r[0], c, d); },
                                     [&](int c) { return proj(R.t[0], at, c); }, nch, lane, P.l1);
   } else if (MODEL == KGE_TRANSD) {
@@ -154,7 +195,7 @@ KGE_DEV float score_group(const TripleRows& R, const ModelParams& P, int lane, f
       for (int e = 0; e < 4; ++e) f4_at(o, e) = ffma(a, f4_get(rm, e), f4_get(x, e));
       return o;
     };
-    return trans_distance<GROUPING>([&](int c) { return proj(R.h[0], ah, c); },
+    return trans_distance<GROUPING, CHSEL>([&](int c) { return proj(R.h[0], ah, c); },
                                     [&](int c) { return ld_chunk<VEC>(R.r[0], c, d); },
                                     [&](int c) { return proj(R.t[0], at, c); }, nch, lane, P.l1);
   } else if (MODEL == KGE_TRANSR) {
@@ -193,7 +234,7 @@ KGE_DEV float score_group(const TripleRows& R, const ModelParams& P, int lane, f
       *reinterpret_cast<float4*>(tp + 4 * c) = at;
     }
     __syncwarp();
-    return trans_distance<GROUPING>(
+    return trans_distance<GROUPING, CHSEL>(
         [&](int c) { return *reinterpret_cast<const float4*>(hp + 4 * c); },
         [&](int c) {
           const float4 b = ld_chunk<VEC>(R.r[0], c, dr);
@@ -262,6 +303,16 @@ KGE_DEV float score_group(const TripleRows& R, const ModelParams& P, int lane, f
     return -group_sum(acc);
   }
   return 0.f;
+}
+
+// register-cache depth for a distance model of width d (see trans_distance)
+inline int ch_select(int width) {
+  const int nch = (width + 3) >> 2;
+  return nch <= 16 ? 2 : (nch <= 32 ? 4 : (nch <= 64 ? 8 : 0));
+}
+constexpr bool is_distance_model(int model) {
+  return model == KGE_TRANSE || model == KGE_TRANSM || model == KGE_TRANSH || model == KGE_TRANSD ||
+         model == KGE_TRANSR;
 }
 
 // shared-memory floats one 8-lane group needs (TransR only)

@@ -13,8 +13,8 @@ namespace kge {
 constexpr int kThreads = 256;
 constexpr int kGroupsPerCta = kThreads / 8;
 
-template <int MODEL, int VEC>
-__global__ void __launch_bounds__(kThreads)
+template <int MODEL, int VEC, int CHSEL>
+__global__ void __launch_bounds__(kThreads, 2)  // <= 128 registers: at least 16 warps per SM in flight
 score_fwd_kernel(ModelParams P, int grouping, const int64_t* __restrict__ h,
                  const int64_t* __restrict__ r, const int64_t* __restrict__ t, int64_t n,
                  float* __restrict__ out, int scratch_floats) {
@@ -27,8 +27,8 @@ score_fwd_kernel(ModelParams P, int grouping, const int64_t* __restrict__ h,
   TripleRows R;
   resolve_rows<MODEL>(R, P, P.tab, P.tab, P.tab, __ldg(h + gi), __ldg(r + gi), __ldg(t + gi));
   float s;
-  if (grouping == KGE_GROUP_TAIL) s = score_group<MODEL, VEC, KGE_GROUP_TAIL>(R, P, lane, scratch);
-  else s = score_group<MODEL, VEC, KGE_GROUP_HEAD>(R, P, lane, scratch);
+  if (grouping == KGE_GROUP_TAIL) s = score_group<MODEL, VEC, KGE_GROUP_TAIL, CHSEL>(R, P, lane, scratch);
+  else s = score_group<MODEL, VEC, KGE_GROUP_HEAD, CHSEL>(R, P, lane, scratch);
   if (valid && lane == 0) out[g] = s;
 }
 
@@ -74,15 +74,26 @@ extern "C" int kge_score_fwd(const kge_model_t* m, int grouping, const int64_t* 
   const size_t smem = (size_t)sf * kGroupsPerCta * sizeof(float);
   const unsigned grid = (unsigned)((n + kGroupsPerCta - 1) / kGroupsPerCta);
   cudaStream_t st = (cudaStream_t)stream;
-#define CALL(M, V)                                                                              \
-  do {                                                                                          \
-    if (smem > 48 * 1024)                                                                       \
-      KGE_CUDA_OK(cudaFuncSetAttribute(score_fwd_kernel<M, V>,                                  \
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    score_fwd_kernel<M, V><<<grid, kThreads, smem, st>>>(P, grouping, h, r, t, n, scores, sf);  \
+  // distance models: the register-cache depth is a template parameter picked from the width
+  const int chsel = is_distance_model(m->model) ? ch_select(m->model == KGE_TRANSR ? m->rel_dim : m->dim) : 0;
+#define LAUNCH(M, V, C)                                                                            \
+  do {                                                                                             \
+    if (smem > 48 * 1024)                                                                          \
+      KGE_CUDA_OK(cudaFuncSetAttribute(score_fwd_kernel<M, V, C>,                                  \
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    score_fwd_kernel<M, V, C><<<grid, kThreads, smem, st>>>(P, grouping, h, r, t, n, scores, sf);  \
+  } while (0)
+#define CALL(M, V)                                                       \
+  do {                                                                   \
+    if (!is_distance_model(M)) { LAUNCH(M, V, 0); }                      \
+    else if (chsel == 2) { LAUNCH(M, V, 2); }                            \
+    else if (chsel == 4) { LAUNCH(M, V, 4); }                            \
+    else if (chsel == 8) { LAUNCH(M, V, 8); }                            \
+    else { LAUNCH(M, V, 0); }                                            \
   } while (0)
   KGE_DISPATCH_MODEL_VEC(m->model, vec, CALL);
 #undef CALL
+#undef LAUNCH
   KGE_CHECK_LAUNCH("score_fwd_kernel");
   return KGE_OK;
 }

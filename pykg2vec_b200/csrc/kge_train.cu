@@ -79,6 +79,30 @@ struct ApplyTasks {
 
 // optimizer 0: SGD  (w -= lr * g)                       torch.optim.SGD, trainer.py:117-121
 // optimizer 1: Adagrad (s += g*g; w -= lr * g / (sqrt(s) + eps))  torch.optim.Adagrad, trainer.py:122-126
+// 128-bit atomic exchange (atom.exch.b128, sm_90+): takes a whole 16-byte chunk of the
+// gradient row out of the scratch in one transaction and leaves zeros behind.
+KGE_DEV float4 exch_zero_b128(float* addr) {
+  unsigned long long lo, hi;
+  asm volatile(
+      "{\n\t.reg .b128 v, o;\n\t"
+      "mov.b128 v, {%2, %3};\n\t"
+      "atom.global.exch.b128 o, [%4], v;\n\t"
+      "mov.b128 {%0, %1}, o;\n\t}"
+      : "=l"(lo), "=l"(hi) : "l"(0ull), "l"(0ull), "l"(addr) : "memory");
+  float4 r;
+  r.x = __uint_as_float((unsigned)(lo & 0xffffffffull)); r.y = __uint_as_float((unsigned)(lo >> 32));
+  r.z = __uint_as_float((unsigned)(hi & 0xffffffffull)); r.w = __uint_as_float((unsigned)(hi >> 32));
+  return r;
+}
+
+template <int OPT>
+KGE_DEV float apply_elem(float wv, float gv, float* s, float lr, float eps) {
+  if (OPT == 0) return wv - lr * gv;
+  const float sv = *s + gv * gv;
+  *s = sv;
+  return wv - lr * gv / (sqrtf(sv) + eps);
+}
+
 template <int OPT>
 __global__ void __launch_bounds__(kThreads)
 apply_rows_kernel(ApplyTasks T, int64_t n, float lr, float eps) {
@@ -91,15 +115,29 @@ apply_rows_kernel(ApplyTasks T, int64_t n, float lr, float eps) {
   float* __restrict__ w = T.w[task] + off;
   float* __restrict__ g = T.g[task] + off;
   float* __restrict__ s = (OPT == 1) ? T.state[task] + off : nullptr;
-  for (int j = lane; j < width; j += 8) {
-    const float gv = atomicExch(g + j, 0.f);
-    if (gv != 0.f) {
-      if (OPT == 0) {
-        w[j] -= lr * gv;
-      } else {
-        const float sv = s[j] + gv * gv;
-        s[j] = sv;
-        w[j] -= lr * gv / (sqrtf(sv) + eps);
+  const bool vec = ((width & 3) == 0) && ((((uintptr_t)w | (uintptr_t)g | (uintptr_t)(OPT == 1 ? s : w)) & 15) == 0);
+  if (vec) {
+    const int nch = width >> 2;
+    for (int c = lane; c < nch; c += 8) {
+      const float4 gv = exch_zero_b128(g + 4 * c);
+      if (gv.x != 0.f || gv.y != 0.f || gv.z != 0.f || gv.w != 0.f) {
+        float4 wv = *reinterpret_cast<float4*>(w + 4 * c);
+        float4 sv = (OPT == 1) ? *reinterpret_cast<float4*>(s + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        wv.x = apply_elem<OPT>(wv.x, gv.x, &sv.x, lr, eps);
+        wv.y = apply_elem<OPT>(wv.y, gv.y, &sv.y, lr, eps);
+        wv.z = apply_elem<OPT>(wv.z, gv.z, &sv.z, lr, eps);
+        wv.w = apply_elem<OPT>(wv.w, gv.w, &sv.w, lr, eps);
+        *reinterpret_cast<float4*>(w + 4 * c) = wv;
+        if (OPT == 1) *reinterpret_cast<float4*>(s + 4 * c) = sv;
+      }
+    }
+  } else {
+    for (int j = lane; j < width; j += 8) {
+      const float gv = atomicExch(g + j, 0.f);
+      if (gv != 0.f) {
+        float sv = (OPT == 1) ? s[j] : 0.f;
+        w[j] = apply_elem<OPT>(w[j], gv, &sv, lr, eps);
+        if (OPT == 1) s[j] = sv;
       }
     }
   }

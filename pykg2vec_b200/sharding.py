@@ -33,6 +33,9 @@ def init_distributed(backend=None):
         return 0, 1
     if not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # keep stdout clean (bench.py prints exactly one JSON line): NCCL's version banner goes
+        # to stdout at NCCL_DEBUG=VERSION/INFO
+        os.environ["NCCL_DEBUG"] = os.environ.get("KGE_NCCL_DEBUG", "WARN")
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         dist.init_process_group(backend=backend)
@@ -49,32 +52,52 @@ def shard_range(total, world, rank):
 def allgather_batch_ids(ids):
     """ids: [k, B] int64 on the rank's device -> [k, world*B]: the global batch every rank
     trains on (replicated update)."""
+    return allgather_batch_ids_async(ids)()
+
+
+def allgather_batch_ids_async(ids):
+    """Start the id all-gather (NCCL runs it on its own stream) and return a closure that makes
+    the current stream wait for it and yields the [k, world*B] global batch.  Issue it BEFORE
+    enqueueing independent work (the evaluation sweep) so the exchange hides behind it."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
-        return ids
+        return lambda: ids
     world = dist.get_world_size()
     k, b = ids.shape
     out = torch.empty((world * k, b), dtype=ids.dtype, device=ids.device)  # concatenated along dim 0
-    dist.all_gather_into_tensor(out, ids.contiguous())
-    return out.view(world, k, b).permute(1, 0, 2).reshape(k, world * b).contiguous()
+    work = dist.all_gather_into_tensor(out, ids.contiguous(), async_op=True)
+
+    def finish():
+        work.wait()
+        return out.view(world, k, b).permute(1, 0, 2).reshape(k, world * b).contiguous()
+    return finish
 
 
 def gather_query_shards(local_counts, total):
     """local_counts: [q_local, 4] int32 of this rank's query shard (shard_range order) ->
     [total, 4] on every rank.  The single collective of replicated-table evaluation."""
+    return gather_query_shards_async(local_counts, total)()
+
+
+def gather_query_shards_async(local_counts, total):
+    """Asynchronous form: returns a closure that waits and assembles the [total, 4] ranks."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
-        return local_counts
-    world, rank = dist.get_world_size(), dist.get_rank()
+        return lambda: local_counts
+    world = dist.get_world_size()
     cap = -(-int(total) // world)
     buf = torch.zeros((cap, 4), dtype=local_counts.dtype, device=local_counts.device)
     buf[:local_counts.shape[0]] = local_counts
     out = torch.empty((world * cap, 4), dtype=local_counts.dtype, device=local_counts.device)
-    dist.all_gather_into_tensor(out, buf)
-    out = out.view(world, cap, 4)
-    parts = []
-    for r in range(world):
-        lo, hi = shard_range(total, world, r)
-        parts.append(out[r, :hi - lo])
-    return torch.cat(parts, dim=0)
+    work = dist.all_gather_into_tensor(out, buf, async_op=True)
+
+    def finish():
+        work.wait()
+        o = out.view(world, cap, 4)
+        parts = []
+        for r in range(world):
+            lo, hi = shard_range(total, world, r)
+            parts.append(o[r, :hi - lo])
+        return torch.cat(parts, dim=0)
+    return finish
 
 
 def cuda_count_fn(name, dim, **spec_kw):

@@ -1,0 +1,71 @@
+"""-m gpu tests that need >= 2 GPUs (skipped otherwise): NCCL path of the sharded evaluation.
+Run under gpurun --gpus 2:  python -m pytest tests/test_gpu_multi.py -m gpu"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.dirname(here))
+    sys.path.insert(0, here)
+    import torch.distributed as dist
+    import gpu_util as gpu
+    import oracle
+    from pykg2vec_b200 import sharding
+    torch.cuda.set_device(rank)
+    sharding.init_distributed(backend="nccl")
+    dev = torch.device("cuda", rank)
+    # ComplEx, YAGO3-10-like proportions scaled down: entity rows partitioned across the ranks
+    N, R, d, Q = 3001, 7, 100, 33
+    om, tabs = gpu.synthetic_case("complex", N, R, d, seed=17)
+    rng = np.random.RandomState(5)
+    qh, qr, qt = rng.randint(N, size=Q), rng.randint(R, size=Q), rng.randint(N, size=Q)
+    ft, fh = gpu.random_filters_csr(rng, N, qh, qr, qt)
+    want = oracle.rank_1vsall(om, qh, qr, qt, ft, fh)
+    lo, hi = sharding.shard_range(N, world, rank)
+    ent_local = [torch.from_numpy(tabs[0][lo:hi].copy()).to(dev), torch.from_numpy(tabs[1][lo:hi].copy()).to(dev)]
+    rel = [torch.from_numpy(tabs[2]).to(dev), torch.from_numpy(tabs[3]).to(dev)]
+    ranker = sharding.RowShardedRanker(sharding.cuda_count_fn("complex", d), N, ent_local, rel, (0, 1), (2, 3))
+    got = ranker.rank_queries(qh, qr, qt, ft, fh)
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    # replicated tables, sharded queries, one gather of the ranks
+    from pykg2vec_b200 import _lib
+    full = [torch.from_numpy(t).to(dev) for t in tabs]
+    desc = _lib.ModelDesc("complex", full, d)
+    qlo, qhi = sharding.shard_range(Q, world, rank)
+    to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    sub = lambda f: (to(f[0][qlo:qhi + 1] - f[0][qlo]), to(f[1][f[0][qlo]:f[0][qhi]]))
+    local = _lib.rank_1vsall(desc, to(qh[qlo:qhi]), to(qr[qlo:qhi]), to(qt[qlo:qhi]), sub(ft), sub(fh))
+    allr = sharding.gather_query_shards(local, Q)
+    np.testing.assert_array_equal(allr.cpu().numpy(), want)
+    g = sharding.allgather_batch_ids(torch.full((6, 4), rank, dtype=torch.int64, device=dev))
+    assert g[0].tolist() == [0] * 4 + [1] * 4
+    dist.barrier()
+    dist.destroy_process_group()
+    open(os.path.join(tmp, "ok%d" % rank), "w").write("ok")
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_row_sharded_and_query_sharded_eval_nccl(tmp_path):
+    world = 2
+    mp.start_processes(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True,
+                       start_method="spawn")
+    assert all(os.path.exists(os.path.join(str(tmp_path), "ok%d" % r)) for r in range(world))

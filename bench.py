@@ -287,7 +287,7 @@ def run_cuda(args):
     sweep_ms /= reps
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
-        return
+        return None
     peak, peak_src, sm_max = peaks()
     alg_bytes = ALG_BYTES_PER_CANDIDATE * w["Q"] * w["N"]
     achieved = alg_bytes / (sweep_ms * 1e-3) / 1e9
@@ -318,7 +318,10 @@ def run_cuda(args):
         "clocks": clocks,
         "roofline": {"kernel": "1-vs-all sweep (tail direction, Q=512 x N=14541)", "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "peak_source": peak_src, "traffic": None, "launch_ms": sweep_ms,
+                     "peak_source": peak_src,
+                     # dram__bytes_read+write of one sweep_tiled_kernel launch, ncu --set full
+                     # (profiles/r1_ncu_sweep_tiled_v1_summary.txt)
+                     "traffic": 12121344, "launch_ms": sweep_ms,
                      "algorithmic_bytes_per_launch": alg_bytes,
                      "note": "algorithmic bytes = the reference-equivalent streaming formulation (one 800-byte "
                              "row per scored candidate, SURVEY.md 8d); a sweep that batches queries re-uses "
@@ -327,7 +330,7 @@ def run_cuda(args):
                                    "peak_tlops": fp32_peak / 1e12, "frac": lane_ops / (sweep_ms * 1e-3) / fp32_peak}},
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    return line
 
 
 # ------------------------------------------------------------------ CPU reference arm ----
@@ -441,7 +444,7 @@ def cpu_baseline(sample_train, sample_queries):
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return
+        return None
     w = WORKLOAD
     # each step: a bounded sample (1 train step + 2 test triples), extrapolated to the step composition
     per_step_queries = 2
@@ -471,7 +474,7 @@ def run_reference(args):
                          "train_step_ms": t_train * 1e3, "eval_ms_per_test_triple": t_query * 1e3},
         "e2e": {"value": value, "unit": "triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    return line
 
 
 def main():
@@ -484,10 +487,26 @@ def main():
                     help="profiling aid: only the HBM-resident leg (no e2e / CPU baseline); never a bench value")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_cuda(args)
+    # stdout carries exactly ONE JSON line: while the run is in progress fd 1 points at stderr so
+    # that banners printed by native libraries (e.g. NCCL's version line) cannot end up there
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    line = None
+    try:
+        line = run_reference(args) if args.impl == "reference" else run_cuda(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
 
 
 if __name__ == "__main__":

@@ -59,7 +59,10 @@ enum kge_model_id {
   KGE_CP = 8,       /* [sub, rel, obj]                  pointwise.py:374-376 */
   KGE_SIMPLE = 9,   /* [ent_h, ent_t, rel, rel_inv]     pointwise.py:522-526 */
   KGE_TRANSM = 10,  /* [ent, rel, theta(R x 1)]         pairwise.py:325-347 */
-  KGE_NUM_MODELS = 11
+  KGE_RESCAL = 11,  /* [ent, rel_matrices(R x d*d)]     pairwise.py:829-865 */
+  KGE_ANALOGY = 12, /* reserved (not implemented)       pointwise.py:97-104 */
+  KGE_SIMPLE_IGNR = 13, /* [ent_h, ent_t, rel, rel_inv]  pointwise.py:573-581 */
+  KGE_NUM_MODELS = 14
 };
 
 /* Which two operands are combined first.  TAIL: (h,r) are the
@@ -99,6 +102,11 @@ int kge_score_fwd(const kge_model_t* m, int grouping, const int64_t* h, const in
  * into it (caller zeroes).  grad_tables[k] may be NULL to skip a table. */
 int kge_score_bwd(const kge_model_t* m, const int64_t* h, const int64_t* r, const int64_t* t,
                   int64_t n, const float* grad_scores, float* const* grad_tables, void* stream);
+
+/* Rescal.embed's side effect (pairwise.py:843-844, get_normalized_data :862-865): every row of
+ * a [rows, width] table divided by its L2 norm, IN PLACE (no epsilon).  Call it on the entity
+ * and relation-matrix tables before scoring, as the reference's forward() does. */
+int kge_normalize_rows(float* table, int64_t rows, int64_t width, void* stream);
 
 /* ---- losses: replace pykg2vec/utils/criterion.py ------------------------
  * Each call writes the scalar loss to loss_out[0] and, when the grad pointers

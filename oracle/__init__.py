@@ -24,7 +24,8 @@ _SO = os.path.join(_OUT_DIR, "libkge_oracle.so")
 
 MODEL_IDS = {
     "transe": 0, "transh": 1, "transd": 2, "transr": 3, "rotate": 4, "hole": 5,
-    "distmult": 6, "complex": 7, "cp": 8, "simple": 9, "transm": 10,
+    "distmult": 6, "complex": 7, "cp": 8, "simple": 9, "transm": 10, "rescal": 11, "analogy": 12,
+    "simple_ignr": 13,
 }
 GROUP_TAIL, GROUP_HEAD = 0, 1
 MAX_TABLES = 6
@@ -90,7 +91,7 @@ class Model:
         # RotatE: theta = r / (embedding_range / pi)  (pairwise.py:748,776-782)
         self.phase_scale = float(np.float32(np.pi / embedding_range)) if embedding_range else 0.0
         self.num_ent = self.tables[0].shape[0]
-        rel_index = {"rotate": 2, "complex": 2}.get(self.name, 1)
+        rel_index = {"rotate": 2, "complex": 2, "simple": 2, "simple_ignr": 2}.get(self.name, 1)
         self.num_rel = self.tables[rel_index].shape[0]
 
     def c_struct(self):
@@ -164,6 +165,19 @@ def loss_selfadv(pos, neg, neg_rate, alpha):
     lib().kgeo_loss_selfadv(_ptr(pos), _ptr(neg), ctypes.c_int64(pos.shape[0]),
                             ctypes.c_int32(neg_rate), ctypes.c_float(alpha), _ptr(out))
     return float(out[0])
+
+
+def normalize_rows(table):
+    """in-place Rescal row normalisation of a contiguous fp32 [rows, width] numpy array"""
+    assert table.dtype == np.float32 and table.flags["C_CONTIGUOUS"]
+    lib().kgeo_normalize_rows(_ptr(table), ctypes.c_int64(table.shape[0]), ctypes.c_int64(table.shape[1]))
+    return table
+
+
+def expf(x):
+    lib().kgeo_expf.restype = ctypes.c_float
+    lib().kgeo_expf.argtypes = [ctypes.c_float]
+    return lib().kgeo_expf(ctypes.c_float(x))
 
 
 def sincosf(x):

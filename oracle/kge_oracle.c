@@ -38,7 +38,7 @@
 #define KGE_MAX_TABLES 6
 enum { KGE_TRANSE = 0, KGE_TRANSH = 1, KGE_TRANSD = 2, KGE_TRANSR = 3, KGE_ROTATE = 4,
        KGE_HOLE = 5, KGE_DISTMULT = 6, KGE_COMPLEX = 7, KGE_CP = 8, KGE_SIMPLE = 9,
-       KGE_TRANSM = 10 };
+       KGE_TRANSM = 10, KGE_RESCAL = 11, KGE_ANALOGY = 12, KGE_SIMPLE_IGNR = 13 };
 enum { KGE_GROUP_TAIL = 0, KGE_GROUP_HEAD = 1 };
 
 typedef struct kge_model {
@@ -103,6 +103,26 @@ void kgeo_sincosf(float x, float* sn, float* cs) {
   }
   *sn = so; *cs = co;
 }
+
+/* ---------------------------------------------- canonical exp / sigmoid ------ */
+/* Cephes expf: k = rint(x*log2e); r = x - k*ln2 (two parts); degree-5 polynomial; scale by 2^k
+ * built from the exponent bits.  x is clamped to [-87, 87].  Pure fmaf: identical on the GPU. */
+float kgeo_expf(float x) {
+  x = fminf(fmaxf(x, -87.0f), 87.0f);
+  const float k = rintf(x * 1.44269504088896341f);
+  float r = fmaf(-k, 0.693359375f, x);
+  r = fmaf(-k, -2.12194440e-4f, r);
+  float p = fmaf(r, 1.9875691500e-4f, 1.3981999507e-3f);
+  p = fmaf(p, r, 8.3334519073e-3f);
+  p = fmaf(p, r, 4.1665795894e-2f);
+  p = fmaf(p, r, 1.6666665459e-1f);
+  p = fmaf(p, r, 5.0000001201e-1f);
+  const float y = fmaf(p, r * r, r) + 1.0f;
+  union { uint32_t u; float f; } two_k;
+  two_k.u = (uint32_t)((int)k + 127) << 23;
+  return y * two_k.f;
+}
+float kgeo_sigmoidf(float x) { return 1.0f / (1.0f + kgeo_expf(-x)); }
 
 /* ------------------------------------------------------- per-model score -- */
 static const float* row(const kge_model_t* m, int k, int64_t i, int width) {
@@ -222,8 +242,105 @@ static float score_one(const kge_model_t* m, int grouping, int64_t h, int64_t r,
       }
       return -rs_finish(&s);
     }
+    case KGE_HOLE: {
+      /* HoLE.forward pairwise.py:1119-1125 AS WRITTEN for torch<1.7 (torch.conj is a no-op on the
+       * real [.,2] view and `*` multiplies (re,im) pairs elementwise), which evaluates
+       *   e = circconv(even(h), even(t)),  even(x)[n] = (x[n] + x[(d-n)%d]) / 2,
+       *   score = -sigmoid(sum_k r^_k e_k)          
+       * re-associated so that the query side is combined first:
+       *   TAIL: g[m] = sum_n eh[n] r^[(m+n)%d] (sequential n);  s = RSUM_m g[m] * et[m]
+       *   HEAD: g[n] = sum_m et[m] r^[(m+n)%d] (sequential m);  s = RSUM_n eh[n] * g[n] */
+      const float *hv = row(m, 0, h, d), *rv = row(m, 1, r, d), *tv = row(m, 0, t, d);
+      float *rn = scratch, *eh = scratch + d, *et = scratch + 2 * d, *g = scratch + 3 * d;
+      const float ir = inv_norm(rv, d);
+      for (int j = 0; j < d; ++j) {
+        rn[j] = rv[j] * ir;
+        eh[j] = 0.5f * (hv[j] + hv[(d - j) % d]);
+        et[j] = 0.5f * (tv[j] + tv[(d - j) % d]);
+      }
+      const float* qe = (grouping == KGE_GROUP_TAIL) ? eh : et;   /* query-side even part */
+      const float* ce = (grouping == KGE_GROUP_TAIL) ? et : eh;   /* candidate-side even part */
+      for (int a = 0; a < d; ++a) {
+        float acc = 0.0f;
+        for (int b = 0; b < d; ++b) acc = fmaf(qe[b], rn[(a + b) % d], acc);
+        g[a] = acc;
+      }
+      rsum_t s; rs_init(&s);
+      for (int j = 0; j < d; ++j) {
+        float* p = rs_at(&s, j);
+        if (grouping == KGE_GROUP_TAIL) *p = fmaf(g[j], ce[j], *p); else *p = fmaf(ce[j], g[j], *p);
+      }
+      return -kgeo_sigmoidf(rs_finish(&s));
+    }
+    case KGE_RESCAL: {
+      /* Rescal.forward pairwise.py:829-865 on tables that embed() has row-normalised in place
+       * (the normalisation is a separate entry point: it mutates the weights, :843-844):
+       *   score = - h^T M_r t,   M_r = rel_matrices[r].view(d, d)
+       *   TAIL: v_k = sum_j h_j M[j,k] (sequential j);  s = RSUM_k v_k t_k
+       *   HEAD: u_j = sum_k M[j,k] t_k (sequential k);  s = RSUM_j h_j u_j */
+      const float *hv = row(m, 0, h, d), *tv = row(m, 0, t, d);
+      const float* M = row(m, 1, r, d * d);
+      float* v = scratch;
+      rsum_t s; rs_init(&s);
+      if (grouping == KGE_GROUP_TAIL) {
+        for (int k = 0; k < d; ++k) v[k] = 0.0f;
+        for (int j = 0; j < d; ++j)
+          for (int k = 0; k < d; ++k) v[k] = fmaf(hv[j], M[(size_t)j * d + k], v[k]);
+        for (int k = 0; k < d; ++k) { float* p = rs_at(&s, k); *p = fmaf(v[k], tv[k], *p); }
+      } else {
+        for (int j = 0; j < d; ++j) {
+          float acc = 0.0f;
+          for (int k = 0; k < d; ++k) acc = fmaf(M[(size_t)j * d + k], tv[k], acc);
+          v[j] = acc;
+        }
+        for (int j = 0; j < d; ++j) { float* p = rs_at(&s, j); *p = fmaf(hv[j], v[j], *p); }
+      }
+      return -rs_finish(&s);
+    }
+    case KGE_SIMPLE:
+    case KGE_SIMPLE_IGNR: {
+      /* SimplE.forward pointwise.py:522-526: init = sum(h1 r1 t1) + sum(h2 r2 t2) / 2 (only the second
+       * sum is halved — operator precedence), score = -clamp(init, -20, 20); SimplE_ignr.forward
+       * :573-581 has no halving.  tables [ent_head, ent_tail, rel, rel_inv];
+       * h1 = ent_head[h], t1 = ent_tail[t], h2 = ent_head[t], t2 = ent_tail[h] (:514-519).
+       * One interleaved accumulator; the halving is folded into the query-side factor (exact). */
+      const float half = (m->model == KGE_SIMPLE) ? 0.5f : 1.0f;
+      const float *h1 = row(m, 0, h, d), *t2 = row(m, 1, h, d), *h2 = row(m, 0, t, d), *t1 = row(m, 1, t, d);
+      const float *r1 = row(m, 2, r, d), *r2 = row(m, 3, r, d);
+      rsum_t s; rs_init(&s);
+      for (int j = 0; j < d; ++j) {
+        float* p = rs_at(&s, j);
+        if (grouping == KGE_GROUP_TAIL) {  /* query (h, r): q1 = h1 r1, q2 = half t2 r2 */
+          const float q1 = h1[j] * r1[j];
+          const float q2 = (t2[j] * r2[j]) * half;
+          *p = fmaf(q1, t1[j], *p);
+          *p = fmaf(q2, h2[j], *p);
+        } else {                           /* query (r, t): q1 = r1 t1, q2 = half r2 h2 */
+          const float q1 = r1[j] * t1[j];
+          const float q2 = (r2[j] * h2[j]) * half;
+          *p = fmaf(h1[j], q1, *p);
+          *p = fmaf(t2[j], q2, *p);
+        }
+      }
+      const float init = rs_finish(&s);
+      return -fminf(fmaxf(init, -20.0f), 20.0f);
+    }
     default: return NAN;
   }
+}
+
+/* Rescal.get_normalized_data pairwise.py:862-865: every row divided by its L2 norm (no epsilon),
+ * applied in place to a [rows, width] table. */
+int kgeo_normalize_rows(float* table, int64_t rows, int64_t width) {
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < rows; ++i) {
+    float* x = table + i * width;
+    rsum_t s; rs_init(&s);
+    for (int64_t j = 0; j < width; ++j) { float* p = rs_at(&s, (int)j); *p = fmaf(x[j], x[j], *p); }
+    const float inv = 1.0f / sqrtf(rs_finish(&s));
+    for (int64_t j = 0; j < width; ++j) x[j] = x[j] * inv;
+  }
+  return 0;
 }
 
 static int scratch_floats(const kge_model_t* m) {

@@ -77,6 +77,27 @@ def score(name, tables, h, r, t, l1_flag=False, margin=0.0, embedding_range=None
         ere, eim, rre, rim = tables
         hr, hi, tr, ti, rr, ri = ere[h], eim[h], ere[t], eim[t], rre[r], rim[r]
         return -torch.sum(hr * tr * rr + hi * ti * rr + hr * ti * ri - hi * tr * ri, -1)
+    if name == "rescal":  # pairwise.py:829-865, on tables already row-normalised by embed()
+        ent, mat = tables
+        d = ent.shape[1]
+        m = mat[r].view(-1, d, d)
+        return -torch.sum(ent[h].unsqueeze(2) * torch.matmul(m, ent[t].unsqueeze(2)), [1, 2])
+    if name in ("simple", "simple_ignr"):  # pointwise.py:514-526, 573-581
+        eh, et, rel, rinv = tables
+        first = torch.sum(eh[h] * rel[r] * et[t], 1)
+        second = torch.sum(eh[t] * rinv[r] * et[h], 1)
+        init = first + second / 2.0 if name == "simple" else first + second
+        return -torch.clamp(init, -20, 20)
+    if name == "hole":
+        # pairwise.py:1119-1125 as evaluated by torch<1.7 (legacy fft on [b,d,2] views, conj a no-op on
+        # real tensors, elementwise product of the (re, im) pairs) -- see tests/golden/make_golden.py
+        ent, rel = tables
+        rn = F.normalize(rel[r], p=2, dim=-1)
+        cdt = torch.complex128 if ent.dtype == torch.float64 else torch.complex64
+        fh = torch.fft.fft(ent[h].to(cdt), dim=1)
+        ft = torch.fft.fft(ent[t].to(cdt), dim=1)
+        e = torch.fft.ifft(torch.complex(fh.real * ft.real, fh.imag * ft.imag), dim=1).real
+        return -torch.sigmoid(torch.sum(rn * e, 1))
     raise NotImplementedError(name)
 
 

@@ -19,10 +19,14 @@ MODEL_MAP = {
     "transm": ("pykg2vec_b200.pairwise", "TransM"),
     "transr": ("pykg2vec_b200.pairwise", "TransR"),
     "rotate": ("pykg2vec_b200.pairwise", "RotatE"),
+    "rescal": ("pykg2vec_b200.pairwise", "Rescal"),
+    "hole": ("pykg2vec_b200.pairwise", "HoLE"),
     "distmult": ("pykg2vec_b200.pointwise", "DistMult"),
     "cp": ("pykg2vec_b200.pointwise", "CP"),
     "complex": ("pykg2vec_b200.pointwise", "Complex"),
     "complexn3": ("pykg2vec_b200.pointwise", "ComplexN3"),
+    "simple": ("pykg2vec_b200.pointwise", "SimplE"),
+    "simple_ignr": ("pykg2vec_b200.pointwise", "SimplE_ignr"),
 }
 
 

@@ -15,7 +15,8 @@ ABI_VERSION = 1
 
 MODEL_IDS = {
     "transe": 0, "transh": 1, "transd": 2, "transr": 3, "rotate": 4, "hole": 5,
-    "distmult": 6, "complex": 7, "cp": 8, "simple": 9, "transm": 10,
+    "distmult": 6, "complex": 7, "cp": 8, "simple": 9, "transm": 10, "rescal": 11, "analogy": 12,
+    "simple_ignr": 13,
 }
 GROUP_TAIL, GROUP_HEAD = 0, 1
 RANK_FORCE_GATHER, RANK_TAIL_ONLY, RANK_HEAD_ONLY = 1, 2, 4
@@ -23,7 +24,7 @@ RANK_FORCE_GATHER, RANK_TAIL_ONLY, RANK_HEAD_ONLY = 1, 2, 4
 # every symbol include/kge_b200.h declares (tests check they are all exported)
 EXPORTS = [
     "kge_abi_version", "kge_version", "kge_last_error", "kge_launch_count",
-    "kge_score_fwd", "kge_score_bwd",
+    "kge_score_fwd", "kge_score_bwd", "kge_normalize_rows",
     "kge_loss_pairwise_hinge", "kge_loss_pointwise_logistic", "kge_loss_selfadv", "kge_reg_fwd_bwd",
     "kge_train_pairwise_hinge_sgd", "kge_optim_apply_rows",
     "kge_rank_workspace_bytes", "kge_rank_1vsall",
@@ -107,7 +108,7 @@ class ModelDesc:
         self.l1_flag = bool(l1_flag)
         self.margin = float(margin)
         self.phase_scale = float(phase_scale)
-        rel_index = {"rotate": 2, "complex": 2}.get(self.name, 1)
+        rel_index = {"rotate": 2, "complex": 2, "simple": 2, "simple_ignr": 2}.get(self.name, 1)
         self.num_ent = int(num_ent if num_ent is not None else self.tables[0].shape[0])
         self.num_rel = int(num_rel if num_rel is not None else self.tables[rel_index].shape[0])
 
@@ -147,6 +148,14 @@ def score_bwd(desc, h, r, t, grad_scores, grad_tables):
     arr = _table_ptr_array(grad_tables)
     check(lib().kge_score_bwd(ctypes.byref(m), _ptr(h), _ptr(r), _ptr(t), ctypes.c_int64(h.numel()),
                               _ptr(_dev_f32(grad_scores, "grad_scores")), arr, _stream()), "kge_score_bwd")
+
+
+def normalize_rows(table):
+    """Rescal.get_normalized_data (pairwise.py:862-865): rows / ||row||_2, IN PLACE."""
+    t = _dev_f32(table, "table")
+    check(lib().kge_normalize_rows(_ptr(t), ctypes.c_int64(t.shape[0]), ctypes.c_int64(t.shape[1]), _stream()),
+          "kge_normalize_rows")
+    return table
 
 
 def loss_pairwise_hinge(pos, neg, margin, want_grad=True):

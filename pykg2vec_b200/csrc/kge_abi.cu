@@ -37,9 +37,9 @@ int sm_count() {
 
 int num_tables(int model) {
   switch (model) {
-    case KGE_TRANSE: case KGE_DISTMULT: case KGE_HOLE: return 2;
+    case KGE_TRANSE: case KGE_DISTMULT: case KGE_HOLE: case KGE_RESCAL: return 2;
     case KGE_TRANSH: case KGE_TRANSR: case KGE_ROTATE: case KGE_CP: case KGE_TRANSM: return 3;
-    case KGE_TRANSD: case KGE_COMPLEX: case KGE_SIMPLE: return 4;
+    case KGE_TRANSD: case KGE_COMPLEX: case KGE_SIMPLE: case KGE_SIMPLE_IGNR: return 4;
     default: return 0;
   }
 }

@@ -91,6 +91,22 @@ KGE_DEV void sincos_canon(float x, float& sn, float& cs) {
   cs = ((q + 1) & 2) ? -co : co;
 }
 
+// Canonical exp / sigmoid (Cephes expf in explicit fma; bit-identical to oracle/kge_oracle.c)
+KGE_DEV float exp_canon(float x) {
+  x = fminf(fmaxf(x, -87.0f), 87.0f);
+  const float k = rintf(fmul(x, 1.44269504088896341f));
+  float r = ffma(-k, 0.693359375f, x);
+  r = ffma(-k, -2.12194440e-4f, r);
+  float p = ffma(r, 1.9875691500e-4f, 1.3981999507e-3f);
+  p = ffma(p, r, 8.3334519073e-3f);
+  p = ffma(p, r, 4.1665795894e-2f);
+  p = ffma(p, r, 1.6666665459e-1f);
+  p = ffma(p, r, 5.0000001201e-1f);
+  const float y = fadd(ffma(p, fmul(r, r), r), 1.0f);
+  return fmul(y, __uint_as_float((unsigned)((int)k + 127) << 23));
+}
+KGE_DEV float sigmoid_canon(float x) { return __frcp_rn(fadd(1.0f, exp_canon(-x))); }
+
 // One 4-element chunk c of a row of width d (elements 4c..4c+3; elements >= d read as 0,
 // which is an exact identity for every accumulation used here).
 template <int VEC>

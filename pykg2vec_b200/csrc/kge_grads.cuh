@@ -42,6 +42,13 @@ KGE_DEV void resolve_grad_rows(GradRows& G, const ModelParams& P, float* const* 
   } else if (MODEL == KGE_COMPLEX) {
     G.h[0] = at(0, h * d); G.h[1] = at(1, h * d); G.t[0] = at(0, t * d); G.t[1] = at(1, t * d);
     G.r[0] = at(2, r * d); G.r[1] = at(3, r * d);
+  } else if (MODEL == KGE_HOLE) {
+    G.h[0] = at(0, h * d); G.t[0] = at(0, t * d); G.r[0] = at(1, r * d);
+  } else if (MODEL == KGE_RESCAL) {
+    G.h[0] = at(0, h * d); G.t[0] = at(0, t * d); G.r[0] = at(1, r * d * d);
+  } else if (MODEL == KGE_SIMPLE || MODEL == KGE_SIMPLE_IGNR) {
+    G.h[0] = at(0, h * d); G.h[1] = at(1, h * d); G.t[0] = at(1, t * d); G.t[1] = at(0, t * d);
+    G.r[0] = at(2, r * d); G.r[1] = at(3, r * d);
   }
 }
 
@@ -394,6 +401,154 @@ KGE_DEV void grad_group(const TripleRows& R, const GradRows& G, const ModelParam
       red_row_chunk<VEC>(G.t[0], c, d, gtr);
       red_row_chunk<VEC>(G.t[1], c, d, gti);
     }
+  } else if (MODEL == KGE_SIMPLE || MODEL == KGE_SIMPLE_IGNR) {
+    const float half = (MODEL == KGE_SIMPLE) ? 0.5f : 1.0f;
+    float acc = 0.f;
+    for (int c = lane; c < nch; c += 8) {
+      const float4 h1 = ld_chunk<VEC>(R.h[0], c, d), t2 = ld_chunk<VEC>(R.h[1], c, d),
+                   t1 = ld_chunk<VEC>(R.t[0], c, d), h2 = ld_chunk<VEC>(R.t[1], c, d),
+                   r1 = ld_chunk<VEC>(R.r[0], c, d), r2 = ld_chunk<VEC>(R.r[1], c, d);
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        acc += f4_get(h1, e) * f4_get(r1, e) * f4_get(t1, e) + half * f4_get(h2, e) * f4_get(r2, e) * f4_get(t2, e);
+    }
+    const float init = group_sum(acc);
+    // -clamp(init, -20, 20): gradient passes only inside the clamp range (torch.clamp backward)
+    const float ng = (init >= -20.f && init <= 20.f) ? -gs : 0.f;
+    const float ngh = ng * half;
+    for (int c = lane; c < nch; c += 8) {
+      const float4 h1 = ld_chunk<VEC>(R.h[0], c, d), t2 = ld_chunk<VEC>(R.h[1], c, d),
+                   t1 = ld_chunk<VEC>(R.t[0], c, d), h2 = ld_chunk<VEC>(R.t[1], c, d),
+                   r1 = ld_chunk<VEC>(R.r[0], c, d), r2 = ld_chunk<VEC>(R.r[1], c, d);
+      float4 gh1, gt2, gt1, gh2, gr1, gr2;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        f4_at(gh1, e) = ng * f4_get(r1, e) * f4_get(t1, e);
+        f4_at(gr1, e) = ng * f4_get(h1, e) * f4_get(t1, e);
+        f4_at(gt1, e) = ng * f4_get(h1, e) * f4_get(r1, e);
+        f4_at(gh2, e) = ngh * f4_get(r2, e) * f4_get(t2, e);
+        f4_at(gr2, e) = ngh * f4_get(h2, e) * f4_get(t2, e);
+        f4_at(gt2, e) = ngh * f4_get(h2, e) * f4_get(r2, e);
+      }
+      red_row_chunk<VEC>(G.h[0], c, d, gh1);
+      red_row_chunk<VEC>(G.h[1], c, d, gt2);
+      red_row_chunk<VEC>(G.t[0], c, d, gt1);
+      red_row_chunk<VEC>(G.t[1], c, d, gh2);
+      red_row_chunk<VEC>(G.r[0], c, d, gr1);
+      red_row_chunk<VEC>(G.r[1], c, d, gr2);
+    }
+  } else if (MODEL == KGE_RESCAL) {
+    // s = -h^T M t:  dh_j = -gs (M t)_j ; dt_k = -gs (h^T M)_k ; dM_jk = -gs h_j t_k
+    const float* M = R.r[0];
+    const float ng = -gs;
+    for (int c = lane; c < nch; c += 8) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);   // (h^T M) chunk c
+      const float4 tc = ld_chunk<VEC>(R.t[0], c, d);
+      for (int j = 0; j < d; ++j) {
+        const float hj = __ldg(R.h[0] + j);
+        const float4 mrow = ld_chunk<VEC>(M + (size_t)j * d, c, d);
+        float4 gm;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          f4_at(v, e) += hj * f4_get(mrow, e);
+          f4_at(gm, e) = ng * hj * f4_get(tc, e);
+        }
+        if (G.r[0]) red_chunk<VEC>(G.r[0] + (size_t)j * d, c, d, gm);
+      }
+      float4 gt;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) f4_at(gt, e) = ng * f4_get(v, e);
+      red_row_chunk<VEC>(G.t[0], c, d, gt);
+    }
+    for (int c = lane; c < nch; c += 8) {           // (M t) rows j in chunk c
+      float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int kc = 0; kc < nch; ++kc) {
+        const float4 tv = ld_chunk<VEC>(R.t[0], kc, d);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = 4 * c + e;
+          if (j < d) {
+            const float4 mrow = ld_chunk<VEC>(M + (size_t)j * d, kc, d);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) f4_at(u, e) += f4_get(mrow, q) * f4_get(tv, q);
+          }
+        }
+      }
+      float4 gh;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) f4_at(gh, e) = ng * f4_get(u, e);
+      red_row_chunk<VEC>(G.h[0], c, d, gh);
+    }
+  } else if (MODEL == KGE_HOLE) {
+    // s = sum_k r^_k e_k, e = circconv(eh, et), score = -sigmoid(s).
+    // scratch: rn, eh, et, deh, det, dr  [dp each]
+    const int dp = nch * 4;
+    float *rn = scratch, *eh = rn + dp, *et = eh + dp, *deh = et + dp, *det = deh + dp, *drn = det + dp;
+    float sr = 0.f;
+    for (int c = lane; c < nch; c += 8) {
+      const float4 b = ld_chunk<VEC>(R.r[0], c, d);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sr = ffma(f4_get(b, e), f4_get(b, e), sr);
+    }
+    sr = group_sum(sr);
+    const float ir = inv_norm_from_sumsq(sr);
+    const bool clamp_r = __fsqrt_rn(sr) < 1e-12f;
+    for (int c = lane; c < nch; c += 8) {
+      const float4 b = ld_chunk<VEC>(R.r[0], c, d);
+      *reinterpret_cast<float4*>(rn + 4 * c) = make_float4(b.x * ir, b.y * ir, b.z * ir, b.w * ir);
+      *reinterpret_cast<float4*>(eh + 4 * c) = even_chunk(R.h[0], c, d);
+      *reinterpret_cast<float4*>(et + 4 * c) = even_chunk(R.t[0], c, d);
+    }
+    group_sync();
+    // deh[n] = sum_m et[m] rn[(m+n)%d]; det[m] = sum_n eh[n] rn[(m+n)%d]; drn[j] = sum_n eh[n] et[(j-n)%d]
+    float s_part = 0.f;
+    for (int c = lane; c < nch; c += 8) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int a = 4 * c + e;
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (a < d) {
+          int idx = a, back = a;
+          for (int b = 0; b < d; ++b) {
+            x += et[b] * rn[idx];
+            y += eh[b] * rn[idx];
+            z += eh[b] * et[back];
+            idx = (idx + 1 == d) ? 0 : idx + 1;
+            back = (back == 0) ? d - 1 : back - 1;
+          }
+          s_part += rn[a] * z;
+        }
+        deh[a] = x; det[a] = y; drn[a] = z;
+      }
+    }
+    const float sv = group_sum(s_part);
+    const float sg = 1.f / (1.f + expf(-sv));
+    const float gp = -gs * sg * (1.f - sg);
+    group_sync();
+    float rdot = 0.f;
+    for (int c = lane; c < nch; c += 8) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const int j = 4 * c + e; if (j < d) rdot += rn[j] * drn[j]; }
+    }
+    rdot = group_sum(rdot);
+    if (clamp_r) rdot = 0.f;
+    for (int c = lane; c < nch; c += 8) {
+      float4 gh, gt, gr;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = 4 * c + e;
+        if (j < d) {
+          const int jm = (j == 0) ? 0 : d - j;
+          f4_at(gh, e) = gp * 0.5f * (deh[j] + deh[jm]);
+          f4_at(gt, e) = gp * 0.5f * (det[j] + det[jm]);
+          f4_at(gr, e) = gp * (drn[j] - rn[j] * rdot) * ir;
+        } else { f4_at(gh, e) = 0.f; f4_at(gt, e) = 0.f; f4_at(gr, e) = 0.f; }
+      }
+      red_row_chunk<VEC>(G.h[0], c, d, gh);
+      red_row_chunk<VEC>(G.t[0], c, d, gt);
+      red_row_chunk<VEC>(G.r[0], c, d, gr);
+    }
+    group_sync();
   } else if (MODEL == KGE_TRANSR) {
     // h^ = h*ih; h'_k = sum_j h^_j M_jk; h'^ = normalise(h'); r^ = normalise(r) (then normalised
     // again inside the distance); x = h'^ + r^^ - t'^.   scratch: hp, tp, dhp, dtp [drp each],
@@ -510,6 +665,8 @@ KGE_DEV void grad_group(const TripleRows& R, const GradRows& G, const ModelParam
 
 // shared-memory floats one 8-lane group needs in the backward kernels
 inline size_t group_scratch_floats_bwd(const kge_model_t* m) {
+  if (m->model == KGE_HOLE) return 6 * (size_t)(((m->dim + 3) >> 2) * 4);
+  if (m->model == KGE_RESCAL) return group_scratch_floats(m);
   if (m->model != KGE_TRANSR) return 0;
   const size_t drp = (size_t)(((m->rel_dim + 3) >> 2) * 4), dp = (size_t)(((m->dim + 3) >> 2) * 4);
   return 4 * drp + 2 * dp;

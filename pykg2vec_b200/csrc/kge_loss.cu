@@ -157,12 +157,51 @@ reg_kernel(ModelParams P, GradTablesR GT, int reg_type, float scale, const int64
   }
 }
 
+// Rescal.get_normalized_data pairwise.py:862-865: row / ||row||_2, in place, no epsilon.
+// One warp per row (rows of the relation-matrix table are d*d wide).
+__global__ void __launch_bounds__(256)
+normalize_rows_kernel(float* __restrict__ table, int64_t rows, int64_t width) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float* x = table + row * width;
+  // canonical RSUM: element j -> partial (j>>2)&7; lanes 0..7 own the partials, the other 24 lanes
+  // help by handling the same partial for later chunks: lane l takes chunks c = l, l+32, ... whose
+  // partial index is l&7; per-partial order must stay increasing in j, so partial p is summed by
+  // lanes p, p+8, p+16, p+24 over disjoint, INTERLEAVED chunk sets -> not the canonical order.
+  // Canonical order therefore uses 8 lanes per row; the remaining lanes only help with the scaling.
+  float s = 0.f;
+  if (lane < 8) {
+    const int64_t nch = (width + 3) >> 2;
+    for (int64_t c = lane; c < nch; c += 8) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int64_t j = 4 * c + e;
+        if (j < width) s = ffma(x[j], x[j], s);
+      }
+    }
+  }
+  s = fadd(s, __shfl_xor_sync(0xffffffffu, s, 4));
+  s = fadd(s, __shfl_xor_sync(0xffffffffu, s, 2));
+  s = fadd(s, __shfl_xor_sync(0xffffffffu, s, 1));
+  s = __shfl_sync(0xffffffffu, s, 0);
+  const float inv = __frcp_rn(__fsqrt_rn(s));
+  for (int64_t j = lane; j < width; j += 32) x[j] = fmul(x[j], inv);
+}
+
 int check_model(const kge_model_t* m);
 int model_vec(const kge_model_t* m);
 
 }  // namespace kge
 
 using namespace kge;
+
+extern "C" int kge_normalize_rows(float* table, int64_t rows, int64_t width, void* stream) {
+  if (!table || rows <= 0 || width <= 0) { set_error("kge_normalize_rows: bad arguments"); return KGE_EINVAL; }
+  normalize_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(table, rows, width);
+  KGE_CHECK_LAUNCH("normalize_rows_kernel");
+  return KGE_OK;
+}
 
 extern "C" int kge_loss_pairwise_hinge(const float* pos, const float* neg, int64_t n, float margin,
                                        float* loss_out, float* grad_pos, float* grad_neg, void* stream) {

@@ -48,6 +48,55 @@ KGE_DEV void resolve_rows(TripleRows& R, const ModelParams& P, const float* cons
     R.h[0] = htab[0] + h * d; R.h[1] = htab[1] + h * d;
     R.t[0] = ttab[0] + t * d; R.t[1] = ttab[1] + t * d;
     R.r[0] = rtab[2] + r * d; R.r[1] = rtab[3] + r * d;
+  } else if (MODEL == KGE_HOLE) {
+    R.h[0] = htab[0] + h * d; R.t[0] = ttab[0] + t * d; R.r[0] = rtab[1] + r * d;
+  } else if (MODEL == KGE_RESCAL) {
+    R.h[0] = htab[0] + h * d; R.t[0] = ttab[0] + t * d; R.r[0] = rtab[1] + r * d * d;
+  } else if (MODEL == KGE_SIMPLE || MODEL == KGE_SIMPLE_IGNR) {
+    // h1 = ent_head[h], t2 = ent_tail[h]; t1 = ent_tail[t], h2 = ent_head[t] (pointwise.py:514-519)
+    R.h[0] = htab[0] + h * d; R.h[1] = htab[1] + h * d;
+    R.t[0] = ttab[1] + t * d; R.t[1] = ttab[0] + t * d;
+    R.r[0] = rtab[2] + r * d; R.r[1] = rtab[3] + r * d;
+  }
+}
+
+// group-scoped barrier for shared-memory scratch shared by the 8 lanes of a group
+KGE_DEV void group_sync() { __syncwarp(group_mask()); }
+
+// even part of a row: (x[j] + x[(d-j)%d]) / 2 for the 4 elements of chunk c (zero beyond d)
+KGE_DEV float4 even_chunk(const float* __restrict__ row, int c, int d) {
+  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int j = 4 * c + e;
+    if (j < d) {
+      const int jm = (j == 0) ? 0 : d - j;
+      f4_at(o, e) = fmul(0.5f, fadd(__ldg(row + j), __ldg(row + jm)));
+    }
+  }
+  return o;
+}
+
+// HoLE query-side vector  g[a] = sum_b qe[b] * rn[(a+b)%d]  (sequential b) for the lane's chunks;
+// qe / rn / g live in the group's shared scratch (each d_pad floats).  pairwise.py:1119-1125 as
+// written for torch<1.7, re-associated (see oracle/kge_oracle.c KGE_HOLE).
+KGE_DEV void hole_query_vector(const float* qe, const float* rn, float* g, int d, int nch, int lane) {
+  for (int c = lane; c < nch; c += 8) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int a = 4 * c + e;
+      if (a < d) {
+        float s = 0.f;
+        int idx = a;
+        for (int b = 0; b < d; ++b) {
+          s = ffma(qe[b], rn[idx], s);
+          idx = (idx + 1 == d) ? 0 : idx + 1;
+        }
+        f4_at(acc, e) = s;
+      }
+    }
+    *reinterpret_cast<float4*>(g + 4 * c) = acc;
   }
 }
 
@@ -301,6 +350,103 @@ KGE_DEV float score_group(const TripleRows& R, const ModelParams& P, int lane, f
       }
     }
     return -group_sum(acc);
+  } else if (MODEL == KGE_HOLE) {
+    // scratch: rn[dp], qe[dp], g[dp]
+    const int dp = nch * 4;
+    float *rn = scratch, *qe = scratch + dp, *g = scratch + 2 * dp;
+    float sr = 0.f;
+    for (int c = lane; c < nch; c += 8) {
+      const float4 b = ld_chunk<VEC>(R.r[0], c, d);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sr = ffma(f4_get(b, e), f4_get(b, e), sr);
+    }
+    const float ir = inv_norm_from_sumsq(group_sum(sr));
+    const float* qrow = (GROUPING == KGE_GROUP_TAIL) ? R.h[0] : R.t[0];
+    const float* crow = (GROUPING == KGE_GROUP_TAIL) ? R.t[0] : R.h[0];
+    for (int c = lane; c < nch; c += 8) {
+      const float4 b = ld_chunk<VEC>(R.r[0], c, d);
+      *reinterpret_cast<float4*>(rn + 4 * c) = make_float4(fmul(b.x, ir), fmul(b.y, ir), fmul(b.z, ir), fmul(b.w, ir));
+      *reinterpret_cast<float4*>(qe + 4 * c) = even_chunk(qrow, c, d);
+    }
+    group_sync();
+    hole_query_vector(qe, rn, g, d, nch, lane);
+    float acc = 0.f;
+    for (int c = lane; c < nch; c += 8) {
+      const float4 gv = *reinterpret_cast<const float4*>(g + 4 * c);
+      const float4 ce = even_chunk(crow, c, d);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc = ffma(f4_get(gv, e), f4_get(ce, e), acc);
+    }
+    group_sync();  // scratch may be reused by the caller's next evaluation
+    return -sigmoid_canon(group_sum(acc));
+  } else if (MODEL == KGE_RESCAL) {
+    // scratch: v[dp].  TAIL: v = h^T M (sequential j), s = RSUM v.t ; HEAD: u = M t (sequential k), s = RSUM h.u
+    const float* M = R.r[0];
+    float* v = scratch;
+    if (GROUPING == KGE_GROUP_TAIL) {
+      for (int c = lane; c < nch; c += 8) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < d; ++j) {
+          const float hj = __ldg(R.h[0] + j);
+          const float4 mrow = ld_chunk<VEC>(M + (size_t)j * d, c, d);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) f4_at(a, e) = ffma(hj, f4_get(mrow, e), f4_get(a, e));
+        }
+        *reinterpret_cast<float4*>(v + 4 * c) = a;
+      }
+    } else {
+      for (int c = lane; c < nch; c += 8) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int kc = 0; kc < nch; ++kc) {
+          const float4 tv = ld_chunk<VEC>(R.t[0], kc, d);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = 4 * c + e;
+            if (j < d) {
+              const float4 mrow = ld_chunk<VEC>(M + (size_t)j * d, kc, d);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) f4_at(a, e) = ffma(f4_get(mrow, q), f4_get(tv, q), f4_get(a, e));
+            }
+          }
+        }
+        *reinterpret_cast<float4*>(v + 4 * c) = a;
+      }
+    }
+    const float* other = (GROUPING == KGE_GROUP_TAIL) ? R.t[0] : R.h[0];
+    float acc = 0.f;
+    for (int c = lane; c < nch; c += 8) {
+      const float4 a = *reinterpret_cast<const float4*>(v + 4 * c);
+      const float4 o = ld_chunk<VEC>(other, c, d);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc = ffma(f4_get(a, e), f4_get(o, e), acc);
+    }
+    return -group_sum(acc);
+  } else if (MODEL == KGE_SIMPLE || MODEL == KGE_SIMPLE_IGNR) {
+    // SimplE.forward pointwise.py:522-526 / SimplE_ignr.forward :573-581
+    const float half = (MODEL == KGE_SIMPLE) ? 0.5f : 1.0f;
+    float acc = 0.f;
+#pragma unroll 2
+    for (int c = lane; c < nch; c += 8) {
+      const float4 h1 = ld_chunk<VEC>(R.h[0], c, d), t2 = ld_chunk<VEC>(R.h[1], c, d),
+                   t1 = ld_chunk<VEC>(R.t[0], c, d), h2 = ld_chunk<VEC>(R.t[1], c, d),
+                   r1 = ld_chunk<VEC>(R.r[0], c, d), r2 = ld_chunk<VEC>(R.r[1], c, d);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (GROUPING == KGE_GROUP_TAIL) {
+          const float q1 = fmul(f4_get(h1, e), f4_get(r1, e));
+          const float q2 = fmul(fmul(f4_get(t2, e), f4_get(r2, e)), half);
+          acc = ffma(q1, f4_get(t1, e), acc);
+          acc = ffma(q2, f4_get(h2, e), acc);
+        } else {
+          const float q1 = fmul(f4_get(r1, e), f4_get(t1, e));
+          const float q2 = fmul(fmul(f4_get(r2, e), f4_get(h2, e)), half);
+          acc = ffma(f4_get(h1, e), q1, acc);
+          acc = ffma(f4_get(t2, e), q2, acc);
+        }
+      }
+    }
+    const float init = group_sum(acc);
+    return -fminf(fmaxf(init, -20.0f), 20.0f);
   }
   return 0.f;
 }
@@ -317,6 +463,9 @@ constexpr bool is_distance_model(int model) {
 
 // shared-memory floats one 8-lane group needs (TransR only)
 inline size_t group_scratch_floats(const kge_model_t* m) {
+  const size_t dp = (size_t)(((m->dim + 3) >> 2) * 4);
+  if (m->model == KGE_HOLE) return 3 * dp;
+  if (m->model == KGE_RESCAL) return dp;
   if (m->model != KGE_TRANSR) return 0;
   return (size_t)2 * (size_t)(((m->rel_dim + 3) >> 2) * 4);
 }
@@ -334,6 +483,10 @@ inline size_t group_scratch_floats(const kge_model_t* m) {
       case KGE_COMPLEX: KGE_DISPATCH_VEC(KGE_COMPLEX, vec, CALL); break;           \
       case KGE_CP: KGE_DISPATCH_VEC(KGE_CP, vec, CALL); break;                     \
       case KGE_TRANSM: KGE_DISPATCH_VEC(KGE_TRANSM, vec, CALL); break;             \
+      case KGE_HOLE: KGE_DISPATCH_VEC(KGE_HOLE, vec, CALL); break;                 \
+      case KGE_RESCAL: KGE_DISPATCH_VEC(KGE_RESCAL, vec, CALL); break;             \
+      case KGE_SIMPLE: KGE_DISPATCH_VEC(KGE_SIMPLE, vec, CALL); break;             \
+      case KGE_SIMPLE_IGNR: KGE_DISPATCH_VEC(KGE_SIMPLE_IGNR, vec, CALL); break;   \
       default: ::kge::set_error("model id %d not supported", (int)(model)); return KGE_ENOTSUP; \
     }                                                                              \
   } while (0)

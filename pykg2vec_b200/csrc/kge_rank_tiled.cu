@@ -49,6 +49,7 @@ struct TiledParams {
   int tiles_per_cta, ntiles;
   int32_t* counts;
   int col, l1;
+  int fin;      // DOT ops: 0 -> -sum ; 1 -> -sigmoid(sum) (HoLE) ; 2 -> -clamp(sum, +-20) (SimplE)
   float margin;
 };
 
@@ -108,12 +109,16 @@ KGE_DEV void pair_op(float& acc, const float4* q, const float4* c) {
 }
 
 template <int OP, bool L1>
-KGE_DEV float finalize(float sum, float qscale, float margin, bool has_scale) {
+KGE_DEV float finalize(float sum, float qscale, float margin, bool has_scale, int fin) {
   if (OP == OP_TRANS_T || OP == OP_TRANS_H) {
     const float dist = L1 ? sum : __fsqrt_rn(sum);
     return has_scale ? fmul(qscale, dist) : dist;
   }
-  if (OP == OP_DOT1 || OP == OP_DOT2) return -sum;
+  if (OP == OP_DOT1 || OP == OP_DOT2) {
+    if (fin == 1) return -sigmoid_canon(sum);
+    if (fin == 2) return -fminf(fmaxf(sum, -20.0f), 20.0f);
+    return -sum;
+  }
   return fsub(sum, margin);
 }
 
@@ -282,7 +287,7 @@ sweep_tiled_kernel(TiledParams P) {
         for (int i = 0; i < NV / 8; ++i) {
           const int jc = (orig0 + i) % kTC;
           const int64_t cand = cbase + (gc + kGC * nt) * kTC + jc;
-          const float s = finalize<OP, L1>(acc[nt][i], qsc, P.margin, has_scale);
+          const float s = finalize<OP, L1>(acc[nt][i], qsc, P.margin, has_scale, P.fin);
           cnt += (qvalid && cand < P.nc && s < th) ? 1 : 0;
         }
       }
@@ -303,7 +308,9 @@ template <int MODEL, int VEC, int DIR>
 __global__ void __launch_bounds__(256)
 prep_query_kernel(ModelParams P, const int64_t* __restrict__ qh, const int64_t* __restrict__ qr,
                   const int64_t* __restrict__ qt, int64_t Q, int dp, float* __restrict__ qvec,
-                  float* __restrict__ qscale, float* __restrict__ thr) {
+                  float* __restrict__ qscale, float* __restrict__ thr, int scratch_floats) {
+  extern __shared__ float4 smem_f4[];
+  float* scratch = reinterpret_cast<float*>(smem_f4) + (size_t)(threadIdx.x >> 3) * scratch_floats;
   const int lane = threadIdx.x & 7;
   const int64_t q = (int64_t)blockIdx.x * 32 + (threadIdx.x >> 3);
   if (q >= Q) return;
@@ -311,10 +318,11 @@ prep_query_kernel(ModelParams P, const int64_t* __restrict__ qh, const int64_t* 
   TripleRows R;
   resolve_rows<MODEL>(R, P, P.qtab, P.qtab, P.qtab, __ldg(qh + q), __ldg(qr + q), __ldg(qt + q));
   {  // threshold = the target's own score in this direction's grouping (== kge_score_fwd)
-    const float s = score_group<MODEL, VEC, DIR == 0 ? KGE_GROUP_TAIL : KGE_GROUP_HEAD>(R, P, lane, nullptr);
+    const float s = score_group<MODEL, VEC, DIR == 0 ? KGE_GROUP_TAIL : KGE_GROUP_HEAD>(R, P, lane, scratch);
     if (lane == 0) thr[q] = s;
   }
-  constexpr int KQ = (MODEL == KGE_COMPLEX) ? 2 : (MODEL == KGE_ROTATE ? (DIR == 0 ? 2 : 4) : 1);
+  constexpr int KQ = (MODEL == KGE_COMPLEX || MODEL == KGE_SIMPLE || MODEL == KGE_SIMPLE_IGNR)
+                         ? 2 : (MODEL == KGE_ROTATE ? (DIR == 0 ? 2 : 4) : 1);
   float* out = qvec + (size_t)q * KQ * dp;
   auto st = [&](int k, int c, float4 v) { *reinterpret_cast<float4*>(out + (size_t)k * dp + 4 * c) = v; };
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -374,6 +382,28 @@ prep_query_kernel(ModelParams P, const int64_t* __restrict__ qh, const int64_t* 
       }
       st(0, c, o0); st(1, c, o1);
     }
+  } else if (MODEL == KGE_HOLE || MODEL == KGE_RESCAL) {
+    // score_group left the query-side vector in the group's scratch (HoLE: g at scratch+2*dp,
+    // RESCAL: v at scratch); entries beyond d are zero.
+    const float* src = (MODEL == KGE_HOLE) ? scratch + 2 * (nch * 4) : scratch;
+    for (int c = lane; c < nchp; c += 8) st(0, c, c < nch ? *reinterpret_cast<const float4*>(src + 4 * c) : zero);
+  } else if (MODEL == KGE_SIMPLE || MODEL == KGE_SIMPLE_IGNR) {
+    const float half = (MODEL == KGE_SIMPLE) ? 0.5f : 1.0f;
+    for (int c = lane; c < nchp; c += 8) {
+      float4 o0 = zero, o1 = zero;
+      if (c < nch) {
+        const float4 r1 = ld_chunk<VEC>(R.r[0], c, d), r2 = ld_chunk<VEC>(R.r[1], c, d);
+        // TAIL: q1 = h1 r1, q2 = half t2 r2 ; HEAD: q1 = r1 t1, q2 = half r2 h2
+        const float4 a = ld_chunk<VEC>(DIR == 0 ? R.h[0] : R.t[0], c, d);
+        const float4 b = ld_chunk<VEC>(DIR == 0 ? R.h[1] : R.t[1], c, d);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          f4_at(o0, e) = fmul(f4_get(a, e), f4_get(r1, e));
+          f4_at(o1, e) = fmul(fmul(f4_get(b, e), f4_get(r2, e)), half);
+        }
+      }
+      st(0, c, o0); st(1, c, o1);
+    }
   } else if (MODEL == KGE_ROTATE) {
     for (int c = lane; c < nchp; c += 8) {
       float4 o0 = zero, o1 = zero, o2 = zero, o3 = zero;
@@ -402,6 +432,19 @@ prep_query_kernel(ModelParams P, const int64_t* __restrict__ qh, const int64_t* 
 }
 
 // candidate scratch: row e -> (normalised | copied) and zero padded to dp
+// HoLE candidates: even part of every row (see even_chunk)
+__global__ void __launch_bounds__(256)
+prep_cand_even_kernel(const float* __restrict__ table, int64_t nc, int d, int dp, float* __restrict__ out) {
+  const int lane = threadIdx.x & 7;
+  const int64_t e = (int64_t)blockIdx.x * 32 + (threadIdx.x >> 3);
+  if (e >= nc) return;
+  const float* row = table + (size_t)e * d;
+  const int nch = (d + 3) >> 2, nchp = dp >> 2;
+  for (int c = lane; c < nchp; c += 8)
+    *reinterpret_cast<float4*>(out + (size_t)e * dp + 4 * c) =
+        c < nch ? even_chunk(row, c, d) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 template <int VEC, bool NORMALISE>
 __global__ void __launch_bounds__(256)
 prep_cand_kernel(const float* __restrict__ table, int64_t nc, int d, int dp, float* __restrict__ out) {
@@ -434,25 +477,19 @@ int model_vec(const kge_model_t* m);
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static int dp_of(const kge_model_t* m) { return ((m->dim + 3) / 4) * 4; }
-static int max_kq(int model) { return model == KGE_ROTATE ? 4 : (model == KGE_COMPLEX ? 2 : 1); }
-static int num_cand_tables(int model) { return (model == KGE_ROTATE || model == KGE_COMPLEX) ? 2 : 1; }
-static bool cand_needs_scratch(const kge_model_t* m) {
-  if (m->model == KGE_TRANSE || m->model == KGE_TRANSM) return true;  // normalised copy
-  if (m->dim % 4 != 0) return true;
-  const int slots[3] = {0, 1, 2};
-  for (int k = 0; k < 3; ++k)
-    if (m->tables[slots[k]] && ((uintptr_t)m->tables[slots[k]] & 15)) return true;
-  return false;
-}
-
+static bool is_simple(int model) { return model == KGE_SIMPLE || model == KGE_SIMPLE_IGNR; }
+static int max_kq(int model) { return model == KGE_ROTATE ? 4 : ((model == KGE_COMPLEX || is_simple(model)) ? 2 : 1); }
+static int num_cand_tables(int model) { return (model == KGE_ROTATE || model == KGE_COMPLEX || is_simple(model)) ? 2 : 1; }
 // candidate source tables of a sweep direction; returns true when a scratch copy is needed
 // (normalised rows for TransE/TransM, padding for d % 4 != 0, unaligned tables)
 static bool cand_sources(const kge_model_t* m, int dir, const float* src[2]) {
   const int KC = num_cand_tables(m->model);
   src[0] = src[1] = nullptr;
   if (m->model == KGE_CP) src[0] = m->tables[dir == 0 ? 2 : 0];
-  else { src[0] = m->tables[0]; if (KC == 2) src[1] = m->tables[1]; }
-  bool scratch = (m->model == KGE_TRANSE || m->model == KGE_TRANSM) || (m->dim % 4 != 0);
+  else if (is_simple(m->model)) {  // TAIL: (t1, h2) = (ent_tail, ent_head)[c]; HEAD: (h1, t2) = (ent_head, ent_tail)[c]
+    src[0] = m->tables[dir == 0 ? 1 : 0]; src[1] = m->tables[dir == 0 ? 0 : 1];
+  } else { src[0] = m->tables[0]; if (KC == 2) src[1] = m->tables[1]; }
+  bool scratch = (m->model == KGE_TRANSE || m->model == KGE_TRANSM || m->model == KGE_HOLE) || (m->dim % 4 != 0);
   for (int k = 0; k < KC; ++k) if ((uintptr_t)src[k] & 15) scratch = true;
   return scratch;
 }
@@ -470,7 +507,9 @@ static int fill_cand_scratch(const kge_model_t* m, const float* const src[2], in
   const unsigned cgrid = (unsigned)((nc + 31) / 32);
   for (int k = 0; k < KC; ++k) {
     float* dst = cscratch + (size_t)k * (size_t)nc * dp;
-    if (normalise) {
+    if (m->model == KGE_HOLE) {
+      prep_cand_even_kernel<<<cgrid, 256, 0, st>>>(src[k], nc, d, dp, dst);
+    } else if (normalise) {
       if (vc == 4) prep_cand_kernel<4, true><<<cgrid, 256, 0, st>>>(src[k], nc, d, dp, dst);
       else if (vc == 2) prep_cand_kernel<2, true><<<cgrid, 256, 0, st>>>(src[k], nc, d, dp, dst);
       else prep_cand_kernel<1, true><<<cgrid, 256, 0, st>>>(src[k], nc, d, dp, dst);
@@ -492,7 +531,7 @@ static float* cand_scratch_ptr(const kge_model_t* m, void* ws, int64_t Q) {
 }
 
 int tiled_prepare_candidates(const kge_model_t* m, int64_t nc, void* ws, int64_t Q, cudaStream_t st) {
-  if (m->model == KGE_CP) return KGE_OK;  // per direction, see tiled_sweep
+  if (m->model == KGE_CP || is_simple(m->model)) return KGE_OK;  // per direction, see tiled_sweep
   const float* src[2];
   if (!cand_sources(m, 0, src)) return KGE_OK;
   return fill_cand_scratch(m, src, num_cand_tables(m->model), nc, cand_scratch_ptr(m, ws, Q), st);
@@ -501,6 +540,7 @@ int tiled_prepare_candidates(const kge_model_t* m, int64_t nc, void* ws, int64_t
 bool tiled_supported(const kge_model_t* m) {
   switch (m->model) {
     case KGE_TRANSE: case KGE_TRANSM: case KGE_DISTMULT: case KGE_CP: case KGE_COMPLEX: case KGE_ROTATE:
+    case KGE_HOLE: case KGE_RESCAL: case KGE_SIMPLE: case KGE_SIMPLE_IGNR:
       return true;
     default: return false;
   }
@@ -532,8 +572,8 @@ int tiled_sweep(const kge_model_t* m, const kge_model_t* mq, int dir, const int6
   const int model = m->model;
   const int d = m->dim, dp = dp_of(m);
   const int op = (model == KGE_TRANSE || model == KGE_TRANSM) ? (dir == 0 ? OP_TRANS_T : OP_TRANS_H)
-               : (model == KGE_DISTMULT || model == KGE_CP) ? OP_DOT1
-               : (model == KGE_COMPLEX) ? OP_DOT2 : (dir == 0 ? OP_ROT_T : OP_ROT_H);
+               : (model == KGE_DISTMULT || model == KGE_CP || model == KGE_HOLE || model == KGE_RESCAL) ? OP_DOT1
+               : (model == KGE_COMPLEX || is_simple(model)) ? OP_DOT2 : (dir == 0 ? OP_ROT_T : OP_ROT_H);
   const int KQ = (op == OP_DOT2 || op == OP_ROT_T) ? 2 : (op == OP_ROT_H ? 4 : 1);
   const int KC = num_cand_tables(model);
   const int TQ = (op == OP_ROT_H) ? 2 : 4;
@@ -550,12 +590,23 @@ int tiled_sweep(const kge_model_t* m, const kge_model_t* mq, int dir, const int6
   const ModelParams PQ = make_params(mq, mq);
   const int vq = model_vec(mq);
   const unsigned qgrid = (unsigned)((Q + 31) / 32);
+  const int psf = (int)group_scratch_floats(mq);
+  const size_t psmem = (size_t)psf * 32 * sizeof(float);
 #define PREP(M, V)                                                                                   \
   do {                                                                                               \
-    if (dir == 0) prep_query_kernel<M, V, 0><<<qgrid, 256, 0, st>>>(PQ, qh, qr, qt, Q, dp, qvec, qscale, thr); \
-    else prep_query_kernel<M, V, 1><<<qgrid, 256, 0, st>>>(PQ, qh, qr, qt, Q, dp, qvec, qscale, thr); \
+    if (dir == 0) {                                                                                  \
+      if (psmem > 48 * 1024) KGE_CUDA_OK(cudaFuncSetAttribute(prep_query_kernel<M, V, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem)); \
+      prep_query_kernel<M, V, 0><<<qgrid, 256, psmem, st>>>(PQ, qh, qr, qt, Q, dp, qvec, qscale, thr, psf); \
+    } else {                                                                                         \
+      if (psmem > 48 * 1024) KGE_CUDA_OK(cudaFuncSetAttribute(prep_query_kernel<M, V, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem)); \
+      prep_query_kernel<M, V, 1><<<qgrid, 256, psmem, st>>>(PQ, qh, qr, qt, Q, dp, qvec, qscale, thr, psf); \
+    }                                                                                                \
   } while (0)
   switch (model) {
+    case KGE_HOLE: KGE_DISPATCH_VEC(KGE_HOLE, vq, PREP); break;
+    case KGE_RESCAL: KGE_DISPATCH_VEC(KGE_RESCAL, vq, PREP); break;
+    case KGE_SIMPLE: KGE_DISPATCH_VEC(KGE_SIMPLE, vq, PREP); break;
+    case KGE_SIMPLE_IGNR: KGE_DISPATCH_VEC(KGE_SIMPLE_IGNR, vq, PREP); break;
     case KGE_TRANSE: KGE_DISPATCH_VEC(KGE_TRANSE, vq, PREP); break;
     case KGE_TRANSM: KGE_DISPATCH_VEC(KGE_TRANSM, vq, PREP); break;
     case KGE_DISTMULT: KGE_DISPATCH_VEC(KGE_DISTMULT, vq, PREP); break;
@@ -575,7 +626,7 @@ int tiled_sweep(const kge_model_t* m, const kge_model_t* mq, int dir, const int6
       for (int k = 0; k < KC; ++k) P.cand[k] = cscratch + (size_t)k * (size_t)nc * dp;
       if (KC == 1) P.cand[1] = nullptr;
       P.cand_pitch = dp;
-      if (model == KGE_CP) {  // subject and object tables differ per direction: (re)fill now
+      if (model == KGE_CP || is_simple(model)) {  // tables differ per direction: (re)fill now
         int rc = fill_cand_scratch(m, src, KC, nc, cscratch, st);
         if (rc) return rc;
       }
@@ -610,6 +661,7 @@ int tiled_sweep(const kge_model_t* m, const kge_model_t* mq, int dir, const int6
   P.tiles_per_cta = (P.ntiles + splits - 1) / splits;
   splits = (P.ntiles + P.tiles_per_cta - 1) / P.tiles_per_cta;
   P.counts = counts; P.col = col; P.l1 = m->l1_flag; P.margin = m->margin;
+  P.fin = (model == KGE_HOLE) ? 1 : (is_simple(model) ? 2 : 0);
 
   switch (op) {
     case OP_TRANS_T: return m->l1_flag ? launch_sweep<OP_TRANS_T, true>(P, QBLK, smem, st, splits, qblocks)

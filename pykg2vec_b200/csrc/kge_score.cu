@@ -54,6 +54,7 @@ int check_model(const kge_model_t* m) {
 int model_vec(const kge_model_t* m) {
   const int nt = num_tables(m->model);
   if (m->model == KGE_TRANSM) return pick_vec(m, 2, m->dim);  // theta is a [R] vector, read as scalars
+  if (m->model == KGE_HOLE) return (m->dim % 4 == 0) ? pick_vec(m, nt, m->dim) : 1;  // mirrored scalar reads
   return pick_vec(m, nt, m->dim, m->model == KGE_TRANSR ? m->rel_dim : 0);
 }
 

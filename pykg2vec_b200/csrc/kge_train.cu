@@ -149,8 +149,10 @@ int model_vec(const kge_model_t* m);
 // which tables a head / relation / tail id touches, per model
 static int roles(int model, int which /*0 h, 1 r, 2 t*/, int out[2]) {
   switch (model) {
-    case KGE_TRANSE: case KGE_DISTMULT: case KGE_TRANSM:
+    case KGE_TRANSE: case KGE_DISTMULT: case KGE_TRANSM: case KGE_HOLE: case KGE_RESCAL:
       out[0] = which == 1 ? 1 : 0; return 1;
+    case KGE_SIMPLE: case KGE_SIMPLE_IGNR:
+      if (which == 1) { out[0] = 2; out[1] = 3; return 2; } out[0] = 0; out[1] = 1; return 2;
     case KGE_CP: out[0] = which; return 1;  // sub, rel, obj
     case KGE_TRANSH: if (which == 1) { out[0] = 1; out[1] = 2; return 2; } out[0] = 0; return 1;
     case KGE_TRANSR: if (which == 1) { out[0] = 1; out[1] = 2; return 2; } out[0] = 0; return 1;
@@ -163,6 +165,7 @@ static int roles(int model, int which /*0 h, 1 r, 2 t*/, int out[2]) {
 static int table_width(const kge_model_t* m, int k) {
   switch (m->model) {
     case KGE_TRANSR: return k == 0 ? m->dim : (k == 1 ? m->rel_dim : m->dim * m->rel_dim);
+    case KGE_RESCAL: return k == 0 ? m->dim : m->dim * m->dim;
     default: return m->dim;
   }
 }

@@ -244,3 +244,70 @@ class RotatE(_KernelScored, PairwiseModel):
         r_e_r = self.rel_embeddings(r) / (self.embedding_range / pi)
         return (self.ent_embeddings(h), self.ent_embeddings_imag(h), torch.cos(r_e_r), torch.sin(r_e_r),
                 self.ent_embeddings(t), self.ent_embeddings_imag(t))
+
+
+class Rescal(_KernelScored, PairwiseModel):
+    """pykg2vec/models/pairwise.py:794-865.  Like the reference, every forward() first replaces
+    both tables by their row-normalised versions IN PLACE (embed(), :843-844) — here one kernel
+    per table (kge_normalize_rows) — and then scores -h^T M_r t."""
+
+    def __init__(self, **kwargs):
+        super(Rescal, self).__init__(self.__class__.__name__.lower())
+        param_list = ["tot_entity", "tot_relation", "hidden_size", "margin"]
+        param_dict = self.load_params(param_list, kwargs)
+        self.__dict__.update(param_dict)
+        self.ent_embeddings = NamedEmbedding("ent_embedding", self.tot_entity, self.hidden_size)
+        self.rel_matrices = NamedEmbedding("rel_matrices", self.tot_relation, self.hidden_size * self.hidden_size)
+        nn.init.xavier_uniform_(self.ent_embeddings.weight)
+        nn.init.xavier_uniform_(self.rel_matrices.weight)
+        self.parameter_list = [self.ent_embeddings, self.rel_matrices]
+        self.loss = Criterion.pairwise_hinge
+
+    def kge_tables(self):
+        return [self.ent_embeddings.weight, self.rel_matrices.weight]
+
+    def kge_spec(self):
+        return ModelSpec("rescal", self.hidden_size)
+
+    def normalize_tables_(self):
+        with torch.no_grad():
+            _lib.normalize_rows(self.ent_embeddings.weight.data)
+            _lib.normalize_rows(self.rel_matrices.weight.data)
+
+    def forward(self, h, r, t):
+        self.normalize_tables_()
+        return ScoreFunction.apply(self.kge_spec(), h, r, t, *self.kge_tables())
+
+    def embed(self, h, r, t):
+        k = self.hidden_size
+        self.normalize_tables_()
+        return (self.ent_embeddings(h).view(-1, k, 1), self.rel_matrices(r).view(-1, k, k),
+                self.ent_embeddings(t).view(-1, k, 1))
+
+
+class HoLE(_KernelScored, PairwiseModel):
+    """pykg2vec/models/pairwise.py:1087-1142.  forward() reproduces what the reference's lines
+    :1119-1125 evaluate under its pinned torch<1.7: e = circconv(even(h),
+    even(t)), score = -sigmoid(<normalize(r), e>).  The legacy torch.fft/ifft the reference
+    calls no longer exist, so parity for HoLE is pinned on an emulation (tests/golden)."""
+
+    def __init__(self, **kwargs):
+        super(HoLE, self).__init__(self.__class__.__name__.lower())
+        param_list = ["tot_entity", "tot_relation", "hidden_size", "cmax", "cmin"]
+        param_dict = self.load_params(param_list, kwargs)
+        self.__dict__.update(param_dict)
+        self.ent_embeddings = NamedEmbedding("ent_embedding", self.tot_entity, self.hidden_size)
+        self.rel_embeddings = NamedEmbedding("rel_embedding", self.tot_relation, self.hidden_size)
+        nn.init.xavier_uniform_(self.ent_embeddings.weight)
+        nn.init.xavier_uniform_(self.rel_embeddings.weight)
+        self.parameter_list = [self.ent_embeddings, self.rel_embeddings]
+        self.loss = Criterion.pairwise_hinge
+
+    def kge_tables(self):
+        return [self.ent_embeddings.weight, self.rel_embeddings.weight]
+
+    def kge_spec(self):
+        return ModelSpec("hole", self.hidden_size)
+
+    def embed(self, h, r, t):
+        return self.ent_embeddings(h), self.rel_embeddings(r), self.ent_embeddings(t)

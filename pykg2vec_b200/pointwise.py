@@ -128,3 +128,64 @@ class ComplexN3(Complex):
 
     def get_reg(self, h, r, t, reg_type="N3"):
         return self._reg(h, r, t, reg_type)
+
+
+class SimplE(_KernelScored, PointwiseModel):
+    """pykg2vec/models/pointwise.py:461-536 (including its quirks: only the inverse-relation sum
+    is halved, :525; get_reg() regularises the id tensors, :528-536)."""
+    _kge_name = "simple"
+
+    def __init__(self, **kwargs):
+        super(SimplE, self).__init__(self.__class__.__name__.lower())
+        param_list = ["tot_entity", "tot_relation", "hidden_size", "lmbda"]
+        param_dict = self.load_params(param_list, kwargs)
+        self.__dict__.update(param_dict)
+        k = self.hidden_size
+        self.tot_train_triples = kwargs['tot_train_triples']
+        self.batch_size = kwargs['batch_size']
+        self.ent_head_embeddings = NamedEmbedding("ent_head_embedding", self.tot_entity, k)
+        self.ent_tail_embeddings = NamedEmbedding("ent_tail_embedding", self.tot_entity, k)
+        self.rel_embeddings = NamedEmbedding("rel_embedding", self.tot_relation, k)
+        self.rel_inv_embeddings = NamedEmbedding("rel_inv_embedding", self.tot_relation, k)
+        for e in (self.ent_head_embeddings, self.ent_tail_embeddings, self.rel_embeddings, self.rel_inv_embeddings):
+            nn.init.xavier_uniform_(e.weight)
+        self.parameter_list = [self.ent_head_embeddings, self.ent_tail_embeddings, self.rel_embeddings,
+                               self.rel_inv_embeddings]
+        self.loss = Criterion.pointwise_logistic
+
+    def kge_tables(self):
+        return [self.ent_head_embeddings.weight, self.ent_tail_embeddings.weight, self.rel_embeddings.weight,
+                self.rel_inv_embeddings.weight]
+
+    def kge_spec(self):
+        return ModelSpec(self._kge_name, self.hidden_size)
+
+    def embed(self, h, r, t):
+        return (self.ent_head_embeddings(h), self.ent_head_embeddings(t), self.rel_embeddings(r),
+                self.rel_inv_embeddings(r), self.ent_tail_embeddings(t), self.ent_tail_embeddings(h))
+
+    def get_reg(self, h, r, t, reg_type="F2"):
+        # the reference applies the regulariser to the ID tensors (a constant w.r.t. the weights)
+        import torch
+        p = {"f2": 2, "n3": 3}.get(reg_type.lower())
+        if p is None:
+            raise NotImplementedError('Unknown regularizer type: %s' % reg_type)
+        term = torch.mean(torch.sum(h.float() ** p, -1) + torch.sum(r.float() ** p, -1) + torch.sum(t.float() ** p, -1))
+        return self.lmbda * term
+
+
+class SimplE_ignr(SimplE):
+    """pykg2vec/models/pointwise.py:539-581."""
+    _kge_name = "simple_ignr"
+
+    def __init__(self, **kwargs):
+        super(SimplE_ignr, self).__init__(**kwargs)
+        self.model_name = 'simple_ignr'
+        self.loss = Criterion.pointwise_logistic
+
+    def embed(self, h, r, t):
+        import torch
+        cat = lambda e1, i1, e2, i2: torch.cat([e1.weight[i1], e2.weight[i2]], 1)
+        return (cat(self.ent_head_embeddings, h, self.ent_head_embeddings, t),
+                cat(self.rel_embeddings, r, self.rel_inv_embeddings, r),
+                cat(self.ent_tail_embeddings, t, self.ent_tail_embeddings, h))

@@ -35,7 +35,10 @@ def init_distributed(backend=None):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # keep stdout clean (bench.py prints exactly one JSON line): NCCL's version banner goes
         # to stdout at NCCL_DEBUG=VERSION/INFO
-        os.environ["NCCL_DEBUG"] = os.environ.get("KGE_NCCL_DEBUG", "WARN")
+        if "KGE_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["KGE_NCCL_DEBUG"]
+        else:
+            os.environ.pop("NCCL_DEBUG", None)
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         dist.init_process_group(backend=backend)

@@ -63,7 +63,29 @@ SPECS = {
     "cp": (ref_pointwise.CP, ["sub_embeddings", "rel_embeddings", "obj_embeddings"]),
     "complex": (ref_pointwise.Complex, ["ent_embeddings_real", "ent_embeddings_img",
                                         "rel_embeddings_real", "rel_embeddings_img"]),
+    "rescal": (ref_pairwise.Rescal, ["ent_embeddings", "rel_matrices"]),
+    "simple": (ref_pointwise.SimplE, ["ent_head_embeddings", "ent_tail_embeddings", "rel_embeddings",
+                                      "rel_inv_embeddings"]),
+    "simple_ignr": (ref_pointwise.SimplE_ignr, ["ent_head_embeddings", "ent_tail_embeddings",
+                                                "rel_embeddings", "rel_inv_embeddings"]),
+    "hole": (ref_pairwise.HoLE, ["ent_embeddings", "rel_embeddings"]),
 }
+
+
+def legacy_hole_forward(model, h, r, t):
+    """HoLE.forward (pairwise.py:1119-1125) cannot run on torch >= 1.8 (torch.fft / torch.ifft are
+    the removed legacy functions).  This reproduces what those lines computed under the pinned
+    torch<1.7: fft of the zero-imaginary [b,d,2] views, torch.conj = no-op on a real tensor, `*`
+    = elementwise product of the (re, im) pairs, ifft, real part.  Everything else (embed(), the
+    tables, normalisation, sigmoid) is the reference's own code."""
+    import torch.nn.functional as F
+    h_e, r_e, t_e = model.embed(h, r, t)
+    r_e = F.normalize(r_e, p=2, dim=-1)
+    fh = torch.fft.fft(h_e.to(torch.complex64), dim=1)
+    ft = torch.fft.fft(t_e.to(torch.complex64), dim=1)
+    z = torch.complex(fh.real * ft.real, fh.imag * ft.imag)
+    e = torch.fft.ifft(z, dim=1).real
+    return -torch.sigmoid(torch.sum(r_e * e, 1))
 
 CASES = [
     # name, model, N, R, kwargs, init ("ref" = reference initialiser, "normal" = N(0, 0.5))
@@ -83,6 +105,12 @@ CASES = [
     ("cp_d36", "cp", 73, 5, dict(hidden_size=36, lmbda=0.1), "normal"),
     ("complex_d200", "complex", 131, 7, dict(hidden_size=200, lmbda=0.1), "ref"),
     ("complex_d50", "complex", 131, 7, dict(hidden_size=50, lmbda=0.1), "normal"),
+    ("rescal_d24", "rescal", 67, 4, dict(hidden_size=24, margin=1.0), "normal"),
+    ("rescal_d50", "rescal", 53, 3, dict(hidden_size=50, margin=1.0), "ref"),
+    ("simple_d48", "simple", 101, 6, dict(hidden_size=48, lmbda=0.1, tot_train_triples=1000, batch_size=100), "normal"),
+    ("simple_ignr_d50", "simple_ignr", 101, 6, dict(hidden_size=50, lmbda=0.1, tot_train_triples=1000, batch_size=100), "normal"),
+    ("hole_d30", "hole", 83, 5, dict(hidden_size=30, cmax=0.5, cmin=-0.5), "normal"),
+    ("hole_d150", "hole", 61, 4, dict(hidden_size=150, cmax=0.5, cmin=-0.5), "ref"),
 ]
 N_TRIPLES = 96
 N_QUERIES = 6
@@ -146,6 +174,8 @@ def csr(dct, keys):
 
 def make_case(name, model, N, R, kw, init, seed):
     m, keys = build_model(model, N, R, kw, init, seed)
+    if model == "hole":
+        m.forward = lambda a, b, c: legacy_hole_forward(m, a, b, c)
     rng = np.random.RandomState(seed + 1000)
     h = rng.randint(N, size=N_TRIPLES).astype(np.int64)
     r = rng.randint(R, size=N_TRIPLES).astype(np.int64)
@@ -153,12 +183,14 @@ def make_case(name, model, N, R, kw, init, seed):
     upstream = rng.standard_normal(N_TRIPLES).astype(np.float32)
     ht, rt, tt = torch.from_numpy(h), torch.from_numpy(r), torch.from_numpy(t)
     m.zero_grad()
-    scores = m(ht, rt, tt)
+    scores = m.forward(ht, rt, tt)  # (Rescal.forward row-normalises its tables in place first)
     (scores * torch.from_numpy(upstream)).sum().backward()
     out = {"model": model, "N": N, "R": R, "h": h, "r": r, "t": t, "upstream": upstream,
            "scores": scores.detach().numpy().copy()}
     for k, v in kw.items():
         out["kw_" + k] = np.asarray(v)
+    if model == "hole":
+        out["emulated_forward"] = np.asarray(True)
     for i, k in enumerate(keys):
         emb = getattr(m, k)
         out["table%d" % i] = emb.weight.detach().numpy().copy()

@@ -33,6 +33,8 @@ def model_kwargs(g):
     dim = int(kw.get("hidden_size", kw.get("ent_hidden_size", 0)))
     rel_dim = int(kw.get("rel_hidden_size", dim))
     margin = float(kw.get("margin", 0.0))
+    if name == "rescal":
+        rel_dim = dim
     return dict(name=name, dim=dim, rel_dim=rel_dim, l1_flag=bool(kw.get("l1_flag", False)),
                 margin=margin,
                 embedding_range=((margin + 2.0) / dim) if name == "rotate" else None)

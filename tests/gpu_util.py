@@ -20,6 +20,7 @@ NUM_TABLE_SPECS = {
     "transe": ["e", "r"], "transh": ["e", "r", "r"], "transd": ["e", "r", "e", "r"],
     "transr": ["e", "r", "M"], "rotate": ["e", "e", "r"], "distmult": ["e", "r"],
     "cp": ["e", "r", "e"], "complex": ["e", "e", "r", "r"], "transm": ["e", "r", "theta"],
+    "hole": ["e", "r"], "rescal": ["e", "MM"], "simple": ["e", "e", "r", "r"], "simple_ignr": ["e", "e", "r", "r"],
 }
 
 
@@ -36,6 +37,8 @@ def synthetic_case(name, N, R, d, seed, dr=None, l1=False, margin=0.0, scale=0.5
             tabs.append((rng.standard_normal((R, dr)) * scale).astype(np.float32))
         elif kind == "M":
             tabs.append((rng.standard_normal((R, d * dr)) * scale).astype(np.float32))
+        elif kind == "MM":
+            tabs.append((rng.standard_normal((R, d * d)) * scale).astype(np.float32))
         elif kind == "theta":
             tabs.append((0.2 + rng.rand(R)).astype(np.float32))
     emb_range = (margin + 2.0) / d if name == "rotate" else None

@@ -50,6 +50,9 @@ def test_score_bwd_vs_reference_autograd(name):
     ("transr", 120, 5, 40, 24, False, 0.0), ("transm", 300, 7, 36, None, False, 0.0),
     ("rotate", 300, 7, 100, None, False, 12.0), ("distmult", 300, 7, 200, None, False, 0.0),
     ("cp", 300, 7, 30, None, False, 0.0), ("complex", 300, 7, 200, None, False, 0.0),
+    ("hole", 200, 5, 30, None, False, 0.0), ("hole", 200, 5, 52, None, False, 0.0),
+    ("rescal", 150, 4, 24, None, False, 0.0), ("simple", 300, 7, 48, None, False, 0.0),
+    ("simple_ignr", 300, 7, 50, None, False, 0.0),
 ], ids=lambda s: "%s-d%d" % (s[0], s[3]))
 def test_score_bwd_vs_fp64_oracle(spec):
     """duplicates in the batch (few entities) exercise the atomic scatter."""
@@ -142,11 +145,13 @@ def test_model_classes_forward_backward_like_reference(name):
     g = gu.load(name)
     if str(g["model"]) == "transm":
         pytest.skip("needs a knowledge graph")
+    if str(g["model"]) == "rescal":
+        pytest.skip("forward() re-normalises the stored (already normalised) tables: covered by test_rescal_model")
     m = _make_model(g)
     h, r, t = _cuda(g["h"]), _cuda(g["r"]), _cuda(g["t"])
     s = m(h, r, t)
     ref = g["scores"]
-    floor = 1e-3 * np.abs(ref).max()
+    floor = 1e-2 * np.abs(ref).max()
     err = np.abs(s.detach().cpu().numpy().astype(np.float64) - ref) / np.maximum(np.abs(ref), floor)
     assert err.max() < 1e-4
     (s * _cuda(g["upstream"])).sum().backward()
@@ -252,3 +257,23 @@ def test_evaluator_matches_oracle_and_reference_metrics():
     assert top.shape == (5,)
     full = oracle.sweep_scores(om, oracle.GROUP_TAIL, int(test[0, 0]), int(test[0, 1]), 0)
     assert set(top.cpu().tolist()) == set(np.argsort(-full, kind="stable")[:5].tolist())
+
+
+def test_rescal_model_normalises_in_place_like_reference():
+    """Rescal.forward mutates its tables (pairwise.py:843-844): rows become unit-norm, then scores
+    match the oracle on the normalised tables; backward reaches both tables."""
+    import oracle
+    import pykg2vec_b200
+    torch.manual_seed(3)
+    m = pykg2vec_b200.import_model("rescal")(tot_entity=90, tot_relation=4, hidden_size=20, margin=1.0).cuda()
+    before = [w.detach().cpu().numpy().copy() for w in m.kge_tables()]
+    rng = np.random.RandomState(0)
+    h, r, t = rng.randint(90, size=40), rng.randint(4, size=40), rng.randint(90, size=40)
+    s = m(_cuda(h), _cuda(r), _cuda(t))
+    want_tabs = [oracle.normalize_rows(b.copy()) for b in before]
+    for w, wt in zip(m.kge_tables(), want_tabs):
+        np.testing.assert_array_equal(w.detach().cpu().numpy(), wt)
+    om = oracle.Model("rescal", want_tabs, 20)
+    np.testing.assert_array_equal(gpu.bits(s.detach().cpu().numpy()), gpu.bits(oracle.score_fwd(om, h, r, t)))
+    s.sum().backward()
+    assert all(w.grad is not None and float(w.grad.abs().sum()) > 0 for w in m.kge_tables())

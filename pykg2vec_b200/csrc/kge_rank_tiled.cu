@@ -18,6 +18,8 @@
 //
 // Bound: fp32 pipe (2-8 instructions per element pair), not HBM: a candidate row is read from
 // L2 once per query BLOCK instead of once per query.
+#include <cuda.h>  // CUtensorMap (driver types only; the encoder is fetched through the runtime)
+
 #include "kge_models.cuh"
 #include "kge_rank.cuh"
 
@@ -74,6 +76,15 @@ KGE_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
 KGE_DEV void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// 2-D tensor-map tile load (TMA): box {DS columns, rows} at (col, row) of a row-major fp32 matrix;
+// out-of-bounds elements are zero-filled and still counted in the transaction bytes.
+KGE_DEV void tma_load_2d(void* dst_smem, const CUtensorMap* tm, int col, int row, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(col), "r"(row), "r"(smem_u32(bar))
+      : "memory");
 }
 
 // ---- per-element pair operations (canonical arithmetic) ---------------------------------------
@@ -156,9 +167,11 @@ KGE_DEV void reduce_scatter(float (&v)[NV], int lane) {
   }
 }
 
+struct TiledMaps { CUtensorMap q, c0, c1; };
+
 template <int OP, bool L1>
 __global__ void __launch_bounds__(kTThreads)
-sweep_tiled_kernel(TiledParams P) {
+sweep_tiled_kernel(const __grid_constant__ TiledParams P, const __grid_constant__ TiledMaps TM) {
   constexpr int KQ = OpTraits<OP>::KQ, KC = OpTraits<OP>::KC, TQ = OpTraits<OP>::TQ;
   constexpr int QBLK = kGQ * TQ;
   constexpr int NV = TQ * kTC;
@@ -196,37 +209,20 @@ sweep_tiled_kernel(TiledParams P) {
   }
   __syncthreads();
 
-  // producer: warp 0 issues the bulk copies of iteration `it` into stage it&1
+  // producer: one thread issues the TMA tile loads of iteration `it` into stage it&1
+  // (one box per candidate table + one for the query block; OOB rows/columns arrive as zeros)
   auto issue = [&](int it) {
-    if (tid >= 32) return;
+    if (tid != 0) return;
     const int stage = it & 1;
     const int tile = t0 + it / P.nslabs, slab = it % P.nslabs;
-    const int slab_len = min(DS, P.dp - slab * DS);
-    const int64_t cbase = (int64_t)tile * kCBLK;
-    const int crows = (int)min((int64_t)kCBLK, P.nc - cbase);
     const bool load_q = (P.nslabs > 1) || (it == 0);
     float* qdst = qbuf + (size_t)(P.nslabs > 1 ? stage : 0) * QBLK * KQ * DS;
     float* cdst = cbuf + (size_t)stage * KC * kCBLK * DS;
-    uint32_t total;
-    if (P.full_rows) total = (uint32_t)(KC * crows * P.dp * 4) + (load_q ? (uint32_t)(qrows * KQ * P.dp * 4) : 0u);
-    else total = (uint32_t)((KC * crows + (load_q ? qrows * KQ : 0)) * slab_len * 4);
-    if (tid == 0) mbar_arrive_expect_tx(&bars[stage], total);
-    __syncwarp();
-    if (P.full_rows) {
-      if (tid < KC) bulk_g2s(cdst + (size_t)tid * kCBLK * DS, P.cand[tid] + cbase * P.cand_pitch,
-                             (uint32_t)(crows * P.dp * 4), &bars[stage]);
-      if (load_q && tid == KC) bulk_g2s(qdst, P.qvec + q0 * KQ * P.dp, (uint32_t)(qrows * KQ * P.dp * 4), &bars[stage]);
-    } else {
-      for (int i = tid; i < KC * crows; i += 32) {
-        const int k = i / crows, row = i % crows;
-        bulk_g2s(cdst + ((size_t)k * kCBLK + row) * DS, P.cand[k] + (cbase + row) * P.cand_pitch + (size_t)slab * DS,
-                 (uint32_t)(slab_len * 4), &bars[stage]);
-      }
-      if (load_q)
-        for (int i = tid; i < qrows * KQ; i += 32)
-          bulk_g2s(qdst + (size_t)i * DS, P.qvec + (q0 * KQ + i) * P.dp + (size_t)slab * DS,
-                   (uint32_t)(slab_len * 4), &bars[stage]);
-    }
+    const uint32_t total = (uint32_t)((KC * kCBLK + (load_q ? QBLK * KQ : 0)) * DS * 4);
+    mbar_arrive_expect_tx(&bars[stage], total);
+    tma_load_2d(cdst, &TM.c0, slab * DS, tile * kCBLK, &bars[stage]);
+    if (KC == 2) tma_load_2d(cdst + (size_t)kCBLK * DS, &TM.c1, slab * DS, tile * kCBLK, &bars[stage]);
+    if (load_q) tma_load_2d(qdst, &TM.q, slab * DS, (int)(q0 * KQ), &bars[stage]);
   };
 
   // which pair(s) this lane finishes after the reduce-scatter, and its (fixed) query row
@@ -557,10 +553,54 @@ size_t tiled_workspace_bytes(const kge_model_t* m, int64_t Q) {
   return bytes;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver-entry-point lookup (no -lcuda link)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess || !p)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// row-major fp32 matrix [rows, cols] with row pitch `pitch` floats; box {box_cols, box_rows}
+static int make_map(CUtensorMap* tm, const float* base, uint64_t rows, uint64_t cols, uint64_t pitch,
+                    uint32_t box_cols, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled is not available"); return KGE_ECUDA; }
+  const cuuint64_t gdim[2] = {cols, rows};
+  const cuuint64_t gstride[1] = {pitch * sizeof(float)};
+  const cuuint32_t box[2] = {box_cols, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return KGE_ECUDA; }
+  return KGE_OK;
+}
+
 template <int OP, bool L1>
 static int launch_sweep(const TiledParams& P, int QBLK, size_t smem, cudaStream_t st, int splits, int qblocks) {
+  constexpr int KQ = OpTraits<OP>::KQ, KC = OpTraits<OP>::KC;
+  TiledMaps TM;
+  int rc = make_map(&TM.q, P.qvec, (uint64_t)P.Q * KQ, (uint64_t)P.dp, (uint64_t)P.dp, (uint32_t)P.DS, (uint32_t)(QBLK * KQ));
+  if (rc) return rc;
+  rc = make_map(&TM.c0, P.cand[0], (uint64_t)P.nc, (uint64_t)P.dp, (uint64_t)P.cand_pitch, (uint32_t)P.DS, (uint32_t)kCBLK);
+  if (rc) return rc;
+  if (KC == 2) {
+    rc = make_map(&TM.c1, P.cand[1], (uint64_t)P.nc, (uint64_t)P.dp, (uint64_t)P.cand_pitch, (uint32_t)P.DS, (uint32_t)kCBLK);
+    if (rc) return rc;
+  } else {
+    TM.c1 = TM.c0;
+  }
   KGE_CUDA_OK(cudaFuncSetAttribute(sweep_tiled_kernel<OP, L1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  sweep_tiled_kernel<OP, L1><<<dim3((unsigned)splits, (unsigned)qblocks), kTThreads, smem, st>>>(P);
+  sweep_tiled_kernel<OP, L1><<<dim3((unsigned)splits, (unsigned)qblocks), kTThreads, smem, st>>>(P, TM);
   KGE_CHECK_LAUNCH("sweep_tiled_kernel");
   (void)QBLK;
   return KGE_OK;
@@ -642,12 +682,11 @@ int tiled_sweep(const kge_model_t* m, const kge_model_t* mq, int dir, const int6
     return hdr + ((size_t)QBLK * KQ * qstages + (size_t)kCBLK * KC * 2) * (size_t)DS * sizeof(float);
   };
   int DS, nslabs, full;
-  if (bytes_for(dp, 1) <= budget) { DS = dp; nslabs = 1; full = 1; }
+  if (dp <= 256 && bytes_for(dp, 1) <= budget) { DS = dp; nslabs = 1; full = 1; }   // box dims are <= 256
   else {
     DS = 32;
-    while (DS + 32 <= dp && bytes_for(DS + 32, 2) <= budget) DS += 32;
+    while (DS + 32 <= dp && DS + 32 <= 256 && bytes_for(DS + 32, 2) <= budget) DS += 32;
     nslabs = (dp + DS - 1) / DS; full = 0;
-    if (nslabs == 1) { full = 1; DS = dp; }
   }
   const size_t smem = bytes_for(DS, nslabs > 1 ? 2 : 1);
   P.qvec = qvec; P.thr = thr; P.qscale = (model == KGE_TRANSM) ? qscale : nullptr;

@@ -189,6 +189,29 @@ int kge_rank_1vsall(const kge_model_t* m, const kge_model_t* mq, int64_t row_lo,
 #define KGE_RANK_TAIL_ONLY 2
 #define KGE_RANK_HEAD_ONLY 4
 
+/* ---- negative sampling on the device: replaces the CPU sampler processes ----
+ * process_function_pairwise / process_function_pointwise (pykg2vec/data/generator.py:42-158).
+ * The positives (all training triples, generator.py:52,109) are packed as 64-bit keys
+ * (h<<42 | r<<22 | t; < 2^22 entities, < 2^20 relations) into an open-addressing hash set in
+ * device memory: slots[capacity], capacity = kge_tripleset_capacity(n) (power of two >= 2n).
+ * kge_sample_negatives draws, for positive i and j < neg_rate, u ~ U[0,1): the TAIL is corrupted
+ * when u > p (generator.py:73) else the head, p = corrupt_head_prob[r] ("bern",
+ * kgcontroller.py:466-492) or 0.5 when NULL ("uniform"); the replacement entity is redrawn
+ * (at most 64 times) while the corrupted triple is in the set (generator.py:76-77,86-87).
+ * layout 0 (pairwise): out_* are [B*neg_rate], negatives of positive i contiguous;
+ * layout 1 (pointwise): out_* are [B*(1+neg_rate)], each positive followed by its negatives,
+ * out_y = +1 / -1 (generator.py:125-156).  The draw is a pure function of (seed, step, index):
+ * counter-based splitmix64, reproduced bit-for-bit by the CPU oracle. */
+int64_t kge_tripleset_capacity(int64_t n);
+int kge_tripleset_build(const int64_t* h, const int64_t* r, const int64_t* t, int64_t n,
+                        uint64_t* slots, int64_t capacity, int64_t num_ent, int64_t num_rel,
+                        void* stream);
+int kge_sample_negatives(const uint64_t* slots, int64_t capacity, const int64_t* pos_h,
+                         const int64_t* pos_r, const int64_t* pos_t, int64_t B, int32_t neg_rate,
+                         const float* corrupt_head_prob, int64_t num_ent, uint64_t seed, uint64_t step,
+                         int32_t layout, int64_t* out_h, int64_t* out_r, int64_t* out_t,
+                         int64_t* out_y, void* stream);
+
 /* Number of kernels this library has launched since load (all streams); used
  * by bench.py for its gpu_launches claim. */
 int64_t kge_launch_count(void);

@@ -167,6 +167,23 @@ def loss_selfadv(pos, neg, neg_rate, alpha):
     return float(out[0])
 
 
+def sample_negatives(train, ph, pr, pt, neg_rate, head_prob, num_ent, seed, step, layout=0):
+    """train: [n,3] int64 positives.  Returns (h, r, t[, y]) numpy int64 arrays."""
+    train = _i64(train)
+    th, tr, tt = _i64(train[:, 0]), _i64(train[:, 1]), _i64(train[:, 2])
+    ph, pr, pt = _i64(ph), _i64(pr), _i64(pt)
+    B = ph.shape[0]
+    n = B * neg_rate if layout == 0 else B * (1 + neg_rate)
+    oh, orr, ot, oy = (np.zeros(n, dtype=np.int64) for _ in range(4))
+    hp = _f32(head_prob) if head_prob is not None else None
+    rc = lib().kgeo_sample_negatives(_ptr(th), _ptr(tr), _ptr(tt), ctypes.c_int64(th.shape[0]), _ptr(ph), _ptr(pr),
+                                     _ptr(pt), ctypes.c_int64(B), ctypes.c_int32(neg_rate), _ptr(hp),
+                                     ctypes.c_int64(num_ent), ctypes.c_uint64(seed), ctypes.c_uint64(step),
+                                     ctypes.c_int32(layout), _ptr(oh), _ptr(orr), _ptr(ot), _ptr(oy))
+    assert rc == 0
+    return (oh, orr, ot) if layout == 0 else (oh, orr, ot, oy)
+
+
 def normalize_rows(table):
     """in-place Rescal row normalisation of a contiguous fp32 [rows, width] numpy array"""
     assert table.dtype == np.float32 and table.flags["C_CONTIGUOUS"]

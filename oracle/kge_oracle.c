@@ -27,8 +27,9 @@
  * reference itself, generated in the build container by
  * tests/golden/make_golden.py and committed under tests/golden/*.npz
  * (tests/test_oracle_golden.py: scores within 1e-4 relative, ranks exact).
- * HoLE cannot be executed by the installed torch (legacy torch.ifft removed) —
- * parity unpinned for HoLE, which is therefore not implemented here yet.
+ * HoLE cannot be executed by the installed torch (legacy torch.ifft removed): its golden
+ * vectors come from an emulation of the legacy semantics (tests/golden/make_golden.py) —
+ * parity for HoLE is pinned on that emulation, not on a run of the reference's own forward().
  */
 #include <math.h>
 #include <stdint.h>
@@ -477,6 +478,60 @@ int kgeo_sweep_scores(const kge_model_t* m, int grouping, int64_t h, int64_t r, 
                                                      : score_one(m, grouping, e, r, t, scratch);
     free(scratch);
   }
+  return 0;
+}
+
+/* ------------------------------------------------------ negative sampling -- */
+/* process_function_pairwise / _pointwise (generator.py:42-158) with the counter-based generator
+ * specified in include/kge_b200.h (kge_sample_negatives).  The positive set is a sorted array of
+ * packed keys searched by bisection (independent of the device's hash table). */
+static uint64_t mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+static uint64_t pack_key(int64_t h, int64_t r, int64_t t) {
+  return ((uint64_t)h << 42) | ((uint64_t)r << 22) | (uint64_t)t;
+}
+static int cmp_u64(const void* a, const void* b) {
+  const uint64_t x = *(const uint64_t*)a, y = *(const uint64_t*)b;
+  return x < y ? -1 : (x > y ? 1 : 0);
+}
+static int contains(const uint64_t* keys, int64_t n, uint64_t key) {
+  int64_t lo = 0, hi = n;
+  while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (keys[mid] < key) lo = mid + 1; else hi = mid; }
+  return lo < n && keys[lo] == key;
+}
+int kgeo_sample_negatives(const int64_t* th, const int64_t* tr, const int64_t* tt, int64_t ntrain,
+                          const int64_t* ph, const int64_t* pr, const int64_t* pt, int64_t B,
+                          int32_t neg_rate, const float* head_prob, int64_t num_ent, uint64_t seed,
+                          uint64_t step, int32_t layout, int64_t* oh, int64_t* orr, int64_t* ot, int64_t* oy) {
+  uint64_t* keys = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)(ntrain > 0 ? ntrain : 1));
+  for (int64_t i = 0; i < ntrain; ++i) keys[i] = pack_key(th[i], tr[i], tt[i]);
+  qsort(keys, (size_t)ntrain, sizeof(uint64_t), cmp_u64);
+  const uint64_t base = mix64(seed ^ mix64(step));
+  for (int64_t idx = 0; idx < B * neg_rate; ++idx) {
+    const int64_t i = idx / neg_rate, j = idx % neg_rate;
+    const int64_t h = ph[i], r = pr[i], t = pt[i];
+    const uint64_t s0 = mix64(base + (uint64_t)idx);
+    const float u = (float)(s0 >> 40) * (1.0f / 16777216.0f);
+    const float prob = head_prob ? head_prob[r] : 0.5f;
+    const int corrupt_tail = u > prob;
+    int64_t e = 0;
+    for (int a = 0; a < 64; ++a) {
+      e = (int64_t)(((unsigned __int128)mix64(s0 + (uint64_t)a + 1ull) * (unsigned __int128)(uint64_t)num_ent) >> 64);
+      const uint64_t key = corrupt_tail ? pack_key(h, r, e) : pack_key(e, r, t);
+      if (!contains(keys, ntrain, key)) break;
+    }
+    const int64_t o = layout == 0 ? idx : i * (1 + neg_rate) + 1 + j;
+    oh[o] = corrupt_tail ? h : e; orr[o] = r; ot[o] = corrupt_tail ? e : t;
+    if (layout == 1) {
+      oy[o] = -1;
+      if (j == 0) { const int64_t p = i * (1 + neg_rate); oh[p] = h; orr[p] = r; ot[p] = t; oy[p] = 1; }
+    }
+  }
+  free(keys);
   return 0;
 }
 

@@ -28,6 +28,7 @@ EXPORTS = [
     "kge_loss_pairwise_hinge", "kge_loss_pointwise_logistic", "kge_loss_selfadv", "kge_reg_fwd_bwd",
     "kge_train_pairwise_hinge_sgd", "kge_optim_apply_rows",
     "kge_rank_workspace_bytes", "kge_rank_1vsall",
+    "kge_tripleset_capacity", "kge_tripleset_build", "kge_sample_negatives",
 ]
 
 
@@ -61,6 +62,7 @@ def lib():
     L.kge_last_error.restype = ctypes.c_char_p
     L.kge_launch_count.restype = ctypes.c_int64
     L.kge_rank_workspace_bytes.restype = ctypes.c_int64
+    L.kge_tripleset_capacity.restype = ctypes.c_int64
     if L.kge_abi_version() != ABI_VERSION:
         raise KgeError("libkge_b200.so ABI %d != binding ABI %d" % (L.kge_abi_version(), ABI_VERSION))
     _lib = L
@@ -259,6 +261,32 @@ def rank_1vsall(desc, qh, qr, qt, filt_t=None, filt_h=None, counts=None, row_lo=
         _ptr(counts), _ptr(workspace), ctypes.c_int64(workspace.numel()), ctypes.c_int(flags), _stream()),
         "kge_rank_1vsall")
     return counts
+
+
+def tripleset_build(h, r, t, num_ent, num_rel):
+    """Hash set of the positive triples on the device -> uint64-as-int64 tensor [capacity]."""
+    n = h.numel()
+    cap = int(lib().kge_tripleset_capacity(ctypes.c_int64(n)))
+    slots = torch.empty(cap, dtype=torch.int64, device=h.device)
+    check(lib().kge_tripleset_build(_ptr(_dev_i64(h, "h")), _ptr(_dev_i64(r, "r")), _ptr(_dev_i64(t, "t")),
+                                    ctypes.c_int64(n), _ptr(slots), ctypes.c_int64(cap), ctypes.c_int64(num_ent),
+                                    ctypes.c_int64(num_rel), _stream()), "kge_tripleset_build")
+    return slots
+
+
+def sample_negatives(slots, ph, pr, pt, neg_rate, head_prob, num_ent, seed, step, layout=0, out=None):
+    """layout 0 -> (nh, nr, nt) each [B*neg_rate]; layout 1 -> (h, r, t, y) each [B*(1+neg_rate)]."""
+    B = ph.numel()
+    n = B * neg_rate if layout == 0 else B * (1 + neg_rate)
+    if out is None:
+        out = torch.empty((4, n), dtype=torch.int64, device=ph.device)
+    check(lib().kge_sample_negatives(_ptr(slots), ctypes.c_int64(slots.numel()), _ptr(_dev_i64(ph, "ph")),
+                                     _ptr(_dev_i64(pr, "pr")), _ptr(_dev_i64(pt, "pt")), ctypes.c_int64(B),
+                                     ctypes.c_int32(neg_rate), _ptr(head_prob), ctypes.c_int64(num_ent),
+                                     ctypes.c_uint64(seed), ctypes.c_uint64(step), ctypes.c_int32(layout),
+                                     _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]), _stream()),
+          "kge_sample_negatives")
+    return (out[0], out[1], out[2]) if layout == 0 else (out[0], out[1], out[2], out[3])
 
 
 def launch_count():

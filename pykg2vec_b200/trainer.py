@@ -165,6 +165,42 @@ class Trainer:
         self.last_h2d_bytes = 6 * B * 8
         return float(call()[0])
 
+    def train_batch_device(self, ids):
+        """One batch whose id arrays are already DEVICE tensors (pykg2vec_b200.generator.Generator).
+        Returns the loss as a device tensor (no host sync)."""
+        self.model.train()
+        ids = list(ids)
+        strategy = self.model.training_strategy
+        if self._fused:
+            with torch.no_grad():
+                if strategy == TrainingStrategy.PAIRWISE_BASED:
+                    return self._fused_pairwise(ids)
+                if strategy == TrainingStrategy.POINTWISE_BASED:
+                    return self._fused_pointwise(ids)
+                raise NotImplementedError("Unknown training strategy: %s" % strategy)
+        self.optimizer.zero_grad()
+        if strategy == TrainingStrategy.PAIRWISE_BASED:
+            loss = self.train_step_pairwise(*ids)
+        elif strategy == TrainingStrategy.POINTWISE_BASED:
+            loss = self.train_step_pointwise(*ids)
+        else:
+            raise NotImplementedError("Unknown training strategy: %s" % strategy)
+        loss.backward()
+        self.optimizer.step()
+        return loss.detach()
+
+    def train_model_epoch(self, generator, num_batch=None):
+        """Trainer.train_model_epoch (trainer.py:259-307) over a device-side Generator: the
+        accumulated loss stays on the device until the end of the epoch (one sync per epoch
+        instead of one `loss.item()` per batch, trainer.py:300)."""
+        if num_batch is None:
+            num_batch = self.config.tot_train_triples // self.config.batch_size
+        generator.start_one_epoch(num_batch)
+        acc = torch.zeros((), dtype=torch.float32, device=self.config.device)
+        for _ in range(num_batch):
+            acc += self.train_batch_device(next(generator)).reshape(())
+        return float(acc.item())
+
     def train_batch(self, data):
         """data: the list Generator yields — 6 id arrays (pairwise) or 4 (pointwise)."""
         self.model.train()

@@ -277,3 +277,69 @@ def test_rescal_model_normalises_in_place_like_reference():
     np.testing.assert_array_equal(gpu.bits(s.detach().cpu().numpy()), gpu.bits(oracle.score_fwd(om, h, r, t)))
     s.sum().backward()
     assert all(w.grad is not None and float(w.grad.abs().sum()) > 0 for w in m.kge_tables())
+
+
+def test_device_sampler_matches_oracle_and_rules():
+    """kge_sample_negatives == oracle bit-for-bit; negatives never hit a positive; layout and
+    labels follow generator.py:42-158; Bernoulli probabilities steer the corrupted side."""
+    import oracle
+    L = _L()
+    rng = np.random.RandomState(0)
+    N, R, n_train = 60, 4, 2500  # dense graph: rejections do happen
+    train = np.unique(np.stack([rng.randint(N, size=n_train), rng.randint(R, size=n_train),
+                                rng.randint(N, size=n_train)], 1), axis=0)
+    slots = L.tripleset_build(_cuda(train[:, 0].copy()), _cuda(train[:, 1].copy()), _cuda(train[:, 2].copy()), N, R)
+    B = 300
+    sel = rng.randint(len(train), size=B)
+    ph, pr, pt = train[sel, 0].copy(), train[sel, 1].copy(), train[sel, 2].copy()
+    positives = set(map(tuple, train.tolist()))
+    for neg_rate, probs in ((1, None), (4, np.array([0.05, 0.5, 0.95, 0.3], dtype=np.float32))):
+        hp = _cuda(probs) if probs is not None else None
+        nh, nr, nt = L.sample_negatives(slots, _cuda(ph), _cuda(pr), _cuda(pt), neg_rate, hp, N, seed=7, step=3)
+        want = oracle.sample_negatives(train, ph, pr, pt, neg_rate, probs, N, 7, 3)
+        for a, b in zip((nh, nr, nt), want):
+            np.testing.assert_array_equal(a.cpu().numpy(), b)
+        nh, nr, nt = nh.cpu().numpy(), nr.cpu().numpy(), nt.cpu().numpy()
+        rep_h, rep_t = np.repeat(ph, neg_rate), np.repeat(pt, neg_rate)
+        assert np.array_equal(nr, np.repeat(pr, neg_rate))
+        assert all((nh[i] == rep_h[i]) or (nt[i] == rep_t[i]) for i in range(len(nh)))  # one side kept
+        assert not any((int(a), int(b), int(c)) in positives for a, b, c in zip(nh, nr, nt))
+        if probs is not None:
+            head_corrupted = nt == rep_t
+            r_rep = np.repeat(pr, neg_rate)
+            assert head_corrupted[r_rep == 2].mean() > 0.8 and head_corrupted[r_rep == 0].mean() < 0.2
+        # pointwise layout: each positive followed by its negatives, labels +1/-1
+        h4, r4, t4, y4 = L.sample_negatives(slots, _cuda(ph), _cuda(pr), _cuda(pt), neg_rate, hp, N, seed=7, step=3, layout=1)
+        w4 = oracle.sample_negatives(train, ph, pr, pt, neg_rate, probs, N, 7, 3, layout=1)
+        for a, b in zip((h4, r4, t4, y4), w4):
+            np.testing.assert_array_equal(a.cpu().numpy(), b)
+        y = y4.cpu().numpy().reshape(B, 1 + neg_rate)
+        assert (y[:, 0] == 1).all() and (y[:, 1:] == -1).all()
+        assert np.array_equal(h4.cpu().numpy().reshape(B, -1)[:, 0], ph)
+    # a different step gives a different draw
+    a = L.sample_negatives(slots, _cuda(ph), _cuda(pr), _cuda(pt), 1, None, N, seed=7, step=4)
+    b = L.sample_negatives(slots, _cuda(ph), _cuda(pr), _cuda(pt), 1, None, N, seed=7, step=3)
+    assert not (torch.equal(a[0], b[0]) and torch.equal(a[2], b[2]))
+
+
+def test_generator_feeds_trainer_epoch():
+    from pykg2vec_b200.generator import Generator, relation_property
+    from pykg2vec_b200.synthetic import SyntheticKnowledgeGraph
+    kg = SyntheticKnowledgeGraph(300, 5, 4000, 50, 50, seed=3)
+    for model_name, opt in (("transe", "sgd"), ("distmult", "adagrad")):
+        tr = _trainer_for(model_name, kg, optimizer=opt, learning_rate=0.05, hidden_size=32, margin=1.0,
+                          l1_flag=False, lmbda=0.01, batch_size=256, neg_rate=2 if model_name == "distmult" else 1,
+                          sampling="bern")
+        gen = Generator(tr.model, tr.config, seed=1)
+        assert gen.head_prob is not None and gen.head_prob.shape[0] == 5
+        before = [w.detach().clone() for w in tr.model.kge_tables()]
+        loss = tr.train_model_epoch(gen, num_batch=5)
+        assert np.isfinite(loss) and loss > 0
+        assert any(not torch.equal(a, b.detach()) for a, b in zip(before, tr.model.kge_tables()))
+        gen.start_one_epoch(1)
+        batch = next(gen)
+        assert len(batch) == (6 if model_name == "transe" else 4) and all(x.is_cuda for x in batch)
+        with pytest.raises(StopIteration):
+            next(gen)
+    p = relation_property(kg.arrays["train"], 5)
+    assert p.shape == (5,) and ((p > 0) & (p < 1)).all()

@@ -188,6 +188,7 @@ int kge_rank_1vsall(const kge_model_t* m, const kge_model_t* mq, int64_t row_lo,
 #define KGE_RANK_FORCE_GATHER 1 /* use the untiled gather sweep even where a tiled kernel exists */
 #define KGE_RANK_TAIL_ONLY 2
 #define KGE_RANK_HEAD_ONLY 4
+#define KGE_RANK_SINGLE_STREAM 8 /* do not overlap the two directions on an internal side stream */
 
 /* ---- negative sampling on the device: replaces the CPU sampler processes ----
  * process_function_pairwise / process_function_pointwise (pykg2vec/data/generator.py:42-158).

@@ -118,6 +118,30 @@ int model_vec(const kge_model_t* m);
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Fork/join helper: the head-direction chain of a rank call runs on a side stream so that its
+// short preparation / filter kernels overlap the other direction's sweep (and fill the idle
+// SMs of its last wave).  Streams and events are created lazily, once per host thread and device;
+// event record / wait are capture-safe, so the pattern also works inside a CUDA graph capture.
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  int device = -1;
+};
+static int side_stream(SideStream** out) {
+  static thread_local SideStream ss[16];
+  int dev = 0;
+  KGE_CUDA_OK(cudaGetDevice(&dev));
+  SideStream& s = ss[dev & 15];
+  if (!s.stream) {
+    KGE_CUDA_OK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    KGE_CUDA_OK(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
+    KGE_CUDA_OK(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
+    s.device = dev;
+  }
+  *out = &s;
+  return KGE_OK;
+}
+
 }  // namespace kge
 
 using namespace kge;
@@ -172,9 +196,22 @@ extern "C" int kge_rank_1vsall(const kge_model_t* m, const kge_model_t* mq, int6
     if (rc) return rc;
   }
 
+  const bool both = !(flags & (KGE_RANK_HEAD_ONLY | KGE_RANK_TAIL_ONLY));
+  // (CP / SimplE refill one shared candidate scratch per direction: their directions stay serial)
+  const bool dirs_independent = m->model != KGE_CP && m->model != KGE_SIMPLE && m->model != KGE_SIMPLE_IGNR;
+  const bool two_streams = both && use_tiled && dirs_independent && !(flags & KGE_RANK_SINGLE_STREAM);
+  SideStream* side = nullptr;
+  cudaStream_t main_st = st;
+  if (two_streams) {
+    rc = side_stream(&side);
+    if (rc) return rc;
+    KGE_CUDA_OK(cudaEventRecord(side->fork, main_st));          // after candidate preparation
+    KGE_CUDA_OK(cudaStreamWaitEvent(side->stream, side->fork, 0));
+  }
   for (int dir = 0; dir < 2; ++dir) {
     if (dir == 0 && (flags & KGE_RANK_HEAD_ONLY)) continue;
     if (dir == 1 && (flags & KGE_RANK_TAIL_ONLY)) continue;
+    st = (two_streams && dir == 1) ? side->stream : main_st;
     float* thr = dir == 0 ? thr_t : thr_h;
     const int col = dir == 0 ? 0 : 2;
     const int64_t* fptr = dir == 0 ? filt_t_ptr : filt_h_ptr;
@@ -228,6 +265,10 @@ extern "C" int kge_rank_1vsall(const kge_model_t* m, const kge_model_t* mq, int6
 #undef CALL_FILT
       KGE_CHECK_LAUNCH("filter_correct_kernel");
     }
+  }
+  if (two_streams) {
+    KGE_CUDA_OK(cudaEventRecord(side->join, side->stream));
+    KGE_CUDA_OK(cudaStreamWaitEvent(main_st, side->join, 0));
   }
   return KGE_OK;
 }

@@ -521,8 +521,8 @@ static int fill_cand_scratch(const kge_model_t* m, const float* const src[2], in
 
 static float* cand_scratch_ptr(const kge_model_t* m, void* ws, int64_t Q) {
   char* w = reinterpret_cast<char*>(ws);
-  w += align_up((size_t)Q * max_kq(m->model) * dp_of(m) * sizeof(float), 256);
-  w += align_up((size_t)Q * sizeof(float), 256);
+  w += 2 * align_up((size_t)Q * max_kq(m->model) * dp_of(m) * sizeof(float), 256);
+  w += 2 * align_up((size_t)Q * sizeof(float), 256);
   return reinterpret_cast<float*>(w);
 }
 
@@ -545,8 +545,8 @@ bool tiled_supported(const kge_model_t* m) {
 size_t tiled_workspace_bytes(const kge_model_t* m, int64_t Q) {
   if (!tiled_supported(m)) return 0;
   const size_t dp = (size_t)dp_of(m);
-  size_t bytes = align_up((size_t)Q * max_kq(m->model) * dp * sizeof(float), 256);  // qvec
-  bytes += align_up((size_t)Q * sizeof(float), 256);                                  // qscale
+  size_t bytes = 2 * align_up((size_t)Q * max_kq(m->model) * dp * sizeof(float), 256);  // qvec, one per direction
+  bytes += 2 * align_up((size_t)Q * sizeof(float), 256);                                  // qscale, one per direction
   // candidate scratch (always reserved: alignment of the tables is only known at call time);
   // CP sweeps the object table for tails and the subject table for heads -> one table at a time
   bytes += align_up((size_t)num_cand_tables(m->model) * (size_t)m->num_ent * dp * sizeof(float), 256);
@@ -618,13 +618,14 @@ int tiled_sweep(const kge_model_t* m, const kge_model_t* mq, int dir, const int6
   const int KC = num_cand_tables(model);
   const int TQ = (op == OP_ROT_H) ? 2 : 4;
   const int QBLK = kGQ * TQ;
-  // workspace carve-up
+  // workspace carve-up: [qvec dir0][qvec dir1][qscale dir0][qscale dir1][candidate scratch]
+  // (the two directions may run concurrently on two streams, so they never share query buffers)
   char* w = reinterpret_cast<char*>(ws);
-  float* qvec = reinterpret_cast<float*>(w);
-  w += align_up((size_t)Q * max_kq(model) * dp * sizeof(float), 256);
-  float* qscale = reinterpret_cast<float*>(w);
-  w += align_up((size_t)Q * sizeof(float), 256);
-  float* cscratch = reinterpret_cast<float*>(w);
+  const size_t qvec_bytes = align_up((size_t)Q * max_kq(model) * dp * sizeof(float), 256);
+  const size_t qs_bytes = align_up((size_t)Q * sizeof(float), 256);
+  float* qvec = reinterpret_cast<float*>(w + (size_t)dir * qvec_bytes);
+  float* qscale = reinterpret_cast<float*>(w + 2 * qvec_bytes + (size_t)dir * qs_bytes);
+  float* cscratch = cand_scratch_ptr(m, ws, Q);
 
   // 1. query vectors (query-side tables)
   const ModelParams PQ = make_params(mq, mq);

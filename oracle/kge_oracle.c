@@ -298,6 +298,36 @@ static float score_one(const kge_model_t* m, int grouping, int64_t h, int64_t r,
       }
       return -rs_finish(&s);
     }
+    case KGE_ANALOGY: {
+      /* ANALOGY.forward pointwise.py:97-104: ComplEx score on the half-width (d/2) tables plus
+       * DistMult score on the full-width tables; tables [ent, rel, ent_re, ent_im, rel_re, rel_im] */
+      const int d2 = d / 2;
+      const float *he = row(m, 0, h, d), *re_ = row(m, 1, r, d), *te = row(m, 0, t, d);
+      const float *hr = row(m, 2, h, d2), *hi = row(m, 3, h, d2), *rr = row(m, 4, r, d2), *ri = row(m, 5, r, d2),
+                  *tr = row(m, 2, t, d2), *ti = row(m, 3, t, d2);
+      rsum_t sc; rs_init(&sc);
+      for (int j = 0; j < d2; ++j) {
+        float* p = rs_at(&sc, j);
+        if (grouping == KGE_GROUP_TAIL) {
+          const float qr = fmaf(hr[j], rr[j], -(hi[j] * ri[j]));
+          const float qi = fmaf(hi[j], rr[j], hr[j] * ri[j]);
+          *p = fmaf(qr, tr[j], *p);
+          *p = fmaf(qi, ti[j], *p);
+        } else {
+          const float qr = fmaf(tr[j], rr[j], ti[j] * ri[j]);
+          const float qi = fmaf(ti[j], rr[j], -(tr[j] * ri[j]));
+          *p = fmaf(hr[j], qr, *p);
+          *p = fmaf(hi[j], qi, *p);
+        }
+      }
+      rsum_t sd; rs_init(&sd);
+      for (int j = 0; j < d; ++j) {
+        float* p = rs_at(&sd, j);
+        if (grouping == KGE_GROUP_TAIL) { const float q = he[j] * re_[j]; *p = fmaf(q, te[j], *p); }
+        else { const float q = re_[j] * te[j]; *p = fmaf(he[j], q, *p); }
+      }
+      return (-rs_finish(&sc)) - rs_finish(&sd);
+    }
     case KGE_SIMPLE:
     case KGE_SIMPLE_IGNR: {
       /* SimplE.forward pointwise.py:522-526: init = sum(h1 r1 t1) + sum(h2 r2 t2) / 2 (only the second

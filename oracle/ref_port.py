@@ -77,6 +77,12 @@ def score(name, tables, h, r, t, l1_flag=False, margin=0.0, embedding_range=None
         ere, eim, rre, rim = tables
         hr, hi, tr, ti, rr, ri = ere[h], eim[h], ere[t], eim[t], rre[r], rim[r]
         return -torch.sum(hr * tr * rr + hi * ti * rr + hr * ti * ri - hi * tr * ri, -1)
+    if name == "analogy":  # pointwise.py:97-104
+        ent, rel, ere, eim, rre, rim = tables
+        hr, hi, tr, ti, rr, ri = ere[h], eim[h], ere[t], eim[t], rre[r], rim[r]
+        cplx = -(hr * tr * rr + hi * ti * rr + hr * ti * ri - hi * tr * ri).sum(-1)
+        dm = -(ent[h] * rel[r] * ent[t]).sum(-1)
+        return cplx + dm
     if name == "rescal":  # pairwise.py:829-865, on tables already row-normalised by embed()
         ent, mat = tables
         d = ent.shape[1]
@@ -113,6 +119,9 @@ def gathered_rows(name, tables, h, r, t):
     if name == "complex":
         ere, eim, rre, rim = tables
         return [ere[h], eim[h], rre[r], rim[r], ere[t], eim[t]]
+    if name == "analogy":  # two groups with different widths (pointwise.py:106-119)
+        ent, rel, ere, eim, rre, rim = tables
+        return [ere[h], eim[h], rre[r], rim[r], ere[t], eim[t], ent[h], rel[r], ent[t]]
     raise NotImplementedError(name)
 
 

@@ -25,6 +25,7 @@ MODEL_MAP = {
     "cp": ("pykg2vec_b200.pointwise", "CP"),
     "complex": ("pykg2vec_b200.pointwise", "Complex"),
     "complexn3": ("pykg2vec_b200.pointwise", "ComplexN3"),
+    "analogy": ("pykg2vec_b200.pointwise", "ANALOGY"),
     "simple": ("pykg2vec_b200.pointwise", "SimplE"),
     "simple_ignr": ("pykg2vec_b200.pointwise", "SimplE_ignr"),
 }

@@ -40,6 +40,7 @@ int num_tables(int model) {
     case KGE_TRANSE: case KGE_DISTMULT: case KGE_HOLE: case KGE_RESCAL: return 2;
     case KGE_TRANSH: case KGE_TRANSR: case KGE_ROTATE: case KGE_CP: case KGE_TRANSM: return 3;
     case KGE_TRANSD: case KGE_COMPLEX: case KGE_SIMPLE: case KGE_SIMPLE_IGNR: return 4;
+    case KGE_ANALOGY: return 6;
     default: return 0;
   }
 }

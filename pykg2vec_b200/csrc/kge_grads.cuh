@@ -14,8 +14,8 @@
 namespace kge {
 
 struct GradRows {
-  float* h[2];
-  float* t[2];
+  float* h[3];
+  float* t[3];
   float* r[3];
 };
 
@@ -23,9 +23,14 @@ template <int MODEL>
 KGE_DEV void resolve_grad_rows(GradRows& G, const ModelParams& P, float* const* gt, int64_t h,
                                int64_t r, int64_t t) {
   const size_t d = (size_t)P.d, dr = (size_t)P.dr;
-  G.h[0] = G.h[1] = G.t[0] = G.t[1] = G.r[0] = G.r[1] = G.r[2] = nullptr;
+  G.h[0] = G.h[1] = G.t[0] = G.t[1] = G.r[0] = G.r[1] = G.r[2] = G.h[2] = G.t[2] = nullptr;
   auto at = [&](int k, size_t off) -> float* { return gt[k] ? gt[k] + off : nullptr; };
-  if (MODEL == KGE_TRANSE || MODEL == KGE_DISTMULT || MODEL == KGE_TRANSM) {
+  if (MODEL == KGE_ANALOGY) {
+    const size_t d2 = d / 2;
+    G.h[0] = at(0, h * d); G.t[0] = at(0, t * d); G.r[0] = at(1, r * d);
+    G.h[1] = at(2, h * d2); G.h[2] = at(3, h * d2); G.t[1] = at(2, t * d2); G.t[2] = at(3, t * d2);
+    G.r[1] = at(4, r * d2); G.r[2] = at(5, r * d2);
+  } else if (MODEL == KGE_TRANSE || MODEL == KGE_DISTMULT || MODEL == KGE_TRANSM) {
     G.h[0] = at(0, h * d); G.t[0] = at(0, t * d); G.r[0] = at(1, r * d);
   } else if (MODEL == KGE_CP) {
     G.h[0] = at(0, h * d); G.t[0] = at(2, t * d); G.r[0] = at(1, r * d);
@@ -400,6 +405,42 @@ KGE_DEV void grad_group(const TripleRows& R, const GradRows& G, const ModelParam
       red_row_chunk<VEC>(G.r[1], c, d, gri);
       red_row_chunk<VEC>(G.t[0], c, d, gtr);
       red_row_chunk<VEC>(G.t[1], c, d, gti);
+    }
+  } else if (MODEL == KGE_ANALOGY) {
+    const float ng = -gs;
+    const int d2 = d / 2, nch2 = (d2 + 3) >> 2;
+    for (int c = lane; c < nch2; c += 8) {
+      const float4 hr = ld_chunk<VEC>(R.h[1], c, d2), hi = ld_chunk<VEC>(R.h[2], c, d2),
+                   rr = ld_chunk<VEC>(R.r[1], c, d2), ri = ld_chunk<VEC>(R.r[2], c, d2),
+                   tr = ld_chunk<VEC>(R.t[1], c, d2), ti = ld_chunk<VEC>(R.t[2], c, d2);
+      float4 ghr, ghi, grr, gri, gtr, gti;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float a = f4_get(hr, e), b = f4_get(hi, e), p = f4_get(rr, e), q = f4_get(ri, e),
+                    x = f4_get(tr, e), y = f4_get(ti, e);
+        f4_at(ghr, e) = ng * (x * p + y * q);
+        f4_at(ghi, e) = ng * (y * p - x * q);
+        f4_at(gtr, e) = ng * (a * p - b * q);
+        f4_at(gti, e) = ng * (b * p + a * q);
+        f4_at(grr, e) = ng * (a * x + b * y);
+        f4_at(gri, e) = ng * (a * y - b * x);
+      }
+      red_row_chunk<VEC>(G.h[1], c, d2, ghr); red_row_chunk<VEC>(G.h[2], c, d2, ghi);
+      red_row_chunk<VEC>(G.r[1], c, d2, grr); red_row_chunk<VEC>(G.r[2], c, d2, gri);
+      red_row_chunk<VEC>(G.t[1], c, d2, gtr); red_row_chunk<VEC>(G.t[2], c, d2, gti);
+    }
+    for (int c = lane; c < nch; c += 8) {
+      const float4 a = ld_chunk<VEC>(R.h[0], c, d), b = ld_chunk<VEC>(R.r[0], c, d), cc = ld_chunk<VEC>(R.t[0], c, d);
+      float4 gh, gr, gtt;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        f4_at(gh, e) = ng * f4_get(b, e) * f4_get(cc, e);
+        f4_at(gr, e) = ng * f4_get(a, e) * f4_get(cc, e);
+        f4_at(gtt, e) = ng * f4_get(a, e) * f4_get(b, e);
+      }
+      red_row_chunk<VEC>(G.h[0], c, d, gh);
+      red_row_chunk<VEC>(G.r[0], c, d, gr);
+      red_row_chunk<VEC>(G.t[0], c, d, gtt);
     }
   } else if (MODEL == KGE_SIMPLE || MODEL == KGE_SIMPLE_IGNR) {
     const float half = (MODEL == KGE_SIMPLE) ? 0.5f : 1.0f;

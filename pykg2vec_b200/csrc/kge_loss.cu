@@ -115,32 +115,41 @@ reg_kernel(ModelParams P, GradTablesR GT, int reg_type, float scale, const int64
   const int64_t hi = __ldg(h + gi), ri = __ldg(r + gi), ti = __ldg(t + gi);
   TripleRows R;
   resolve_rows<MODEL>(R, P, P.tab, P.tab, P.tab, hi, ri, ti);
-  const float* rows[6] = {R.h[0], R.h[1], R.r[0], R.r[1], R.t[0], R.t[1]};
+  // gathered rows, their widths and their gradient rows (up to 9: ANALOGY)
+  const float* rows[9] = {R.h[0], R.h[1], R.r[0], R.r[1], R.t[0], R.t[1], nullptr, nullptr, nullptr};
+  int width[9] = {P.d, P.d, P.d, P.d, P.d, P.d, P.d, P.d, P.d};
+  float* grows[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   const size_t d = (size_t)P.d;
-  float* grows[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  if (want_grad && valid) {
-    auto at = [&](int k, size_t off) -> float* { return GT.t[k] ? GT.t[k] + off : nullptr; };
-    if (MODEL == KGE_DISTMULT) { grows[0] = at(0, hi * d); grows[2] = at(1, ri * d); grows[4] = at(0, ti * d); }
-    if (MODEL == KGE_CP) { grows[0] = at(0, hi * d); grows[2] = at(1, ri * d); grows[4] = at(2, ti * d); }
-    if (MODEL == KGE_COMPLEX) {
-      grows[0] = at(0, hi * d); grows[1] = at(1, hi * d); grows[2] = at(2, ri * d);
-      grows[3] = at(3, ri * d); grows[4] = at(0, ti * d); grows[5] = at(1, ti * d);
-    }
+  auto at = [&](int k, size_t off) -> float* { return (want_grad && valid && GT.t[k]) ? GT.t[k] + off : nullptr; };
+  if (MODEL == KGE_DISTMULT) { grows[0] = at(0, hi * d); grows[2] = at(1, ri * d); grows[4] = at(0, ti * d); }
+  if (MODEL == KGE_CP) { grows[0] = at(0, hi * d); grows[2] = at(1, ri * d); grows[4] = at(2, ti * d); }
+  if (MODEL == KGE_COMPLEX) {
+    grows[0] = at(0, hi * d); grows[1] = at(1, hi * d); grows[2] = at(2, ri * d);
+    grows[3] = at(3, ri * d); grows[4] = at(0, ti * d); grows[5] = at(1, ti * d);
   }
-  const int nch = (P.d + 3) >> 2;
+  if (MODEL == KGE_ANALOGY) {  // (re, im) half-width rows + full-width rows (pointwise.py:106-119)
+    const size_t d2 = d / 2;
+    rows[0] = R.h[1]; rows[1] = R.h[2]; rows[2] = R.r[1]; rows[3] = R.r[2]; rows[4] = R.t[1]; rows[5] = R.t[2];
+    rows[6] = R.h[0]; rows[7] = R.r[0]; rows[8] = R.t[0];
+    for (int k = 0; k < 6; ++k) width[k] = P.d / 2;
+    grows[0] = at(2, hi * d2); grows[1] = at(3, hi * d2); grows[2] = at(4, ri * d2); grows[3] = at(5, ri * d2);
+    grows[4] = at(2, ti * d2); grows[5] = at(3, ti * d2);
+    grows[6] = at(0, hi * d); grows[7] = at(1, ri * d); grows[8] = at(0, ti * d);
+  }
   float acc = 0.f;
 #pragma unroll
-  for (int k = 0; k < 6; ++k) {
+  for (int k = 0; k < 9; ++k) {
     if (!rows[k]) continue;
-    for (int c = lane; c < nch; c += 8) {
-      const float4 v = ld_chunk<VEC>(rows[k], c, P.d);
+    const int w = width[k], nchk = (w + 3) >> 2;
+    for (int c = lane; c < nchk; c += 8) {
+      const float4 v = ld_chunk<VEC>(rows[k], c, w);
       float4 gv;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         acc += reg_g(f4_get(v, e), reg_type);
         f4_at(gv, e) = grad_scale * scale * reg_dg(f4_get(v, e), reg_type);
       }
-      if (grows[k]) red_chunk<VEC>(grows[k], c, P.d, gv);
+      if (grows[k]) red_chunk<VEC>(grows[k], c, w, gv);
     }
   }
   // block reduction -> one atomic per CTA
@@ -237,7 +246,7 @@ extern "C" int kge_reg_fwd_bwd(const kge_model_t* m, int reg_type, float lmbda, 
   int rc = check_model(m);
   if (rc) return rc;
   if (n <= 0 || !h || !r || !t || !reg_out || reg_type < 0 || reg_type > 2) { set_error("kge_reg_fwd_bwd: bad arguments"); return KGE_EINVAL; }
-  if (m->model != KGE_DISTMULT && m->model != KGE_COMPLEX && m->model != KGE_CP) {
+  if (m->model != KGE_DISTMULT && m->model != KGE_COMPLEX && m->model != KGE_CP && m->model != KGE_ANALOGY) {
     set_error("kge_reg_fwd_bwd: model %d has no row regulariser", m->model); return KGE_ENOTSUP;
   }
   const ModelParams P = make_params(m, nullptr);
@@ -260,6 +269,7 @@ extern "C" int kge_reg_fwd_bwd(const kge_model_t* m, int reg_type, float lmbda, 
   switch (m->model) {
     case KGE_DISTMULT: KGE_DISPATCH_VEC(KGE_DISTMULT, vec, CALL); break;
     case KGE_CP: KGE_DISPATCH_VEC(KGE_CP, vec, CALL); break;
+    case KGE_ANALOGY: KGE_DISPATCH_VEC(KGE_ANALOGY, vec, CALL); break;
     default: KGE_DISPATCH_VEC(KGE_COMPLEX, vec, CALL); break;
   }
 #undef CALL

@@ -10,8 +10,8 @@
 namespace kge {
 
 struct TripleRows {
-  const float* h[2];  // head-side rows   (ent / ent_re, ent_map / ent_im)
-  const float* t[2];  // tail-side rows
+  const float* h[3];  // head-side rows   (ent / ent_re, ent_map / ent_im, ...)
+  const float* t[3];  // tail-side rows
   const float* r[3];  // relation-side rows (rel / rel_re, w / rel_map / rel_im / M_r / theta)
 };
 
@@ -23,8 +23,15 @@ KGE_DEV void resolve_rows(TripleRows& R, const ModelParams& P, const float* cons
                           const float* const* ttab, const float* const* rtab, int64_t h, int64_t r,
                           int64_t t) {
   const size_t d = (size_t)P.d, dr = (size_t)P.dr;
-  R.h[1] = R.t[1] = R.r[1] = R.r[2] = nullptr;
-  if (MODEL == KGE_TRANSE || MODEL == KGE_DISTMULT) {
+  R.h[1] = R.t[1] = R.r[1] = R.r[2] = R.h[2] = R.t[2] = nullptr;
+  if (MODEL == KGE_ANALOGY) {
+    // [ent, rel, ent_re, ent_im, rel_re, rel_im]; slot 0: full-width rows, 1/2: half-width re/im
+    const size_t d2 = d / 2;
+    R.h[0] = htab[0] + h * d; R.t[0] = ttab[0] + t * d; R.r[0] = rtab[1] + r * d;
+    R.h[1] = htab[2] + h * d2; R.h[2] = htab[3] + h * d2;
+    R.t[1] = ttab[2] + t * d2; R.t[2] = ttab[3] + t * d2;
+    R.r[1] = rtab[4] + r * d2; R.r[2] = rtab[5] + r * d2;
+  } else if (MODEL == KGE_TRANSE || MODEL == KGE_DISTMULT) {
     R.h[0] = htab[0] + h * d; R.t[0] = ttab[0] + t * d; R.r[0] = rtab[1] + r * d;
   } else if (MODEL == KGE_TRANSM) {
     R.h[0] = htab[0] + h * d; R.t[0] = ttab[0] + t * d; R.r[0] = rtab[1] + r * d;
@@ -350,6 +357,39 @@ KGE_DEV float score_group(const TripleRows& R, const ModelParams& P, int lane, f
       }
     }
     return -group_sum(acc);
+  } else if (MODEL == KGE_ANALOGY) {
+    // ANALOGY.forward pointwise.py:97-104: ComplEx(d/2) + DistMult(d)
+    const int d2 = d / 2, nch2 = (d2 + 3) >> 2;
+    float ac = 0.f;
+    for (int c = lane; c < nch2; c += 8) {
+      const float4 hr = ld_chunk<VEC>(R.h[1], c, d2), hi = ld_chunk<VEC>(R.h[2], c, d2),
+                   rr = ld_chunk<VEC>(R.r[1], c, d2), ri = ld_chunk<VEC>(R.r[2], c, d2),
+                   tr = ld_chunk<VEC>(R.t[1], c, d2), ti = ld_chunk<VEC>(R.t[2], c, d2);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (GROUPING == KGE_GROUP_TAIL) {
+          const float qr = ffma(f4_get(hr, e), f4_get(rr, e), -fmul(f4_get(hi, e), f4_get(ri, e)));
+          const float qi = ffma(f4_get(hi, e), f4_get(rr, e), fmul(f4_get(hr, e), f4_get(ri, e)));
+          ac = ffma(qr, f4_get(tr, e), ac);
+          ac = ffma(qi, f4_get(ti, e), ac);
+        } else {
+          const float qr = ffma(f4_get(tr, e), f4_get(rr, e), fmul(f4_get(ti, e), f4_get(ri, e)));
+          const float qi = ffma(f4_get(ti, e), f4_get(rr, e), -fmul(f4_get(tr, e), f4_get(ri, e)));
+          ac = ffma(f4_get(hr, e), qr, ac);
+          ac = ffma(f4_get(hi, e), qi, ac);
+        }
+      }
+    }
+    float ad = 0.f;
+    for (int c = lane; c < nch; c += 8) {
+      const float4 a = ld_chunk<VEC>(R.h[0], c, d), b = ld_chunk<VEC>(R.r[0], c, d), cc = ld_chunk<VEC>(R.t[0], c, d);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (GROUPING == KGE_GROUP_TAIL) ad = ffma(fmul(f4_get(a, e), f4_get(b, e)), f4_get(cc, e), ad);
+        else ad = ffma(f4_get(a, e), fmul(f4_get(b, e), f4_get(cc, e)), ad);
+      }
+    }
+    return fsub(-group_sum(ac), group_sum(ad));
   } else if (MODEL == KGE_HOLE) {
     // scratch: rn[dp], qe[dp], g[dp]
     const int dp = nch * 4;
@@ -484,6 +524,7 @@ inline size_t group_scratch_floats(const kge_model_t* m) {
       case KGE_CP: KGE_DISPATCH_VEC(KGE_CP, vec, CALL); break;                     \
       case KGE_TRANSM: KGE_DISPATCH_VEC(KGE_TRANSM, vec, CALL); break;             \
       case KGE_HOLE: KGE_DISPATCH_VEC(KGE_HOLE, vec, CALL); break;                 \
+      case KGE_ANALOGY: KGE_DISPATCH_VEC(KGE_ANALOGY, vec, CALL); break;           \
       case KGE_RESCAL: KGE_DISPATCH_VEC(KGE_RESCAL, vec, CALL); break;             \
       case KGE_SIMPLE: KGE_DISPATCH_VEC(KGE_SIMPLE, vec, CALL); break;             \
       case KGE_SIMPLE_IGNR: KGE_DISPATCH_VEC(KGE_SIMPLE_IGNR, vec, CALL); break;   \

@@ -43,6 +43,7 @@ int check_model(const kge_model_t* m) {
   }
   for (int k = 0; k < nt; ++k)
     if (!m->tables[k]) { set_error("tables[%d] is NULL", k); return KGE_EINVAL; }
+  if (m->model == KGE_ANALOGY && (m->dim % 2)) { set_error("ANALOGY needs an even hidden_size"); return KGE_EINVAL; }
   if (m->model != KGE_TRANSR && m->rel_dim != m->dim) {
     // TransD as written only broadcasts when ent_hidden_size == rel_hidden_size (pairwise.py:275-278)
     set_error("rel_dim (%d) must equal dim (%d) for this model", m->rel_dim, m->dim);
@@ -54,6 +55,10 @@ int check_model(const kge_model_t* m) {
 int model_vec(const kge_model_t* m) {
   const int nt = num_tables(m->model);
   if (m->model == KGE_TRANSM) return pick_vec(m, 2, m->dim);  // theta is a [R] vector, read as scalars
+  if (m->model == KGE_ANALOGY) {  // half-width rows must keep the vector alignment too
+    if (m->dim % 2) return 1;
+    return pick_vec(m, nt, m->dim / 2);
+  }
   if (m->model == KGE_HOLE) return (m->dim % 4 == 0) ? pick_vec(m, nt, m->dim) : 1;  // mirrored scalar reads
   return pick_vec(m, nt, m->dim, m->model == KGE_TRANSR ? m->rel_dim : 0);
 }

@@ -67,7 +67,7 @@ train_hinge_kernel(ModelParams P, GradTablesT GT, const int64_t* __restrict__ ph
 }
 
 // ---- sparse optimizer application ---------------------------------------------
-constexpr int kMaxTasks = 12;
+constexpr int kMaxTasks = 18;
 struct ApplyTasks {
   int ntasks;
   float* w[kMaxTasks];      // table to update
@@ -147,8 +147,11 @@ int check_model(const kge_model_t* m);
 int model_vec(const kge_model_t* m);
 
 // which tables a head / relation / tail id touches, per model
-static int roles(int model, int which /*0 h, 1 r, 2 t*/, int out[2]) {
+static int roles(int model, int which /*0 h, 1 r, 2 t*/, int out[3]) {
   switch (model) {
+    case KGE_ANALOGY:
+      if (which == 1) { out[0] = 1; out[1] = 4; out[2] = 5; return 3; }
+      out[0] = 0; out[1] = 2; out[2] = 3; return 3;
     case KGE_TRANSE: case KGE_DISTMULT: case KGE_TRANSM: case KGE_HOLE: case KGE_RESCAL:
       out[0] = which == 1 ? 1 : 0; return 1;
     case KGE_SIMPLE: case KGE_SIMPLE_IGNR:
@@ -166,6 +169,7 @@ static int table_width(const kge_model_t* m, int k) {
   switch (m->model) {
     case KGE_TRANSR: return k == 0 ? m->dim : (k == 1 ? m->rel_dim : m->dim * m->rel_dim);
     case KGE_RESCAL: return k == 0 ? m->dim : m->dim * m->dim;
+    case KGE_ANALOGY: return k < 2 ? m->dim : m->dim / 2;
     default: return m->dim;
   }
 }
@@ -178,7 +182,7 @@ int launch_apply(const kge_model_t* m, float* const* tables_rw, float* const* gr
   for (int s = 0; s < nsets; ++s) {
     const int64_t* idarr[3] = {hs[s], rs[s], ts[s]};
     for (int which = 0; which < 3; ++which) {
-      int tabs[2];
+      int tabs[3];
       const int nt = roles(m->model, which, tabs);
       for (int q = 0; q < nt; ++q) {
         const int k = tabs[q];

@@ -189,3 +189,41 @@ class SimplE_ignr(SimplE):
         return (cat(self.ent_head_embeddings, h, self.ent_head_embeddings, t),
                 cat(self.rel_embeddings, r, self.rel_inv_embeddings, r),
                 cat(self.ent_tail_embeddings, t, self.ent_tail_embeddings, h))
+
+
+class ANALOGY(_RowRegularised, PointwiseModel):
+    """pykg2vec/models/pointwise.py:13-119: ComplEx on half-width tables + DistMult on full-width."""
+
+    def __init__(self, **kwargs):
+        super(ANALOGY, self).__init__(self.__class__.__name__.lower())
+        param_list = ["tot_entity", "tot_relation", "hidden_size", "lmbda"]
+        param_dict = self.load_params(param_list, kwargs)
+        self.__dict__.update(param_dict)
+        k = self.hidden_size
+        self.ent_embeddings = NamedEmbedding("ent_embedding", self.tot_entity, k)
+        self.rel_embeddings = NamedEmbedding("rel_embedding", self.tot_relation, k)
+        self.ent_embeddings_real = NamedEmbedding("emb_e_real", self.tot_entity, k // 2)
+        self.ent_embeddings_img = NamedEmbedding("emb_e_img", self.tot_entity, k // 2)
+        self.rel_embeddings_real = NamedEmbedding("emb_rel_real", self.tot_relation, k // 2)
+        self.rel_embeddings_img = NamedEmbedding("emb_rel_img", self.tot_relation, k // 2)
+        self.parameter_list = [self.ent_embeddings, self.rel_embeddings, self.ent_embeddings_real,
+                               self.ent_embeddings_img, self.rel_embeddings_real, self.rel_embeddings_img]
+        for e in self.parameter_list:
+            nn.init.xavier_uniform_(e.weight)
+        self.loss = Criterion.pointwise_logistic
+
+    def kge_tables(self):
+        return [e.weight for e in self.parameter_list]
+
+    def kge_spec(self):
+        return ModelSpec("analogy", self.hidden_size)
+
+    def embed(self, h, r, t):
+        return self.ent_embeddings(h), self.rel_embeddings(r), self.ent_embeddings(t)
+
+    def embed_complex(self, h, r, t):
+        return (self.ent_embeddings_real(h), self.ent_embeddings_img(h), self.rel_embeddings_real(r),
+                self.rel_embeddings_img(r), self.ent_embeddings_real(t), self.ent_embeddings_img(t))
+
+    def get_reg(self, h, r, t, reg_type="F2"):
+        return self._reg(h, r, t, reg_type)

@@ -69,6 +69,8 @@ SPECS = {
     "simple_ignr": (ref_pointwise.SimplE_ignr, ["ent_head_embeddings", "ent_tail_embeddings",
                                                 "rel_embeddings", "rel_inv_embeddings"]),
     "hole": (ref_pairwise.HoLE, ["ent_embeddings", "rel_embeddings"]),
+    "analogy": (ref_pointwise.ANALOGY, ["ent_embeddings", "rel_embeddings", "ent_embeddings_real",
+                                        "ent_embeddings_img", "rel_embeddings_real", "rel_embeddings_img"]),
 }
 
 
@@ -109,6 +111,8 @@ CASES = [
     ("rescal_d50", "rescal", 53, 3, dict(hidden_size=50, margin=1.0), "ref"),
     ("simple_d48", "simple", 101, 6, dict(hidden_size=48, lmbda=0.1, tot_train_triples=1000, batch_size=100), "normal"),
     ("simple_ignr_d50", "simple_ignr", 101, 6, dict(hidden_size=50, lmbda=0.1, tot_train_triples=1000, batch_size=100), "normal"),
+    ("analogy_d48", "analogy", 89, 5, dict(hidden_size=48, lmbda=0.1), "normal"),
+    ("analogy_d100", "analogy", 71, 4, dict(hidden_size=100, lmbda=0.1), "ref"),
     ("hole_d30", "hole", 83, 5, dict(hidden_size=30, cmax=0.5, cmin=-0.5), "normal"),
     ("hole_d150", "hole", 61, 4, dict(hidden_size=150, cmax=0.5, cmin=-0.5), "ref"),
 ]
@@ -197,7 +201,7 @@ def make_case(name, model, N, R, kw, init, seed):
         out["grad%d" % i] = emb.weight.grad.detach().numpy().copy()
     out["table_keys"] = np.asarray(keys)
     # regularisers (pointwise models)
-    if model in ("distmult", "complex", "cp"):
+    if model in ("distmult", "complex", "cp", "analogy"):
         with torch.no_grad():
             out["reg_f2"] = np.float32(m.get_reg(ht, rt, tt, reg_type="F2").item())
             out["reg_n3"] = np.float32(m.get_reg(ht, rt, tt, reg_type="N3").item())

@@ -141,3 +141,72 @@ def test_rank_row_shards_add_up():
                       (_cuda(fh[0]), _cuda(fh[1])), counts=counts, row_lo=lo, row_hi=hi, query_desc=qdesc,
                       tgt_h=_cuda(qh), tgt_t=_cuda(qt))
     np.testing.assert_array_equal(counts.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("name,N,R,d", [("transe", 1, 1, 4), ("transe", 5, 2, 3), ("distmult", 33, 1, 1),
+                                        ("complex", 31, 3, 2), ("rotate", 65, 2, 6), ("transh", 2, 1, 5)])
+def test_tiny_and_ragged_shapes(name, N, R, d):
+    """degenerate geometries: fewer entities than one candidate tile, widths below one 16-byte
+    chunk, a single entity (every rank is 0), Q not a multiple of the query block."""
+    import oracle
+    L = _lib()
+    om, _ = gpu.synthetic_case(name, N, R, d, seed=N * 7 + d, margin=3.0 if name == "rotate" else 0.0)
+    desc = gpu.desc_from_oracle_model(om)
+    rng = np.random.RandomState(d)
+    Q = 67
+    qh, qr, qt = rng.randint(N, size=Q), rng.randint(R, size=Q), rng.randint(N, size=Q)
+    s = L.score_fwd(desc, _cuda(qh), _cuda(qr), _cuda(qt)).cpu().numpy()
+    np.testing.assert_array_equal(gpu.bits(s), gpu.bits(oracle.score_fwd(om, qh, qr, qt)))
+    ft, fh = gpu.random_filters_csr(rng, N, qh, qr, qt, per_query=3)
+    want = oracle.rank_1vsall(om, qh, qr, qt, ft, fh)
+    for flags in (0, 1, 8):
+        got = L.rank_1vsall(desc, _cuda(qh), _cuda(qr), _cuda(qt), (_cuda(ft[0]), _cuda(ft[1])),
+                            (_cuda(fh[0]), _cuda(fh[1])), flags=flags).cpu().numpy()
+        np.testing.assert_array_equal(got, want)
+    if N == 1:
+        assert (want == 0).all()
+
+
+def test_rank_direction_flags_and_empty_filters():
+    import oracle
+    L = _lib()
+    om, _ = gpu.synthetic_case("distmult", 300, 4, 64, seed=2)
+    desc = gpu.desc_from_oracle_model(om)
+    rng = np.random.RandomState(1)
+    Q = 9
+    qh, qr, qt = rng.randint(300, size=Q), rng.randint(4, size=Q), rng.randint(300, size=Q)
+    want = oracle.rank_1vsall(om, qh, qr, qt)  # no filters: filtered == raw
+    assert (want[:, 0] == want[:, 1]).all() and (want[:, 2] == want[:, 3]).all()
+    tail = L.rank_1vsall(desc, _cuda(qh), _cuda(qr), _cuda(qt), flags=L.RANK_TAIL_ONLY).cpu().numpy()
+    head = L.rank_1vsall(desc, _cuda(qh), _cuda(qr), _cuda(qt), flags=L.RANK_HEAD_ONLY).cpu().numpy()
+    np.testing.assert_array_equal(tail[:, :2], want[:, :2]); assert (tail[:, 2:] == 0).all()
+    np.testing.assert_array_equal(head[:, 2:], want[:, 2:]); assert (head[:, :2] == 0).all()
+    # all-empty CSR filters (ptr of zeros) behave like no filters
+    z = torch.zeros(Q + 1, dtype=torch.int64, device="cuda")
+    e = torch.zeros(1, dtype=torch.int64, device="cuda")
+    got = L.rank_1vsall(desc, _cuda(qh), _cuda(qr), _cuda(qt), (z, e[:0]), (z, e[:0])).cpu().numpy()
+    np.testing.assert_array_equal(got, want)
+    # too many queries for one call is an argument error, not a crash
+    big = torch.zeros(70000, dtype=torch.int64, device="cuda")
+    with pytest.raises(L.KgeError):
+        L.rank_1vsall(desc, big, big, big)
+
+
+def test_evaluator_batches_large_query_sets():
+    """Evaluator.rank_triples splits > QUERY_BATCH queries into several kernel calls."""
+    import oracle
+    import pykg2vec_b200
+    from pykg2vec_b200.evaluator import Evaluator
+    from pykg2vec_b200.synthetic import SyntheticConfig, SyntheticKnowledgeGraph
+    kg = SyntheticKnowledgeGraph(40, 3, 50, 5, 5, seed=0)
+    cfg = SyntheticConfig(kg, hidden_size=8, l1_flag=True)
+    torch.manual_seed(0)
+    m = pykg2vec_b200.import_model("transe")(**cfg.__dict__).cuda()
+    ev = Evaluator(m, cfg)
+    ev.QUERY_BATCH = 500
+    rng = np.random.RandomState(0)
+    Q = 1203
+    qh, qr, qt = rng.randint(40, size=Q), rng.randint(3, size=Q), rng.randint(40, size=Q)
+    got = ev.rank_triples(qh, qr, qt)
+    om = oracle.Model("transe", [w.detach().cpu().numpy() for w in m.kge_tables()], 8, l1_flag=True)
+    np.testing.assert_array_equal(got, oracle.rank_1vsall(om, qh, qr, qt))

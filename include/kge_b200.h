@@ -53,14 +53,14 @@ enum kge_model_id {
   KGE_TRANSD = 2,   /* [ent, rel, ent_map, rel_map]     pairwise.py:229-278 */
   KGE_TRANSR = 3,   /* [ent, rel, rel_matrix]           pairwise.py:405-470 */
   KGE_ROTATE = 4,   /* [ent_re, ent_im, rel]            pairwise.py:765-791 */
-  KGE_HOLE = 5,     /* [ent, rel]                       pairwise.py:1119-1125 */
+  KGE_HOLE = 5,     /* [ent, rel]  (as evaluated by torch<1.7) pairwise.py:1119-1125 */
   KGE_DISTMULT = 6, /* [ent, rel]                       pointwise.py:444-446 */
   KGE_COMPLEX = 7,  /* [ent_re, ent_im, rel_re, rel_im] pointwise.py:163-188 */
   KGE_CP = 8,       /* [sub, rel, obj]                  pointwise.py:374-376 */
   KGE_SIMPLE = 9,   /* [ent_h, ent_t, rel, rel_inv]     pointwise.py:522-526 */
   KGE_TRANSM = 10,  /* [ent, rel, theta(R x 1)]         pairwise.py:325-347 */
   KGE_RESCAL = 11,  /* [ent, rel_matrices(R x d*d)]     pairwise.py:829-865 */
-  KGE_ANALOGY = 12, /* reserved (not implemented)       pointwise.py:97-104 */
+  KGE_ANALOGY = 12, /* [ent, rel, ent_re, ent_im, rel_re, rel_im] (re/im half width) pointwise.py:97-104 */
   KGE_SIMPLE_IGNR = 13, /* [ent_h, ent_t, rel, rel_inv]  pointwise.py:573-581 */
   KGE_NUM_MODELS = 14
 };

@@ -8,13 +8,14 @@
 // butterfly (4,2,1) is done as a reduce-scatter so that each lane finishes a different pair —
 // hence bit-identical to kge_score_fwd / the gather sweep / the CPU oracle.
 //
-// Data movement (B200): operands are staged in shared memory by bulk-async copies
-// (cp.async.bulk global->shared, completion on an mbarrier; UBLKCP in SASS), double
-// buffered.  Query vectors are prepared once per call (prep_query_kernel) into a compact
-// [Q][KQ][dp] buffer; candidates come straight from the model tables (or from a
-// normalised / padded scratch copy).  Two modes, chosen on the host from the shared-memory
-// budget: "full rows" (query block resident for the whole CTA, one bulk copy per candidate
-// tile) and "slabs" of DS elements of the embedding axis for wide models (d = 500, 1000).
+// Data movement (B200): operand tiles are staged in shared memory by 2-D TMA tensor-map loads
+// (cp.async.bulk.tensor.2d, completion on an mbarrier; UTMALDG.2D in SASS), double buffered;
+// out-of-range rows / columns arrive zero-filled.  Query vectors are prepared once per call
+// (prep_query_kernel, which also yields the thresholds) into a compact [Q][KQ][dp] buffer;
+// candidates come straight from the model tables (or from a normalised / even-part / padded
+// scratch copy).  Two modes, chosen on the host from the shared-memory budget: whole rows (query
+// block resident for the whole CTA, one box per candidate tile) and slabs of DS <= 256 elements
+// of the embedding axis for wide models (d = 500, 1000), accumulators living across slabs.
 //
 // Bound: fp32 pipe (2-8 instructions per element pair), not HBM: a candidate row is read from
 // L2 once per query BLOCK instead of once per query.
@@ -47,7 +48,7 @@ struct TiledParams {
   const float* thr;       // [Q]
   const float* qscale;    // [Q] (TransM theta[r]) or nullptr
   int64_t Q, nc;
-  int dp, DS, nslabs, full_rows;
+  int dp, DS, nslabs;
   int tiles_per_cta, ntiles;
   int32_t* counts;
   int col, l1;
@@ -73,11 +74,6 @@ KGE_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   } while (!ok);
 }
-KGE_DEV void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
 // 2-D tensor-map tile load (TMA): box {DS columns, rows} at (col, row) of a row-major fp32 matrix;
 // out-of-bounds elements are zero-filled and still counted in the transaction bytes.
 KGE_DEV void tma_load_2d(void* dst_smem, const CUtensorMap* tm, int col, int row, uint64_t* bar) {
@@ -682,16 +678,16 @@ int tiled_sweep(const kge_model_t* m, const kge_model_t* mq, int dir, const int6
   auto bytes_for = [&](int DS, int qstages) {
     return hdr + ((size_t)QBLK * KQ * qstages + (size_t)kCBLK * KC * 2) * (size_t)DS * sizeof(float);
   };
-  int DS, nslabs, full;
-  if (dp <= 256 && bytes_for(dp, 1) <= budget) { DS = dp; nslabs = 1; full = 1; }   // box dims are <= 256
+  int DS, nslabs;
+  if (dp <= 256 && bytes_for(dp, 1) <= budget) { DS = dp; nslabs = 1; }   // whole rows; box dims are <= 256
   else {
     DS = 32;
     while (DS + 32 <= dp && DS + 32 <= 256 && bytes_for(DS + 32, 2) <= budget) DS += 32;
-    nslabs = (dp + DS - 1) / DS; full = 0;
+    nslabs = (dp + DS - 1) / DS;
   }
   const size_t smem = bytes_for(DS, nslabs > 1 ? 2 : 1);
   P.qvec = qvec; P.thr = thr; P.qscale = (model == KGE_TRANSM) ? qscale : nullptr;
-  P.Q = Q; P.nc = nc; P.dp = dp; P.DS = DS; P.nslabs = nslabs; P.full_rows = full;
+  P.Q = Q; P.nc = nc; P.dp = dp; P.DS = DS; P.nslabs = nslabs;
   P.ntiles = (int)((nc + kCBLK - 1) / kCBLK);
   const int qblocks = (int)((Q + QBLK - 1) / QBLK);
   const int ctas_per_sm = smem * 2 + 2048 <= 227 * 1024 ? 2 : 1;

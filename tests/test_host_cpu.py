@@ -110,3 +110,28 @@ def test_metric_calculator_walk_equals_counts():
     assert (mc.rank_tail[0], mc.f_rank_tail[0], mc.rank_head[0], mc.f_rank_head[0]) == (raw_t, filt_t, raw_h, filt_h)
     ptr, idx = build_filter_csr([(h, r), (999, 0)], mc.hr_t)
     assert ptr.tolist() == [0, len(mc.hr_t[(h, r)]), len(mc.hr_t[(h, r)])] and set(idx.tolist()) == mc.hr_t[(h, r)]
+
+
+def test_relation_property_matches_reference_definition():
+    """Bernoulli head-corruption probability = |distinct tails| / (|distinct heads| + |distinct tails|)
+    per relation over the training triples (kgcontroller.py:466-492)."""
+    from pykg2vec_b200.generator import relation_property
+    train = np.array([[0, 0, 1], [0, 0, 2], [0, 0, 3], [4, 0, 3],   # r0: heads {0,4}, tails {1,2,3} -> 3/5
+                      [1, 1, 1], [2, 1, 1]])                         # r1: heads {1,2}, tails {1}     -> 1/3
+    p = relation_property(train, 3)
+    assert p[0] == pytest.approx(3 / 5) and p[1] == pytest.approx(1 / 3) and p[2] == 0.0
+
+
+def test_oracle_sampler_rules_on_cpu():
+    """the oracle's negative sampler (the checker of kge_sample_negatives) obeys generator.py:42-158"""
+    import oracle
+    rng = np.random.RandomState(1)
+    train = np.unique(np.stack([rng.randint(30, size=600), rng.randint(3, size=600), rng.randint(30, size=600)], 1), axis=0)
+    pos = train[rng.randint(len(train), size=100)]
+    nh, nr, nt = oracle.sample_negatives(train, pos[:, 0], pos[:, 1], pos[:, 2], 3, None, 30, seed=5, step=0)
+    known = set(map(tuple, train.tolist()))
+    assert not any((int(a), int(b), int(c)) in known for a, b, c in zip(nh, nr, nt))
+    rep = np.repeat(pos, 3, axis=0)
+    assert np.array_equal(nr, rep[:, 1]) and ((nh == rep[:, 0]) | (nt == rep[:, 2])).all()
+    tail_corrupted = (nh == rep[:, 0]).mean()
+    assert 0.3 < tail_corrupted < 0.7  # uniform sampling: p = 0.5

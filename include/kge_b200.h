@@ -35,8 +35,8 @@
 extern "C" {
 #endif
 
-#define KGE_ABI_VERSION 1
-#define KGE_MAX_TABLES 6
+#define KGE_ABI_VERSION 2
+#define KGE_MAX_TABLES 16
 
 /* status codes */
 #define KGE_OK 0
@@ -62,7 +62,9 @@ enum kge_model_id {
   KGE_RESCAL = 11,  /* [ent, rel_matrices(R x d*d)]     pairwise.py:829-865 */
   KGE_ANALOGY = 12, /* [ent, rel, ent_re, ent_im, rel_re, rel_im] (re/im half width) pointwise.py:97-104 */
   KGE_SIMPLE_IGNR = 13, /* [ent_h, ent_t, rel, rel_inv]  pointwise.py:573-581 */
-  KGE_NUM_MODELS = 14
+  KGE_QUATE = 14,   /* [ent_s, ent_x, ent_y, ent_z, rel_s, rel_x, rel_y, rel_z]  pointwise.py:678-694 */
+  KGE_OCTONIONE = 15, /* [ent_1..ent_8, rel_1..rel_8]   pointwise.py:886-899 */
+  KGE_NUM_MODELS = 16
 };
 
 /* Which two operands are combined first.  TAIL: (h,r) are the
@@ -124,8 +126,9 @@ int kge_loss_selfadv(const float* pos, const float* neg, int64_t B, int32_t neg_
 
 /* get_reg() of DistMult / Complex / ComplexN3 (pointwise.py:448-458,190-202,224-238):
  * reg_out[0] = lmbda * mean_i sum_{gathered rows} sum_j g(x_j); g = x^2 (reg_type 0, "F2"),
- * x^3 signed (1, DistMult/Complex "N3"), |x|^3 (2, ComplexN3 "N3").  When grad_tables
- * is non-NULL the gradient scaled by grad_scale is accumulated into it. */
+ * x^3 signed (1, DistMult/Complex "N3"), |x|^3 (2, ComplexN3 "N3").  QuatE / OctonionE
+ * (pointwise.py:696-727, :901-960) average over batch AND width: lmbda * sum_rows mean_{i,j} g(x).
+ * When grad_tables is non-NULL the gradient scaled by grad_scale is accumulated into it. */
 int kge_reg_fwd_bwd(const kge_model_t* m, int reg_type, float lmbda, const int64_t* h,
                     const int64_t* r, const int64_t* t, int64_t n, float* reg_out,
                     float grad_scale, float* const* grad_tables, void* stream);

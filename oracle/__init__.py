@@ -25,10 +25,10 @@ _SO = os.path.join(_OUT_DIR, "libkge_oracle.so")
 MODEL_IDS = {
     "transe": 0, "transh": 1, "transd": 2, "transr": 3, "rotate": 4, "hole": 5,
     "distmult": 6, "complex": 7, "cp": 8, "simple": 9, "transm": 10, "rescal": 11, "analogy": 12,
-    "simple_ignr": 13,
+    "simple_ignr": 13, "quate": 14, "octonione": 15,
 }
 GROUP_TAIL, GROUP_HEAD = 0, 1
-MAX_TABLES = 6
+MAX_TABLES = 16
 
 
 class KgeModel(ctypes.Structure):
@@ -91,7 +91,8 @@ class Model:
         # RotatE: theta = r / (embedding_range / pi)  (pairwise.py:748,776-782)
         self.phase_scale = float(np.float32(np.pi / embedding_range)) if embedding_range else 0.0
         self.num_ent = self.tables[0].shape[0]
-        rel_index = {"rotate": 2, "complex": 2, "simple": 2, "simple_ignr": 2}.get(self.name, 1)
+        rel_index = {"rotate": 2, "complex": 2, "simple": 2, "simple_ignr": 2, "quate": 4,
+                     "octonione": 8}.get(self.name, 1)
         self.num_rel = self.tables[rel_index].shape[0]
 
     def c_struct(self):

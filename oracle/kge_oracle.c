@@ -36,10 +36,11 @@
 #include <stdlib.h>
 #include <string.h>
 
-#define KGE_MAX_TABLES 6
+#define KGE_MAX_TABLES 16
 enum { KGE_TRANSE = 0, KGE_TRANSH = 1, KGE_TRANSD = 2, KGE_TRANSR = 3, KGE_ROTATE = 4,
        KGE_HOLE = 5, KGE_DISTMULT = 6, KGE_COMPLEX = 7, KGE_CP = 8, KGE_SIMPLE = 9,
-       KGE_TRANSM = 10, KGE_RESCAL = 11, KGE_ANALOGY = 12, KGE_SIMPLE_IGNR = 13 };
+       KGE_TRANSM = 10, KGE_RESCAL = 11, KGE_ANALOGY = 12, KGE_SIMPLE_IGNR = 13, KGE_QUATE = 14,
+       KGE_OCTONIONE = 15 };
 enum { KGE_GROUP_TAIL = 0, KGE_GROUP_HEAD = 1 };
 
 typedef struct kge_model {
@@ -124,6 +125,14 @@ float kgeo_expf(float x) {
   return y * two_k.f;
 }
 float kgeo_sigmoidf(float x) { return 1.0f / (1.0f + kgeo_expf(-x)); }
+
+/* Hamilton product, QuatE/OctonionE._qmult (pointwise.py:962-968), canonical fma order */
+static void hyper_qmult(const float A[4], const float B[4], float O[4]) {
+  O[0] = fmaf(-A[3], B[3], fmaf(-A[2], B[2], fmaf(-A[1], B[1], A[0] * B[0])));
+  O[1] = fmaf(-B[2], A[3], fmaf(A[2], B[3], fmaf(B[0], A[1], A[0] * B[1])));
+  O[2] = fmaf(-B[3], A[1], fmaf(A[3], B[1], fmaf(B[0], A[2], A[0] * B[2])));
+  O[3] = fmaf(-B[1], A[2], fmaf(A[1], B[2], fmaf(B[0], A[3], A[0] * B[3])));
+}
 
 /* ------------------------------------------------------- per-model score -- */
 static const float* row(const kge_model_t* m, int k, int64_t i, int width) {
@@ -295,6 +304,37 @@ static float score_one(const kge_model_t* m, int grouping, int64_t h, int64_t r,
           v[j] = acc;
         }
         for (int j = 0; j < d; ++j) { float* p = rs_at(&s, j); *p = fmaf(hv[j], v[j], *p); }
+      }
+      return -rs_finish(&s);
+    }
+    case KGE_QUATE:
+    case KGE_OCTONIONE: {
+      /* QuatE.forward pointwise.py:678-694 / OctonionE.forward pointwise.py:886-899 (+ _qmult, _qstar,
+       * _omult, _onorm :962-1002): per embedding dimension the relation (hyper)complex number is
+       * normalised to unit modulus, multiplied with the head's, and the result is dotted with the
+       * tail's.  tables [ent_1..ent_C, rel_1..rel_C], C = 4 or 8.  Both groupings use this arithmetic. */
+      const int C = (m->model == KGE_QUATE) ? 4 : 8;
+      rsum_t s; rs_init(&s);
+      for (int j = 0; j < d; ++j) {
+        float hc[8], rc[8], tc[8], o[8];
+        for (int c = 0; c < C; ++c) { hc[c] = row(m, c, h, d)[j]; tc[c] = row(m, c, t, d)[j]; rc[c] = row(m, C + c, r, d)[j]; }
+        float den2 = rc[0] * rc[0];
+        for (int c = 1; c < C; ++c) den2 = fmaf(rc[c], rc[c], den2);
+        const float inv = 1.0f / sqrtf(den2);
+        for (int c = 0; c < C; ++c) rc[c] = rc[c] * inv;
+        if (C == 4) {
+          hyper_qmult(hc, rc, o);
+        } else {
+          float dstar[4] = {rc[4], -rc[5], -rc[6], -rc[7]}, cstar[4] = {rc[0], -rc[1], -rc[2], -rc[3]};
+          float p1[4], p2[4], p3[4], p4[4];
+          hyper_qmult(hc, rc, p1);          /* a (x) c   */
+          hyper_qmult(dstar, hc + 4, p2);   /* d* (x) b  */
+          hyper_qmult(rc + 4, hc, p3);      /* d (x) a   */
+          hyper_qmult(hc + 4, cstar, p4);   /* b (x) c*  */
+          for (int c = 0; c < 4; ++c) { o[c] = p1[c] - p2[c]; o[4 + c] = p3[c] + p4[c]; }
+        }
+        float* p = rs_at(&s, j);
+        for (int c = 0; c < C; ++c) *p = fmaf(o[c], tc[c], *p);
       }
       return -rs_finish(&s);
     }
@@ -565,4 +605,4 @@ int kgeo_sample_negatives(const int64_t* th, const int64_t* tr, const int64_t* t
   return 0;
 }
 
-int kgeo_abi_version(void) { return 1; }
+int kgeo_abi_version(void) { return 2; }

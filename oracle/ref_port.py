@@ -77,6 +77,29 @@ def score(name, tables, h, r, t, l1_flag=False, margin=0.0, embedding_range=None
         ere, eim, rre, rim = tables
         hr, hi, tr, ti, rr, ri = ere[h], eim[h], ere[t], eim[t], rre[r], rim[r]
         return -torch.sum(hr * tr * rr + hi * ti * rr + hr * ti * ri - hi * tr * ri, -1)
+    if name in ("quate", "octonione"):  # pointwise.py:678-694 / :886-899 (+ _qmult/_qstar/_omult/_onorm)
+        C = 4 if name == "quate" else 8
+        hc, tc = [tb[h] for tb in tables[:C]], [tb[t] for tb in tables[:C]]
+        rc = [tb[r] for tb in tables[C:2 * C]]
+        den = torch.sqrt(sum(x ** 2 for x in rc))
+        rc = [x / den for x in rc]
+
+        def qmult(a, b):
+            return (a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3],
+                    a[0] * b[1] + b[0] * a[1] + a[2] * b[3] - b[2] * a[3],
+                    a[0] * b[2] + b[0] * a[2] + a[3] * b[1] - b[3] * a[1],
+                    a[0] * b[3] + b[0] * a[3] + a[1] * b[2] - b[1] * a[2])
+
+        def star(a):
+            return (a[0], -a[1], -a[2], -a[3])
+        if C == 4:
+            o = qmult(hc, rc)
+        else:
+            a, b, c, d_ = hc[:4], hc[4:], rc[:4], rc[4:]
+            p1, p2 = qmult(a, c), qmult(star(d_), b)
+            p3, p4 = qmult(d_, a), qmult(b, star(c))
+            o = tuple(x - y for x, y in zip(p1, p2)) + tuple(x + y for x, y in zip(p3, p4))
+        return -torch.sum(sum(x * y for x, y in zip(o, tc)), -1)
     if name == "analogy":  # pointwise.py:97-104
         ent, rel, ere, eim, rre, rim = tables
         hr, hi, tr, ti, rr, ri = ere[h], eim[h], ere[t], eim[t], rre[r], rim[r]
@@ -128,6 +151,11 @@ def gathered_rows(name, tables, h, r, t):
 def reg(name, tables, h, r, t, lmbda, reg_type):
     """reg_type 0: F2 (x**2); 1: signed N3 (x**3, Complex/DistMult 'n3');
     2: |x|**3 (ComplexN3.get_reg, pointwise.py:224-238)."""
+    if name.lower() in ("quate", "octonione"):  # pointwise.py:696-727 / :901-960: mean over [b, d] per table
+        C = 4 if name.lower() == "quate" else 8
+        rows = [tb[h] for tb in tables[:C]] + [tb[t] for tb in tables[:C]] + [tb[r] for tb in tables[C:2 * C]]
+        p = 2 if reg_type == 0 else 3
+        return lmbda * sum(torch.mean(torch.abs(x) ** p) for x in rows)
     rows = gathered_rows(name, tables, h, r, t)
     if reg_type == 0:
         per = sum(torch.sum(x ** 2, -1) for x in rows)

@@ -26,6 +26,8 @@ MODEL_MAP = {
     "complex": ("pykg2vec_b200.pointwise", "Complex"),
     "complexn3": ("pykg2vec_b200.pointwise", "ComplexN3"),
     "analogy": ("pykg2vec_b200.pointwise", "ANALOGY"),
+    "quate": ("pykg2vec_b200.pointwise", "QuatE"),
+    "octonione": ("pykg2vec_b200.pointwise", "OctonionE"),
     "simple": ("pykg2vec_b200.pointwise", "SimplE"),
     "simple_ignr": ("pykg2vec_b200.pointwise", "SimplE_ignr"),
 }

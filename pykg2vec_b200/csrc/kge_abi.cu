@@ -41,6 +41,8 @@ int num_tables(int model) {
     case KGE_TRANSH: case KGE_TRANSR: case KGE_ROTATE: case KGE_CP: case KGE_TRANSM: return 3;
     case KGE_TRANSD: case KGE_COMPLEX: case KGE_SIMPLE: case KGE_SIMPLE_IGNR: return 4;
     case KGE_ANALOGY: return 6;
+    case KGE_QUATE: return 8;
+    case KGE_OCTONIONE: return 16;
     default: return 0;
   }
 }

@@ -28,7 +28,8 @@ score_bwd_kernel(ModelParams P, GradTables GT, const int64_t* __restrict__ h,
   GradRows G;
   resolve_grad_rows<MODEL>(G, P, GT.t, hi, ri, ti);
   if (!valid) {  // idle groups run the math (full-warp shuffles) but scatter nothing
-    G.h[0] = G.h[1] = G.h[2] = G.t[0] = G.t[1] = G.t[2] = G.r[0] = G.r[1] = G.r[2] = nullptr;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) G.h[c] = G.t[c] = G.r[c] = nullptr;
   }
   grad_group<MODEL, VEC, CHSEL>(R, G, P, lane, __ldg(gout + gi), scratch);
 }

@@ -14,18 +14,23 @@
 namespace kge {
 
 struct GradRows {
-  float* h[3];
-  float* t[3];
-  float* r[3];
+  float* h[8];
+  float* t[8];
+  float* r[8];
 };
 
 template <int MODEL>
 KGE_DEV void resolve_grad_rows(GradRows& G, const ModelParams& P, float* const* gt, int64_t h,
                                int64_t r, int64_t t) {
   const size_t d = (size_t)P.d, dr = (size_t)P.dr;
-  G.h[0] = G.h[1] = G.t[0] = G.t[1] = G.r[0] = G.r[1] = G.r[2] = G.h[2] = G.t[2] = nullptr;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) G.h[c] = G.t[c] = G.r[c] = nullptr;
   auto at = [&](int k, size_t off) -> float* { return gt[k] ? gt[k] + off : nullptr; };
-  if (MODEL == KGE_ANALOGY) {
+  if (MODEL == KGE_QUATE || MODEL == KGE_OCTONIONE) {
+    constexpr int C = (MODEL == KGE_QUATE) ? 4 : 8;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { G.h[c] = at(c, h * d); G.t[c] = at(c, t * d); G.r[c] = at(C + c, r * d); }
+  } else if (MODEL == KGE_ANALOGY) {
     const size_t d2 = d / 2;
     G.h[0] = at(0, h * d); G.t[0] = at(0, t * d); G.r[0] = at(1, r * d);
     G.h[1] = at(2, h * d2); G.h[2] = at(3, h * d2); G.t[1] = at(2, t * d2); G.t[2] = at(3, t * d2);
@@ -405,6 +410,65 @@ KGE_DEV void grad_group(const TripleRows& R, const GradRows& G, const ModelParam
       red_row_chunk<VEC>(G.r[1], c, d, gri);
       red_row_chunk<VEC>(G.t[0], c, d, gtr);
       red_row_chunk<VEC>(G.t[1], c, d, gti);
+    }
+  } else if (MODEL == KGE_QUATE || MODEL == KGE_OCTONIONE) {
+    // score = -sum_j <h (x) r^, t>:  d t = -gs * o;  (d h, d r^) through the (bi)linear product;
+    // d r through the per-dimension unit-modulus normalisation.  Scalar atomics (rows are strided).
+    constexpr int C = (MODEL == KGE_QUATE) ? 4 : 8;
+    const float ng = -gs;
+    for (int c = lane; c < nch; c += 8) {
+      for (int e = 0; e < 4; ++e) {
+        const int j = 4 * c + e;
+        if (j >= d) continue;
+        float hc[C], rc[C], tc[C], o[C], dh[C], drn[C];
+        float inv;
+#pragma unroll
+        for (int k = 0; k < C; ++k) { hc[k] = __ldg(R.h[k] + j); rc[k] = __ldg(R.r[k] + j); tc[k] = __ldg(R.t[k] + j); }
+        hyper_product<C>(hc, rc, o, &inv);   // rc now holds r^
+        // dO = ng * t
+        float dO[C];
+#pragma unroll
+        for (int k = 0; k < C; ++k) dO[k] = ng * tc[k];
+        auto qmult_bwd = [](const float* A, const float* B, const float* g, float* dA, float* dB, float sA, float sB) {
+          // out = qmult(A, B); accumulate sA * dA, sB * dB (pointers may be null)
+          if (dA) {
+            dA[0] += sA * ( g[0] * B[0] + g[1] * B[1] + g[2] * B[2] + g[3] * B[3]);
+            dA[1] += sA * (-g[0] * B[1] + g[1] * B[0] - g[2] * B[3] + g[3] * B[2]);
+            dA[2] += sA * (-g[0] * B[2] + g[1] * B[3] + g[2] * B[0] - g[3] * B[1]);
+            dA[3] += sA * (-g[0] * B[3] - g[1] * B[2] + g[2] * B[1] + g[3] * B[0]);
+          }
+          if (dB) {
+            dB[0] += sB * ( g[0] * A[0] + g[1] * A[1] + g[2] * A[2] + g[3] * A[3]);
+            dB[1] += sB * (-g[0] * A[1] + g[1] * A[0] + g[2] * A[3] - g[3] * A[2]);
+            dB[2] += sB * (-g[0] * A[2] - g[1] * A[3] + g[2] * A[0] + g[3] * A[1]);
+            dB[3] += sB * (-g[0] * A[3] + g[1] * A[2] - g[2] * A[1] + g[3] * A[0]);
+          }
+        };
+#pragma unroll
+        for (int k = 0; k < C; ++k) { dh[k] = 0.f; drn[k] = 0.f; }
+        if (C == 4) {
+          qmult_bwd(hc, rc, dO, dh, drn, 1.f, 1.f);
+        } else {
+          const float dstar[4] = {rc[4], -rc[5], -rc[6], -rc[7]}, cstar[4] = {rc[0], -rc[1], -rc[2], -rc[3]};
+          float gds[4] = {0.f, 0.f, 0.f, 0.f}, gcs[4] = {0.f, 0.f, 0.f, 0.f};
+          // o[0..3] = qmult(a, c) - qmult(d*, b);   o[4..7] = qmult(d, a) + qmult(b, c*)
+          qmult_bwd(hc, rc, dO, dh, drn, 1.f, 1.f);                   // a, c
+          qmult_bwd(dstar, hc + 4, dO, gds, dh + 4, -1.f, -1.f);      // d*, b  (minus sign)
+          qmult_bwd(rc + 4, hc, dO + 4, drn + 4, dh, 1.f, 1.f);       // d, a
+          qmult_bwd(hc + 4, cstar, dO + 4, dh + 4, gcs, 1.f, 1.f);    // b, c*
+          drn[4] += gds[0]; drn[5] -= gds[1]; drn[6] -= gds[2]; drn[7] -= gds[3];
+          drn[0] += gcs[0]; drn[1] -= gcs[1]; drn[2] -= gcs[2]; drn[3] -= gcs[3];
+        }
+        float dot = 0.f;
+#pragma unroll
+        for (int k = 0; k < C; ++k) dot += rc[k] * drn[k];
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+          if (G.h[k]) atomicAdd(G.h[k] + j, dh[k]);
+          if (G.t[k]) atomicAdd(G.t[k] + j, ng * o[k]);
+          if (G.r[k]) atomicAdd(G.r[k] + j, (drn[k] - rc[k] * dot) * inv);
+        }
+      }
     }
   } else if (MODEL == KGE_ANALOGY) {
     const float ng = -gs;

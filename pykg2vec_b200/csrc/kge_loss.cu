@@ -115,10 +115,16 @@ reg_kernel(ModelParams P, GradTablesR GT, int reg_type, float scale, const int64
   const int64_t hi = __ldg(h + gi), ri = __ldg(r + gi), ti = __ldg(t + gi);
   TripleRows R;
   resolve_rows<MODEL>(R, P, P.tab, P.tab, P.tab, hi, ri, ti);
-  // gathered rows, their widths and their gradient rows (up to 9: ANALOGY)
-  const float* rows[9] = {R.h[0], R.h[1], R.r[0], R.r[1], R.t[0], R.t[1], nullptr, nullptr, nullptr};
-  int width[9] = {P.d, P.d, P.d, P.d, P.d, P.d, P.d, P.d, P.d};
-  float* grows[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // gathered rows, their widths and their gradient rows (up to 24: OctonionE)
+  constexpr int kMaxRows = (MODEL == KGE_OCTONIONE) ? 24 : (MODEL == KGE_QUATE ? 12 : 9);
+  const float* rows[kMaxRows];
+  int width[kMaxRows];
+  float* grows[kMaxRows];
+#pragma unroll
+  for (int k = 0; k < kMaxRows; ++k) { rows[k] = nullptr; width[k] = P.d; grows[k] = nullptr; }
+  if (MODEL == KGE_DISTMULT || MODEL == KGE_CP || MODEL == KGE_COMPLEX) {
+    rows[0] = R.h[0]; rows[1] = R.h[1]; rows[2] = R.r[0]; rows[3] = R.r[1]; rows[4] = R.t[0]; rows[5] = R.t[1];
+  }
   const size_t d = (size_t)P.d;
   auto at = [&](int k, size_t off) -> float* { return (want_grad && valid && GT.t[k]) ? GT.t[k] + off : nullptr; };
   if (MODEL == KGE_DISTMULT) { grows[0] = at(0, hi * d); grows[2] = at(1, ri * d); grows[4] = at(0, ti * d); }
@@ -136,9 +142,17 @@ reg_kernel(ModelParams P, GradTablesR GT, int reg_type, float scale, const int64
     grows[4] = at(2, ti * d2); grows[5] = at(3, ti * d2);
     grows[6] = at(0, hi * d); grows[7] = at(1, ri * d); grows[8] = at(0, ti * d);
   }
+  if (MODEL == KGE_QUATE || MODEL == KGE_OCTONIONE) {  // pointwise.py:696-727 / :901-960
+    constexpr int C = (MODEL == KGE_QUATE) ? 4 : 8;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      rows[c] = R.h[c]; rows[C + c] = R.t[c]; rows[2 * C + c] = R.r[c];
+      grows[c] = at(c, hi * d); grows[C + c] = at(c, ti * d); grows[2 * C + c] = at(C + c, ri * d);
+    }
+  }
   float acc = 0.f;
 #pragma unroll
-  for (int k = 0; k < 9; ++k) {
+  for (int k = 0; k < kMaxRows; ++k) {
     if (!rows[k]) continue;
     const int w = width[k], nchk = (w + 3) >> 2;
     for (int c = lane; c < nchk; c += 8) {
@@ -246,7 +260,8 @@ extern "C" int kge_reg_fwd_bwd(const kge_model_t* m, int reg_type, float lmbda, 
   int rc = check_model(m);
   if (rc) return rc;
   if (n <= 0 || !h || !r || !t || !reg_out || reg_type < 0 || reg_type > 2) { set_error("kge_reg_fwd_bwd: bad arguments"); return KGE_EINVAL; }
-  if (m->model != KGE_DISTMULT && m->model != KGE_COMPLEX && m->model != KGE_CP && m->model != KGE_ANALOGY) {
+  const bool hyper = (m->model == KGE_QUATE || m->model == KGE_OCTONIONE);
+  if (m->model != KGE_DISTMULT && m->model != KGE_COMPLEX && m->model != KGE_CP && m->model != KGE_ANALOGY && !hyper) {
     set_error("kge_reg_fwd_bwd: model %d has no row regulariser", m->model); return KGE_ENOTSUP;
   }
   const ModelParams P = make_params(m, nullptr);
@@ -263,13 +278,16 @@ extern "C" int kge_reg_fwd_bwd(const kge_model_t* m, int reg_type, float lmbda, 
   cudaStream_t st = (cudaStream_t)stream;
   KGE_CUDA_OK(cudaMemsetAsync(reg_out, 0, sizeof(float), st));
   const unsigned grid = (unsigned)((n + 31) / 32);
-  const float scale = lmbda / (float)n;
+  // QuatE / OctonionE average over the width as well (torch.mean over [b, d] per gathered table)
+  const float scale = hyper ? lmbda / ((float)n * (float)m->dim) : lmbda / (float)n;
   const int want = grad_tables ? 1 : 0;
 #define CALL(M, V) reg_kernel<M, V><<<grid, 256, 0, st>>>(P, GT, reg_type, scale, h, r, t, n, reg_out, grad_scale, want)
   switch (m->model) {
     case KGE_DISTMULT: KGE_DISPATCH_VEC(KGE_DISTMULT, vec, CALL); break;
     case KGE_CP: KGE_DISPATCH_VEC(KGE_CP, vec, CALL); break;
     case KGE_ANALOGY: KGE_DISPATCH_VEC(KGE_ANALOGY, vec, CALL); break;
+    case KGE_QUATE: KGE_DISPATCH_VEC(KGE_QUATE, vec, CALL); break;
+    case KGE_OCTONIONE: KGE_DISPATCH_VEC(KGE_OCTONIONE, vec, CALL); break;
     default: KGE_DISPATCH_VEC(KGE_COMPLEX, vec, CALL); break;
   }
 #undef CALL

@@ -10,9 +10,9 @@
 namespace kge {
 
 struct TripleRows {
-  const float* h[3];  // head-side rows   (ent / ent_re, ent_map / ent_im, ...)
-  const float* t[3];  // tail-side rows
-  const float* r[3];  // relation-side rows (rel / rel_re, w / rel_map / rel_im / M_r / theta)
+  const float* h[8];  // head-side rows   (ent / ent_re, ent_map / ent_im, ... up to 8 octonion parts)
+  const float* t[8];  // tail-side rows
+  const float* r[8];  // relation-side rows (rel / rel_re, w / rel_map / rel_im / M_r / theta)
 };
 
 // Row pointers of triple (h, r, t).  htab/ttab/rtab: the table sets the head-side,
@@ -24,7 +24,11 @@ KGE_DEV void resolve_rows(TripleRows& R, const ModelParams& P, const float* cons
                           int64_t t) {
   const size_t d = (size_t)P.d, dr = (size_t)P.dr;
   R.h[1] = R.t[1] = R.r[1] = R.r[2] = R.h[2] = R.t[2] = nullptr;
-  if (MODEL == KGE_ANALOGY) {
+  if (MODEL == KGE_QUATE || MODEL == KGE_OCTONIONE) {
+    constexpr int C = (MODEL == KGE_QUATE) ? 4 : 8;   // [ent_1..ent_C, rel_1..rel_C]
+#pragma unroll
+    for (int c = 0; c < C; ++c) { R.h[c] = htab[c] + h * d; R.t[c] = ttab[c] + t * d; R.r[c] = rtab[C + c] + r * d; }
+  } else if (MODEL == KGE_ANALOGY) {
     // [ent, rel, ent_re, ent_im, rel_re, rel_im]; slot 0: full-width rows, 1/2: half-width re/im
     const size_t d2 = d / 2;
     R.h[0] = htab[0] + h * d; R.t[0] = ttab[0] + t * d; R.r[0] = rtab[1] + r * d;
@@ -104,6 +108,37 @@ KGE_DEV void hole_query_vector(const float* qe, const float* rn, float* g, int d
       }
     }
     *reinterpret_cast<float4*>(g + 4 * c) = acc;
+  }
+}
+
+// Hamilton product (QuatE/OctonionE._qmult, pointwise.py:962-968) in the canonical fma order
+KGE_DEV void hyper_qmult(const float* A, const float* B, float* O) {
+  O[0] = ffma(-A[3], B[3], ffma(-A[2], B[2], ffma(-A[1], B[1], fmul(A[0], B[0]))));
+  O[1] = ffma(-B[2], A[3], ffma(A[2], B[3], ffma(B[0], A[1], fmul(A[0], B[1]))));
+  O[2] = ffma(-B[3], A[1], ffma(A[3], B[1], ffma(B[0], A[2], fmul(A[0], B[2]))));
+  O[3] = ffma(-B[1], A[2], ffma(A[1], B[2], ffma(B[0], A[3], fmul(A[0], B[3]))));
+}
+// unit-modulus relation (_onorm / QuatE.forward :681-685) and the product h (x) r^ for C = 4 / 8 parts
+template <int C>
+KGE_DEV void hyper_product(const float* hc, float* rc /* in: raw, out: normalised */, float* o, float* inv_out) {
+  float den2 = fmul(rc[0], rc[0]);
+#pragma unroll
+  for (int c = 1; c < C; ++c) den2 = ffma(rc[c], rc[c], den2);
+  const float inv = __frcp_rn(__fsqrt_rn(den2));
+#pragma unroll
+  for (int c = 0; c < C; ++c) rc[c] = fmul(rc[c], inv);
+  if (inv_out) *inv_out = inv;
+  if (C == 4) {
+    hyper_qmult(hc, rc, o);
+  } else {
+    const float dstar[4] = {rc[4], -rc[5], -rc[6], -rc[7]}, cstar[4] = {rc[0], -rc[1], -rc[2], -rc[3]};
+    float p1[4], p2[4], p3[4], p4[4];
+    hyper_qmult(hc, rc, p1);
+    hyper_qmult(dstar, hc + 4, p2);
+    hyper_qmult(rc + 4, hc, p3);
+    hyper_qmult(hc + 4, cstar, p4);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { o[c] = fsub(p1[c], p2[c]); o[4 + c] = fadd(p3[c], p4[c]); }
   }
 }
 
@@ -357,6 +392,25 @@ KGE_DEV float score_group(const TripleRows& R, const ModelParams& P, int lane, f
       }
     }
     return -group_sum(acc);
+  } else if (MODEL == KGE_QUATE || MODEL == KGE_OCTONIONE) {
+    // QuatE.forward pointwise.py:678-694 / OctonionE.forward :886-899 (grouping-independent)
+    constexpr int C = (MODEL == KGE_QUATE) ? 4 : 8;
+    float acc = 0.f;
+    for (int c = lane; c < nch; c += 8) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = 4 * c + e;
+        if (j < d) {
+          float hc[C], rc[C], tc[C], o[C];
+#pragma unroll
+          for (int k = 0; k < C; ++k) { hc[k] = __ldg(R.h[k] + j); rc[k] = __ldg(R.r[k] + j); tc[k] = __ldg(R.t[k] + j); }
+          hyper_product<C>(hc, rc, o, nullptr);
+#pragma unroll
+          for (int k = 0; k < C; ++k) acc = ffma(o[k], tc[k], acc);
+        }
+      }
+    }
+    return -group_sum(acc);
   } else if (MODEL == KGE_ANALOGY) {
     // ANALOGY.forward pointwise.py:97-104: ComplEx(d/2) + DistMult(d)
     const int d2 = d / 2, nch2 = (d2 + 3) >> 2;
@@ -525,6 +579,8 @@ inline size_t group_scratch_floats(const kge_model_t* m) {
       case KGE_TRANSM: KGE_DISPATCH_VEC(KGE_TRANSM, vec, CALL); break;             \
       case KGE_HOLE: KGE_DISPATCH_VEC(KGE_HOLE, vec, CALL); break;                 \
       case KGE_ANALOGY: KGE_DISPATCH_VEC(KGE_ANALOGY, vec, CALL); break;           \
+      case KGE_QUATE: KGE_DISPATCH_VEC(KGE_QUATE, vec, CALL); break;               \
+      case KGE_OCTONIONE: KGE_DISPATCH_VEC(KGE_OCTONIONE, vec, CALL); break;       \
       case KGE_RESCAL: KGE_DISPATCH_VEC(KGE_RESCAL, vec, CALL); break;             \
       case KGE_SIMPLE: KGE_DISPATCH_VEC(KGE_SIMPLE, vec, CALL); break;             \
       case KGE_SIMPLE_IGNR: KGE_DISPATCH_VEC(KGE_SIMPLE_IGNR, vec, CALL); break;   \

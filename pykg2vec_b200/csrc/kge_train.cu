@@ -67,7 +67,7 @@ train_hinge_kernel(ModelParams P, GradTablesT GT, const int64_t* __restrict__ ph
 }
 
 // ---- sparse optimizer application ---------------------------------------------
-constexpr int kMaxTasks = 18;
+constexpr int kMaxTasks = 48;
 struct ApplyTasks {
   int ntasks;
   float* w[kMaxTasks];      // table to update
@@ -147,8 +147,13 @@ int check_model(const kge_model_t* m);
 int model_vec(const kge_model_t* m);
 
 // which tables a head / relation / tail id touches, per model
-static int roles(int model, int which /*0 h, 1 r, 2 t*/, int out[3]) {
+static int roles(int model, int which /*0 h, 1 r, 2 t*/, int out[8]) {
   switch (model) {
+    case KGE_QUATE: case KGE_OCTONIONE: {
+      const int C = model == KGE_QUATE ? 4 : 8;
+      for (int c = 0; c < C; ++c) out[c] = (which == 1 ? C : 0) + c;
+      return C;
+    }
     case KGE_ANALOGY:
       if (which == 1) { out[0] = 1; out[1] = 4; out[2] = 5; return 3; }
       out[0] = 0; out[1] = 2; out[2] = 3; return 3;
@@ -182,7 +187,7 @@ int launch_apply(const kge_model_t* m, float* const* tables_rw, float* const* gr
   for (int s = 0; s < nsets; ++s) {
     const int64_t* idarr[3] = {hs[s], rs[s], ts[s]};
     for (int which = 0; which < 3; ++which) {
-      int tabs[3];
+      int tabs[8];
       const int nt = roles(m->model, which, tabs);
       for (int q = 0; q < nt; ++q) {
         const int k = tabs[q];

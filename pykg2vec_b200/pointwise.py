@@ -227,3 +227,90 @@ class ANALOGY(_RowRegularised, PointwiseModel):
 
     def get_reg(self, h, r, t, reg_type="F2"):
         return self._reg(h, r, t, reg_type)
+
+
+class _HyperComplex(_KernelScored, PointwiseModel):
+    """Shared surface of QuatE / OctonionE: C entity-part tables, C relation-part tables (+ the unused
+    rel_w table the reference also registers), score = -sum <h (x) unit(r), t>."""
+    _kge_name = None
+    _parts = 0
+
+    def kge_tables(self):
+        return [e.weight for e in self.parameter_list[:2 * self._parts]]
+
+    def kge_spec(self):
+        return ModelSpec(self._kge_name, self.hidden_size)
+
+    def get_reg(self, h, r, t, reg_type='N3'):
+        key = reg_type.lower()
+        if key not in ("f2", "n3"):
+            raise NotImplementedError('Unknown regularizer type: %s' % reg_type)
+        # |x|**2 == x**2 (code 0); |x|**3 (code 2); averaged over batch and width by the kernel
+        return RegFunction.apply(self.kge_spec(), 0 if key == "f2" else 2, float(self.lmbda), h, r, t,
+                                 *self.kge_tables())
+
+
+class QuatE(_HyperComplex):
+    """pykg2vec/models/pointwise.py:584-769 (fc / bn / dropout members are registered but unused by
+    forward(), exactly as in the reference, so checkpoints keep their keys)."""
+    _kge_name, _parts = "quate", 4
+
+    def __init__(self, **kwargs):
+        super(QuatE, self).__init__(self.__class__.__name__.lower())
+        param_list = ["tot_entity", "tot_relation", "hidden_size", "lmbda"]
+        param_dict = self.load_params(param_list, kwargs)
+        self.__dict__.update(param_dict)
+        k = self.hidden_size
+        self.ent_s_embedding = NamedEmbedding("ent_s_embedding", self.tot_entity, k)
+        self.ent_x_embedding = NamedEmbedding("ent_x_embedding", self.tot_entity, k)
+        self.ent_y_embedding = NamedEmbedding("ent_y_embedding", self.tot_entity, k)
+        self.ent_z_embedding = NamedEmbedding("ent_z_embedding", self.tot_entity, k)
+        self.rel_s_embedding = NamedEmbedding("rel_s_embedding", self.tot_relation, k)
+        self.rel_x_embedding = NamedEmbedding("rel_x_embedding", self.tot_relation, k)
+        self.rel_y_embedding = NamedEmbedding("rel_y_embedding", self.tot_relation, k)
+        self.rel_z_embedding = NamedEmbedding("rel_z_embedding", self.tot_relation, k)
+        self.rel_w_embedding = NamedEmbedding("rel_w_embedding", self.tot_relation, k)
+        self.fc = nn.Linear(100, 50, bias=False)
+        self.ent_dropout = nn.Dropout(0)
+        self.rel_dropout = nn.Dropout(0)
+        self.bn = nn.BatchNorm1d(k)
+        self.parameter_list = [self.ent_s_embedding, self.ent_x_embedding, self.ent_y_embedding, self.ent_z_embedding,
+                               self.rel_s_embedding, self.rel_x_embedding, self.rel_y_embedding, self.rel_z_embedding,
+                               self.rel_w_embedding]
+        for e in self.parameter_list:  # the reference's quaternion init is overwritten by xavier (:628-636)
+            nn.init.xavier_uniform_(e.weight.data)
+        self.loss = Criterion.pointwise_logistic
+
+    def embed(self, h, r, t):
+        e, rl = self.parameter_list[:4], self.parameter_list[4:8]
+        return tuple(x(h) for x in e) + tuple(x(t) for x in e) + tuple(x(r) for x in rl)
+
+
+class OctonionE(_HyperComplex):
+    """pykg2vec/models/pointwise.py:772-1002."""
+    _kge_name, _parts = "octonione", 8
+
+    def __init__(self, **kwargs):
+        super(OctonionE, self).__init__(self.__class__.__name__.lower())
+        param_list = ["tot_entity", "tot_relation", "hidden_size", "lmbda"]
+        param_dict = self.load_params(param_list, kwargs)
+        self.__dict__.update(param_dict)
+        k = self.hidden_size
+        self.parameter_list = []
+        for i in range(1, 9):
+            emb = NamedEmbedding("ent_embedding_%d" % i, self.tot_entity, k)
+            setattr(self, "ent_embedding_%d" % i, emb)
+            self.parameter_list.append(emb)
+        for i in range(1, 9):
+            emb = NamedEmbedding("rel_embedding_%d" % i, self.tot_relation, k)
+            setattr(self, "rel_embedding_%d" % i, emb)
+            self.parameter_list.append(emb)
+        self.rel_w_embedding = NamedEmbedding("rel_w_embedding", self.tot_relation, k)
+        self.parameter_list.append(self.rel_w_embedding)
+        for e in self.parameter_list:
+            nn.init.xavier_uniform_(e.weight.data)
+        self.loss = Criterion.pointwise_logistic
+
+    def embed(self, h, r, t):
+        e, rl = self.parameter_list[:8], self.parameter_list[8:16]
+        return tuple(x(h) for x in e) + tuple(x(t) for x in e) + tuple(x(r) for x in rl)

@@ -69,6 +69,10 @@ SPECS = {
     "simple_ignr": (ref_pointwise.SimplE_ignr, ["ent_head_embeddings", "ent_tail_embeddings",
                                                 "rel_embeddings", "rel_inv_embeddings"]),
     "hole": (ref_pairwise.HoLE, ["ent_embeddings", "rel_embeddings"]),
+    "quate": (ref_pointwise.QuatE, ["ent_s_embedding", "ent_x_embedding", "ent_y_embedding", "ent_z_embedding",
+                                    "rel_s_embedding", "rel_x_embedding", "rel_y_embedding", "rel_z_embedding"]),
+    "octonione": (ref_pointwise.OctonionE, ["ent_embedding_%d" % i for i in range(1, 9)] +
+                  ["rel_embedding_%d" % i for i in range(1, 9)]),
     "analogy": (ref_pointwise.ANALOGY, ["ent_embeddings", "rel_embeddings", "ent_embeddings_real",
                                         "ent_embeddings_img", "rel_embeddings_real", "rel_embeddings_img"]),
 }
@@ -111,6 +115,10 @@ CASES = [
     ("rescal_d50", "rescal", 53, 3, dict(hidden_size=50, margin=1.0), "ref"),
     ("simple_d48", "simple", 101, 6, dict(hidden_size=48, lmbda=0.1, tot_train_triples=1000, batch_size=100), "normal"),
     ("simple_ignr_d50", "simple_ignr", 101, 6, dict(hidden_size=50, lmbda=0.1, tot_train_triples=1000, batch_size=100), "normal"),
+    ("quate_d20", "quate", 61, 4, dict(hidden_size=20, lmbda=0.1), "normal"),
+    ("quate_d50", "quate", 53, 3, dict(hidden_size=50, lmbda=0.1), "ref"),
+    ("octonione_d12", "octonione", 47, 3, dict(hidden_size=12, lmbda=0.1), "normal"),
+    ("octonione_d50", "octonione", 41, 3, dict(hidden_size=50, lmbda=0.1), "ref"),
     ("analogy_d48", "analogy", 89, 5, dict(hidden_size=48, lmbda=0.1), "normal"),
     ("analogy_d100", "analogy", 71, 4, dict(hidden_size=100, lmbda=0.1), "ref"),
     ("hole_d30", "hole", 83, 5, dict(hidden_size=30, cmax=0.5, cmin=-0.5), "normal"),
@@ -201,6 +209,10 @@ def make_case(name, model, N, R, kw, init, seed):
         out["grad%d" % i] = emb.weight.grad.detach().numpy().copy()
     out["table_keys"] = np.asarray(keys)
     # regularisers (pointwise models)
+    if model in ("quate", "octonione"):
+        with torch.no_grad():
+            out["reg_f2"] = np.float32(m.get_reg(ht, rt, tt, reg_type="F2").item())
+            out["reg_absn3"] = np.float32(m.get_reg(ht, rt, tt, reg_type="N3").item())
     if model in ("distmult", "complex", "cp", "analogy"):
         with torch.no_grad():
             out["reg_f2"] = np.float32(m.get_reg(ht, rt, tt, reg_type="F2").item())

@@ -20,7 +20,7 @@ NUM_TABLE_SPECS = {
     "transe": ["e", "r"], "transh": ["e", "r", "r"], "transd": ["e", "r", "e", "r"],
     "transr": ["e", "r", "M"], "rotate": ["e", "e", "r"], "distmult": ["e", "r"],
     "cp": ["e", "r", "e"], "complex": ["e", "e", "r", "r"], "transm": ["e", "r", "theta"],
-    "analogy": ["e", "r", "e2", "e2", "r2", "r2"], "hole": ["e", "r"], "rescal": ["e", "MM"], "simple": ["e", "e", "r", "r"], "simple_ignr": ["e", "e", "r", "r"],
+    "analogy": ["e", "r", "e2", "e2", "r2", "r2"], "quate": ["e"] * 4 + ["r"] * 4, "octonione": ["e"] * 8 + ["r"] * 8, "hole": ["e", "r"], "rescal": ["e", "MM"], "simple": ["e", "e", "r", "r"], "simple_ignr": ["e", "e", "r", "r"],
 }
 
 

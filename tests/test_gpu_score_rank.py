@@ -71,6 +71,9 @@ SYN = [
     ("hole", 400, 7, 32, None, False, 0.0),
     ("rescal", 500, 5, 48, None, False, 0.0),
     ("rescal", 300, 5, 50, None, False, 0.0),
+    ("quate", 400, 5, 100, None, False, 0.0),
+    ("quate", 300, 5, 30, None, False, 0.0),
+    ("octonione", 300, 5, 48, None, False, 0.0),
     ("analogy", 700, 7, 200, None, False, 0.0),
     ("analogy", 500, 7, 36, None, False, 0.0),
     ("simple", 900, 7, 200, None, False, 0.0),

@@ -32,8 +32,8 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
 
 def test_struct_layout_matches_header():
     from pykg2vec_b200 import _lib
-    # int32 x4, float x2, int64 x2, 6 pointers
-    assert ctypes.sizeof(_lib.KgeModel) == 4 * 4 + 2 * 4 + 2 * 8 + 6 * 8
+    # int32 x4, float x2, int64 x2, 16 pointers
+    assert ctypes.sizeof(_lib.KgeModel) == 4 * 4 + 2 * 4 + 2 * 8 + 16 * 8
     import oracle
     assert ctypes.sizeof(oracle.KgeModel) == ctypes.sizeof(_lib.KgeModel)
     assert _lib.MODEL_IDS == oracle.MODEL_IDS

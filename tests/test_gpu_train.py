@@ -135,7 +135,8 @@ def _make_model(g, device="cuda"):
     cls = pykg2vec_b200.import_model(str(g["model"]))
     m = cls(tot_entity=int(g["N"]), tot_relation=int(g["R"]), **kw)
     sd = {str(k) + ".weight": torch.from_numpy(g["table%d" % i]) for i, k in enumerate(g["table_keys"])}
-    m.load_state_dict(sd)
+    missing = m.load_state_dict(sd, strict=False)  # (QuatE/OctonionE register tables forward() never reads)
+    assert not missing.unexpected_keys
     return m.to(device)
 
 

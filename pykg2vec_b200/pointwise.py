@@ -277,7 +277,14 @@ class QuatE(_HyperComplex):
         self.parameter_list = [self.ent_s_embedding, self.ent_x_embedding, self.ent_y_embedding, self.ent_z_embedding,
                                self.rel_s_embedding, self.rel_x_embedding, self.rel_y_embedding, self.rel_z_embedding,
                                self.rel_w_embedding]
-        for e in self.parameter_list:  # the reference's quaternion init is overwritten by xavier (:628-636)
+        # Reference quirk kept for checkpoint compatibility (pointwise.py:621-636): the four relation
+        # part tables are re-assigned data drawn with in_features = tot_entity, so their weights have
+        # tot_entity rows (only the first tot_relation are ever addressed); everything is then
+        # overwritten by xavier_uniform_.
+        import torch
+        for e in (self.rel_s_embedding, self.rel_x_embedding, self.rel_y_embedding, self.rel_z_embedding):
+            e.weight.data = torch.empty(self.tot_entity, k)
+        for e in self.parameter_list:
             nn.init.xavier_uniform_(e.weight.data)
         self.loss = Criterion.pointwise_logistic
 

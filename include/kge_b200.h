@@ -64,7 +64,8 @@ enum kge_model_id {
   KGE_SIMPLE_IGNR = 13, /* [ent_h, ent_t, rel, rel_inv]  pointwise.py:573-581 */
   KGE_QUATE = 14,   /* [ent_s, ent_x, ent_y, ent_z, rel_s, rel_x, rel_y, rel_z]  pointwise.py:678-694 */
   KGE_OCTONIONE = 15, /* [ent_1..ent_8, rel_1..rel_8]   pointwise.py:886-899 */
-  KGE_NUM_MODELS = 16
+  KGE_KG2E = 16,    /* [ent_mu, ent_sigma, rel_mu, rel_sigma] pairwise.py:1021-1084 */
+  KGE_NUM_MODELS = 17
 };
 
 /* Which two operands are combined first.  TAIL: (h,r) are the

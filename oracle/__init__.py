@@ -25,7 +25,7 @@ _SO = os.path.join(_OUT_DIR, "libkge_oracle.so")
 MODEL_IDS = {
     "transe": 0, "transh": 1, "transd": 2, "transr": 3, "rotate": 4, "hole": 5,
     "distmult": 6, "complex": 7, "cp": 8, "simple": 9, "transm": 10, "rescal": 11, "analogy": 12,
-    "simple_ignr": 13, "quate": 14, "octonione": 15,
+    "simple_ignr": 13, "quate": 14, "octonione": 15, "kg2e": 16,
 }
 GROUP_TAIL, GROUP_HEAD = 0, 1
 MAX_TABLES = 16
@@ -92,7 +92,7 @@ class Model:
         self.phase_scale = float(np.float32(np.pi / embedding_range)) if embedding_range else 0.0
         self.num_ent = self.tables[0].shape[0]
         rel_index = {"rotate": 2, "complex": 2, "simple": 2, "simple_ignr": 2, "quate": 4,
-                     "octonione": 8}.get(self.name, 1)
+                     "octonione": 8, "kg2e": 2}.get(self.name, 1)
         self.num_rel = self.tables[rel_index].shape[0]
 
     def c_struct(self):
@@ -190,6 +190,12 @@ def normalize_rows(table):
     assert table.dtype == np.float32 and table.flags["C_CONTIGUOUS"]
     lib().kgeo_normalize_rows(_ptr(table), ctypes.c_int64(table.shape[0]), ctypes.c_int64(table.shape[1]))
     return table
+
+
+def logf(x):
+    lib().kgeo_logf.restype = ctypes.c_float
+    lib().kgeo_logf.argtypes = [ctypes.c_float]
+    return lib().kgeo_logf(ctypes.c_float(x))
 
 
 def expf(x):

@@ -40,7 +40,7 @@
 enum { KGE_TRANSE = 0, KGE_TRANSH = 1, KGE_TRANSD = 2, KGE_TRANSR = 3, KGE_ROTATE = 4,
        KGE_HOLE = 5, KGE_DISTMULT = 6, KGE_COMPLEX = 7, KGE_CP = 8, KGE_SIMPLE = 9,
        KGE_TRANSM = 10, KGE_RESCAL = 11, KGE_ANALOGY = 12, KGE_SIMPLE_IGNR = 13, KGE_QUATE = 14,
-       KGE_OCTONIONE = 15 };
+       KGE_OCTONIONE = 15, KGE_KG2E = 16 };
 enum { KGE_GROUP_TAIL = 0, KGE_GROUP_HEAD = 1 };
 
 typedef struct kge_model {
@@ -125,6 +125,43 @@ float kgeo_expf(float x) {
   return y * two_k.f;
 }
 float kgeo_sigmoidf(float x) { return 1.0f / (1.0f + kgeo_expf(-x)); }
+
+/* Canonical natural logarithm (Cephes logf in explicit fma; identical on the GPU).  x <= 0 -> -inf / NaN;
+ * subnormal inputs are first scaled by 2^23. */
+float kgeo_logf(float x) {
+  if (!(x > 0.0f)) return x == 0.0f ? -INFINITY : NAN;
+  if (isinf(x)) return x;
+  int e = 0;
+  if (x < 1.17549435e-38f) { x = x * 8388608.0f; e = -23; }
+  union { float f; uint32_t u; } v; v.f = x;
+  e += (int)((v.u >> 23) & 0xff) - 126;
+  v.u = (v.u & 0x007fffffu) | 0x3f000000u;  /* mantissa in [0.5, 1) */
+  float m = v.f;
+  if (m < 0.707106781186547524f) { e -= 1; m = (m + m) - 1.0f; } else { m = m - 1.0f; }
+  const float z = m * m;
+  float y = fmaf(7.0376836292e-2f, m, -1.1514610310e-1f);
+  y = fmaf(y, m, 1.1676998740e-1f);
+  y = fmaf(y, m, -1.2420140846e-1f);
+  y = fmaf(y, m, 1.4249322787e-1f);
+  y = fmaf(y, m, -1.6668057665e-1f);
+  y = fmaf(y, m, 2.0000714765e-1f);
+  y = fmaf(y, m, -2.4999993993e-1f);
+  y = fmaf(y, m, 3.3333331174e-1f);
+  y = (y * m) * z;
+  const float fe = (float)e;
+  y = fmaf(-2.12194440e-4f, fe, y);
+  y = fmaf(-0.5f, z, y);
+  float r = m + y;
+  r = fmaf(0.693359375f, fe, r);
+  return r;
+}
+
+/* 1 / ||x||_2 without epsilon (KG2E.get_normalized_data pairwise.py:1056-1059, Rescal :862-865) */
+static float inv_norm_noeps(const float* x, int d) {
+  rsum_t s; rs_init(&s);
+  for (int j = 0; j < d; ++j) { float* p = rs_at(&s, j); *p = fmaf(x[j], x[j], *p); }
+  return 1.0f / sqrtf(rs_finish(&s));
+}
 
 /* Hamilton product, QuatE/OctonionE._qmult (pointwise.py:962-968), canonical fma order */
 static void hyper_qmult(const float A[4], const float B[4], float O[4]) {
@@ -306,6 +343,27 @@ static float score_one(const kge_model_t* m, int grouping, int64_t h, int64_t r,
         for (int j = 0; j < d; ++j) { float* p = rs_at(&s, j); *p = fmaf(hv[j], v[j], *p); }
       }
       return -rs_finish(&s);
+    }
+    case KGE_KG2E: {
+      /* KG2E.forward/_cal_score_kl_divergence pairwise.py:1021-1084: all six gathered rows are divided
+       * by their L2 norm (no epsilon), then  score = sum (s_h+s_r)/s_t + sum (mu_t-mu_h-mu_r)^2/s_t
+       * + sum (log s_t - log(s_h+s_r)) - d.  tables [ent_mu, ent_sigma, rel_mu, rel_sigma].
+       * Both groupings use this arithmetic. */
+      const float *hm = row(m, 0, h, d), *hs = row(m, 1, h, d), *rm = row(m, 2, r, d), *rsg = row(m, 3, r, d),
+                  *tm = row(m, 0, t, d), *ts = row(m, 1, t, d);
+      const float ihm = inv_norm_noeps(hm, d), ihs = inv_norm_noeps(hs, d), irm = inv_norm_noeps(rm, d),
+                  irs = inv_norm_noeps(rsg, d), itm = inv_norm_noeps(tm, d), its = inv_norm_noeps(ts, d);
+      rsum_t T, M, D; rs_init(&T); rs_init(&M); rs_init(&D);
+      for (int j = 0; j < d; ++j) {
+        const float cs = hs[j] * ihs + rsg[j] * irs;
+        const float cm = hm[j] * ihm + rm[j] * irm;
+        const float st = ts[j] * its;
+        const float x = tm[j] * itm - cm;
+        float* p = rs_at(&T, j); *p = *p + cs / st;
+        p = rs_at(&M, j); *p = *p + (x * x) / st;
+        p = rs_at(&D, j); *p = *p + (kgeo_logf(st) - kgeo_logf(cs));
+      }
+      return ((rs_finish(&T) + rs_finish(&M)) + rs_finish(&D)) - (float)d;
     }
     case KGE_QUATE:
     case KGE_OCTONIONE: {

@@ -77,6 +77,12 @@ def score(name, tables, h, r, t, l1_flag=False, margin=0.0, embedding_range=None
         ere, eim, rre, rim = tables
         hr, hi, tr, ti, rr, ri = ere[h], eim[h], ere[t], eim[t], rre[r], rim[r]
         return -torch.sum(hr * tr * rr + hi * ti * rr + hr * ti * ri - hi * tr * ri, -1)
+    if name == "kg2e":  # pairwise.py:1021-1084
+        emu, esig, rmu, rsig = tables
+        nrm = lambda x: x / torch.norm(x, 2, 1).view(-1, 1)
+        hm, hs, rm, rs_, tm, ts = nrm(emu[h]), nrm(esig[h]), nrm(rmu[r]), nrm(rsig[r]), nrm(emu[t]), nrm(esig[t])
+        cs, cm = hs + rs_, hm + rm
+        return (cs / ts).sum(-1) + ((tm - cm) ** 2 / ts).sum(-1) + (torch.log(ts) - torch.log(cs)).sum(-1) - emu.shape[1]
     if name in ("quate", "octonione"):  # pointwise.py:678-694 / :886-899 (+ _qmult/_qstar/_omult/_onorm)
         C = 4 if name == "quate" else 8
         hc, tc = [tb[h] for tb in tables[:C]], [tb[t] for tb in tables[:C]]

@@ -21,6 +21,7 @@ MODEL_MAP = {
     "rotate": ("pykg2vec_b200.pairwise", "RotatE"),
     "rescal": ("pykg2vec_b200.pairwise", "Rescal"),
     "hole": ("pykg2vec_b200.pairwise", "HoLE"),
+    "kg2e": ("pykg2vec_b200.pairwise", "KG2E"),
     "distmult": ("pykg2vec_b200.pointwise", "DistMult"),
     "cp": ("pykg2vec_b200.pointwise", "CP"),
     "complex": ("pykg2vec_b200.pointwise", "Complex"),

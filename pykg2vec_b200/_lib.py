@@ -16,7 +16,7 @@ ABI_VERSION = 2
 MODEL_IDS = {
     "transe": 0, "transh": 1, "transd": 2, "transr": 3, "rotate": 4, "hole": 5,
     "distmult": 6, "complex": 7, "cp": 8, "simple": 9, "transm": 10, "rescal": 11, "analogy": 12,
-    "simple_ignr": 13, "quate": 14, "octonione": 15,
+    "simple_ignr": 13, "quate": 14, "octonione": 15, "kg2e": 16,
 }
 GROUP_TAIL, GROUP_HEAD = 0, 1
 RANK_FORCE_GATHER, RANK_TAIL_ONLY, RANK_HEAD_ONLY = 1, 2, 4
@@ -111,7 +111,7 @@ class ModelDesc:
         self.margin = float(margin)
         self.phase_scale = float(phase_scale)
         rel_index = {"rotate": 2, "complex": 2, "simple": 2, "simple_ignr": 2, "quate": 4,
-                     "octonione": 8}.get(self.name, 1)
+                     "octonione": 8, "kg2e": 2}.get(self.name, 1)
         self.num_ent = int(num_ent if num_ent is not None else self.tables[0].shape[0])
         self.num_rel = int(num_rel if num_rel is not None else self.tables[rel_index].shape[0])
 

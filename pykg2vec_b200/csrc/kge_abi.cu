@@ -39,7 +39,7 @@ int num_tables(int model) {
   switch (model) {
     case KGE_TRANSE: case KGE_DISTMULT: case KGE_HOLE: case KGE_RESCAL: return 2;
     case KGE_TRANSH: case KGE_TRANSR: case KGE_ROTATE: case KGE_CP: case KGE_TRANSM: return 3;
-    case KGE_TRANSD: case KGE_COMPLEX: case KGE_SIMPLE: case KGE_SIMPLE_IGNR: return 4;
+    case KGE_TRANSD: case KGE_COMPLEX: case KGE_SIMPLE: case KGE_SIMPLE_IGNR: case KGE_KG2E: return 4;
     case KGE_ANALOGY: return 6;
     case KGE_QUATE: return 8;
     case KGE_OCTONIONE: return 16;

@@ -107,6 +107,34 @@ KGE_DEV float exp_canon(float x) {
 }
 KGE_DEV float sigmoid_canon(float x) { return __frcp_rn(fadd(1.0f, exp_canon(-x))); }
 
+// Canonical natural logarithm (Cephes logf in explicit fma; bit-identical to oracle/kge_oracle.c)
+KGE_DEV float log_canon(float x) {
+  if (!(x > 0.0f)) return x == 0.0f ? -INFINITY : NAN;
+  if (isinf(x)) return x;
+  int e = 0;
+  if (x < 1.17549435e-38f) { x = fmul(x, 8388608.0f); e = -23; }
+  unsigned u = __float_as_uint(x);
+  e += (int)((u >> 23) & 0xff) - 126;
+  float m = __uint_as_float((u & 0x007fffffu) | 0x3f000000u);
+  if (m < 0.707106781186547524f) { e -= 1; m = fsub(fadd(m, m), 1.0f); } else { m = fsub(m, 1.0f); }
+  const float z = fmul(m, m);
+  float y = ffma(7.0376836292e-2f, m, -1.1514610310e-1f);
+  y = ffma(y, m, 1.1676998740e-1f);
+  y = ffma(y, m, -1.2420140846e-1f);
+  y = ffma(y, m, 1.4249322787e-1f);
+  y = ffma(y, m, -1.6668057665e-1f);
+  y = ffma(y, m, 2.0000714765e-1f);
+  y = ffma(y, m, -2.4999993993e-1f);
+  y = ffma(y, m, 3.3333331174e-1f);
+  y = fmul(fmul(y, m), z);
+  const float fe = (float)e;
+  y = ffma(-2.12194440e-4f, fe, y);
+  y = ffma(-0.5f, z, y);
+  float r = fadd(m, y);
+  r = ffma(0.693359375f, fe, r);
+  return r;
+}
+
 // One 4-element chunk c of a row of width d (elements 4c..4c+3; elements >= d read as 0,
 // which is an exact identity for every accumulation used here).
 template <int VEC>

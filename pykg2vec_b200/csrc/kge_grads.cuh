@@ -26,7 +26,10 @@ KGE_DEV void resolve_grad_rows(GradRows& G, const ModelParams& P, float* const* 
 #pragma unroll
   for (int c = 0; c < 8; ++c) G.h[c] = G.t[c] = G.r[c] = nullptr;
   auto at = [&](int k, size_t off) -> float* { return gt[k] ? gt[k] + off : nullptr; };
-  if (MODEL == KGE_QUATE || MODEL == KGE_OCTONIONE) {
+  if (MODEL == KGE_KG2E) {
+    G.h[0] = at(0, h * d); G.h[1] = at(1, h * d); G.t[0] = at(0, t * d); G.t[1] = at(1, t * d);
+    G.r[0] = at(2, r * d); G.r[1] = at(3, r * d);
+  } else if (MODEL == KGE_QUATE || MODEL == KGE_OCTONIONE) {
     constexpr int C = (MODEL == KGE_QUATE) ? 4 : 8;
 #pragma unroll
     for (int c = 0; c < C; ++c) { G.h[c] = at(c, h * d); G.t[c] = at(c, t * d); G.r[c] = at(C + c, r * d); }
@@ -411,6 +414,53 @@ KGE_DEV void grad_group(const TripleRows& R, const GradRows& G, const ModelParam
       red_row_chunk<VEC>(G.t[0], c, d, gtr);
       red_row_chunk<VEC>(G.t[1], c, d, gti);
     }
+  } else if (MODEL == KGE_KG2E) {
+    // rows k: 0 h_mu, 1 h_sigma, 2 r_mu, 3 r_sigma, 4 t_mu, 5 t_sigma; y^ = y / ||y||
+    const float* rows6[6] = {R.h[0], R.h[1], R.r[0], R.r[1], R.t[0], R.t[1]};
+    float* grows6[6] = {G.h[0], G.h[1], G.r[0], G.r[1], G.t[0], G.t[1]};
+    float inv[6], dot[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      float s = 0.f;
+      for (int c = lane; c < nch; c += 8) {
+        const float4 x = ld_chunk<VEC>(rows6[k], c, d);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s = ffma(f4_get(x, e), f4_get(x, e), s);
+      }
+      inv[k] = __frcp_rn(__fsqrt_rn(group_sum(s)));
+      dot[k] = 0.f;
+    }
+    // d score / d normalised operands at element j
+    auto elem = [&](int j, float (&y)[6], float (&dy)[6]) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) y[k] = __ldg(rows6[k] + j) * inv[k];
+      const float cs = y[1] + y[3], cm = y[0] + y[2], st = y[5], x = y[4] - cm;
+      const float ist = 1.f / st, ics = 1.f / cs;
+      dy[0] = -2.f * x * ist; dy[2] = dy[0]; dy[4] = 2.f * x * ist;
+      dy[1] = ist - ics; dy[3] = dy[1];
+      dy[5] = (-(cs + x * x) * ist + 1.f) * ist;
+    };
+    for (int c = lane; c < nch; c += 8)
+      for (int e = 0; e < 4; ++e) {
+        const int j = 4 * c + e;
+        if (j >= d) continue;
+        float y[6], dy[6];
+        elem(j, y, dy);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) dot[k] += y[k] * dy[k];
+      }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) dot[k] = group_sum(dot[k]);
+    for (int c = lane; c < nch; c += 8)
+      for (int e = 0; e < 4; ++e) {
+        const int j = 4 * c + e;
+        if (j >= d) continue;
+        float y[6], dy[6];
+        elem(j, y, dy);
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+          if (grows6[k]) atomicAdd(grows6[k] + j, gs * (dy[k] - y[k] * dot[k]) * inv[k]);
+      }
   } else if (MODEL == KGE_QUATE || MODEL == KGE_OCTONIONE) {
     // score = -sum_j <h (x) r^, t>:  d t = -gs * o;  (d h, d r^) through the (bi)linear product;
     // d r through the per-dimension unit-modulus normalisation.  Scalar atomics (rows are strided).

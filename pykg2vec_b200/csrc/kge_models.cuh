@@ -24,7 +24,10 @@ KGE_DEV void resolve_rows(TripleRows& R, const ModelParams& P, const float* cons
                           int64_t t) {
   const size_t d = (size_t)P.d, dr = (size_t)P.dr;
   R.h[1] = R.t[1] = R.r[1] = R.r[2] = R.h[2] = R.t[2] = nullptr;
-  if (MODEL == KGE_QUATE || MODEL == KGE_OCTONIONE) {
+  if (MODEL == KGE_KG2E) {  // [ent_mu, ent_sigma, rel_mu, rel_sigma]
+    R.h[0] = htab[0] + h * d; R.h[1] = htab[1] + h * d; R.t[0] = ttab[0] + t * d; R.t[1] = ttab[1] + t * d;
+    R.r[0] = rtab[2] + r * d; R.r[1] = rtab[3] + r * d;
+  } else if (MODEL == KGE_QUATE || MODEL == KGE_OCTONIONE) {
     constexpr int C = (MODEL == KGE_QUATE) ? 4 : 8;   // [ent_1..ent_C, rel_1..rel_C]
 #pragma unroll
     for (int c = 0; c < C; ++c) { R.h[c] = htab[c] + h * d; R.t[c] = ttab[c] + t * d; R.r[c] = rtab[C + c] + r * d; }
@@ -392,6 +395,39 @@ KGE_DEV float score_group(const TripleRows& R, const ModelParams& P, int lane, f
       }
     }
     return -group_sum(acc);
+  } else if (MODEL == KGE_KG2E) {
+    // KG2E.forward / _cal_score_kl_divergence pairwise.py:1021-1084 (grouping-independent)
+    const float* rows6[6] = {R.h[0], R.h[1], R.r[0], R.r[1], R.t[0], R.t[1]};
+    float inv[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      float s = 0.f;
+      for (int c = lane; c < nch; c += 8) {
+        const float4 x = ld_chunk<VEC>(rows6[k], c, d);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s = ffma(f4_get(x, e), f4_get(x, e), s);
+      }
+      inv[k] = __frcp_rn(__fsqrt_rn(group_sum(s)));
+    }
+    float T = 0.f, M = 0.f, D = 0.f;
+    for (int c = lane; c < nch; c += 8) {
+      const float4 hm = ld_chunk<VEC>(R.h[0], c, d), hs = ld_chunk<VEC>(R.h[1], c, d), rm = ld_chunk<VEC>(R.r[0], c, d),
+                   rs = ld_chunk<VEC>(R.r[1], c, d), tm = ld_chunk<VEC>(R.t[0], c, d), ts = ld_chunk<VEC>(R.t[1], c, d);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (4 * c + e < d) {  // (padding would feed 0/0 into the divisions)
+          const float cs = fadd(fmul(f4_get(hs, e), inv[1]), fmul(f4_get(rs, e), inv[3]));
+          const float cm = fadd(fmul(f4_get(hm, e), inv[0]), fmul(f4_get(rm, e), inv[2]));
+          const float st = fmul(f4_get(ts, e), inv[5]);
+          const float x = fsub(fmul(f4_get(tm, e), inv[4]), cm);
+          T = fadd(T, __fdiv_rn(cs, st));
+          M = fadd(M, __fdiv_rn(fmul(x, x), st));
+          D = fadd(D, fsub(log_canon(st), log_canon(cs)));
+        }
+      }
+    }
+    T = group_sum(T); M = group_sum(M); D = group_sum(D);
+    return fsub(fadd(fadd(T, M), D), (float)d);
   } else if (MODEL == KGE_QUATE || MODEL == KGE_OCTONIONE) {
     // QuatE.forward pointwise.py:678-694 / OctonionE.forward :886-899 (grouping-independent)
     constexpr int C = (MODEL == KGE_QUATE) ? 4 : 8;
@@ -580,6 +616,7 @@ inline size_t group_scratch_floats(const kge_model_t* m) {
       case KGE_HOLE: KGE_DISPATCH_VEC(KGE_HOLE, vec, CALL); break;                 \
       case KGE_ANALOGY: KGE_DISPATCH_VEC(KGE_ANALOGY, vec, CALL); break;           \
       case KGE_QUATE: KGE_DISPATCH_VEC(KGE_QUATE, vec, CALL); break;               \
+      case KGE_KG2E: KGE_DISPATCH_VEC(KGE_KG2E, vec, CALL); break;                 \
       case KGE_OCTONIONE: KGE_DISPATCH_VEC(KGE_OCTONIONE, vec, CALL); break;       \
       case KGE_RESCAL: KGE_DISPATCH_VEC(KGE_RESCAL, vec, CALL); break;             \
       case KGE_SIMPLE: KGE_DISPATCH_VEC(KGE_SIMPLE, vec, CALL); break;             \

@@ -166,7 +166,8 @@ static int roles(int model, int which /*0 h, 1 r, 2 t*/, int out[8]) {
     case KGE_TRANSR: if (which == 1) { out[0] = 1; out[1] = 2; return 2; } out[0] = 0; return 1;
     case KGE_TRANSD: if (which == 1) { out[0] = 1; out[1] = 3; return 2; } out[0] = 0; out[1] = 2; return 2;
     case KGE_ROTATE: if (which == 1) { out[0] = 2; return 1; } out[0] = 0; out[1] = 1; return 2;
-    case KGE_COMPLEX: if (which == 1) { out[0] = 2; out[1] = 3; return 2; } out[0] = 0; out[1] = 1; return 2;
+    case KGE_COMPLEX: case KGE_KG2E:
+      if (which == 1) { out[0] = 2; out[1] = 3; return 2; } out[0] = 0; out[1] = 1; return 2;
     default: return 0;
   }
 }

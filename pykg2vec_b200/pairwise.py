@@ -311,3 +311,41 @@ class HoLE(_KernelScored, PairwiseModel):
 
     def embed(self, h, r, t):
         return self.ent_embeddings(h), self.rel_embeddings(r), self.ent_embeddings(t)
+
+
+class KG2E(_KernelScored, PairwiseModel):
+    """pykg2vec/models/pairwise.py:966-1084 (KL-divergence score on row-normalised means/variances)."""
+
+    def __init__(self, **kwargs):
+        super(KG2E, self).__init__(self.__class__.__name__.lower())
+        param_list = ["tot_entity", "tot_relation", "hidden_size", "cmax", "cmin"]
+        param_dict = self.load_params(param_list, kwargs)
+        self.__dict__.update(param_dict)
+        self.ent_embeddings_mu = NamedEmbedding("ent_embeddings_mu", self.tot_entity, self.hidden_size)
+        self.rel_embeddings_mu = NamedEmbedding("rel_embeddings_mu", self.tot_relation, self.hidden_size)
+        self.ent_embeddings_sigma = NamedEmbedding("ent_embeddings_sigma", self.tot_entity, self.hidden_size)
+        self.rel_embeddings_sigma = NamedEmbedding("rel_embeddings_sigma", self.tot_relation, self.hidden_size)
+        for e in (self.ent_embeddings_mu, self.rel_embeddings_mu, self.ent_embeddings_sigma, self.rel_embeddings_sigma):
+            nn.init.xavier_uniform_(e.weight)
+        self.parameter_list = [self.ent_embeddings_mu, self.ent_embeddings_sigma, self.rel_embeddings_mu,
+                               self.rel_embeddings_sigma]
+        # sigma <- clamp(sigma + 1, cmin, cmax), re-registered as new Parameters (pairwise.py:1011-1014)
+        for e in (self.ent_embeddings_sigma, self.rel_embeddings_sigma):
+            e.weight = nn.Parameter(torch.clamp(e.weight.detach() + 1.0, min=float(self.cmin), max=float(self.cmax)))
+        self.loss = Criterion.pairwise_hinge
+
+    def kge_tables(self):
+        return [e.weight for e in self.parameter_list]
+
+    def kge_spec(self):
+        return ModelSpec("kg2e", self.hidden_size)
+
+    @staticmethod
+    def get_normalized_data(embedding, p=2, dim=1):
+        norms = torch.norm(embedding, p, dim)
+        return embedding.div(norms.view(-1, 1).expand_as(embedding))
+
+    def embed(self, h, r, t):
+        n = self.get_normalized_data
+        return (n(self.ent_embeddings_mu(h)), n(self.ent_embeddings_sigma(h)), n(self.rel_embeddings_mu(r)),
+                n(self.rel_embeddings_sigma(r)), n(self.ent_embeddings_mu(t)), n(self.ent_embeddings_sigma(t)))

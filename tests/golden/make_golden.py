@@ -69,6 +69,8 @@ SPECS = {
     "simple_ignr": (ref_pointwise.SimplE_ignr, ["ent_head_embeddings", "ent_tail_embeddings",
                                                 "rel_embeddings", "rel_inv_embeddings"]),
     "hole": (ref_pairwise.HoLE, ["ent_embeddings", "rel_embeddings"]),
+    "kg2e": (ref_pairwise.KG2E, ["ent_embeddings_mu", "ent_embeddings_sigma", "rel_embeddings_mu",
+                                 "rel_embeddings_sigma"]),
     "quate": (ref_pointwise.QuatE, ["ent_s_embedding", "ent_x_embedding", "ent_y_embedding", "ent_z_embedding",
                                     "rel_s_embedding", "rel_x_embedding", "rel_y_embedding", "rel_z_embedding"]),
     "octonione": (ref_pointwise.OctonionE, ["ent_embedding_%d" % i for i in range(1, 9)] +
@@ -115,6 +117,8 @@ CASES = [
     ("rescal_d50", "rescal", 53, 3, dict(hidden_size=50, margin=1.0), "ref"),
     ("simple_d48", "simple", 101, 6, dict(hidden_size=48, lmbda=0.1, tot_train_triples=1000, batch_size=100), "normal"),
     ("simple_ignr_d50", "simple_ignr", 101, 6, dict(hidden_size=50, lmbda=0.1, tot_train_triples=1000, batch_size=100), "normal"),
+    ("kg2e_d40", "kg2e", 71, 4, dict(hidden_size=40, cmax=5.0, cmin=0.05), "ref"),
+    ("kg2e_d50", "kg2e", 59, 3, dict(hidden_size=50, cmax=5.0, cmin=0.05), "ref"),
     ("quate_d20", "quate", 61, 4, dict(hidden_size=20, lmbda=0.1), "normal"),
     ("quate_d50", "quate", 53, 3, dict(hidden_size=50, lmbda=0.1), "ref"),
     ("octonione_d12", "octonione", 47, 3, dict(hidden_size=12, lmbda=0.1), "normal"),

@@ -71,6 +71,8 @@ SYN = [
     ("hole", 400, 7, 32, None, False, 0.0),
     ("rescal", 500, 5, 48, None, False, 0.0),
     ("rescal", 300, 5, 50, None, False, 0.0),
+    ("kg2e", 500, 5, 100, None, False, 0.0),
+    ("kg2e", 300, 5, 50, None, False, 0.0),
     ("quate", 400, 5, 100, None, False, 0.0),
     ("quate", 300, 5, 30, None, False, 0.0),
     ("octonione", 300, 5, 48, None, False, 0.0),

@@ -366,8 +366,8 @@ def run_cuda(args):
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src,
                      # dram__bytes_read+write of one sweep_tiled_kernel launch, ncu --set full
-                     # (profiles/r1_ncu_sweep_tiled_v1_summary.txt)
-                     "traffic": 12121344, "launch_ms": sweep_ms,
+                     # (profiles/r1_ncu_sweep_tiled_v2_summary.txt)
+                     "traffic": 12088576, "launch_ms": sweep_ms,
                      "algorithmic_bytes_per_launch": alg_bytes,
                      "note": "algorithmic bytes = the reference-equivalent streaming formulation (one 800-byte "
                              "row per scored candidate, SURVEY.md 8d); a sweep that batches queries re-uses "

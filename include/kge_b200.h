@@ -65,7 +65,13 @@ enum kge_model_id {
   KGE_QUATE = 14,   /* [ent_s, ent_x, ent_y, ent_z, rel_s, rel_x, rel_y, rel_z]  pointwise.py:678-694 */
   KGE_OCTONIONE = 15, /* [ent_1..ent_8, rel_1..rel_8]   pointwise.py:886-899 */
   KGE_KG2E = 16,    /* [ent_mu, ent_sigma, rel_mu, rel_sigma] pairwise.py:1021-1084 */
-  KGE_NUM_MODELS = 17
+  /* dense-layer models: the trailing tables are GLOBAL parameters (not indexed by ids);
+   * fp32 CUDA-core kernels in this round (the tensor-core formulation is round-2 work) */
+  KGE_SLM = 17,     /* [ent, rel, mr1(d x k), mr2(d x k)]                    pairwise.py:525-541 */
+  KGE_SME = 18,     /* [ent, rel, mu1, mu2, bu, mv1, mv2, bv] (d x d, d x 1)  pairwise.py:617-661 */
+  KGE_SME_BL = 19,  /* same tables                                           pairwise.py:680-724 */
+  KGE_NTN = 20,     /* [ent, rel, mr1, mr2, br(1 x k), mr(k x d*d)]          pairwise.py:919-960 */
+  KGE_NUM_MODELS = 21
 };
 
 /* Which two operands are combined first.  TAIL: (h,r) are the

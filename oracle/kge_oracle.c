@@ -40,7 +40,7 @@
 enum { KGE_TRANSE = 0, KGE_TRANSH = 1, KGE_TRANSD = 2, KGE_TRANSR = 3, KGE_ROTATE = 4,
        KGE_HOLE = 5, KGE_DISTMULT = 6, KGE_COMPLEX = 7, KGE_CP = 8, KGE_SIMPLE = 9,
        KGE_TRANSM = 10, KGE_RESCAL = 11, KGE_ANALOGY = 12, KGE_SIMPLE_IGNR = 13, KGE_QUATE = 14,
-       KGE_OCTONIONE = 15, KGE_KG2E = 16 };
+       KGE_OCTONIONE = 15, KGE_KG2E = 16, KGE_SLM = 17, KGE_SME = 18, KGE_SME_BL = 19, KGE_NTN = 20 };
 enum { KGE_GROUP_TAIL = 0, KGE_GROUP_HEAD = 1 };
 
 typedef struct kge_model {
@@ -125,6 +125,22 @@ float kgeo_expf(float x) {
   return y * two_k.f;
 }
 float kgeo_sigmoidf(float x) { return 1.0f / (1.0f + kgeo_expf(-x)); }
+
+/* Canonical tanh (Cephes tanhf: odd polynomial below 0.625, else 1 - 2/(exp(2|x|)+1)) */
+float kgeo_tanhf(float x) {
+  const float ax = fabsf(x);
+  if (ax < 0.625f) {
+    const float z = x * x;
+    float p = fmaf(-5.70498872745e-3f, z, 2.06390887954e-2f);
+    p = fmaf(p, z, -5.37397155531e-2f);
+    p = fmaf(p, z, 1.33314422036e-1f);
+    p = fmaf(p, z, -3.33332819422e-1f);
+    return fmaf(p * z, x, x);
+  }
+  const float e = kgeo_expf(2.0f * ax);
+  const float t = 1.0f - 2.0f * (1.0f / (e + 1.0f));
+  return x < 0.0f ? -t : t;
+}
 
 /* Canonical natural logarithm (Cephes logf in explicit fma; identical on the GPU).  x <= 0 -> -inf / NaN;
  * subnormal inputs are first scaled by 2^23. */
@@ -343,6 +359,69 @@ static float score_one(const kge_model_t* m, int grouping, int64_t h, int64_t r,
         for (int j = 0; j < d; ++j) { float* p = rs_at(&s, j); *p = fmaf(hv[j], v[j], *p); }
       }
       return -rs_finish(&s);
+    }
+    case KGE_SLM:
+    case KGE_NTN: {
+      /* SLM.forward/layer pairwise.py:525-541:  -sum_k r^_k tanh((h^ mr1)_k + (t^ mr2)_k)
+       * NTN.forward/train_layer pairwise.py:919-960: adds the bilinear tensor term h^T W_k t^ and the bias:
+       *   pre_k = ((h^T W_k t^ + (h^ mr1)_k) + (t^ mr2)_k) + br_k
+       * tables SLM [ent, rel, mr1(d x k), mr2(d x k)], NTN [.., br(1 x k), mr(k x d*d)]; k = rel_dim.
+       * Matrix-vector products accumulate sequentially over the input index; h^T W_k t^ is
+       * v_j = sum_i h^_i W_k[i,j] (sequential i), then RSUM_j v_j t^_j.  Grouping-independent. */
+      const int K = m->rel_dim;
+      const float *hv = row(m, 0, h, d), *rv = row(m, 1, r, K), *tv = row(m, 0, t, d);
+      const float *mr1 = m->tables[2], *mr2 = m->tables[3];
+      const float ih = inv_norm(hv, d), ir = inv_norm(rv, K), it = inv_norm(tv, d);
+      float *hn = scratch, *tn = scratch + d;
+      for (int i = 0; i < d; ++i) { hn[i] = hv[i] * ih; tn[i] = tv[i] * it; }
+      rsum_t s; rs_init(&s);
+      for (int k = 0; k < K; ++k) {
+        float a = 0.0f, b = 0.0f;
+        for (int i = 0; i < d; ++i) { a = fmaf(hn[i], mr1[(size_t)i * K + k], a); b = fmaf(tn[i], mr2[(size_t)i * K + k], b); }
+        float pre;
+        if (m->model == KGE_NTN) {
+          const float* W = m->tables[5] + (size_t)k * d * d;
+          rsum_t q; rs_init(&q);
+          for (int j = 0; j < d; ++j) {
+            float v = 0.0f;
+            for (int i = 0; i < d; ++i) v = fmaf(hn[i], W[(size_t)i * d + j], v);
+            float* p = rs_at(&q, j); *p = fmaf(v, tn[j], *p);
+          }
+          pre = ((rs_finish(&q) + a) + b) + m->tables[4][k];
+        } else {
+          pre = a + b;
+        }
+        float* p = rs_at(&s, k);
+        *p = fmaf(rv[k] * ir, kgeo_tanhf(pre), *p);
+      }
+      return -rs_finish(&s);
+    }
+    case KGE_SME:
+    case KGE_SME_BL: {
+      /* SME.forward pairwise.py:617-661:  -sum_k (mu1 h^ + mu2 r^ + bu)_k (mv1 t^ + mv2 r^ + bv)_k
+       * SME_BL.forward pairwise.py:680-724: +sum_k ((mu1 h^)(mu2 r^) + bu)_k ((mv1 t^)(mv2 r^) + bv)_k
+       * tables [ent, rel, mu1, mu2, bu, mv1, mv2, bv], matrices d x d (row k dotted with the vector,
+       * sequential over the input index).  Grouping-independent. */
+      const float *hv = row(m, 0, h, d), *rv = row(m, 1, r, d), *tv = row(m, 0, t, d);
+      const float *mu1 = m->tables[2], *mu2 = m->tables[3], *bu = m->tables[4], *mv1 = m->tables[5],
+                  *mv2 = m->tables[6], *bv = m->tables[7];
+      const float ih = inv_norm(hv, d), ir = inv_norm(rv, d), it = inv_norm(tv, d);
+      float *hn = scratch, *rn = scratch + d, *tn = scratch + 2 * d;
+      for (int i = 0; i < d; ++i) { hn[i] = hv[i] * ih; rn[i] = rv[i] * ir; tn[i] = tv[i] * it; }
+      rsum_t s; rs_init(&s);
+      for (int k = 0; k < d; ++k) {
+        float u1 = 0.0f, u2 = 0.0f, v1 = 0.0f, v2 = 0.0f;
+        for (int i = 0; i < d; ++i) {
+          u1 = fmaf(mu1[(size_t)k * d + i], hn[i], u1); u2 = fmaf(mu2[(size_t)k * d + i], rn[i], u2);
+          v1 = fmaf(mv1[(size_t)k * d + i], tn[i], v1); v2 = fmaf(mv2[(size_t)k * d + i], rn[i], v2);
+        }
+        float gu, gv;
+        if (m->model == KGE_SME) { gu = (u1 + u2) + bu[k]; gv = (v1 + v2) + bv[k]; }
+        else { gu = u1 * u2 + bu[k]; gv = v1 * v2 + bv[k]; }
+        float* p = rs_at(&s, k); *p = fmaf(gu, gv, *p);
+      }
+      const float tot = rs_finish(&s);
+      return m->model == KGE_SME ? -tot : tot;
     }
     case KGE_KG2E: {
       /* KG2E.forward/_cal_score_kl_divergence pairwise.py:1021-1084: all six gathered rows are divided

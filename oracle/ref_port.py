@@ -77,6 +77,26 @@ def score(name, tables, h, r, t, l1_flag=False, margin=0.0, embedding_range=None
         ere, eim, rre, rim = tables
         hr, hi, tr, ti, rr, ri = ere[h], eim[h], ere[t], eim[t], rre[r], rim[r]
         return -torch.sum(hr * tr * rr + hi * ti * rr + hr * ti * ri - hi * tr * ri, -1)
+    if name in ("slm", "ntn"):  # pairwise.py:525-541 / :919-960
+        ent, rel, mr1, mr2 = tables[:4]
+        nh, nr, nt = F.normalize(ent[h], p=2, dim=-1), F.normalize(rel[r], p=2, dim=-1), F.normalize(ent[t], p=2, dim=-1)
+        pre = torch.matmul(nh, mr1) + torch.matmul(nt, mr2)
+        if name == "ntn":
+            br, mr = tables[4], tables[5]
+            K, d = rel.shape[1], ent.shape[1]
+            exp_h = nh.unsqueeze(0).repeat(K, 1, 1)
+            temp = torch.matmul(exp_h, mr.view(K, d, d)).permute(1, 0, 2)
+            htmrt = torch.squeeze(torch.matmul(temp, nt.unsqueeze(-1)), dim=-1)
+            pre = htmrt + torch.matmul(nh, mr1) + torch.matmul(nt, mr2) + br
+        return -torch.sum(nr * torch.tanh(pre), -1)
+    if name in ("sme", "sme_bl"):  # pairwise.py:617-661 / :680-724
+        ent, rel, mu1, mu2, bu, mv1, mv2, bv = tables
+        nh, nr, nt = F.normalize(ent[h], p=2, dim=-1), F.normalize(rel[r], p=2, dim=-1), F.normalize(ent[t], p=2, dim=-1)
+        u1, u2 = torch.matmul(mu1, nh.T), torch.matmul(mu2, nr.T)
+        v1, v2 = torch.matmul(mv1, nt.T), torch.matmul(mv2, nr.T)
+        if name == "sme":
+            return -torch.sum((u1 + u2 + bu).T * (v1 + v2 + bv).T, 1)
+        return torch.sum((u1 * u2 + bu).T * (v1 * v2 + bv).T, -1)
     if name == "kg2e":  # pairwise.py:1021-1084
         emu, esig, rmu, rsig = tables
         nrm = lambda x: x / torch.norm(x, 2, 1).view(-1, 1)

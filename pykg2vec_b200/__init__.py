@@ -22,6 +22,10 @@ MODEL_MAP = {
     "rescal": ("pykg2vec_b200.pairwise", "Rescal"),
     "hole": ("pykg2vec_b200.pairwise", "HoLE"),
     "kg2e": ("pykg2vec_b200.pairwise", "KG2E"),
+    "slm": ("pykg2vec_b200.pairwise", "SLM"),
+    "ntn": ("pykg2vec_b200.pairwise", "NTN"),
+    "sme": ("pykg2vec_b200.pairwise", "SME"),
+    "sme_bl": ("pykg2vec_b200.pairwise", "SME_BL"),
     "distmult": ("pykg2vec_b200.pointwise", "DistMult"),
     "cp": ("pykg2vec_b200.pointwise", "CP"),
     "complex": ("pykg2vec_b200.pointwise", "Complex"),

@@ -31,6 +31,7 @@ score_bwd_kernel(ModelParams P, GradTables GT, const int64_t* __restrict__ h,
 #pragma unroll
     for (int c = 0; c < 8; ++c) G.h[c] = G.t[c] = G.r[c] = nullptr;
   }
+  if (!valid && (MODEL == KGE_SLM || MODEL == KGE_NTN || MODEL == KGE_SME || MODEL == KGE_SME_BL)) return;
   grad_group<MODEL, VEC, CHSEL>(R, G, P, lane, __ldg(gout + gi), scratch);
 }
 
@@ -63,6 +64,10 @@ extern "C" int kge_score_bwd(const kge_model_t* m, const int64_t* h, const int64
   if (m->model == KGE_TRANSM) GT.t[2] = nullptr;  // theta is a buffer, not a parameter (pairwise.py:315)
   const int sf = (int)group_scratch_floats_bwd(m);
   const size_t smem = (size_t)sf * kGroupsPerCta * sizeof(float);
+  if (smem > 227 * 1024) {
+    set_error("%s: embedding width too large for this model's per-group scratch (%zu B of shared memory)", "kge_score_bwd", smem);
+    return KGE_ENOTSUP;
+  }
   const unsigned grid = (unsigned)((n + kGroupsPerCta - 1) / kGroupsPerCta);
   cudaStream_t st = (cudaStream_t)stream;
   const int chsel = (m->model == KGE_TRANSE || m->model == KGE_TRANSM) ? ch_select(m->dim) : 0;

@@ -107,6 +107,22 @@ KGE_DEV float exp_canon(float x) {
 }
 KGE_DEV float sigmoid_canon(float x) { return __frcp_rn(fadd(1.0f, exp_canon(-x))); }
 
+// Canonical tanh (Cephes tanhf; bit-identical to oracle/kge_oracle.c)
+KGE_DEV float tanh_canon(float x) {
+  const float ax = fabsf(x);
+  if (ax < 0.625f) {
+    const float z = fmul(x, x);
+    float p = ffma(-5.70498872745e-3f, z, 2.06390887954e-2f);
+    p = ffma(p, z, -5.37397155531e-2f);
+    p = ffma(p, z, 1.33314422036e-1f);
+    p = ffma(p, z, -3.33332819422e-1f);
+    return ffma(fmul(p, z), x, x);
+  }
+  const float e = exp_canon(fmul(2.0f, ax));
+  const float t = fsub(1.0f, fmul(2.0f, __frcp_rn(fadd(e, 1.0f))));
+  return x < 0.0f ? -t : t;
+}
+
 // Canonical natural logarithm (Cephes logf in explicit fma; bit-identical to oracle/kge_oracle.c)
 KGE_DEV float log_canon(float x) {
   if (!(x > 0.0f)) return x == 0.0f ? -INFINITY : NAN;

@@ -26,7 +26,12 @@ KGE_DEV void resolve_grad_rows(GradRows& G, const ModelParams& P, float* const* 
 #pragma unroll
   for (int c = 0; c < 8; ++c) G.h[c] = G.t[c] = G.r[c] = nullptr;
   auto at = [&](int k, size_t off) -> float* { return gt[k] ? gt[k] + off : nullptr; };
-  if (MODEL == KGE_KG2E) {
+  if (MODEL == KGE_SLM || MODEL == KGE_NTN || MODEL == KGE_SME || MODEL == KGE_SME_BL) {
+    G.h[0] = at(0, h * d); G.t[0] = at(0, t * d); G.r[0] = at(1, r * dr);
+    // dense parameters: whole gradient tables (not per-row)
+#pragma unroll
+    for (int k = 2; k < 8; ++k) G.r[k] = gt[k];
+  } else if (MODEL == KGE_KG2E) {
     G.h[0] = at(0, h * d); G.h[1] = at(1, h * d); G.t[0] = at(0, t * d); G.t[1] = at(1, t * d);
     G.r[0] = at(2, r * d); G.r[1] = at(3, r * d);
   } else if (MODEL == KGE_QUATE || MODEL == KGE_OCTONIONE) {
@@ -414,6 +419,177 @@ KGE_DEV void grad_group(const TripleRows& R, const GradRows& G, const ModelParam
       red_row_chunk<VEC>(G.t[0], c, d, gtr);
       red_row_chunk<VEC>(G.t[1], c, d, gti);
     }
+  } else if (MODEL == KGE_SLM || MODEL == KGE_NTN) {
+    // s = -sum_k r^_k tanh(pre_k).  scratch: [6 dm forward pieces] dpre, dhn, dtn  (dm each)
+    const int K = P.dr, nchk = (K + 3) >> 2, dm = dense_dm(d, K);
+    DenseCtx X;
+    slm_ntn_fill<MODEL, VEC>(R, P, lane, scratch, X);
+    float *dpre = scratch + 6 * dm, *dhn = scratch + 7 * dm, *dtn = scratch + 8 * dm;
+    float* gmr1 = G.r[2]; float* gmr2 = G.r[3];
+    const float ng = -gs;
+    float rdot = 0.f;
+    for (int c = lane; c < nchk; c += 8) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int k = 4 * c + e;
+        const float a = X.act[k], rk = X.rn[k];
+        dpre[k] = (k < K) ? ng * rk * (1.f - a * a) : 0.f;
+        rdot += rk * (ng * a);
+      }
+    }
+    for (int c = lane; c < nch; c += 8) { *reinterpret_cast<float4*>(dhn + 4 * c) = make_float4(0.f, 0.f, 0.f, 0.f); *reinterpret_cast<float4*>(dtn + 4 * c) = make_float4(0.f, 0.f, 0.f, 0.f); }
+    rdot = group_sum(rdot);
+    if (X.clamp_r) rdot = 0.f;
+    group_sync();
+    // relation row: d r = (d r^ - r^ <r^, d r^>) * ir,  d r^_k = ng * act_k
+    for (int c = lane; c < nchk; c += 8) {
+      float4 gr;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const int k = 4 * c + e; f4_at(gr, e) = (ng * X.act[k] - X.rn[k] * rdot) * X.ir; }
+      red_row_chunk<VEC>(G.r[0], c, K, gr);
+      if (MODEL == KGE_NTN && G.r[4]) red_chunk<VEC>(G.r[4], c, K, *reinterpret_cast<const float4*>(dpre + 4 * c));
+    }
+    // linear layers: d hn_i += sum_k mr1[i,k] dpre_k ; d mr1[i,k] += hn_i dpre_k (same for t / mr2)
+    const float* mr1 = P.tab[2];
+    const float* mr2 = P.tab[3];
+    for (int c = lane; c < nch; c += 8) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = 4 * c + e;
+        if (i >= d) continue;
+        float ah = 0.f, at = 0.f;
+        const float hi = X.hn[i], ti = X.tn[i];
+        for (int kc = 0; kc < nchk; ++kc) {
+          const float4 m1 = ld_chunk<VEC>(mr1 + (size_t)i * K, kc, K), m2 = ld_chunk<VEC>(mr2 + (size_t)i * K, kc, K);
+          const float4 dp = *reinterpret_cast<const float4*>(dpre + 4 * kc);
+          float4 g1, g2;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            ah += f4_get(m1, q) * f4_get(dp, q); at += f4_get(m2, q) * f4_get(dp, q);
+            f4_at(g1, q) = hi * f4_get(dp, q); f4_at(g2, q) = ti * f4_get(dp, q);
+          }
+          if (gmr1) red_chunk<VEC>(gmr1 + (size_t)i * K, kc, K, g1);
+          if (gmr2) red_chunk<VEC>(gmr2 + (size_t)i * K, kc, K, g2);
+        }
+        dhn[i] += ah; dtn[i] += at;
+      }
+    }
+    if (MODEL == KGE_NTN) {
+      // bilinear tensor: pre_k += h^T W_k t^ :  d hn_i += dpre_k sum_j W[i,j] tn_j ; d tn_j += dpre_k sum_i hn_i W[i,j]
+      //                                         d W_k[i,j] += dpre_k hn_i tn_j
+      group_sync();
+      for (int k = 0; k < K; ++k) {
+        const float dk = dpre[k];
+        const float* W = P.tab[5] + (size_t)k * d * d;
+        float* gW = G.r[5] ? G.r[5] + (size_t)k * d * d : nullptr;
+        for (int c = lane; c < nch; c += 8) {       // lane owns columns j = 4c..4c+3
+          const float4 tt = *reinterpret_cast<const float4*>(X.tn + 4 * c);
+          float4 accj = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int i = 0; i < d; ++i) {
+            const float hi = X.hn[i];
+            const float4 w = ld_chunk<VEC>(W + (size_t)i * d, c, d);
+            float4 gw;
+            float rowdot = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              f4_at(accj, q) += hi * f4_get(w, q);
+              rowdot += f4_get(w, q) * f4_get(tt, q);
+              f4_at(gw, q) = dk * hi * f4_get(tt, q);
+            }
+            if (gW) red_chunk<VEC>(gW + (size_t)i * d, c, d, gw);
+            atomicAdd(dhn + i, dk * rowdot);   // shared-memory accumulate across the lanes' column chunks
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) if (4 * c + q < d) dtn[4 * c + q] += dk * f4_get(accj, q);
+        }
+        group_sync();
+      }
+    }
+    group_sync();
+    float hdot = 0.f, tdot = 0.f;
+    for (int c = lane; c < nch; c += 8) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const int i = 4 * c + e; if (i < d) { hdot += X.hn[i] * dhn[i]; tdot += X.tn[i] * dtn[i]; } }
+    }
+    hdot = group_sum(hdot); tdot = group_sum(tdot);
+    if (X.clamp_h) hdot = 0.f;
+    if (X.clamp_t) tdot = 0.f;
+    for (int c = lane; c < nch; c += 8) {
+      float4 gh, gtt;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = 4 * c + e;
+        f4_at(gh, e) = (i < d) ? (dhn[i] - X.hn[i] * hdot) * X.ih : 0.f;
+        f4_at(gtt, e) = (i < d) ? (dtn[i] - X.tn[i] * tdot) * X.it : 0.f;
+      }
+      red_row_chunk<VEC>(G.h[0], c, d, gh);
+      red_row_chunk<VEC>(G.t[0], c, d, gtt);
+    }
+    group_sync();
+  } else if (MODEL == KGE_SME || MODEL == KGE_SME_BL) {
+    // scratch: [9 dm forward pieces] dhn, drn, dtn
+    const int dm = nch * 4;
+    DenseCtx X;
+    sme_fill<MODEL, VEC>(R, P, lane, scratch, X);
+    float *dhn = scratch + 9 * dm, *drn = scratch + 10 * dm, *dtn = scratch + 11 * dm;
+    for (int c = lane; c < nch; c += 8) {
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(dhn + 4 * c) = z; *reinterpret_cast<float4*>(drn + 4 * c) = z; *reinterpret_cast<float4*>(dtn + 4 * c) = z;
+    }
+    group_sync();
+    const float ng = (MODEL == KGE_SME) ? -gs : gs;
+    const float *mu1 = P.tab[2], *mu2 = P.tab[3], *mv1 = P.tab[5], *mv2 = P.tab[6];
+    for (int c = lane; c < nch; c += 8) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int k = 4 * c + e;
+        if (k >= d) continue;
+        const float dgu = ng * X.gv[k], dgv = ng * X.gu[k];
+        float du1, du2, dv1, dv2;
+        if (MODEL == KGE_SME) { du1 = du2 = dgu; dv1 = dv2 = dgv; }
+        else { du1 = dgu * X.u2[k]; du2 = dgu * X.u1[k]; dv1 = dgv * X.v2[k]; dv2 = dgv * X.v1[k]; }
+        if (G.r[4]) atomicAdd(G.r[4] + k, dgu);
+        if (G.r[7]) atomicAdd(G.r[7] + k, dgv);
+        const size_t ro = (size_t)k * d;
+        for (int i = 0; i < d; ++i) {
+          const float hi = X.hn[i], ri = X.rn[i], ti = X.tn[i];
+          atomicAdd(dhn + i, __ldg(mu1 + ro + i) * du1);
+          atomicAdd(drn + i, __ldg(mu2 + ro + i) * du2 + __ldg(mv2 + ro + i) * dv2);
+          atomicAdd(dtn + i, __ldg(mv1 + ro + i) * dv1);
+          if (G.r[2]) atomicAdd(G.r[2] + ro + i, du1 * hi);
+          if (G.r[3]) atomicAdd(G.r[3] + ro + i, du2 * ri);
+          if (G.r[5]) atomicAdd(G.r[5] + ro + i, dv1 * ti);
+          if (G.r[6]) atomicAdd(G.r[6] + ro + i, dv2 * ri);
+        }
+      }
+    }
+    group_sync();
+    float hdot = 0.f, tdot = 0.f, rdot = 0.f;
+    for (int c = lane; c < nch; c += 8) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = 4 * c + e;
+        if (i < d) { hdot += X.hn[i] * dhn[i]; tdot += X.tn[i] * dtn[i]; rdot += X.rn[i] * drn[i]; }
+      }
+    }
+    hdot = group_sum(hdot); tdot = group_sum(tdot); rdot = group_sum(rdot);
+    if (X.clamp_h) hdot = 0.f;
+    if (X.clamp_t) tdot = 0.f;
+    if (X.clamp_r) rdot = 0.f;
+    for (int c = lane; c < nch; c += 8) {
+      float4 gh, gtt, gr;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = 4 * c + e;
+        f4_at(gh, e) = (i < d) ? (dhn[i] - X.hn[i] * hdot) * X.ih : 0.f;
+        f4_at(gtt, e) = (i < d) ? (dtn[i] - X.tn[i] * tdot) * X.it : 0.f;
+        f4_at(gr, e) = (i < d) ? (drn[i] - X.rn[i] * rdot) * X.ir : 0.f;
+      }
+      red_row_chunk<VEC>(G.h[0], c, d, gh);
+      red_row_chunk<VEC>(G.t[0], c, d, gtt);
+      red_row_chunk<VEC>(G.r[0], c, d, gr);
+    }
+    group_sync();
   } else if (MODEL == KGE_KG2E) {
     // rows k: 0 h_mu, 1 h_sigma, 2 r_mu, 3 r_sigma, 4 t_mu, 5 t_sigma; y^ = y / ||y||
     const float* rows6[6] = {R.h[0], R.h[1], R.r[0], R.r[1], R.t[0], R.t[1]};
@@ -820,6 +996,8 @@ KGE_DEV void grad_group(const TripleRows& R, const GradRows& G, const ModelParam
 
 // shared-memory floats one 8-lane group needs in the backward kernels
 inline size_t group_scratch_floats_bwd(const kge_model_t* m) {
+  if (m->model == KGE_SLM || m->model == KGE_NTN) return 9 * (size_t)dense_dm(m->dim, m->rel_dim);
+  if (m->model == KGE_SME || m->model == KGE_SME_BL) return 12 * (size_t)(((m->dim + 3) >> 2) * 4);
   if (m->model == KGE_HOLE) return 6 * (size_t)(((m->dim + 3) >> 2) * 4);
   if (m->model == KGE_RESCAL) return group_scratch_floats(m);
   if (m->model != KGE_TRANSR) return 0;

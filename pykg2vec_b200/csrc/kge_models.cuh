@@ -24,7 +24,10 @@ KGE_DEV void resolve_rows(TripleRows& R, const ModelParams& P, const float* cons
                           int64_t t) {
   const size_t d = (size_t)P.d, dr = (size_t)P.dr;
   R.h[1] = R.t[1] = R.r[1] = R.r[2] = R.h[2] = R.t[2] = nullptr;
-  if (MODEL == KGE_KG2E) {  // [ent_mu, ent_sigma, rel_mu, rel_sigma]
+  if (MODEL == KGE_SLM || MODEL == KGE_NTN || MODEL == KGE_SME || MODEL == KGE_SME_BL) {
+    // only the embedding rows are per-triple; the dense parameters are read through P.tab[2..]
+    R.h[0] = htab[0] + h * d; R.t[0] = ttab[0] + t * d; R.r[0] = rtab[1] + r * dr;
+  } else if (MODEL == KGE_KG2E) {  // [ent_mu, ent_sigma, rel_mu, rel_sigma]
     R.h[0] = htab[0] + h * d; R.h[1] = htab[1] + h * d; R.t[0] = ttab[0] + t * d; R.t[1] = ttab[1] + t * d;
     R.r[0] = rtab[2] + r * d; R.r[1] = rtab[3] + r * d;
   } else if (MODEL == KGE_QUATE || MODEL == KGE_OCTONIONE) {
@@ -234,6 +237,131 @@ KGE_DEV float group_dot(const float* __restrict__ a, const float* __restrict__ b
   return group_sum(s);
 }
 
+// ---- dense-layer models (SLM / NTN / SME / SME_BL): shared forward pieces left in the group's scratch
+struct DenseCtx {
+  float ih, it, ir;                 // inverse norms
+  bool clamp_h, clamp_t, clamp_r;   // norm below eps (F.normalize divides by the constant eps)
+  float *hn, *tn, *rn;              // normalised operands
+  float *act, *A, *B;               // SLM/NTN: tanh(pre), (h^ mr1), (t^ mr2)
+  float *gu, *gv, *u1, *u2, *v1, *v2;  // SME / SME_BL
+};
+inline __host__ __device__ int dense_dm(int d, int K) { return ((d > K ? d : K) + 3) / 4 * 4; }
+
+template <int VEC>
+KGE_DEV void dense_normalise(const TripleRows& R, int d, int K, int lane, DenseCtx& X) {
+  const int nch = (d + 3) >> 2, nchk = (K + 3) >> 2;
+  float sh = 0.f, st = 0.f, sr = 0.f;
+  for (int c = lane; c < nch; c += 8) {
+    const float4 a = ld_chunk<VEC>(R.h[0], c, d), b = ld_chunk<VEC>(R.t[0], c, d);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { sh = ffma(f4_get(a, e), f4_get(a, e), sh); st = ffma(f4_get(b, e), f4_get(b, e), st); }
+  }
+  for (int c = lane; c < nchk; c += 8) {
+    const float4 b = ld_chunk<VEC>(R.r[0], c, K);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) sr = ffma(f4_get(b, e), f4_get(b, e), sr);
+  }
+  sh = group_sum(sh); st = group_sum(st); sr = group_sum(sr);
+  X.ih = inv_norm_from_sumsq(sh); X.it = inv_norm_from_sumsq(st); X.ir = inv_norm_from_sumsq(sr);
+  X.clamp_h = __fsqrt_rn(sh) < 1e-12f; X.clamp_t = __fsqrt_rn(st) < 1e-12f; X.clamp_r = __fsqrt_rn(sr) < 1e-12f;
+  for (int c = lane; c < nch; c += 8) {
+    const float4 a = ld_chunk<VEC>(R.h[0], c, d), b = ld_chunk<VEC>(R.t[0], c, d);
+    *reinterpret_cast<float4*>(X.hn + 4 * c) = make_float4(fmul(a.x, X.ih), fmul(a.y, X.ih), fmul(a.z, X.ih), fmul(a.w, X.ih));
+    *reinterpret_cast<float4*>(X.tn + 4 * c) = make_float4(fmul(b.x, X.it), fmul(b.y, X.it), fmul(b.z, X.it), fmul(b.w, X.it));
+  }
+  for (int c = lane; c < nchk; c += 8) {
+    const float4 b = ld_chunk<VEC>(R.r[0], c, K);
+    *reinterpret_cast<float4*>(X.rn + 4 * c) = make_float4(fmul(b.x, X.ir), fmul(b.y, X.ir), fmul(b.z, X.ir), fmul(b.w, X.ir));
+  }
+  group_sync();
+}
+
+// scratch layout (dm floats each): hn, tn, rn, act, A, B
+template <int MODEL, int VEC>
+KGE_DEV void slm_ntn_fill(const TripleRows& R, const ModelParams& P, int lane, float* scratch, DenseCtx& X) {
+  const int d = P.d, K = P.dr, nch = (d + 3) >> 2, nchk = (K + 3) >> 2, dm = dense_dm(d, K);
+  X.hn = scratch; X.tn = scratch + dm; X.rn = scratch + 2 * dm; X.act = scratch + 3 * dm;
+  X.A = scratch + 4 * dm; X.B = scratch + 5 * dm;
+  dense_normalise<VEC>(R, d, K, lane, X);
+  const float* mr1 = P.tab[2];
+  const float* mr2 = P.tab[3];
+  for (int c = lane; c < nchk; c += 8) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    for (int i = 0; i < d; ++i) {
+      const float hi = X.hn[i], ti = X.tn[i];
+      const float4 m1 = ld_chunk<VEC>(mr1 + (size_t)i * K, c, K), m2 = ld_chunk<VEC>(mr2 + (size_t)i * K, c, K);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { f4_at(a, e) = ffma(hi, f4_get(m1, e), f4_get(a, e)); f4_at(b, e) = ffma(ti, f4_get(m2, e), f4_get(b, e)); }
+    }
+    if (MODEL == KGE_SLM) {
+      float4 o;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) f4_at(o, e) = tanh_canon(fadd(f4_get(a, e), f4_get(b, e)));
+      *reinterpret_cast<float4*>(X.act + 4 * c) = o;
+    } else {
+      *reinterpret_cast<float4*>(X.A + 4 * c) = a;
+      *reinterpret_cast<float4*>(X.B + 4 * c) = b;
+    }
+  }
+  if (MODEL == KGE_NTN) {
+    group_sync();
+    const float* br = P.tab[4];
+    for (int k = 0; k < K; ++k) {
+      const float* W = P.tab[5] + (size_t)k * d * d;
+      float part = 0.f;
+      for (int c = lane; c < nch; c += 8) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < d; ++i) {
+          const float hi = X.hn[i];
+          const float4 w = ld_chunk<VEC>(W + (size_t)i * d, c, d);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) f4_at(v, e) = ffma(hi, f4_get(w, e), f4_get(v, e));
+        }
+        const float4 tt = *reinterpret_cast<const float4*>(X.tn + 4 * c);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) part = ffma(f4_get(v, e), f4_get(tt, e), part);
+      }
+      const float bil = group_sum(part);
+      if (lane == 0) X.act[k] = tanh_canon(fadd(fadd(fadd(bil, X.A[k]), X.B[k]), __ldg(br + k)));
+    }
+    if (lane == 0) for (int k = K; k < nchk * 4; ++k) X.act[k] = 0.f;
+  }
+  group_sync();
+}
+
+// scratch layout (dm floats each): hn, rn, tn, gu, gv, u1, u2, v1, v2
+template <int MODEL, int VEC>
+KGE_DEV void sme_fill(const TripleRows& R, const ModelParams& P, int lane, float* scratch, DenseCtx& X) {
+  const int d = P.d, nch = (d + 3) >> 2, dm = nch * 4;
+  X.hn = scratch; X.rn = scratch + dm; X.tn = scratch + 2 * dm; X.gu = scratch + 3 * dm; X.gv = scratch + 4 * dm;
+  X.u1 = scratch + 5 * dm; X.u2 = scratch + 6 * dm; X.v1 = scratch + 7 * dm; X.v2 = scratch + 8 * dm;
+  dense_normalise<VEC>(R, d, d, lane, X);
+  const float *mu1 = P.tab[2], *mu2 = P.tab[3], *bu = P.tab[4], *mv1 = P.tab[5], *mv2 = P.tab[6], *bv = P.tab[7];
+  for (int c = lane; c < nch; c += 8) {
+    float4 GU = make_float4(0.f, 0.f, 0.f, 0.f), GV = GU, U1 = GU, U2 = GU, V1 = GU, V2 = GU;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k = 4 * c + e;
+      if (k < d) {
+        float u1 = 0.f, u2 = 0.f, v1 = 0.f, v2 = 0.f;
+        const float *r1 = mu1 + (size_t)k * d, *r2 = mu2 + (size_t)k * d, *r3 = mv1 + (size_t)k * d, *r4 = mv2 + (size_t)k * d;
+        for (int i = 0; i < d; ++i) {
+          const float hi = X.hn[i], ri = X.rn[i], ti = X.tn[i];
+          u1 = ffma(__ldg(r1 + i), hi, u1); u2 = ffma(__ldg(r2 + i), ri, u2);
+          v1 = ffma(__ldg(r3 + i), ti, v1); v2 = ffma(__ldg(r4 + i), ri, v2);
+        }
+        f4_at(U1, e) = u1; f4_at(U2, e) = u2; f4_at(V1, e) = v1; f4_at(V2, e) = v2;
+        if (MODEL == KGE_SME) { f4_at(GU, e) = fadd(fadd(u1, u2), __ldg(bu + k)); f4_at(GV, e) = fadd(fadd(v1, v2), __ldg(bv + k)); }
+        else { f4_at(GU, e) = fadd(fmul(u1, u2), __ldg(bu + k)); f4_at(GV, e) = fadd(fmul(v1, v2), __ldg(bv + k)); }
+      }
+    }
+    *reinterpret_cast<float4*>(X.gu + 4 * c) = GU; *reinterpret_cast<float4*>(X.gv + 4 * c) = GV;
+    *reinterpret_cast<float4*>(X.u1 + 4 * c) = U1; *reinterpret_cast<float4*>(X.u2 + 4 * c) = U2;
+    *reinterpret_cast<float4*>(X.v1 + 4 * c) = V1; *reinterpret_cast<float4*>(X.v2 + 4 * c) = V2;
+  }
+  group_sync();
+}
+
 // `scratch`: per-group shared memory, only used by TransR (2 * dr_pad floats).
 template <int MODEL, int VEC, int GROUPING, int CHSEL = -1>
 KGE_DEV float score_group(const TripleRows& R, const ModelParams& P, int lane, float* scratch) {
@@ -395,6 +523,32 @@ KGE_DEV float score_group(const TripleRows& R, const ModelParams& P, int lane, f
       }
     }
     return -group_sum(acc);
+  } else if (MODEL == KGE_SLM || MODEL == KGE_NTN) {
+    // SLM.forward/layer pairwise.py:525-541; NTN.forward/train_layer pairwise.py:919-960
+    const int K = P.dr, nchk = (K + 3) >> 2;
+    DenseCtx X;
+    slm_ntn_fill<MODEL, VEC>(R, P, lane, scratch, X);
+    float acc = 0.f;
+    for (int c = lane; c < nchk; c += 8) {
+      const float4 rr = *reinterpret_cast<const float4*>(X.rn + 4 * c), aa = *reinterpret_cast<const float4*>(X.act + 4 * c);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc = ffma(f4_get(rr, e), f4_get(aa, e), acc);
+    }
+    group_sync();
+    return -group_sum(acc);
+  } else if (MODEL == KGE_SME || MODEL == KGE_SME_BL) {
+    // SME.forward pairwise.py:617-661 / SME_BL.forward :680-724
+    DenseCtx X;
+    sme_fill<MODEL, VEC>(R, P, lane, scratch, X);
+    float acc = 0.f;
+    for (int c = lane; c < nch; c += 8) {
+      const float4 gu = *reinterpret_cast<const float4*>(X.gu + 4 * c), gv = *reinterpret_cast<const float4*>(X.gv + 4 * c);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc = ffma(f4_get(gu, e), f4_get(gv, e), acc);
+    }
+    group_sync();
+    const float tot = group_sum(acc);
+    return MODEL == KGE_SME ? -tot : tot;
   } else if (MODEL == KGE_KG2E) {
     // KG2E.forward / _cal_score_kl_divergence pairwise.py:1021-1084 (grouping-independent)
     const float* rows6[6] = {R.h[0], R.h[1], R.r[0], R.r[1], R.t[0], R.t[1]};
@@ -594,6 +748,8 @@ constexpr bool is_distance_model(int model) {
 // shared-memory floats one 8-lane group needs (TransR only)
 inline size_t group_scratch_floats(const kge_model_t* m) {
   const size_t dp = (size_t)(((m->dim + 3) >> 2) * 4);
+  if (m->model == KGE_SLM || m->model == KGE_NTN) return 6 * (size_t)dense_dm(m->dim, m->rel_dim);
+  if (m->model == KGE_SME || m->model == KGE_SME_BL) return 9 * dp;
   if (m->model == KGE_HOLE) return 3 * dp;
   if (m->model == KGE_RESCAL) return dp;
   if (m->model != KGE_TRANSR) return 0;
@@ -617,6 +773,10 @@ inline size_t group_scratch_floats(const kge_model_t* m) {
       case KGE_ANALOGY: KGE_DISPATCH_VEC(KGE_ANALOGY, vec, CALL); break;           \
       case KGE_QUATE: KGE_DISPATCH_VEC(KGE_QUATE, vec, CALL); break;               \
       case KGE_KG2E: KGE_DISPATCH_VEC(KGE_KG2E, vec, CALL); break;                 \
+      case KGE_SLM: KGE_DISPATCH_VEC(KGE_SLM, vec, CALL); break;                   \
+      case KGE_NTN: KGE_DISPATCH_VEC(KGE_NTN, vec, CALL); break;                   \
+      case KGE_SME: KGE_DISPATCH_VEC(KGE_SME, vec, CALL); break;                   \
+      case KGE_SME_BL: KGE_DISPATCH_VEC(KGE_SME_BL, vec, CALL); break;             \
       case KGE_OCTONIONE: KGE_DISPATCH_VEC(KGE_OCTONIONE, vec, CALL); break;       \
       case KGE_RESCAL: KGE_DISPATCH_VEC(KGE_RESCAL, vec, CALL); break;             \
       case KGE_SIMPLE: KGE_DISPATCH_VEC(KGE_SIMPLE, vec, CALL); break;             \

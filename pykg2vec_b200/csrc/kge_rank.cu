@@ -185,6 +185,7 @@ extern "C" int kge_rank_1vsall(const kge_model_t* m, const kge_model_t* mq, int6
   if (vq < vec) vec = vq;
   const int sf = (int)group_scratch_floats(m);
   const size_t smem = (size_t)sf * kGroupsPerCta * sizeof(float);
+  if (smem > 227 * 1024) { set_error("kge_rank_1vsall: embedding width too large for this model's scratch"); return KGE_ENOTSUP; }
   float* thr_t = reinterpret_cast<float*>(workspace);
   float* thr_h = thr_t + Q;
   void* tiled_ws = reinterpret_cast<char*>(workspace) + align_up((size_t)2 * (size_t)Q * sizeof(float), 256);

@@ -44,7 +44,8 @@ int check_model(const kge_model_t* m) {
   for (int k = 0; k < nt; ++k)
     if (!m->tables[k]) { set_error("tables[%d] is NULL", k); return KGE_EINVAL; }
   if (m->model == KGE_ANALOGY && (m->dim % 2)) { set_error("ANALOGY needs an even hidden_size"); return KGE_EINVAL; }
-  if (m->model != KGE_TRANSR && m->rel_dim != m->dim) {
+  const bool free_rel_dim = m->model == KGE_TRANSR || m->model == KGE_SLM || m->model == KGE_NTN;
+  if (!free_rel_dim && m->rel_dim != m->dim) {
     // TransD as written only broadcasts when ent_hidden_size == rel_hidden_size (pairwise.py:275-278)
     set_error("rel_dim (%d) must equal dim (%d) for this model", m->rel_dim, m->dim);
     return KGE_EINVAL;
@@ -60,6 +61,8 @@ int model_vec(const kge_model_t* m) {
     return pick_vec(m, nt, m->dim / 2);
   }
   if (m->model == KGE_HOLE) return (m->dim % 4 == 0) ? pick_vec(m, nt, m->dim) : 1;  // mirrored scalar reads
+  if (m->model == KGE_SLM || m->model == KGE_NTN) return pick_vec(m, nt, m->dim, m->rel_dim);
+  if (m->model == KGE_SME || m->model == KGE_SME_BL) return pick_vec(m, 2, m->dim);  // matrices: scalar reads
   return pick_vec(m, nt, m->dim, m->model == KGE_TRANSR ? m->rel_dim : 0);
 }
 
@@ -78,6 +81,10 @@ extern "C" int kge_score_fwd(const kge_model_t* m, int grouping, const int64_t* 
   const int vec = model_vec(m);
   const int sf = (int)group_scratch_floats(m);
   const size_t smem = (size_t)sf * kGroupsPerCta * sizeof(float);
+  if (smem > 227 * 1024) {
+    set_error("%s: embedding width too large for this model's per-group scratch (%zu B of shared memory)", "kge_score_fwd", smem);
+    return KGE_ENOTSUP;
+  }
   const unsigned grid = (unsigned)((n + kGroupsPerCta - 1) / kGroupsPerCta);
   cudaStream_t st = (cudaStream_t)stream;
   // distance models: the register-cache depth is a template parameter picked from the width

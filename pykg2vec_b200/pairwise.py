@@ -349,3 +349,104 @@ class KG2E(_KernelScored, PairwiseModel):
         n = self.get_normalized_data
         return (n(self.ent_embeddings_mu(h)), n(self.ent_embeddings_sigma(h)), n(self.rel_embeddings_mu(r)),
                 n(self.rel_embeddings_sigma(r)), n(self.ent_embeddings_mu(t)), n(self.ent_embeddings_sigma(t)))
+
+
+class _DenseLayerModel(_KernelScored, PairwiseModel):
+    """Models whose trailing tables are global dense parameters (not indexed by ids): the fused
+    sparse optimizer does not apply to them, training goes through autograd + a torch optimizer."""
+    kge_dense_params = True
+
+    def kge_tables(self):
+        return [e.weight for e in self.parameter_list]
+
+    def embed(self, h, r, t):
+        return self.ent_embeddings(h), self.rel_embeddings(r), self.ent_embeddings(t)
+
+
+class SLM(_DenseLayerModel):
+    """pykg2vec/models/pairwise.py:473-541."""
+
+    def __init__(self, **kwargs):
+        super(SLM, self).__init__(self.__class__.__name__.lower())
+        param_list = ["tot_entity", "tot_relation", "rel_hidden_size", "ent_hidden_size"]
+        param_dict = self.load_params(param_list, kwargs)
+        self.__dict__.update(param_dict)
+        self.ent_embeddings = NamedEmbedding("ent_embedding", self.tot_entity, self.ent_hidden_size)
+        self.rel_embeddings = NamedEmbedding("rel_embedding", self.tot_relation, self.rel_hidden_size)
+        self.mr1 = NamedEmbedding("mr1", self.ent_hidden_size, self.rel_hidden_size)
+        self.mr2 = NamedEmbedding("mr2", self.ent_hidden_size, self.rel_hidden_size)
+        self.parameter_list = [self.ent_embeddings, self.rel_embeddings, self.mr1, self.mr2]
+        for e in self.parameter_list:
+            nn.init.xavier_uniform_(e.weight)
+        self.loss = Criterion.pairwise_hinge
+
+    def kge_spec(self):
+        return ModelSpec("slm", self.ent_hidden_size, rel_dim=self.rel_hidden_size)
+
+
+class NTN(_DenseLayerModel):
+    """pykg2vec/models/pairwise.py:868-963 (fp32 CUDA-core kernels; the grouped tensor-core
+    formulation of the bilinear term is round-2 work)."""
+
+    def __init__(self, **kwargs):
+        super(NTN, self).__init__(self.__class__.__name__.lower())
+        param_list = ["tot_entity", "tot_relation", "ent_hidden_size", "rel_hidden_size", "lmbda"]
+        param_dict = self.load_params(param_list, kwargs)
+        self.__dict__.update(param_dict)
+        d, k = self.ent_hidden_size, self.rel_hidden_size
+        self.ent_embeddings = NamedEmbedding("ent_embedding", self.tot_entity, d)
+        self.rel_embeddings = NamedEmbedding("rel_embedding", self.tot_relation, k)
+        self.mr1 = NamedEmbedding("mr1", d, k)
+        self.mr2 = NamedEmbedding("mr2", d, k)
+        self.br = NamedEmbedding("br", 1, k)
+        self.mr = NamedEmbedding("mr", k, d * d)
+        self.parameter_list = [self.ent_embeddings, self.rel_embeddings, self.mr1, self.mr2, self.br, self.mr]
+        for e in self.parameter_list:
+            nn.init.xavier_uniform_(e.weight)
+        self.loss = Criterion.pairwise_hinge
+
+    def kge_spec(self):
+        return ModelSpec("ntn", self.ent_hidden_size, rel_dim=self.rel_hidden_size)
+
+    def get_reg(self, h, r, t):
+        # lmbda * sqrt(sum over ALL parameters of ||theta||^2) (pairwise.py:962-963): a whole-table
+        # reduction, not part of the batch score; plain tensor code as in the reference
+        return self.lmbda * torch.sqrt(sum(torch.sum(torch.pow(var.weight, 2)) for var in self.parameter_list))
+
+
+class SME(_DenseLayerModel):
+    """pykg2vec/models/pairwise.py:544-661 (linear semantic matching energy)."""
+    _kge_name = "sme"
+
+    def __init__(self, **kwargs):
+        super(SME, self).__init__(self.__class__.__name__.lower())
+        param_list = ["tot_entity", "tot_relation", "hidden_size"]
+        param_dict = self.load_params(param_list, kwargs)
+        self.__dict__.update(param_dict)
+        d = self.hidden_size
+        self.ent_embeddings = NamedEmbedding("ent_embedding", self.tot_entity, d)
+        self.rel_embeddings = NamedEmbedding("rel_embedding", self.tot_relation, d)
+        self.mu1 = NamedEmbedding("mu1", d, d)
+        self.mu2 = NamedEmbedding("mu2", d, d)
+        self.bu = NamedEmbedding("bu", d, 1)
+        self.mv1 = NamedEmbedding("mv1", d, d)
+        self.mv2 = NamedEmbedding("mv2", d, d)
+        self.bv = NamedEmbedding("bv", d, 1)
+        self.parameter_list = [self.ent_embeddings, self.rel_embeddings, self.mu1, self.mu2, self.bu, self.mv1,
+                               self.mv2, self.bv]
+        for e in self.parameter_list:
+            nn.init.xavier_uniform_(e.weight)
+        self.loss = Criterion.pairwise_hinge
+
+    def kge_spec(self):
+        return ModelSpec(self._kge_name, self.hidden_size)
+
+
+class SME_BL(SME):
+    """pykg2vec/models/pairwise.py:664-724 (bilinear variant; note the POSITIVE sign of its score)."""
+    _kge_name = "sme_bl"
+
+    def __init__(self, **kwargs):
+        super(SME_BL, self).__init__(**kwargs)
+        self.model_name = self.__class__.__name__.lower()
+        self.loss = Criterion.pairwise_hinge

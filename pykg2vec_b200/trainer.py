@@ -56,7 +56,7 @@ class Trainer:
         else:
             raise NotImplementedError("No support for %s optimizer" % name)
         self._fused = name in ("sgd", "adagrad") and getattr(self.config, "fused_step", True) and \
-            hasattr(self.model, "kge_desc")
+            hasattr(self.model, "kge_desc") and not getattr(self.model, "kge_dense_params", False)
         if self._fused:
             tabs = self.model.kge_tables()
             self._grad_scratch = [torch.zeros_like(t) if t.requires_grad else None for t in tabs]

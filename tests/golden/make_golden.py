@@ -69,6 +69,10 @@ SPECS = {
     "simple_ignr": (ref_pointwise.SimplE_ignr, ["ent_head_embeddings", "ent_tail_embeddings",
                                                 "rel_embeddings", "rel_inv_embeddings"]),
     "hole": (ref_pairwise.HoLE, ["ent_embeddings", "rel_embeddings"]),
+    "slm": (ref_pairwise.SLM, ["ent_embeddings", "rel_embeddings", "mr1", "mr2"]),
+    "ntn": (ref_pairwise.NTN, ["ent_embeddings", "rel_embeddings", "mr1", "mr2", "br", "mr"]),
+    "sme": (ref_pairwise.SME, ["ent_embeddings", "rel_embeddings", "mu1", "mu2", "bu", "mv1", "mv2", "bv"]),
+    "sme_bl": (ref_pairwise.SME_BL, ["ent_embeddings", "rel_embeddings", "mu1", "mu2", "bu", "mv1", "mv2", "bv"]),
     "kg2e": (ref_pairwise.KG2E, ["ent_embeddings_mu", "ent_embeddings_sigma", "rel_embeddings_mu",
                                  "rel_embeddings_sigma"]),
     "quate": (ref_pointwise.QuatE, ["ent_s_embedding", "ent_x_embedding", "ent_y_embedding", "ent_z_embedding",
@@ -117,6 +121,12 @@ CASES = [
     ("rescal_d50", "rescal", 53, 3, dict(hidden_size=50, margin=1.0), "ref"),
     ("simple_d48", "simple", 101, 6, dict(hidden_size=48, lmbda=0.1, tot_train_triples=1000, batch_size=100), "normal"),
     ("simple_ignr_d50", "simple_ignr", 101, 6, dict(hidden_size=50, lmbda=0.1, tot_train_triples=1000, batch_size=100), "normal"),
+    ("slm_24x16", "slm", 71, 4, dict(ent_hidden_size=24, rel_hidden_size=16), "normal"),
+    ("slm_50x30", "slm", 53, 3, dict(ent_hidden_size=50, rel_hidden_size=30), "ref"),
+    ("ntn_16x12", "ntn", 47, 3, dict(ent_hidden_size=16, rel_hidden_size=12, lmbda=0.1), "normal"),
+    ("ntn_20x20", "ntn", 41, 3, dict(ent_hidden_size=20, rel_hidden_size=20, lmbda=0.1), "ref"),
+    ("sme_d24", "sme", 61, 4, dict(hidden_size=24), "normal"),
+    ("sme_bl_d20", "sme_bl", 53, 3, dict(hidden_size=20), "normal"),
     ("kg2e_d40", "kg2e", 71, 4, dict(hidden_size=40, cmax=5.0, cmin=0.05), "ref"),
     ("kg2e_d50", "kg2e", 59, 3, dict(hidden_size=50, cmax=5.0, cmin=0.05), "ref"),
     ("quate_d20", "quate", 61, 4, dict(hidden_size=20, lmbda=0.1), "normal"),

@@ -33,7 +33,7 @@ def model_kwargs(g):
     dim = int(kw.get("hidden_size", kw.get("ent_hidden_size", 0)))
     rel_dim = int(kw.get("rel_hidden_size", dim))
     margin = float(kw.get("margin", 0.0))
-    if name == "rescal":
+    if name in ("rescal", "sme", "sme_bl"):
         rel_dim = dim
     return dict(name=name, dim=dim, rel_dim=rel_dim, l1_flag=bool(kw.get("l1_flag", False)),
                 margin=margin,

@@ -71,6 +71,12 @@ SYN = [
     ("hole", 400, 7, 32, None, False, 0.0),
     ("rescal", 500, 5, 48, None, False, 0.0),
     ("rescal", 300, 5, 50, None, False, 0.0),
+    ("slm", 400, 5, 64, 32, False, 0.0),
+    ("slm", 300, 5, 50, 30, False, 0.0),
+    ("ntn", 200, 4, 32, 16, False, 0.0),
+    ("ntn", 150, 4, 20, 20, False, 0.0),
+    ("sme", 300, 5, 48, None, False, 0.0),
+    ("sme_bl", 300, 5, 50, None, False, 0.0),
     ("kg2e", 500, 5, 100, None, False, 0.0),
     ("kg2e", 300, 5, 50, None, False, 0.0),
     ("quate", 400, 5, 100, None, False, 0.0),

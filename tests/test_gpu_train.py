@@ -53,7 +53,8 @@ def test_score_bwd_vs_reference_autograd(name):
     ("hole", 200, 5, 30, None, False, 0.0), ("hole", 200, 5, 52, None, False, 0.0),
     ("rescal", 150, 4, 24, None, False, 0.0), ("simple", 300, 7, 48, None, False, 0.0),
     ("simple_ignr", 300, 7, 50, None, False, 0.0), ("analogy", 300, 7, 48, None, False, 0.0),
-    ("kg2e", 200, 5, 40, None, False, 0.0), ("quate", 200, 5, 24, None, False, 0.0), ("octonione", 150, 5, 12, None, False, 0.0),
+    ("slm", 200, 5, 24, 16, False, 0.0), ("ntn", 120, 4, 16, 12, False, 0.0), ("sme", 150, 5, 24, None, False, 0.0),
+    ("sme_bl", 150, 5, 20, None, False, 0.0), ("kg2e", 200, 5, 40, None, False, 0.0), ("quate", 200, 5, 24, None, False, 0.0), ("octonione", 150, 5, 12, None, False, 0.0),
 ], ids=lambda s: "%s-d%d" % (s[0], s[3]))
 def test_score_bwd_vs_fp64_oracle(spec):
     """duplicates in the batch (few entities) exercise the atomic scatter."""

@@ -73,7 +73,7 @@ extern "C" int kge_score_bwd(const kge_model_t* m, const int64_t* h, const int64
   const int chsel = (m->model == KGE_TRANSE || m->model == KGE_TRANSM) ? ch_select(m->dim) : 0;
 #define LAUNCH(M, V, C)                                                                            \
   do {                                                                                             \
-    if (smem > 48 * 1024)                                                                          \
+    if (smem > 40 * 1024)                                                                          \
       KGE_CUDA_OK(cudaFuncSetAttribute(score_bwd_kernel<M, V, C>,                                  \
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
     score_bwd_kernel<M, V, C><<<grid, kThreads, smem, st>>>(P, GT, h, r, t, n, grad_scores, sf);   \

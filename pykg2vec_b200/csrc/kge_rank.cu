@@ -220,7 +220,7 @@ extern "C" int kge_rank_1vsall(const kge_model_t* m, const kge_model_t* mq, int6
     const int64_t nnz = dir == 0 ? filt_t_nnz : filt_h_nnz;
     const int64_t* tgt = dir == 0 ? tgt_t : tgt_h;
 #define SET_SMEM(K)                                                                          \
-  if (smem > 48 * 1024)                                                                      \
+  if (smem > 40 * 1024)                                                                      \
     KGE_CUDA_OK(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #define CALL_THR(M, V)                                                                         \
   do {                                                                                         \

@@ -632,10 +632,10 @@ int tiled_sweep(const kge_model_t* m, const kge_model_t* mq, int dir, const int6
 #define PREP(M, V)                                                                                   \
   do {                                                                                               \
     if (dir == 0) {                                                                                  \
-      if (psmem > 48 * 1024) KGE_CUDA_OK(cudaFuncSetAttribute(prep_query_kernel<M, V, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem)); \
+      if (psmem > 40 * 1024) KGE_CUDA_OK(cudaFuncSetAttribute(prep_query_kernel<M, V, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem)); \
       prep_query_kernel<M, V, 0><<<qgrid, 256, psmem, st>>>(PQ, qh, qr, qt, Q, dp, qvec, qscale, thr, psf); \
     } else {                                                                                         \
-      if (psmem > 48 * 1024) KGE_CUDA_OK(cudaFuncSetAttribute(prep_query_kernel<M, V, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem)); \
+      if (psmem > 40 * 1024) KGE_CUDA_OK(cudaFuncSetAttribute(prep_query_kernel<M, V, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem)); \
       prep_query_kernel<M, V, 1><<<qgrid, 256, psmem, st>>>(PQ, qh, qr, qt, Q, dp, qvec, qscale, thr, psf); \
     }                                                                                                \
   } while (0)

@@ -94,7 +94,7 @@ extern "C" int kge_score_fwd(const kge_model_t* m, int grouping, const int64_t* 
                         ? ch_select(m->model == KGE_TRANSR ? m->rel_dim : m->dim) : 0;
 #define LAUNCH(M, V, C)                                                                            \
   do {                                                                                             \
-    if (smem > 48 * 1024)                                                                          \
+    if (smem > 40 * 1024)                                                                          \
       KGE_CUDA_OK(cudaFuncSetAttribute(score_fwd_kernel<M, V, C>,                                  \
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
     score_fwd_kernel<M, V, C><<<grid, kThreads, smem, st>>>(P, grouping, h, r, t, n, scores, sf);  \

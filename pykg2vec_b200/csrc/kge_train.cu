@@ -248,7 +248,7 @@ extern "C" int kge_train_pairwise_hinge_sgd(const kge_model_t* m, float* const* 
   const unsigned grid = (unsigned)((n + kGroupsPerCta - 1) / kGroupsPerCta);
 #define CALL(M, V)                                                                               \
   do {                                                                                           \
-    if (smem > 48 * 1024)                                                                        \
+    if (smem > 40 * 1024)                                                                        \
       KGE_CUDA_OK(cudaFuncSetAttribute(train_hinge_kernel<M, V>,                                 \
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     train_hinge_kernel<M, V><<<grid, kThreads, smem, st>>>(P, GT, pos_h, pos_r, pos_t, neg_h, neg_r, \

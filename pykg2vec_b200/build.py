@@ -13,6 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_build")
+OBJ_DIR = os.path.join(OUT_DIR, "obj")  # intermediate objects: listed in .gpurunignore (only the .so travels)
 LIB = os.path.join(OUT_DIR, "libkge_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
@@ -35,7 +36,7 @@ def _stamp():
 
 
 def _compile(src, verbose):
-    obj = os.path.join(OUT_DIR, os.path.basename(src)[:-3] + ".o")
+    obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
     cmd = [NVCC] + FLAGS + ["-c", src, "-o", obj]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = os.path.join(OUT_DIR, os.path.basename(src)[:-3] + ".ptxas.log")
@@ -50,7 +51,7 @@ def _compile(src, verbose):
 
 def build(force=False, verbose=False):
     """Compile every .cu under csrc/ and link the C-ABI shared library. Returns its path."""
-    os.makedirs(OUT_DIR, exist_ok=True)
+    os.makedirs(OBJ_DIR, exist_ok=True)
     stamp_file = os.path.join(OUT_DIR, "stamp.txt")
     stamp = _stamp()
     if not force and os.path.exists(LIB) and os.path.exists(stamp_file):

@@ -10,12 +10,15 @@
 //
 // Data movement (B200): operand tiles are staged in shared memory by 2-D TMA tensor-map loads
 // (cp.async.bulk.tensor.2d, completion on an mbarrier; UTMALDG.2D in SASS), double buffered;
-// out-of-range rows / columns arrive zero-filled.  Query vectors are prepared once per call
-// (prep_query_kernel, which also yields the thresholds) into a compact [Q][KQ][dp] buffer;
-// candidates come straight from the model tables (or from a normalised / even-part / padded
-// scratch copy).  Two modes, chosen on the host from the shared-memory budget: whole rows (query
-// block resident for the whole CTA, one box per candidate tile) and slabs of DS <= 256 elements
-// of the embedding axis for wide models (d = 500, 1000), accumulators living across slabs.
+// out-of-range rows / columns arrive zero-filled.  A tile is stored OCTET-MAJOR: one {32 columns
+// x rows} box per octet of the embedding axis lands as [octet][row][32 floats], so a group's 8
+// lanes read 128 contiguous bytes (conflict-free for every width) and every address in the
+// compute loop is a per-lane base plus a compile-time immediate.  Query vectors are prepared
+// once per call (prep_query_kernel, which also yields the thresholds) into a compact
+// [Q][KQ][dp] buffer; candidates come straight from the model tables (or from a normalised /
+// even-part / padded scratch copy).  Two modes, chosen on the host from the shared-memory
+// budget: whole rows (query block resident for the whole CTA) and slabs of DS <= 256 columns for
+// wide models (d = 500, 1000), accumulators living across slabs.
 //
 // Bound: fp32 pipe (2-8 instructions per element pair), not HBM: a candidate row is read from
 // L2 once per query BLOCK instead of once per query.
@@ -115,11 +118,23 @@ KGE_DEV void pair_op(float& acc, const float4* q, const float4* c) {
   }
 }
 
+// Plain L2 distances are compared in the SUM domain: sqrt_rn is monotone, so
+//   sqrt_rn(sum) < th   <=>   sum < T(th),   T(th) = min{x >= 0 : sqrt_rn(x) >= th},
+// and T is found exactly by walking a few ulps around th*th.  Saves the IEEE square root per
+// (query, candidate) pair without changing a single comparison result.
+KGE_DEV float sqrt_domain_threshold(float th) {
+  if (!(th > 0.f)) return 0.f;                       // sqrt(.) >= 0 is never below th (also th = NaN)
+  float x = fmul(th, th);                            // may round to +inf or to 0
+  while (__fsqrt_rn(x) >= th) x = __uint_as_float(__float_as_uint(x) - 1u);  // never reaches below +0: sqrt(0) < th
+  while (__fsqrt_rn(x) < th) x = __uint_as_float(__float_as_uint(x) + 1u);   // stops at +inf at the latest
+  return x;
+}
+
 template <int OP, bool L1>
 KGE_DEV float finalize(float sum, float qscale, float margin, bool has_scale, int fin) {
   if (OP == OP_TRANS_T || OP == OP_TRANS_H) {
-    const float dist = L1 ? sum : __fsqrt_rn(sum);
-    return has_scale ? fmul(qscale, dist) : dist;
+    if (L1 || !has_scale) return sum;                // L2 without a scale: threshold is in the sum domain
+    return fmul(qscale, __fsqrt_rn(sum));
   }
   if (OP == OP_DOT1 || OP == OP_DOT2) {
     if (fin == 1) return -sigmoid_canon(sum);
@@ -133,7 +148,7 @@ KGE_DEV float finalize(float sum, float qscale, float margin, bool has_scale, in
 // complete sums of the pairs  orig = b4*NV/2 + b2*NV/4 + b1*NV/8 + i  (b* = lane bits 2,1,0).
 template <int NV>
 KGE_DEV void reduce_scatter(float (&v)[NV], int lane) {
-  const unsigned m = group_mask();
+  const unsigned m = 0xffffffffu;  // the whole warp is converged here; xor 4/2/1 stays inside the 8-lane group
   {
     const bool hi = lane & 4;
 #pragma unroll
@@ -171,54 +186,77 @@ sweep_tiled_kernel(const __grid_constant__ TiledParams P, const __grid_constant_
   constexpr int KQ = OpTraits<OP>::KQ, KC = OpTraits<OP>::KC, TQ = OpTraits<OP>::TQ;
   constexpr int QBLK = kGQ * TQ;
   constexpr int NV = TQ * kTC;
+  constexpr int kWarps = kTThreads / 32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  // layout: [2 mbarriers][thr QBLK][qs QBLK][cnt QBLK] | q stages | c stages
+  // layout: [2 mbarriers][2 stage-release counters][thr QBLK][qs QBLK][cnt QBLK] | q stages | c stages
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
-  float* s_thr = reinterpret_cast<float*>(smem_raw + 16);
+  unsigned* s_done = reinterpret_cast<unsigned*>(smem_raw + 16);
+  float* s_thr = reinterpret_cast<float*>(smem_raw + 32);
   float* s_qs = s_thr + QBLK;
   int* s_cnt = reinterpret_cast<int*>(s_qs + QBLK);
-  const int hdr = ((16 + 3 * QBLK * 4) + 127) / 128 * 128;
+  const int hdr = ((32 + 3 * QBLK * 4) + 127) / 128 * 128;
   const int DS = P.DS;
   const int qstages = P.nslabs > 1 ? 2 : 1;
-  float* qbuf = reinterpret_cast<float*>(smem_raw + hdr);                      // [qstages][QBLK][KQ][DS]
-  float* cbuf = qbuf + (size_t)qstages * QBLK * KQ * DS;                        // [2][KC][CBLK][DS]
-  const int tid = threadIdx.x, lane = tid & 7, grp = tid >> 3;
-  const int gq = grp / kGC, gc = grp % kGC;
+  // thread mapping: the 4 groups of a warp share the candidate column group `gc` and cover 4
+  // adjacent query sub-blocks (`warp` comes through a shuffle so that it is known to be uniform)
+  const int tid = threadIdx.x, lane = tid & 7, lane32 = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int g = (tid >> 3) & 3;
+  const int gc = warp % kGC, gq = (warp / kGC) * 4 + g;
   const int64_t q0 = (int64_t)blockIdx.y * QBLK;
   const int qrows = (int)min((int64_t)QBLK, P.Q - q0);
   const int t0 = blockIdx.x * P.tiles_per_cta;
   const int ntile_local = min(P.tiles_per_cta, P.ntiles - t0);
   if (ntile_local <= 0) return;
   const int T = ntile_local * P.nslabs;
+  const bool sum_domain = (OP == OP_TRANS_T || OP == OP_TRANS_H) && !L1 && P.qscale == nullptr;
 
   if (tid < QBLK) {
-    const bool ok = tid < qrows;
-    s_thr[tid] = ok ? __ldg(P.thr + q0 + tid) : 0.f;
-    s_qs[tid] = (ok && P.qscale) ? __ldg(P.qscale + q0 + tid) : 1.f;
+    // rows beyond Q get a threshold no score is below, so they never count
+    float th = tid < qrows ? __ldg(P.thr + q0 + tid) : -INFINITY;
+    if (sum_domain) th = sqrt_domain_threshold(th);
+    s_thr[tid] = th;
+    s_qs[tid] = (tid < qrows && P.qscale) ? __ldg(P.qscale + q0 + tid) : 1.f;
     s_cnt[tid] = 0;
   }
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
+    s_done[0] = 0u;
+    s_done[1] = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
 
-  // producer: one thread issues the TMA tile loads of iteration `it` into stage it&1
-  // (one box per candidate table + one for the query block; OOB rows/columns arrive as zeros)
-  auto issue = [&](int it) {
-    if (tid != 0) return;
+  // producer: ONE WARP issues the TMA loads of iteration `it` into stage it&1.  A tile is stored
+  // OCTET-MAJOR — [octet of 32 columns][row][32 floats] — by one {32 x rows} box per octet and
+  // operand (lanes 0..noct-1 issue one octet each), so that every shared-memory address of the
+  // compute loop is  per-lane base + compile-time immediate  whatever the embedding width is.
+  // Out-of-range rows / columns arrive as zeros.
+  constexpr uint32_t kQOct = (uint32_t)(QBLK * KQ) * 128u;     // bytes of one query octet  [QBLK*KQ][32]
+  constexpr uint32_t kCOct = (uint32_t)(KC * kCBLK) * 128u;    // bytes of one candidate octet [KC][CBLK][32]
+  const uint32_t q_stage_bytes = (uint32_t)(QBLK * KQ) * (uint32_t)DS * 4u;
+  const uint32_t c_stage_bytes = (uint32_t)(KC * kCBLK) * (uint32_t)DS * 4u;
+  unsigned char* const qbase = smem_raw + hdr;
+  unsigned char* const cbase = qbase + (size_t)qstages * q_stage_bytes;
+  auto issue = [&](int it) {   // called by all 32 lanes of one warp
     const int stage = it & 1;
     const int tile = t0 + it / P.nslabs, slab = it % P.nslabs;
     const bool load_q = (P.nslabs > 1) || (it == 0);
-    float* qdst = qbuf + (size_t)(P.nslabs > 1 ? stage : 0) * QBLK * KQ * DS;
-    float* cdst = cbuf + (size_t)stage * KC * kCBLK * DS;
-    const uint32_t total = (uint32_t)((KC * kCBLK + (load_q ? QBLK * KQ : 0)) * DS * 4);
-    mbar_arrive_expect_tx(&bars[stage], total);
-    tma_load_2d(cdst, &TM.c0, slab * DS, tile * kCBLK, &bars[stage]);
-    if (KC == 2) tma_load_2d(cdst + (size_t)kCBLK * DS, &TM.c1, slab * DS, tile * kCBLK, &bars[stage]);
-    if (load_q) tma_load_2d(qdst, &TM.q, slab * DS, (int)(q0 * KQ), &bars[stage]);
+    const int noct = (min(DS, P.dp - slab * DS) + 31) >> 5;
+    if (lane32 == 0)
+      mbar_arrive_expect_tx(&bars[stage], (uint32_t)noct * (kCOct + (load_q ? kQOct : 0u)));
+    __syncwarp();
+    if (lane32 < noct) {
+      unsigned char* cdst = cbase + (size_t)stage * c_stage_bytes + (size_t)lane32 * kCOct;
+      const int col = slab * DS + 32 * lane32;
+      tma_load_2d(cdst, &TM.c0, col, tile * kCBLK, &bars[stage]);
+      if (KC == 2) tma_load_2d(cdst + (size_t)kCBLK * 128u, &TM.c1, col, tile * kCBLK, &bars[stage]);
+      if (load_q)
+        tma_load_2d(qbase + (size_t)(P.nslabs > 1 ? stage : 0) * q_stage_bytes + (size_t)lane32 * kQOct, &TM.q, col,
+                    (int)(q0 * KQ), &bars[stage]);
+    }
   };
 
   // which pair(s) this lane finishes after the reduce-scatter, and its (fixed) query row
@@ -226,17 +264,18 @@ sweep_tiled_kernel(const __grid_constant__ TiledParams P, const __grid_constant_
   const int orig0 = b4 * (NV / 2) + b2 * (NV / 4) + b1 * (NV / 8);
   const int my_iq = orig0 / kTC;                 // same for all of the lane's results
   const int qrow = gq * TQ + my_iq;
-  const bool qvalid = qrow < qrows;
   const float th = s_thr[qrow], qsc = s_qs[qrow];
   const bool has_scale = P.qscale != nullptr;
   int cnt = 0;
 
   float acc[kNT][NV];
-  issue(0);
+  if (warp == 0) {
+    issue(0);
+    if (T > 1) issue(1);
+  }
+  int tile = t0, slab = 0;
   for (int it = 0; it < T; ++it) {
     const int stage = it & 1;
-    const int tile = t0 + it / P.nslabs, slab = it % P.nslabs;
-    if (it + 1 < T) issue(it + 1);
     if (slab == 0) {
 #pragma unroll
       for (int nt = 0; nt < kNT; ++nt)
@@ -244,47 +283,62 @@ sweep_tiled_kernel(const __grid_constant__ TiledParams P, const __grid_constant_
         for (int i = 0; i < NV; ++i) acc[nt][i] = 0.f;
     }
     mbar_wait(&bars[stage], (uint32_t)((it >> 1) & 1));
-    const int slab_len = min(DS, P.dp - slab * DS);
-    const int nch = slab_len >> 2;
-    const float* qs = qbuf + (size_t)(P.nslabs > 1 ? stage : 0) * QBLK * KQ * DS + (size_t)(gq * TQ) * KQ * DS;
-    const float* cs = cbuf + (size_t)stage * KC * kCBLK * DS;
-    for (int c = lane; c < nch; c += 8) {
+    const int nch = min(DS, P.dp - slab * DS) >> 2;
+    // lane's chunk c = 8*octet + lane of row r sits at  octet*OctBytes + r*128 + lane*16
+    const unsigned char* qs = qbase + (size_t)(P.nslabs > 1 ? stage : 0) * q_stage_bytes + (gq * TQ * KQ) * 128 + lane * 16;
+    const unsigned char* cs = cbase + (size_t)stage * c_stage_bytes + (gc * kTC) * 128 + lane * 16;
+    for (int c = lane; c < nch; c += 8, qs += kQOct, cs += kCOct) {
       float4 q4[TQ][KQ];
 #pragma unroll
       for (int i = 0; i < TQ; ++i)
 #pragma unroll
         for (int k = 0; k < KQ; ++k)
-          q4[i][k] = *reinterpret_cast<const float4*>(qs + ((size_t)i * KQ + k) * DS + 4 * c);
+          q4[i][k] = *reinterpret_cast<const float4*>(qs + (i * KQ + k) * 128);
 #pragma unroll
       for (int nt = 0; nt < kNT; ++nt) {
         float4 c4[kTC][KC];
-        const int crow0 = (gc + kGC * nt) * kTC;
 #pragma unroll
         for (int j = 0; j < kTC; ++j)
 #pragma unroll
           for (int k = 0; k < KC; ++k)
-            c4[j][k] = *reinterpret_cast<const float4*>(cs + ((size_t)k * kCBLK + crow0 + j) * DS + 4 * c);
+            c4[j][k] = *reinterpret_cast<const float4*>(cs + (k * kCBLK + kGC * kTC * nt + j) * 128);
 #pragma unroll
         for (int i = 0; i < TQ; ++i)
 #pragma unroll
           for (int j = 0; j < kTC; ++j) pair_op<OP, L1>(acc[nt][i * kTC + j], q4[i], c4[j]);
       }
     }
+    // Stage recycling without a CTA barrier: every warp bumps the stage's release counter when it
+    // has read its last operand of this iteration; the warp that arrives last (count % kWarps ==
+    // kWarps-1) refills the stage with iteration it+2.  No warp ever waits for another warp —
+    // only for data.
+    __syncwarp();
+    {
+      unsigned prev = 0u;
+      if (lane32 == 0) {
+        __threadfence_block();
+        prev = atomicAdd(&s_done[stage], 1u);
+        __threadfence_block();
+      }
+      prev = __shfl_sync(0xffffffffu, prev, 0);
+      if ((prev % kWarps) == kWarps - 1 && it + 2 < T) issue(it + 2);
+    }
     if (slab == P.nslabs - 1) {
-      const int64_t cbase = (int64_t)tile * kCBLK;
+      // candidates of this tile that exist (the last tile may be ragged; missing rows are zeros)
+      const int nvalid = (int)min((int64_t)kCBLK, P.nc - (int64_t)tile * kCBLK);
 #pragma unroll
       for (int nt = 0; nt < kNT; ++nt) {
         reduce_scatter<NV>(acc[nt], lane);
 #pragma unroll
         for (int i = 0; i < NV / 8; ++i) {
           const int jc = (orig0 + i) % kTC;
-          const int64_t cand = cbase + (gc + kGC * nt) * kTC + jc;
+          const int local = (gc + kGC * nt) * kTC + jc;
           const float s = finalize<OP, L1>(acc[nt][i], qsc, P.margin, has_scale, P.fin);
-          cnt += (qvalid && cand < P.nc && s < th) ? 1 : 0;
+          cnt += (local < nvalid && s < th) ? 1 : 0;
         }
       }
     }
-    __syncthreads();  // everyone is done with stage `stage` before it is refilled at it+2
+    if (++slab == P.nslabs) { slab = 0; ++tile; }
   }
   if (cnt) atomicAdd(&s_cnt[qrow], cnt);
   __syncthreads();
@@ -585,12 +639,13 @@ template <int OP, bool L1>
 static int launch_sweep(const TiledParams& P, int QBLK, size_t smem, cudaStream_t st, int splits, int qblocks) {
   constexpr int KQ = OpTraits<OP>::KQ, KC = OpTraits<OP>::KC;
   TiledMaps TM;
-  int rc = make_map(&TM.q, P.qvec, (uint64_t)P.Q * KQ, (uint64_t)P.dp, (uint64_t)P.dp, (uint32_t)P.DS, (uint32_t)(QBLK * KQ));
+  // one box = one octet: 32 columns x all rows of the tile (columns >= dp / rows >= extent read as zeros)
+  int rc = make_map(&TM.q, P.qvec, (uint64_t)P.Q * KQ, (uint64_t)P.dp, (uint64_t)P.dp, 32u, (uint32_t)(QBLK * KQ));
   if (rc) return rc;
-  rc = make_map(&TM.c0, P.cand[0], (uint64_t)P.nc, (uint64_t)P.dp, (uint64_t)P.cand_pitch, (uint32_t)P.DS, (uint32_t)kCBLK);
+  rc = make_map(&TM.c0, P.cand[0], (uint64_t)P.nc, (uint64_t)P.dp, (uint64_t)P.cand_pitch, 32u, (uint32_t)kCBLK);
   if (rc) return rc;
   if (KC == 2) {
-    rc = make_map(&TM.c1, P.cand[1], (uint64_t)P.nc, (uint64_t)P.dp, (uint64_t)P.cand_pitch, (uint32_t)P.DS, (uint32_t)kCBLK);
+    rc = make_map(&TM.c1, P.cand[1], (uint64_t)P.nc, (uint64_t)P.dp, (uint64_t)P.cand_pitch, 32u, (uint32_t)kCBLK);
     if (rc) return rc;
   } else {
     TM.c1 = TM.c0;
@@ -672,17 +727,20 @@ int tiled_sweep(const kge_model_t* m, const kge_model_t* mq, int dir, const int6
     }
   }
 
-  // 3. shared-memory plan: full rows when they fit in ~110 KB (2 CTAs/SM), else slabs of DS elements
-  const size_t budget = 110 * 1024;
-  const size_t hdr = align_up(16 + 3 * (size_t)QBLK * 4, 128);
+  // 3. shared-memory plan (DS = columns staged per iteration, a multiple of 32 = whole octets):
+  // whole rows when two CTAs of them fit in one SM (228 KB minus 1 KB reserved per CTA), else
+  // slabs of DS columns with the accumulators living across slabs
+  const size_t budget = (228 * 1024) / 2 - 1024;
+  const size_t hdr = align_up(32 + 3 * (size_t)QBLK * 4, 128);
   auto bytes_for = [&](int DS, int qstages) {
     return hdr + ((size_t)QBLK * KQ * qstages + (size_t)kCBLK * KC * 2) * (size_t)DS * sizeof(float);
   };
+  const int dp32 = (dp + 31) / 32 * 32;
   int DS, nslabs;
-  if (dp <= 256 && bytes_for(dp, 1) <= budget) { DS = dp; nslabs = 1; }   // whole rows; box dims are <= 256
+  if (dp32 <= 256 && bytes_for(dp32, 1) <= budget) { DS = dp32; nslabs = 1; }
   else {
     DS = 32;
-    while (DS + 32 <= dp && DS + 32 <= 256 && bytes_for(DS + 32, 2) <= budget) DS += 32;
+    while (DS + 32 <= dp32 && DS + 32 <= 256 && bytes_for(DS + 32, 2) <= budget) DS += 32;
     nslabs = (dp + DS - 1) / DS;
   }
   const size_t smem = bytes_for(DS, nslabs > 1 ? 2 : 1);
@@ -690,7 +748,7 @@ int tiled_sweep(const kge_model_t* m, const kge_model_t* mq, int dir, const int6
   P.Q = Q; P.nc = nc; P.dp = dp; P.DS = DS; P.nslabs = nslabs;
   P.ntiles = (int)((nc + kCBLK - 1) / kCBLK);
   const int qblocks = (int)((Q + QBLK - 1) / QBLK);
-  const int ctas_per_sm = smem * 2 + 2048 <= 227 * 1024 ? 2 : 1;
+  const int ctas_per_sm = (smem + 1024) * 2 <= 228 * 1024 ? 2 : 1;
   int splits = (sm_count() * ctas_per_sm + qblocks - 1) / qblocks;
   if (splits < 1) splits = 1;
   if (splits > P.ntiles) splits = P.ntiles;

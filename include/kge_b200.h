@@ -71,7 +71,13 @@ enum kge_model_id {
   KGE_SME = 18,     /* [ent, rel, mu1, mu2, bu, mv1, mv2, bv] (d x d, d x 1)  pairwise.py:617-661 */
   KGE_SME_BL = 19,  /* same tables                                           pairwise.py:680-724 */
   KGE_NTN = 20,     /* [ent, rel, mr1, mr2, br(1 x k), mr(k x d*d)]          pairwise.py:919-960 */
-  KGE_NUM_MODELS = 21
+  /* ConvKB: Conv2d(1->F,(3,w)) over the stacked [h;r;t], concat, Linear->1 with NO
+   * nonlinearity in between (pointwise.py:302-318), i.e. an affine map of (h,r,t):
+   *   score = <a_h,h> + <a_r,r> + <a_t,t> + c0 .
+   * tables: [ent, rel, A(3 x d: rows a_h, a_r, a_t), c0(1)] with A, c0 the collapse of the
+   * convolution filters with the Linear weights (host mirror: class ConvKB, pointwise.py). */
+  KGE_CONVKB = 21,
+  KGE_NUM_MODELS = 22
 };
 
 /* Which two operands are combined first.  TAIL: (h,r) are the

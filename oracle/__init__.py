@@ -25,7 +25,7 @@ _SO = os.path.join(_OUT_DIR, "libkge_oracle.so")
 MODEL_IDS = {
     "transe": 0, "transh": 1, "transd": 2, "transr": 3, "rotate": 4, "hole": 5,
     "distmult": 6, "complex": 7, "cp": 8, "simple": 9, "transm": 10, "rescal": 11, "analogy": 12,
-    "simple_ignr": 13, "quate": 14, "octonione": 15, "kg2e": 16, "slm": 17, "sme": 18, "sme_bl": 19, "ntn": 20,
+    "simple_ignr": 13, "quate": 14, "octonione": 15, "kg2e": 16, "slm": 17, "sme": 18, "sme_bl": 19, "ntn": 20, "convkb": 21,
 }
 GROUP_TAIL, GROUP_HEAD = 0, 1
 MAX_TABLES = 16

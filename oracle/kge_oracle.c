@@ -40,7 +40,7 @@
 enum { KGE_TRANSE = 0, KGE_TRANSH = 1, KGE_TRANSD = 2, KGE_TRANSR = 3, KGE_ROTATE = 4,
        KGE_HOLE = 5, KGE_DISTMULT = 6, KGE_COMPLEX = 7, KGE_CP = 8, KGE_SIMPLE = 9,
        KGE_TRANSM = 10, KGE_RESCAL = 11, KGE_ANALOGY = 12, KGE_SIMPLE_IGNR = 13, KGE_QUATE = 14,
-       KGE_OCTONIONE = 15, KGE_KG2E = 16, KGE_SLM = 17, KGE_SME = 18, KGE_SME_BL = 19, KGE_NTN = 20 };
+       KGE_OCTONIONE = 15, KGE_KG2E = 16, KGE_SLM = 17, KGE_SME = 18, KGE_SME_BL = 19, KGE_NTN = 20, KGE_CONVKB = 21 };
 enum { KGE_GROUP_TAIL = 0, KGE_GROUP_HEAD = 1 };
 
 typedef struct kge_model {
@@ -284,6 +284,19 @@ static float score_one(const kge_model_t* m, int grouping, int64_t h, int64_t r,
         else { const float q = rv[j] * tv[j]; *p = fmaf(hv[j], q, *p); }
       }
       return -rs_finish(&s);
+    }
+    case KGE_CONVKB: { /* pointwise.py:302-318, collapsed: tables [ent, rel, A(3 x d), c0(1)] (include/kge_b200.h) */
+      const float *hv = row(m, 0, h, d), *rv = row(m, 1, r, d), *tv = row(m, 0, t, d);
+      const float *ah = m->tables[2], *ar = ah + d, *at = ah + 2 * (size_t)d;
+      rsum_t sh, sr, st; rs_init(&sh); rs_init(&sr); rs_init(&st);
+      for (int j = 0; j < d; ++j) {
+        float* p = rs_at(&sh, j); *p = fmaf(hv[j], ah[j], *p);
+        p = rs_at(&sr, j); *p = fmaf(rv[j], ar[j], *p);
+        p = rs_at(&st, j); *p = fmaf(tv[j], at[j], *p);
+      }
+      const float a = rs_finish(&sh), b = rs_finish(&sr), c = rs_finish(&st);
+      const float s = (grouping == KGE_GROUP_TAIL) ? ((a + b) + c) : (a + (b + c));
+      return s + m->tables[3][0];
     }
     case KGE_COMPLEX: { /* pointwise.py:163-188 */
       const float *hr = row(m, 0, h, d), *hi = row(m, 1, h, d), *rr = row(m, 2, r, d),

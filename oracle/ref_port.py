@@ -137,6 +137,21 @@ def score(name, tables, h, r, t, l1_flag=False, margin=0.0, embedding_range=None
         d = ent.shape[1]
         m = mat[r].view(-1, d, d)
         return -torch.sum(ent[h].unsqueeze(2) * torch.matmul(m, ent[t].unsqueeze(2)), [1, 2])
+    if name == "convkb_raw":
+        # pointwise.py:302-318 as written.  tables = [ent, rel, conv_w0, conv_b0, conv_w1, conv_b1, ...,
+        # fc_w, fc_b]: Conv2d(1->F,(3,w)) over the stacked [h;r;t] for every filter size, concat along
+        # the width, flatten, Linear -> 1.
+        ent, rel = tables[0], tables[1]
+        fc_w, fc_b = tables[-2], tables[-1]
+        x = torch.stack([ent[h], rel[r], ent[t]], dim=1).unsqueeze(1)          # [b,1,3,k]
+        outs = [F.conv2d(x, tables[i], tables[i + 1]) for i in range(2, len(tables) - 2, 2)]
+        flat = torch.cat(outs, dim=3).view(x.shape[0], -1)
+        return torch.squeeze(F.linear(flat, fc_w, fc_b), dim=-1)
+    if name == "convkb":
+        # the same map in the collapsed affine form of the C-ABI (include/kge_b200.h KGE_CONVKB):
+        # tables = [ent, rel, A(3 x k), c0(1)] from convkb_collapse() below
+        ent, rel, A, c0 = tables
+        return (ent[h] * A[0]).sum(-1) + (rel[r] * A[1]).sum(-1) + (ent[t] * A[2]).sum(-1) + c0[0]
     if name in ("simple", "simple_ignr"):  # pointwise.py:514-526, 573-581
         eh, et, rel, rinv = tables
         first = torch.sum(eh[h] * rel[r] * et[t], 1)
@@ -154,6 +169,29 @@ def score(name, tables, h, r, t, l1_flag=False, margin=0.0, embedding_range=None
         e = torch.fft.ifft(torch.complex(fh.real * ft.real, fh.imag * ft.imag), dim=1).real
         return -torch.sigmoid(torch.sum(rn * e, 1))
     raise NotImplementedError(name)
+
+
+def convkb_collapse(conv_ws, conv_bs, fc_w, fc_b, k):
+    """ConvKB has no nonlinearity between its convolutions and its Linear layer
+    (pointwise.py:311-316), so score = <a_h,h> + <a_r,r> + <a_t,t> + c0 with
+      A[row, j] = sum_w sum_f sum_q K_w[f,0,row,q] * W[f, off_w + j - q]   (0 <= j-q <= k-w)
+      c0        = fc_b + sum_w sum_f b_w[f] * sum_p W[f, off_w + p]
+    where W = fc_w.view(F, sum_w(k-w+1)) (concat along the width, then flatten: index f*sumP+off+p).
+    Returns (A [3,k], c0 [1]) in the dtype of fc_w; differentiable w.r.t. every argument."""
+    nf = conv_ws[0].shape[0]
+    W = fc_w.reshape(nf, -1)
+    A = torch.zeros((3, k), dtype=fc_w.dtype, device=fc_w.device)
+    c0 = fc_b.reshape(1).clone()
+    off = 0
+    for kw_, kb_ in zip(conv_ws, conv_bs):
+        w = kw_.shape[-1]
+        P = k - w + 1
+        Wf = W[:, off:off + P]                                   # [F, P]
+        # out[row, j] = sum_f sum_q Wf[f, j-q] * K[f, row, q]
+        A = A + F.conv_transpose1d(Wf.unsqueeze(0), kw_[:, 0]).squeeze(0)
+        c0 = c0 + (kb_ * Wf.sum(1)).sum().reshape(1)
+        off += P
+    return A, c0
 
 
 def gathered_rows(name, tables, h, r, t):

@@ -35,6 +35,7 @@ MODEL_MAP = {
     "octonione": ("pykg2vec_b200.pointwise", "OctonionE"),
     "simple": ("pykg2vec_b200.pointwise", "SimplE"),
     "simple_ignr": ("pykg2vec_b200.pointwise", "SimplE_ignr"),
+    "convkb": ("pykg2vec_b200.pointwise", "ConvKB"),
 }
 
 

@@ -42,7 +42,7 @@ int num_tables(int model) {
     case KGE_TRANSD: case KGE_COMPLEX: case KGE_SIMPLE: case KGE_SIMPLE_IGNR: case KGE_KG2E: return 4;
     case KGE_ANALOGY: return 6;
     case KGE_QUATE: case KGE_SME: case KGE_SME_BL: return 8;
-    case KGE_SLM: return 4;
+    case KGE_SLM: case KGE_CONVKB: return 4;
     case KGE_NTN: return 6;
     case KGE_OCTONIONE: return 16;
     default: return 0;

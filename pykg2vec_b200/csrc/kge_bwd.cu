@@ -31,7 +31,7 @@ score_bwd_kernel(ModelParams P, GradTables GT, const int64_t* __restrict__ h,
 #pragma unroll
     for (int c = 0; c < 8; ++c) G.h[c] = G.t[c] = G.r[c] = nullptr;
   }
-  if (!valid && (MODEL == KGE_SLM || MODEL == KGE_NTN || MODEL == KGE_SME || MODEL == KGE_SME_BL)) return;
+  if (!valid && (MODEL == KGE_SLM || MODEL == KGE_NTN || MODEL == KGE_SME || MODEL == KGE_SME_BL || MODEL == KGE_CONVKB)) return;
   grad_group<MODEL, VEC, CHSEL>(R, G, P, lane, __ldg(gout + gi), scratch);
 }
 

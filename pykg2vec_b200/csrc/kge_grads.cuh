@@ -26,7 +26,7 @@ KGE_DEV void resolve_grad_rows(GradRows& G, const ModelParams& P, float* const* 
 #pragma unroll
   for (int c = 0; c < 8; ++c) G.h[c] = G.t[c] = G.r[c] = nullptr;
   auto at = [&](int k, size_t off) -> float* { return gt[k] ? gt[k] + off : nullptr; };
-  if (MODEL == KGE_SLM || MODEL == KGE_NTN || MODEL == KGE_SME || MODEL == KGE_SME_BL) {
+  if (MODEL == KGE_SLM || MODEL == KGE_NTN || MODEL == KGE_SME || MODEL == KGE_SME_BL || MODEL == KGE_CONVKB) {
     G.h[0] = at(0, h * d); G.t[0] = at(0, t * d); G.r[0] = at(1, r * dr);
     // dense parameters: whole gradient tables (not per-row)
 #pragma unroll
@@ -394,6 +394,25 @@ KGE_DEV void grad_group(const TripleRows& R, const GradRows& G, const ModelParam
       red_row_chunk<VEC>(G.r[0], c, d, gr);
       red_row_chunk<VEC>(G.t[0], c, d, gtt);
     }
+  } else if (MODEL == KGE_CONVKB) {
+    // s = <a_h,h> + <a_r,r> + <a_t,t> + c0:  d row = gs * a ;  d a += gs * row ;  d c0 += gs
+    const float* A = P.tab[2];
+    float* gA = G.r[2];
+    for (int c = lane; c < nch; c += 8) {
+      const float4 a = ld_chunk<VEC>(R.h[0], c, d), b = ld_chunk<VEC>(R.r[0], c, d), cc = ld_chunk<VEC>(R.t[0], c, d);
+      const float4 wa = ld_chunk<VEC>(A, c, d), wb = ld_chunk<VEC>(A + d, c, d), wc = ld_chunk<VEC>(A + 2 * (size_t)d, c, d);
+      float4 gh, gr, gtt, ga, gb, gc;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        f4_at(gh, e) = gs * f4_get(wa, e); f4_at(gr, e) = gs * f4_get(wb, e); f4_at(gtt, e) = gs * f4_get(wc, e);
+        f4_at(ga, e) = gs * f4_get(a, e); f4_at(gb, e) = gs * f4_get(b, e); f4_at(gc, e) = gs * f4_get(cc, e);
+      }
+      red_row_chunk<VEC>(G.h[0], c, d, gh);
+      red_row_chunk<VEC>(G.r[0], c, d, gr);
+      red_row_chunk<VEC>(G.t[0], c, d, gtt);
+      if (gA) { red_chunk<VEC>(gA, c, d, ga); red_chunk<VEC>(gA + d, c, d, gb); red_chunk<VEC>(gA + 2 * (size_t)d, c, d, gc); }
+    }
+    if (lane == 0 && G.r[3]) atomicAdd(G.r[3], gs);
   } else if (MODEL == KGE_COMPLEX) {
     const float ng = -gs;
     for (int c = lane; c < nch; c += 8) {

@@ -24,7 +24,7 @@ KGE_DEV void resolve_rows(TripleRows& R, const ModelParams& P, const float* cons
                           int64_t t) {
   const size_t d = (size_t)P.d, dr = (size_t)P.dr;
   R.h[1] = R.t[1] = R.r[1] = R.r[2] = R.h[2] = R.t[2] = nullptr;
-  if (MODEL == KGE_SLM || MODEL == KGE_NTN || MODEL == KGE_SME || MODEL == KGE_SME_BL) {
+  if (MODEL == KGE_SLM || MODEL == KGE_NTN || MODEL == KGE_SME || MODEL == KGE_SME_BL || MODEL == KGE_CONVKB) {
     // only the embedding rows are per-triple; the dense parameters are read through P.tab[2..]
     R.h[0] = htab[0] + h * d; R.t[0] = ttab[0] + t * d; R.r[0] = rtab[1] + r * dr;
   } else if (MODEL == KGE_KG2E) {  // [ent_mu, ent_sigma, rel_mu, rel_sigma]
@@ -499,6 +499,25 @@ KGE_DEV float score_group(const TripleRows& R, const ModelParams& P, int lane, f
       }
     }
     return -group_sum(acc);
+  } else if (MODEL == KGE_CONVKB) {
+    // ConvKB.forward pointwise.py:302-318 in its collapsed affine form (include/kge_b200.h):
+    // three canonical sums, combined in the grouping's order, plus the constant
+    const float* A = P.tab[2];
+    float sh = 0.f, sr = 0.f, st = 0.f;
+#pragma unroll 2
+    for (int c = lane; c < nch; c += 8) {
+      const float4 a = ld_chunk<VEC>(R.h[0], c, d), b = ld_chunk<VEC>(R.r[0], c, d), cc = ld_chunk<VEC>(R.t[0], c, d);
+      const float4 wa = ld_chunk<VEC>(A, c, d), wb = ld_chunk<VEC>(A + d, c, d), wc = ld_chunk<VEC>(A + 2 * (size_t)d, c, d);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        sh = ffma(f4_get(a, e), f4_get(wa, e), sh);
+        sr = ffma(f4_get(b, e), f4_get(wb, e), sr);
+        st = ffma(f4_get(cc, e), f4_get(wc, e), st);
+      }
+    }
+    sh = group_sum(sh); sr = group_sum(sr); st = group_sum(st);
+    const float s = (GROUPING == KGE_GROUP_TAIL) ? fadd(fadd(sh, sr), st) : fadd(sh, fadd(sr, st));
+    return fadd(s, __ldg(P.tab[3]));
   } else if (MODEL == KGE_COMPLEX) {
     // Complex.forward pointwise.py:163-188
     float acc = 0.f;
@@ -781,6 +800,7 @@ inline size_t group_scratch_floats(const kge_model_t* m) {
       case KGE_RESCAL: KGE_DISPATCH_VEC(KGE_RESCAL, vec, CALL); break;             \
       case KGE_SIMPLE: KGE_DISPATCH_VEC(KGE_SIMPLE, vec, CALL); break;             \
       case KGE_SIMPLE_IGNR: KGE_DISPATCH_VEC(KGE_SIMPLE_IGNR, vec, CALL); break;   \
+      case KGE_CONVKB: KGE_DISPATCH_VEC(KGE_CONVKB, vec, CALL); break;             \
       default: ::kge::set_error("model id %d not supported", (int)(model)); return KGE_ENOTSUP; \
     }                                                                              \
   } while (0)

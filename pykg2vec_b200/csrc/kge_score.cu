@@ -63,6 +63,7 @@ int model_vec(const kge_model_t* m) {
   if (m->model == KGE_HOLE) return (m->dim % 4 == 0) ? pick_vec(m, nt, m->dim) : 1;  // mirrored scalar reads
   if (m->model == KGE_SLM || m->model == KGE_NTN) return pick_vec(m, nt, m->dim, m->rel_dim);
   if (m->model == KGE_SME || m->model == KGE_SME_BL) return pick_vec(m, 2, m->dim);  // matrices: scalar reads
+  if (m->model == KGE_CONVKB) return pick_vec(m, 3, m->dim);                          // c0 is one scalar
   return pick_vec(m, nt, m->dim, m->model == KGE_TRANSR ? m->rel_dim : 0);
 }
 

@@ -1,5 +1,6 @@
 """Pointwise (logistic) models — same surface as pykg2vec/models/pointwise.py; forward()
 and get_reg() are CUDA kernels (kge_score_fwd / kge_reg_fwd_bwd)."""
+import torch
 import torch.nn as nn
 
 from .criterion import Criterion
@@ -321,3 +322,67 @@ class OctonionE(_HyperComplex):
     def embed(self, h, r, t):
         e, rl = self.parameter_list[:8], self.parameter_list[8:16]
         return tuple(x(h) for x in e) + tuple(x(t) for x in e) + tuple(x(r) for x in rl)
+
+
+class ConvKB(_KernelScored, PointwiseModel):
+    """pykg2vec/models/pointwise.py:241-318.
+
+    The reference stacks [h; r; t] into a [b,1,3,k] image, applies Conv2d(1 -> F, (3, w)) for every
+    filter size w, concatenates, flattens and applies Linear -> 1 — with NO nonlinearity in between
+    (pointwise.py:311-316).  The score is therefore an affine map of the three rows,
+        score = <a_h, h> + <a_r, r> + <a_t, t> + c0,
+    and the per-triple work is three length-k dot products: that is what the CUDA kernel evaluates
+    (KGE_CONVKB, include/kge_b200.h).  The [3,k] coefficient rows and c0 are the collapse of the
+    convolution filters with the Linear weights (`_collapse`, tiny: 3k outputs), recomputed from the
+    live parameters on every call and differentiable, so `fc1` trains through autograd exactly as in
+    the reference.  As in the reference, `conv_list` is a plain Python list: its filters are not
+    registered parameters, are not in state_dict() and are never updated by the optimizer."""
+    kge_dense_params = True
+
+    def __init__(self, **kwargs):
+        super(ConvKB, self).__init__(self.__class__.__name__.lower())
+        param_list = ["tot_entity", "tot_relation", "hidden_size", "num_filters", "filter_sizes"]
+        param_dict = self.load_params(param_list, kwargs)
+        self.__dict__.update(param_dict)
+        k = self.hidden_size
+        device = kwargs["device"]
+        self.filter_sizes = [int(w) for w in self.filter_sizes]
+        self.ent_embeddings = NamedEmbedding("ent_embedding", self.tot_entity, k)
+        self.rel_embeddings = NamedEmbedding("rel_embedding", self.tot_relation, k)
+        nn.init.xavier_uniform_(self.ent_embeddings.weight)
+        nn.init.xavier_uniform_(self.rel_embeddings.weight)
+        self.parameter_list = [self.ent_embeddings, self.rel_embeddings]
+        self.conv_list = [nn.Conv2d(1, self.num_filters, (3, w), stride=(1, 1)).to(device) for w in self.filter_sizes]
+        conv_out_dim = self.num_filters * sum(k - w + 1 for w in self.filter_sizes)
+        self.fc1 = nn.Linear(in_features=conv_out_dim, out_features=1, bias=True)
+        self.loss = Criterion.pointwise_logistic
+
+    def _collapse(self):
+        """(A [3,k], c0 [1]):  A[row, j] = sum_w sum_f sum_q K_w[f,0,row,q] * W[f, off_w + j - q],
+        c0 = fc_b + sum_w sum_f b_w[f] * sum_p W[f, off_w + p],  W = fc1.weight.view(F, -1)
+        (the concat is along the width, the flatten is filter-major: index f*sumP + off_w + p)."""
+        k, nf = self.hidden_size, self.num_filters
+        W = self.fc1.weight.view(nf, -1)
+        dev = W.device
+        A = torch.zeros((3, k), dtype=W.dtype, device=dev)
+        c0 = self.fc1.bias.reshape(1)
+        off = 0
+        for conv, w in zip(self.conv_list, self.filter_sizes):
+            P = k - w + 1
+            Wf = W[:, off:off + P]
+            K = conv.weight.detach().to(dev)[:, 0]                        # [F, 3, w], not trained
+            parts = [torch.nn.functional.pad(torch.matmul(K[:, :, q].t(), Wf), (q, w - 1 - q)) for q in range(w)]
+            A = A + sum(parts)
+            c0 = c0 + torch.dot(conv.bias.detach().to(dev), Wf.sum(1)).reshape(1)
+            off += P
+        return A.contiguous(), c0
+
+    def kge_tables(self):
+        A, c0 = self._collapse()
+        return [self.ent_embeddings.weight, self.rel_embeddings.weight, A, c0]
+
+    def kge_spec(self):
+        return ModelSpec("convkb", self.hidden_size)
+
+    def embed(self, h, r, t):
+        return self.ent_embeddings(h), self.rel_embeddings(r), self.ent_embeddings(t)

@@ -81,6 +81,7 @@ SPECS = {
                   ["rel_embedding_%d" % i for i in range(1, 9)]),
     "analogy": (ref_pointwise.ANALOGY, ["ent_embeddings", "rel_embeddings", "ent_embeddings_real",
                                         "ent_embeddings_img", "rel_embeddings_real", "rel_embeddings_img"]),
+    "convkb": (ref_pointwise.ConvKB, ["ent_embeddings", "rel_embeddings"]),
 }
 
 
@@ -137,6 +138,9 @@ CASES = [
     ("analogy_d100", "analogy", 71, 4, dict(hidden_size=100, lmbda=0.1), "ref"),
     ("hole_d30", "hole", 83, 5, dict(hidden_size=30, cmax=0.5, cmin=-0.5), "normal"),
     ("hole_d150", "hole", 61, 4, dict(hidden_size=150, cmax=0.5, cmin=-0.5), "ref"),
+    # (new cases are appended so that the seeds of the existing ones never change)
+    ("convkb_d24", "convkb", 71, 4, dict(hidden_size=24, num_filters=5, filter_sizes=[1, 2, 3], device="cpu"), "normal"),
+    ("convkb_d100", "convkb", 53, 3, dict(hidden_size=100, num_filters=50, filter_sizes=[1, 2], device="cpu"), "ref"),
 ]
 N_TRIPLES = 96
 N_QUERIES = 6
@@ -222,6 +226,26 @@ def make_case(name, model, N, R, kw, init, seed):
         out["table%d" % i] = emb.weight.detach().numpy().copy()
         out["grad%d" % i] = emb.weight.grad.detach().numpy().copy()
     out["table_keys"] = np.asarray(keys)
+    if model == "convkb":
+        # raw parameters of the reference (conv_list is a plain Python list: not in state_dict) and
+        # their gradients, plus the C-ABI tables 2/3 = the collapsed affine form computed in fp64
+        # from those parameters (oracle/ref_port.py convkb_collapse; see include/kge_b200.h)
+        sys.path.insert(0, os.path.join(HERE, "..", ".."))
+        from oracle import ref_port
+        raw = [m.ent_embeddings.weight, m.rel_embeddings.weight]
+        for conv in m.conv_list:
+            raw += [conv.weight, conv.bias]
+        raw += [m.fc1.weight, m.fc1.bias]
+        for i, p_ in enumerate(raw):
+            out["raw%d" % i] = p_.detach().numpy().copy()
+            out["rawgrad%d" % i] = p_.grad.detach().numpy().copy()
+        A, c0 = ref_port.convkb_collapse([c.weight.detach().double() for c in m.conv_list],
+                                         [c.bias.detach().double() for c in m.conv_list],
+                                         m.fc1.weight.detach().double(), m.fc1.bias.detach().double(),
+                                         int(kw["hidden_size"]))
+        out["table2"] = A.numpy().astype(np.float32)
+        out["table3"] = c0.numpy().astype(np.float32)
+        del out["kw_device"]
     # regularisers (pointwise models)
     if model in ("quate", "octonione"):
         with torch.no_grad():
@@ -331,8 +355,11 @@ def make_pretrained(n_ent=1024, n_rel=32, seed=3):
 
 if __name__ == "__main__":
     torch.set_num_threads(1)
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]   # optional: regenerate just these cases
     for i, (name, model, N, R, kw, init) in enumerate(CASES):
-        make_case(name, model, N, R, kw, init, seed=100 + i)
-    make_losses()
-    make_settle()
-    make_pretrained()
+        if not only or name in only:
+            make_case(name, model, N, R, kw, init, seed=100 + i)
+    if not only:
+        make_losses()
+        make_settle()
+        make_pretrained()

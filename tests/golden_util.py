@@ -26,6 +26,15 @@ def tables_of(g):
     return out
 
 
+def raw_tables_of(g):
+    """ConvKB only: the reference's own parameters [ent, rel, conv_w0, conv_b0, ..., fc_w, fc_b]."""
+    out, k = [], 0
+    while "raw%d" % k in g:
+        out.append(g["raw%d" % k])
+        k += 1
+    return out
+
+
 def model_kwargs(g):
     """-> dict(name, dim, rel_dim, l1_flag, margin, embedding_range)"""
     name = str(g["model"])

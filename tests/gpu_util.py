@@ -22,6 +22,7 @@ NUM_TABLE_SPECS = {
     "cp": ["e", "r", "e"], "complex": ["e", "e", "r", "r"], "transm": ["e", "r", "theta"],
     "analogy": ["e", "r", "e2", "e2", "r2", "r2"], "kg2e": ["e", "e+", "r", "r+"], "slm": ["e", "r", "dk", "dk"], "ntn": ["e", "r", "dk", "dk", "1k", "kdd"],
     "sme": ["e", "r", "dd", "dd", "d1", "dd", "dd", "d1"], "sme_bl": ["e", "r", "dd", "dd", "d1", "dd", "dd", "d1"], "quate": ["e"] * 4 + ["r"] * 4, "octonione": ["e"] * 8 + ["r"] * 8, "hole": ["e", "r"], "rescal": ["e", "MM"], "simple": ["e", "e", "r", "r"], "simple_ignr": ["e", "e", "r", "r"],
+    "convkb": ["e", "r", "3d", "1"],
 }
 
 
@@ -38,8 +39,8 @@ def synthetic_case(name, N, R, d, seed, dr=None, l1=False, margin=0.0, scale=0.5
             tabs.append((rng.standard_normal((R, dr)) * scale).astype(np.float32))
         elif kind == "M":
             tabs.append((rng.standard_normal((R, d * dr)) * scale).astype(np.float32))
-        elif kind in ("dk", "1k", "kdd", "dd", "d1"):  # global dense parameters
-            shape = {"dk": (d, dr), "1k": (1, dr), "kdd": (dr, d * d), "dd": (d, d), "d1": (d, 1)}[kind]
+        elif kind in ("dk", "1k", "kdd", "dd", "d1", "3d", "1"):  # global dense parameters
+            shape = {"dk": (d, dr), "1k": (1, dr), "kdd": (dr, d * d), "dd": (d, d), "d1": (d, 1), "3d": (3, d), "1": (1,)}[kind]
             tabs.append((rng.standard_normal(shape) * scale).astype(np.float32))
         elif kind in ("e+", "r+"):  # strictly positive (variances)
             rows = N if kind == "e+" else R

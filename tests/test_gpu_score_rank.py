@@ -86,6 +86,8 @@ SYN = [
     ("analogy", 500, 7, 36, None, False, 0.0),
     ("simple", 900, 7, 200, None, False, 0.0),
     ("simple_ignr", 700, 7, 50, None, False, 0.0),
+    ("convkb", 900, 7, 100, None, False, 0.0),
+    ("convkb", 500, 5, 50, None, False, 0.0),
 ]
 
 

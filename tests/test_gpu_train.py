@@ -40,7 +40,7 @@ def test_score_bwd_vs_reference_autograd(name):
     desc = gpu.desc_from_golden(g)
     grads = [torch.zeros_like(t) for t in desc.tables]
     L.score_bwd(desc, _cuda(g["h"]), _cuda(g["r"]), _cuda(g["t"]), _cuda(g["upstream"]), grads)
-    want = [g["grad%d" % k] for k in range(len(grads))]
+    want = [g.get("grad%d" % k) for k in range(len(grads))]   # (ConvKB: no reference gradient for the collapsed tables)
     _check_grads([x.cpu().numpy() for x in grads], want, what=name)
 
 
@@ -55,6 +55,7 @@ def test_score_bwd_vs_reference_autograd(name):
     ("simple_ignr", 300, 7, 50, None, False, 0.0), ("analogy", 300, 7, 48, None, False, 0.0),
     ("slm", 200, 5, 24, 16, False, 0.0), ("ntn", 120, 4, 16, 12, False, 0.0), ("sme", 150, 5, 24, None, False, 0.0),
     ("sme_bl", 150, 5, 20, None, False, 0.0), ("kg2e", 200, 5, 40, None, False, 0.0), ("quate", 200, 5, 24, None, False, 0.0), ("octonione", 150, 5, 12, None, False, 0.0),
+    ("convkb", 200, 5, 50, None, False, 0.0), ("convkb", 150, 5, 37, None, False, 0.0),
 ], ids=lambda s: "%s-d%d" % (s[0], s[3]))
 def test_score_bwd_vs_fp64_oracle(spec):
     """duplicates in the batch (few entities) exercise the atomic scatter."""
@@ -134,8 +135,17 @@ def _make_model(g, device="cuda"):
     import pykg2vec_b200
     kw = {k[3:]: (g[k].item() if g[k].ndim == 0 else g[k]) for k in g if k.startswith("kw_")}
     cls = pykg2vec_b200.import_model(str(g["model"]))
+    if str(g["model"]) == "convkb":
+        kw["device"] = device   # the reference's ConvKB takes the device of its (unregistered) conv_list
     m = cls(tot_entity=int(g["N"]), tot_relation=int(g["R"]), **kw)
     sd = {str(k) + ".weight": torch.from_numpy(g["table%d" % i]) for i, k in enumerate(g["table_keys"])}
+    if str(g["model"]) == "convkb":
+        raw = gu.raw_tables_of(g)
+        sd["fc1.weight"], sd["fc1.bias"] = torch.from_numpy(raw[-2]), torch.from_numpy(raw[-1])
+        with torch.no_grad():
+            for i, conv in enumerate(m.conv_list):   # plain Python list: not part of state_dict
+                conv.weight.copy_(torch.from_numpy(raw[2 + 2 * i]))
+                conv.bias.copy_(torch.from_numpy(raw[3 + 2 * i]))
     missing = m.load_state_dict(sd, strict=False)  # (QuatE/OctonionE register tables forward() never reads)
     assert not missing.unexpected_keys
     return m.to(device)
@@ -160,6 +170,11 @@ def test_model_classes_forward_backward_like_reference(name):
     (s * _cuda(g["upstream"])).sum().backward()
     got = [getattr(m, str(k)).weight.grad.cpu().numpy() for k in g["table_keys"]]
     _check_grads(got, [g["grad%d" % i] for i in range(len(got))], what=name)
+    if str(g["model"]) == "convkb":   # the Linear layer trains through the collapse
+        raw_n = len(gu.raw_tables_of(g))
+        _check_grads([m.fc1.weight.grad.cpu().numpy(), m.fc1.bias.grad.cpu().numpy()],
+                     [g["rawgrad%d" % (raw_n - 2)], g["rawgrad%d" % (raw_n - 1)]], what=name + " fc1")
+        assert "conv_list" not in "".join(m.state_dict().keys())
     embs = m.embed(h, r, t)
     assert all(e.shape[0] == h.numel() for e in embs)
 
@@ -346,3 +361,39 @@ def test_generator_feeds_trainer_epoch():
             next(gen)
     p = relation_property(kg.arrays["train"], 5)
     assert p.shape == (5,) and ((p > 0) & (p < 1)).all()
+
+
+def test_convkb_trains_like_the_written_chain():
+    """ConvKB (kernel on the collapsed affine form) follows the as-written conv -> concat -> Linear
+    chain through whole optimizer steps: same loss and same updated parameters as torch autograd
+    on oracle.ref_port's restatement, with the convolution filters left untouched (they are not
+    registered parameters in the reference either, pointwise.py:280)."""
+    import pykg2vec_b200
+    from oracle import ref_port
+    from pykg2vec_b200.criterion import Criterion
+    g = gu.load("convkb_d24")
+    m = _make_model(g)
+    raw = [torch.from_numpy(x.astype(np.float64)) for x in gu.raw_tables_of(g)]
+    train_idx = [0, 1, len(raw) - 2, len(raw) - 1]          # ent, rel, fc1.weight, fc1.bias
+    params = [raw[i].clone().requires_grad_() for i in train_idx]
+    opt_ref = torch.optim.SGD(params, lr=0.05)
+    opt = torch.optim.SGD(m.parameters(), lr=0.05)
+    assert len(list(m.parameters())) == 4
+    conv_before = [c.weight.detach().clone() for c in m.conv_list]
+    h, r, t = g["h"], g["r"], g["t"]
+    y = np.where(np.arange(len(h)) % 2 == 0, 1.0, -1.0).astype(np.float32)
+    for step in range(3):
+        tabs = list(raw)
+        for i, p in zip(train_idx, params):
+            tabs[i] = p
+        s_ref = ref_port.score("convkb_raw", tabs, torch.from_numpy(h), torch.from_numpy(r), torch.from_numpy(t))
+        loss_ref = ref_port.pointwise_logistic(s_ref, torch.from_numpy(y).double())
+        opt_ref.zero_grad(); loss_ref.backward(); opt_ref.step()
+        loss = Criterion.pointwise_logistic(m(_cuda(h), _cuda(r), _cuda(t)), _cuda(y)) + m.get_reg(None, None, None)
+        opt.zero_grad(); loss.backward(); opt.step()
+        assert abs(loss.item() - loss_ref.item()) <= 2e-5 * abs(loss_ref.item())
+    got = [m.ent_embeddings.weight, m.rel_embeddings.weight, m.fc1.weight, m.fc1.bias]
+    for a, b in zip(got, params):
+        np.testing.assert_allclose(a.detach().cpu().numpy(), b.detach().numpy(), rtol=2e-4, atol=2e-6)
+    for c, w0 in zip(m.conv_list, conv_before):
+        assert torch.equal(c.weight.detach(), w0)

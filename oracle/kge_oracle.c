@@ -260,16 +260,25 @@ static float score_one(const kge_model_t* m, int grouping, int64_t h, int64_t r,
       const float *hr = row(m, 0, h, d), *hi = row(m, 1, h, d), *rr = row(m, 2, r, d),
                   *tr = row(m, 0, t, d), *ti = row(m, 1, t, d);
       rsum_t s; rs_init(&s);
-      for (int j = 0; j < d; ++j) {
-        float im, re; kgeo_sincosf(rr[j] * m->phase_scale, &im, &re);
-        const float u = hi[j] * im;
-        const float sr0 = fmaf(hr[j], re, -u);
-        const float v = hi[j] * re;
-        const float si0 = fmaf(hr[j], im, v);
-        const float sr = sr0 - tr[j], si = si0 - ti[j];
-        float* p = rs_at(&s, j);
-        *p = fmaf(sr, sr, *p);
-        *p = fmaf(si, si, *p);
+      for (int c = 0; c < d; c += 4) { /* chunk-wise: 4 real-part terms, then 4 imaginary-part terms */
+        const int n = (d - c) < 4 ? (d - c) : 4;
+        float sr[4], si[4];
+        for (int e = 0; e < n; ++e) {
+          const int j = c + e;
+          float im, re; kgeo_sincosf(rr[j] * m->phase_scale, &im, &re);
+          if (grouping == KGE_GROUP_TAIL) {   /* |h o r - t|^2 as written */
+            const float qr = fmaf(hr[j], re, -(hi[j] * im));
+            const float qi = fmaf(hr[j], im, hi[j] * re);
+            sr[e] = qr - tr[j]; si[e] = qi - ti[j];
+          } else {                            /* |t o conj(r) - h|^2: the same value for the unit rotation */
+            const float qr = fmaf(tr[j], re, ti[j] * im);
+            const float qi = fmaf(ti[j], re, -(tr[j] * im));
+            sr[e] = qr - hr[j]; si[e] = qi - hi[j];
+          }
+        }
+        float* p = rs_at(&s, c);
+        for (int e = 0; e < n; ++e) *p = fmaf(sr[e], sr[e], *p);
+        for (int e = 0; e < n; ++e) *p = fmaf(si[e], si[e], *p);
       }
       return rs_finish(&s) - m->margin; /* -(margin - sum) */
     }
@@ -302,18 +311,26 @@ static float score_one(const kge_model_t* m, int grouping, int64_t h, int64_t r,
       const float *hr = row(m, 0, h, d), *hi = row(m, 1, h, d), *rr = row(m, 2, r, d),
                   *ri = row(m, 3, r, d), *tr = row(m, 0, t, d), *ti = row(m, 1, t, d);
       rsum_t s; rs_init(&s);
-      for (int j = 0; j < d; ++j) {
-        float* p = rs_at(&s, j);
+      for (int c = 0; c < d; c += 4) { /* chunk-wise: 4 real-part terms, then 4 imaginary-part terms */
+        const int n = (d - c) < 4 ? (d - c) : 4;
+        float qr[4], qi[4];
+        for (int e = 0; e < n; ++e) {
+          const int j = c + e;
+          if (grouping == KGE_GROUP_TAIL) {
+            qr[e] = fmaf(hr[j], rr[j], -(hi[j] * ri[j]));
+            qi[e] = fmaf(hi[j], rr[j], hr[j] * ri[j]);
+          } else {
+            qr[e] = fmaf(tr[j], rr[j], ti[j] * ri[j]);
+            qi[e] = fmaf(ti[j], rr[j], -(tr[j] * ri[j]));
+          }
+        }
+        float* p = rs_at(&s, c);
         if (grouping == KGE_GROUP_TAIL) {
-          const float qr = fmaf(hr[j], rr[j], -(hi[j] * ri[j]));
-          const float qi = fmaf(hi[j], rr[j], hr[j] * ri[j]);
-          *p = fmaf(qr, tr[j], *p);
-          *p = fmaf(qi, ti[j], *p);
+          for (int e = 0; e < n; ++e) *p = fmaf(qr[e], tr[c + e], *p);
+          for (int e = 0; e < n; ++e) *p = fmaf(qi[e], ti[c + e], *p);
         } else {
-          const float qr = fmaf(tr[j], rr[j], ti[j] * ri[j]);
-          const float qi = fmaf(ti[j], rr[j], -(tr[j] * ri[j]));
-          *p = fmaf(hr[j], qr, *p);
-          *p = fmaf(hi[j], qi, *p);
+          for (int e = 0; e < n; ++e) *p = fmaf(hr[c + e], qr[e], *p);
+          for (int e = 0; e < n; ++e) *p = fmaf(hi[c + e], qi[e], *p);
         }
       }
       return -rs_finish(&s);
@@ -529,18 +546,26 @@ static float score_one(const kge_model_t* m, int grouping, int64_t h, int64_t r,
       const float *h1 = row(m, 0, h, d), *t2 = row(m, 1, h, d), *h2 = row(m, 0, t, d), *t1 = row(m, 1, t, d);
       const float *r1 = row(m, 2, r, d), *r2 = row(m, 3, r, d);
       rsum_t s; rs_init(&s);
-      for (int j = 0; j < d; ++j) {
-        float* p = rs_at(&s, j);
-        if (grouping == KGE_GROUP_TAIL) {  /* query (h, r): q1 = h1 r1, q2 = half t2 r2 */
-          const float q1 = h1[j] * r1[j];
-          const float q2 = (t2[j] * r2[j]) * half;
-          *p = fmaf(q1, t1[j], *p);
-          *p = fmaf(q2, h2[j], *p);
-        } else {                           /* query (r, t): q1 = r1 t1, q2 = half r2 h2 */
-          const float q1 = r1[j] * t1[j];
-          const float q2 = (r2[j] * h2[j]) * half;
-          *p = fmaf(h1[j], q1, *p);
-          *p = fmaf(t2[j], q2, *p);
+      for (int c = 0; c < d; c += 4) { /* chunk-wise: 4 terms of the first product, then 4 of the second */
+        const int n = (d - c) < 4 ? (d - c) : 4;
+        float q1[4], q2[4];
+        for (int e = 0; e < n; ++e) {
+          const int j = c + e;
+          if (grouping == KGE_GROUP_TAIL) {  /* query (h, r): q1 = h1 r1, q2 = half t2 r2 */
+            q1[e] = h1[j] * r1[j];
+            q2[e] = (t2[j] * r2[j]) * half;
+          } else {                           /* query (r, t): q1 = r1 t1, q2 = half r2 h2 */
+            q1[e] = r1[j] * t1[j];
+            q2[e] = (r2[j] * h2[j]) * half;
+          }
+        }
+        float* p = rs_at(&s, c);
+        if (grouping == KGE_GROUP_TAIL) {
+          for (int e = 0; e < n; ++e) *p = fmaf(q1[e], t1[c + e], *p);
+          for (int e = 0; e < n; ++e) *p = fmaf(q2[e], h2[c + e], *p);
+        } else {
+          for (int e = 0; e < n; ++e) *p = fmaf(h1[c + e], q1[e], *p);
+          for (int e = 0; e < n; ++e) *p = fmaf(t2[c + e], q2[e], *p);
         }
       }
       const float init = rs_finish(&s);

@@ -77,6 +77,18 @@ KGE_DEV void resolve_rows(TripleRows& R, const ModelParams& P, const float* cons
   }
 }
 
+// RotatE query-side product (canonical): x o r = (xr re - xi im, xr im + xi re), or with the
+// conjugate rotation x o conj(r) = (xr re + xi im, xi re - xr im)
+KGE_DEV void rot_query(float xr, float xi, float re, float im, bool conj, float& qr, float& qi) {
+  if (!conj) {
+    qr = ffma(xr, re, -fmul(xi, im));
+    qi = ffma(xr, im, fmul(xi, re));
+  } else {
+    qr = ffma(xr, re, fmul(xi, im));
+    qi = ffma(xi, re, -fmul(xr, im));
+  }
+}
+
 // group-scoped barrier for shared-memory scratch shared by the 8 lanes of a group
 KGE_DEV void group_sync() { __syncwarp(group_mask()); }
 
@@ -464,25 +476,36 @@ KGE_DEV float score_group(const TripleRows& R, const ModelParams& P, int lane, f
         },
         [&](int c) { return *reinterpret_cast<const float4*>(tp + 4 * c); }, nchr, lane, P.l1);
   } else if (MODEL == KGE_ROTATE) {
-    // RotatE.embed/forward pairwise.py:765-791
+    // RotatE.embed/forward pairwise.py:765-791.  TAIL: |h o r - t|^2 as written; HEAD: the query
+    // side is t o conj(r) and the candidate h stays raw: |t o conj(r) - h|^2 (equal for the unit
+    // rotation e^{i theta}; rule 5: each grouping has its own canonical arithmetic)
     float acc = 0.f;
 #pragma unroll 2
     for (int c = lane; c < nch; c += 8) {
       const float4 hr = ld_chunk<VEC>(R.h[0], c, d), hi = ld_chunk<VEC>(R.h[1], c, d),
                    rr = ld_chunk<VEC>(R.r[0], c, d), tr = ld_chunk<VEC>(R.t[0], c, d),
                    ti = ld_chunk<VEC>(R.t[1], c, d);
+      float4 sr4, si4;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        float im, re;
+        float im, re, qr, qi;
         sincos_canon(fmul(f4_get(rr, e), P.phase), im, re);
-        const float u = fmul(f4_get(hi, e), im);
-        const float sr0 = ffma(f4_get(hr, e), re, -u);
-        const float v = fmul(f4_get(hi, e), re);
-        const float si0 = ffma(f4_get(hr, e), im, v);
-        const float sr = fsub(sr0, f4_get(tr, e)), si = fsub(si0, f4_get(ti, e));
-        acc = ffma(sr, sr, acc);
-        acc = ffma(si, si, acc);
+        if (GROUPING == KGE_GROUP_TAIL) {
+          rot_query(f4_get(hr, e), f4_get(hi, e), re, im, false, qr, qi);
+          f4_at(sr4, e) = fsub(qr, f4_get(tr, e));
+          f4_at(si4, e) = fsub(qi, f4_get(ti, e));
+        } else {
+          rot_query(f4_get(tr, e), f4_get(ti, e), re, im, true, qr, qi);
+          f4_at(sr4, e) = fsub(qr, f4_get(hr, e));
+          f4_at(si4, e) = fsub(qi, f4_get(hi, e));
+        }
       }
+      // two-term sums accumulate chunk-wise: the chunk's 4 first terms, then its 4 second terms
+      // (DESIGN.md §3 rule 6)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc = ffma(f4_get(sr4, e), f4_get(sr4, e), acc);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc = ffma(f4_get(si4, e), f4_get(si4, e), acc);
     }
     return fsub(group_sum(acc), P.margin);
   } else if (MODEL == KGE_DISTMULT || MODEL == KGE_CP) {
@@ -526,20 +549,24 @@ KGE_DEV float score_group(const TripleRows& R, const ModelParams& P, int lane, f
       const float4 hr = ld_chunk<VEC>(R.h[0], c, d), hi = ld_chunk<VEC>(R.h[1], c, d),
                    rr = ld_chunk<VEC>(R.r[0], c, d), ri = ld_chunk<VEC>(R.r[1], c, d),
                    tr = ld_chunk<VEC>(R.t[0], c, d), ti = ld_chunk<VEC>(R.t[1], c, d);
+      float4 qr4, qi4;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         if (GROUPING == KGE_GROUP_TAIL) {
-          const float qr = ffma(f4_get(hr, e), f4_get(rr, e), -fmul(f4_get(hi, e), f4_get(ri, e)));
-          const float qi = ffma(f4_get(hi, e), f4_get(rr, e), fmul(f4_get(hr, e), f4_get(ri, e)));
-          acc = ffma(qr, f4_get(tr, e), acc);
-          acc = ffma(qi, f4_get(ti, e), acc);
+          f4_at(qr4, e) = ffma(f4_get(hr, e), f4_get(rr, e), -fmul(f4_get(hi, e), f4_get(ri, e)));
+          f4_at(qi4, e) = ffma(f4_get(hi, e), f4_get(rr, e), fmul(f4_get(hr, e), f4_get(ri, e)));
         } else {
-          const float qr = ffma(f4_get(tr, e), f4_get(rr, e), fmul(f4_get(ti, e), f4_get(ri, e)));
-          const float qi = ffma(f4_get(ti, e), f4_get(rr, e), -fmul(f4_get(tr, e), f4_get(ri, e)));
-          acc = ffma(f4_get(hr, e), qr, acc);
-          acc = ffma(f4_get(hi, e), qi, acc);
+          f4_at(qr4, e) = ffma(f4_get(tr, e), f4_get(rr, e), fmul(f4_get(ti, e), f4_get(ri, e)));
+          f4_at(qi4, e) = ffma(f4_get(ti, e), f4_get(rr, e), -fmul(f4_get(tr, e), f4_get(ri, e)));
         }
       }
+      // chunk-wise: 4 real-part terms, then 4 imaginary-part terms (DESIGN.md §3 rule 6)
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        acc = (GROUPING == KGE_GROUP_TAIL) ? ffma(f4_get(qr4, e), f4_get(tr, e), acc) : ffma(f4_get(hr, e), f4_get(qr4, e), acc);
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        acc = (GROUPING == KGE_GROUP_TAIL) ? ffma(f4_get(qi4, e), f4_get(ti, e), acc) : ffma(f4_get(hi, e), f4_get(qi4, e), acc);
     }
     return -group_sum(acc);
   } else if (MODEL == KGE_SLM || MODEL == KGE_NTN) {
@@ -733,20 +760,24 @@ KGE_DEV float score_group(const TripleRows& R, const ModelParams& P, int lane, f
       const float4 h1 = ld_chunk<VEC>(R.h[0], c, d), t2 = ld_chunk<VEC>(R.h[1], c, d),
                    t1 = ld_chunk<VEC>(R.t[0], c, d), h2 = ld_chunk<VEC>(R.t[1], c, d),
                    r1 = ld_chunk<VEC>(R.r[0], c, d), r2 = ld_chunk<VEC>(R.r[1], c, d);
+      float4 qa, qb;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         if (GROUPING == KGE_GROUP_TAIL) {
-          const float q1 = fmul(f4_get(h1, e), f4_get(r1, e));
-          const float q2 = fmul(fmul(f4_get(t2, e), f4_get(r2, e)), half);
-          acc = ffma(q1, f4_get(t1, e), acc);
-          acc = ffma(q2, f4_get(h2, e), acc);
+          f4_at(qa, e) = fmul(f4_get(h1, e), f4_get(r1, e));
+          f4_at(qb, e) = fmul(fmul(f4_get(t2, e), f4_get(r2, e)), half);
         } else {
-          const float q1 = fmul(f4_get(r1, e), f4_get(t1, e));
-          const float q2 = fmul(fmul(f4_get(r2, e), f4_get(h2, e)), half);
-          acc = ffma(f4_get(h1, e), q1, acc);
-          acc = ffma(f4_get(t2, e), q2, acc);
+          f4_at(qa, e) = fmul(f4_get(r1, e), f4_get(t1, e));
+          f4_at(qb, e) = fmul(fmul(f4_get(r2, e), f4_get(h2, e)), half);
         }
       }
+      // chunk-wise: 4 terms of the first product, then 4 of the second (DESIGN.md §3 rule 6)
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        acc = (GROUPING == KGE_GROUP_TAIL) ? ffma(f4_get(qa, e), f4_get(t1, e), acc) : ffma(f4_get(h1, e), f4_get(qa, e), acc);
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        acc = (GROUPING == KGE_GROUP_TAIL) ? ffma(f4_get(qb, e), f4_get(h2, e), acc) : ffma(f4_get(t2, e), f4_get(qb, e), acc);
     }
     const float init = group_sum(acc);
     return -fminf(fmaxf(init, -20.0f), 20.0f);

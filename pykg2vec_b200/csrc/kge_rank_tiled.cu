@@ -37,12 +37,11 @@ constexpr int kNT = 4;                   // register tiles (candidate sub-blocks
 constexpr int kTC = 4;                   // candidates per register tile
 constexpr int kCBLK = kGC * kNT * kTC;   // 32 candidates per tile
 
-enum { OP_TRANS_T = 0, OP_TRANS_H = 1, OP_DOT1 = 2, OP_DOT2 = 3, OP_ROT_T = 4, OP_ROT_H = 5 };
+enum { OP_TRANS_T = 0, OP_TRANS_H = 1, OP_DOT1 = 2, OP_DOT2 = 3, OP_ROT = 4 };
 
 template <int OP> struct OpTraits { static constexpr int KQ = 1, KC = 1, TQ = 4; };
 template <> struct OpTraits<OP_DOT2> { static constexpr int KQ = 2, KC = 2, TQ = 4; };
-template <> struct OpTraits<OP_ROT_T> { static constexpr int KQ = 2, KC = 2, TQ = 4; };
-template <> struct OpTraits<OP_ROT_H> { static constexpr int KQ = 4, KC = 2, TQ = 2; };
+template <> struct OpTraits<OP_ROT> { static constexpr int KQ = 2, KC = 2, TQ = 4; };
 
 struct TiledParams {
   const float* qvec;      // [Q][KQ][dp]
@@ -87,34 +86,31 @@ KGE_DEV void tma_load_2d(void* dst_smem, const CUtensorMap* tm, int col, int row
 }
 
 // ---- per-element pair operations (canonical arithmetic) ---------------------------------------
+// Two-term models (DOT2, ROT) accumulate chunk-wise — the chunk's 4 first terms, then its 4
+// second terms (DESIGN.md §3 rule 6) — so the two operand halves are consumed one after the other
+// and never have to be live in registers together.
 template <int OP, bool L1>
 KGE_DEV void pair_op(float& acc, const float4* q, const float4* c) {
+  if (OP == OP_TRANS_T || OP == OP_TRANS_H) {
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    if (OP == OP_TRANS_T || OP == OP_TRANS_H) {
+    for (int e = 0; e < 4; ++e) {
       const float x = (OP == OP_TRANS_T) ? fsub(f4_get(q[0], e), f4_get(c[0], e))
                                          : fadd(f4_get(c[0], e), f4_get(q[0], e));
       if (L1) acc = fadd(acc, fabsf(x)); else acc = ffma(x, x, acc);
-    } else if (OP == OP_DOT1) {
-      acc = ffma(f4_get(q[0], e), f4_get(c[0], e), acc);
-    } else if (OP == OP_DOT2) {
-      acc = ffma(f4_get(q[0], e), f4_get(c[0], e), acc);
-      acc = ffma(f4_get(q[1], e), f4_get(c[1], e), acc);
-    } else if (OP == OP_ROT_T) {
-      const float sr = fsub(f4_get(q[0], e), f4_get(c[0], e));
-      const float si = fsub(f4_get(q[1], e), f4_get(c[1], e));
-      acc = ffma(sr, sr, acc);
-      acc = ffma(si, si, acc);
-    } else {  // OP_ROT_H: q = (re, im, t_re, t_im), c = (h_re, h_im)
-      const float re = f4_get(q[0], e), im = f4_get(q[1], e);
-      const float u = fmul(f4_get(c[1], e), im);
-      const float sr0 = ffma(f4_get(c[0], e), re, -u);
-      const float v = fmul(f4_get(c[1], e), re);
-      const float si0 = ffma(f4_get(c[0], e), im, v);
-      const float sr = fsub(sr0, f4_get(q[2], e)), si = fsub(si0, f4_get(q[3], e));
-      acc = ffma(sr, sr, acc);
-      acc = ffma(si, si, acc);
     }
+  } else if (OP == OP_DOT1) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc = ffma(f4_get(q[0], e), f4_get(c[0], e), acc);
+  } else if (OP == OP_DOT2) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc = ffma(f4_get(q[0], e), f4_get(c[0], e), acc);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc = ffma(f4_get(q[1], e), f4_get(c[1], e), acc);
+  } else {  // OP_ROT: |q - c|^2 over (re, im); q = h o r (tail sweep) or t o conj(r) (head sweep)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { const float sr = fsub(f4_get(q[0], e), f4_get(c[0], e)); acc = ffma(sr, sr, acc); }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { const float si = fsub(f4_get(q[1], e), f4_get(c[1], e)); acc = ffma(si, si, acc); }
   }
 }
 
@@ -181,8 +177,7 @@ KGE_DEV void reduce_scatter(float (&v)[NV], int lane) {
 struct TiledMaps { CUtensorMap q, c0, c1; };
 
 template <int OP, bool L1>
-__global__ void __launch_bounds__(kTThreads)
-sweep_tiled_kernel(const __grid_constant__ TiledParams P, const __grid_constant__ TiledMaps TM) {
+__device__ __forceinline__ void sweep_tiled_body(const TiledParams& P, const TiledMaps& TM) {
   constexpr int KQ = OpTraits<OP>::KQ, KC = OpTraits<OP>::KC, TQ = OpTraits<OP>::TQ;
   constexpr int QBLK = kGQ * TQ;
   constexpr int NV = TQ * kTC;
@@ -287,25 +282,56 @@ sweep_tiled_kernel(const __grid_constant__ TiledParams P, const __grid_constant_
     // lane's chunk c = 8*octet + lane of row r sits at  octet*OctBytes + r*128 + lane*16
     const unsigned char* qs = qbase + (size_t)(P.nslabs > 1 ? stage : 0) * q_stage_bytes + (gq * TQ * KQ) * 128 + lane * 16;
     const unsigned char* cs = cbase + (size_t)stage * c_stage_bytes + (gc * kTC) * 128 + lane * 16;
+#pragma unroll 1
     for (int c = lane; c < nch; c += 8, qs += kQOct, cs += kCOct) {
-      float4 q4[TQ][KQ];
+      if constexpr (OP == OP_DOT2 || OP == OP_ROT) {
+        // two-term ops: all first-term operands, then all second-term operands — every accumulator
+        // still sees its chunk's 4 first terms before its 4 second terms, and only one half of
+        // the operands is live at a time (fits 2 CTAs per SM)
 #pragma unroll
-      for (int i = 0; i < TQ; ++i)
+        for (int k = 0; k < 2; ++k) {
+          float4 qk[TQ];
 #pragma unroll
-        for (int k = 0; k < KQ; ++k)
-          q4[i][k] = *reinterpret_cast<const float4*>(qs + (i * KQ + k) * 128);
+          for (int i = 0; i < TQ; ++i) qk[i] = *reinterpret_cast<const float4*>(qs + (i * KQ + k) * 128);
 #pragma unroll
-      for (int nt = 0; nt < kNT; ++nt) {
-        float4 c4[kTC][KC];
+          for (int nt = 0; nt < kNT; ++nt) {
+            float4 ck[kTC];
 #pragma unroll
-        for (int j = 0; j < kTC; ++j)
+            for (int j = 0; j < kTC; ++j)
+              ck[j] = *reinterpret_cast<const float4*>(cs + (k * kCBLK + kGC * kTC * nt + j) * 128);
 #pragma unroll
-          for (int k = 0; k < KC; ++k)
-            c4[j][k] = *reinterpret_cast<const float4*>(cs + (k * kCBLK + kGC * kTC * nt + j) * 128);
+            for (int i = 0; i < TQ; ++i)
+#pragma unroll
+              for (int j = 0; j < kTC; ++j) {
+                float& a = acc[nt][i * kTC + j];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  if (OP == OP_DOT2) a = ffma(f4_get(qk[i], e), f4_get(ck[j], e), a);
+                  else { const float x = fsub(f4_get(qk[i], e), f4_get(ck[j], e)); a = ffma(x, x, a); }
+                }
+              }
+          }
+        }
+      } else {
+        float4 q4[TQ][KQ];
 #pragma unroll
         for (int i = 0; i < TQ; ++i)
 #pragma unroll
-          for (int j = 0; j < kTC; ++j) pair_op<OP, L1>(acc[nt][i * kTC + j], q4[i], c4[j]);
+          for (int k = 0; k < KQ; ++k)
+            q4[i][k] = *reinterpret_cast<const float4*>(qs + (i * KQ + k) * 128);
+#pragma unroll
+        for (int nt = 0; nt < kNT; ++nt) {
+          float4 c4[kTC][KC];
+#pragma unroll
+          for (int j = 0; j < kTC; ++j)
+#pragma unroll
+            for (int k = 0; k < KC; ++k)
+              c4[j][k] = *reinterpret_cast<const float4*>(cs + (k * kCBLK + kGC * kTC * nt + j) * 128);
+#pragma unroll
+          for (int i = 0; i < TQ; ++i)
+#pragma unroll
+            for (int j = 0; j < kTC; ++j) pair_op<OP, L1>(acc[nt][i * kTC + j], q4[i], c4[j]);
+        }
       }
     }
     // Stage recycling without a CTA barrier: every warp bumps the stage's release counter when it
@@ -348,6 +374,20 @@ sweep_tiled_kernel(const __grid_constant__ TiledParams P, const __grid_constant_
   }
 }
 
+// Two entry points over the same body: ptxas keeps the one-term ops within 128 registers on its
+// own (and spills if it is told to), while the two-term dot kernel needs the explicit
+// 2-CTAs-per-SM bound to stop it from hoisting the next operand loads into extra registers.
+template <int OP, bool L1>
+__global__ void __launch_bounds__(kTThreads)
+sweep_tiled_kernel(const __grid_constant__ TiledParams P, const __grid_constant__ TiledMaps TM) {
+  sweep_tiled_body<OP, L1>(P, TM);
+}
+template <int OP, bool L1>
+__global__ void __launch_bounds__(kTThreads, 2)
+sweep_tiled_kernel_2cta(const __grid_constant__ TiledParams P, const __grid_constant__ TiledMaps TM) {
+  sweep_tiled_body<OP, L1>(P, TM);
+}
+
 // ---- preparation kernels -------------------------------------------------------------------------
 // query vectors [Q][KQ][dp] (zero padded) + qscale; one 8-lane group per query
 template <int MODEL, int VEC, int DIR>
@@ -368,7 +408,7 @@ prep_query_kernel(ModelParams P, const int64_t* __restrict__ qh, const int64_t* 
     if (lane == 0) thr[q] = s;
   }
   constexpr int KQ = (MODEL == KGE_COMPLEX || MODEL == KGE_SIMPLE || MODEL == KGE_SIMPLE_IGNR)
-                         ? 2 : (MODEL == KGE_ROTATE ? (DIR == 0 ? 2 : 4) : 1);
+                         ? 2 : (MODEL == KGE_ROTATE ? 2 : 1);
   float* out = qvec + (size_t)q * KQ * dp;
   auto st = [&](int k, int c, float4 v) { *reinterpret_cast<float4*>(out + (size_t)k * dp + 4 * c) = v; };
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -451,28 +491,22 @@ prep_query_kernel(ModelParams P, const int64_t* __restrict__ qh, const int64_t* 
       st(0, c, o0); st(1, c, o1);
     }
   } else if (MODEL == KGE_ROTATE) {
+    // TAIL: q = h o r ; HEAD: q = t o conj(r)  (|h o r - t| = |h - t o conj(r)| for the unit rotation;
+    // each grouping is its own canonical arithmetic, DESIGN.md §3 rule 5)
+    const float* er = (DIR == 0) ? R.h[0] : R.t[0];
+    const float* ei = (DIR == 0) ? R.h[1] : R.t[1];
     for (int c = lane; c < nchp; c += 8) {
-      float4 o0 = zero, o1 = zero, o2 = zero, o3 = zero;
+      float4 o0 = zero, o1 = zero;
       if (c < nch) {
-        const float4 rr = ld_chunk<VEC>(R.r[0], c, d);
-        float4 re, im;
+        const float4 rr = ld_chunk<VEC>(R.r[0], c, d), xr = ld_chunk<VEC>(er, c, d), xi = ld_chunk<VEC>(ei, c, d);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) sincos_canon(fmul(f4_get(rr, e), P.phase), f4_at(im, e), f4_at(re, e));
-        if (DIR == 0) {
-          const float4 hr = ld_chunk<VEC>(R.h[0], c, d), hi = ld_chunk<VEC>(R.h[1], c, d);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float u = fmul(f4_get(hi, e), f4_get(im, e));
-            f4_at(o0, e) = ffma(f4_get(hr, e), f4_get(re, e), -u);
-            const float v = fmul(f4_get(hi, e), f4_get(re, e));
-            f4_at(o1, e) = ffma(f4_get(hr, e), f4_get(im, e), v);
-          }
-        } else {
-          o0 = re; o1 = im; o2 = ld_chunk<VEC>(R.t[0], c, d); o3 = ld_chunk<VEC>(R.t[1], c, d);
+        for (int e = 0; e < 4; ++e) {
+          float im, re;
+          sincos_canon(fmul(f4_get(rr, e), P.phase), im, re);
+          rot_query(f4_get(xr, e), f4_get(xi, e), re, im, DIR == 1, f4_at(o0, e), f4_at(o1, e));
         }
       }
       st(0, c, o0); st(1, c, o1);
-      if (DIR == 1) { st(2, c, o2); st(3, c, o3); }
     }
   }
 }
@@ -524,7 +558,7 @@ int model_vec(const kge_model_t* m);
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static int dp_of(const kge_model_t* m) { return ((m->dim + 3) / 4) * 4; }
 static bool is_simple(int model) { return model == KGE_SIMPLE || model == KGE_SIMPLE_IGNR; }
-static int max_kq(int model) { return model == KGE_ROTATE ? 4 : ((model == KGE_COMPLEX || is_simple(model)) ? 2 : 1); }
+static int max_kq(int model) { return (model == KGE_ROTATE || model == KGE_COMPLEX || is_simple(model)) ? 2 : 1; }
 static int num_cand_tables(int model) { return (model == KGE_ROTATE || model == KGE_COMPLEX || is_simple(model)) ? 2 : 1; }
 // candidate source tables of a sweep direction; returns true when a scratch copy is needed
 // (normalised rows for TransE/TransM, padding for d % 4 != 0, unaligned tables)
@@ -650,8 +684,13 @@ static int launch_sweep(const TiledParams& P, int QBLK, size_t smem, cudaStream_
   } else {
     TM.c1 = TM.c0;
   }
-  KGE_CUDA_OK(cudaFuncSetAttribute(sweep_tiled_kernel<OP, L1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  sweep_tiled_kernel<OP, L1><<<dim3((unsigned)splits, (unsigned)qblocks), kTThreads, smem, st>>>(P, TM);
+  if constexpr (OP == OP_DOT2) {
+    KGE_CUDA_OK(cudaFuncSetAttribute(sweep_tiled_kernel_2cta<OP, L1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sweep_tiled_kernel_2cta<OP, L1><<<dim3((unsigned)splits, (unsigned)qblocks), kTThreads, smem, st>>>(P, TM);
+  } else {
+    KGE_CUDA_OK(cudaFuncSetAttribute(sweep_tiled_kernel<OP, L1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sweep_tiled_kernel<OP, L1><<<dim3((unsigned)splits, (unsigned)qblocks), kTThreads, smem, st>>>(P, TM);
+  }
   KGE_CHECK_LAUNCH("sweep_tiled_kernel");
   (void)QBLK;
   return KGE_OK;
@@ -664,10 +703,10 @@ int tiled_sweep(const kge_model_t* m, const kge_model_t* mq, int dir, const int6
   const int d = m->dim, dp = dp_of(m);
   const int op = (model == KGE_TRANSE || model == KGE_TRANSM) ? (dir == 0 ? OP_TRANS_T : OP_TRANS_H)
                : (model == KGE_DISTMULT || model == KGE_CP || model == KGE_HOLE || model == KGE_RESCAL) ? OP_DOT1
-               : (model == KGE_COMPLEX || is_simple(model)) ? OP_DOT2 : (dir == 0 ? OP_ROT_T : OP_ROT_H);
-  const int KQ = (op == OP_DOT2 || op == OP_ROT_T) ? 2 : (op == OP_ROT_H ? 4 : 1);
+               : (model == KGE_COMPLEX || is_simple(model)) ? OP_DOT2 : OP_ROT;
+  const int KQ = (op == OP_DOT2 || op == OP_ROT) ? 2 : 1;
   const int KC = num_cand_tables(model);
-  const int TQ = (op == OP_ROT_H) ? 2 : 4;
+  const int TQ = 4;
   const int QBLK = kGQ * TQ;
   // workspace carve-up: [qvec dir0][qvec dir1][qscale dir0][qscale dir1][candidate scratch]
   // (the two directions may run concurrently on two streams, so they never share query buffers)
@@ -764,8 +803,7 @@ int tiled_sweep(const kge_model_t* m, const kge_model_t* mq, int dir, const int6
                                        : launch_sweep<OP_TRANS_H, false>(P, QBLK, smem, st, splits, qblocks);
     case OP_DOT1: return launch_sweep<OP_DOT1, false>(P, QBLK, smem, st, splits, qblocks);
     case OP_DOT2: return launch_sweep<OP_DOT2, false>(P, QBLK, smem, st, splits, qblocks);
-    case OP_ROT_T: return launch_sweep<OP_ROT_T, false>(P, QBLK, smem, st, splits, qblocks);
-    default: return launch_sweep<OP_ROT_H, false>(P, QBLK, smem, st, splits, qblocks);
+    default: return launch_sweep<OP_ROT, false>(P, QBLK, smem, st, splits, qblocks);
   }
 }
 

@@ -196,9 +196,9 @@ def run_cuda(args):
                                           w["lr"], loss_buf)
             loss = float(loss_buf.item())
             return loss, ranks
-        loss = tr.train_batch(ids)
-        ranks = ev.rank_triples(q[:, 0], q[:, 1], q[:, 2], ft, fh)
-        return loss, ranks
+        pending_loss = tr.train_batch(ids, sync=False)   # H2D + kernels + D2H enqueued as one graph
+        ranks = ev.rank_triples(q[:, 0], q[:, 1], q[:, 2], ft, fh)   # host staging overlaps it; syncs
+        return float(pending_loss), ranks                # pinned loss of this step, read on the host
 
     def barrier():
         if world > 1:

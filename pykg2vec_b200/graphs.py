@@ -23,6 +23,7 @@ class StagedGraph:
         self.h_out = torch.empty_like(out_like).pin_memory()
         self.body = body
         self.graph = None
+        self._done = None   # event of the last asynchronous replay
 
     def _run_eager(self, body=None):
         self.d_in.copy_(self.h_in, non_blocking=True)
@@ -43,8 +44,32 @@ class StagedGraph:
         self.graph = g
         return self
 
-    def __call__(self):
-        """h_in must already hold the inputs.  Returns the pinned result (valid until next call)."""
+    def wait_idle(self):
+        """Block until the last asynchronous replay has finished (h_in may be rewritten, h_out read)."""
+        if self._done is not None:
+            self._done.synchronize()
+            self._done = None
+
+    def __call__(self, sync=True):
+        """h_in must already hold the inputs.  Returns the pinned result (valid until next call).
+        sync=False only enqueues the replay: the result is valid after wait_idle() (or any later
+        synchronisation of the stream), so the next call's host work overlaps this one's kernels."""
         self.graph.replay()
-        torch.cuda.current_stream(self.device).synchronize()
+        if sync:
+            torch.cuda.current_stream(self.device).synchronize()
+            self._done = None
+        else:
+            self._done = torch.cuda.Event()
+            self._done.record(torch.cuda.current_stream(self.device))
         return self.h_out
+
+
+class PendingScalar:
+    """A host scalar produced by an asynchronous StagedGraph replay; float() waits for it."""
+
+    def __init__(self, staged):
+        self._staged = staged
+
+    def __float__(self):
+        self._staged.wait_idle()
+        return float(self._staged.h_out[0])

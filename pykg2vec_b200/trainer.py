@@ -134,7 +134,7 @@ class Trainer:
         dev = self._pinned[:k, :n].to(self.config.device, non_blocking=True)
         return [dev[i, :lens[i]] for i in range(k)], k * n * 8
 
-    def _graphed_hinge_step(self, data):
+    def _graphed_hinge_step(self, data, sync=True):
         """Pairwise hinge + SGD as ONE CUDA graph: H2D of the packed [6,B] ids from a pinned
         buffer, the two training kernels, D2H of the loss."""
         from .graphs import StagedGraph
@@ -159,10 +159,15 @@ class Trainer:
             call = StagedGraph(self.config.device, 6 * B, torch.empty(1, dtype=torch.float32), make_body(lr),
                                warm_body=make_body(0.0)).capture()
             self._graphs[key] = call
+        call.wait_idle()  # an earlier asynchronous step may still be reading the staging buffer
         buf = call.h_in.numpy().reshape(6, B)
         for i, a in enumerate(data):
             buf[i] = a
         self.last_h2d_bytes = 6 * B * 8
+        if not sync:
+            from .graphs import PendingScalar
+            call(sync=False)
+            return PendingScalar(call)
         return float(call()[0])
 
     def train_batch_device(self, ids):
@@ -201,15 +206,18 @@ class Trainer:
             acc += self.train_batch_device(next(generator)).reshape(())
         return float(acc.item())
 
-    def train_batch(self, data):
-        """data: the list Generator yields — 6 id arrays (pairwise) or 4 (pointwise)."""
+    def train_batch(self, data, sync=True):
+        """data: the list Generator yields — 6 id arrays (pairwise) or 4 (pointwise).  Returns the
+        batch loss as a float (the reference reads `loss.item()` per batch, trainer.py:300).
+        sync=False (graph-staged steps only) returns a handle instead — float(handle) waits for the
+        D2H copy — so the caller's next host work overlaps this step's kernels."""
         self.model.train()
         data = list(data)
         if (self._fused and getattr(self.config, "cuda_graph", True)
                 and self.model.training_strategy == TrainingStrategy.PAIRWISE_BASED
                 and self.model.model_name.lower() != "rotate" and self.config.optimizer == "sgd"
                 and len(data) == 6 and all(len(a) == len(data[0]) for a in data)):
-            return self._graphed_hinge_step(data)
+            return self._graphed_hinge_step(data, sync=sync)
         ids, nbytes = self._to_device(list(data))
         self.last_h2d_bytes = nbytes
         strategy = self.model.training_strategy

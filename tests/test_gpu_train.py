@@ -397,3 +397,27 @@ def test_convkb_trains_like_the_written_chain():
         np.testing.assert_allclose(a.detach().cpu().numpy(), b.detach().numpy(), rtol=2e-4, atol=2e-6)
     for c, w0 in zip(m.conv_list, conv_before):
         assert torch.equal(c.weight.detach(), w0)
+
+
+def test_train_batch_async_handle_equals_sync():
+    """train_batch(sync=False) enqueues the same graph-staged step and hands back the loss lazily:
+    identical losses and weights to the synchronous calls."""
+    from pykg2vec_b200.synthetic import SyntheticKnowledgeGraph
+    kg = SyntheticKnowledgeGraph(400, 6, 2000, 50, 50, seed=1)
+    kw = dict(optimizer="sgd", learning_rate=0.05, hidden_size=64, margin=1.0, l1_flag=False, neg_rate=1)
+    a = _trainer_for("transe", kg, fused_step=True, **kw)
+    b = _trainer_for("transe", kg, fused_step=True, **kw)
+    b.model.load_state_dict(a.model.state_dict())
+    rng = np.random.RandomState(4)
+    B = 128
+    batches = [[rng.randint(400, size=B), rng.randint(6, size=B), rng.randint(400, size=B),
+                rng.randint(400, size=B), rng.randint(6, size=B), rng.randint(400, size=B)] for _ in range(4)]
+    want = [a.train_batch(d) for d in batches]
+    got = []
+    for d in batches:
+        h = b.train_batch(d, sync=False)      # enqueued only
+        _ = sum(int(x.sum()) for x in d)      # host work overlapping the step
+        got.append(float(h))                  # waits for this step's D2H (the handle is valid until the next call)
+    assert got == want
+    for (ka, va), (kb, vb) in zip(a.model.state_dict().items(), b.model.state_dict().items()):
+        assert torch.equal(va, vb), ka

@@ -418,6 +418,7 @@ def test_train_batch_async_handle_equals_sync():
         h = b.train_batch(d, sync=False)      # enqueued only
         _ = sum(int(x.sum()) for x in d)      # host work overlapping the step
         got.append(float(h))                  # waits for this step's D2H (the handle is valid until the next call)
-    assert got == want
+    # (the loss and the row gradients are accumulated with float atomics: equal up to summation order)
+    np.testing.assert_allclose(got, want, rtol=1e-5)
     for (ka, va), (kb, vb) in zip(a.model.state_dict().items(), b.model.state_dict().items()):
-        assert torch.equal(va, vb), ka
+        np.testing.assert_allclose(va.cpu().numpy(), vb.cpu().numpy(), rtol=0, atol=2e-6, err_msg=ka)

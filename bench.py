@@ -262,6 +262,8 @@ def run_cuda(args):
                 b.record()
                 torch.cuda.synchronize()
                 tot += a.elapsed_time(b)
+                if os.environ.get("KGE_BENCH_DEBUG"):
+                    sys.stderr.write("rank %d step %d: %.3f ms\n" % (rank, i, a.elapsed_time(b)))
             else:
                 t0 = time.perf_counter()
                 fn(i)
@@ -296,6 +298,11 @@ def run_cuda(args):
         sustained_steps += args.steps
     ms_sustained = (time.perf_counter() - t_s0) * 1e3 / max(sustained_steps, 1)
     barrier()
+    # no cyclic-GC pauses inside the timed legs: at N > 1 a pause on ONE rank stalls every rank's
+    # id all-gather (seen as a single 3 ms step among 0.43 ms ones, profiles/r1_bench_n4_v3.err)
+    import gc
+    gc.collect()
+    gc.disable()
     launches0 = _lib.launch_count()
     ms_res = max_over_ranks(timed(resident_step, args.warmup, args.steps, True))
     launches = _lib.launch_count() - launches0
@@ -313,6 +320,7 @@ def run_cuda(args):
     torch.cuda.synchronize()
     ms_warm = max_over_ranks(a.elapsed_time(b))
     ms_e2e = max_over_ranks(timed(e2e_step, args.warmup, args.steps, False)) if not args.lite else float("nan")
+    gc.enable()
     # dominant kernel: the 1-vs-all sweep.  Timed alone (raw counts, one direction per launch pair)
     # with CUDA events on the launching stream.
     ids, qh, qr, qt, ft, fh = devin[args.warmup]

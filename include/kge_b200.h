@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define KGE_ABI_VERSION 2
+#define KGE_ABI_VERSION 3
 #define KGE_MAX_TABLES 16
 
 /* status codes */
@@ -205,6 +205,49 @@ int kge_rank_1vsall(const kge_model_t* m, const kge_model_t* mq, int64_t row_lo,
 #define KGE_RANK_TAIL_ONLY 2
 #define KGE_RANK_HEAD_ONLY 4
 #define KGE_RANK_SINGLE_STREAM 8 /* do not overlap the two directions on an internal side stream */
+
+/* ---- projection-model tail: x.E^T + b -> sigmoid, multi-class BCE, rank counts ----------
+ * The last layer shared by the reference's projection models:
+ *   ConvE.inner_forward    pykg2vec/models/projection.py:100-102   (torch.matmul(x, E.T); + b; sigmoid)
+ *   TuckER :335-336, InteractE :444-447, HypER :607-609, AcrE :735-738; ProjE_pointwise.g :248-256 (no bias)
+ * x [B,k] is the trunk's output (device, fp32 row-major), ent the [N,k] entity table, bias [N] or NULL.
+ * preds[b*N + n] = sigmoid(sum_j x[b,j] ent[n,j] + bias[n]); canonical arithmetic: one sequential
+ * fma chain over j from 0, one add, canonical sigmoid (DESIGN.md §3 rule 8) — bit-identical to
+ * oracle/kge_oracle.c and to what kge_proj_rank compares. */
+int kge_proj_tail_fwd(const float* x, const float* ent, const float* bias, int64_t B, int64_t N,
+                      int32_t k, float* preds, void* stream);
+
+/* Backward of kge_proj_tail_fwd (autograd through matmul/add/sigmoid, trainer.py:298).  With
+ * g = grad_preds * preds * (1 - preds):  grad_x[B,k] += g E;  grad_ent[N,k] += g^T x;
+ * grad_bias[N] += column sums of g.  All three are ACCUMULATED (caller zeroes; grad_ent is the dense
+ * nn.Embedding gradient the gather of the input rows also adds into) and may be NULL. */
+int kge_proj_tail_bwd(const float* grad_preds, const float* preds, const float* x, const float* ent,
+                      int64_t B, int64_t N, int32_t k, float* grad_x, float* grad_ent,
+                      float* grad_bias, void* stream);
+
+/* One direction of Criterion.multi_class_bce (pykg2vec/utils/criterion.py:41-50):
+ *   y = labels * label_scale + label_shift       (:43-45: scale = 1 - label_smoothing, shift = 1/tot_entity;
+ *                                                 pass 1, 0 when label_smoothing is None)
+ *   loss_out[0] = mean_{b,n} BCEWithLogits(preds, y)   (:46-47, applied to the already-sigmoided preds
+ *                                                 exactly as the reference does)
+ * and, when grad_preds is non-NULL, grad_preds = grad_scale * d loss / d preds.  labels is the dense
+ * [B,N] fp32 matrix the reference's generator yields (generator.py:160-230). */
+int kge_proj_bce(const float* preds, const float* labels, int64_t B, int64_t N, float label_scale,
+                 float label_shift, float grad_scale, float* loss_out, float* grad_preds, void* stream);
+
+/* predict_tail_rank / predict_head_rank (projection.py:119-125: topk of -preds over all N entities,
+ * one query at a time) + MetricCalculator.get_*_rank (evaluator.py:70-123), for Q queries at once and
+ * without materialising the [Q,N] prediction matrix:
+ *   counts[q*4 + 2*direction]     += #{n : pred(q,n) > pred(q,tgt[q])}
+ *   counts[q*4 + 2*direction + 1] += the same minus #{n in filter row q, n != tgt[q] : ...}
+ * direction 0 = tail (x from (h, r), tgt = t, filter hr_t), 1 = head (x from (t, r + R), tgt = h, tr_h).
+ * Filters: CSR over queries, ptr[Q+1] / idx[nnz] int64 (NULL / nnz 0 -> filtered == raw).
+ * workspace >= kge_proj_rank_workspace_bytes(Q) bytes of device memory. */
+int64_t kge_proj_rank_workspace_bytes(int64_t Q);
+int kge_proj_rank(const float* x, const float* ent, const float* bias, int64_t Q, int64_t N, int32_t k,
+                  const int64_t* tgt, const int64_t* filt_ptr, const int64_t* filt_idx, int64_t filt_nnz,
+                  int32_t direction, int32_t* counts, void* workspace, int64_t workspace_bytes,
+                  void* stream);
 
 /* ---- negative sampling on the device: replaces the CPU sampler processes ----
  * process_function_pairwise / process_function_pointwise (pykg2vec/data/generator.py:42-158).

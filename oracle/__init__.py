@@ -214,3 +214,59 @@ def sincosf(x):
     s, c = ctypes.c_float(), ctypes.c_float()
     lib().kgeo_sincosf(ctypes.c_float(x), ctypes.byref(s), ctypes.byref(c))
     return s.value, c.value
+
+
+# ---- projection-model tail (x.E^T + b -> sigmoid, BCE, rank counts) -------------------------
+def proj_tail_fwd(x, ent, bias=None):
+    x, ent = _f32(x), _f32(ent)
+    bias = _f32(bias).reshape(-1) if bias is not None else None
+    B, k = x.shape
+    N = ent.shape[0]
+    out = np.empty((B, N), dtype=np.float32)
+    rc = lib().kgeo_proj_tail_fwd(_ptr(x), _ptr(ent), _ptr(bias), ctypes.c_int64(B), ctypes.c_int64(N),
+                                  ctypes.c_int32(k), _ptr(out))
+    assert rc == 0
+    return out
+
+
+def proj_bce(preds, labels, label_scale=1.0, label_shift=0.0, grad_scale=1.0):
+    """-> (loss, grad_preds) of one direction of Criterion.multi_class_bce."""
+    preds, labels = _f32(preds), _f32(labels)
+    B, N = preds.shape
+    loss = np.zeros(1, dtype=np.float32)
+    g = np.empty((B, N), dtype=np.float32)
+    rc = lib().kgeo_proj_bce(_ptr(preds), _ptr(labels), ctypes.c_int64(B), ctypes.c_int64(N),
+                             ctypes.c_float(label_scale), ctypes.c_float(label_shift),
+                             ctypes.c_float(grad_scale), _ptr(loss), _ptr(g))
+    assert rc == 0
+    return float(loss[0]), g
+
+
+def proj_tail_bwd(grad_preds, preds, x, ent):
+    """-> (grad_x [B,k], grad_ent [N,k], grad_bias [N]) accumulated in double."""
+    grad_preds, preds, x, ent = _f32(grad_preds), _f32(preds), _f32(x), _f32(ent)
+    B, k = x.shape
+    N = ent.shape[0]
+    gx = np.zeros((B, k), dtype=np.float32)
+    ge = np.zeros((N, k), dtype=np.float32)
+    gb = np.zeros(N, dtype=np.float32)
+    rc = lib().kgeo_proj_tail_bwd(_ptr(grad_preds), _ptr(preds), _ptr(x), _ptr(ent), ctypes.c_int64(B),
+                                  ctypes.c_int64(N), ctypes.c_int32(k), _ptr(gx), _ptr(ge), _ptr(gb))
+    assert rc == 0
+    return gx, ge, gb
+
+
+def proj_rank(x, ent, bias, tgt, filt=None, direction=0, counts=None):
+    """counts [Q,4] (+= into columns 2*direction, 2*direction+1); filt = (ptr, idx) or None."""
+    x, ent = _f32(x), _f32(ent)
+    bias = _f32(bias).reshape(-1) if bias is not None else None
+    tgt = _i64(tgt)
+    Q, k = x.shape
+    if counts is None:
+        counts = np.zeros((Q, 4), dtype=np.int32)
+    fp, fi = (None, None) if filt is None else (_i64(filt[0]), _i64(filt[1]))
+    rc = lib().kgeo_proj_rank(_ptr(x), _ptr(ent), _ptr(bias), ctypes.c_int64(Q), ctypes.c_int64(ent.shape[0]),
+                              ctypes.c_int32(k), _ptr(tgt), _ptr(fp), _ptr(fi), ctypes.c_int32(direction),
+                              _ptr(counts))
+    assert rc == 0
+    return counts

@@ -780,4 +780,106 @@ int kgeo_sample_negatives(const int64_t* th, const int64_t* tr, const int64_t* t
   return 0;
 }
 
-int kgeo_abi_version(void) { return 2; }
+/* ------------------------------------------------ projection-model tail ---- */
+/* The last layer every projection model of the reference shares:
+ *     preds = sigmoid(x . E^T + b)          ConvE.inner_forward projection.py:100-102
+ * (same shape in TuckER :335-336, InteractE :444-447, HypER :607-609, AcrE :735-738 and, without
+ * bias, ProjE_pointwise.g :248-256).  x is [B,k] (the trunk's output), E the [N,k] entity table,
+ * b a [N] bias row (NULL = none).
+ * Canonical arithmetic of this path (rule 8): the dot product is ONE sequential
+ * fmaf chain over j = 0..k-1 starting from 0.0f (the order in which a register-tiled GEMM
+ * accumulates an output element), then one add of the bias, then the canonical sigmoid. */
+static float proj_pred(const float* x, const float* e, int k, const float* bias, int64_t n) {
+  float acc = 0.0f;
+  for (int j = 0; j < k; ++j) acc = fmaf(x[j], e[j], acc);
+  if (bias) acc = acc + bias[n];
+  return kgeo_sigmoidf(acc);
+}
+
+int kgeo_proj_tail_fwd(const float* x, const float* ent, const float* bias, int64_t B, int64_t N,
+                       int32_t k, float* preds) {
+#pragma omp parallel for schedule(static)
+  for (int64_t b = 0; b < B; ++b)
+    for (int64_t n = 0; n < N; ++n)
+      preds[b * N + n] = proj_pred(x + b * k, ent + n * k, k, bias, n);
+  return 0;
+}
+
+/* One direction of Criterion.multi_class_bce (criterion.py:41-50):
+ *     y    = labels * label_scale + label_shift        (:43-45; scale = 1 - smoothing, shift = 1/N)
+ *     loss = mean_{b,n} BCEWithLogits(preds, y)         (:46-47 — applied to the ALREADY sigmoided
+ *                                                       preds, as the reference does)
+ * BCEWithLogits(z, y) = (1 - y) z + softplus(-z).  grad_preds = grad_scale * d loss / d preds
+ *                     = grad_scale * (sigmoid(z) - y) / (B N).
+ * The per-element terms use the canonical exp / log / sigmoid; the sum is taken in double here
+ * (the CUDA kernel sums fp32 partials: compared with a tolerance, not bit for bit). */
+int kgeo_proj_bce(const float* preds, const float* labels, int64_t B, int64_t N, float label_scale,
+                  float label_shift, float grad_scale, float* loss_out, float* grad_preds) {
+  const int64_t n = B * N;
+  const float gs = (float)((double)grad_scale / ((double)B * (double)N));
+  double acc = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : acc)
+  for (int64_t i = 0; i < n; ++i) {
+    const float z = preds[i];
+    const float y = labels[i] * label_scale + label_shift;
+    const float sp = fmaxf(-z, 0.0f) + kgeo_logf(1.0f + kgeo_expf(-fabsf(z)));
+    acc += (double)fmaf(1.0f - y, z, sp);
+    if (grad_preds) grad_preds[i] = (kgeo_sigmoidf(z) - y) * gs;
+  }
+  loss_out[0] = (float)(acc / (double)n);
+  return 0;
+}
+
+/* Backward of the tail: with g = grad_preds * preds * (1 - preds)  (d sigmoid),
+ *     grad_x[b,:] += sum_n g[b,n] E[n,:];  grad_ent[n,:] += sum_b g[b,n] x[b,:];  grad_bias[n] += sum_b g[b,n]
+ * accumulated in double (a tolerance reference for the CUDA GEMMs, whose summation order is free). */
+int kgeo_proj_tail_bwd(const float* grad_preds, const float* preds, const float* x, const float* ent,
+                       int64_t B, int64_t N, int32_t k, float* grad_x, float* grad_ent, float* grad_bias) {
+  double* gx = (double*)calloc((size_t)(B * k), sizeof(double));
+  double* ge = (double*)calloc((size_t)(N * k), sizeof(double));
+  double* gb = (double*)calloc((size_t)N, sizeof(double));
+  for (int64_t b = 0; b < B; ++b)
+    for (int64_t n = 0; n < N; ++n) {
+      const float p = preds[b * N + n];
+      const double g = (double)(grad_preds[b * N + n] * (p * (1.0f - p)));
+      gb[n] += g;
+      for (int j = 0; j < k; ++j) {
+        gx[b * k + j] += g * (double)ent[n * k + j];
+        ge[n * k + j] += g * (double)x[b * k + j];
+      }
+    }
+  if (grad_x) for (int64_t i = 0; i < B * k; ++i) grad_x[i] += (float)gx[i];
+  if (grad_ent) for (int64_t i = 0; i < N * k; ++i) grad_ent[i] += (float)ge[i];
+  if (grad_bias) for (int64_t i = 0; i < N; ++i) grad_bias[i] += (float)gb[i];
+  free(gx); free(ge); free(gb);
+  return 0;
+}
+
+/* predict_tail_rank / predict_head_rank (projection.py:119-125: topk of -preds over all N) walked
+ * by MetricCalculator.get_*_rank (evaluator.py:70-123), in the count formulation:
+ *   rank0 = #{n : preds[q,n] > preds[q,tgt]};  filtered = rank0 - #{n in filter, n != tgt : same}
+ * counts[q*4 + 2*dir + {0,1}] accumulated (dir 0 = tail -> columns 0,1; 1 = head -> 2,3). */
+int kgeo_proj_rank(const float* x, const float* ent, const float* bias, int64_t Q, int64_t N, int32_t k,
+                   const int64_t* tgt, const int64_t* filt_ptr, const int64_t* filt_idx, int32_t dir,
+                   int32_t* counts) {
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int64_t q = 0; q < Q; ++q) {
+    const float* xq = x + q * k;
+    const int64_t t = tgt[q];
+    const float thr = proj_pred(xq, ent + t * k, k, bias, t);
+    int32_t raw = 0, sub = 0;
+    for (int64_t n = 0; n < N; ++n) raw += proj_pred(xq, ent + n * k, k, bias, n) > thr;
+    if (filt_ptr)
+      for (int64_t p = filt_ptr[q]; p < filt_ptr[q + 1]; ++p) {
+        const int64_t e = filt_idx[p];
+        if (e == t) continue;
+        sub += proj_pred(xq, ent + e * k, k, bias, e) > thr;
+      }
+    counts[q * 4 + 2 * dir + 0] += raw;
+    counts[q * 4 + 2 * dir + 1] += raw - sub;
+  }
+  return 0;
+}
+
+
+int kgeo_abi_version(void) { return 3; }

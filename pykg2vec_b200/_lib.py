@@ -11,7 +11,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_build", "libkge_b200.so")
 MAX_TABLES = 16
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 MODEL_IDS = {
     "transe": 0, "transh": 1, "transd": 2, "transr": 3, "rotate": 4, "hole": 5,
@@ -29,6 +29,7 @@ EXPORTS = [
     "kge_train_pairwise_hinge_sgd", "kge_optim_apply_rows",
     "kge_rank_workspace_bytes", "kge_rank_1vsall",
     "kge_tripleset_capacity", "kge_tripleset_build", "kge_sample_negatives",
+    "kge_proj_tail_fwd", "kge_proj_tail_bwd", "kge_proj_bce", "kge_proj_rank_workspace_bytes", "kge_proj_rank",
 ]
 
 
@@ -63,6 +64,7 @@ def lib():
     L.kge_launch_count.restype = ctypes.c_int64
     L.kge_rank_workspace_bytes.restype = ctypes.c_int64
     L.kge_tripleset_capacity.restype = ctypes.c_int64
+    L.kge_proj_rank_workspace_bytes.restype = ctypes.c_int64
     if L.kge_abi_version() != ABI_VERSION:
         raise KgeError("libkge_b200.so ABI %d != binding ABI %d" % (L.kge_abi_version(), ABI_VERSION))
     _lib = L
@@ -288,6 +290,77 @@ def sample_negatives(slots, ph, pr, pt, neg_rate, head_prob, num_ent, seed, step
                                      _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]), _stream()),
           "kge_sample_negatives")
     return (out[0], out[1], out[2]) if layout == 0 else (out[0], out[1], out[2], out[3])
+
+
+# ---- projection-model tail (include/kge_b200.h: kge_proj_*) ------------------------------------
+def _bias_row(bias, N):
+    if bias is None:
+        return None
+    b = _dev_f32(bias, "bias")
+    if b.numel() != N:
+        raise KgeError("bias must hold one value per entity (%d), got %d" % (N, b.numel()))
+    return b
+
+
+def proj_tail_fwd(x, ent, bias=None, out=None):
+    """preds [B,N] = sigmoid(x . ent^T + bias)   (projection.py:100-102)."""
+    x, ent = _dev_f32(x, "x"), _dev_f32(ent, "ent")
+    if x.dim() != 2 or ent.dim() != 2 or x.shape[1] != ent.shape[1]:
+        raise KgeError("x must be [B,k] and ent [N,k]")
+    B, k = x.shape
+    N = ent.shape[0]
+    bias = _bias_row(bias, N)
+    if out is None:
+        out = torch.empty((B, N), dtype=torch.float32, device=x.device)
+    check(lib().kge_proj_tail_fwd(_ptr(x), _ptr(ent), _ptr(bias), ctypes.c_int64(B), ctypes.c_int64(N),
+                                  ctypes.c_int32(k), _ptr(out), _stream()), "kge_proj_tail_fwd")
+    return out
+
+
+def proj_tail_bwd(grad_preds, preds, x, ent, grad_x=None, grad_ent=None, grad_bias=None):
+    """Accumulates into the given (zero-filled or partially filled) gradient buffers."""
+    B, k = x.shape
+    N = ent.shape[0]
+    check(lib().kge_proj_tail_bwd(_ptr(_dev_f32(grad_preds, "grad_preds")), _ptr(_dev_f32(preds, "preds")),
+                                  _ptr(_dev_f32(x, "x")), _ptr(_dev_f32(ent, "ent")), ctypes.c_int64(B),
+                                  ctypes.c_int64(N), ctypes.c_int32(k), _ptr(grad_x), _ptr(grad_ent),
+                                  _ptr(grad_bias), _stream()), "kge_proj_tail_bwd")
+
+
+def proj_bce(preds, labels, label_scale=1.0, label_shift=0.0, grad_scale=1.0, want_grad=True):
+    """One direction of Criterion.multi_class_bce -> (loss [1], grad_preds [B,N] or None)."""
+    preds, labels = _dev_f32(preds, "preds"), _dev_f32(labels, "labels")
+    if preds.dim() != 2 or preds.shape != labels.shape:
+        raise KgeError("preds and labels must both be [B,N]")
+    B, N = preds.shape
+    loss = torch.empty(1, dtype=torch.float32, device=preds.device)
+    g = torch.empty_like(preds) if want_grad else None
+    check(lib().kge_proj_bce(_ptr(preds), _ptr(labels), ctypes.c_int64(B), ctypes.c_int64(N),
+                             ctypes.c_float(label_scale), ctypes.c_float(label_shift), ctypes.c_float(grad_scale),
+                             _ptr(loss), _ptr(g), _stream()), "kge_proj_bce")
+    return loss, g
+
+
+def proj_rank(x, ent, bias, tgt, filt=None, direction=0, counts=None, workspace=None):
+    """counts [Q,4] int32 += rank counts of direction 0 (tail: columns 0,1) or 1 (head: 2,3)."""
+    x, ent, tgt = _dev_f32(x, "x"), _dev_f32(ent, "ent"), _dev_i64(tgt, "tgt")
+    Q, k = x.shape
+    N = ent.shape[0]
+    bias = _bias_row(bias, N)
+    if tgt.numel() != Q:
+        raise KgeError("one target id per query row")
+    if counts is None:
+        counts = torch.zeros((Q, 4), dtype=torch.int32, device=x.device)
+    nbytes = int(lib().kge_proj_rank_workspace_bytes(ctypes.c_int64(Q)))
+    if workspace is None or workspace.numel() < nbytes:
+        workspace = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=x.device)
+    fp, fi = filt if filt is not None else (None, None)
+    check(lib().kge_proj_rank(_ptr(x), _ptr(ent), _ptr(bias), ctypes.c_int64(Q), ctypes.c_int64(N),
+                              ctypes.c_int32(k), _ptr(tgt), _ptr(fp), _ptr(fi),
+                              ctypes.c_int64(fi.numel() if fi is not None else 0), ctypes.c_int32(direction),
+                              _ptr(counts), _ptr(workspace), ctypes.c_int64(workspace.numel()), _stream()),
+          "kge_proj_rank")
+    return counts
 
 
 def launch_count():

@@ -1,0 +1,104 @@
+// kge_proj.cu — C-ABI launchers of the projection-model tail (kernels and launch plans:
+// kge_proj.cuh; declarations and reference citations: include/kge_b200.h).
+#include "kge_proj.cuh"
+
+using namespace kge;
+
+namespace {
+
+int check_dims(const char* fn, int64_t B, int64_t N, int32_t k) {
+  if (B < 0 || N < 0 || k <= 0 || B > (1ll << 30) || N > (1ll << 30)) {
+    set_error("%s: bad shape B=%lld N=%lld k=%d", fn, (long long)B, (long long)N, (int)k);
+    return KGE_EINVAL;
+  }
+  if ((B + PBM - 1) / PBM > 65535) {
+    set_error("%s: %lld rows exceed 65535 row tiles per call", fn, (long long)B);
+    return KGE_EINVAL;
+  }
+  return KGE_OK;
+}
+
+template <int EPI>
+int launch_gemm(const ProjLaunch& L, cudaStream_t st, const char* what) {
+  proj_gemm_kernel<EPI><<<dim3(L.gx, L.gy, L.gz), PTHREADS, 0, st>>>(L.g);
+  KGE_CHECK_LAUNCH(what);
+  return KGE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int kge_proj_tail_fwd(const float* x, const float* ent, const float* bias, int64_t B, int64_t N,
+                      int32_t k, float* preds, void* stream) {
+  if (!x || !ent || !preds) { set_error("kge_proj_tail_fwd: null pointer"); return KGE_EINVAL; }
+  if (int rc = check_dims("kge_proj_tail_fwd", B, N, k)) return rc;
+  if (B == 0 || N == 0) return KGE_OK;
+  return launch_gemm<EPI_SIGMOID>(proj_plan_fwd(x, ent, bias, B, N, k, preds), (cudaStream_t)stream,
+                                  "proj_gemm_kernel<sigmoid>");
+}
+
+int kge_proj_tail_bwd(const float* grad_preds, const float* preds, const float* x, const float* ent,
+                      int64_t B, int64_t N, int32_t k, float* grad_x, float* grad_ent,
+                      float* grad_bias, void* stream) {
+  if (!grad_preds || !preds || !x || !ent) { set_error("kge_proj_tail_bwd: null pointer"); return KGE_EINVAL; }
+  if (int rc = check_dims("kge_proj_tail_bwd", B, N, k)) return rc;
+  if ((N + PBM - 1) / PBM > 65535) { set_error("kge_proj_tail_bwd: N too large"); return KGE_EINVAL; }
+  if (B == 0 || N == 0) return KGE_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (grad_x)
+    if (int rc = launch_gemm<EPI_ATOMIC>(proj_plan_grad_x(grad_preds, preds, ent, B, N, k, grad_x, 2 * sm_count()),
+                                         st, "proj_gemm_kernel<grad_x>")) return rc;
+  if (grad_ent)
+    if (int rc = launch_gemm<EPI_ATOMIC>(proj_plan_grad_ent(grad_preds, preds, x, B, N, k, grad_ent), st,
+                                         "proj_gemm_kernel<grad_ent>")) return rc;
+  if (grad_bias) {
+    proj_colsum_kernel<<<proj_tiles(N, 256), 256, 0, st>>>(grad_preds, preds, (int)B, N, grad_bias);
+    KGE_CHECK_LAUNCH("proj_colsum_kernel");
+  }
+  return KGE_OK;
+}
+
+int kge_proj_bce(const float* preds, const float* labels, int64_t B, int64_t N, float label_scale,
+                 float label_shift, float grad_scale, float* loss_out, float* grad_preds, void* stream) {
+  if (!preds || !labels || !loss_out) { set_error("kge_proj_bce: null pointer"); return KGE_EINVAL; }
+  if (B <= 0 || N <= 0) { set_error("kge_proj_bce: empty batch"); return KGE_EINVAL; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n = (long long)B * N;
+  KGE_CUDA_OK(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
+  proj_bce_kernel<<<proj_bce_blocks(n, sm_count()), 256, 0, st>>>(
+      preds, labels, n, label_scale, label_shift, proj_bce_grad_factor(grad_scale, B, N),
+      proj_bce_inv_count(B, N), loss_out, grad_preds);
+  KGE_CHECK_LAUNCH("proj_bce_kernel");
+  return KGE_OK;
+}
+
+int64_t kge_proj_rank_workspace_bytes(int64_t Q) { return (Q > 0 ? Q : 1) * (int64_t)sizeof(float); }
+
+int kge_proj_rank(const float* x, const float* ent, const float* bias, int64_t Q, int64_t N, int32_t k,
+                  const int64_t* tgt, const int64_t* filt_ptr, const int64_t* filt_idx, int64_t filt_nnz,
+                  int32_t direction, int32_t* counts, void* workspace, int64_t workspace_bytes,
+                  void* stream) {
+  if (!x || !ent || !tgt || !counts || !workspace) { set_error("kge_proj_rank: null pointer"); return KGE_EINVAL; }
+  if (direction != 0 && direction != 1) { set_error("kge_proj_rank: direction must be 0 or 1"); return KGE_EINVAL; }
+  if (int rc = check_dims("kge_proj_rank", Q, N, k)) return rc;
+  if (workspace_bytes < kge_proj_rank_workspace_bytes(Q)) {
+    set_error("kge_proj_rank: workspace too small");
+    return KGE_EWORKSPACE;
+  }
+  if (Q == 0 || N == 0) return KGE_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* thr = (float*)workspace;
+  proj_target_kernel<<<proj_tiles(Q, 128), 128, 0, st>>>(x, ent, bias, tgt, (int)Q, k, thr);
+  KGE_CHECK_LAUNCH("proj_target_kernel");
+  if (int rc = launch_gemm<EPI_COUNT>(proj_plan_count(x, ent, bias, Q, N, k, thr, counts, direction), st,
+                                      "proj_gemm_kernel<count>")) return rc;
+  if (filt_ptr && filt_idx && filt_nnz > 0) {
+    proj_filter_kernel<<<(unsigned)Q, 128, 0, st>>>(x, ent, bias, tgt, filt_ptr, filt_idx, k, thr, counts,
+                                                    2 * direction);
+    KGE_CHECK_LAUNCH("proj_filter_kernel");
+  }
+  return KGE_OK;
+}
+
+}  // extern "C"

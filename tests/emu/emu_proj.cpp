@@ -1,0 +1,71 @@
+// tests/emu/emu_proj.cpp — TEST INFRASTRUCTURE.  Runs the projection-tail kernels of
+// pykg2vec_b200/csrc/kge_proj.cuh on the host, CUDA thread by CUDA thread (tests/emu/cuda_runtime.h),
+// with the SAME launch plans the C-ABI launchers use, so the tiling, strides, split-K ranges,
+// padding, shuffles and atomics are checked against the oracle without a GPU
+// (tests/test_emu_proj.py).  Not a product path: nothing in pykg2vec_b200/ can reach it.
+#include "kge_proj.cuh"
+
+namespace cuda_emu {
+thread_local dim3 t_threadIdx, t_blockIdx;
+dim3 g_blockDim, g_gridDim;
+BlockCtx* g_block = nullptr;
+std::mutex g_atomic_mu;
+}  // namespace cuda_emu
+
+namespace kge {  // host-side symbols kge_common.cuh declares (defined in kge_abi.cu in the product)
+void set_error(const char*, ...) {}
+int cuda_fail(cudaError_t, const char*) { return KGE_ECUDA; }
+void count_launch(int) {}
+int sm_count() { return 148; }
+}  // namespace kge
+
+using namespace kge;
+
+template <int EPI>
+static void run_gemm(const ProjLaunch& L) {
+  cuda_emu::launch(dim3(L.gx, L.gy, L.gz), dim3(PTHREADS), [&] { proj_gemm_kernel<EPI>(L.g); });
+}
+
+extern "C" {
+
+int emu_proj_tail_fwd(const float* x, const float* ent, const float* bias, int64_t B, int64_t N, int32_t k,
+                      float* preds) {
+  run_gemm<EPI_SIGMOID>(proj_plan_fwd(x, ent, bias, B, N, k, preds));
+  return 0;
+}
+
+int emu_proj_tail_bwd(const float* grad_preds, const float* preds, const float* x, const float* ent, int64_t B,
+                      int64_t N, int32_t k, float* grad_x, float* grad_ent, float* grad_bias, int32_t target_ctas) {
+  if (grad_x) run_gemm<EPI_ATOMIC>(proj_plan_grad_x(grad_preds, preds, ent, B, N, k, grad_x, target_ctas));
+  if (grad_ent) run_gemm<EPI_ATOMIC>(proj_plan_grad_ent(grad_preds, preds, x, B, N, k, grad_ent));
+  if (grad_bias)
+    cuda_emu::launch(dim3(proj_tiles(N, 256)), dim3(256),
+                     [&] { proj_colsum_kernel(grad_preds, preds, (int)B, N, grad_bias); });
+  return 0;
+}
+
+int emu_proj_bce(const float* preds, const float* labels, int64_t B, int64_t N, float label_scale,
+                 float label_shift, float grad_scale, float* loss_out, float* grad_preds, int32_t sms) {
+  const long long n = (long long)B * N;
+  loss_out[0] = 0.f;
+  cuda_emu::launch(dim3(proj_bce_blocks(n, sms)), dim3(256), [&] {
+    proj_bce_kernel(preds, labels, n, label_scale, label_shift, proj_bce_grad_factor(grad_scale, B, N),
+                    proj_bce_inv_count(B, N), loss_out, grad_preds);
+  });
+  return 0;
+}
+
+int emu_proj_rank(const float* x, const float* ent, const float* bias, int64_t Q, int64_t N, int32_t k,
+                  const int64_t* tgt, const int64_t* filt_ptr, const int64_t* filt_idx, int64_t filt_nnz,
+                  int32_t direction, int32_t* counts, float* thr) {
+  cuda_emu::launch(dim3(proj_tiles(Q, 128)), dim3(128),
+                   [&] { proj_target_kernel(x, ent, bias, tgt, (int)Q, k, thr); });
+  run_gemm<EPI_COUNT>(proj_plan_count(x, ent, bias, Q, N, k, thr, counts, direction));
+  if (filt_ptr && filt_idx && filt_nnz > 0)
+    cuda_emu::launch(dim3((unsigned)Q), dim3(128), [&] {
+      proj_filter_kernel(x, ent, bias, tgt, filt_ptr, filt_idx, k, thr, counts, 2 * direction);
+    });
+  return 0;
+}
+
+}  // extern "C"

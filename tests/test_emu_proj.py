@@ -1,0 +1,133 @@
+"""CPU check of the projection-tail CUDA kernels' LOGIC (no GPU in the build container).
+
+pykg2vec_b200/csrc/kge_proj.cuh is compiled with g++ against tests/emu/cuda_runtime.h, which runs
+every CUDA thread of a block as a host thread (barrier = __syncthreads, lane exchange =
+__shfl_xor_sync, host atomics), through the same launch plans the C-ABI launchers use.  What this
+pins before the GPU run: tiling and strides of the three GEMM uses, zero padding, split-K
+ranges, the half-warp count reduction, the filter correction and the BCE reduction — against the
+oracle (bit-exact where the arithmetic is canonical, tolerance where the summation order is free).
+The real kernels are checked on the B200 by tests/test_gpu_proj.py."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SRC = os.path.join(HERE, "emu", "emu_proj.cpp")
+OUT = os.path.join(HERE, "emu", "_build", "libemu_proj.so")
+DEPS = [SRC, os.path.join(HERE, "emu", "cuda_runtime.h"),
+        os.path.join(ROOT, "pykg2vec_b200", "csrc", "kge_proj.cuh"),
+        os.path.join(ROOT, "pykg2vec_b200", "csrc", "kge_common.cuh")]
+
+
+@pytest.fixture(scope="module")
+def emu():
+    if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in DEPS):
+        os.makedirs(os.path.dirname(OUT), exist_ok=True)
+        cmd = ["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-mfma",
+               "-pthread", "-w", "-I", os.path.join(HERE, "emu"), "-I", os.path.join(ROOT, "pykg2vec_b200", "csrc"),
+               "-o", OUT + ".tmp", SRC]
+        subprocess.run(cmd, check=True)
+        os.replace(OUT + ".tmp", OUT)
+    return ctypes.CDLL(OUT)
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+def _case(B, N, k, seed, bias=True):
+    rng = np.random.RandomState(seed)
+    x = np.maximum(rng.standard_normal((B, k)) * 0.7, 0).astype(np.float32)   # post-ReLU operand
+    ent = (rng.standard_normal((N, k)) * 0.5).astype(np.float32)
+    b = (rng.standard_normal(N) * 0.3).astype(np.float32) if bias else None
+    return x, ent, b
+
+
+SHAPES = [(70, 131, 48, True), (5, 64, 50, True), (64, 65, 7, False), (1, 200, 16, True), (33, 1, 100, False)]
+
+
+@pytest.mark.parametrize("B,N,k,bias", SHAPES)
+def test_emulated_forward_is_bit_exact(emu, B, N, k, bias):
+    x, ent, b = _case(B, N, k, seed=B * 1000 + N)
+    got = np.full((B, N), np.nan, dtype=np.float32)
+    emu.emu_proj_tail_fwd(_p(x), _p(ent), _p(b), ctypes.c_int64(B), ctypes.c_int64(N), ctypes.c_int32(k), _p(got))
+    want = oracle.proj_tail_fwd(x, ent, b)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_emulated_forward_unaligned_operands(emu):
+    """operands that are not 16-byte aligned must take the scalar loader and give the same bits"""
+    B, N, k = 9, 77, 48
+    x, ent, b = _case(B, N, k, seed=5)
+    xb = np.zeros(B * k + 1, dtype=np.float32)
+    xo = xb[1:].reshape(B, k)
+    xo[:] = x
+    assert xo.ctypes.data % 16 != 0
+    got = np.empty((B, N), dtype=np.float32)
+    emu.emu_proj_tail_fwd(_p(xo), _p(ent), _p(b), ctypes.c_int64(B), ctypes.c_int64(N), ctypes.c_int32(k), _p(got))
+    assert np.array_equal(got, oracle.proj_tail_fwd(x, ent, b))
+
+
+@pytest.mark.parametrize("B,N,k,bias", SHAPES[:4])
+def test_emulated_rank_counts(emu, B, N, k, bias):
+    x, ent, b = _case(B, N, k, seed=B * 77 + N)
+    rng = np.random.RandomState(B + N)
+    tgt = rng.randint(N, size=B).astype(np.int64)
+    ptr = np.zeros(B + 1, dtype=np.int64)
+    rows = []
+    for q in range(B):
+        n = rng.randint(0, min(N, 9))
+        row = rng.choice(N, size=n, replace=False)
+        if q % 2 == 0 and n:
+            row[0] = tgt[q]            # the target itself appears in its filter row (hr_t contains t)
+        rows.append(np.unique(row))
+        ptr[q + 1] = ptr[q] + len(rows[-1])
+    idx = np.concatenate(rows).astype(np.int64) if ptr[-1] else np.zeros(0, dtype=np.int64)
+    for direction in (0, 1):
+        got = np.zeros((B, 4), dtype=np.int32)
+        thr = np.zeros(B, dtype=np.float32)
+        emu.emu_proj_rank(_p(x), _p(ent), _p(b), ctypes.c_int64(B), ctypes.c_int64(N), ctypes.c_int32(k), _p(tgt),
+                          _p(ptr), _p(idx), ctypes.c_int64(len(idx)), ctypes.c_int32(direction), _p(got), _p(thr))
+        want = oracle.proj_rank(x, ent, b, tgt, (ptr, idx), direction)
+        assert np.array_equal(got, want)
+        # and the counts are what counting over the forward matrix gives
+        preds = oracle.proj_tail_fwd(x, ent, b)
+        raw = (preds > preds[np.arange(B), tgt][:, None]).sum(1)
+        assert np.array_equal(got[:, 2 * direction], raw)
+
+
+@pytest.mark.parametrize("B,N,k,ctas", [(70, 131, 48, 12), (5, 300, 50, 296), (64, 65, 7, 1), (20, 97, 100, 7)])
+def test_emulated_backward(emu, B, N, k, ctas):
+    x, ent, b = _case(B, N, k, seed=B + 3 * N)
+    rng = np.random.RandomState(k)
+    preds = oracle.proj_tail_fwd(x, ent, b)
+    gp = (rng.standard_normal((B, N)) * 0.1).astype(np.float32)
+    gx = np.zeros((B, k), dtype=np.float32)
+    ge = np.full((N, k), 0.25, dtype=np.float32)       # accumulate semantics: pre-filled
+    gb = np.full(N, -0.5, dtype=np.float32)
+    emu.emu_proj_tail_bwd(_p(gp), _p(preds), _p(x), _p(ent), ctypes.c_int64(B), ctypes.c_int64(N), ctypes.c_int32(k),
+                          _p(gx), _p(ge), _p(gb), ctypes.c_int32(ctas))
+    wx, we, wb = oracle.proj_tail_bwd(gp, preds, x, ent)
+    for got, want in ((gx, wx), (ge - 0.25, we), (gb + 0.5, wb)):
+        assert np.abs(got - want).max() <= 2e-6 * max(1.0, np.abs(want).max())
+
+
+@pytest.mark.parametrize("B,N,sms", [(7, 131, 148), (64, 300, 1), (3, 5, 148)])
+def test_emulated_bce(emu, B, N, sms):
+    rng = np.random.RandomState(B * N)
+    preds = (1.0 / (1.0 + np.exp(-rng.standard_normal((B, N)) * 3))).astype(np.float32)
+    labels = (rng.rand(B, N) < 0.1).astype(np.float32)
+    scale, shift = np.float32(1.0 - 0.1), np.float32(1.0 / N)
+    loss = np.zeros(1, dtype=np.float32)
+    g = np.empty((B, N), dtype=np.float32)
+    emu.emu_proj_bce(_p(preds), _p(labels), ctypes.c_int64(B), ctypes.c_int64(N), ctypes.c_float(scale),
+                     ctypes.c_float(shift), ctypes.c_float(1.0), _p(loss), _p(g), ctypes.c_int32(sms))
+    want_loss, want_g = oracle.proj_bce(preds, labels, scale, shift, 1.0)
+    assert abs(loss[0] - want_loss) <= 2e-6 * abs(want_loss)
+    assert np.array_equal(g.view(np.uint32), want_g.view(np.uint32))

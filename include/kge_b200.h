@@ -249,6 +249,30 @@ int kge_proj_rank(const float* x, const float* ent, const float* bias, int64_t Q
                   int32_t direction, int32_t* counts, void* workspace, int64_t workspace_bytes,
                   void* stream);
 
+/* ---- ConvE trunk, inference mode ----------------------------------------------------------
+ * ConvE.forward + inner_forward up to the x.E^T product (pykg2vec/models/projection.py:104-112,
+ * :86-99) with self.training == False: x[q,:] = relu(fc(flatten(relu(bn1(conv2d_1(bn0(
+ * [ent[e[q]] ; rel[r[q]]] viewed as [1, 2*hidden_size_2, hidden_size_1])))))))  — dropouts are
+ * identities, BatchNorm uses running statistics, bn2 is not applied (projection.py:97-98).
+ * All pointers are device fp32 tensors with the reference's state_dict shapes:
+ *   ent [N,k], rel [2R,k] (reciprocal relations: the head direction passes r + R, :107-108),
+ *   bn0_* [1], conv_weight [32,1,3,3], conv_bias [32], bn1_* [32], fc_weight [k, F], fc_bias [k],
+ *   F = 32 * (2*hidden_size_2 - 2) * (hidden_size_1 - 2), hidden_size_2 = hidden_size / hidden_size_1.
+ * x is [Q,k]; workspace >= kge_conve_trunk_workspace_bytes() bytes (the flattened feature maps).
+ * Training (batch statistics, dropout, autograd) stays with the framework's own layers. */
+typedef struct kge_conve {
+  int32_t hidden_size, hidden_size_1;
+  float bn0_eps, bn1_eps;
+  const float* ent; const float* rel;
+  const float* bn0_weight; const float* bn0_bias; const float* bn0_mean; const float* bn0_var;
+  const float* conv_weight; const float* conv_bias;
+  const float* bn1_weight; const float* bn1_bias; const float* bn1_mean; const float* bn1_var;
+  const float* fc_weight; const float* fc_bias;
+} kge_conve_t;
+int64_t kge_conve_trunk_workspace_bytes(const kge_conve_t* p, int64_t Q);
+int kge_conve_trunk_fwd(const kge_conve_t* p, const int64_t* e, const int64_t* r, int64_t Q, float* x,
+                        void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- negative sampling on the device: replaces the CPU sampler processes ----
  * process_function_pairwise / process_function_pointwise (pykg2vec/data/generator.py:42-158).
  * The positives (all training triples, generator.py:52,109) are packed as 64-bit keys

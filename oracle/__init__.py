@@ -270,3 +270,33 @@ def proj_rank(x, ent, bias, tgt, filt=None, direction=0, counts=None):
                               _ptr(counts))
     assert rc == 0
     return counts
+
+
+class KgeConve(ctypes.Structure):
+    _fields_ = [("hidden_size", ctypes.c_int32), ("hidden_size_1", ctypes.c_int32),
+                ("bn0_eps", ctypes.c_float), ("bn1_eps", ctypes.c_float)] + \
+               [(n, ctypes.c_void_p) for n in ("ent", "rel", "bn0_weight", "bn0_bias", "bn0_mean", "bn0_var",
+                                               "conv_weight", "conv_bias", "bn1_weight", "bn1_bias", "bn1_mean",
+                                               "bn1_var", "fc_weight", "fc_bias")]
+
+
+CONVE_KEYS = {"ent": "ent_embeddings.weight", "rel": "rel_embeddings.weight", "bn0_weight": "bn0.weight",
+              "bn0_bias": "bn0.bias", "bn0_mean": "bn0.running_mean", "bn0_var": "bn0.running_var",
+              "conv_weight": "conv2d_1.weight", "conv_bias": "conv2d_1.bias", "bn1_weight": "bn1.weight",
+              "bn1_bias": "bn1.bias", "bn1_mean": "bn1.running_mean", "bn1_var": "bn1.running_var",
+              "fc_weight": "fc.weight", "fc_bias": "fc.bias"}
+
+
+def conve_trunk_fwd(state, hidden_size, hidden_size_1, e, r, eps=1e-5):
+    """state: dict state_dict-key -> numpy array (the reference ConvE's parameters and BN buffers);
+    e, r: ids (r already offset by tot_relation for the head direction).  -> x [Q, hidden_size]."""
+    keep = {f: _f32(state[k]) for f, k in CONVE_KEYS.items()}
+    p = KgeConve()
+    p.hidden_size, p.hidden_size_1, p.bn0_eps, p.bn1_eps = hidden_size, hidden_size_1, eps, eps
+    for f, a in keep.items():
+        setattr(p, f, a.ctypes.data)
+    e, r = _i64(e), _i64(r)
+    x = np.empty((e.shape[0], hidden_size), dtype=np.float32)
+    rc = lib().kgeo_conve_trunk_fwd(ctypes.byref(p), _ptr(e), _ptr(r), ctypes.c_int64(e.shape[0]), _ptr(x))
+    assert rc == 0
+    return x

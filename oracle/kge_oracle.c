@@ -882,4 +882,64 @@ int kgeo_proj_rank(const float* x, const float* ent, const float* bias, int64_t 
 }
 
 
+/* ConvE trunk in inference mode: ConvE.forward + inner_forward up to the x.E^T product
+ * (projection.py:104-112, :86-99 with self.training == False).  Canonical arithmetic as
+ * pykg2vec_b200/csrc/kge_conve.cuh states it (BatchNorm folded to fma(v, a, c); conv = 9
+ * sequential fmaf from 0 then + bias; Linear = one sequential fmaf chain, + bias). */
+typedef struct kge_conve {
+  int32_t hidden_size, hidden_size_1;
+  float bn0_eps, bn1_eps;
+  const float* ent; const float* rel;
+  const float* bn0_weight; const float* bn0_bias; const float* bn0_mean; const float* bn0_var;
+  const float* conv_weight; const float* conv_bias;
+  const float* bn1_weight; const float* bn1_bias; const float* bn1_mean; const float* bn1_var;
+  const float* fc_weight; const float* fc_bias;
+} kge_conve_t;
+
+static void bn_fold(float w, float b, float mean, float var, float eps, float* a, float* c) {
+  *a = w / sqrtf(var + eps);
+  *c = b - mean * *a;
+}
+
+int kgeo_conve_trunk_fwd(const kge_conve_t* p, const int64_t* e, const int64_t* r, int64_t Q, float* x) {
+  const int k = p->hidden_size, W = p->hidden_size_1, h2 = k / W, H = 2 * h2;
+  const int Ho = H - 2, Wo = W - 2, plane = Ho * Wo;
+  const int64_t F = (int64_t)32 * plane;
+  float a0, c0, a1[32], c1[32];
+  bn_fold(p->bn0_weight[0], p->bn0_bias[0], p->bn0_mean[0], p->bn0_var[0], p->bn0_eps, &a0, &c0);
+  for (int c = 0; c < 32; ++c)
+    bn_fold(p->bn1_weight[c], p->bn1_bias[c], p->bn1_mean[c], p->bn1_var[c], p->bn1_eps, &a1[c], &c1[c]);
+#pragma omp parallel
+  {
+    float* img = (float*)malloc(sizeof(float) * (size_t)(H * W));
+    float* feat = (float*)malloc(sizeof(float) * (size_t)F);
+#pragma omp for schedule(static)
+    for (int64_t q = 0; q < Q; ++q) {
+      const float* er = p->ent + e[q] * k;
+      const float* rr = p->rel + r[q] * k;
+      for (int i = 0; i < h2 * W; ++i) {   /* torch.cat([e.view(h2,W), r.view(h2,W)], dim=height) */
+        img[i] = fmaf(er[i], a0, c0);
+        img[h2 * W + i] = fmaf(rr[i], a0, c0);
+      }
+      for (int c = 0; c < 32; ++c)
+        for (int i = 0; i < Ho; ++i)
+          for (int j = 0; j < Wo; ++j) {
+            float acc = 0.0f;
+            for (int di = 0; di < 3; ++di)
+              for (int dj = 0; dj < 3; ++dj)
+                acc = fmaf(p->conv_weight[c * 9 + di * 3 + dj], img[(i + di) * W + j + dj], acc);
+            feat[c * plane + i * Wo + j] = fmaxf(fmaf(acc + p->conv_bias[c], a1[c], c1[c]), 0.0f);
+          }
+      for (int n = 0; n < k; ++n) {
+        const float* w = p->fc_weight + (int64_t)n * F;
+        float acc = 0.0f;
+        for (int64_t f = 0; f < F; ++f) acc = fmaf(feat[f], w[f], acc);
+        x[q * k + n] = fmaxf(acc + p->fc_bias[n], 0.0f);
+      }
+    }
+    free(img); free(feat);
+  }
+  return 0;
+}
+
 int kgeo_abi_version(void) { return 3; }

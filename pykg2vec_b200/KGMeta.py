@@ -59,3 +59,14 @@ class PointwiseModel(nn.Module, Model):
         self.model_name = model_name
         self.training_strategy = TrainingStrategy.POINTWISE_BASED
         self.database = {}
+
+
+class ProjectionModel(nn.Module, Model):
+    """Meta class of the models with a neural projection trunk (KGMeta.py:67-80)."""
+    __metaclass__ = ABCMeta
+
+    def __init__(self, model_name):
+        super(ProjectionModel, self).__init__()
+        self.model_name = model_name
+        self.training_strategy = TrainingStrategy.PROJECTION_BASED
+        self.database = {}

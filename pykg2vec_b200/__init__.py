@@ -3,7 +3,7 @@
 Package layout (only what the hot path needs):
   csrc/        CUDA kernels + the C-ABI (include/kge_b200.h)  -> _build/libkge_b200.so
   _lib.py      ctypes binding of the C-ABI
-  functional.py, criterion.py, KGMeta.py, Domain.py, pairwise.py, pointwise.py
+  functional.py, criterion.py, KGMeta.py, Domain.py, pairwise.py, pointwise.py, projection.py
                host-side mirror of pykg2vec.models.* / pykg2vec.utils.criterion
   evaluator.py mirror of pykg2vec.utils.evaluator (batched 1-vs-all rank kernel)
   trainer.py   mirror of the Trainer hot loop (train_step_* + fused sparse steps)
@@ -36,6 +36,7 @@ MODEL_MAP = {
     "simple": ("pykg2vec_b200.pointwise", "SimplE"),
     "simple_ignr": ("pykg2vec_b200.pointwise", "SimplE_ignr"),
     "convkb": ("pykg2vec_b200.pointwise", "ConvKB"),
+    "conve": ("pykg2vec_b200.projection", "ConvE"),
 }
 
 

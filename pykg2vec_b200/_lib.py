@@ -30,6 +30,7 @@ EXPORTS = [
     "kge_rank_workspace_bytes", "kge_rank_1vsall",
     "kge_tripleset_capacity", "kge_tripleset_build", "kge_sample_negatives",
     "kge_proj_tail_fwd", "kge_proj_tail_bwd", "kge_proj_bce", "kge_proj_rank_workspace_bytes", "kge_proj_rank",
+    "kge_conve_trunk_workspace_bytes", "kge_conve_trunk_fwd",
 ]
 
 
@@ -65,6 +66,7 @@ def lib():
     L.kge_rank_workspace_bytes.restype = ctypes.c_int64
     L.kge_tripleset_capacity.restype = ctypes.c_int64
     L.kge_proj_rank_workspace_bytes.restype = ctypes.c_int64
+    L.kge_conve_trunk_workspace_bytes.restype = ctypes.c_int64
     if L.kge_abi_version() != ABI_VERSION:
         raise KgeError("libkge_b200.so ABI %d != binding ABI %d" % (L.kge_abi_version(), ABI_VERSION))
     _lib = L
@@ -361,6 +363,44 @@ def proj_rank(x, ent, bias, tgt, filt=None, direction=0, counts=None, workspace=
                               _ptr(counts), _ptr(workspace), ctypes.c_int64(workspace.numel()), _stream()),
           "kge_proj_rank")
     return counts
+
+
+class KgeConve(ctypes.Structure):
+    """kge_conve_t of include/kge_b200.h."""
+    _fields_ = [("hidden_size", ctypes.c_int32), ("hidden_size_1", ctypes.c_int32),
+                ("bn0_eps", ctypes.c_float), ("bn1_eps", ctypes.c_float)] + \
+               [(n, ctypes.c_void_p) for n in ("ent", "rel", "bn0_weight", "bn0_bias", "bn0_mean", "bn0_var",
+                                               "conv_weight", "conv_bias", "bn1_weight", "bn1_bias", "bn1_mean",
+                                               "bn1_var", "fc_weight", "fc_bias")]
+
+
+def conve_trunk_fwd(model, e, r, out=None):
+    """ConvE inference trunk (projection.py:104-112, :86-99, eval mode): x [Q,k] for entity ids e and
+    relation ids r (already offset by tot_relation for the head direction).  `model` is a ConvE with
+    the reference's sub-module names."""
+    e, r = _dev_i64(e, "e"), _dev_i64(r, "r")
+    Q = e.numel()
+    if r.numel() != Q:
+        raise KgeError("e and r must have equal length")
+    tensors = {"ent": model.ent_embeddings.weight, "rel": model.rel_embeddings.weight,
+               "bn0_weight": model.bn0.weight, "bn0_bias": model.bn0.bias,
+               "bn0_mean": model.bn0.running_mean, "bn0_var": model.bn0.running_var,
+               "conv_weight": model.conv2d_1.weight, "conv_bias": model.conv2d_1.bias,
+               "bn1_weight": model.bn1.weight, "bn1_bias": model.bn1.bias,
+               "bn1_mean": model.bn1.running_mean, "bn1_var": model.bn1.running_var,
+               "fc_weight": model.fc.weight, "fc_bias": model.fc.bias}
+    p = KgeConve()
+    p.hidden_size, p.hidden_size_1 = int(model.hidden_size), int(model.hidden_size_1)
+    p.bn0_eps, p.bn1_eps = float(model.bn0.eps), float(model.bn1.eps)
+    for name, t in tensors.items():
+        setattr(p, name, _dev_f32(t.detach(), name).data_ptr())
+    nbytes = int(lib().kge_conve_trunk_workspace_bytes(ctypes.byref(p), ctypes.c_int64(Q)))
+    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=e.device)
+    if out is None:
+        out = torch.empty((Q, p.hidden_size), dtype=torch.float32, device=e.device)
+    check(lib().kge_conve_trunk_fwd(ctypes.byref(p), _ptr(e), _ptr(r), ctypes.c_int64(Q), _ptr(out), _ptr(ws),
+                                    ctypes.c_int64(ws.numel()), _stream()), "kge_conve_trunk_fwd")
+    return out
 
 
 def launch_count():

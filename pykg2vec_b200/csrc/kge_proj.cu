@@ -1,6 +1,8 @@
 // kge_proj.cu — C-ABI launchers of the projection-model tail (kernels and launch plans:
-// kge_proj.cuh; declarations and reference citations: include/kge_b200.h).
-#include "kge_proj.cuh"
+// kge_proj.cuh) and of ConvE's inference trunk (kge_conve.cuh, which reuses the same tiled GEMM —
+// one translation unit so the kernel template is instantiated once).  Declarations and reference
+// citations: include/kge_b200.h.
+#include "kge_conve.cuh"
 
 using namespace kge;
 
@@ -34,7 +36,7 @@ int kge_proj_tail_fwd(const float* x, const float* ent, const float* bias, int64
   if (!x || !ent || !preds) { set_error("kge_proj_tail_fwd: null pointer"); return KGE_EINVAL; }
   if (int rc = check_dims("kge_proj_tail_fwd", B, N, k)) return rc;
   if (B == 0 || N == 0) return KGE_OK;
-  return launch_gemm<EPI_SIGMOID>(proj_plan_fwd(x, ent, bias, B, N, k, preds), (cudaStream_t)stream,
+  return launch_gemm<EPI_STORE>(proj_plan_fwd(x, ent, bias, B, N, k, preds), (cudaStream_t)stream,
                                   "proj_gemm_kernel<sigmoid>");
 }
 
@@ -99,6 +101,49 @@ int kge_proj_rank(const float* x, const float* ent, const float* bias, int64_t Q
     KGE_CHECK_LAUNCH("proj_filter_kernel");
   }
   return KGE_OK;
+}
+
+
+// ---- ConvE inference trunk ----------------------------------------------------------------
+
+int64_t kge_conve_trunk_workspace_bytes(const kge_conve_t* p, int64_t Q) {
+  if (!p || p->hidden_size_1 < 3 || p->hidden_size < p->hidden_size_1) return 0;
+  const int h2 = p->hidden_size / p->hidden_size_1;
+  return (Q > 0 ? Q : 1) * conve_feat_width(h2, p->hidden_size_1) * (int64_t)sizeof(float);
+}
+
+int kge_conve_trunk_fwd(const kge_conve_t* p, const int64_t* e, const int64_t* r, int64_t Q, float* x,
+                        void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!p || !e || !r || !x || !workspace) { set_error("kge_conve_trunk_fwd: null pointer"); return KGE_EINVAL; }
+  const int k = p->hidden_size, h1 = p->hidden_size_1;
+  if (k <= 0 || h1 < 3 || k / h1 < 2 || (k / h1) * h1 != k || 2 * k > CONVE_MAX_IMAGE) {
+    set_error("kge_conve_trunk_fwd: unsupported image (hidden_size %d, hidden_size_1 %d)", k, h1);
+    return KGE_ENOTSUP;
+  }
+  const float* ptrs[] = {p->ent, p->rel, p->bn0_weight, p->bn0_bias, p->bn0_mean, p->bn0_var, p->conv_weight,
+                         p->conv_bias, p->bn1_weight, p->bn1_bias, p->bn1_mean, p->bn1_var, p->fc_weight, p->fc_bias};
+  for (const float* q : ptrs)
+    if (!q) { set_error("kge_conve_trunk_fwd: null parameter tensor"); return KGE_EINVAL; }
+  if (Q < 0 || (Q + PBM - 1) / PBM > 65535) { set_error("kge_conve_trunk_fwd: bad Q"); return KGE_EINVAL; }
+  if (workspace_bytes < kge_conve_trunk_workspace_bytes(p, Q)) {
+    set_error("kge_conve_trunk_fwd: workspace too small");
+    return KGE_EWORKSPACE;
+  }
+  if (Q == 0) return KGE_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int h2 = k / h1;
+  ConveFeat f{};
+  f.ent = p->ent; f.rel = p->rel; f.e = e; f.r = r; f.k = k; f.h2 = h2; f.h1 = h1;
+  f.bn0_w = p->bn0_weight; f.bn0_b = p->bn0_bias; f.bn0_mean = p->bn0_mean; f.bn0_var = p->bn0_var;
+  f.bn0_eps = p->bn0_eps;
+  f.conv_w = p->conv_weight; f.conv_b = p->conv_bias;
+  f.bn1_w = p->bn1_weight; f.bn1_b = p->bn1_bias; f.bn1_mean = p->bn1_mean; f.bn1_var = p->bn1_var;
+  f.bn1_eps = p->bn1_eps;
+  f.feat = (float*)workspace;
+  conve_feature_kernel<<<(unsigned)Q, CONVE_THREADS, 0, st>>>(f);
+  KGE_CHECK_LAUNCH("conve_feature_kernel");
+  const ProjLaunch L = conve_plan_fc(f.feat, p->fc_weight, p->fc_bias, Q, conve_feat_width(h2, h1), k, x);
+  return launch_gemm<EPI_STORE>(L, st, "proj_gemm_kernel<fc>");
 }
 
 }  // extern "C"

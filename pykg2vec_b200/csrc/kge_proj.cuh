@@ -4,7 +4,7 @@
 //     Criterion.multi_class_bce                    criterion.py:41-50
 //     predict_tail_rank / predict_head_rank        projection.py:119-125  (+ evaluator.py:70-123)
 // as one register-tiled fp32 GEMM kernel with three epilogues:
-//     EPI_SIGMOID  store sigmoid(acc + bias)                        -> forward()
+//     EPI_STORE    store act(acc + bias), act = sigmoid | relu      -> forward(); ConvE's Linear layer
 //     EPI_COUNT    count sigmoid(acc + bias) > target pred per row  -> rank counts, no [Q,N] matrix
 //     EPI_ATOMIC   accumulate acc into C (split-K)                  -> grad_x, grad_ent
 // Canonical arithmetic (DESIGN.md §3 rule 8): an output element is ONE sequential fma chain over
@@ -18,7 +18,8 @@
 namespace kge {
 
 constexpr int PBM = 64, PBN = 64, PBK = 16, PTHREADS = 256;
-enum { EPI_SIGMOID = 0, EPI_ATOMIC = 1, EPI_COUNT = 2 };
+enum { EPI_STORE = 0, EPI_ATOMIC = 1, EPI_COUNT = 2 };
+enum { ACT_SIGMOID = 0, ACT_RELU = 1 };
 
 // C(m,n) = sum_k A(m,k) * B(n,k) with A(m,k) = A[m*sAm + k*sAk], B(n,k) = B[n*sBn + k*sBk].
 struct ProjGemm {
@@ -28,7 +29,8 @@ struct ProjGemm {
   int M, N, K, klen;    // klen = contraction range per blockIdx.z (multiple of PBK)
   int avec, bvec;       // 16-byte loads along k are legal for A / B
   float* C; long long ldc;
-  const float* bias;    // [N] or null (SIGMOID, COUNT)
+  const float* bias;    // [N] or null (STORE, COUNT)
+  int act;              // STORE: ACT_SIGMOID or ACT_RELU
   const float* thr;     // COUNT: [M] prediction of the target
   int* counts;          // COUNT: counts[m*4 + coff] and [m*4 + coff + 1] += #better
   int coff;
@@ -137,10 +139,10 @@ __global__ void __launch_bounds__(PTHREADS) proj_gemm_kernel(const ProjGemm g) {
         const int gn = n0 + tx * 4 + j;
         if (gn >= g.N) continue;
         float* dst = g.C + (long long)gm * g.ldc + gn;
-        if (EPI == EPI_SIGMOID) {
+        if (EPI == EPI_STORE) {
           float l = acc[i][j];
           if (g.bias) l = fadd(l, __ldg(g.bias + gn));
-          *dst = sigmoid_canon(l);
+          *dst = (g.act == ACT_RELU) ? fmaxf(l, 0.f) : sigmoid_canon(l);
         } else {
           atomicAdd(dst, acc[i][j]);
         }
@@ -252,7 +254,7 @@ inline ProjLaunch proj_plan_fwd(const float* x, const float* ent, const float* b
   g.B = ent; g.sBn = k; g.sBk = 1;
   g.M = (int)B; g.N = (int)N; g.K = k; g.klen = (int)proj_tiles(k, PBK) * PBK;
   g.avec = proj_vec_ok(x, k, 1); g.bvec = proj_vec_ok(ent, k, 1);
-  g.C = preds; g.ldc = N; g.bias = bias;
+  g.C = preds; g.ldc = N; g.bias = bias; g.act = ACT_SIGMOID;
   L.gx = proj_tiles(N, PBN); L.gy = proj_tiles(B, PBM); L.gz = 1;
   return L;
 }

@@ -229,6 +229,8 @@ class Evaluator:
         out = np.empty((Q, 4), dtype=np.int32)
         self.last_h2d_bytes = 0
         self.last_d2h_bytes = 0
+        if hasattr(self.model, "proj_query"):
+            return self._rank_triples_projection(hs, rs, ts, filt_t, filt_h, out)
         for lo in range(0, Q, self.QUERY_BATCH):
             hi = min(Q, lo + self.QUERY_BATCH)
             q = hi - lo
@@ -253,6 +255,45 @@ class Evaluator:
             out[lo:hi] = res.numpy()
             self.last_h2d_bytes += call.h_in.numel() * 8
             self.last_d2h_bytes += res.numel() * 4
+        return out
+
+    def _rank_triples_projection(self, hs, rs, ts, filt_t, filt_h, out):
+        """Projection models (ConvE, ...): the reference evaluates them one query at a time through
+        predict_tail_rank / predict_head_rank — a [1,N] forward plus a full topk each
+        (evaluator.py:249-263, projection.py:119-125).  Here a batch of queries goes through the
+        model's trunk once per direction and kge_proj_rank counts the better-scored entities
+        without materialising [Q,N] predictions."""
+        dev = self._dev()
+        Q = hs.shape[0]
+        ent, bias = self.model.proj_tail_tables()
+        for lo in range(0, Q, self.QUERY_BATCH):
+            hi = min(Q, lo + self.QUERY_BATCH)
+            q = hi - lo
+            parts = [hs[lo:hi], rs[lo:hi], ts[lo:hi]]
+            if filt_t is not None:
+                tp, ti = filt_t
+                hp, hidx = filt_h
+                parts += [tp[lo:hi + 1] - tp[lo], hp[lo:hi + 1] - hp[lo], ti[tp[lo]:tp[hi]], hidx[hp[lo]:hp[hi]]]
+            words = sum(len(a) for a in parts)
+            stage = torch.empty(words, dtype=torch.int64).pin_memory()
+            buf, o, views = stage.numpy(), 0, []
+            for a in parts:
+                buf[o:o + len(a)] = a
+                views.append((o, o + len(a)))
+                o += len(a)
+            d_in = stage.to(dev, non_blocking=True)
+            v = [d_in[a:b] for a, b in views]
+            h, r, t = v[0], v[1], v[2]
+            ft = (v[3], v[5]) if filt_t is not None and len(parts[5]) else None
+            fh = (v[4], v[6]) if filt_t is not None and len(parts[6]) else None
+            counts = torch.zeros((q, 4), dtype=torch.int32, device=dev)
+            x_t = self.model.proj_query(h, r, direction="tail").contiguous()
+            x_h = self.model.proj_query(t, r, direction="head").contiguous()
+            _lib.proj_rank(x_t, ent.detach(), bias.detach(), t, ft, 0, counts)
+            _lib.proj_rank(x_h, ent.detach(), bias.detach(), h, fh, 1, counts)
+            out[lo:hi] = counts.cpu().numpy()
+            self.last_h2d_bytes += words * 8
+            self.last_d2h_bytes += q * 16
         return out
 
     @staticmethod

@@ -108,3 +108,48 @@ class SelfAdvFunction(torch.autograd.Function):
     def backward(ctx, g):
         gp, gn = ctx.saved_tensors
         return gp * g, gn * g, None, None
+
+
+class ProjTailFunction(torch.autograd.Function):
+    """preds [B,N] = sigmoid(x . E^T + b): the last layer of the projection models
+    (projection.py:100-102).  Backward: kge_proj_tail_bwd (three tiled GEMM launches fused with
+    the sigmoid derivative) — dense gradients for x, the entity table and the bias row."""
+
+    @staticmethod
+    def forward(ctx, x, ent, bias):
+        _require_cuda(x, ent)
+        x, ent_c = x.contiguous(), ent.contiguous()
+        bias_c = bias.contiguous() if bias is not None else None
+        preds = _lib.proj_tail_fwd(x.detach(), ent_c.detach(), bias_c.detach() if bias_c is not None else None)
+        ctx.has_bias = bias is not None
+        ctx.bias_shape = tuple(bias.shape) if bias is not None else None
+        ctx.save_for_backward(x, ent_c, preds)
+        return preds
+
+    @staticmethod
+    def backward(ctx, gpreds):
+        x, ent, preds = ctx.saved_tensors
+        gx = torch.zeros_like(x) if ctx.needs_input_grad[0] else None
+        ge = torch.zeros_like(ent) if ctx.needs_input_grad[1] else None
+        gb = torch.zeros(ent.shape[0], dtype=torch.float32, device=x.device) \
+            if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        _lib.proj_tail_bwd(gpreds.contiguous(), preds, x, ent, gx, ge, gb)
+        return gx, ge, (gb.reshape(ctx.bias_shape) if gb is not None else None)
+
+
+class MultiClassBceFunction(torch.autograd.Function):
+    """One direction of Criterion.multi_class_bce (criterion.py:41-50): value and d loss/d preds
+    in one kernel (kge_proj_bce)."""
+
+    @staticmethod
+    def forward(ctx, preds, labels, label_scale, label_shift):
+        _require_cuda(preds, labels)
+        loss, g = _lib.proj_bce(preds.contiguous(), labels.contiguous().float(), float(label_scale),
+                                float(label_shift), 1.0, want_grad=True)
+        ctx.save_for_backward(g)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, gout):
+        (g,) = ctx.saved_tensors
+        return g * gout, None, None, None

@@ -81,6 +81,38 @@ class Trainer:
         loss = loss + self.model.get_reg(h, r, t)
         return loss
 
+    def train_step_projection(self, h, r, t, hr_t, tr_h):
+        """trainer.py:159-174: both directions through the model, Criterion.multi_class_bce over the
+        dense [b,N] label matrices (ConvE family) or the model's own loss terms (ProjE)."""
+        if self.model.model_name.lower() in ["conve", "tucker", "interacte", "hyper", "acre"]:
+            pred_tails = self.model(h, r, direction="tail")
+            pred_heads = self.model(t, r, direction="head")
+            if hasattr(self.config, 'label_smoothing'):
+                loss = self.model.loss(pred_heads, pred_tails, tr_h, hr_t, self.config.label_smoothing,
+                                       self.config.tot_entity)
+            else:
+                loss = self.model.loss(pred_heads, pred_tails, tr_h, hr_t, None, None)
+        else:
+            pred_tails = self.model(h, r, hr_t, direction="tail")
+            pred_heads = self.model(t, r, tr_h, direction="head")
+            loss = self.model.loss(pred_heads, pred_tails)
+        loss = loss + self.model.get_reg(h, r, t)
+        return loss
+
+    def _projection_batch(self, data):
+        """[h, r, t, hr_t, tr_h] as Generator yields them for PROJECTION_BASED models
+        (generator.py:160-230: three id arrays and two dense [b, N] label tensors)."""
+        dev = self.config.device
+        ids, nbytes = self._to_device(list(data[:3]))
+        labels = []
+        for lab in data[3:5]:
+            lab = torch.as_tensor(lab, dtype=torch.float32)
+            if not lab.is_cuda:
+                nbytes += lab.numel() * 4
+                lab = lab.to(dev, non_blocking=True)
+            labels.append(lab)
+        return ids + labels, nbytes
+
     # ---- fused steps --------------------------------------------------------------------------
     def _opt_code(self):
         return 0 if self.config.optimizer == "sgd" else 1
@@ -188,6 +220,8 @@ class Trainer:
             loss = self.train_step_pairwise(*ids)
         elif strategy == TrainingStrategy.POINTWISE_BASED:
             loss = self.train_step_pointwise(*ids)
+        elif strategy == TrainingStrategy.PROJECTION_BASED:
+            loss = self.train_step_projection(*ids)
         else:
             raise NotImplementedError("Unknown training strategy: %s" % strategy)
         loss.backward()
@@ -218,9 +252,12 @@ class Trainer:
                 and self.model.model_name.lower() != "rotate" and self.config.optimizer == "sgd"
                 and len(data) == 6 and all(len(a) == len(data[0]) for a in data)):
             return self._graphed_hinge_step(data, sync=sync)
-        ids, nbytes = self._to_device(list(data))
-        self.last_h2d_bytes = nbytes
         strategy = self.model.training_strategy
+        if strategy == TrainingStrategy.PROJECTION_BASED:
+            ids, nbytes = self._projection_batch(data)
+        else:
+            ids, nbytes = self._to_device(list(data))
+        self.last_h2d_bytes = nbytes
         if self._fused:
             with torch.no_grad():
                 if strategy == TrainingStrategy.PAIRWISE_BASED:
@@ -235,6 +272,8 @@ class Trainer:
             loss = self.train_step_pairwise(*ids)
         elif strategy == TrainingStrategy.POINTWISE_BASED:
             loss = self.train_step_pointwise(*ids)
+        elif strategy == TrainingStrategy.PROJECTION_BASED:
+            loss = self.train_step_projection(*ids)
         else:
             raise NotImplementedError("Unknown training strategy: %s" % strategy)
         loss.backward()

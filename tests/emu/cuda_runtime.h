@@ -120,6 +120,7 @@ inline float __fsub_rn(float a, float b) { return a - b; }
 inline float __fmul_rn(float a, float b) { return a * b; }
 inline float __fsqrt_rn(float a) { return sqrtf(a); }
 inline float __frcp_rn(float a) { return 1.0f / a; }
+inline float __fdiv_rn(float a, float b) { return a / b; }
 inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 using std::max;

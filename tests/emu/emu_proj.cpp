@@ -3,7 +3,7 @@
 // with the SAME launch plans the C-ABI launchers use, so the tiling, strides, split-K ranges,
 // padding, shuffles and atomics are checked against the oracle without a GPU
 // (tests/test_emu_proj.py).  Not a product path: nothing in pykg2vec_b200/ can reach it.
-#include "kge_proj.cuh"
+#include "kge_conve.cuh"
 
 namespace cuda_emu {
 thread_local dim3 t_threadIdx, t_blockIdx;
@@ -30,7 +30,7 @@ extern "C" {
 
 int emu_proj_tail_fwd(const float* x, const float* ent, const float* bias, int64_t B, int64_t N, int32_t k,
                       float* preds) {
-  run_gemm<EPI_SIGMOID>(proj_plan_fwd(x, ent, bias, B, N, k, preds));
+  run_gemm<EPI_STORE>(proj_plan_fwd(x, ent, bias, B, N, k, preds));
   return 0;
 }
 
@@ -65,6 +65,22 @@ int emu_proj_rank(const float* x, const float* ent, const float* bias, int64_t Q
     cuda_emu::launch(dim3((unsigned)Q), dim3(128), [&] {
       proj_filter_kernel(x, ent, bias, tgt, filt_ptr, filt_idx, k, thr, counts, 2 * direction);
     });
+  return 0;
+}
+
+int emu_conve_trunk_fwd(const kge_conve_t* p, const int64_t* e, const int64_t* r, int64_t Q, float* x,
+                        float* feat) {
+  const int k = p->hidden_size, h1 = p->hidden_size_1, h2 = k / h1;
+  ConveFeat f{};
+  f.ent = p->ent; f.rel = p->rel; f.e = e; f.r = r; f.k = k; f.h2 = h2; f.h1 = h1;
+  f.bn0_w = p->bn0_weight; f.bn0_b = p->bn0_bias; f.bn0_mean = p->bn0_mean; f.bn0_var = p->bn0_var;
+  f.bn0_eps = p->bn0_eps;
+  f.conv_w = p->conv_weight; f.conv_b = p->conv_bias;
+  f.bn1_w = p->bn1_weight; f.bn1_b = p->bn1_bias; f.bn1_mean = p->bn1_mean; f.bn1_var = p->bn1_var;
+  f.bn1_eps = p->bn1_eps;
+  f.feat = feat;
+  cuda_emu::launch(dim3((unsigned)Q), dim3(CONVE_THREADS), [&] { conve_feature_kernel(f); });
+  run_gemm<EPI_STORE>(conve_plan_fc(feat, p->fc_weight, p->fc_bias, Q, conve_feat_width(h2, h1), k, x));
   return 0;
 }
 

@@ -7,11 +7,23 @@ import numpy as np
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 NON_CASES = {"losses", "settle"}
+PROJ_PREFIXES = ("conve_",)
 
 
 def case_names():
     names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-    return [n for n in names if n not in NON_CASES]
+    return [n for n in names if n not in NON_CASES and not n.startswith(PROJ_PREFIXES)]
+
+
+def proj_case_names():
+    """ConvE cases (tests/golden/make_golden_proj.py): full state_dict + tail operands, not table lists."""
+    names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    return [n for n in names if n.startswith(PROJ_PREFIXES)]
+
+
+def proj_state(g):
+    """state_dict (numpy) of the reference ConvE stored in a conve_* case"""
+    return {k[3:]: g[k] for k in g if k.startswith("sd_") and not k.startswith("sd_after_")}
 
 
 def load(name):

@@ -20,7 +20,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "emu", "emu_proj.cpp")
 OUT = os.path.join(HERE, "emu", "_build", "libemu_proj.so")
-DEPS = [SRC, os.path.join(HERE, "emu", "cuda_runtime.h"),
+DEPS = [SRC, os.path.join(HERE, "emu", "cuda_runtime.h"), os.path.join(ROOT, "pykg2vec_b200", "csrc", "kge_conve.cuh"),
         os.path.join(ROOT, "pykg2vec_b200", "csrc", "kge_proj.cuh"),
         os.path.join(ROOT, "pykg2vec_b200", "csrc", "kge_common.cuh")]
 
@@ -131,3 +131,26 @@ def test_emulated_bce(emu, B, N, sms):
     want_loss, want_g = oracle.proj_bce(preds, labels, scale, shift, 1.0)
     assert abs(loss[0] - want_loss) <= 2e-6 * abs(want_loss)
     assert np.array_equal(g.view(np.uint32), want_g.view(np.uint32))
+
+
+@pytest.mark.parametrize("name,Q", [("conve_d48", 7), ("conve_d100", 3)])
+def test_emulated_conve_trunk(emu, name, Q):
+    """gather + bn0 + conv + bn1 + relu kernel and the Linear GEMM, on the reference's own ConvE
+    parameters: bit-exact vs the oracle, which is pinned on the reference's x (test_oracle_proj)."""
+    g = np.load(os.path.join(HERE, "golden", name + ".npz"))
+    state = {k[3:]: g[k] for k in g.files if k.startswith("sd_") and not k.startswith("sd_after_")}
+    k, k1, R = int(g["hidden_size"]), int(g["hidden_size_1"]), int(g["R"])
+    keep = {f: np.ascontiguousarray(state[key], dtype=np.float32) for f, key in oracle.CONVE_KEYS.items()}
+    p = oracle.KgeConve()
+    p.hidden_size, p.hidden_size_1, p.bn0_eps, p.bn1_eps = k, k1, 1e-5, 1e-5
+    for f, a in keep.items():
+        setattr(p, f, a.ctypes.data)
+    e = np.ascontiguousarray(g["t"][:Q])
+    r = np.ascontiguousarray(g["r"][:Q] + R)     # head direction: reciprocal relation ids
+    F = 32 * (2 * (k // k1) - 2) * (k1 - 2)
+    x = np.full((Q, k), np.nan, dtype=np.float32)
+    feat = np.empty((Q, F), dtype=np.float32)
+    emu.emu_conve_trunk_fwd(ctypes.byref(p), _p(e), _p(r), ctypes.c_int64(Q), _p(x), _p(feat))
+    want = oracle.conve_trunk_fwd(state, k, k1, e, r)
+    assert np.array_equal(x.view(np.uint32), want.view(np.uint32))
+    assert np.abs(x - g["x_head"][:Q]).max() <= 1e-5

@@ -885,7 +885,8 @@ int kgeo_proj_rank(const float* x, const float* ent, const float* bias, int64_t 
 /* ConvE trunk in inference mode: ConvE.forward + inner_forward up to the x.E^T product
  * (projection.py:104-112, :86-99 with self.training == False).  Canonical arithmetic as
  * pykg2vec_b200/csrc/kge_conve.cuh states it (BatchNorm folded to fma(v, a, c); conv = 9
- * sequential fmaf from 0 then + bias; Linear = one sequential fmaf chain, + bias). */
+ * sequential fmaf from 0 then + bias; Linear = one sequential fmaf chain per slice of 512
+ * consecutive features, the slice sums added in ascending order, then + bias). */
 typedef struct kge_conve {
   int32_t hidden_size, hidden_size_1;
   float bn0_eps, bn1_eps;
@@ -930,11 +931,16 @@ int kgeo_conve_trunk_fwd(const kge_conve_t* p, const int64_t* e, const int64_t* 
                 acc = fmaf(p->conv_weight[c * 9 + di * 3 + dj], img[(i + di) * W + j + dj], acc);
             feat[c * plane + i * Wo + j] = fmaxf(fmaf(acc + p->conv_bias[c], a1[c], c1[c]), 0.0f);
           }
-      for (int n = 0; n < k; ++n) {
+      for (int n = 0; n < k; ++n) {   /* Linear: per-slice fmaf chains, slice sums added in order */
         const float* w = p->fc_weight + (int64_t)n * F;
-        float acc = 0.0f;
-        for (int64_t f = 0; f < F; ++f) acc = fmaf(feat[f], w[f], acc);
-        x[q * k + n] = fmaxf(acc + p->fc_bias[n], 0.0f);
+        float total = 0.0f;
+        for (int64_t f0 = 0; f0 < F; f0 += 512) {
+          const int64_t f1 = f0 + 512 < F ? f0 + 512 : F;
+          float acc = 0.0f;
+          for (int64_t f = f0; f < f1; ++f) acc = fmaf(feat[f], w[f], acc);
+          total = (f0 == 0) ? acc : total + acc;
+        }
+        x[q * k + n] = fmaxf(total + p->fc_bias[n], 0.0f);
       }
     }
     free(img); free(feat);

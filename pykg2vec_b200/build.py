@@ -30,7 +30,7 @@ def _stamp():
     h = hashlib.sha256()
     for p in sorted(glob.glob(os.path.join(CSRC, "*")) + [os.path.join(HERE, "..", "include", "kge_b200.h")]):
         with open(p, "rb") as f:
-            h.update(p.encode() + b"\0" + f.read())
+            h.update(os.path.basename(p).encode() + b"\0" + f.read())   # location-independent (GPU box path differs)
     h.update(" ".join(FLAGS).encode())
     return h.hexdigest()
 

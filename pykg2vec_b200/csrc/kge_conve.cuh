@@ -3,11 +3,14 @@
 // identities, bn0 / bn1 use their running statistics, bn2 is skipped):
 //     image[2*h2, h1] = [ent[e] ; rel[r]]            two gathered rows stacked along the height
 //     bn0 -> conv 3x3 (1 -> 32 channels, stride 1, no padding) -> bn1 -> relu -> flatten   (kernel below)
-//     x = relu(feat . fc.weight^T + fc.bias)          (the tiled GEMM of kge_proj.cuh, ACT_RELU)
+//     x = relu(feat . fc.weight^T + fc.bias)          (the tiled GEMM of kge_proj.cuh over column slices
+//                                                      + the ordered combine kernel below)
 // Canonical arithmetic (restated by oracle/kge_oracle.c kgeo_conve_trunk_fwd, bit for bit):
 //     BatchNorm(v) = fma(v, a, c) with a = w / sqrt(var + eps), c = b - mean * a   (ATen folds the
 //     inference transform the same way); conv = 9 sequential fma from 0 in (di, dj) row-major order,
-//     then + conv bias; Linear = one sequential fma chain over the flattened features, + bias.
+//     then + conv bias; Linear = one sequential fma chain from 0 per slice of CONVE_FC_SLICE consecutive
+//     features (so the contraction spreads over many CTAs whatever the batch size), the slice sums added
+//     in ascending slice order, then + bias.
 #pragma once
 #include "kge_proj.cuh"
 
@@ -16,6 +19,7 @@ namespace kge {
 constexpr int CONVE_CH = 32;        // conv2d_1 output channels (projection.py:48)
 constexpr int CONVE_THREADS = 256;
 constexpr int CONVE_MAX_IMAGE = 4096;  // floats of the stacked image held in shared memory (k <= 2048)
+constexpr int CONVE_FC_SLICE = 512;    // features per partial product of the Linear layer (multiple of PBK)
 
 struct ConveFeat {
   const float* ent; const float* rel;
@@ -68,18 +72,31 @@ __global__ void __launch_bounds__(CONVE_THREADS) conve_feature_kernel(const Conv
 
 inline long long conve_feat_width(int h2, int h1) { return (long long)CONVE_CH * (2 * h2 - 2) * (h1 - 2); }
 
-// x[Q,k] = relu(feat[Q,F] . fc_w[k,F]^T + fc_b)
-inline ProjLaunch conve_plan_fc(const float* feat, const float* fc_w, const float* fc_b, long long Q,
-                                long long F, int k, float* x) {
+inline int conve_fc_slices(long long F) { return (int)((F + CONVE_FC_SLICE - 1) / CONVE_FC_SLICE); }
+
+// partial[s][Q,k] = feat[Q, slice s] . fc_w[k, slice s]^T   (no bias, no activation)
+inline ProjLaunch conve_plan_fc(const float* feat, const float* fc_w, long long Q, long long F, int k,
+                                float* partial) {
   ProjLaunch L{};
   ProjGemm& g = L.g;
   g.A = feat; g.sAm = F; g.sAk = 1; g.Ap = nullptr;
   g.B = fc_w; g.sBn = F; g.sBk = 1;
-  g.M = (int)Q; g.N = k; g.K = (int)F; g.klen = (int)proj_tiles(F, PBK) * PBK;
+  g.M = (int)Q; g.N = k; g.K = (int)F; g.klen = CONVE_FC_SLICE;
   g.avec = proj_vec_ok(feat, F, 1); g.bvec = proj_vec_ok(fc_w, F, 1);
-  g.C = x; g.ldc = k; g.bias = fc_b; g.act = ACT_RELU;
-  L.gx = proj_tiles(k, PBN); L.gy = proj_tiles(Q, PBM); L.gz = 1;
+  g.C = partial; g.ldc = k; g.zstride = Q * k; g.bias = nullptr; g.act = ACT_NONE;
+  L.gx = proj_tiles(k, PBN); L.gy = proj_tiles(Q, PBM); L.gz = (unsigned)conve_fc_slices(F);
   return L;
+}
+
+// x[i] = relu(((P_0[i] + P_1[i]) + ... + P_{S-1}[i]) + fc_b[i % k])
+__global__ void __launch_bounds__(256)
+conve_fc_combine_kernel(const float* __restrict__ partial, int slices, long long n, int k,
+                        const float* __restrict__ fc_b, float* __restrict__ x) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  float acc = __ldg(partial + i);
+  for (int s = 1; s < slices; ++s) acc = fadd(acc, __ldg(partial + (long long)s * n + i));
+  x[i] = fmaxf(fadd(acc, __ldg(fc_b + (int)(i % k))), 0.f);
 }
 
 }  // namespace kge

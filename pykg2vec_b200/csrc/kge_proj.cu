@@ -109,7 +109,8 @@ int kge_proj_rank(const float* x, const float* ent, const float* bias, int64_t Q
 int64_t kge_conve_trunk_workspace_bytes(const kge_conve_t* p, int64_t Q) {
   if (!p || p->hidden_size_1 < 3 || p->hidden_size < p->hidden_size_1) return 0;
   const int h2 = p->hidden_size / p->hidden_size_1;
-  return (Q > 0 ? Q : 1) * conve_feat_width(h2, p->hidden_size_1) * (int64_t)sizeof(float);
+  const long long F = conve_feat_width(h2, p->hidden_size_1), q = Q > 0 ? Q : 1;
+  return (q * F + (long long)conve_fc_slices(F) * q * p->hidden_size) * (int64_t)sizeof(float);
 }
 
 int kge_conve_trunk_fwd(const kge_conve_t* p, const int64_t* e, const int64_t* r, int64_t Q, float* x,
@@ -142,8 +143,14 @@ int kge_conve_trunk_fwd(const kge_conve_t* p, const int64_t* e, const int64_t* r
   f.feat = (float*)workspace;
   conve_feature_kernel<<<(unsigned)Q, CONVE_THREADS, 0, st>>>(f);
   KGE_CHECK_LAUNCH("conve_feature_kernel");
-  const ProjLaunch L = conve_plan_fc(f.feat, p->fc_weight, p->fc_bias, Q, conve_feat_width(h2, h1), k, x);
-  return launch_gemm<EPI_STORE>(L, st, "proj_gemm_kernel<fc>");
+  const long long F = conve_feat_width(h2, h1);
+  float* partial = f.feat + Q * F;
+  if (int rc = launch_gemm<EPI_STORE>(conve_plan_fc(f.feat, p->fc_weight, Q, F, k, partial), st,
+                                      "proj_gemm_kernel<fc>")) return rc;
+  conve_fc_combine_kernel<<<proj_tiles(Q * k, 256), 256, 0, st>>>(partial, conve_fc_slices(F), Q * k, k,
+                                                                 p->fc_bias, x);
+  KGE_CHECK_LAUNCH("conve_fc_combine_kernel");
+  return KGE_OK;
 }
 
 }  // extern "C"

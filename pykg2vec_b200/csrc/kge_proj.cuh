@@ -19,7 +19,7 @@ namespace kge {
 
 constexpr int PBM = 64, PBN = 64, PBK = 16, PTHREADS = 256;
 enum { EPI_STORE = 0, EPI_ATOMIC = 1, EPI_COUNT = 2 };
-enum { ACT_SIGMOID = 0, ACT_RELU = 1 };
+enum { ACT_SIGMOID = 0, ACT_RELU = 1, ACT_NONE = 2 };
 
 // C(m,n) = sum_k A(m,k) * B(n,k) with A(m,k) = A[m*sAm + k*sAk], B(n,k) = B[n*sBn + k*sBk].
 struct ProjGemm {
@@ -29,20 +29,26 @@ struct ProjGemm {
   int M, N, K, klen;    // klen = contraction range per blockIdx.z (multiple of PBK)
   int avec, bvec;       // 16-byte loads along k are legal for A / B
   float* C; long long ldc;
+  long long zstride;    // STORE: slice blockIdx.z writes to C + blockIdx.z * zstride (partial products)
   const float* bias;    // [N] or null (STORE, COUNT)
-  int act;              // STORE: ACT_SIGMOID or ACT_RELU
+  int act;              // STORE: ACT_SIGMOID, ACT_RELU or ACT_NONE
   const float* thr;     // COUNT: [M] prediction of the target
   int* counts;          // COUNT: counts[m*4 + coff] and [m*4 + coff + 1] += #better
   int coff;
 };
 
-// Stage a [ROWS x PBK] operand tile k-major: S[kk][row].  Rows / k beyond the operand read as 0.
+// Staging of a [ROWS x PBK] operand tile, k-major in shared memory (S[kk][row]), in two halves
+// so that the global loads of chunk c+1 are in flight while chunk c is multiplied: fetch() reads
+// this thread's 4 elements into registers, place() writes them to shared memory.  Rows / k beyond
+// the operand read as 0 (an exact identity for the fma chain).
+struct ProjRegs { float v[4]; };
+
 template <int ROWS>
-KGE_DEV void proj_load_tile(float (*S)[ROWS + 4], const float* __restrict__ P,
-                            const float* __restrict__ Pp, long long sr, long long sk, int vec,
-                            int r0, int nrows, int k0, int kend, int tid) {
-  static_assert(ROWS * PBK == 4 * PTHREADS, "one 16-byte load per thread");
-  if (vec && !Pp) {  // sk == 1, rows 16-byte aligned: thread -> (row, 4 consecutive k)
+KGE_DEV void proj_fetch_tile(ProjRegs& R, const float* __restrict__ P, const float* __restrict__ Pp,
+                             long long sr, long long sk, bool usevec, int r0, int nrows, int k0,
+                             int kend, int tid) {
+  static_assert(ROWS * PBK == 4 * PTHREADS, "four elements per thread");
+  if (usevec) {  // sk == 1, rows 16-byte aligned: thread -> (row, 4 consecutive k), one 16-byte load
     const int rr = tid >> 2, kq = (tid & 3) * 4;
     const int gr = r0 + rr, gk = k0 + kq;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -56,11 +62,13 @@ KGE_DEV void proj_load_tile(float (*S)[ROWS + 4], const float* __restrict__ P,
         if (gk + 2 < kend) v.z = __ldg(src + 2);
       }
     }
-    S[kq + 0][rr] = v.x; S[kq + 1][rr] = v.y; S[kq + 2][rr] = v.z; S[kq + 3][rr] = v.w;
+    R.v[0] = v.x; R.v[1] = v.y; R.v[2] = v.z; R.v[3] = v.w;
     return;
   }
   const bool kcontig = (sk == 1);
-  for (int i = tid; i < ROWS * PBK; i += PTHREADS) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int i = tid + u * PTHREADS;
     int rr, kk;
     if (kcontig) { kk = i % PBK; rr = i / PBK; } else { rr = i % ROWS; kk = i / ROWS; }
     const int gr = r0 + rr, gk = k0 + kk;
@@ -70,7 +78,24 @@ KGE_DEV void proj_load_tile(float (*S)[ROWS + 4], const float* __restrict__ P,
       v = __ldg(P + off);
       if (Pp) { const float p = __ldg(Pp + off); v = fmul(v, fmul(p, fsub(1.0f, p))); }
     }
-    S[kk][rr] = v;
+    R.v[u] = v;
+  }
+}
+
+template <int ROWS>
+KGE_DEV void proj_place_tile(float (*S)[ROWS + 4], const ProjRegs& R, long long sk, bool usevec, int tid) {
+  if (usevec) {
+    const int rr = tid >> 2, kq = (tid & 3) * 4;
+    S[kq + 0][rr] = R.v[0]; S[kq + 1][rr] = R.v[1]; S[kq + 2][rr] = R.v[2]; S[kq + 3][rr] = R.v[3];
+    return;
+  }
+  const bool kcontig = (sk == 1);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int i = tid + u * PTHREADS;
+    int rr, kk;
+    if (kcontig) { kk = i % PBK; rr = i / PBK; } else { rr = i % ROWS; kk = i / ROWS; }
+    S[kk][rr] = R.v[u];
   }
 }
 
@@ -82,16 +107,26 @@ __global__ void __launch_bounds__(PTHREADS) proj_gemm_kernel(const ProjGemm g) {
   const int m0 = blockIdx.y * PBM, n0 = blockIdx.x * PBN;
   const int kbeg = blockIdx.z * g.klen;
   const int kend = min(g.K, kbeg + g.klen);
+  const bool avec = g.avec && !g.Ap, bvec = g.bvec != 0;
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
+  ProjRegs ra, rb;
+  if (kbeg < kend) {
+    proj_fetch_tile<PBM>(ra, g.A, g.Ap, g.sAm, g.sAk, avec, m0, g.M, kbeg, kend, tid);
+    proj_fetch_tile<PBN>(rb, g.B, nullptr, g.sBn, g.sBk, bvec, n0, g.N, kbeg, kend, tid);
+  }
   for (int k0 = kbeg; k0 < kend; k0 += PBK) {
-    proj_load_tile<PBM>(As, g.A, g.Ap, g.sAm, g.sAk, g.avec, m0, g.M, k0, kend, tid);
-    proj_load_tile<PBN>(Bs, g.B, nullptr, g.sBn, g.sBk, g.bvec, n0, g.N, k0, kend, tid);
+    proj_place_tile<PBM>(As, ra, g.sAk, avec, tid);
+    proj_place_tile<PBN>(Bs, rb, g.sBk, bvec, tid);
     __syncthreads();
+    if (k0 + PBK < kend) {  // next chunk's loads overlap this chunk's multiply
+      proj_fetch_tile<PBM>(ra, g.A, g.Ap, g.sAm, g.sAk, avec, m0, g.M, k0 + PBK, kend, tid);
+      proj_fetch_tile<PBN>(rb, g.B, nullptr, g.sBn, g.sBk, bvec, n0, g.N, k0 + PBK, kend, tid);
+    }
 #pragma unroll
     for (int kk = 0; kk < PBK; ++kk) {
       const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
@@ -138,11 +173,11 @@ __global__ void __launch_bounds__(PTHREADS) proj_gemm_kernel(const ProjGemm g) {
       for (int j = 0; j < 4; ++j) {
         const int gn = n0 + tx * 4 + j;
         if (gn >= g.N) continue;
-        float* dst = g.C + (long long)gm * g.ldc + gn;
+        float* dst = g.C + (long long)blockIdx.z * g.zstride + (long long)gm * g.ldc + gn;
         if (EPI == EPI_STORE) {
           float l = acc[i][j];
           if (g.bias) l = fadd(l, __ldg(g.bias + gn));
-          *dst = (g.act == ACT_RELU) ? fmaxf(l, 0.f) : sigmoid_canon(l);
+          *dst = (g.act == ACT_SIGMOID) ? sigmoid_canon(l) : (g.act == ACT_RELU ? fmaxf(l, 0.f) : l);
         } else {
           atomicAdd(dst, acc[i][j]);
         }

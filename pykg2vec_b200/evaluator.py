@@ -275,7 +275,11 @@ class Evaluator:
                 hp, hidx = filt_h
                 parts += [tp[lo:hi + 1] - tp[lo], hp[lo:hi + 1] - hp[lo], ti[tp[lo]:tp[hi]], hidx[hp[lo]:hp[hi]]]
             words = sum(len(a) for a in parts)
-            stage = torch.empty(words, dtype=torch.int64).pin_memory()
+            stage = getattr(self, "_proj_stage", None)
+            if stage is None or stage.numel() < words:   # pinned staging buffer, grown geometrically
+                stage = self._proj_stage = torch.empty(max(words, 2 * (stage.numel() if stage is not None else 0)),
+                                                       dtype=torch.int64).pin_memory()
+            stage = stage[:words]
             buf, o, views = stage.numpy(), 0, []
             for a in parts:
                 buf[o:o + len(a)] = a

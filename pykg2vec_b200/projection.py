@@ -10,7 +10,8 @@ batches of queries with kge_proj_rank (counts only, no [Q, N] matrix, no sort).
 The trunk in front of it (BatchNorm -> 3x3 conv -> BatchNorm -> ReLU -> Linear -> BatchNorm ->
 ReLU on a [b, 1, 2*h2, h1] image) runs in two ways:
   * training (autograd needed, BatchNorm batch statistics): the reference's own torch layers,
-    with TF32 convolutions disabled so the trunk stays fp32 like the reference's CPU path;
+    with TF32 convolutions disabled in forward and backward so the trunk stays fp32 like the
+    reference's CPU path;
   * evaluation (`proj_query`, used by the batched Evaluator): kge_conve_trunk_fwd — gather +
     BN0 + conv + BN1 + ReLU in one kernel and the Linear layer through the same tiled GEMM as the
     tail.
@@ -23,6 +24,36 @@ from .criterion import Criterion
 from .Domain import NamedEmbedding
 from .functional import ProjTailFunction, _require_cuda
 from .KGMeta import ProjectionModel
+
+
+class _Fp32Conv2d(torch.autograd.Function):
+    """conv2d whose forward AND backward run with TF32 convolutions disabled: the reference's
+    numbers are the fp32 CPU path's, and cuDNN would otherwise round operands to 10-bit
+    mantissas (torch.backends.cudnn.allow_tf32 defaults to True).  A context manager around the
+    forward call alone would not cover the backward pass, which runs later inside
+    loss.backward()."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, padding, dilation, groups):
+        ctx.save_for_backward(x, weight)
+        ctx.conf = (stride, padding, dilation, groups, bias is not None)
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            return torch.nn.functional.conv2d(x, weight, bias, stride, padding, dilation, groups)
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, weight = ctx.saved_tensors
+        stride, padding, dilation, groups, has_bias = ctx.conf
+        mask = [ctx.needs_input_grad[0], ctx.needs_input_grad[1], has_bias and ctx.needs_input_grad[2]]
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            gx, gw, gb = torch.ops.aten.convolution_backward(
+                gout.contiguous(), x, weight, [weight.shape[0]] if has_bias else None, list(stride),
+                list(padding), list(dilation), False, [0, 0], groups, mask)
+        return gx, gw, gb, None, None, None, None
+
+
+def _conv2d_fp32(conv, x):
+    return _Fp32Conv2d.apply(x, conv.weight, conv.bias, conv.stride, conv.padding, conv.dilation, conv.groups)
 
 
 class ConvE(ProjectionModel):
@@ -65,11 +96,10 @@ class ConvE(ProjectionModel):
         stacked_e = e_emb.view(-1, 1, self.hidden_size_2, self.hidden_size_1)
         stacked_r = r_emb.view(-1, 1, self.hidden_size_2, self.hidden_size_1)
         x = torch.cat([stacked_e, stacked_r], 2)
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-            x = self.bn0(x)
-            x = self.inp_drop(x)
-            x = self.conv2d_1(x)
-            x = self.bn1(x)
+        x = self.bn0(x)
+        x = self.inp_drop(x)
+        x = _conv2d_fp32(self.conv2d_1, x)
+        x = self.bn1(x)
         x = torch.relu(x)
         x = self.feat_drop(x)
         x = x.view(e.shape[0], -1)

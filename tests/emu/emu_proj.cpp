@@ -80,7 +80,12 @@ int emu_conve_trunk_fwd(const kge_conve_t* p, const int64_t* e, const int64_t* r
   f.bn1_eps = p->bn1_eps;
   f.feat = feat;
   cuda_emu::launch(dim3((unsigned)Q), dim3(CONVE_THREADS), [&] { conve_feature_kernel(f); });
-  run_gemm<EPI_STORE>(conve_plan_fc(feat, p->fc_weight, p->fc_bias, Q, conve_feat_width(h2, h1), k, x));
+  const long long F = conve_feat_width(h2, h1);
+  float* partial = feat + Q * F;   // the caller sizes feat as the C-ABI workspace: [Q,F] + [slices,Q,k]
+  run_gemm<EPI_STORE>(conve_plan_fc(feat, p->fc_weight, Q, F, k, partial));
+  cuda_emu::launch(dim3(proj_tiles(Q * k, 256)), dim3(256), [&] {
+    conve_fc_combine_kernel(partial, conve_fc_slices(F), Q * k, k, p->fc_bias, x);
+  });
   return 0;
 }
 

@@ -54,7 +54,7 @@ SHAPES = [(70, 131, 48, True), (5, 64, 50, True), (64, 65, 7, False), (1, 200, 1
 
 @pytest.mark.parametrize("B,N,k,bias", SHAPES)
 def test_emulated_forward_is_bit_exact(emu, B, N, k, bias):
-    x, ent, b = _case(B, N, k, seed=B * 1000 + N)
+    x, ent, b = _case(B, N, k, seed=B * 1000 + N, bias=bias)
     got = np.full((B, N), np.nan, dtype=np.float32)
     emu.emu_proj_tail_fwd(_p(x), _p(ent), _p(b), ctypes.c_int64(B), ctypes.c_int64(N), ctypes.c_int32(k), _p(got))
     want = oracle.proj_tail_fwd(x, ent, b)
@@ -76,7 +76,7 @@ def test_emulated_forward_unaligned_operands(emu):
 
 @pytest.mark.parametrize("B,N,k,bias", SHAPES[:4])
 def test_emulated_rank_counts(emu, B, N, k, bias):
-    x, ent, b = _case(B, N, k, seed=B * 77 + N)
+    x, ent, b = _case(B, N, k, seed=B * 77 + N, bias=bias)
     rng = np.random.RandomState(B + N)
     tgt = rng.randint(N, size=B).astype(np.int64)
     ptr = np.zeros(B + 1, dtype=np.int64)
@@ -149,7 +149,7 @@ def test_emulated_conve_trunk(emu, name, Q):
     r = np.ascontiguousarray(g["r"][:Q] + R)     # head direction: reciprocal relation ids
     F = 32 * (2 * (k // k1) - 2) * (k1 - 2)
     x = np.full((Q, k), np.nan, dtype=np.float32)
-    feat = np.empty((Q, F), dtype=np.float32)
+    feat = np.empty(Q * F + ((F + 511) // 512) * Q * k, dtype=np.float32)   # workspace: features + slice partials
     emu.emu_conve_trunk_fwd(ctypes.byref(p), _p(e), _p(r), ctypes.c_int64(Q), _p(x), _p(feat))
     want = oracle.conve_trunk_fwd(state, k, k1, e, r)
     assert np.array_equal(x.view(np.uint32), want.view(np.uint32))

@@ -40,7 +40,7 @@ SHAPES = [(70, 131, 48, True), (5, 64, 50, True), (64, 65, 7, False), (1, 200, 1
 @pytest.mark.parametrize("B,N,k,bias", SHAPES, ids=lambda v: str(v))
 def test_tail_forward_bit_exact_vs_oracle(B, N, k, bias):
     L = _L()
-    x, ent, b = _case(B, N, k, seed=B * 1000 + N)
+    x, ent, b = _case(B, N, k, seed=B * 1000 + N, bias=bias)
     got = L.proj_tail_fwd(_cuda(x), _cuda(ent), _cuda(b) if bias else None).cpu().numpy()
     want = oracle.proj_tail_fwd(x, ent, b)
     assert np.array_equal(gpu.bits(got), gpu.bits(want))
@@ -71,7 +71,7 @@ def test_tail_forward_vs_torch_fp32():
 @pytest.mark.parametrize("B,N,k,bias", SHAPES[:4] + [(300, 14541, 200, True)], ids=lambda v: str(v))
 def test_rank_counts_exact_vs_oracle(B, N, k, bias):
     L = _L()
-    x, ent, b = _case(B, N, k, seed=B * 77 + N)
+    x, ent, b = _case(B, N, k, seed=B * 77 + N, bias=bias)
     rng = np.random.RandomState(B + N)
     tgt = rng.randint(N, size=B).astype(np.int64)
     dummy = np.zeros(B, dtype=np.int64)
@@ -258,7 +258,9 @@ def test_conve_training_step_matches_reference_autograd(name):
         else:
             got = got.reshape(-1)[::37]
             want = g["gradsample_" + key]
-        scale = max(np.abs(want).max(), 1e-12)
+        # bn0's scale and shift are (mathematically) invisible behind bn1's batch normalisation: their
+        # true gradient is 0 and what autograd returns is rounding noise of order 1e-7 — hence the floor
+        scale = max(np.abs(want).max(), 1e-5)
         assert np.abs(got - want).max() / scale < 5e-4, key
     for key, v in m.state_dict().items():
         if "running" in key:

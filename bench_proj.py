@@ -85,15 +85,22 @@ def main():
             torch.cuda.synchronize()
             continue
         gemm_flops = 2.0 * B * N * K
-        ms = time_ms(lambda: _lib.proj_tail_fwd(x, ent, bias, out=preds), args.reps, flush)
-        emit(kernel="proj_tail_fwd", case=label, ms=ms, flops=gemm_flops, bytes=(B * K + N * K + N + B * N) * 4)
-        ms = time_ms(lambda: torch.sigmoid(torch.addmm(bias, x, ent.T)), args.reps, flush)
-        emit(kernel="torch addmm+sigmoid (library)", case=label, ms=ms, flops=gemm_flops)
         counts = torch.zeros((B, 4), dtype=torch.int32, device=dev)
         ws = torch.empty(B * 4 + 16, dtype=torch.uint8, device=dev)
-        ms = time_ms(lambda: _lib.proj_rank(x, ent, bias, tgt, None, 0, counts, ws), args.reps, flush)
-        emit(kernel="proj_rank (1 direction, raw)", case=label, ms=ms, flops=gemm_flops,
-             bytes=(B * K + N * K + N) * 4, scored_per_s=B * N / ms * 1e3)
+        for tile, tname in ((None, "auto"), ("0", "64x64"), ("1", "64x128"), ("2", "128x128")):
+            if tile is None:
+                os.environ.pop("KGE_PROJ_TILE", None)
+            else:
+                os.environ["KGE_PROJ_TILE"] = tile      # read by the library at every call
+            ms = time_ms(lambda: _lib.proj_tail_fwd(x, ent, bias, out=preds), args.reps, flush)
+            emit(kernel="proj_tail_fwd", tile=tname, case=label, ms=ms, flops=gemm_flops,
+                 bytes=(B * K + N * K + N + B * N) * 4)
+            ms = time_ms(lambda: _lib.proj_rank(x, ent, bias, tgt, None, 0, counts, ws), args.reps, flush)
+            emit(kernel="proj_rank (1 direction, raw)", tile=tname, case=label, ms=ms, flops=gemm_flops,
+                 bytes=(B * K + N * K + N) * 4, scored_per_s=B * N / ms * 1e3)
+        os.environ.pop("KGE_PROJ_TILE", None)
+        ms = time_ms(lambda: torch.sigmoid(torch.addmm(bias, x, ent.T)), args.reps, flush)
+        emit(kernel="torch addmm+sigmoid (library)", case=label, ms=ms, flops=gemm_flops)
         ms = time_ms(lambda: torch.topk(-torch.sigmoid(torch.addmm(bias, x, ent.T)), k=N), max(args.reps // 4, 3), flush)
         emit(kernel="torch addmm+sigmoid+topk(N) (library, batched)", case=label, ms=ms, scored_per_s=B * N / ms * 1e3)
         labels = (torch.rand((B, N), device=dev, generator=gen) < 0.01).float()

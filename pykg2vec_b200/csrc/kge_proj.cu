@@ -2,6 +2,8 @@
 // kge_proj.cuh) and of ConvE's inference trunk (kge_conve.cuh, which reuses the same tiled GEMM —
 // one translation unit so the kernel template is instantiated once).  Declarations and reference
 // citations: include/kge_b200.h.
+#include <cstdlib>
+
 #include "kge_conve.cuh"
 
 using namespace kge;
@@ -22,9 +24,22 @@ int check_dims(const char* fn, int64_t B, int64_t N, int32_t k) {
 
 template <int EPI>
 int launch_gemm(const ProjLaunch& L, cudaStream_t st, const char* what) {
-  proj_gemm_kernel<EPI><<<dim3(L.gx, L.gy, L.gz), PTHREADS, 0, st>>>(L.g);
+  const dim3 grid(L.gx, L.gy, L.gz);
+  switch (L.tile) {
+    case PROJ_TILE_128x128: proj_gemm_kernel<EPI, 8, 8><<<grid, PTHREADS, 0, st>>>(L.g); break;
+    case PROJ_TILE_64x128: proj_gemm_kernel<EPI, 4, 8><<<grid, PTHREADS, 0, st>>>(L.g); break;
+    default: proj_gemm_kernel<EPI, 4, 4><<<grid, PTHREADS, 0, st>>>(L.g); break;
+  }
   KGE_CHECK_LAUNCH(what);
   return KGE_OK;
+}
+
+// CTA tile of the forward / counting launches: proj_pick_tile(), or KGE_PROJ_TILE=0|1|2 in the
+// environment (64x64 | 64x128 | 128x128; used by bench_proj.py and the tests to time / check each).
+int pick_tile(int64_t M, int64_t N) {
+  if (const char* e = getenv("KGE_PROJ_TILE"))
+    if (e[0] >= '0' && e[0] <= '2' && e[1] == 0) return e[0] - '0';
+  return proj_pick_tile(M, N, sm_count());
 }
 
 }  // namespace
@@ -36,8 +51,8 @@ int kge_proj_tail_fwd(const float* x, const float* ent, const float* bias, int64
   if (!x || !ent || !preds) { set_error("kge_proj_tail_fwd: null pointer"); return KGE_EINVAL; }
   if (int rc = check_dims("kge_proj_tail_fwd", B, N, k)) return rc;
   if (B == 0 || N == 0) return KGE_OK;
-  return launch_gemm<EPI_STORE>(proj_plan_fwd(x, ent, bias, B, N, k, preds), (cudaStream_t)stream,
-                                  "proj_gemm_kernel<sigmoid>");
+  return launch_gemm<EPI_STORE>(proj_plan_fwd(x, ent, bias, B, N, k, preds, pick_tile(B, N)),
+                                (cudaStream_t)stream, "proj_gemm_kernel<sigmoid>");
 }
 
 int kge_proj_tail_bwd(const float* grad_preds, const float* preds, const float* x, const float* ent,
@@ -93,8 +108,8 @@ int kge_proj_rank(const float* x, const float* ent, const float* bias, int64_t Q
   float* thr = (float*)workspace;
   proj_target_kernel<<<proj_tiles(Q, 128), 128, 0, st>>>(x, ent, bias, tgt, (int)Q, k, thr);
   KGE_CHECK_LAUNCH("proj_target_kernel");
-  if (int rc = launch_gemm<EPI_COUNT>(proj_plan_count(x, ent, bias, Q, N, k, thr, counts, direction), st,
-                                      "proj_gemm_kernel<count>")) return rc;
+  if (int rc = launch_gemm<EPI_COUNT>(proj_plan_count(x, ent, bias, Q, N, k, thr, counts, direction,
+                                                      pick_tile(Q, N)), st, "proj_gemm_kernel<count>")) return rc;
   if (filt_ptr && filt_idx && filt_nnz > 0) {
     proj_filter_kernel<<<(unsigned)Q, 128, 0, st>>>(x, ent, bias, tgt, filt_ptr, filt_idx, k, thr, counts,
                                                     2 * direction);

@@ -39,35 +39,41 @@ struct ProjGemm {
 
 // Staging of a [ROWS x PBK] operand tile, k-major in shared memory (S[kk][row]), in two halves
 // so that the global loads of chunk c+1 are in flight while chunk c is multiplied: fetch() reads
-// this thread's 4 elements into registers, place() writes them to shared memory.  Rows / k beyond
-// the operand read as 0 (an exact identity for the fma chain).
-struct ProjRegs { float v[4]; };
+// this thread's ROWS/16 elements into registers, place() writes them to shared memory.  Rows / k
+// beyond the operand read as 0 (an exact identity for the fma chain).
+template <int ROWS>
+struct ProjRegs { float v[ROWS / 16]; };
 
 template <int ROWS>
-KGE_DEV void proj_fetch_tile(ProjRegs& R, const float* __restrict__ P, const float* __restrict__ Pp,
+KGE_DEV void proj_fetch_tile(ProjRegs<ROWS>& R, const float* __restrict__ P, const float* __restrict__ Pp,
                              long long sr, long long sk, bool usevec, int r0, int nrows, int k0,
                              int kend, int tid) {
-  static_assert(ROWS * PBK == 4 * PTHREADS, "four elements per thread");
-  if (usevec) {  // sk == 1, rows 16-byte aligned: thread -> (row, 4 consecutive k), one 16-byte load
-    const int rr = tid >> 2, kq = (tid & 3) * 4;
-    const int gr = r0 + rr, gk = k0 + kq;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (gr < nrows && gk < kend) {
-      const float* src = P + (long long)gr * sr + gk;
-      if (gk + 3 < kend) {
-        v = __ldg(reinterpret_cast<const float4*>(src));
-      } else {
-        v.x = __ldg(src);
-        if (gk + 1 < kend) v.y = __ldg(src + 1);
-        if (gk + 2 < kend) v.z = __ldg(src + 2);
+  static_assert(ROWS % 64 == 0, "whole 16-byte loads per thread");
+  constexpr int PER = ROWS / 16;   // elements per thread (ROWS * PBK / PTHREADS)
+  if (usevec) {  // sk == 1, rows 16-byte aligned: 16-byte load f -> (row f/4, 4 consecutive k)
+#pragma unroll
+    for (int u = 0; u < PER / 4; ++u) {
+      const int f = tid + u * PTHREADS;
+      const int rr = f >> 2, kq = (f & 3) * 4;
+      const int gr = r0 + rr, gk = k0 + kq;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gr < nrows && gk < kend) {
+        const float* src = P + (long long)gr * sr + gk;
+        if (gk + 3 < kend) {
+          v = __ldg(reinterpret_cast<const float4*>(src));
+        } else {
+          v.x = __ldg(src);
+          if (gk + 1 < kend) v.y = __ldg(src + 1);
+          if (gk + 2 < kend) v.z = __ldg(src + 2);
+        }
       }
+      R.v[4 * u + 0] = v.x; R.v[4 * u + 1] = v.y; R.v[4 * u + 2] = v.z; R.v[4 * u + 3] = v.w;
     }
-    R.v[0] = v.x; R.v[1] = v.y; R.v[2] = v.z; R.v[3] = v.w;
     return;
   }
   const bool kcontig = (sk == 1);
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
+  for (int u = 0; u < PER; ++u) {
     const int i = tid + u * PTHREADS;
     int rr, kk;
     if (kcontig) { kk = i % PBK; rr = i / PBK; } else { rr = i % ROWS; kk = i / ROWS; }
@@ -83,15 +89,21 @@ KGE_DEV void proj_fetch_tile(ProjRegs& R, const float* __restrict__ P, const flo
 }
 
 template <int ROWS>
-KGE_DEV void proj_place_tile(float (*S)[ROWS + 4], const ProjRegs& R, long long sk, bool usevec, int tid) {
+KGE_DEV void proj_place_tile(float (*S)[ROWS + 4], const ProjRegs<ROWS>& R, long long sk, bool usevec, int tid) {
+  constexpr int PER = ROWS / 16;
   if (usevec) {
-    const int rr = tid >> 2, kq = (tid & 3) * 4;
-    S[kq + 0][rr] = R.v[0]; S[kq + 1][rr] = R.v[1]; S[kq + 2][rr] = R.v[2]; S[kq + 3][rr] = R.v[3];
+#pragma unroll
+    for (int u = 0; u < PER / 4; ++u) {
+      const int f = tid + u * PTHREADS;
+      const int rr = f >> 2, kq = (f & 3) * 4;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) S[kq + e][rr] = R.v[4 * u + e];
+    }
     return;
   }
   const bool kcontig = (sk == 1);
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
+  for (int u = 0; u < PER; ++u) {
     const int i = tid + u * PTHREADS;
     int rr, kk;
     if (kcontig) { kk = i % PBK; rr = i / PBK; } else { rr = i % ROWS; kk = i / ROWS; }
@@ -99,58 +111,71 @@ KGE_DEV void proj_place_tile(float (*S)[ROWS + 4], const ProjRegs& R, long long 
   }
 }
 
-template <int EPI>
+// Thread (ty, tx) of the 16x16 thread grid owns TM x TN outputs of the (16*TM) x (16*TN) CTA tile,
+// in groups of 4 consecutive rows / columns 64 apart: row(i) = (i/4)*64 + ty*4 + i%4, likewise
+// col(j) with tx — so every shared-memory operand read is one conflict-free 16-byte load per group
+// and a half-warp covers 64 consecutive output columns.
+template <int EPI, int TM, int TN>
 __global__ void __launch_bounds__(PTHREADS) proj_gemm_kernel(const ProjGemm g) {
-  __shared__ __align__(16) float As[PBK][PBM + 4];
-  __shared__ __align__(16) float Bs[PBK][PBN + 4];
+  constexpr int BM = 16 * TM, BN = 16 * TN;
+  __shared__ __align__(16) float As[PBK][BM + 4];
+  __shared__ __align__(16) float Bs[PBK][BN + 4];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int m0 = blockIdx.y * PBM, n0 = blockIdx.x * PBN;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int kbeg = blockIdx.z * g.klen;
   const int kend = min(g.K, kbeg + g.klen);
   const bool avec = g.avec && !g.Ap, bvec = g.bvec != 0;
-  float acc[4][4];
+  float acc[TM][TN];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < TM; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-  ProjRegs ra, rb;
+  ProjRegs<BM> ra;
+  ProjRegs<BN> rb;
   if (kbeg < kend) {
-    proj_fetch_tile<PBM>(ra, g.A, g.Ap, g.sAm, g.sAk, avec, m0, g.M, kbeg, kend, tid);
-    proj_fetch_tile<PBN>(rb, g.B, nullptr, g.sBn, g.sBk, bvec, n0, g.N, kbeg, kend, tid);
+    proj_fetch_tile<BM>(ra, g.A, g.Ap, g.sAm, g.sAk, avec, m0, g.M, kbeg, kend, tid);
+    proj_fetch_tile<BN>(rb, g.B, nullptr, g.sBn, g.sBk, bvec, n0, g.N, kbeg, kend, tid);
   }
   for (int k0 = kbeg; k0 < kend; k0 += PBK) {
-    proj_place_tile<PBM>(As, ra, g.sAk, avec, tid);
-    proj_place_tile<PBN>(Bs, rb, g.sBk, bvec, tid);
+    proj_place_tile<BM>(As, ra, g.sAk, avec, tid);
+    proj_place_tile<BN>(Bs, rb, g.sBk, bvec, tid);
     __syncthreads();
     if (k0 + PBK < kend) {  // next chunk's loads overlap this chunk's multiply
-      proj_fetch_tile<PBM>(ra, g.A, g.Ap, g.sAm, g.sAk, avec, m0, g.M, k0 + PBK, kend, tid);
-      proj_fetch_tile<PBN>(rb, g.B, nullptr, g.sBn, g.sBk, bvec, n0, g.N, k0 + PBK, kend, tid);
+      proj_fetch_tile<BM>(ra, g.A, g.Ap, g.sAm, g.sAk, avec, m0, g.M, k0 + PBK, kend, tid);
+      proj_fetch_tile<BN>(rb, g.B, nullptr, g.sBn, g.sBk, bvec, n0, g.N, k0 + PBK, kend, tid);
     }
 #pragma unroll
     for (int kk = 0; kk < PBK; ++kk) {
-      const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-      const float av[4] = {a4.x, a4.y, a4.z, a4.w};
-      const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
+      float av[TM], bv[TN];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int gi = 0; gi < TM / 4; ++gi) {
+        const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][gi * 64 + ty * 4]);
+        av[4 * gi + 0] = a4.x; av[4 * gi + 1] = a4.y; av[4 * gi + 2] = a4.z; av[4 * gi + 3] = a4.w;
+      }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = ffma(av[i], bv[j], acc[i][j]);
+      for (int gj = 0; gj < TN / 4; ++gj) {
+        const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][gj * 64 + tx * 4]);
+        bv[4 * gj + 0] = b4.x; bv[4 * gj + 1] = b4.y; bv[4 * gj + 2] = b4.z; bv[4 * gj + 3] = b4.w;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = ffma(av[i], bv[j], acc[i][j]);
     }
     __syncthreads();
   }
 
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int gm = m0 + ty * 4 + i;
+  for (int i = 0; i < TM; ++i) {
+    const int gm = m0 + (i / 4) * 64 + ty * 4 + (i % 4);
     if (EPI == EPI_COUNT) {
       int c = 0;
       if (gm < g.M) {
         const float th = __ldg(g.thr + gm);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int gn = n0 + tx * 4 + j;
+        for (int j = 0; j < TN; ++j) {
+          const int gn = n0 + (j / 4) * 64 + tx * 4 + (j % 4);
           if (gn < g.N) {
             float l = acc[i][j];
             if (g.bias) l = fadd(l, __ldg(g.bias + gn));
@@ -170,8 +195,8 @@ __global__ void __launch_bounds__(PTHREADS) proj_gemm_kernel(const ProjGemm g) {
     } else {
       if (gm >= g.M) continue;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int gn = n0 + tx * 4 + j;
+      for (int j = 0; j < TN; ++j) {
+        const int gn = n0 + (j / 4) * 64 + tx * 4 + (j % 4);
         if (gn >= g.N) continue;
         float* dst = g.C + (long long)blockIdx.z * g.zstride + (long long)gm * g.ldc + gn;
         if (EPI == EPI_STORE) {
@@ -273,7 +298,19 @@ proj_colsum_kernel(const float* __restrict__ gp, const float* __restrict__ preds
 
 // ---- launch plans: plain C++ (shared by the C-ABI launchers in kge_proj.cu and by the CPU
 // emulation test tests/emu/, which runs these kernels thread by thread on the host) ------------
-struct ProjLaunch { ProjGemm g; unsigned gx, gy, gz; };
+// CTA tile variants of proj_gemm_kernel: rows x columns (thread tile = rows/16 x columns/16)
+enum { PROJ_TILE_64x64 = 0, PROJ_TILE_64x128 = 1, PROJ_TILE_128x128 = 2, PROJ_TILE_AUTO = -1 };
+inline int proj_tile_rows(int tile) { return tile == PROJ_TILE_128x128 ? 128 : 64; }
+inline int proj_tile_cols(int tile) { return tile == PROJ_TILE_64x64 ? 64 : 128; }
+// Large tiles halve the shared-memory operand traffic per fma (a 16-byte read feeds 32 fma instead
+// of 16) but need enough CTAs to fill 148 SMs (>= 2 waves of 2 resident CTAs).
+inline int proj_pick_tile(long long M, long long N, int sms) {
+  if (((M + 127) / 128) * ((N + 127) / 128) >= 2ll * sms) return PROJ_TILE_128x128;
+  if (((M + 63) / 64) * ((N + 127) / 128) >= 2ll * sms) return PROJ_TILE_64x128;
+  return PROJ_TILE_64x64;
+}
+
+struct ProjLaunch { ProjGemm g; unsigned gx, gy, gz; int tile; };
 
 inline int proj_vec_ok(const float* p, long long row_stride, long long k_stride) {
   return k_stride == 1 && (row_stride % 4 == 0) && (((uintptr_t)p & 15) == 0);
@@ -282,21 +319,23 @@ inline unsigned proj_tiles(long long n, int tile) { return (unsigned)((n + tile 
 
 // preds[B,N] = sigmoid(x[B,k] . ent[N,k]^T + bias)   — also the frame of the counting launch
 inline ProjLaunch proj_plan_fwd(const float* x, const float* ent, const float* bias, long long B,
-                                long long N, int k, float* preds) {
+                                long long N, int k, float* preds, int tile = PROJ_TILE_64x64) {
   ProjLaunch L{};
+  L.tile = tile;
   ProjGemm& g = L.g;
   g.A = x; g.sAm = k; g.sAk = 1; g.Ap = nullptr;
   g.B = ent; g.sBn = k; g.sBk = 1;
   g.M = (int)B; g.N = (int)N; g.K = k; g.klen = (int)proj_tiles(k, PBK) * PBK;
   g.avec = proj_vec_ok(x, k, 1); g.bvec = proj_vec_ok(ent, k, 1);
   g.C = preds; g.ldc = N; g.bias = bias; g.act = ACT_SIGMOID;
-  L.gx = proj_tiles(N, PBN); L.gy = proj_tiles(B, PBM); L.gz = 1;
+  L.gx = proj_tiles(N, proj_tile_cols(tile)); L.gy = proj_tiles(B, proj_tile_rows(tile)); L.gz = 1;
   return L;
 }
 
 inline ProjLaunch proj_plan_count(const float* x, const float* ent, const float* bias, long long Q,
-                                  long long N, int k, const float* thr, int* counts, int direction) {
-  ProjLaunch L = proj_plan_fwd(x, ent, bias, Q, N, k, nullptr);
+                                  long long N, int k, const float* thr, int* counts, int direction,
+                                  int tile = PROJ_TILE_64x64) {
+  ProjLaunch L = proj_plan_fwd(x, ent, bias, Q, N, k, nullptr, tile);
   L.g.thr = thr; L.g.counts = counts; L.g.coff = 2 * direction;
   return L;
 }

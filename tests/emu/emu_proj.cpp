@@ -23,14 +23,19 @@ using namespace kge;
 
 template <int EPI>
 static void run_gemm(const ProjLaunch& L) {
-  cuda_emu::launch(dim3(L.gx, L.gy, L.gz), dim3(PTHREADS), [&] { proj_gemm_kernel<EPI>(L.g); });
+  const dim3 grid(L.gx, L.gy, L.gz);
+  switch (L.tile) {
+    case PROJ_TILE_128x128: cuda_emu::launch(grid, dim3(PTHREADS), [&] { proj_gemm_kernel<EPI, 8, 8>(L.g); }); break;
+    case PROJ_TILE_64x128: cuda_emu::launch(grid, dim3(PTHREADS), [&] { proj_gemm_kernel<EPI, 4, 8>(L.g); }); break;
+    default: cuda_emu::launch(grid, dim3(PTHREADS), [&] { proj_gemm_kernel<EPI, 4, 4>(L.g); }); break;
+  }
 }
 
 extern "C" {
 
 int emu_proj_tail_fwd(const float* x, const float* ent, const float* bias, int64_t B, int64_t N, int32_t k,
-                      float* preds) {
-  run_gemm<EPI_STORE>(proj_plan_fwd(x, ent, bias, B, N, k, preds));
+                      float* preds, int32_t tile) {
+  run_gemm<EPI_STORE>(proj_plan_fwd(x, ent, bias, B, N, k, preds, tile));
   return 0;
 }
 
@@ -57,10 +62,10 @@ int emu_proj_bce(const float* preds, const float* labels, int64_t B, int64_t N, 
 
 int emu_proj_rank(const float* x, const float* ent, const float* bias, int64_t Q, int64_t N, int32_t k,
                   const int64_t* tgt, const int64_t* filt_ptr, const int64_t* filt_idx, int64_t filt_nnz,
-                  int32_t direction, int32_t* counts, float* thr) {
+                  int32_t direction, int32_t* counts, float* thr, int32_t tile) {
   cuda_emu::launch(dim3(proj_tiles(Q, 128)), dim3(128),
                    [&] { proj_target_kernel(x, ent, bias, tgt, (int)Q, k, thr); });
-  run_gemm<EPI_COUNT>(proj_plan_count(x, ent, bias, Q, N, k, thr, counts, direction));
+  run_gemm<EPI_COUNT>(proj_plan_count(x, ent, bias, Q, N, k, thr, counts, direction, tile));
   if (filt_ptr && filt_idx && filt_nnz > 0)
     cuda_emu::launch(dim3((unsigned)Q), dim3(128), [&] {
       proj_filter_kernel(x, ent, bias, tgt, filt_ptr, filt_idx, k, thr, counts, 2 * direction);

@@ -52,11 +52,13 @@ def _case(B, N, k, seed, bias=True):
 SHAPES = [(70, 131, 48, True), (5, 64, 50, True), (64, 65, 7, False), (1, 200, 16, True), (33, 1, 100, False)]
 
 
-@pytest.mark.parametrize("B,N,k,bias", SHAPES)
-def test_emulated_forward_is_bit_exact(emu, B, N, k, bias):
+@pytest.mark.parametrize("tile", [0, 1, 2], ids=["64x64", "64x128", "128x128"])
+@pytest.mark.parametrize("B,N,k,bias", SHAPES + [(130, 140, 20, True)])
+def test_emulated_forward_is_bit_exact(emu, B, N, k, bias, tile):
     x, ent, b = _case(B, N, k, seed=B * 1000 + N, bias=bias)
     got = np.full((B, N), np.nan, dtype=np.float32)
-    emu.emu_proj_tail_fwd(_p(x), _p(ent), _p(b), ctypes.c_int64(B), ctypes.c_int64(N), ctypes.c_int32(k), _p(got))
+    emu.emu_proj_tail_fwd(_p(x), _p(ent), _p(b), ctypes.c_int64(B), ctypes.c_int64(N), ctypes.c_int32(k), _p(got),
+                          ctypes.c_int32(tile))
     want = oracle.proj_tail_fwd(x, ent, b)
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
 
@@ -70,12 +72,14 @@ def test_emulated_forward_unaligned_operands(emu):
     xo[:] = x
     assert xo.ctypes.data % 16 != 0
     got = np.empty((B, N), dtype=np.float32)
-    emu.emu_proj_tail_fwd(_p(xo), _p(ent), _p(b), ctypes.c_int64(B), ctypes.c_int64(N), ctypes.c_int32(k), _p(got))
+    emu.emu_proj_tail_fwd(_p(xo), _p(ent), _p(b), ctypes.c_int64(B), ctypes.c_int64(N), ctypes.c_int32(k), _p(got),
+                          ctypes.c_int32(2))
     assert np.array_equal(got, oracle.proj_tail_fwd(x, ent, b))
 
 
-@pytest.mark.parametrize("B,N,k,bias", SHAPES[:4])
-def test_emulated_rank_counts(emu, B, N, k, bias):
+@pytest.mark.parametrize("tile", [0, 1, 2], ids=["64x64", "64x128", "128x128"])
+@pytest.mark.parametrize("B,N,k,bias", SHAPES[:4] + [(130, 140, 20, True)])
+def test_emulated_rank_counts(emu, B, N, k, bias, tile):
     x, ent, b = _case(B, N, k, seed=B * 77 + N, bias=bias)
     rng = np.random.RandomState(B + N)
     tgt = rng.randint(N, size=B).astype(np.int64)
@@ -93,7 +97,8 @@ def test_emulated_rank_counts(emu, B, N, k, bias):
         got = np.zeros((B, 4), dtype=np.int32)
         thr = np.zeros(B, dtype=np.float32)
         emu.emu_proj_rank(_p(x), _p(ent), _p(b), ctypes.c_int64(B), ctypes.c_int64(N), ctypes.c_int32(k), _p(tgt),
-                          _p(ptr), _p(idx), ctypes.c_int64(len(idx)), ctypes.c_int32(direction), _p(got), _p(thr))
+                          _p(ptr), _p(idx), ctypes.c_int64(len(idx)), ctypes.c_int32(direction), _p(got), _p(thr),
+                          ctypes.c_int32(tile))
         want = oracle.proj_rank(x, ent, b, tgt, (ptr, idx), direction)
         assert np.array_equal(got, want)
         # and the counts are what counting over the forward matrix gives

@@ -37,8 +37,14 @@ SHAPES = [(70, 131, 48, True), (5, 64, 50, True), (64, 65, 7, False), (1, 200, 1
           (128, 14541, 200, True), (257, 1000, 33, True)]
 
 
+TILES = [None, "0", "1", "2"]   # KGE_PROJ_TILE: library heuristic, 64x64, 64x128, 128x128 CTA tiles
+
+
+@pytest.mark.parametrize("tile", TILES, ids=lambda v: "tile-%s" % v)
 @pytest.mark.parametrize("B,N,k,bias", SHAPES, ids=lambda v: str(v))
-def test_tail_forward_bit_exact_vs_oracle(B, N, k, bias):
+def test_tail_forward_bit_exact_vs_oracle(B, N, k, bias, tile, monkeypatch):
+    if tile is not None:
+        monkeypatch.setenv("KGE_PROJ_TILE", tile)
     L = _L()
     x, ent, b = _case(B, N, k, seed=B * 1000 + N, bias=bias)
     got = L.proj_tail_fwd(_cuda(x), _cuda(ent), _cuda(b) if bias else None).cpu().numpy()
@@ -68,8 +74,11 @@ def test_tail_forward_vs_torch_fp32():
     assert ((got.double() - want).abs() / want).max().item() < 1e-5
 
 
+@pytest.mark.parametrize("tile", TILES, ids=lambda v: "tile-%s" % v)
 @pytest.mark.parametrize("B,N,k,bias", SHAPES[:4] + [(300, 14541, 200, True)], ids=lambda v: str(v))
-def test_rank_counts_exact_vs_oracle(B, N, k, bias):
+def test_rank_counts_exact_vs_oracle(B, N, k, bias, tile, monkeypatch):
+    if tile is not None:
+        monkeypatch.setenv("KGE_PROJ_TILE", tile)
     L = _L()
     x, ent, b = _case(B, N, k, seed=B * 77 + N, bias=bias)
     rng = np.random.RandomState(B + N)

@@ -131,6 +131,29 @@ def main():
             ms = time_ms(lambda: ev.rank_triples(hs, rs, ts), args.reps, flush)
         emit(kernel="Evaluator.rank_triples ConvE e2e (host ids in, ranks out)", case="eval Q=512", ms=ms,
              scored_per_s=2 * 512 * N / ms * 1e3)
+        # training step end to end (adam, B=128, label smoothing 0.1): the reference's data path (ids +
+        # two dense [B,N] label matrices from the host every step, generator.py:160-236) vs label rows
+        # built on the device from CSRs (pykg2vec_b200.generator.Generator)
+        from pykg2vec_b200.generator import Generator
+        from pykg2vec_b200.synthetic import SyntheticConfig, SyntheticKnowledgeGraph
+        from pykg2vec_b200.trainer import Trainer
+        kg = SyntheticKnowledgeGraph.shaped_like("fb15k_237", scale=0.2)
+        cfg = SyntheticConfig(kg, device="cuda", optimizer="adam", learning_rate=0.003, batch_size=128, neg_rate=0,
+                              hidden_size=K, hidden_size_1=K1, lmbda=0.1, input_dropout=0.2, feature_map_dropout=0.2,
+                              hidden_dropout=0.3, label_smoothing=0.1)
+        tmodel = import_model("conve")(**cfg.__dict__)
+        tr = Trainer(tmodel, cfg)
+        tr.build_model()
+        gen = Generator(tmodel, cfg, seed=0)
+        gen.start_one_epoch(10 ** 6)
+        ms = time_ms(lambda: tr.train_batch_device(next(gen)), args.reps, flush)
+        emit(kernel="ConvE train step, device label rows (Generator -> train_batch_device)", case="train B=128", ms=ms,
+             scored_per_s=2 * 128 * N / ms * 1e3)
+        hb, rb, tb, lt, lh = (v.cpu() for v in next(gen))
+        host = [hb.numpy(), rb.numpy(), tb.numpy(), lt, lh]
+        ms = time_ms(lambda: tr.train_batch(host), args.reps, flush)
+        emit(kernel="ConvE train step, host dense labels (reference data path: 2*B*N floats H2D)", case="train B=128",
+             ms=ms, scored_per_s=2 * 128 * N / ms * 1e3, h2d_bytes=tr.last_h2d_bytes)
     if args.out:
         with open(args.out, "w") as f:
             for l in lines:

@@ -235,6 +235,16 @@ int kge_proj_tail_bwd(const float* grad_preds, const float* preds, const float* 
 int kge_proj_bce(const float* preds, const float* labels, int64_t B, int64_t N, float label_scale,
                  float label_shift, float grad_scale, float* loss_out, float* grad_preds, void* stream);
 
+/* The dense label matrices of a PROJECTION_BASED batch, built on the device: what
+ * process_function_multiclass (pykg2vec/data/generator.py:160-236) assembles on the host per batch with
+ * torch.sparse(...).to_dense() and ships as two [B, N] float tensors.  labels[b, :] = 0 except 1.0 at the
+ * entities idx[ptr[row] .. ptr[row+1]) with row = rows[b] (rows == NULL: row = b).  ptr/idx are a CSR of
+ * hr_t_train (or tr_h_train) over its distinct keys, rows[b] the key row of training triple b — so a
+ * batch moves B ids instead of B*N floats over PCIe.  (The -1 entries the reference adds when
+ * neg_rate > 0, used by ProjE only, are not produced.) */
+int kge_proj_labels(const int64_t* rows, const int64_t* ptr, const int64_t* idx, int64_t B, int64_t N,
+                    float* labels, void* stream);
+
 /* predict_tail_rank / predict_head_rank (projection.py:119-125: topk of -preds over all N entities,
  * one query at a time) + MetricCalculator.get_*_rank (evaluator.py:70-123), for Q queries at once and
  * without materialising the [Q,N] prediction matrix:

@@ -29,7 +29,7 @@ EXPORTS = [
     "kge_train_pairwise_hinge_sgd", "kge_optim_apply_rows",
     "kge_rank_workspace_bytes", "kge_rank_1vsall",
     "kge_tripleset_capacity", "kge_tripleset_build", "kge_sample_negatives",
-    "kge_proj_tail_fwd", "kge_proj_tail_bwd", "kge_proj_bce", "kge_proj_rank_workspace_bytes", "kge_proj_rank",
+    "kge_proj_tail_fwd", "kge_proj_tail_bwd", "kge_proj_bce", "kge_proj_rank_workspace_bytes", "kge_proj_rank", "kge_proj_labels",
     "kge_conve_trunk_workspace_bytes", "kge_conve_trunk_fwd",
 ]
 
@@ -341,6 +341,19 @@ def proj_bce(preds, labels, label_scale=1.0, label_shift=0.0, grad_scale=1.0, wa
                              ctypes.c_float(label_scale), ctypes.c_float(label_shift), ctypes.c_float(grad_scale),
                              _ptr(loss), _ptr(g), _stream()), "kge_proj_bce")
     return loss, g
+
+
+def proj_labels(rows, ptr, idx, B, N, out=None):
+    """Dense [B,N] fp32 label rows (1.0 at the known positives) from a device CSR; rows = CSR row of
+    each batch element (None: row b)."""
+    ptr, idx = _dev_i64(ptr, "ptr"), _dev_i64(idx, "idx")
+    if rows is not None and _dev_i64(rows, "rows").numel() != B:
+        raise KgeError("rows must hold one CSR row id per batch element")
+    if out is None:
+        out = torch.empty((B, N), dtype=torch.float32, device=ptr.device)
+    check(lib().kge_proj_labels(_ptr(rows), _ptr(ptr), _ptr(idx), ctypes.c_int64(B), ctypes.c_int64(N),
+                                _ptr(_dev_f32(out, "labels")), _stream()), "kge_proj_labels")
+    return out
 
 
 def proj_rank(x, ent, bias, tgt, filt=None, direction=0, counts=None, workspace=None):

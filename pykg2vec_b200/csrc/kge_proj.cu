@@ -90,6 +90,18 @@ int kge_proj_bce(const float* preds, const float* labels, int64_t B, int64_t N, 
   return KGE_OK;
 }
 
+int kge_proj_labels(const int64_t* rows, const int64_t* ptr, const int64_t* idx, int64_t B, int64_t N,
+                    float* labels, void* stream) {
+  if (!ptr || !idx || !labels) { set_error("kge_proj_labels: null pointer"); return KGE_EINVAL; }
+  if (B < 0 || N <= 0 || B > 0x7fffffffll) { set_error("kge_proj_labels: bad shape"); return KGE_EINVAL; }
+  if (B == 0) return KGE_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  KGE_CUDA_OK(cudaMemsetAsync(labels, 0, sizeof(float) * (size_t)B * (size_t)N, st));
+  proj_labels_kernel<<<(unsigned)B, 128, 0, st>>>(rows, ptr, idx, N, labels);
+  KGE_CHECK_LAUNCH("proj_labels_kernel");
+  return KGE_OK;
+}
+
 int64_t kge_proj_rank_workspace_bytes(int64_t Q) { return (Q > 0 ? Q : 1) * (int64_t)sizeof(float); }
 
 int kge_proj_rank(const float* x, const float* ent, const float* bias, int64_t Q, int64_t N, int32_t k,

@@ -296,6 +296,18 @@ proj_colsum_kernel(const float* __restrict__ gp, const float* __restrict__ preds
   gb[n] += acc;
 }
 
+// Dense multi-class label rows from CSR rows of known positives: labels[b, idx[p]] = 1 for p in
+// [ptr[row], ptr[row+1]), row = rows[b] (or b when rows is null); the buffer is zero-filled before.
+// What process_function_multiclass builds on the host per batch (generator.py:160-236, neg_rate 0).
+__global__ void __launch_bounds__(128)
+proj_labels_kernel(const int64_t* __restrict__ rows, const int64_t* __restrict__ ptr,
+                   const int64_t* __restrict__ idx, long long N, float* __restrict__ labels) {
+  const long long b = blockIdx.x;
+  const int64_t row = rows ? __ldg(rows + b) : b;
+  const int64_t beg = __ldg(ptr + row), end = __ldg(ptr + row + 1);
+  for (int64_t p = beg + threadIdx.x; p < end; p += blockDim.x) labels[b * N + __ldg(idx + p)] = 1.0f;
+}
+
 // ---- launch plans: plain C++ (shared by the C-ABI launchers in kge_proj.cu and by the CPU
 // emulation test tests/emu/, which runs these kernels thread by thread on the host) ------------
 // CTA tile variants of proj_gemm_kernel: rows x columns (thread tile = rows/16 x columns/16)

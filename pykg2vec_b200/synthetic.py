@@ -53,6 +53,14 @@ class SyntheticKnowledgeGraph:
                     tr_h.setdefault((int(t), int(r)), set()).add(int(h))
             self._cache["hr_t"], self._cache["tr_h"] = hr_t, tr_h
             return self._cache[key]
+        elif key in ("hr_t_train", "tr_h_train"):
+            # training split only, as kgcontroller.py builds them for the multi-class label rows
+            hr_t, tr_h = {}, {}
+            for h, r, t in self.arrays["train"]:
+                hr_t.setdefault((int(h), int(r)), set()).add(int(t))
+                tr_h.setdefault((int(t), int(r)), set()).add(int(h))
+            self._cache["hr_t_train"], self._cache["tr_h_train"] = hr_t, tr_h
+            return self._cache[key]
         else:
             raise ValueError("Unknown cache data key %s" % key)
         self._cache[key] = val

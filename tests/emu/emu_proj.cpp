@@ -73,6 +73,13 @@ int emu_proj_rank(const float* x, const float* ent, const float* bias, int64_t Q
   return 0;
 }
 
+int emu_proj_labels(const int64_t* rows, const int64_t* ptr, const int64_t* idx, int64_t B, int64_t N,
+                    float* labels) {
+  memset(labels, 0, sizeof(float) * (size_t)B * (size_t)N);
+  cuda_emu::launch(dim3((unsigned)B), dim3(128), [&] { proj_labels_kernel(rows, ptr, idx, N, labels); });
+  return 0;
+}
+
 int emu_conve_trunk_fwd(const kge_conve_t* p, const int64_t* e, const int64_t* r, int64_t Q, float* x,
                         float* feat) {
   const int k = p->hidden_size, h1 = p->hidden_size_1, h2 = k / h1;

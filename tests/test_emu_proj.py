@@ -159,3 +159,23 @@ def test_emulated_conve_trunk(emu, name, Q):
     want = oracle.conve_trunk_fwd(state, k, k1, e, r)
     assert np.array_equal(x.view(np.uint32), want.view(np.uint32))
     assert np.abs(x - g["x_head"][:Q]).max() <= 1e-5
+
+
+@pytest.mark.parametrize("with_rows", [False, True])
+def test_emulated_label_rows(emu, with_rows):
+    rng = np.random.RandomState(9)
+    K, N, B = 11, 300, 7
+    sizes = rng.randint(0, 200, size=K)
+    sizes[3] = 0
+    ptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    idx = np.concatenate([rng.choice(N, size=n, replace=False) for n in sizes]).astype(np.int64)
+    rows = rng.randint(K, size=B).astype(np.int64) if with_rows else None
+    if not with_rows:
+        B = K
+    got = np.full((B, N), np.nan, dtype=np.float32)
+    emu.emu_proj_labels(_p(rows), _p(ptr), _p(idx), ctypes.c_int64(B), ctypes.c_int64(N), _p(got))
+    want = np.zeros((B, N), dtype=np.float32)
+    for b in range(B):
+        row = rows[b] if with_rows else b
+        want[b, idx[ptr[row]:ptr[row + 1]]] = 1.0
+    assert np.array_equal(got, want)

@@ -298,3 +298,54 @@ def test_conve_trainer_batches_reduce_the_loss():
     losses = [tr.train_batch([h, r, t, torch.from_numpy(hr_t), torch.from_numpy(tr_h)]) for _ in range(8)]
     assert all(np.isfinite(losses)) and losses[-1] < losses[0]
     assert tr.last_h2d_bytes >= 2 * B * N * 4
+
+
+@pytest.mark.parametrize("with_rows", [False, True])
+def test_label_rows_kernel(with_rows):
+    L = _L()
+    rng = np.random.RandomState(9)
+    K, N, B = 40, 14541, 33
+    sizes = rng.randint(0, 600, size=K)
+    sizes[3] = 0
+    ptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    idx = np.concatenate([rng.choice(N, size=n, replace=False) for n in sizes]).astype(np.int64)
+    rows = rng.randint(K, size=B).astype(np.int64) if with_rows else None
+    if not with_rows:
+        B = K
+    got = L.proj_labels(_cuda(rows) if with_rows else None, _cuda(ptr), _cuda(idx), B, N).cpu().numpy()
+    want = np.zeros((B, N), dtype=np.float32)
+    for b in range(B):
+        row = rows[b] if with_rows else b
+        want[b, idx[ptr[row]:ptr[row + 1]]] = 1.0
+    assert np.array_equal(got, want)
+
+
+def test_conve_epoch_on_device_generator():
+    """Generator (device label rows) -> Trainer.train_model_epoch -> batched Evaluator, ConvE, adam"""
+    from pykg2vec_b200 import import_model
+    from pykg2vec_b200.generator import Generator
+    from pykg2vec_b200.synthetic import SyntheticConfig, SyntheticKnowledgeGraph
+    from pykg2vec_b200.trainer import Trainer
+    kg = SyntheticKnowledgeGraph(200, 5, 2000, 60, 60, seed=3)
+    cfg = SyntheticConfig(kg, device="cuda", optimizer="adam", learning_rate=0.003, batch_size=64, neg_rate=0,
+                          hidden_size=48, hidden_size_1=8, lmbda=0.1, input_dropout=0.0, feature_map_dropout=0.0,
+                          hidden_dropout=0.0, label_smoothing=0.1, test_num=50)
+    torch.manual_seed(0)
+    model = import_model("conve")(**cfg.__dict__)
+    tr = Trainer(model, cfg)
+    tr.build_model()
+    gen = Generator(model, cfg, seed=1)
+    # the label rows of a batch are the dense hr_t_train / tr_h_train rows of its triples
+    gen.start_one_epoch(1)
+    h, r, t, hr_t, tr_h = next(gen)
+    known = kg.read_cache_data("hr_t_train")
+    hn, rn = h.cpu().numpy(), r.cpu().numpy()
+    lab = hr_t.cpu().numpy()
+    assert lab.shape == (64, 200) and tr_h.shape == (64, 200)
+    for i in range(64):
+        assert set(np.nonzero(lab[i])[0].tolist()) == known[(int(hn[i]), int(rn[i]))]
+    losses = [tr.train_model_epoch(gen, num_batch=10) for _ in range(4)]
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+    model.eval()
+    scores = tr.evaluator.mini_test(epoch=0)
+    assert set(scores) == {"mr", "fmr", "mrr", "fmrr"} and 1.0 <= scores["fmr"] <= scores["mr"] <= 200.0

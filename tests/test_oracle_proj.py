@@ -126,3 +126,17 @@ def test_conve_mirror_contract_errors():
         m(e, r, direction="sideways")
     with pytest.raises(_lib.KgeError, match="no CPU"):      # no CPU fallback for the product path
         m(e, r, direction="tail")
+
+
+def test_label_csr_host_logic():
+    """Generator's CSR of hr_t_train / tr_h_train over distinct keys + row of every training triple"""
+    from pykg2vec_b200.generator import _label_csr
+    from pykg2vec_b200.synthetic import SyntheticKnowledgeGraph
+    kg = SyntheticKnowledgeGraph(50, 3, 400, 10, 10, seed=1)
+    arr = kg.arrays["train"]
+    for key, a, b in (("hr_t_train", 0, 1), ("tr_h_train", 2, 1)):
+        known = kg.read_cache_data(key)
+        rows, ptr, idx = (x.numpy() for x in _label_csr(known, arr[:, a], arr[:, b], "cpu"))
+        assert len(ptr) - 1 == len(known) and ptr[-1] == len(idx) == sum(len(v) for v in known.values())
+        for i in range(len(arr)):
+            assert set(idx[ptr[rows[i]]:ptr[rows[i] + 1]].tolist()) == known[(int(arr[i, a]), int(arr[i, b]))]

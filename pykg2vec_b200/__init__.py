@@ -37,6 +37,7 @@ MODEL_MAP = {
     "simple_ignr": ("pykg2vec_b200.pointwise", "SimplE_ignr"),
     "convkb": ("pykg2vec_b200.pointwise", "ConvKB"),
     "conve": ("pykg2vec_b200.projection", "ConvE"),
+    "tucker": ("pykg2vec_b200.projection", "TuckER"),
 }
 
 

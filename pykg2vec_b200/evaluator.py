@@ -293,8 +293,9 @@ class Evaluator:
             counts = torch.zeros((q, 4), dtype=torch.int32, device=dev)
             x_t = self.model.proj_query(h, r, direction="tail").contiguous()
             x_h = self.model.proj_query(t, r, direction="head").contiguous()
-            _lib.proj_rank(x_t, ent.detach(), bias.detach(), t, ft, 0, counts)
-            _lib.proj_rank(x_h, ent.detach(), bias.detach(), h, fh, 1, counts)
+            bias_row = bias.detach() if bias is not None else None
+            _lib.proj_rank(x_t, ent.detach(), bias_row, t, ft, 0, counts)
+            _lib.proj_rank(x_h, ent.detach(), bias_row, h, fh, 1, counts)
             out[lo:hi] = counts.cpu().numpy()
             self.last_h2d_bytes += words * 8
             self.last_d2h_bytes += q * 16

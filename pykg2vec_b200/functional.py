@@ -133,7 +133,7 @@ class ProjTailFunction(torch.autograd.Function):
         ge = torch.zeros_like(ent) if ctx.needs_input_grad[1] else None
         gb = torch.zeros(ent.shape[0], dtype=torch.float32, device=x.device) \
             if (ctx.has_bias and ctx.needs_input_grad[2]) else None
-        _lib.proj_tail_bwd(gpreds.contiguous(), preds, x, ent, gx, ge, gb)
+        _lib.proj_tail_bwd(gpreds.contiguous(), preds, x.detach(), ent.detach(), gx, ge, gb)
         return gx, ge, (gb.reshape(ctx.bias_shape) if gb is not None else None)
 
 

@@ -137,3 +137,55 @@ class ConvE(ProjectionModel):
     def predict_head_rank(self, e, r, topk=-1):
         _, rank = torch.topk(-self.forward(e, r, direction="head"), k=topk)
         return rank
+
+
+class TuckER(ProjectionModel):
+    """pykg2vec/models/projection.py:258-345 — same kwargs, tables (ent_embeddings, rel_embeddings, W),
+    parameter_list and loss binding.  The trunk (normalise, contract the relation with the core tensor,
+    multiply, normalise) is a handful of small dense ops and stays on torch; the product against every
+    entity, its loss and the evaluation ranks are the kge_proj_* kernels (no bias row).  As in the
+    reference the `direction` argument is validated and otherwise ignored: both directions apply the
+    same function, to (h, r) and to (t, r)."""
+
+    def __init__(self, **kwargs):
+        super(TuckER, self).__init__(self.__class__.__name__.lower())
+        param_list = ["tot_entity", "tot_relation", "ent_hidden_size", "rel_hidden_size", "lmbda",
+                      "input_dropout", "hidden_dropout1", "hidden_dropout2"]
+        param_dict = self.load_params(param_list, kwargs)
+        self.__dict__.update(param_dict)
+        self.d1, self.d2 = self.ent_hidden_size, self.rel_hidden_size
+        self.ent_embeddings = NamedEmbedding("ent_embedding", self.tot_entity, self.d1)
+        self.rel_embeddings = NamedEmbedding("rel_embedding", self.tot_relation, self.d2)
+        self.W = NamedEmbedding("W", self.d2, self.d1 * self.d1)
+        nn.init.xavier_uniform_(self.ent_embeddings.weight)
+        nn.init.xavier_uniform_(self.rel_embeddings.weight)
+        nn.init.xavier_uniform_(self.W.weight)
+        self.parameter_list = [self.ent_embeddings, self.rel_embeddings, self.W]
+        self.inp_drop = nn.Dropout(self.input_dropout)
+        self.hidden_dropout1 = nn.Dropout(self.hidden_dropout1)
+        self.hidden_dropout2 = nn.Dropout(self.hidden_dropout2)
+        self.loss = Criterion.multi_class_bce
+
+    def proj_query(self, e1, r, direction="tail"):
+        assert direction in ("head", "tail"), "Unknown forward direction"
+        _require_cuda(e1, r, self.ent_embeddings.weight)
+        e1 = torch.nn.functional.normalize(self.ent_embeddings(e1), p=2, dim=1)
+        e1 = self.inp_drop(e1).view(-1, 1, self.d1)
+        W_mat = torch.matmul(self.rel_embeddings(r), self.W.weight.view(self.d2, -1)).view(-1, self.d1, self.d1)
+        W_mat = self.hidden_dropout1(W_mat)
+        x = torch.matmul(e1, W_mat).view(-1, self.d1)
+        return self.hidden_dropout2(torch.nn.functional.normalize(x, p=2, dim=1))
+
+    def proj_tail_tables(self):
+        return self.ent_embeddings.weight, None
+
+    def forward(self, e1, r, direction="head"):
+        return ProjTailFunction.apply(self.proj_query(e1, r, direction), self.ent_embeddings.weight, None)
+
+    def predict_tail_rank(self, e, r, topk=-1):
+        _, rank = torch.topk(-self.forward(e, r, direction="tail"), k=topk)
+        return rank
+
+    def predict_head_rank(self, e, r, topk=-1):
+        _, rank = torch.topk(-self.forward(e, r, direction="head"), k=topk)
+        return rank

@@ -150,7 +150,67 @@ def make_case(name, N, R, k, k1, b, seed):
     print("wrote", name, "loss", out["tr_loss"], "ranks[0]", out["ranks"][0], "preds", p_tail[0, :3].numpy())
 
 
+def tucker_trunk(m, e, r):
+    """TuckER.forward before the x.E^T product (projection.py:322-335), the reference's own tensors."""
+    import torch.nn.functional as F
+    e1 = F.normalize(m.ent_embeddings(e), p=2, dim=1)
+    e1 = m.inp_drop(e1).view(-1, 1, m.d1)
+    W_mat = torch.matmul(m.rel_embeddings(r), m.W.weight.view(m.d2, -1)).view(-1, m.d1, m.d1)
+    W_mat = m.hidden_dropout1(W_mat)
+    x = torch.matmul(e1, W_mat).view(-1, m.d1)
+    return m.hidden_dropout2(F.normalize(x, p=2, dim=1))
+
+
+def make_tucker(name, N, R, d1, d2, b, seed):
+    """TuckER (projection.py:258-345): no bias, no reciprocal relations — both directions run the
+    same function on (h, r) and (t, r)."""
+    torch.manual_seed(seed)
+    rng = np.random.RandomState(seed + 1000)
+    m = ref_projection.TuckER(tot_entity=N, tot_relation=R, ent_hidden_size=d1, rel_hidden_size=d2, lmbda=0.1,
+                              input_dropout=0.0, hidden_dropout1=0.0, hidden_dropout2=0.0)
+    with torch.no_grad():
+        m.ent_embeddings.weight.normal_(0.0, 0.5)
+        m.rel_embeddings.weight.normal_(0.0, 0.5)
+        m.W.weight.normal_(0.0, 0.3)
+    out = {"N": N, "R": R, "ent_hidden_size": d1, "rel_hidden_size": d2, "label_smoothing": np.float32(LABEL_SMOOTHING)}
+    for key, v in m.state_dict().items():
+        out["sd_" + key] = v.detach().numpy().copy()
+    h = rng.randint(N, size=b).astype(np.int64)
+    r = rng.randint(R, size=b).astype(np.int64)
+    t = rng.randint(N, size=b).astype(np.int64)
+    ht, rt, tt = torch.from_numpy(h), torch.from_numpy(r), torch.from_numpy(t)
+    out.update(h=h, r=r, t=t)
+    m.eval()
+    with torch.no_grad():
+        x_tail, x_head = tucker_trunk(m, ht, rt), tucker_trunk(m, tt, rt)
+        p_tail, p_head = m.forward(ht, rt, direction="tail"), m.forward(tt, rt, direction="head")
+        for x, p in ((x_tail, p_tail), (x_head, p_head)):
+            assert torch.equal(torch.sigmoid(torch.matmul(x, m.ent_embeddings.weight.T)), p)
+    out.update(x_tail=x_tail.numpy().copy(), x_head=x_head.numpy().copy(),
+               preds_tail=p_tail.numpy().copy(), preds_head=p_head.numpy().copy())
+    q = [(int(h[i]), int(r[i]), int(t[i])) for i in range(N_QUERIES)]
+    hr_t, tr_h = mg.random_filters(rng, N, R, q)
+    out["ranks"] = mg.reference_ranks(m, N, q, hr_t, tr_h)
+    out["filt_t_ptr"], out["filt_t_idx"] = mg.csr(hr_t, [(a, b_) for a, b_, c in q])
+    out["filt_h_ptr"], out["filt_h_idx"] = mg.csr(tr_h, [(c, b_) for a, b_, c in q])
+    m.train()
+    lab_t = (rng.rand(b, N) < 0.03).astype(np.float32)
+    lab_h = (rng.rand(b, N) < 0.03).astype(np.float32)
+    lab_t[np.arange(b), t] = 1.0
+    lab_h[np.arange(b), h] = 1.0
+    m.zero_grad()
+    loss = Criterion.multi_class_bce(m(tt, rt, direction="head"), m(ht, rt, direction="tail"),
+                                     torch.from_numpy(lab_h), torch.from_numpy(lab_t), LABEL_SMOOTHING, N)
+    loss.backward()
+    out.update(tr_labels_tail=lab_t, tr_labels_head=lab_h, tr_loss=np.float32(loss.item()))
+    for key, p in m.named_parameters():
+        out["grad_" + key] = p.grad.detach().numpy().copy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print("wrote", name, "loss", out["tr_loss"], "ranks[0]", out["ranks"][0])
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
+    make_tucker("tucker_d32", 97, 5, 32, 16, 24, seed=950)
     for i, (name, N, R, k, k1, b) in enumerate(CASES):
         make_case(name, N, R, k, k1, b, seed=900 + i)

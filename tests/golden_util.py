@@ -7,7 +7,7 @@ import numpy as np
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 NON_CASES = {"losses", "settle"}
-PROJ_PREFIXES = ("conve_",)
+PROJ_PREFIXES = ("conve_", "tucker_")
 
 
 def case_names():
@@ -18,7 +18,7 @@ def case_names():
 def proj_case_names():
     """ConvE cases (tests/golden/make_golden_proj.py): full state_dict + tail operands, not table lists."""
     names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-    return [n for n in names if n.startswith(PROJ_PREFIXES)]
+    return [n for n in names if n.startswith("conve_")]
 
 
 def proj_state(g):

@@ -349,3 +349,45 @@ def test_conve_epoch_on_device_generator():
     model.eval()
     scores = tr.evaluator.mini_test(epoch=0)
     assert set(scores) == {"mr", "fmr", "mrr", "fmrr"} and 1.0 <= scores["fmr"] <= scores["mr"] <= 200.0
+
+
+def _tucker(g, train=False):
+    from pykg2vec_b200 import import_model
+    m = import_model("tucker")(tot_entity=int(g["N"]), tot_relation=int(g["R"]),
+                               ent_hidden_size=int(g["ent_hidden_size"]), rel_hidden_size=int(g["rel_hidden_size"]),
+                               lmbda=0.1, input_dropout=0.0, hidden_dropout1=0.0, hidden_dropout2=0.0)
+    m.load_state_dict({k_: torch.from_numpy(np.asarray(v)) for k_, v in gu.proj_state(g).items()}, strict=True)
+    return m.cuda().train(train)
+
+
+def test_tucker_matches_reference():
+    """TuckER (bias-free tail, torch trunk): predictions, Evaluator ranks, training loss and gradients
+    vs the reference's own outputs"""
+    from pykg2vec_b200.evaluator import Evaluator
+    from pykg2vec_b200.trainer import Trainer
+    g = gu.load("tucker_d32")
+    m = _tucker(g)
+    h, r, t = _cuda(g["h"]), _cuda(g["r"]), _cuda(g["t"])
+    with torch.no_grad():
+        assert gu.rel_err(m(h, r, direction="tail").cpu().numpy(), g["preds_tail"]).max() < 1e-4
+        assert gu.rel_err(m(t, r, direction="head").cpu().numpy(), g["preds_head"]).max() < 1e-4
+    Q = g["ranks"].shape[0]
+    ev = object.__new__(Evaluator)
+    ev.model, ev.config = m, types.SimpleNamespace(device="cuda", tot_entity=int(g["N"]))
+    ev._filter_cache, ev._workspace = {}, None
+    with torch.no_grad():
+        got = ev.rank_triples(g["h"][:Q], g["r"][:Q], g["t"][:Q], (g["filt_t_ptr"], g["filt_t_idx"]),
+                              (g["filt_h_ptr"], g["filt_h_idx"]))
+    assert np.array_equal(got, g["ranks"])
+    m = _tucker(g, train=True)
+    tr = object.__new__(Trainer)
+    tr.model = m
+    tr.config = types.SimpleNamespace(device="cuda", label_smoothing=float(g["label_smoothing"]), tot_entity=int(g["N"]))
+    m.zero_grad()
+    loss = tr.train_step_projection(h, r, t, _cuda(g["tr_labels_tail"]), _cuda(g["tr_labels_head"]))
+    loss.backward()
+    assert abs(loss.item() - float(g["tr_loss"])) <= 1e-5 * abs(float(g["tr_loss"]))
+    for key, p in m.named_parameters():
+        want = g["grad_" + key]
+        err = np.abs(p.grad.cpu().numpy() - want).max() / max(np.abs(want).max(), 1e-5)
+        assert err < 5e-4, (key, err)

@@ -140,3 +140,29 @@ def test_label_csr_host_logic():
         assert len(ptr) - 1 == len(known) and ptr[-1] == len(idx) == sum(len(v) for v in known.values())
         for i in range(len(arr)):
             assert set(idx[ptr[rows[i]]:ptr[rows[i] + 1]].tolist()) == known[(int(arr[i, a]), int(arr[i, b]))]
+
+
+def test_tucker_tail_and_ranks_match_reference():
+    """TuckER's tail has no bias row (projection.py:335-336): oracle vs the reference's outputs"""
+    g = gu.load("tucker_d32")
+    E = g["sd_ent_embeddings.weight"]
+    for tag in ("tail", "head"):
+        assert gu.rel_err(oracle.proj_tail_fwd(g["x_" + tag], E, None), g["preds_" + tag]).max() < 1e-6
+    Q = g["ranks"].shape[0]
+    c = np.zeros((Q, 4), dtype=np.int32)
+    oracle.proj_rank(g["x_tail"][:Q], E, None, g["t"][:Q], (g["filt_t_ptr"], g["filt_t_idx"]), 0, c)
+    oracle.proj_rank(g["x_head"][:Q], E, None, g["h"][:Q], (g["filt_h_ptr"], g["filt_h_idx"]), 1, c)
+    assert np.array_equal(c, g["ranks"])
+
+
+def test_tucker_mirror_surface():
+    from pykg2vec_b200 import import_model
+    g = gu.load("tucker_d32")
+    st = gu.proj_state(g)
+    m = import_model("tucker")(tot_entity=int(g["N"]), tot_relation=int(g["R"]), ent_hidden_size=32,
+                               rel_hidden_size=16, lmbda=0.1, input_dropout=0.0, hidden_dropout1=0.0,
+                               hidden_dropout2=0.0)
+    assert sorted(m.state_dict()) == sorted(st) == ["W.weight", "ent_embeddings.weight", "rel_embeddings.weight"]
+    m.load_state_dict({k_: torch.from_numpy(np.asarray(v)) for k_, v in st.items()}, strict=True)
+    assert [p.name for p in m.parameter_list] == ["ent_embedding", "rel_embedding", "W"]
+    assert m.training_strategy.name == "PROJECTION_BASED" and m.model_name == "tucker"

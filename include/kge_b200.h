@@ -206,6 +206,18 @@ int kge_rank_1vsall(const kge_model_t* m, const kge_model_t* mq, int64_t row_lo,
 #define KGE_RANK_HEAD_ONLY 4
 #define KGE_RANK_SINGLE_STREAM 8 /* do not overlap the two directions on an internal side stream */
 
+/* ---- per-relation entity projection (relation-grouped evaluation of TransH / TransD) ----------
+ * TransH.embed/_projection (pykg2vec/models/pairwise.py:166-182) and TransD.embed/_projection
+ * (:240-249,275-278) project the h and t rows with a vector chosen by the relation and then apply
+ * TransE's distance.  For a fixed relation r this writes the projected row of EVERY entity,
+ *   KGE_TRANSH: out[e] = ent[e] - (ent[e] . w~_r) w~_r,  w~_r = w[r] / max(|w[r]|, 1e-12)
+ *   KGE_TRANSD: out[e] = ent[e] + (ent[e] . ent_map[e]) rel_map[r]
+ * in exactly the arithmetic kge_score_fwd applies to the rows of a triple, so that
+ *   score_model(h, r, t) == score_TransE over tables [out, rel] at (h, r, t)   bit for bit
+ * and the test triples of relation r can be ranked by kge_rank_1vsall with a KGE_TRANSE model over
+ * [out, rel] (the tiled sweep) instead of the per-pair gather sweep.  out: [num_ent, dim] fp32. */
+int kge_project_entities(const kge_model_t* m, int64_t r, float* out, void* stream);
+
 /* ---- projection-model tail: x.E^T + b -> sigmoid, multi-class BCE, rank counts ----------
  * The last layer shared by the reference's projection models:
  *   ConvE.inner_forward    pykg2vec/models/projection.py:100-102   (torch.matmul(x, E.T); + b; sigmoid)

@@ -30,7 +30,7 @@ EXPORTS = [
     "kge_rank_workspace_bytes", "kge_rank_1vsall",
     "kge_tripleset_capacity", "kge_tripleset_build", "kge_sample_negatives",
     "kge_proj_tail_fwd", "kge_proj_tail_bwd", "kge_proj_bce", "kge_proj_rank_workspace_bytes", "kge_proj_rank", "kge_proj_labels",
-    "kge_conve_trunk_workspace_bytes", "kge_conve_trunk_fwd",
+    "kge_conve_trunk_workspace_bytes", "kge_conve_trunk_fwd", "kge_project_entities",
 ]
 
 
@@ -266,6 +266,17 @@ def rank_1vsall(desc, qh, qr, qt, filt_t=None, filt_h=None, counts=None, row_lo=
         _ptr(counts), _ptr(workspace), ctypes.c_int64(workspace.numel()), ctypes.c_int(flags), _stream()),
         "kge_rank_1vsall")
     return counts
+
+
+def project_entities(desc, r, out=None):
+    """TransH / TransD: the projected row of every entity for relation r, [num_ent, dim]
+    (include/kge_b200.h kge_project_entities) — TransE over [out, rel] then equals the model."""
+    if out is None:
+        out = torch.empty((desc.num_ent, desc.dim), dtype=torch.float32, device=desc.tables[0].device)
+    m = desc.c_struct()
+    check(lib().kge_project_entities(ctypes.byref(m), ctypes.c_int64(int(r)), _ptr(_dev_f32(out, "out")), _stream()),
+          "kge_project_entities")
+    return out
 
 
 def tripleset_build(h, r, t, num_ent, num_rel):

@@ -231,6 +231,8 @@ class Evaluator:
         self.last_d2h_bytes = 0
         if hasattr(self.model, "proj_query"):
             return self._rank_triples_projection(hs, rs, ts, filt_t, filt_h, out)
+        if self._use_relation_groups(rs):
+            return self._rank_triples_by_relation(hs, rs, ts, filt_t, filt_h, out)
         for lo in range(0, Q, self.QUERY_BATCH):
             hi = min(Q, lo + self.QUERY_BATCH)
             q = hi - lo
@@ -255,6 +257,81 @@ class Evaluator:
             out[lo:hi] = res.numpy()
             self.last_h2d_bytes += call.h_in.numel() * 8
             self.last_d2h_bytes += res.numel() * 4
+        return out
+
+    # ---- TransH / TransD: relation-grouped evaluation ---------------------------------------------
+    GROUP_MIN_QUERIES_PER_RELATION = 32
+    GROUPED_BY_DEFAULT = False   # opt-in (config.relation_grouped_eval = True / None) until timed on a B200
+
+    def _use_relation_groups(self, rs):
+        """TransH / TransD project the candidate rows with a relation-dependent vector, so their
+        1-vs-all sweep is the per-pair gather kernel (every pair re-reads and re-projects the
+        candidate row).  When a batch holds many test triples per relation it is cheaper to project
+        the whole entity table once per relation (kge_project_entities) and rank that relation's
+        queries with TransE's tiled sweep over the projected table — same bits, hence same ranks
+        (tests/test_emu_project.py, tests/test_gpu_score_rank.py).  config.relation_grouped_eval:
+        True / False forces the choice, None (default) decides by queries per distinct relation."""
+        if getattr(self.model, "model_name", "") not in ("transh", "transd") or len(rs) == 0:
+            return False
+        force = getattr(self.config, "relation_grouped_eval", self.GROUPED_BY_DEFAULT)
+        if force is not None:
+            return bool(force)
+        return len(rs) >= self.GROUP_MIN_QUERIES_PER_RELATION * len(np.unique(rs))
+
+    def _rank_triples_by_relation(self, hs, rs, ts, filt_t, filt_h, out):
+        dev = self._dev()
+        Q = hs.shape[0]
+        order = np.argsort(rs, kind="stable")
+        rel_sorted = rs[order]
+        starts = np.flatnonzero(np.r_[True, rel_sorted[1:] != rel_sorted[:-1]])
+        ends = np.r_[starts[1:], Q]
+
+        def reorder(filt):   # CSR rows permuted into the sorted query order
+            if filt is None:
+                return None
+            ptr, idx = np.asarray(filt[0], dtype=np.int64), np.asarray(filt[1], dtype=np.int64)
+            lens = (ptr[1:] - ptr[:-1])[order]
+            new_ptr = np.zeros(Q + 1, dtype=np.int64)
+            np.cumsum(lens, out=new_ptr[1:])
+            take = np.repeat(ptr[:-1][order] - new_ptr[:-1], lens) + np.arange(new_ptr[-1], dtype=np.int64)
+            return new_ptr, idx[take]
+
+        ft, fh = reorder(filt_t), reorder(filt_h)
+        parts = [hs[order], rel_sorted, ts[order]]
+        if ft is not None:
+            parts += [ft[0], fh[0], ft[1], fh[1]]
+        words = sum(len(a) for a in parts)
+        stage = torch.empty(words, dtype=torch.int64).pin_memory()
+        buf, o, v = stage.numpy(), 0, []
+        for a in parts:
+            buf[o:o + len(a)] = a
+            v.append((o, o + len(a)))
+            o += len(a)
+        d_in = stage.to(dev, non_blocking=True)
+        v = [d_in[a:b] for a, b in v]
+        desc = self.model.kge_desc()
+        proj = torch.empty((desc.num_ent, desc.dim), dtype=torch.float32, device=dev)
+        te = _lib.ModelDesc("transe", [proj, desc.tables[1]], desc.dim, l1_flag=desc.l1_flag)
+        counts = torch.zeros((Q, 4), dtype=torch.int32, device=dev)
+        ws = torch.empty(max(_lib.rank_workspace_bytes(te, min(Q, 65535)), 16), dtype=torch.uint8, device=dev)
+        for a, b in zip(starts.tolist(), ends.tolist()):
+            _lib.project_entities(desc, int(rel_sorted[a]), proj)
+            for lo in range(a, b, 65535):
+                hi = min(b, lo + 65535)
+                f_t = f_h = None
+                if ft is not None:
+                    tp, hp = v[3][lo:hi + 1], v[4][lo:hi + 1]
+                    f_t = ((tp - tp[0]).contiguous(), v[5][int(ft[0][lo]):int(ft[0][hi])])
+                    f_h = ((hp - hp[0]).contiguous(), v[6][int(fh[0][lo]):int(fh[0][hi])])
+                    if f_t[1].numel() == 0:
+                        f_t = None
+                    if f_h[1].numel() == 0:
+                        f_h = None
+                _lib.rank_1vsall(te, v[0][lo:hi], v[1][lo:hi], v[2][lo:hi], f_t, f_h, counts=counts[lo:hi],
+                                 workspace=ws)
+        out[order] = counts.cpu().numpy()
+        self.last_h2d_bytes = words * 8
+        self.last_d2h_bytes = Q * 16
         return out
 
     def _rank_triples_projection(self, hs, rs, ts, filt_t, filt_h, out):

@@ -135,6 +135,9 @@ inline float __shfl_xor_sync(unsigned mask, float v, int lane_mask) {
   return __uint_as_float(::cuda_emu::shfl(mask, __float_as_uint(v), lane ^ lane_mask));
 }
 
+// warp barrier among the lanes named by the mask
+inline void __syncwarp(unsigned mask = 0xffffffffu) { (void)::cuda_emu::shfl(mask, 0u, ::cuda_emu::linear_tid() & 31); }
+
 inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline int atomicSub(int* p, int v) { return __atomic_fetch_sub(p, v, __ATOMIC_SEQ_CST); }
 inline float atomicAdd(float* p, float v) {

@@ -269,8 +269,8 @@ def test_conve_training_step_matches_reference_autograd(name):
             want = g["gradsample_" + key]
         # bn0's scale and shift are (mathematically) invisible behind bn1's batch normalisation: their
         # true gradient is 0 and what autograd returns is rounding noise of order 1e-7 — hence the floor
-        scale = max(np.abs(want).max(), 1e-5)
-        assert np.abs(got - want).max() / scale < 5e-4, key
+        # (likewise conv / fc biases in front of a training-mode BatchNorm): relative bound + a floor
+        assert np.abs(got - want).max() <= 5e-4 * np.abs(want).max() + 1e-7, key
     for key, v in m.state_dict().items():
         if "running" in key:
             assert np.abs(v.cpu().numpy() - g["sd_after_" + key]).max() < 1e-5, key
@@ -389,5 +389,4 @@ def test_tucker_matches_reference():
     assert abs(loss.item() - float(g["tr_loss"])) <= 1e-5 * abs(float(g["tr_loss"]))
     for key, p in m.named_parameters():
         want = g["grad_" + key]
-        err = np.abs(p.grad.cpu().numpy() - want).max() / max(np.abs(want).max(), 1e-5)
-        assert err < 5e-4, (key, err)
+        assert np.abs(p.grad.cpu().numpy() - want).max() <= 5e-4 * np.abs(want).max() + 1e-7, key

@@ -1,0 +1,65 @@
+"""CPU check (no GPU) of the per-model score functions in pykg2vec_b200/csrc/kge_models.cuh — the
+device math behind kge_score_fwd and the gather sweep — run under the host emulation of
+tests/emu/ with the thread mapping of score_fwd_kernel, against the oracle, BIT FOR BIT, on the
+tables of every golden case (both groupings).  A regression net for the model math that needs no
+GPU; the compiled kernels themselves are checked on the B200 by tests/test_gpu_score_rank.py."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import golden_util as gu
+import oracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SRC = os.path.join(HERE, "emu", "emu_score.cpp")
+OUT = os.path.join(HERE, "emu", "_build", "libemu_score.so")
+DEPS = [SRC, os.path.join(HERE, "emu", "cuda_runtime.h")] + \
+       [os.path.join(ROOT, "pykg2vec_b200", "csrc", f) for f in ("kge_models.cuh", "kge_common.cuh")]
+CASES = [n for n in gu.case_names()]
+
+
+@pytest.fixture(scope="module")
+def emu():
+    if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in DEPS):
+        os.makedirs(os.path.dirname(OUT), exist_ok=True)
+        cmd = ["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-mfma",
+               "-pthread", "-w", "-I", os.path.join(HERE, "emu"), "-I", os.path.join(ROOT, "pykg2vec_b200", "csrc"),
+               "-o", OUT + ".tmp", SRC]
+        subprocess.run(cmd, check=True)
+        os.replace(OUT + ".tmp", OUT)
+    return ctypes.CDLL(OUT)
+
+
+def _widths(om):
+    return [t.shape[-1] if t.ndim > 1 else 1 for t in om.tables]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_emulated_score_functions_are_bit_exact(emu, name):
+    g = gu.load(name)
+    om = gu.oracle_model(g)
+    m = om.c_struct()
+    n = min(40, len(g["h"]))           # 2 CTAs, the second one partly idle
+    h, r, t = (np.ascontiguousarray(g[k][:n], dtype=np.int64) for k in ("h", "r", "t"))
+    if om.name == "rescal":            # Rescal.forward row-normalises its tables in place first
+        for tab in om.tables:
+            oracle.normalize_rows(tab)
+    # 16-byte row loads are legal when every row width is a multiple of 4 floats (numpy buffers are
+    # 16-byte aligned); the scalar path is always legal and must give the same bits
+    vecs = [1] + ([4] if all(w % 4 == 0 for w in _widths(om)) and om.dim % 4 == 0 else [])
+    if om.name in ("analogy",) and (om.dim // 2) % 4:
+        vecs = [1]
+    for grouping in (oracle.GROUP_TAIL, oracle.GROUP_HEAD):
+        want = oracle.score_fwd(om, h, r, t, grouping)
+        for vec in vecs:
+            got = np.full(n, np.nan, dtype=np.float32)
+            rc = emu.emu_score_fwd(ctypes.byref(m), ctypes.c_int(grouping), ctypes.c_int(vec),
+                                   h.ctypes.data_as(ctypes.c_void_p), r.ctypes.data_as(ctypes.c_void_p),
+                                   t.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(n),
+                                   got.ctypes.data_as(ctypes.c_void_p))
+            assert rc == 0
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (name, grouping, vec)

@@ -63,3 +63,49 @@ def test_emulated_score_functions_are_bit_exact(emu, name):
                                    got.ctypes.data_as(ctypes.c_void_p))
             assert rc == 0
             assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (name, grouping, vec)
+
+
+# ---- backward: grad_group<MODEL, VEC> of kge_grads.cuh vs the reference's own autograd -------------
+SRC_BWD = os.path.join(HERE, "emu", "emu_bwd.cpp")
+OUT_BWD = os.path.join(HERE, "emu", "_build", "libemu_bwd.so")
+GRAD_TOL = 2e-4   # relative to the largest |gradient| of the table (as tests/test_gpu_train.py)
+
+
+@pytest.fixture(scope="module")
+def emu_bwd():
+    deps = [SRC_BWD, os.path.join(HERE, "emu", "cuda_runtime.h")] + \
+           [os.path.join(ROOT, "pykg2vec_b200", "csrc", f) for f in ("kge_grads.cuh", "kge_models.cuh", "kge_common.cuh")]
+    if not os.path.exists(OUT_BWD) or any(os.path.getmtime(d) > os.path.getmtime(OUT_BWD) for d in deps):
+        os.makedirs(os.path.dirname(OUT_BWD), exist_ok=True)
+        cmd = ["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-mfma",
+               "-pthread", "-w", "-I", os.path.join(HERE, "emu"), "-I", os.path.join(ROOT, "pykg2vec_b200", "csrc"),
+               "-o", OUT_BWD + ".tmp", SRC_BWD]
+        subprocess.run(cmd, check=True)
+        os.replace(OUT_BWD + ".tmp", OUT_BWD)
+    return ctypes.CDLL(OUT_BWD)
+
+
+@pytest.mark.parametrize("name", [n for n in CASES if "pretrained" not in n])
+def test_emulated_gradients_match_reference_autograd(emu_bwd, name):
+    g = gu.load(name)
+    om = gu.oracle_model(g)
+    m = om.c_struct()
+    h, r, t = (np.ascontiguousarray(g[k], dtype=np.int64) for k in ("h", "r", "t"))
+    up = np.ascontiguousarray(g["upstream"], dtype=np.float32)
+    grads = [np.zeros_like(tab) for tab in om.tables]
+    arr = (ctypes.c_void_p * 16)()
+    for k, a in enumerate(grads):
+        arr[k] = a.ctypes.data
+    vec = 4 if (all(w % 4 == 0 for w in _widths(om)) and om.dim % 4 == 0 and not (om.name == "analogy" and (om.dim // 2) % 4)) else 1
+    rc = emu_bwd.emu_score_bwd(ctypes.byref(m), ctypes.c_int(vec), ctypes.c_int(len(grads)),
+                               h.ctypes.data_as(ctypes.c_void_p), r.ctypes.data_as(ctypes.c_void_p),
+                               t.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(len(h)),
+                               up.ctypes.data_as(ctypes.c_void_p), arr)
+    assert rc == 0
+    for k, got in enumerate(grads):
+        if "grad%d" % k not in g:      # ConvKB: no reference gradient for the collapsed tables
+            continue
+        want = np.asarray(g["grad%d" % k], dtype=np.float64).reshape(got.shape)
+        scale = max(np.abs(want).max(), 1e-12)
+        err = np.abs(got.astype(np.float64) - want).max() / scale
+        assert err < GRAD_TOL, "%s table %d: rel err %.3g" % (name, k, err)

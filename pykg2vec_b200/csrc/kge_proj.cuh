@@ -17,7 +17,8 @@
 
 namespace kge {
 
-constexpr int PBM = 64, PBN = 64, PBK = 16, PTHREADS = 256;
+constexpr int PBM = 64, PBN = 64;   // the 64x64 CTA tile (gradient and Linear-layer launches; smallest forward tile)
+constexpr int PBK = 16, PTHREADS = 256;
 enum { EPI_STORE = 0, EPI_ATOMIC = 1, EPI_COUNT = 2 };
 enum { ACT_SIGMOID = 0, ACT_RELU = 1, ACT_NONE = 2 };
 
@@ -311,7 +312,7 @@ proj_labels_kernel(const int64_t* __restrict__ rows, const int64_t* __restrict__
 // ---- launch plans: plain C++ (shared by the C-ABI launchers in kge_proj.cu and by the CPU
 // emulation test tests/emu/, which runs these kernels thread by thread on the host) ------------
 // CTA tile variants of proj_gemm_kernel: rows x columns (thread tile = rows/16 x columns/16)
-enum { PROJ_TILE_64x64 = 0, PROJ_TILE_64x128 = 1, PROJ_TILE_128x128 = 2, PROJ_TILE_AUTO = -1 };
+enum { PROJ_TILE_64x64 = 0, PROJ_TILE_64x128 = 1, PROJ_TILE_128x128 = 2 };
 inline int proj_tile_rows(int tile) { return tile == PROJ_TILE_128x128 ? 128 : 64; }
 inline int proj_tile_cols(int tile) { return tile == PROJ_TILE_64x64 ? 64 : 128; }
 // Large tiles halve the shared-memory operand traffic per fma (a 16-byte read feeds 32 fma instead

@@ -111,7 +111,13 @@ inline void launch(dim3 grid, dim3 block, const std::function<void()>& body) {
 // NOTE: a thread that returns early from a kernel that later calls __syncthreads() would hang a
 // pthread barrier (on the GPU exited threads are dropped from the barrier count); none of the
 // emulated kernels does that.
+// CUDA_EMU_NO_BARRIERS: positive control of the race check (tests/test_emu_races.py) — with the block
+// barrier compiled out ThreadSanitizer must report the shared-memory races it is there to find.
+#ifdef CUDA_EMU_NO_BARRIERS
+inline void __syncthreads() {}
+#else
 inline void __syncthreads() { pthread_barrier_wait(&::cuda_emu::g_block->barrier); }
+#endif
 
 template <class T> inline T __ldg(const T* p) { return *p; }
 inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }

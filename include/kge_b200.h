@@ -218,6 +218,15 @@ int kge_rank_1vsall(const kge_model_t* m, const kge_model_t* mq, int64_t row_lo,
  * [out, rel] (the tiled sweep) instead of the per-pair gather sweep.  out: [num_ent, dim] fp32. */
 int kge_project_entities(const kge_model_t* m, int64_t r, float* out, void* stream);
 
+/* KGE_TRANSR is accepted as well: out[e] = normalize(ent[e]) . M_r, [num_ent, rel_dim]
+ * (TransR.transform on the normalised rows, pairwise.py:405-413,430-442).  Together with the ONCE
+ * normalised relation rows written by kge_normalize_rows_to (F.normalize(rel), pairwise.py:430-432, in
+ * the canonical arithmetic: row * (1 / max(|row|, 1e-12))), TransE of width rel_dim over
+ * [out, normalised rel] applies the reference's second normalisation (:463-465) and reproduces
+ * score_TransR bit for bit.  (Proved on the oracle with the emulated kernels, tests/test_emu_project.py;
+ * the relation-grouped Evaluator uses it for TransR only on request — not yet timed on a B200.) */
+int kge_normalize_rows_to(const float* table, int64_t rows, int64_t width, float* out, void* stream);
+
 /* ---- projection-model tail: x.E^T + b -> sigmoid, multi-class BCE, rank counts ----------
  * The last layer shared by the reference's projection models:
  *   ConvE.inner_forward    pykg2vec/models/projection.py:100-102   (torch.matmul(x, E.T); + b; sigmoid)

@@ -30,7 +30,7 @@ EXPORTS = [
     "kge_rank_workspace_bytes", "kge_rank_1vsall",
     "kge_tripleset_capacity", "kge_tripleset_build", "kge_sample_negatives",
     "kge_proj_tail_fwd", "kge_proj_tail_bwd", "kge_proj_bce", "kge_proj_rank_workspace_bytes", "kge_proj_rank", "kge_proj_labels",
-    "kge_conve_trunk_workspace_bytes", "kge_conve_trunk_fwd", "kge_project_entities",
+    "kge_conve_trunk_workspace_bytes", "kge_conve_trunk_fwd", "kge_project_entities", "kge_normalize_rows_to",
 ]
 
 
@@ -272,10 +272,22 @@ def project_entities(desc, r, out=None):
     """TransH / TransD: the projected row of every entity for relation r, [num_ent, dim]
     (include/kge_b200.h kge_project_entities) — TransE over [out, rel] then equals the model."""
     if out is None:
-        out = torch.empty((desc.num_ent, desc.dim), dtype=torch.float32, device=desc.tables[0].device)
+        width = desc.rel_dim if desc.name == "transr" else desc.dim
+        out = torch.empty((desc.num_ent, width), dtype=torch.float32, device=desc.tables[0].device)
     m = desc.c_struct()
     check(lib().kge_project_entities(ctypes.byref(m), ctypes.c_int64(int(r)), _ptr(_dev_f32(out, "out")), _stream()),
           "kge_project_entities")
+    return out
+
+
+def normalize_rows_to(table, out=None):
+    """F.normalize(table, dim=-1) in the canonical arithmetic into a new tensor (TransR's first
+    normalisation of the relation rows, pairwise.py:430-432)."""
+    t = _dev_f32(table, "table")
+    if out is None:
+        out = torch.empty_like(t)
+    check(lib().kge_normalize_rows_to(_ptr(t), ctypes.c_int64(t.shape[0]), ctypes.c_int64(t.shape[1]),
+                                      _ptr(_dev_f32(out, "out")), _stream()), "kge_normalize_rows_to")
     return out
 
 

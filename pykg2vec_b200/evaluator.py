@@ -272,7 +272,10 @@ class Evaluator:
         (tests/test_emu_project.py, tests/test_gpu_score_rank.py).  FB15k-237 shape, 20,466 test
         triples: TransH 349 -> 30 ms, TransD 344 -> 111 ms, identical ranks.  config.relation_grouped_eval:
         True / False forces the choice, None (default) decides by queries per distinct relation."""
-        if getattr(self.model, "model_name", "") not in ("transh", "transd") or len(rs) == 0:
+        name = getattr(self.model, "model_name", "")
+        if name == "transr":   # same scheme (P_r = normalize(ent) . M_r), proved on the oracle but not yet
+            return getattr(self.config, "relation_grouped_eval", None) is True   # timed on a B200: on request only
+        if name not in ("transh", "transd") or len(rs) == 0:
             return False
         force = getattr(self.config, "relation_grouped_eval", self.GROUPED_BY_DEFAULT)
         if force is not None:
@@ -311,8 +314,12 @@ class Evaluator:
         d_in = stage.to(dev, non_blocking=True)
         v = [d_in[a:b] for a, b in v]
         desc = self.model.kge_desc()
-        proj = torch.empty((desc.num_ent, desc.dim), dtype=torch.float32, device=dev)
-        te = _lib.ModelDesc("transe", [proj, desc.tables[1]], desc.dim, l1_flag=desc.l1_flag)
+        if desc.name == "transr":   # TransE of width rel_dim over [normalize(ent) . M_r, normalize(rel)]
+            width, rel_rows = desc.rel_dim, _lib.normalize_rows_to(desc.tables[1])
+        else:
+            width, rel_rows = desc.dim, desc.tables[1]
+        proj = torch.empty((desc.num_ent, width), dtype=torch.float32, device=dev)
+        te = _lib.ModelDesc("transe", [proj, rel_rows], width, l1_flag=desc.l1_flag)
         counts = torch.zeros((Q, 4), dtype=torch.int32, device=dev)
         ws = torch.empty(max(_lib.rank_workspace_bytes(te, min(Q, 65535)), 16), dtype=torch.uint8, device=dev)
         for a, b in zip(starts.tolist(), ends.tolist()):

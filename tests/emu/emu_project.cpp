@@ -31,9 +31,21 @@ static void run(const ModelParams& P, int vec, int64_t r, int64_t n, float* out)
 
 extern "C" int emu_project_entities(const kge_model_t* m, int64_t r, float* out) {
   const ModelParams P = make_params(m, nullptr);
+  if (m->model == KGE_TRANSR) {
+    run<KGE_TRANSR>(P, pick_vec(m, 3, m->dim, m->rel_dim), r, m->num_ent, out);
+    return 0;
+  }
   const int vec = pick_vec(m, m->model == KGE_TRANSH ? 3 : 4, m->dim);
   if (m->model == KGE_TRANSH) run<KGE_TRANSH>(P, vec, r, m->num_ent, out);
   else if (m->model == KGE_TRANSD) run<KGE_TRANSD>(P, vec, r, m->num_ent, out);
   else return -1;
+  return 0;
+}
+
+extern "C" int emu_normalize_rows(const float* in, int64_t n, int width, int vec, float* out) {
+  const dim3 grid((unsigned)((n + 31) / 32)), block(256);
+  if (vec == 4) cuda_emu::launch(grid, block, [&] { normalize_rows_kernel<4>(in, n, width, out); });
+  else if (vec == 2) cuda_emu::launch(grid, block, [&] { normalize_rows_kernel<2>(in, n, width, out); });
+  else cuda_emu::launch(grid, block, [&] { normalize_rows_kernel<1>(in, n, width, out); });
   return 0;
 }

@@ -199,6 +199,13 @@ static int run_project() {
   m.model = KGE_TRANSD; m.tables[2] = em.data(); m.tables[3] = rm.data();
   P = make_params(&m, nullptr);
   cuda_emu::launch(dim3((unsigned)((N + 31) / 32)), dim3(256), [&] { project_rows_kernel<KGE_TRANSD, 1>(P, 2, N, out.data()); });
+  const int dr = 16;
+  auto mats = rnd(R * d * dr, 6, 0.3f), relr = rnd(R * dr, 7);
+  std::vector<float> outr(N * dr), rhat(R * dr);
+  m.model = KGE_TRANSR; m.rel_dim = dr; m.tables[1] = relr.data(); m.tables[2] = mats.data();
+  P = make_params(&m, nullptr);
+  cuda_emu::launch(dim3((unsigned)((N + 31) / 32)), dim3(256), [&] { project_rows_kernel<KGE_TRANSR, 4>(P, 0, N, outr.data()); });
+  cuda_emu::launch(dim3(1), dim3(256), [&] { normalize_rows_kernel<4>(relr.data(), R, dr, rhat.data()); });
   return 0;
 }
 

@@ -65,3 +65,31 @@ def test_transe_on_projected_table_equals_projected_model(emu, name, N, R, d, l1
         filt = (np.arange(q + 1, dtype=np.int64) * 3, rng.randint(N, size=3 * q).astype(np.int64))
         assert np.array_equal(oracle.rank_1vsall(te, h[:q], rr[:q], t[:q], filt, filt),
                               oracle.rank_1vsall(om, h[:q], rr[:q], t[:q], filt, filt))
+
+
+@pytest.mark.parametrize("N,R,d,dr,l1", [(40, 3, 24, 16, False), (25, 2, 50, 50, True), (30, 2, 10, 7, False)])
+def test_transe_on_projected_table_equals_transr(emu, N, R, d, dr, l1):
+    """TransR: P_r = normalize(ent) . M_r and the once-normalised relation rows; TransE (width d_r) over
+    them applies the reference's second normalisation — bit-identical scores in both groupings"""
+    rng = np.random.RandomState(N * d + dr)
+    ent = (rng.standard_normal((N, d)) * 0.5).astype(np.float32)
+    rel = (rng.standard_normal((R, dr)) * 0.5).astype(np.float32)
+    mats = (rng.standard_normal((R, d * dr)) * 0.3).astype(np.float32)
+    om = oracle.Model("transr", [ent, rel, mats], d, rel_dim=dr, l1_flag=l1)
+    m = om.c_struct()
+    vec = 4 if (d % 4 == 0 and dr % 4 == 0) else 1
+    rhat = np.full((R, dr), np.nan, dtype=np.float32)
+    emu.emu_normalize_rows(rel.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(R), ctypes.c_int(dr), ctypes.c_int(vec),
+                           rhat.ctypes.data_as(ctypes.c_void_p))
+    for r in range(R):
+        P = np.full((N, dr), np.nan, dtype=np.float32)
+        assert emu.emu_project_entities(ctypes.byref(m), ctypes.c_int64(r), P.ctypes.data_as(ctypes.c_void_p)) == 0
+        assert np.isfinite(P).all()
+        te = oracle.Model("transe", [P, rhat], dr, l1_flag=l1)
+        n = 48
+        h, t = rng.randint(N, size=n), rng.randint(N, size=n)
+        rr = np.full(n, r, dtype=np.int64)
+        for grouping in (oracle.GROUP_TAIL, oracle.GROUP_HEAD):
+            want = oracle.score_fwd(om, h, rr, t, grouping)
+            got = oracle.score_fwd(te, h, rr, t, grouping)
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (r, grouping)

@@ -265,3 +265,25 @@ def test_relation_grouped_evaluation_equals_gather_sweep(name, d, l1):
     assert np.array_equal(ev.rank_triples(qh, qr, qt, ft, fh), want)
     ev.config.relation_grouped_eval = True
     assert np.array_equal(ev.rank_triples(qh, qr, qt)[:, 0], want[:, 0])     # no filters
+
+
+@pytest.mark.skipif(__import__("os").environ.get("KGE_RUN_UNVERIFIED") != "1",
+                    reason="TransR relation-grouped evaluation: proved on the oracle with the emulated kernels "
+                           "(tests/test_emu_project.py) but written after the round's GPU minutes were spent; "
+                           "run with KGE_RUN_UNVERIFIED=1 on a B200 before enabling it by default")
+def test_relation_grouped_evaluation_transr():
+    import types
+    import oracle
+    from pykg2vec_b200.evaluator import Evaluator
+    N, R, d, dr, Q = 500, 4, 24, 16, 160
+    om, tabs = gpu.synthetic_case("transr", N, R, d, seed=11, dr=dr)
+    desc = gpu.desc_from_oracle_model(om)
+    rng = np.random.RandomState(4)
+    qh, qr, qt = rng.randint(N, size=Q), rng.randint(R, size=Q), rng.randint(N, size=Q)
+    ft, fh = gpu.random_filters_csr(rng, N, qh, qr, qt, per_query=9)
+    model = types.SimpleNamespace(model_name="transr", kge_desc=lambda: desc, kge_tables=lambda: desc.tables)
+    ev = object.__new__(Evaluator)
+    ev.model = model
+    ev.config = types.SimpleNamespace(device="cuda", tot_entity=N, relation_grouped_eval=True, cuda_graph=False)
+    ev._filter_cache, ev._workspace = {}, None
+    assert np.array_equal(ev.rank_triples(qh, qr, qt, ft, fh), oracle.rank_1vsall(om, qh, qr, qt, ft, fh))

@@ -179,3 +179,32 @@ def test_emulated_label_rows(emu, with_rows):
         row = rows[b] if with_rows else b
         want[b, idx[ptr[row]:ptr[row + 1]]] = 1.0
     assert np.array_equal(got, want)
+
+
+def test_emulated_random_shapes(emu):
+    """seeded sweep over awkward shapes (1-wide operands, sizes straddling the 64 / 128 tile edges and the
+    16-deep k chunks, every CTA tile): forward bits, rank counts and gradients against the oracle"""
+    rng = np.random.RandomState(1234)
+    edges = [1, 2, 15, 16, 17, 63, 64, 65, 127, 128, 129, 130]
+    for it in range(10):
+        B, N, k = int(rng.choice(edges)), int(rng.choice(edges)), int(rng.choice([1, 3, 4, 15, 16, 17, 33, 48]))
+        tile = it % 3
+        x, ent, b = _case(B, N, k, seed=it, bias=bool(it % 2))
+        got = np.full((B, N), np.nan, dtype=np.float32)
+        emu.emu_proj_tail_fwd(_p(x), _p(ent), _p(b), ctypes.c_int64(B), ctypes.c_int64(N), ctypes.c_int32(k), _p(got),
+                              ctypes.c_int32(tile))
+        want = oracle.proj_tail_fwd(x, ent, b)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (B, N, k, tile)
+        tgt = rng.randint(N, size=B).astype(np.int64)
+        counts = np.zeros((B, 4), dtype=np.int32)
+        thr = np.zeros(B, dtype=np.float32)
+        emu.emu_proj_rank(_p(x), _p(ent), _p(b), ctypes.c_int64(B), ctypes.c_int64(N), ctypes.c_int32(k), _p(tgt),
+                          None, None, ctypes.c_int64(0), ctypes.c_int32(1), _p(counts), _p(thr), ctypes.c_int32(tile))
+        assert np.array_equal(counts, oracle.proj_rank(x, ent, b, tgt, None, 1)), (B, N, k, tile)
+        gp = (rng.standard_normal((B, N)) * 0.1).astype(np.float32)
+        gx, ge, gb = np.zeros((B, k), np.float32), np.zeros((N, k), np.float32), np.zeros(N, np.float32)
+        emu.emu_proj_tail_bwd(_p(gp), _p(want), _p(x), _p(ent), ctypes.c_int64(B), ctypes.c_int64(N), ctypes.c_int32(k),
+                              _p(gx), _p(ge), _p(gb), ctypes.c_int32(int(rng.choice([1, 5, 296]))))
+        wx, we, wb = oracle.proj_tail_bwd(gp, want, x, ent)
+        for a, w in ((gx, wx), (ge, we), (gb, wb)):
+            assert np.abs(a - w).max() <= 2e-6 * max(1.0, np.abs(w).max()), (B, N, k)

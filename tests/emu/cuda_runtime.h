@@ -7,7 +7,9 @@
 // __shfl_xor_sync an exchange among the lanes named by its mask, atomics are host atomics, and
 // the rounding intrinsics map to the IEEE operations they denote (build with -ffp-contract=off).
 // It models correctness only (no memory model subtleties, no timing); blocks run one at a time,
-// so __shared__ variables are function-local statics.
+// so __shared__ variables are function-local statics.  A kernel thread that returns before a later
+// __syncthreads() would hang the barrier (on the GPU exited threads leave the barrier count); none of
+// the emulated kernels does that.
 #pragma once
 #include <math.h>
 #include <pthread.h>
@@ -77,29 +79,32 @@ inline uint32_t shfl(unsigned mask, uint32_t val, int src_lane) {
   return out;
 }
 
-// run `body` once per CUDA thread of every block of the grid (blocks sequentially)
+// run `body` once per CUDA thread of every block of the grid.  Blocks run one after the other (their
+// __shared__ variables are function-local statics); the host threads are created once per launch and
+// walk the blocks together, separated by the block barrier.
 inline void launch(dim3 grid, dim3 block, const std::function<void()>& body) {
   g_gridDim = grid; g_blockDim = block;
   const int nthreads = (int)(block.x * block.y * block.z);
-  for (unsigned bz = 0; bz < grid.z; ++bz)
-    for (unsigned by = 0; by < grid.y; ++by)
-      for (unsigned bx = 0; bx < grid.x; ++bx) {
-        BlockCtx ctx;
-        pthread_barrier_init(&ctx.barrier, nullptr, nthreads);
-        ctx.warps = std::vector<WarpExchange>((nthreads + 31) / 32);
-        g_block = &ctx;
-        std::vector<std::thread> th;
-        th.reserve(nthreads);
-        for (int t = 0; t < nthreads; ++t)
-          th.emplace_back([&, t] {
+  BlockCtx ctx;
+  pthread_barrier_init(&ctx.barrier, nullptr, nthreads);
+  ctx.warps = std::vector<WarpExchange>((nthreads + 31) / 32);
+  g_block = &ctx;
+  std::vector<std::thread> th;
+  th.reserve(nthreads);
+  for (int t = 0; t < nthreads; ++t)
+    th.emplace_back([&, t] {
+      t_threadIdx = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
+      for (unsigned bz = 0; bz < grid.z; ++bz)
+        for (unsigned by = 0; by < grid.y; ++by)
+          for (unsigned bx = 0; bx < grid.x; ++bx) {
             t_blockIdx = dim3(bx, by, bz);
-            t_threadIdx = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
             body();
-          });
-        for (auto& x : th) x.join();
-        pthread_barrier_destroy(&ctx.barrier);
-        g_block = nullptr;
-      }
+            pthread_barrier_wait(&ctx.barrier);   // end of this block for every thread
+          }
+    });
+  for (auto& x : th) x.join();
+  pthread_barrier_destroy(&ctx.barrier);
+  g_block = nullptr;
 }
 }  // namespace cuda_emu
 

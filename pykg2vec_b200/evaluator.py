@@ -273,9 +273,11 @@ class Evaluator:
         triples: TransH 349 -> 30 ms, TransD 344 -> 111 ms, identical ranks.  config.relation_grouped_eval:
         True / False forces the choice, None (default) decides by queries per distinct relation."""
         name = getattr(self.model, "model_name", "")
+        if len(rs) == 0:
+            return False
         if name == "transr":   # same scheme (P_r = normalize(ent) . M_r), proved on the oracle but not yet
             return getattr(self.config, "relation_grouped_eval", None) is True   # timed on a B200: on request only
-        if name not in ("transh", "transd") or len(rs) == 0:
+        if name not in ("transh", "transd"):
             return False
         force = getattr(self.config, "relation_grouped_eval", self.GROUPED_BY_DEFAULT)
         if force is not None:

@@ -234,7 +234,9 @@ int kge_normalize_rows_to(const float* table, int64_t rows, int64_t width, float
  * x [B,k] is the trunk's output (device, fp32 row-major), ent the [N,k] entity table, bias [N] or NULL.
  * preds[b*N + n] = sigmoid(sum_j x[b,j] ent[n,j] + bias[n]); canonical arithmetic: one sequential
  * fma chain over j from 0, one add, canonical sigmoid (DESIGN.md §3 rule 8) — bit-identical to
- * oracle/kge_oracle.c and to what kge_proj_rank compares. */
+ * oracle/kge_oracle.c and to what kge_proj_rank compares, whatever CTA tile the launcher picks
+ * (64x64 / 64x128 / 128x128 by problem size; the environment variable KGE_PROJ_TILE=0|1|2 forces one —
+ * a testing / benchmarking aid, read at every call). */
 int kge_proj_tail_fwd(const float* x, const float* ent, const float* bias, int64_t B, int64_t N,
                       int32_t k, float* preds, void* stream);
 

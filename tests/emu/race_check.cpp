@@ -17,8 +17,12 @@
 #include <string>
 
 #include "kge_conve.cuh"
+#ifndef RACE_CHECK_MINIMAL   // the barrier-free control build only needs the projection kernels
 #include "kge_grads.cuh"
 #include "kge_project.cuh"
+#else
+#include "kge_models.cuh"
+#endif
 
 namespace cuda_emu {
 thread_local dim3 t_threadIdx, t_blockIdx;
@@ -37,6 +41,7 @@ int num_tables(int) { return 0; }
 
 using namespace kge;
 
+#ifndef RACE_CHECK_MINIMAL
 constexpr int kMaxScratch = 8192;
 struct GradTables { float* t[KGE_MAX_TABLES]; };
 
@@ -120,6 +125,8 @@ static int run_score(const char* path) {
   return 0;
 }
 
+#endif  // RACE_CHECK_MINIMAL
+
 static std::vector<float> rnd(size_t n, unsigned seed, float scale = 0.5f, bool positive = false) {
   std::mt19937 g(seed);
   std::normal_distribution<float> d(0.f, scale);
@@ -187,6 +194,7 @@ static int run_conve() {
   return 0;
 }
 
+#ifndef RACE_CHECK_MINIMAL
 static int run_project() {
   const int d = 24; const long long N = 50, R = 3;
   auto ent = rnd(N * d, 1), rel = rnd(R * d, 2), w = rnd(R * d, 3), em = rnd(N * d, 4), rm = rnd(R * d, 5);
@@ -209,12 +217,16 @@ static int run_project() {
   return 0;
 }
 
+#endif  // RACE_CHECK_MINIMAL
+
 int main(int argc, char** argv) {
   const std::string cmd = argc > 1 ? argv[1] : "";
+#ifndef RACE_CHECK_MINIMAL
   if (cmd == "score" && argc > 2) return run_score(argv[2]);
+  if (cmd == "project") return run_project();
+#endif
   if (cmd == "proj") return run_proj();
   if (cmd == "conve") return run_conve();
-  if (cmd == "project") return run_project();
   fprintf(stderr, "usage: race_check score <blob> | proj | conve | project\n");
   return 64;
 }

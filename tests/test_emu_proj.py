@@ -9,32 +9,20 @@ oracle (bit-exact where the arithmetic is canonical, tolerance where the summati
 The real kernels are checked on the B200 by tests/test_gpu_proj.py."""
 import ctypes
 import os
-import subprocess
 
 import numpy as np
 import pytest
 
 import oracle
 
+import emu_build
+
 HERE = os.path.dirname(os.path.abspath(__file__))
-ROOT = os.path.dirname(HERE)
-SRC = os.path.join(HERE, "emu", "emu_proj.cpp")
-OUT = os.path.join(HERE, "emu", "_build", "libemu_proj.so")
-DEPS = [SRC, os.path.join(HERE, "emu", "cuda_runtime.h"), os.path.join(ROOT, "pykg2vec_b200", "csrc", "kge_conve.cuh"),
-        os.path.join(ROOT, "pykg2vec_b200", "csrc", "kge_proj.cuh"),
-        os.path.join(ROOT, "pykg2vec_b200", "csrc", "kge_common.cuh")]
 
 
 @pytest.fixture(scope="module")
 def emu():
-    if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in DEPS):
-        os.makedirs(os.path.dirname(OUT), exist_ok=True)
-        cmd = ["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-mfma",
-               "-pthread", "-w", "-I", os.path.join(HERE, "emu"), "-I", os.path.join(ROOT, "pykg2vec_b200", "csrc"),
-               "-o", OUT + ".tmp", SRC]
-        subprocess.run(cmd, check=True)
-        os.replace(OUT + ".tmp", OUT)
-    return ctypes.CDLL(OUT)
+    return ctypes.CDLL(emu_build.proj_lib())
 
 
 def _p(a):

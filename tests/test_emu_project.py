@@ -3,32 +3,18 @@ emulation of tests/emu/: for a fixed relation r, TransE over [P_r, rel] must giv
 scores BIT FOR BIT (the oracle evaluates both sides) — the identity the relation-grouped 1-vs-all
 evaluation of these models rests on."""
 import ctypes
-import os
-import subprocess
 
 import numpy as np
 import pytest
 
 import oracle
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-ROOT = os.path.dirname(HERE)
-SRC = os.path.join(HERE, "emu", "emu_project.cpp")
-OUT = os.path.join(HERE, "emu", "_build", "libemu_project.so")
-DEPS = [SRC, os.path.join(HERE, "emu", "cuda_runtime.h")] + \
-       [os.path.join(ROOT, "pykg2vec_b200", "csrc", f) for f in ("kge_project.cuh", "kge_models.cuh", "kge_common.cuh")]
+import emu_build
 
 
 @pytest.fixture(scope="module")
 def emu():
-    if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in DEPS):
-        os.makedirs(os.path.dirname(OUT), exist_ok=True)
-        cmd = ["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-mfma",
-               "-pthread", "-w", "-I", os.path.join(HERE, "emu"), "-I", os.path.join(ROOT, "pykg2vec_b200", "csrc"),
-               "-o", OUT + ".tmp", SRC]
-        subprocess.run(cmd, check=True)
-        os.replace(OUT + ".tmp", OUT)
-    return ctypes.CDLL(OUT)
+    return ctypes.CDLL(emu_build.models_lib())
 
 
 def _tables(name, N, R, d, seed):

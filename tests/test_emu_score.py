@@ -4,8 +4,6 @@ tests/emu/ with the thread mapping of score_fwd_kernel, against the oracle, BIT 
 tables of every golden case (both groupings).  A regression net for the model math that needs no
 GPU; the compiled kernels themselves are checked on the B200 by tests/test_gpu_score_rank.py."""
 import ctypes
-import os
-import subprocess
 
 import numpy as np
 import pytest
@@ -13,25 +11,14 @@ import pytest
 import golden_util as gu
 import oracle
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-ROOT = os.path.dirname(HERE)
-SRC = os.path.join(HERE, "emu", "emu_score.cpp")
-OUT = os.path.join(HERE, "emu", "_build", "libemu_score.so")
-DEPS = [SRC, os.path.join(HERE, "emu", "cuda_runtime.h")] + \
-       [os.path.join(ROOT, "pykg2vec_b200", "csrc", f) for f in ("kge_models.cuh", "kge_common.cuh")]
+import emu_build
+
 CASES = [n for n in gu.case_names()]
 
 
 @pytest.fixture(scope="module")
 def emu():
-    if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in DEPS):
-        os.makedirs(os.path.dirname(OUT), exist_ok=True)
-        cmd = ["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-mfma",
-               "-pthread", "-w", "-I", os.path.join(HERE, "emu"), "-I", os.path.join(ROOT, "pykg2vec_b200", "csrc"),
-               "-o", OUT + ".tmp", SRC]
-        subprocess.run(cmd, check=True)
-        os.replace(OUT + ".tmp", OUT)
-    return ctypes.CDLL(OUT)
+    return ctypes.CDLL(emu_build.models_lib())
 
 
 def _widths(om):
@@ -66,23 +53,12 @@ def test_emulated_score_functions_are_bit_exact(emu, name):
 
 
 # ---- backward: grad_group<MODEL, VEC> of kge_grads.cuh vs the reference's own autograd -------------
-SRC_BWD = os.path.join(HERE, "emu", "emu_bwd.cpp")
-OUT_BWD = os.path.join(HERE, "emu", "_build", "libemu_bwd.so")
 GRAD_TOL = 2e-4   # relative to the largest |gradient| of the table (as tests/test_gpu_train.py)
 
 
 @pytest.fixture(scope="module")
-def emu_bwd():
-    deps = [SRC_BWD, os.path.join(HERE, "emu", "cuda_runtime.h")] + \
-           [os.path.join(ROOT, "pykg2vec_b200", "csrc", f) for f in ("kge_grads.cuh", "kge_models.cuh", "kge_common.cuh")]
-    if not os.path.exists(OUT_BWD) or any(os.path.getmtime(d) > os.path.getmtime(OUT_BWD) for d in deps):
-        os.makedirs(os.path.dirname(OUT_BWD), exist_ok=True)
-        cmd = ["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-mfma",
-               "-pthread", "-w", "-I", os.path.join(HERE, "emu"), "-I", os.path.join(ROOT, "pykg2vec_b200", "csrc"),
-               "-o", OUT_BWD + ".tmp", SRC_BWD]
-        subprocess.run(cmd, check=True)
-        os.replace(OUT_BWD + ".tmp", OUT_BWD)
-    return ctypes.CDLL(OUT_BWD)
+def emu_bwd(emu):
+    return emu
 
 
 @pytest.mark.parametrize("name", [n for n in CASES if "pretrained" not in n])

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define KGE_ABI_VERSION 3
+#define KGE_ABI_VERSION 4
 #define KGE_MAX_TABLES 16
 
 /* status codes */
@@ -205,6 +205,22 @@ int kge_rank_1vsall(const kge_model_t* m, const kge_model_t* mq, int64_t row_lo,
 #define KGE_RANK_TAIL_ONLY 2
 #define KGE_RANK_HEAD_ONLY 4
 #define KGE_RANK_SINGLE_STREAM 8 /* do not overlap the two directions on an internal side stream */
+#define KGE_RANK_NO_TC 16 /* keep the sweep on the fp32 pipe (no tensor-core level; same counts either way) */
+
+/* Two-level exact sweep (TransE -l1 False, DistMult, CP, ComplEx, RESCAL, RotatE; >= 1024 candidate rows):
+ * level 1 evaluates the Q x N x K contraction on the tensor cores (tcgen05.mma, bf16 x 3 split, fp32
+ * accumulation in TMEM) and counts every candidate whose accumulator clears the query's threshold by
+ * more than a proven error bound; level 2 re-evaluates the few (query, candidate) pairs inside the
+ * band in the canonical fp32 arithmetic.  The counts equal the fp32 specification's for every input
+ * (DESIGN.md §4b).  kge_rank_tc_probe exposes level 1 of ONE direction (0 tail, 1 head) for tests and
+ * measurements: dots[Q * (row_hi-row_lo)] receives the raw accumulators D(q, c) (may be NULL), tau[Q*2]
+ * the per-query thresholds (certainly better: D > tau[2q]; certainly not: D < tau[2q+1]; may be NULL);
+ * counts[Q*4] is accumulated exactly as by kge_rank_1vsall (raw and "filtered" columns both get the raw
+ * count: no filter pass here).  KGE_ENOTSUP when the model / table size has no tensor-core sweep. */
+int kge_rank_tc_probe(const kge_model_t* m, const kge_model_t* mq, int64_t row_lo, int64_t row_hi,
+                      const int64_t* qh, const int64_t* qr, const int64_t* qt, int64_t Q, int direction,
+                      float* dots, float* tau, int32_t* counts, void* workspace, int64_t workspace_bytes,
+                      void* stream);
 
 /* ---- per-relation entity projection (relation-grouped evaluation of TransH / TransD) ----------
  * TransH.embed/_projection (pykg2vec/models/pairwise.py:166-182) and TransD.embed/_projection

@@ -11,7 +11,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_build", "libkge_b200.so")
 MAX_TABLES = 16
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 MODEL_IDS = {
     "transe": 0, "transh": 1, "transd": 2, "transr": 3, "rotate": 4, "hole": 5,
@@ -20,6 +20,7 @@ MODEL_IDS = {
 }
 GROUP_TAIL, GROUP_HEAD = 0, 1
 RANK_FORCE_GATHER, RANK_TAIL_ONLY, RANK_HEAD_ONLY = 1, 2, 4
+RANK_SINGLE_STREAM, RANK_NO_TC = 8, 16
 
 # every symbol include/kge_b200.h declares (tests check they are all exported)
 EXPORTS = [
@@ -27,7 +28,7 @@ EXPORTS = [
     "kge_score_fwd", "kge_score_bwd", "kge_normalize_rows",
     "kge_loss_pairwise_hinge", "kge_loss_pointwise_logistic", "kge_loss_selfadv", "kge_reg_fwd_bwd",
     "kge_train_pairwise_hinge_sgd", "kge_optim_apply_rows",
-    "kge_rank_workspace_bytes", "kge_rank_1vsall",
+    "kge_rank_workspace_bytes", "kge_rank_1vsall", "kge_rank_tc_probe",
     "kge_tripleset_capacity", "kge_tripleset_build", "kge_sample_negatives",
     "kge_proj_tail_fwd", "kge_proj_tail_bwd", "kge_proj_bce", "kge_proj_rank_workspace_bytes", "kge_proj_rank", "kge_proj_labels",
     "kge_conve_trunk_workspace_bytes", "kge_conve_trunk_fwd", "kge_project_entities", "kge_normalize_rows_to",
@@ -266,6 +267,27 @@ def rank_1vsall(desc, qh, qr, qt, filt_t=None, filt_h=None, counts=None, row_lo=
         _ptr(counts), _ptr(workspace), ctypes.c_int64(workspace.numel()), ctypes.c_int(flags), _stream()),
         "kge_rank_1vsall")
     return counts
+
+
+def rank_tc_probe(desc, qh, qr, qt, direction, want_dots=True, query_desc=None, row_lo=0, row_hi=None):
+    """Level 1 (tensor cores) of the two-level exact sweep for ONE direction (include/kge_b200.h):
+    -> (dots [Q, nc] raw accumulators or None, tau [Q,2] (hi, lo), counts [Q,4])."""
+    qh, qr, qt = _dev_i64(qh, "qh"), _dev_i64(qr, "qr"), _dev_i64(qt, "qt")
+    Q = qh.numel()
+    if row_hi is None:
+        row_hi = row_lo + desc.num_ent
+    nc = row_hi - row_lo
+    dots = torch.empty((Q, nc), dtype=torch.float32, device=qh.device) if want_dots else None
+    tau = torch.empty((Q, 2), dtype=torch.float32, device=qh.device)
+    counts = torch.zeros((Q, 4), dtype=torch.int32, device=qh.device)
+    ws = torch.empty(max(rank_workspace_bytes(desc, Q), 16), dtype=torch.uint8, device=qh.device)
+    m = desc.c_struct()
+    mq = query_desc.c_struct() if query_desc is not None else None
+    check(lib().kge_rank_tc_probe(
+        ctypes.byref(m), ctypes.byref(mq) if mq is not None else None, ctypes.c_int64(row_lo), ctypes.c_int64(row_hi),
+        _ptr(qh), _ptr(qr), _ptr(qt), ctypes.c_int64(Q), ctypes.c_int(direction), _ptr(dots), _ptr(tau),
+        _ptr(counts), _ptr(ws), ctypes.c_int64(ws.numel()), _stream()), "kge_rank_tc_probe")
+    return dots, tau, counts
 
 
 def project_entities(desc, r, out=None):

@@ -113,8 +113,92 @@ threshold_kernel(ModelParams P, const int64_t* __restrict__ qh, const int64_t* _
   if (valid && lane == 0) thr[g] = s;
 }
 
+// Level 2 of the tensor-core sweep (kge_rank_tc.cu): the (query, candidate) pairs whose tensor-core
+// accumulator fell inside the query's uncertainty band are re-evaluated with the canonical fp32
+// group function — the arithmetic of kge_score_fwd and of the fp32 sweeps — and compared exactly.
+// The last CTA to finish then commits the direction: counts += tc_counts, or (list overflow) raises
+// ctrl[3] so that the fp32 tiled sweep enqueued behind this kernel ranks the direction instead.
+template <int MODEL, int VEC, int GROUPING>
+__global__ void __launch_bounds__(kThreads)
+band_resolve_kernel(ModelParams P, const int64_t* __restrict__ qh, const int64_t* __restrict__ qr,
+                    const int64_t* __restrict__ qt, const float* __restrict__ thr,
+                    const unsigned long long* __restrict__ list, unsigned* __restrict__ ctrl, unsigned cap,
+                    int64_t Q, int32_t* __restrict__ tc_counts, int32_t* __restrict__ counts, int col,
+                    int scratch_floats) {
+  extern __shared__ float4 smem_f4[];
+  __shared__ int s_last;
+  float* scratch = reinterpret_cast<float*>(smem_f4) + (size_t)(threadIdx.x >> 3) * scratch_floats;
+  const int lane = threadIdx.x & 7;
+  const unsigned total = *reinterpret_cast<volatile unsigned*>(&ctrl[0]);
+  const bool overflow = total > cap || *reinterpret_cast<volatile unsigned*>(&ctrl[1]) != 0u;
+  if (!overflow) {
+    for (unsigned k = blockIdx.x * kGroupsPerCta + (threadIdx.x >> 3); k < total; k += gridDim.x * kGroupsPerCta) {
+      const unsigned long long pr = list[k];
+      const int64_t q = (int64_t)(pr >> 32), e = (int64_t)(pr & 0xffffffffull);
+      TripleRows R;
+      if (GROUPING == KGE_GROUP_TAIL)
+        resolve_rows<MODEL>(R, P, P.qtab, P.tab, P.qtab, __ldg(qh + q), __ldg(qr + q), e);
+      else
+        resolve_rows<MODEL>(R, P, P.tab, P.qtab, P.qtab, e, __ldg(qr + q), __ldg(qt + q));
+      const float s = score_group<MODEL, VEC, GROUPING>(R, P, lane, scratch);
+      if (lane == 0 && s < __ldg(thr + q)) atomicAdd(tc_counts + q, 1);
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&ctrl[2], 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (overflow) {
+    if (threadIdx.x == 0) ctrl[3] = 1u;
+    return;
+  }
+  for (int64_t q = threadIdx.x; q < Q; q += kThreads) {
+    const int c = *reinterpret_cast<volatile int32_t*>(tc_counts + q);
+    if (c) { atomicAdd(counts + q * 4 + col, c); atomicAdd(counts + q * 4 + col + 1, c); }
+  }
+}
+
 int check_model(const kge_model_t* m);
 int model_vec(const kge_model_t* m);
+
+int band_resolve(const kge_model_t* m, const kge_model_t* mq, int dir, const int64_t* qh, const int64_t* qr,
+                 const int64_t* qt, const float* thr, int64_t Q, const TcDirBuffers& B, int32_t* counts, int col,
+                 cudaStream_t st) {
+  const ModelParams P = make_params(m, mq);
+  int vec = model_vec(m);
+  const int vq = model_vec(mq);
+  if (vq < vec) vec = vq;
+  const int sf = (int)group_scratch_floats(m);
+  const size_t smem = (size_t)sf * kGroupsPerCta * sizeof(float);
+  const unsigned grid = (unsigned)(2 * sm_count());
+#define SET_SMEM_BR(K)                                                                        \
+  if (smem > 40 * 1024)                                                                       \
+    KGE_CUDA_OK(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#define CALL_BR(M, V)                                                                          \
+  do {                                                                                         \
+    if (dir == 0) { SET_SMEM_BR((band_resolve_kernel<M, V, KGE_GROUP_TAIL>));                  \
+      band_resolve_kernel<M, V, KGE_GROUP_TAIL><<<grid, kThreads, smem, st>>>(                 \
+          P, qh, qr, qt, thr, B.list, B.ctrl, B.cap, Q, B.tc_counts, counts, col, sf); }       \
+    else { SET_SMEM_BR((band_resolve_kernel<M, V, KGE_GROUP_HEAD>));                           \
+      band_resolve_kernel<M, V, KGE_GROUP_HEAD><<<grid, kThreads, smem, st>>>(                 \
+          P, qh, qr, qt, thr, B.list, B.ctrl, B.cap, Q, B.tc_counts, counts, col, sf); }       \
+  } while (0)
+  switch (m->model) {   // the models tc_supported() admits
+    case KGE_TRANSE: KGE_DISPATCH_VEC(KGE_TRANSE, vec, CALL_BR); break;
+    case KGE_DISTMULT: KGE_DISPATCH_VEC(KGE_DISTMULT, vec, CALL_BR); break;
+    case KGE_CP: KGE_DISPATCH_VEC(KGE_CP, vec, CALL_BR); break;
+    case KGE_COMPLEX: KGE_DISPATCH_VEC(KGE_COMPLEX, vec, CALL_BR); break;
+    case KGE_RESCAL: KGE_DISPATCH_VEC(KGE_RESCAL, vec, CALL_BR); break;
+    case KGE_ROTATE: KGE_DISPATCH_VEC(KGE_ROTATE, vec, CALL_BR); break;
+    default: set_error("band_resolve: model %d has no tensor-core sweep", (int)m->model); return KGE_ENOTSUP;
+  }
+#undef CALL_BR
+#undef SET_SMEM_BR
+  KGE_CHECK_LAUNCH("band_resolve_kernel");
+  return KGE_OK;
+}
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -192,8 +276,9 @@ extern "C" int kge_rank_1vsall(const kge_model_t* m, const kge_model_t* mq, int6
   const unsigned qgrid = (unsigned)((Q + kGroupsPerCta - 1) / kGroupsPerCta);
   const dim3 sgrid((unsigned)((nc + kCandsPerCta - 1) / kCandsPerCta), (unsigned)Q);
   const bool use_tiled = !(flags & KGE_RANK_FORCE_GATHER) && tiled_supported(m);
+  const bool use_tc = use_tiled && !(flags & KGE_RANK_NO_TC) && tc_supported(m, nc);
   if (use_tiled) {
-    rc = tiled_prepare_candidates(m, nc, tiled_ws, Q, st);
+    rc = tiled_prepare_candidates(m, nc, tiled_ws, Q, use_tc, st);
     if (rc) return rc;
   }
 
@@ -236,7 +321,7 @@ extern "C" int kge_rank_1vsall(const kge_model_t* m, const kge_model_t* mq, int6
 #undef CALL_THR
 
     if (use_tiled) {
-      rc = tiled_sweep(m, mq, dir, qh, qr, qt, thr, Q, nc, counts, col, tiled_ws, st);
+      rc = tiled_sweep(m, mq, dir, qh, qr, qt, thr, Q, nc, counts, col, tiled_ws, use_tc, nullptr, nullptr, st);
       if (rc) return rc;
     } else {
 #define CALL_SWEEP(M, V)                                                                       \
@@ -272,4 +357,33 @@ extern "C" int kge_rank_1vsall(const kge_model_t* m, const kge_model_t* mq, int6
     KGE_CUDA_OK(cudaStreamWaitEvent(main_st, side->join, 0));
   }
   return KGE_OK;
+}
+
+// Test / measurement aid for the tensor-core level of one direction: raw accumulators and the two
+// per-query thresholds (see include/kge_b200.h).
+extern "C" int kge_rank_tc_probe(const kge_model_t* m, const kge_model_t* mq, int64_t row_lo, int64_t row_hi,
+                                 const int64_t* qh, const int64_t* qr, const int64_t* qt, int64_t Q, int direction,
+                                 float* dots, float* tau, int32_t* counts, void* workspace, int64_t workspace_bytes,
+                                 void* stream) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  if (!mq) mq = m;
+  rc = check_model(mq);
+  if (rc) return rc;
+  if (Q <= 0 || Q > 65535 || !qh || !qr || !qt || !counts || !workspace || row_lo < 0 || row_hi <= row_lo ||
+      row_hi - row_lo > m->num_ent || (direction != 0 && direction != 1)) {
+    set_error("kge_rank_tc_probe: bad arguments"); return KGE_EINVAL;
+  }
+  const int64_t nc = row_hi - row_lo;
+  if (!tiled_supported(m) || !tc_supported(m, nc)) {
+    set_error("kge_rank_tc_probe: no tensor-core sweep for this model / table size"); return KGE_ENOTSUP;
+  }
+  if (workspace_bytes < kge_rank_workspace_bytes(m, Q)) { set_error("workspace too small"); return KGE_EWORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  float* thr = reinterpret_cast<float*>(workspace) + (direction == 0 ? 0 : Q);
+  void* tiled_ws = reinterpret_cast<char*>(workspace) + align_up((size_t)2 * (size_t)Q * sizeof(float), 256);
+  rc = tiled_prepare_candidates(m, nc, tiled_ws, Q, true, st);
+  if (rc) return rc;
+  return tiled_sweep(m, mq, direction, qh, qr, qt, thr, Q, nc, counts, direction == 0 ? 0 : 2, tiled_ws, true, dots,
+                     tau, st);
 }

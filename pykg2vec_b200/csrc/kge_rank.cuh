@@ -1,18 +1,43 @@
-// kge_rank.cuh — interface between the rank driver (kge_rank.cu) and the tiled sweep
-// (kge_rank_tiled.cu).
+// kge_rank.cuh — interface between the rank driver (kge_rank.cu), the fp32 tiled sweep
+// (kge_rank_tiled.cu) and the tensor-core sweep (kge_rank_tc.cu).
 #pragma once
 #include "kge_common.cuh"
 
 namespace kge {
 bool tiled_supported(const kge_model_t* m);
 size_t tiled_workspace_bytes(const kge_model_t* m, int64_t Q);
-// Once per rank call: candidate-side scratch (normalised / padded copies) shared by both
-// directions.
-int tiled_prepare_candidates(const kge_model_t* m, int64_t nc, void* ws, int64_t Q, cudaStream_t st);
+// Once per rank call: candidate-side scratch (normalised / padded copies, and the bf16 split of the
+// tensor-core path when `use_tc`) shared by both directions.
+int tiled_prepare_candidates(const kge_model_t* m, int64_t nc, void* ws, int64_t Q, bool use_tc, cudaStream_t st);
 // dir 0: tail sweep (TAIL grouping), 1: head sweep (HEAD grouping).  Writes the query vectors
 // AND the thresholds thr[q] (the target's own score), then adds
 // #{e < nc : score(q, e) < thr[q]} to counts[q*4+col] and counts[q*4+col+1].
+// use_tc: level 1 on the tensor cores + exact resolution of the ambiguous pairs (kge_rank_tc.cu);
+// the fp32 sweep is still enqueued but returns at once unless the pair list overflowed.
+// tc_dbg (tests): optional [Q][nc] raw tensor-core accumulators; tc_tau_out: optional [Q][2] thresholds.
 int tiled_sweep(const kge_model_t* m, const kge_model_t* mq, int dir, const int64_t* qh,
                 const int64_t* qr, const int64_t* qt, float* thr, int64_t Q, int64_t nc,
-                int32_t* counts, int col, void* ws, cudaStream_t st);
+                int32_t* counts, int col, void* ws, bool use_tc, float* tc_dbg, float* tc_tau_out,
+                cudaStream_t st);
+
+// ---- tensor-core sweep (kge_rank_tc.cu) -------------------------------------------------------------
+struct TcDirBuffers {
+  int32_t* tc_counts;          // [Q] certain counts of level 1 (+ the resolved pairs of level 2)
+  unsigned* ctrl;              // [0] pair-list length, [1] overflow, [2] ticket, [3] run-the-fp32-sweep flag
+  unsigned long long* list;    // (q << 32 | local candidate row)
+  unsigned cap;
+  const float* tau;            // [Q][2] accumulator thresholds (hi, lo)
+};
+bool tc_supported(const kge_model_t* m, int64_t nc);
+size_t tc_workspace_bytes(const kge_model_t* m, int64_t Q);
+int tc_prepare_candidates(const kge_model_t* m, const float* const cand[2], int64_t pitch, int64_t nc, void* tcws,
+                          int64_t Q, cudaStream_t st);
+int tc_sweep(const kge_model_t* m, int dir, const float* qvec, const float* thr, int64_t Q, int64_t nc, void* tcws,
+             TcDirBuffers* out, float* dbg, cudaStream_t st);
+// Level 2 (kge_rank.cu): exact fp32 re-evaluation of the listed pairs, then the last CTA adds the
+// direction's counts to counts[q*4+col], counts[q*4+col+1] — or, if the list overflowed, raises
+// ctrl[3] so that the fp32 sweep enqueued next does the whole direction instead.
+int band_resolve(const kge_model_t* m, const kge_model_t* mq, int dir, const int64_t* qh, const int64_t* qr,
+                 const int64_t* qt, const float* thr, int64_t Q, const TcDirBuffers& B, int32_t* counts, int col,
+                 cudaStream_t st);
 }  // namespace kge

@@ -1,0 +1,614 @@
+// kge_rank_tc.cu — 1-vs-all sweep on the 5th-generation tensor cores (tcgen05 + TMEM), EXACT.
+//
+// The batched 1-vs-all sweep of the dot-product / squared-distance models (DistMult, CP, ComplEx,
+// RESCAL's h^T M_r . t, TransE-L2, RotatE) is a Q x N x K contraction.  Ranks, however, are
+// specified in exact fp32 canonical arithmetic.  The two are reconciled by a
+// TWO-LEVEL comparison instead of trying to make the MMA bit-reproducible:
+//
+//   level 1 (this file, tensor cores): every fp32 operand x is split into two bf16 terms
+//       x0 = bf16_rn(x), x1 = bf16_rn(x - x0)            (|x - x0 - x1| <= 2^-18 |x|)
+//     and D(q,c) = sum_k a0 b0 + a0 b1 + a1 b0 is accumulated in fp32 in TMEM by three
+//     tcgen05.mma (kind::f16, bf16 inputs) passes per 16-wide k-step; operand tiles arrive by TMA
+//     (128-byte swizzle), accumulators are double buffered in TMEM and read back by tcgen05.ld.
+//     Squared distances use |q - c|^2 = |q|^2 - 2 (q.c - |c|^2/2): the candidate norm term rides
+//     in three extra k-columns (a 3-way bf16 split of |c|^2/2 against -1), so the epilogue only
+//     compares the accumulator with two per-query constants:
+//         D > tau_hi[q]  -> the candidate certainly outranks the target (counted here)
+//         D < tau_lo[q]  -> it certainly does not
+//         otherwise      -> (q, c) is appended to a list
+//     tau_hi/lo = centre -+ E with E a PROVEN bound on |D_tc - D_exact| + |canonical fp32 score -
+//     exact score| (prep_query below; derivation in DESIGN.md §4b).
+//   level 2 (kge_rank.cu, band_resolve_kernel): the listed pairs — a handful per query — are
+//     re-evaluated with the canonical fp32 group function (the arithmetic of kge_score_fwd /
+//     the fp32 sweeps / the CPU oracle) and compared exactly.
+//
+// The final counts therefore equal the fp32 specification's for every input.  If the list
+// overflows (degenerate tables: thousands of exact ties per query) the fp32 tiled sweep of
+// kge_rank_tiled.cu runs instead, decided on the device (no host sync).
+//
+// Replaces: Evaluator.test_tail_rank / test_head_rank forward over all N entities + topk
+// (pykg2vec/utils/evaluator.py:249-273,309-334) for models pairwise.py:56-93 (TransE, -l1 False),
+// :765-791 (RotatE), :829-865 (Rescal), pointwise.py:444-446 (DistMult), :163-188 (Complex),
+// :374-376 (CP).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "kge_models.cuh"
+#include "kge_rank.cuh"
+
+namespace kge {
+
+constexpr int kTcBM = 128;        // queries per CTA (UMMA M)
+constexpr int kTcBN = 128;        // candidates per tile (UMMA N)
+constexpr int kTcBK = 64;         // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int kTcThreads = 192;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int kTcTmemCols = 256;  // two accumulator stages of kTcBN fp32 columns
+constexpr int kTcMaxStages = 6;
+constexpr uint32_t kTcTileBytes = kTcBN * kTcBK * 2;   // one operand k-block tile: 128 rows x 128 B = 16 KB
+constexpr int kTcResidentMaxKb = 4;                    // query block stays in smem when Kp <= 256
+
+struct TcParams {
+  const float* tau;        // [Q][2]: tau_hi, tau_lo
+  int32_t* tc_counts;      // [Q]
+  unsigned* ctrl;          // [0] list length, [1] overflow, [2] ticket, [3] run-fallback flag
+  unsigned long long* list;
+  unsigned cap;
+  int64_t Q, nc;
+  int Kp, nkb, a_resident, nstages;
+  int tiles_per_cta, ntiles;
+  float* dbg;              // optional [Q][nc] raw accumulators (tests)
+};
+struct TcMaps { CUtensorMap a0, a1, b0, b1; };
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+KGE_DEV uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+KGE_DEV void tc_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(count) : "memory");
+}
+KGE_DEV void tc_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(bytes) : "memory");
+}
+KGE_DEV void tc_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
+}
+// Bounded wait: a protocol bug must end in a trap (a loud launch failure), never in a hung GPU.
+KGE_DEV void tc_mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = tc_smem_u32(bar);
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s at 1.9 GHz
+  }
+}
+KGE_DEV void tc_tma_load_2d(uint32_t dst_smem, const CUtensorMap* tm, int col, int row, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tm)), "r"(col), "r"(row), "r"(tc_smem_u32(bar))
+      : "memory");
+}
+KGE_DEV void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+KGE_DEV void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+KGE_DEV void tc_commit(uint64_t* bar) {   // arrives on `bar` when every MMA issued so far by this thread has completed
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+               ::"r"(tc_smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, bf16 inputs, fp32 accumulate, M = 128, N = kTcBN, K = 16
+KGE_DEV void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// shared-memory matrix descriptor: K-major operand tile [rows][64 bf16] written by TMA with the
+// 128-byte swizzle.  start address >> 4 in bits [0,14); leading byte offset (unused for swizzled
+// K-major, canonical value 1) in [16,30); stride byte offset = 8 rows x 128 B = 1024 (>> 4) in
+// [32,46); descriptor version 1 in [46,48); layout type SWIZZLE_128B = 2 in [61,64).
+KGE_DEV uint64_t tc_smem_desc(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor (kind::f16): D fp32 (bits [4,6) = 1), A and B bf16 ([7,10) = [10,13) = 1),
+// both K-major (bits 15, 16 = 0), N >> 3 in [17,23), M >> 4 in [24,29)
+constexpr uint32_t kTcIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcBN >> 3) << 17) |
+                              ((uint32_t)(kTcBM >> 4) << 24);
+
+KGE_DEV void tc_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+}
+KGE_DEV uint32_t tc_tmem_ld1(uint32_t taddr) {
+  uint32_t v;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+  return v;
+}
+KGE_DEV void tc_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- the sweep ------------------------------------------------------------------------------------
+// grid (splits, query blocks); CTA = 128 queries x a run of 128-candidate tiles.
+//   warp 0 lane 0 : TMA producer (query k-blocks once when they fit, candidate k-blocks through a
+//                   ring of stages)
+//   warp 1 lane 0 : issues the tcgen05.mma chain of a tile into accumulator stage t&1; tcgen05.commit
+//                   releases smem stages and publishes finished accumulators
+//   warps 2..5    : epilogue — warp w owns TMEM lanes 32*(w&3).. (= query rows), reads 32 columns
+//                   (= candidates) per tcgen05.ld and compares them with the row's two thresholds
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMaps TM) {
+  extern __shared__ unsigned char tc_smem_raw[];
+  const int t0 = blockIdx.x * P.tiles_per_cta;
+  const int ntl = min(P.tiles_per_cta, P.ntiles - t0);
+  if (ntl <= 0) return;
+  const uint32_t raw = tc_smem_u32(tc_smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B tiles need 1024-byte alignment
+  unsigned char* const gbase = tc_smem_raw + (base - raw);
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(gbase);    // control block: first 1024 bytes
+  uint64_t* const full = bars;                                  // [kTcMaxStages]
+  uint64_t* const empty = bars + kTcMaxStages;                  // [kTcMaxStages]
+  uint64_t* const a_full = bars + 2 * kTcMaxStages;             // [1]
+  uint64_t* const tmem_full = a_full + 1;                       // [2]
+  uint64_t* const tmem_empty = tmem_full + 2;                   // [2]
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(gbase + 512);
+  const uint32_t a_base = base + 1024u;                                            // resident query k-blocks
+  const uint32_t a_bytes = P.a_resident ? (uint32_t)P.nkb * 2u * kTcTileBytes : 0u;
+  const uint32_t st_base = a_base + a_bytes;
+  const uint32_t st_bytes = (P.a_resident ? 2u : 4u) * kTcTileBytes;              // [B0][B1]([A0][A1])
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int64_t q0 = (int64_t)blockIdx.y * kTcBM;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < P.nstages; ++s) { tc_mbar_init(&full[s], 1); tc_mbar_init(&empty[s], 1); }
+    tc_mbar_init(a_full, 1);
+    for (int s = 0; s < 2; ++s) { tc_mbar_init(&tmem_full[s], 1); tc_mbar_init(&tmem_empty[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {   // TMEM allocation is warp-collective; the same warp frees it
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(tc_smem_u32(tmem_slot)), "r"((uint32_t)kTcTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      if (P.a_resident) {
+        tc_mbar_expect_tx(a_full, a_bytes);
+        for (int kb = 0; kb < P.nkb; ++kb) {
+          tc_tma_load_2d(a_base + (uint32_t)kb * 2u * kTcTileBytes, &TM.a0, kb * kTcBK, (int)q0, a_full);
+          tc_tma_load_2d(a_base + (uint32_t)kb * 2u * kTcTileBytes + kTcTileBytes, &TM.a1, kb * kTcBK, (int)q0, a_full);
+        }
+      }
+      int stage = 0; uint32_t phase = 0;
+      for (int t = 0; t < ntl; ++t) {
+        const int row = (t0 + t) * kTcBN;
+        for (int kb = 0; kb < P.nkb; ++kb) {
+          tc_mbar_wait(&empty[stage], phase ^ 1u);
+          tc_mbar_expect_tx(&full[stage], st_bytes);
+          const uint32_t sb = st_base + (uint32_t)stage * st_bytes;
+          tc_tma_load_2d(sb, &TM.b0, kb * kTcBK, row, &full[stage]);
+          tc_tma_load_2d(sb + kTcTileBytes, &TM.b1, kb * kTcBK, row, &full[stage]);
+          if (!P.a_resident) {
+            tc_tma_load_2d(sb + 2u * kTcTileBytes, &TM.a0, kb * kTcBK, (int)q0, &full[stage]);
+            tc_tma_load_2d(sb + 3u * kTcTileBytes, &TM.a1, kb * kTcBK, (int)q0, &full[stage]);
+          }
+          if (++stage == P.nstages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      if (P.a_resident) { tc_mbar_wait(a_full, 0u); }
+      int stage = 0; uint32_t phase = 0;
+      for (int t = 0; t < ntl; ++t) {
+        const int as = t & 1;
+        tc_mbar_wait(&tmem_empty[as], (uint32_t)(((t >> 1) & 1) ^ 1));   // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * kTcBN);
+        for (int kb = 0; kb < P.nkb; ++kb) {
+          tc_mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sb = st_base + (uint32_t)stage * st_bytes;
+          const uint32_t b0 = sb, b1 = sb + kTcTileBytes;
+          const uint32_t a0 = P.a_resident ? a_base + (uint32_t)kb * 2u * kTcTileBytes : sb + 2u * kTcTileBytes;
+          const uint32_t a1 = a0 + kTcTileBytes;
+          const int nks = min(kTcBK / 16, (P.Kp - kb * kTcBK + 15) / 16);
+          const uint64_t da0 = tc_smem_desc(a0), da1 = tc_smem_desc(a1), db0 = tc_smem_desc(b0), db1 = tc_smem_desc(b1);
+          for (int k = 0; k < nks; ++k) {   // 16 bf16 = 32 bytes further along the swizzled row: +2 in the address field
+            const uint64_t ko = (uint64_t)(2 * k);
+            tc_mma(d_tmem, da0 + ko, db0 + ko, kTcIdesc, (kb | k) != 0 ? 1u : 0u);
+            tc_mma(d_tmem, da0 + ko, db1 + ko, kTcIdesc, 1u);
+            tc_mma(d_tmem, da1 + ko, db0 + ko, kTcIdesc, 1u);
+          }
+          tc_commit(&empty[stage]);                         // smem stage reusable once these MMAs are done
+          if (kb == P.nkb - 1) tc_commit(&tmem_full[as]);   // ... and the accumulator is complete
+          if (++stage == P.nstages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else {
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;
+    const int64_t q = q0 + row;
+    const bool live = q < P.Q;
+    const float tau_hi = live ? __ldg(P.tau + 2 * q) : INFINITY;
+    const float tau_lo = live ? __ldg(P.tau + 2 * q + 1) : INFINITY;
+    int cnt = 0;
+    for (int t = 0; t < ntl; ++t) {
+      const int as = t & 1;
+      tc_mbar_wait(&tmem_full[as], (uint32_t)((t >> 1) & 1));
+      tc_fence_after();
+      const int64_t cbase = (int64_t)(t0 + t) * kTcBN;
+      const int nvalid = (int)min((int64_t)kTcBN, P.nc - cbase);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * kTcBN);
+      for (int cb = 0; cb * 32 < nvalid; ++cb) {
+        uint32_t v[32];
+        tc_tmem_ld32(taddr + (uint32_t)(cb * 32), v);
+        tc_tmem_wait_ld();
+        const int nv = min(32, nvalid - cb * 32);
+        int hi = 0, lo = 0;
+        if (nv == 32) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float x = __uint_as_float(v[j]);
+            hi += (x > tau_hi) ? 1 : 0;
+            lo += (x >= tau_lo) ? 1 : 0;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float x = __uint_as_float(v[j]);
+            hi += (j < nv && x > tau_hi) ? 1 : 0;
+            lo += (j < nv && x >= tau_lo) ? 1 : 0;
+          }
+        }
+        cnt += hi;
+        if (P.dbg && live) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nv) P.dbg[(size_t)q * (size_t)P.nc + (size_t)(cbase + cb * 32 + j)] = __uint_as_float(v[j]);
+        }
+        if (__any_sync(0xffffffffu, lo != hi)) {   // rare: some row of this warp has candidates inside its band
+          for (int j = 0; j < nv; ++j) {
+            const float x = __uint_as_float(tc_tmem_ld1(taddr + (uint32_t)(cb * 32 + j)));
+            tc_tmem_wait_ld();
+            if (x >= tau_lo && !(x > tau_hi)) {
+              const unsigned idx = atomicAdd(&P.ctrl[0], 1u);
+              if (idx < P.cap) P.list[idx] = ((unsigned long long)q << 32) | (unsigned long long)(cbase + cb * 32 + j);
+              else P.ctrl[1] = 1u;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc_mbar_arrive(&tmem_empty[as]);
+    }
+    if (live && cnt) atomicAdd(P.tc_counts + q, cnt);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTcTmemCols) : "memory");
+  }
+}
+
+// ---- operand preparation --------------------------------------------------------------------------
+KGE_DEV double tc_group_sum_d(double v) {
+  const unsigned m = group_mask();
+  v += __shfl_xor_sync(m, v, 4);
+  v += __shfl_xor_sync(m, v, 2);
+  v += __shfl_xor_sync(m, v, 1);
+  return v;
+}
+KGE_DEV void tc_split_store(__nv_bfloat16* o0, __nv_bfloat16* o1, float4 x, float sign) {
+  __nv_bfloat16 h[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float xv = sign * f4_get(x, e);
+    h[e] = __float2bfloat16_rn(xv);
+    l[e] = __float2bfloat16_rn(__fsub_rn(xv, __bfloat162float(h[e])));   // xv - h is exact in fp32
+  }
+  *reinterpret_cast<uint2*>(o0) = *reinterpret_cast<const uint2*>(h);
+  *reinterpret_cast<uint2*>(o1) = *reinterpret_cast<const uint2*>(l);
+}
+
+// One 8-lane group per candidate row: bf16 split of its KC arrays (concatenated along k), the three
+// norm columns (squared-distance models) and the running max of |c|^2.
+__global__ void __launch_bounds__(256)
+tc_prep_cand_kernel(const float* __restrict__ c0, const float* __restrict__ c1, int64_t pitch, int64_t nc, int dp,
+                    int KC, int Kp, int aug, __nv_bfloat16* __restrict__ B0, __nv_bfloat16* __restrict__ B1,
+                    unsigned* __restrict__ cmax_bits) {
+  const int lane = threadIdx.x & 7;
+  const int64_t e = (int64_t)blockIdx.x * 32 + (threadIdx.x >> 3);
+  if (e >= nc) return;
+  const int nchp = dp >> 2;
+  __nv_bfloat16* o0 = B0 + (size_t)e * Kp;
+  __nv_bfloat16* o1 = B1 + (size_t)e * Kp;
+  double ss = 0.0;
+  for (int k = 0; k < KC; ++k) {
+    const float* row = (k == 0 ? c0 : c1) + (size_t)e * pitch;
+    for (int c = lane; c < nchp; c += 8) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(row) + c);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ss += (double)f4_get(x, j) * (double)f4_get(x, j);
+      tc_split_store(o0 + k * dp + 4 * c, o1 + k * dp + 4 * c, x, 1.0f);
+    }
+  }
+  ss = tc_group_sum_d(ss);
+  const int K = KC * dp;
+  for (int c = K / 4 + lane; c < Kp / 4; c += 8) {   // norm columns + zero padding (K and Kp are multiples of 4)
+    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { h[j] = __float2bfloat16_rn(0.f); l[j] = h[j]; }
+    if (aug && c == K / 4) {   // |c|^2 / 2 = n0 + n1 + n2 (+ <= 2^-26 relative), multiplied by the query's -1 columns
+      const float half = (float)(0.5 * ss);
+      const __nv_bfloat16 n0 = __float2bfloat16_rn(half);
+      const float r1 = __fsub_rn(half, __bfloat162float(n0));
+      const __nv_bfloat16 n1 = __float2bfloat16_rn(r1);
+      const __nv_bfloat16 n2 = __float2bfloat16_rn(__fsub_rn(r1, __bfloat162float(n1)));
+      h[0] = n0; h[1] = n1; h[2] = n2;
+    }
+    *reinterpret_cast<uint2*>(o0 + 4 * c) = *reinterpret_cast<const uint2*>(h);
+    *reinterpret_cast<uint2*>(o1 + 4 * c) = *reinterpret_cast<const uint2*>(l);
+  }
+  if (lane == 0) atomicMax(cmax_bits, __float_as_uint(__double2float_ru(ss)));   // non-negative floats order like their bits
+}
+
+// The L2 sum-domain threshold of kge_rank_tiled.cu (rule 7 of DESIGN.md §3), restated for this file.
+KGE_DEV float tc_sqrt_domain_threshold(float th) {
+  if (!(th > 0.f)) return 0.f;
+  float x = fmul(th, th);
+  while (__fsqrt_rn(x) >= th) x = __uint_as_float(__float_as_uint(x) - 1u);
+  while (__fsqrt_rn(x) < th) x = __uint_as_float(__float_as_uint(x) + 1u);
+  return x;
+}
+
+// One 8-lane group per query: bf16 split of its KQ query vectors (sign -1 for the head sweep of the
+// translational models, whose canonical distance is |c + q|), the -1 norm columns, and the two
+// accumulator thresholds.  kind: 0 dot product (better <=> sum > -thr), 1 squared distance compared in
+// the sum domain (TransE-L2), 2 squared distance minus margin (RotatE).
+//
+// Error budget (all in double, rounded outwards to float at the end); A = |q| * max|c| >= sum |q_k c_k|:
+//   split     : |x - x0 - x1| <= 2^-18 |x| per operand -> dropped terms <= 3 * 2^-18 * 1.01 A   (bounded by 2^-16 A)
+//   accumulate: the tensor core adds exact products into an fp32 accumulator; each of the nmma
+//               instructions may lose <= 2 ulp of the running magnitude (<= A)                  -> nmma * 2^-22 A
+//   E_tc = 2 * (2^-16 + nmma * 2^-22) * A      (factor 2: safety; tests measure the real error)
+//   norm columns: 3-way bf16 split of |c|^2/2, float rounding of it                              -> 2^-22 max|c|^2
+//   canonical fp32 chain vs exact value of the same fp32 operands (RSUM, 8 partials, K/8 fma each
+//               + 3 butterfly adds; squared distances add one rounding of (q - c) per element):
+//               gamma = (K/8 + 8) * 2^-24 (+ 2^-22)  times  A  (dot)  or  (|q| + max|c|)^2  (distance)
+__global__ void __launch_bounds__(256)
+tc_prep_query_kernel(const float* __restrict__ qvec, const float* __restrict__ thr, int64_t Q, int dp, int KQ,
+                     int Kp, int kind, float sign, float margin, const unsigned* __restrict__ cmax_bits,
+                     __nv_bfloat16* __restrict__ A0, __nv_bfloat16* __restrict__ A1, float* __restrict__ tau,
+                     int32_t* __restrict__ tc_counts, unsigned* __restrict__ ctrl) {
+  if (blockIdx.x == 0 && threadIdx.x < 4) ctrl[threadIdx.x] = 0u;   // list length, overflow, ticket, fallback flag
+  const int lane = threadIdx.x & 7;
+  const int64_t q = (int64_t)blockIdx.x * 32 + (threadIdx.x >> 3);
+  if (q >= Q) return;
+  const int nchp = dp >> 2;
+  const int K = KQ * dp;
+  __nv_bfloat16* o0 = A0 + (size_t)q * Kp;
+  __nv_bfloat16* o1 = A1 + (size_t)q * Kp;
+  const float* src = qvec + (size_t)q * K;
+  double ss = 0.0;
+  for (int c = lane; c < KQ * nchp; c += 8) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(src) + c);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ss += (double)f4_get(x, j) * (double)f4_get(x, j);
+    tc_split_store(o0 + 4 * c, o1 + 4 * c, x, sign);
+  }
+  ss = tc_group_sum_d(ss);
+  for (int c = K / 4 + lane; c < Kp / 4; c += 8) {
+    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { h[j] = __float2bfloat16_rn(0.f); l[j] = h[j]; }
+    if (kind != 0 && c == K / 4) { h[0] = h[1] = h[2] = __float2bfloat16_rn(-1.0f); }
+    *reinterpret_cast<uint2*>(o0 + 4 * c) = *reinterpret_cast<const uint2*>(h);
+    *reinterpret_cast<uint2*>(o1 + 4 * c) = *reinterpret_cast<const uint2*>(l);
+  }
+  if (lane != 0) return;
+  tc_counts[q] = 0;
+  const double cmax2 = (double)__uint_as_float(*cmax_bits);
+  const double cmax = sqrt(cmax2) * (1.0 + 1e-7), nq = sqrt(ss) * (1.0 + 1e-7);
+  const double A = nq * cmax;
+  const int nmma = 3 * ((Kp + 15) / 16);
+  const double e_tc = 2.0 * (ldexp(1.0, -16) + (double)nmma * ldexp(1.0, -22)) * A + ldexp(1.0, -22) * cmax2 + 1e-30;
+  const double gamma = ((double)K / 8.0 + 8.0) * ldexp(1.0, -24);
+  const float th = thr[q];
+  double centre, half;
+  if (kind == 0) {
+    centre = -(double)th;                        // canonical: -sum < th  <=>  sum > -th (negation is exact)
+    half = e_tc + gamma * A;
+  } else {
+    const double smax = (nq + cmax) * (nq + cmax);
+    const double g2 = gamma + ldexp(1.0, -22);
+    if (kind == 1) {                             // canonical: sum < T(th)
+      const double T = (double)tc_sqrt_domain_threshold(th);
+      centre = 0.5 * (ss - T);
+      half = 0.5 * (2.0 * e_tc + g2 * smax) + ldexp(1.0, -50) * ss;
+    } else {                                     // canonical: fsub(sum, margin) < th
+      centre = 0.5 * (ss - (double)th - (double)margin);
+      half = 0.5 * (2.0 * e_tc + g2 * smax + ldexp(1.0, -24) * (smax * 1.01 + fabs((double)margin))) + ldexp(1.0, -50) * ss;
+    }
+  }
+  // NaN thresholds propagate: every comparison with them is false, as `s < NaN` is in the exact path
+  tau[2 * q] = __double2float_ru(centre + half);
+  tau[2 * q + 1] = __double2float_rd(centre - half);
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+static inline size_t tc_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static int tc_dp(const kge_model_t* m) { return ((m->dim + 3) / 4) * 4; }
+static int tc_kq(int model) { return (model == KGE_ROTATE || model == KGE_COMPLEX) ? 2 : 1; }
+static int tc_kind(const kge_model_t* m) {
+  return (m->model == KGE_TRANSE) ? 1 : (m->model == KGE_ROTATE ? 2 : 0);
+}
+static int tc_kp(const kge_model_t* m) {
+  const int K = tc_kq(m->model) * tc_dp(m) + (tc_kind(m) != 0 ? 3 : 0);
+  return (K + 15) / 16 * 16;
+}
+
+bool tc_supported(const kge_model_t* m, int64_t nc) {
+  if (nc < 1024) return false;                      // small tables: the fp32 sweep is launch-latency sized anyway
+  if (nc >= ((int64_t)1 << 31)) return false;
+  switch (m->model) {
+    case KGE_TRANSE: return m->l1_flag == 0;        // L1 distances are not a contraction
+    case KGE_DISTMULT: case KGE_CP: case KGE_COMPLEX: case KGE_RESCAL: case KGE_ROTATE: return true;
+    default: return false;                          // HoLE / SimplE / TransM: saturating or scaled finalisers
+  }
+}
+
+unsigned tc_list_capacity(int64_t Q) {
+  int64_t cap = 256 * Q;
+  if (cap < 16384) cap = 16384;
+  if (cap > (1 << 24)) cap = 1 << 24;
+  return (unsigned)cap;
+}
+
+// workspace carve-up (after the fp32 tiled sweep's region)
+struct TcLayout {
+  size_t a[2][2], tau[2], cnt[2], ctrl[2], list[2], b[2], cmax, total;
+};
+static TcLayout tc_layout(const kge_model_t* m, int64_t Q) {
+  TcLayout L;
+  const size_t Kp = (size_t)tc_kp(m);
+  size_t o = 0;
+  for (int d = 0; d < 2; ++d) {
+    for (int k = 0; k < 2; ++k) { L.a[d][k] = o; o += tc_align_up((size_t)Q * Kp * 2, 256); }
+    L.tau[d] = o; o += tc_align_up((size_t)Q * 2 * sizeof(float), 256);
+    L.cnt[d] = o; o += tc_align_up((size_t)Q * sizeof(int32_t), 256);
+    L.ctrl[d] = o; o += 256;
+    L.list[d] = o; o += tc_align_up((size_t)tc_list_capacity(Q) * 8, 256);
+  }
+  for (int k = 0; k < 2; ++k) { L.b[k] = o; o += tc_align_up((size_t)m->num_ent * Kp * 2, 256); }
+  L.cmax = o; o += 256;
+  L.total = o;
+  return L;
+}
+size_t tc_workspace_bytes(const kge_model_t* m, int64_t Q) {
+  if (!tc_supported(m, (int64_t)1 << 20)) return 0;   // model-level support (row count is only known per call)
+  return tc_layout(m, Q).total;
+}
+
+typedef CUresult (*TcEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                               const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TcEncodeFn tc_encode_fn() {
+  static TcEncodeFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess || !p)
+    return nullptr;
+  fn = reinterpret_cast<TcEncodeFn>(p);
+  return fn;
+}
+// bf16 matrix [rows][Kp] row-major; box = {64 columns (128 bytes), 128 rows}, 128-byte swizzle, zero fill
+static int tc_make_map(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t Kp) {
+  TcEncodeFn fn = tc_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled is not available"); return KGE_ECUDA; }
+  const cuuint64_t gdim[2] = {Kp, rows};
+  const cuuint64_t gstride[1] = {Kp * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)kTcBK, (cuuint32_t)kTcBN};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (bf16) failed (%d)", (int)r); return KGE_ECUDA; }
+  return KGE_OK;
+}
+
+// candidate split of the fp32 arrays the fp32 sweep would read (cand[k], row pitch `pitch` floats)
+int tc_prepare_candidates(const kge_model_t* m, const float* const cand[2], int64_t pitch, int64_t nc, void* tcws,
+                          int64_t Q, cudaStream_t st) {
+  const TcLayout L = tc_layout(m, Q);
+  char* w = reinterpret_cast<char*>(tcws);
+  unsigned* cmax = reinterpret_cast<unsigned*>(w + L.cmax);
+  KGE_CUDA_OK(cudaMemsetAsync(cmax, 0, sizeof(unsigned), st));
+  const int KC = tc_kq(m->model);
+  tc_prep_cand_kernel<<<(unsigned)((nc + 31) / 32), 256, 0, st>>>(
+      cand[0], KC == 2 ? cand[1] : cand[0], pitch, nc, tc_dp(m), KC, tc_kp(m), tc_kind(m) != 0 ? 1 : 0,
+      reinterpret_cast<__nv_bfloat16*>(w + L.b[0]), reinterpret_cast<__nv_bfloat16*>(w + L.b[1]), cmax);
+  KGE_CHECK_LAUNCH("tc_prep_cand_kernel");
+  return KGE_OK;
+}
+
+// Level 1 of one direction: query split + thresholds, then the tensor-core sweep.  On return (in
+// stream order) tc_counts[q] holds the certain counts and list/ctrl the ambiguous pairs.
+int tc_sweep(const kge_model_t* m, int dir, const float* qvec, const float* thr, int64_t Q, int64_t nc, void* tcws,
+             TcDirBuffers* out, float* dbg, cudaStream_t st) {
+  const TcLayout L = tc_layout(m, Q);
+  char* w = reinterpret_cast<char*>(tcws);
+  const int Kp = tc_kp(m), KQ = tc_kq(m->model), dp = tc_dp(m), kind = tc_kind(m);
+  __nv_bfloat16* A0 = reinterpret_cast<__nv_bfloat16*>(w + L.a[dir][0]);
+  __nv_bfloat16* A1 = reinterpret_cast<__nv_bfloat16*>(w + L.a[dir][1]);
+  float* tau = reinterpret_cast<float*>(w + L.tau[dir]);
+  int32_t* cnt = reinterpret_cast<int32_t*>(w + L.cnt[dir]);
+  unsigned* ctrl = reinterpret_cast<unsigned*>(w + L.ctrl[dir]);
+  unsigned long long* list = reinterpret_cast<unsigned long long*>(w + L.list[dir]);
+  const unsigned* cmax = reinterpret_cast<const unsigned*>(w + L.cmax);
+  // head sweep of TransE: canonical distance is |c + q| with q = r^ - t^  ->  contract with -q
+  const float sign = (m->model == KGE_TRANSE && dir == 1) ? -1.0f : 1.0f;
+  tc_prep_query_kernel<<<(unsigned)((Q + 31) / 32), 256, 0, st>>>(qvec, thr, Q, dp, KQ, Kp, kind, sign, m->margin,
+                                                                cmax, A0, A1, tau, cnt, ctrl);
+  KGE_CHECK_LAUNCH("tc_prep_query_kernel");
+
+  TcParams P;
+  P.tau = tau; P.tc_counts = cnt; P.ctrl = ctrl; P.list = list; P.cap = tc_list_capacity(Q);
+  P.Q = Q; P.nc = nc; P.Kp = Kp; P.nkb = (Kp + kTcBK - 1) / kTcBK;
+  P.a_resident = P.nkb <= kTcResidentMaxKb ? 1 : 0;
+  const size_t budget = 227 * 1024 - 2048;   // control block + alignment slack
+  const size_t a_bytes = P.a_resident ? (size_t)P.nkb * 2 * kTcTileBytes : 0;
+  const size_t st_bytes = (P.a_resident ? 2 : 4) * (size_t)kTcTileBytes;
+  int nstages = (int)((budget - a_bytes) / st_bytes);
+  if (nstages > kTcMaxStages) nstages = kTcMaxStages;
+  if (nstages < 2) { set_error("tc_sweep: shared-memory plan failed"); return KGE_ENOTSUP; }
+  P.nstages = nstages;
+  P.ntiles = (int)((nc + kTcBN - 1) / kTcBN);
+  const int qblocks = (int)((Q + kTcBM - 1) / kTcBM);
+  int splits = (sm_count() + qblocks - 1) / qblocks;
+  if (splits < 1) splits = 1;
+  if (splits > P.ntiles) splits = P.ntiles;
+  P.tiles_per_cta = (P.ntiles + splits - 1) / splits;
+  splits = (P.ntiles + P.tiles_per_cta - 1) / P.tiles_per_cta;
+  P.dbg = dbg;
+  TcMaps TM;
+  int rc = tc_make_map(&TM.a0, A0, (uint64_t)Q, (uint64_t)Kp); if (rc) return rc;
+  rc = tc_make_map(&TM.a1, A1, (uint64_t)Q, (uint64_t)Kp); if (rc) return rc;
+  rc = tc_make_map(&TM.b0, w + L.b[0], (uint64_t)nc, (uint64_t)Kp); if (rc) return rc;
+  rc = tc_make_map(&TM.b1, w + L.b[1], (uint64_t)nc, (uint64_t)Kp); if (rc) return rc;
+  const size_t smem = 2048 + a_bytes + (size_t)nstages * st_bytes;
+  KGE_CUDA_OK(cudaFuncSetAttribute(tc_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tc_sweep_kernel<<<dim3((unsigned)splits, (unsigned)qblocks), kTcThreads, smem, st>>>(P, TM);
+  KGE_CHECK_LAUNCH("tc_sweep_kernel");
+  out->tc_counts = cnt; out->ctrl = ctrl; out->list = list; out->cap = P.cap; out->tau = tau;
+  return KGE_OK;
+}
+
+}  // namespace kge

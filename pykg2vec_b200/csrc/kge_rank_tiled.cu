@@ -56,6 +56,9 @@ struct TiledParams {
   int col, l1;
   int fin;      // DOT ops: 0 -> -sum ; 1 -> -sigmoid(sum) (HoLE) ; 2 -> -clamp(sum, +-20) (SimplE)
   float margin;
+  // tensor-core path: the fp32 sweep is enqueued behind it as the exact fallback and runs only when
+  // the device raised this flag (ambiguous-pair list overflow); nullptr -> always run
+  const unsigned* run_flag;
 };
 
 // ---- mbarrier / bulk-copy primitives ------------------------------------------------------
@@ -203,6 +206,7 @@ __device__ __forceinline__ void sweep_tiled_body(const TiledParams& P, const Til
   const int t0 = blockIdx.x * P.tiles_per_cta;
   const int ntile_local = min(P.tiles_per_cta, P.ntiles - t0);
   if (ntile_local <= 0) return;
+  if (P.run_flag != nullptr && *reinterpret_cast<const volatile unsigned*>(P.run_flag) == 0u) return;
   const int T = ntile_local * P.nslabs;
   const bool sum_domain = (OP == OP_TRANS_T || OP == OP_TRANS_H) && !L1 && P.qscale == nullptr;
 
@@ -609,12 +613,30 @@ static float* cand_scratch_ptr(const kge_model_t* m, void* ws, int64_t Q) {
   w += 2 * align_up((size_t)Q * sizeof(float), 256);
   return reinterpret_cast<float*>(w);
 }
+static size_t cand_scratch_bytes(const kge_model_t* m) {
+  return align_up((size_t)num_cand_tables(m->model) * (size_t)m->num_ent * (size_t)dp_of(m) * sizeof(float), 256);
+}
+// the tensor-core path's region follows the candidate scratch
+static void* tc_ws_ptr(const kge_model_t* m, void* ws, int64_t Q) {
+  return reinterpret_cast<char*>(cand_scratch_ptr(m, ws, Q)) + cand_scratch_bytes(m);
+}
 
-int tiled_prepare_candidates(const kge_model_t* m, int64_t nc, void* ws, int64_t Q, cudaStream_t st) {
+int tiled_prepare_candidates(const kge_model_t* m, int64_t nc, void* ws, int64_t Q, bool use_tc, cudaStream_t st) {
   if (m->model == KGE_CP || is_simple(m->model)) return KGE_OK;  // per direction, see tiled_sweep
   const float* src[2];
-  if (!cand_sources(m, 0, src)) return KGE_OK;
-  return fill_cand_scratch(m, src, num_cand_tables(m->model), nc, cand_scratch_ptr(m, ws, Q), st);
+  const int KC = num_cand_tables(m->model);
+  float* cscratch = cand_scratch_ptr(m, ws, Q);
+  const bool scratch = cand_sources(m, 0, src);
+  if (scratch) {
+    int rc = fill_cand_scratch(m, src, KC, nc, cscratch, st);
+    if (rc) return rc;
+  }
+  if (use_tc) {   // bf16 split of exactly the fp32 arrays the fp32 sweep reads
+    const float* cand[2] = {scratch ? cscratch : src[0],
+                            KC == 2 ? (scratch ? cscratch + (size_t)nc * dp_of(m) : src[1]) : nullptr};
+    return tc_prepare_candidates(m, cand, scratch ? dp_of(m) : m->dim, nc, tc_ws_ptr(m, ws, Q), Q, st);
+  }
+  return KGE_OK;
 }
 
 bool tiled_supported(const kge_model_t* m) {
@@ -633,7 +655,8 @@ size_t tiled_workspace_bytes(const kge_model_t* m, int64_t Q) {
   bytes += 2 * align_up((size_t)Q * sizeof(float), 256);                                  // qscale, one per direction
   // candidate scratch (always reserved: alignment of the tables is only known at call time);
   // CP sweeps the object table for tails and the subject table for heads -> one table at a time
-  bytes += align_up((size_t)num_cand_tables(m->model) * (size_t)m->num_ent * dp * sizeof(float), 256);
+  bytes += cand_scratch_bytes(m);
+  bytes += tc_workspace_bytes(m, Q);
   return bytes;
 }
 
@@ -698,7 +721,8 @@ static int launch_sweep(const TiledParams& P, int QBLK, size_t smem, cudaStream_
 
 int tiled_sweep(const kge_model_t* m, const kge_model_t* mq, int dir, const int64_t* qh,
                 const int64_t* qr, const int64_t* qt, float* thr, int64_t Q, int64_t nc,
-                int32_t* counts, int col, void* ws, cudaStream_t st) {
+                int32_t* counts, int col, void* ws, bool use_tc, float* tc_dbg, float* tc_tau_out,
+                cudaStream_t st) {
   const int model = m->model;
   const int d = m->dim, dp = dp_of(m);
   const int op = (model == KGE_TRANSE || model == KGE_TRANSM) ? (dir == 0 ? OP_TRANS_T : OP_TRANS_H)
@@ -783,6 +807,25 @@ int tiled_sweep(const kge_model_t* m, const kge_model_t* mq, int dir, const int6
     nslabs = (dp + DS - 1) / DS;
   }
   const size_t smem = bytes_for(DS, nslabs > 1 ? 2 : 1);
+  P.run_flag = nullptr;
+  if (use_tc) {
+    // level 1 on the tensor cores, level 2 = exact fp32 resolution of the ambiguous pairs; the fp32
+    // sweep below stays enqueued as the fallback and returns at once unless the list overflowed
+    void* tcws = tc_ws_ptr(m, ws, Q);
+    if (model == KGE_CP) {   // candidate table differs per direction
+      const float* cand[2] = {P.cand[0], nullptr};
+      int rc = tc_prepare_candidates(m, cand, P.cand_pitch, nc, tcws, Q, st);
+      if (rc) return rc;
+    }
+    TcDirBuffers B;
+    int rc = tc_sweep(m, dir, qvec, thr, Q, nc, tcws, &B, tc_dbg, st);
+    if (rc) return rc;
+    if (tc_tau_out)
+      KGE_CUDA_OK(cudaMemcpyAsync(tc_tau_out, B.tau, (size_t)Q * 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    rc = band_resolve(m, mq, dir, qh, qr, qt, thr, Q, B, counts, col, st);
+    if (rc) return rc;
+    P.run_flag = B.ctrl + 3;
+  }
   P.qvec = qvec; P.thr = thr; P.qscale = (model == KGE_TRANSM) ? qscale : nullptr;
   P.Q = Q; P.nc = nc; P.dp = dp; P.DS = DS; P.nslabs = nslabs;
   P.ntiles = (int)((nc + kCBLK - 1) / kCBLK);

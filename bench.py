@@ -2,10 +2,10 @@
 """bench.py — scored triples/sec (train + 1-vs-all eval), FB15k-237 shape, TransE d=200.
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (port)
+    python bench.py --impl reference --steps K --warmup W    # the UNMODIFIED reference on the host cores
 
 Workload (BASELINE.json configs[1]): TransE, N=14,541 entities, R=237 relations, d=200,
-L2 norm, hinge margin 5.0 (pykg2vec/hyperparams/TransE.yaml:10), SGD lr 0.01, batch 512,
+L2 norm (-l1 False), hinge margin 5.0 (pykg2vec/hyperparams/TransE.yaml:10), SGD lr 0.01, batch 512,
 neg_rate 1, synthetic FB15k-237-shaped graph (no dataset is obtainable offline), tables
 xavier-uniform random-init.
 
@@ -19,12 +19,14 @@ One STEP = what the reference repeats on this path for one batch of each kind:
 `value` = scored triples / second of the whole job with inputs resident in HBM;
 `e2e` = the same through the host API (Trainer.train_batch + Evaluator.rank_triples:
 host id buffers in, pinned H2D, kernels, D2H of loss and ranks) — copies inside the timing.
+`train_triples_per_s` / `eval_scores_per_s` time the two halves separately (the eval half is
+99.99 % of the scored triples, so `value` alone says nothing about training).
 
-Multi-GPU (torchrun, one rank per GPU): weak scaling — every rank brings its own training
-batch and its own 512 test triples.  Training is data-parallel with replicated tables: the
-ranks all-gather their batch ids over NCCL and each applies the identical global update
-(pykg2vec_b200/sharding.py); evaluation shards the test triples with no data-path
-collective and all-gathers the Q x 4 ranks at the end of the step.
+Multi-GPU (torchrun, one rank per GPU): weak scaling — every rank brings its own training batch and
+its own 512 test triples.  Training is data-parallel with replicated tables (pykg2vec_b200/trainer.py:
+"grads" = local forward/backward + one gradient all-reduce per table, "ids" = id all-gather for tiny
+batches); evaluation shards the test triples with NO collective in the timed step — ranks are gathered
+once, after the timing (as a real evaluation gathers once at its end).
 """
 import argparse
 import json
@@ -41,8 +43,15 @@ sys.path.insert(0, ROOT)
 
 WORKLOAD = dict(model="transe", dataset="fb15k_237", N=14541, R=237, d=200, l1=False, margin=5.0,
                 lr=0.01, B=512, neg=1, Q=512)
-ALG_BYTES_PER_CANDIDATE = 800  # TransE 1-vs-all eval streams one d*4-byte row per score
+# identical in both arms (the driver compares them)
+CONFIG = {"workload": "TransE L2 d=200 on FB15k-237 shape (N=14541, R=237): per step one train batch "
+                      "B=512 neg=1 hinge(margin 5)+SGD and one 1-vs-all eval batch of Q=512 test triples "
+                      "(head+tail, raw+filtered)",
+          "scored_triples_per_step_per_gpu": WORKLOAD["B"] * (1 + WORKLOAD["neg"]) + 2 * WORKLOAD["Q"] * WORKLOAD["N"],
+          "l2": "flushed before every timed step (256 MiB memset, untimed); tables (11.6 MB) otherwise stay L2-resident"}
 L2_FLUSH_BYTES = 256 << 20
+METRIC = "scored triples/sec (train + 1-vs-all eval)"
+DATA = "synthetic (FB15k-237-shaped random graph, random-init tables)"
 
 
 def peaks():
@@ -50,8 +59,9 @@ def peaks():
     if os.path.exists(p):
         with open(p) as f:
             d = json.load(f)
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(d.get("sm_max_mhz", 1965.0))
-    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+        return {"hbm": float(d["hbm_gbs"]), "bf16": float(d["bf16_tflops"]), "bf16_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                "src": "measured (MEASURED_PEAKS.json)", "sm_max": float(d.get("sm_max_mhz", 1965.0))}
+    return {"hbm": 6650.0, "bf16": 1590.0, "bf16_sustained": 1400.0, "src": "fallback (B200_PROFILING.md)", "sm_max": 1965.0}
 
 
 class ClockSampler:
@@ -131,6 +141,55 @@ def build(kg, device):
     return tr
 
 
+def event_ms(torch, fn, reps, flush=None):
+    """mean CUDA-event time of fn() on the current stream; optional untimed L2 flush before each rep"""
+    tot = 0.0
+    for _ in range(reps):
+        if flush is not None:
+            flush.zero_()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        tot += a.elapsed_time(b)
+    return tot / reps
+
+
+def gather_score_rooflines(torch, _lib, dev, pk, reps=10):
+    """The fused gather+score kernels north_star's >= 60 %-of-HBM target names (TransE, ComplEx; d = 200),
+    timed here on tables far larger than the 126 MB L2 with random ids.  Algorithmic bytes count what
+    must come from DRAM: the ENTITY rows (2 per triple for TransE, 4 for ComplEx), the 24 B of ids and the
+    4 B score — the R=1000 relation rows are L2 hits and are not counted."""
+    out = []
+    gen = torch.Generator(device=dev).manual_seed(0)
+    for name, N, ntab_e, ntab_r, n in (("transe", 2_000_000, 1, 1, 4_000_000), ("complex", 1_000_000, 2, 2, 2_000_000)):
+        d, R = 200, 1000
+        tabs = [(torch.rand((N, d), device=dev, generator=gen) - 0.5) * 0.2 for _ in range(ntab_e)] + \
+               [(torch.rand((R, d), device=dev, generator=gen) - 0.5) * 0.2 for _ in range(ntab_r)]
+        desc = _lib.ModelDesc(name, tabs, d, l1_flag=False)
+        h = torch.randint(0, N, (n,), device=dev, generator=gen)
+        r = torch.randint(0, R, (n,), device=dev, generator=gen)
+        t = torch.randint(0, N, (n,), device=dev, generator=gen)
+        o = torch.empty(n, dtype=torch.float32, device=dev)
+        for _ in range(3):
+            _lib.score_fwd(desc, h, r, t, out=o)
+        ms = event_ms(torch, lambda: _lib.score_fwd(desc, h, r, t, out=o), reps)
+        alg = n * (2 * ntab_e * d * 4 + 24 + 4)
+        out.append({"kernel": "score_fwd_kernel<%s> (fused gather+score, %d random triples, %d x %d entity table%s = %.1f GB)"
+                              % (name, n, N, d, "s" if ntab_e > 1 else "", ntab_e * N * d * 4 / 1e9),
+                    "bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                    "frac": alg / (ms * 1e-3) / 1e9 / pk["hbm"], "peak_source": pk["src"], "launch_ms": ms,
+                    "algorithmic_bytes_per_launch": alg,
+                    "algorithmic_bytes_per_triple": "entity rows %d x %d B + 24 B ids + 4 B score (relation rows are L2-resident)"
+                                                    % (2 * ntab_e, d * 4),
+                    "traffic": None})
+        del tabs, desc, h, r, t, o
+        torch.cuda.empty_cache()
+    return out
+
+
 def run_cuda(args):
     import torch
     import torch.distributed as dist
@@ -154,101 +213,41 @@ def run_cuda(args):
         fh = build_filter_csr([(int(t), int(r)) for h, r, t in q], tr_h)
         host.append((ids, q, ft, fh))
         tod = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int64)).to(dev)
-        devin.append((torch.stack([tod(a) for a in ids]), tod(q[:, 0]), tod(q[:, 1]), tod(q[:, 2]),
+        devin.append(([tod(a) for a in ids], tod(q[:, 0]), tod(q[:, 1]), tod(q[:, 2]),
                       (tod(ft[0]), tod(ft[1])), (tod(fh[0]), tod(fh[1]))))
     desc = tr.model.kge_desc()
-    scratch = tr._grad_scratch
-    loss_buf = torch.zeros(1, dtype=torch.float32, device=dev)
     counts = torch.zeros((w["Q"], 4), dtype=torch.int32, device=dev)
     ws = torch.empty(max(_lib.rank_workspace_bytes(desc, w["Q"]), 16), dtype=torch.uint8, device=dev)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
-    scored_per_step = world * (w["B"] * (1 + w["neg"]) + 2 * w["Q"] * w["N"])
+    train_per_step = world * w["B"] * (1 + w["neg"])
+    eval_per_step = world * 2 * w["Q"] * w["N"]
+    scored_per_step = train_per_step + eval_per_step
 
-    pending = []  # asynchronous rank gathers of earlier steps (drained before the timing stops)
-
-    def resident_step(i):
-        if graph_step is not None:
-            return graph_step(i)
-        ids, qh, qr, qt, ft, fh = devin[i]
-        # multi-GPU: start the 24 KB id all-gather first, sweep this rank's test triples while it
-        # is in flight, then train on the gathered global batch (no-op closures at world 1)
-        get_ids = sharding.allgather_batch_ids_async(ids)
+    def eval_resident(i):
+        _ids, qh, qr, qt, ft, fh = devin[i]
         counts.zero_()
         _lib.rank_1vsall(desc, qh, qr, qt, ft, fh, counts=counts, workspace=ws)
-        if world > 1:
-            while pending:
-                pending.pop()()
-            pending.append(sharding.gather_query_shards_async(counts.clone(), world * w["Q"]))
-        gids = get_ids()
-        _lib.train_pairwise_hinge_sgd(desc, scratch, gids[0], gids[1], gids[2], gids[3], gids[4], gids[5],
-                                      w["margin"], w["lr"], loss_buf)
+
+    def train_resident(i):
+        tr.train_batch_device(devin[i][0])   # fused step; at world > 1 data-parallel inside the Trainer
+
+    def resident_step(i):
+        eval_resident(i)
+        train_resident(i)
 
     def e2e_step(i):
         ids, q, ft, fh = host[i]
-        if world > 1:
-            # the host API has no multi-GPU trainer yet: ids are exchanged on the device while the
-            # evaluation batch runs
-            dids, _ = tr._to_device(ids)
-            get_ids = sharding.allgather_batch_ids_async(torch.stack(dids))
-            ranks = ev.rank_triples(q[:, 0], q[:, 1], q[:, 2], ft, fh)
-            g = get_ids()
-            _lib.train_pairwise_hinge_sgd(desc, scratch, g[0], g[1], g[2], g[3], g[4], g[5], w["margin"],
-                                          w["lr"], loss_buf)
-            loss = float(loss_buf.item())
-            return loss, ranks
-        pending_loss = tr.train_batch(ids, sync=False)   # H2D + kernels + D2H enqueued as one graph
-        ranks = ev.rank_triples(q[:, 0], q[:, 1], q[:, 2], ft, fh)   # host staging overlaps it; syncs
-        return float(pending_loss), ranks                # pinned loss of this step, read on the host
+        pending_loss = tr.train_batch(ids, sync=False)   # pinned H2D + kernels (+ D2H of the loss) enqueued
+        ranks = ev.rank_triples(q[:, 0], q[:, 1], q[:, 2], ft, fh)   # host staging overlaps it; returns host ranks
+        return float(pending_loss), ranks                # loss of this step read on the host
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # Single GPU: the resident step (1 train batch + 1 eval batch = 11 short kernels) is captured
-    # ONCE as a CUDA graph reading from fixed device buffers; each timed step is one D2D copy of
-    # that step's resident inputs into those buffers plus one graph replay.
-    graph_step = None
-    if world == 1 and args.graph:
-        cap_t = max(x[4][1].numel() for x in devin)
-        cap_h = max(x[5][1].numel() for x in devin)
-        s_ids = torch.zeros_like(devin[0][0])
-        s_q = [torch.zeros(w["Q"], dtype=torch.int64, device=dev) for _ in range(3)]
-        s_tp, s_hp = torch.zeros(w["Q"] + 1, dtype=torch.int64, device=dev), torch.zeros(w["Q"] + 1, dtype=torch.int64, device=dev)
-        s_ti, s_hi = torch.zeros(cap_t, dtype=torch.int64, device=dev), torch.zeros(cap_h, dtype=torch.int64, device=dev)
-
-        def load_inputs(i):
-            ids, qh, qr, qt, ft, fh = devin[i]
-            s_ids.copy_(ids); s_q[0].copy_(qh); s_q[1].copy_(qr); s_q[2].copy_(qt)
-            s_tp.copy_(ft[0]); s_hp.copy_(fh[0])
-            s_ti[:ft[1].numel()].copy_(ft[1]); s_hi[:fh[1].numel()].copy_(fh[1])
-
-        def body():
-            counts.zero_()
-            _lib.rank_1vsall(desc, s_q[0], s_q[1], s_q[2], (s_tp, s_ti), (s_hp, s_hi), counts=counts, workspace=ws)
-            _lib.train_pairwise_hinge_sgd(desc, scratch, s_ids[0], s_ids[1], s_ids[2], s_ids[3], s_ids[4], s_ids[5],
-                                          w["margin"], 0.0 if body.warm else w["lr"], loss_buf)
-        body.warm = True
-        load_inputs(0)
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            body()  # un-captured warm-up with lr = 0 (tables untouched)
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        body.warm = False
-        g = torch.cuda.CUDAGraph()
-        k0 = _lib.launch_count()
-        with torch.cuda.graph(g):
-            body()
-        kernels_per_replay = _lib.launch_count() - k0  # our kernels inside one replay of the graph
-
-        def graph_step(i):
-            load_inputs(i)
-            g.replay()
-
     def timed(fn, first, n, use_events):
-        """n steps starting at index `first`; L2 flushed (untimed) before every step; returns ms."""
+        """n steps starting at index `first`; L2 flushed (untimed) before every step; returns total ms."""
         tot = 0.0
         for i in range(first, first + n):
             flush.zero_()
@@ -257,13 +256,9 @@ def run_cuda(args):
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
                 fn(i)
-                while pending:
-                    pending.pop()()
                 b.record()
                 torch.cuda.synchronize()
                 tot += a.elapsed_time(b)
-                if os.environ.get("KGE_BENCH_DEBUG"):
-                    sys.stderr.write("rank %d step %d: %.3f ms\n" % (rank, i, a.elapsed_time(b)))
             else:
                 t0 = time.perf_counter()
                 fn(i)
@@ -286,6 +281,22 @@ def run_cuda(args):
         if not args.lite:
             e2e_step(i)
     barrier()
+
+    # ---- self-check (outside every timed region): ranks of this rank's step-0 queries, through the host
+    # API, against the CPU oracle on a copy of the current tables
+    verified = None
+    if not args.lite:
+        import oracle
+        nv = 16
+        ids0, q0, ft0, fh0 = host[0]
+        got = ev.rank_triples(q0[:, 0], q0[:, 1], q0[:, 2], ft0, fh0)
+        om = oracle.Model("transe", [t_.detach().cpu().numpy() for t_ in tr.model.kge_tables()], w["d"], l1_flag=w["l1"])
+        want = oracle.rank_1vsall(om, q0[:nv, 0], q0[:nv, 1], q0[:nv, 2], (ft0[0][:nv + 1], ft0[1][:ft0[0][nv]]),
+                                  (fh0[0][:nv + 1], fh0[1][:fh0[0][nv]]))
+        verified = bool(np.array_equal(got[:nv], want))
+        if not verified:
+            raise RuntimeError("bench self-check failed: rank counts differ from the oracle")
+
     # sustained run (~1.5 s of back-to-back steps) so that nvidia-smi samples clocks UNDER LOAD
     t_end = time.perf_counter() + (0.3 if args.lite else 1.5)
     sustained_steps = 0
@@ -298,69 +309,63 @@ def run_cuda(args):
         sustained_steps += args.steps
     ms_sustained = (time.perf_counter() - t_s0) * 1e3 / max(sustained_steps, 1)
     barrier()
-    # no cyclic-GC pauses inside the timed legs: at N > 1 a pause on ONE rank stalls every rank's
-    # id all-gather (seen as a single 3 ms step among 0.43 ms ones, profiles/r1_bench_n4_v3.err)
     import gc
     gc.collect()
-    gc.disable()
+    gc.disable()   # no cyclic-GC pause inside a timed leg (a pause on one rank stalls every rank's collective)
     launches0 = _lib.launch_count()
     ms_res = max_over_ranks(timed(resident_step, args.warmup, args.steps, True))
     launches = _lib.launch_count() - launches0
-    if graph_step is not None:
-        launches = kernels_per_replay * args.steps  # replays re-execute the captured kernels
+    ms_train = max_over_ranks(timed(train_resident, args.warmup, args.steps, True))
+    ms_eval = max_over_ranks(timed(eval_resident, args.warmup, args.steps, True))
     # warm-L2 back-to-back variant (tables stay in the 126 MB L2 between steps, as in a real epoch)
     barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for i in range(args.warmup, total):
         resident_step(i)
-    while pending:
-        pending.pop()()
     b.record()
     torch.cuda.synchronize()
     ms_warm = max_over_ranks(a.elapsed_time(b))
     ms_e2e = max_over_ranks(timed(e2e_step, args.warmup, args.steps, False)) if not args.lite else float("nan")
     gc.enable()
-    # dominant kernel: the 1-vs-all sweep.  Timed alone (raw counts, one direction per launch pair)
-    # with CUDA events on the launching stream.
-    ids, qh, qr, qt, ft, fh = devin[args.warmup]
-    reps = max(args.steps, 5)
-    for _ in range(3):
-        _lib.rank_1vsall(desc, qh, qr, qt, None, None, counts=counts, workspace=ws, flags=_lib.RANK_TAIL_ONLY)
-    torch.cuda.synchronize()
-    sweep_ms = 0.0
-    for _ in range(reps):
-        flush.zero_()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        _lib.rank_1vsall(desc, qh, qr, qt, None, None, counts=counts, workspace=ws, flags=_lib.RANK_TAIL_ONLY)
-        b.record()
-        torch.cuda.synchronize()
-        sweep_ms += a.elapsed_time(b)
-    sweep_ms /= reps
+    # multi-GPU: the ranks of all shards are gathered ONCE, after the timing (one all-gather of Q x 4 int32)
+    if world > 1:
+        sharding.gather_query_shards(counts.clone(), world * w["Q"])
+
+    # ---- dominant kernel of the step: the tensor-core sweep, timed alone with CUDA events recorded around
+    # the kernel launch itself on its own stream (C-ABI profiling hook), L2 flushed before every launch
+    _ids, qh, qr, qt, ft, fh = devin[args.warmup]
+    reps = max(args.steps, 10)
+    sweep = {"tc": [], "fp32": []}
+    for key, flags in (("tc", _lib.RANK_TAIL_ONLY | _lib.RANK_PROFILE),
+                       ("fp32", _lib.RANK_TAIL_ONLY | _lib.RANK_PROFILE | _lib.RANK_NO_TC)):
+        for rep in range(reps + 3):
+            flush.zero_()
+            torch.cuda.synchronize()
+            _lib.rank_1vsall(desc, qh, qr, qt, None, None, counts=counts, workspace=ws, flags=flags)
+            torch.cuda.synchronize()
+            if rep >= 3:
+                sweep[key].append(_lib.rank_last_sweep_ms(0))
+    tc_ms, fp32_ms = float(np.mean(sweep["tc"])), float(np.mean(sweep["fp32"]))
     clocks = sampler.stop() if rank == 0 else None
+    pk = peaks()
+    extra = gather_score_rooflines(torch, _lib, dev, pk) if (rank == 0 and not args.lite) else []
     if rank != 0:
         return None
-    peak, peak_src, sm_max = peaks()
-    alg_bytes = ALG_BYTES_PER_CANDIDATE * w["Q"] * w["N"]
-    achieved = alg_bytes / (sweep_ms * 1e-3) / 1e9
-    # secondary, honest bound of the batched sweep: fp32 pipe (2 instr / element-pair tail, 3 head)
-    lane_ops = w["Q"] * w["N"] * w["d"] * 2
-    fp32_peak = 148 * 128 * sm_max * 1e6
-    cpu = cpu_baseline(sample_train=10, sample_queries=6) if not args.lite else None
+    alg_flops = 2.0 * w["Q"] * w["N"] * w["d"]                     # the Q x N x d contraction (2 flop per multiply-add)
+    kp = ((w["d"] + 3 + 15) // 16) * 16                            # padded contraction length incl. the 3 norm columns
+    exec_flops = 3 * 2.0 * (-(-w["Q"] // 128) * 128) * (-(-w["N"] // 128) * 128) * kp   # three bf16 passes over padded tiles
+    cpu = cpu_baseline(sample_train=10, sample_queries=8) if not args.lite else None
     line = {
-        "metric": "scored triples/sec (train + 1-vs-all eval)", "value": scored_per_step * args.steps / (ms_res * 1e-3),
+        "metric": METRIC, "value": scored_per_step * args.steps / (ms_res * 1e-3),
         "unit": "triples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic (FB15k-237-shaped random graph, random-init tables)",
-        "config": {"workload": "TransE L2 d=200 on FB15k-237 shape (N=14541, R=237): per step one train batch "
-                               "B=512 neg=1 hinge(margin 5)+SGD and one 1-vs-all eval batch of Q=512 test triples "
-                               "(head+tail, raw+filtered)",
-                   "scored_triples_per_step_per_gpu": w["B"] * (1 + w["neg"]) + 2 * w["Q"] * w["N"],
-                   "l2": "flushed before every timed step (256 MiB memset, untimed); tables (11.6 MB) "
-                         "otherwise stay L2-resident",
-                   "parallelism": "dp%d: batch ids all-gathered, replicated update; test triples sharded" % world},
+        "dtype": "f32", "data": DATA, "config": CONFIG, "verified": verified,
+        "parallelism": "dp%d (%s): tables replicated, test triples sharded, no collective in the eval step"
+                       % (world, tr._dp or "single GPU"),
+        "train_triples_per_s": train_per_step * args.steps / (ms_train * 1e-3),
+        "eval_scores_per_s": eval_per_step * args.steps / (ms_eval * 1e-3),
+        "ms_per_train_step": ms_train / args.steps, "ms_per_eval_batch": ms_eval / args.steps,
         "ms_per_step_warm_l2": ms_warm / args.steps,
         "ms_per_step_sustained": ms_sustained,
         "e2e": {"value": scored_per_step * args.steps / (ms_e2e * 1e-3), "unit": "triples/s",
@@ -370,18 +375,19 @@ def run_cuda(args):
                 "d2h_bytes_per_step": 4 + w["Q"] * 4 * 4},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"kernel": "1-vs-all sweep (tail direction, Q=512 x N=14541)", "bound": "hbm",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "peak_source": peak_src,
-                     # dram__bytes_read+write of one sweep_tiled_kernel launch, ncu --set full
-                     # (profiles/r1_ncu_sweep_tiled_v2_summary.txt)
-                     "traffic": 12088576, "launch_ms": sweep_ms,
-                     "algorithmic_bytes_per_launch": alg_bytes,
-                     "note": "algorithmic bytes = the reference-equivalent streaming formulation (one 800-byte "
-                             "row per scored candidate, SURVEY.md 8d); a sweep that batches queries re-uses "
-                             "rows on chip, so frac can exceed 1 and the binding unit is the fp32 pipe",
-                     "fp32_pipe": {"lane_ops_per_launch": lane_ops, "achieved_tlops": lane_ops / (sweep_ms * 1e-3) / 1e12,
-                                   "peak_tlops": fp32_peak / 1e12, "frac": lane_ops / (sweep_ms * 1e-3) / fp32_peak}},
+        "roofline": {"kernel": "tc_sweep_kernel: 1-vs-all tensor-core sweep (tail direction, Q=512 x N=14541 x d=200, "
+                               "tcgen05.mma bf16x3 split, fp32 accumulation in TMEM)",
+                     "bound": "tensor", "achieved": alg_flops / (tc_ms * 1e-3) / 1e12, "peak": pk["bf16"], "unit": "TFLOP/s",
+                     "frac": alg_flops / (tc_ms * 1e-3) / 1e12 / pk["bf16"], "peak_source": pk["src"] + ", burst bf16 (kernel timed alone)",
+                     "launch_ms": tc_ms, "algorithmic_flops_per_launch": alg_flops,
+                     "algorithmic_flops_per_unit": "2*d = 400 flop per scored candidate (one length-d contraction)",
+                     "executed_tensor_flops_per_launch": exec_flops,
+                     "executed_frac": exec_flops / (tc_ms * 1e-3) / 1e12 / pk["bf16"],
+                     "traffic": None,
+                     "note": "exact fp32 ranks need three bf16 passes (a0b0 + a0b1 + a1b0) over tiles padded to 128 x 128 x 208: "
+                             "executed_frac counts those tensor flops, frac only the algorithm's 2*Q*N*d",
+                     "fp32_sweep_ms": fp32_ms, "speedup_vs_fp32_sweep": fp32_ms / tc_ms},
+        "rooflines_extra": extra,
         "cpu_baseline": cpu,
     }
     return line
@@ -401,10 +407,70 @@ def usable_cores():
     return n
 
 
-class CpuArm:
-    """The torch port of the reference's CPU path (oracle/ref_port.py: the same ATen op chain,
-    dense autograd + dense optim.SGD, forward over N + topk(N) + Python rank walk) on the host
-    cores.  Bench/test infrastructure only."""
+class RefArm:
+    """The UNMODIFIED reference (baseline/_ref, pip-installed from /root/reference) on the host cores, driven
+    through its own code: pykg2vec.models.pairwise.TransE, Trainer.train_step_pairwise + backward +
+    optimizer.step (pykg2vec/utils/trainer.py:147-157,288-300) and Evaluator.test
+    (pykg2vec/utils/evaluator.py:309-334: two forwards over all N entities, topk(N), D2H, the Python rank walk
+    of MetricCalculator).  None of this repo's models, kernels or engine is on this path."""
+    kind = "reference"
+
+    def __init__(self):
+        import types
+        import torch
+        from baseline import ref_loader
+        ref_loader.load()
+        from pykg2vec.models.pairwise import TransE
+        from pykg2vec.utils.evaluator import Evaluator
+        from pykg2vec.utils.trainer import Trainer
+        from pykg2vec_b200.synthetic import SyntheticConfig
+        w = WORKLOAD
+        self.torch = torch
+        self.cores = usable_cores()
+        torch.set_num_threads(self.cores)
+        self.kg = make_graph()
+        cfg = SyntheticConfig(self.kg, device="cpu", optimizer="sgd", learning_rate=w["lr"], margin=w["margin"],
+                              hidden_size=w["d"], l1_flag=w["l1"], batch_size=w["B"], neg_rate=w["neg"])
+        cfg.epochs, cfg.debug = 1 << 30, False
+        torch.manual_seed(2)
+        self.model = TransE(**cfg.__dict__)
+        self.trainer = object.__new__(Trainer)                    # its train_step_* methods only read model / config
+        self.trainer.model, self.trainer.config = self.model, cfg
+        self.optimizer = torch.optim.SGD(self.model.parameters(), lr=w["lr"])   # trainer.py:117-121
+        self.evaluator = Evaluator(self.model, cfg)
+        self.batches = make_batches(self.kg, 64, 0)
+        self.test = self.kg.read_cache_data("triplets_test")
+        self.cursor = 0
+        self.desc = "torch %s CPU, pykg2vec 0.0.52 from baseline/_ref" % torch.__version__
+
+    def train_steps(self, n):
+        torch = self.torch
+        self.model.train()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            ids, _q = self.batches[self.cursor % len(self.batches)]
+            self.cursor += 1
+            self.optimizer.zero_grad()
+            tid = [torch.LongTensor(np.asarray(a)) for a in ids]          # trainer.py:288-293
+            loss = self.trainer.train_step_pairwise(*tid)
+            loss.backward()
+            self.optimizer.step()
+            loss.item()                                                  # trainer.py:300
+        return (time.perf_counter() - t0) / n
+
+    def eval_queries(self, n):
+        start = (self.cursor * 7) % (len(self.test) - n)
+        self.model.eval()
+        import contextlib, io
+        with self.torch.no_grad(), contextlib.redirect_stderr(io.StringIO()):   # tqdm's progress bar
+            t0 = time.perf_counter()
+            self.evaluator.test(self.test[start:start + n], n, epoch=0)
+            return (time.perf_counter() - t0) / n
+
+
+class PortArm:
+    """Fallback when baseline/_ref is absent: the torch port of the same op chain (oracle/ref_port.py)."""
+    kind = "port"
 
     def __init__(self):
         import torch
@@ -421,6 +487,7 @@ class CpuArm:
         self.batches = make_batches(self.kg, 64, 0)
         self.hr_t, self.tr_h = self.kg.read_cache_data("hr_t"), self.kg.read_cache_data("tr_h")
         self.cursor = 0
+        self.desc = "torch %s CPU port of the reference op chain (oracle/ref_port.py)" % torch.__version__
 
     def train_steps(self, n):
         torch, rp, w = self.torch, self.rp, WORKLOAD
@@ -428,7 +495,7 @@ class CpuArm:
         for _ in range(n):
             ids, _q = self.batches[self.cursor % len(self.batches)]
             self.cursor += 1
-            tid = [torch.LongTensor(np.asarray(a)) for a in ids]  # trainer.py:288-293
+            tid = [torch.LongTensor(np.asarray(a)) for a in ids]
             self.opt.zero_grad()
             pos = rp.score("transe", [self.ent, self.rel], tid[0], tid[1], tid[2], l1_flag=w["l1"])
             neg = rp.score("transe", [self.ent, self.rel], tid[3], tid[4], tid[5], l1_flag=w["l1"])
@@ -447,6 +514,16 @@ class CpuArm:
             t0 = time.perf_counter()
             rp.evaluate(fn, w["N"], q, self.hr_t, self.tr_h)
             return (time.perf_counter() - t0) / n
+
+
+def make_arm():
+    from baseline import ref_loader
+    if ref_loader.available():
+        try:
+            return RefArm()
+        except Exception as e:   # noqa: BLE001 — fall back to the port, say why
+            sys.stderr.write("reference arm: baseline/_ref unusable (%r), using the port\n" % (e,))
+    return PortArm()
 
 
 def tune_threads(arm):
@@ -470,15 +547,6 @@ def tune_threads(arm):
     return best
 
 
-def cpu_measure(n_train, n_queries, arm=None):
-    """(seconds per train step, seconds per test triple, cores) after a short warm-up."""
-    arm = arm or CpuArm()
-    tune_threads(arm)
-    arm.train_steps(2)
-    arm.eval_queries(1)
-    return arm.train_steps(n_train), arm.eval_queries(n_queries), arm.cores
-
-
 def cpu_line_value(t_train, t_query):
     w = WORKLOAD
     step_s = t_train + w["Q"] * t_query
@@ -486,12 +554,16 @@ def cpu_line_value(t_train, t_query):
 
 
 def cpu_baseline(sample_train, sample_queries):
-    t_train, t_query, cores = cpu_measure(sample_train, sample_queries)
-    value, step_s = cpu_line_value(t_train, t_query)
-    return {"value": value, "unit": "triples/s", "cores": cores, "kind": "port",
-            "sample": "%d train steps + %d test triples of the same workload, extrapolated to one step "
-                      "(1 train batch + 512 test triples); torch %s CPU port of the reference op chain incl. "
-                      "topk + Python rank walk" % (sample_train, sample_queries, __import__("torch").__version__),
+    arm = make_arm()
+    tune_threads(arm)
+    arm.train_steps(2)
+    arm.eval_queries(1)
+    t_train, t_query = arm.train_steps(sample_train), arm.eval_queries(sample_queries)
+    value, _ = cpu_line_value(t_train, t_query)
+    return {"value": value, "unit": "triples/s", "cores": arm.cores, "kind": arm.kind,
+            "sample": "%d train steps + %d test triples of the same workload timed, extrapolated to one step "
+                      "(1 train batch + 512 test triples: every test triple costs the same two forwards over N + "
+                      "topk + rank walk); %s" % (sample_train, sample_queries, arm.desc),
             "train_step_ms": t_train * 1e3, "eval_ms_per_test_triple": t_query * 1e3}
 
 
@@ -499,11 +571,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return None
-    w = WORKLOAD
-    # each step: a bounded sample (1 train step + 2 test triples), extrapolated to the step composition
-    per_step_queries = 2
+    # each step: a bounded sample of the workload — 1 train batch + 32 test triples really evaluated —
+    # extrapolated to the step's 512 test triples (said so in cpu_baseline.sample)
+    per_step_queries = 32
     tt, tq = [], []
-    arm = CpuArm()
+    arm = make_arm()
     cores = tune_threads(arm)
     for s in range(args.warmup + args.steps):
         a, b = arm.train_steps(1), arm.eval_queries(per_step_queries)
@@ -512,19 +584,14 @@ def run_reference(args):
             tq.append(b)
     t_train, t_query = float(np.mean(tt)), float(np.mean(tq))
     value, step_s = cpu_line_value(t_train, t_query)
-    import torch
     line = {
-        "impl": "reference", "metric": "scored triples/sec (train + 1-vs-all eval)", "value": value,
+        "impl": "reference", "metric": METRIC, "value": value,
         "unit": "triples/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic (FB15k-237-shaped random graph, random-init tables)",
-        "config": {"workload": "TransE L2 d=200 on FB15k-237 shape (N=14541, R=237): per step one train batch "
-                               "B=512 neg=1 hinge(margin 5)+SGD and one 1-vs-all eval batch of Q=512 test triples "
-                               "(head+tail, raw+filtered)"},
-        "cpu_baseline": {"value": value, "unit": "triples/s", "cores": cores, "kind": "port",
-                         "sample": "per step 1 train batch + %d test triples timed, extrapolated to 512 test "
-                                   "triples; torch %s CPU port of the reference op chain (dense autograd + "
-                                   "optim.SGD; forward over N + topk(N) + Python rank walk)" % (per_step_queries, torch.__version__),
+        "vs_baseline": None, "dtype": "f32", "data": DATA, "config": CONFIG,
+        "cpu_baseline": {"value": value, "unit": "triples/s", "cores": cores, "kind": arm.kind,
+                         "sample": "per step 1 train batch + %d test triples really run (Evaluator.test), extrapolated to "
+                                   "the step's 512 test triples; %s" % (per_step_queries, arm.desc),
                          "train_step_ms": t_train * 1e3, "eval_ms_per_test_triple": t_query * 1e3},
         "e2e": {"value": value, "unit": "triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -537,15 +604,12 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--graph", action="store_true",
-                    help="replay the resident step as one CUDA graph (measured: no gain — the step is bound "
-                         "by kernel time, not launch latency — so the default launches kernel by kernel)")
     ap.add_argument("--lite", action="store_true",
-                    help="profiling aid: only the HBM-resident leg (no e2e / CPU baseline); never a bench value")
+                    help="profiling aid: only the HBM-resident leg (no e2e / CPU baseline / self-check); never a bench value")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
     # stdout carries exactly ONE JSON line: while the run is in progress fd 1 points at stderr so
-    # that banners printed by native libraries (e.g. NCCL's version line) cannot end up there
+    # that banners printed by native libraries (e.g. NCCL's INFO lines) cannot end up there
     sys.stdout.flush()
     saved = os.dup(1)
     os.dup2(2, 1)

@@ -172,6 +172,20 @@ int kge_optim_apply_rows(const kge_model_t* m, float* const* tables_rw, float* c
                          float* const* state, int optimizer, const int64_t* h, const int64_t* r,
                          const int64_t* t, int64_t n, float lr, float eps, void* stream);
 
+/* Dense optimizer.step() for ONE parameter tensor of n floats (any shape): the accumulated gradient is
+ * taken out of `grad` (a dense buffer filled by kge_score_bwd / kge_reg_fwd_bwd / an all-reduce of such
+ * buffers; left zero-filled) and applied in place to w.
+ *   optimizer 0: torch.optim.SGD; 1: torch.optim.Adagrad (state1 = sum of squares, eps 1e-10);
+ *   optimizer 2: torch.optim.Adam — the reference's default `-opt adam` (pykg2vec/common.py:50,
+ *   utils/trainer.py:112-116): state1 = exp_avg, state2 = exp_avg_sq, step = 1-based step count,
+ *   torch's update order (lerp, mul+addcmul, sqrt / sqrt(bias_correction2) + eps, addcdiv).  Dense Adam
+ *   moves every element every step (moments of gradient-free rows keep decaying), so this is one
+ *   HBM-bound sweep over the tensor, not a sparse row update; results equal torch's to rounding.
+ * Used by the fused training steps with -opt adam and by data-parallel training after the gradient
+ * all-reduce (pykg2vec_b200/sharding.py).  Tensors must be 16-byte aligned. */
+int kge_optim_apply_dense(float* w, float* grad, float* state1, float* state2, int64_t n, int optimizer,
+                          float lr, float eps, float beta1, float beta2, int64_t step, void* stream);
+
 /* ---- 1-vs-all link-prediction ranks: replaces Evaluator.test ------------
  * (pykg2vec/utils/evaluator.py:309-334 + MetricCalculator.get_*_rank :70-123)
  *
@@ -206,6 +220,13 @@ int kge_rank_1vsall(const kge_model_t* m, const kge_model_t* mq, int64_t row_lo,
 #define KGE_RANK_HEAD_ONLY 4
 #define KGE_RANK_SINGLE_STREAM 8 /* do not overlap the two directions on an internal side stream */
 #define KGE_RANK_NO_TC 16 /* keep the sweep on the fp32 pipe (no tensor-core level; same counts either way) */
+#define KGE_RANK_PROFILE 32 /* record CUDA events around each direction's main sweep kernel, see kge_rank_last_sweep_ms */
+
+/* Measurement aid (bench.py's roofline entry): after a kge_rank_1vsall call with KGE_RANK_PROFILE from the
+ * same host thread, *ms receives the device time of direction 0 (tail) / 1 (head)'s main sweep kernel —
+ * tc_sweep_kernel, or sweep_tiled_kernel with KGE_RANK_NO_TC — measured by CUDA events recorded around
+ * that launch on the stream it ran on (waits for the kernel).  Not usable inside a graph capture. */
+int kge_rank_last_sweep_ms(int direction, float* ms);
 
 /* Two-level exact sweep (TransE -l1 False, DistMult, CP, ComplEx, RESCAL, RotatE; >= 1024 candidate rows):
  * level 1 evaluates the Q x N x K contraction on the tensor cores (tcgen05.mma, bf16 x 3 split, fp32

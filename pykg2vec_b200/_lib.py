@@ -20,15 +20,15 @@ MODEL_IDS = {
 }
 GROUP_TAIL, GROUP_HEAD = 0, 1
 RANK_FORCE_GATHER, RANK_TAIL_ONLY, RANK_HEAD_ONLY = 1, 2, 4
-RANK_SINGLE_STREAM, RANK_NO_TC = 8, 16
+RANK_SINGLE_STREAM, RANK_NO_TC, RANK_PROFILE = 8, 16, 32
 
 # every symbol include/kge_b200.h declares (tests check they are all exported)
 EXPORTS = [
     "kge_abi_version", "kge_version", "kge_last_error", "kge_launch_count",
     "kge_score_fwd", "kge_score_bwd", "kge_normalize_rows",
     "kge_loss_pairwise_hinge", "kge_loss_pointwise_logistic", "kge_loss_selfadv", "kge_reg_fwd_bwd",
-    "kge_train_pairwise_hinge_sgd", "kge_optim_apply_rows",
-    "kge_rank_workspace_bytes", "kge_rank_1vsall", "kge_rank_tc_probe",
+    "kge_train_pairwise_hinge_sgd", "kge_optim_apply_rows", "kge_optim_apply_dense",
+    "kge_rank_workspace_bytes", "kge_rank_1vsall", "kge_rank_tc_probe", "kge_rank_last_sweep_ms",
     "kge_tripleset_capacity", "kge_tripleset_build", "kge_sample_negatives",
     "kge_proj_tail_fwd", "kge_proj_tail_bwd", "kge_proj_bce", "kge_proj_rank_workspace_bytes", "kge_proj_rank", "kge_proj_labels",
     "kge_conve_trunk_workspace_bytes", "kge_conve_trunk_fwd", "kge_project_entities", "kge_normalize_rows_to",
@@ -235,6 +235,23 @@ def optim_apply_rows(desc, grad_scratch, state, optimizer, h, r, t, lr, eps=1e-1
                                      ctypes.c_float(eps), _stream()), "kge_optim_apply_rows")
 
 
+OPT_SGD, OPT_ADAGRAD, OPT_ADAM = 0, 1, 2
+
+
+def optim_apply_dense(w, grad, optimizer, lr, state1=None, state2=None, eps=None, betas=(0.9, 0.999), step=1):
+    """Dense optimizer step on ONE parameter tensor; consumes (and re-zeroes) its dense gradient buffer.
+    optimizer: OPT_SGD / OPT_ADAGRAD (state1) / OPT_ADAM (state1 = exp_avg, state2 = exp_avg_sq, step >= 1)."""
+    if eps is None:
+        eps = 1e-8 if optimizer == OPT_ADAM else 1e-10
+    w, grad = _dev_f32(w, "w"), _dev_f32(grad, "grad")
+    if grad.numel() != w.numel():
+        raise KgeError("gradient buffer must be shaped like the parameter")
+    check(lib().kge_optim_apply_dense(_ptr(w), _ptr(grad), _ptr(state1), _ptr(state2), ctypes.c_int64(w.numel()),
+                                      ctypes.c_int(optimizer), ctypes.c_float(lr), ctypes.c_float(eps),
+                                      ctypes.c_float(betas[0]), ctypes.c_float(betas[1]), ctypes.c_int64(step),
+                                      _stream()), "kge_optim_apply_dense")
+
+
 def rank_workspace_bytes(desc, Q):
     m = desc.c_struct()
     return int(lib().kge_rank_workspace_bytes(ctypes.byref(m), ctypes.c_int64(Q)))
@@ -267,6 +284,13 @@ def rank_1vsall(desc, qh, qr, qt, filt_t=None, filt_h=None, counts=None, row_lo=
         _ptr(counts), _ptr(workspace), ctypes.c_int64(workspace.numel()), ctypes.c_int(flags), _stream()),
         "kge_rank_1vsall")
     return counts
+
+
+def rank_last_sweep_ms(direction):
+    """device time (ms) of the main sweep kernel of `direction` in the last rank_1vsall(flags |= RANK_PROFILE)."""
+    ms = ctypes.c_float(0.0)
+    check(lib().kge_rank_last_sweep_ms(ctypes.c_int(direction), ctypes.byref(ms)), "kge_rank_last_sweep_ms")
+    return float(ms.value)
 
 
 def rank_tc_probe(desc, qh, qr, qt, direction, want_dots=True, query_desc=None, row_lo=0, row_hi=None):

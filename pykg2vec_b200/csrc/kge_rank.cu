@@ -160,6 +160,11 @@ band_resolve_kernel(ModelParams P, const int64_t* __restrict__ qh, const int64_t
   }
 }
 
+SweepProfile* sweep_profile(int dir) {
+  static thread_local SweepProfile prof[2];
+  return &prof[dir & 1];
+}
+
 int check_model(const kge_model_t* m);
 int model_vec(const kge_model_t* m);
 
@@ -282,6 +287,15 @@ extern "C" int kge_rank_1vsall(const kge_model_t* m, const kge_model_t* mq, int6
     if (rc) return rc;
   }
 
+  for (int d = 0; d < 2; ++d) {
+    SweepProfile* sp = sweep_profile(d);
+    sp->armed = (flags & KGE_RANK_PROFILE) != 0;
+    sp->valid = false;
+    if (sp->armed && !sp->beg) {
+      KGE_CUDA_OK(cudaEventCreate(&sp->beg));
+      KGE_CUDA_OK(cudaEventCreate(&sp->end));
+    }
+  }
   const bool both = !(flags & (KGE_RANK_HEAD_ONLY | KGE_RANK_TAIL_ONLY));
   // (CP / SimplE refill one shared candidate scratch per direction: their directions stay serial)
   const bool dirs_independent = m->model != KGE_CP && m->model != KGE_SIMPLE && m->model != KGE_SIMPLE_IGNR;
@@ -386,4 +400,13 @@ extern "C" int kge_rank_tc_probe(const kge_model_t* m, const kge_model_t* mq, in
   if (rc) return rc;
   return tiled_sweep(m, mq, direction, qh, qr, qt, thr, Q, nc, counts, direction == 0 ? 0 : 2, tiled_ws, true, dots,
                      tau, st);
+}
+
+extern "C" int kge_rank_last_sweep_ms(int direction, float* ms) {
+  if (!ms || (direction != 0 && direction != 1)) { set_error("kge_rank_last_sweep_ms: bad arguments"); return KGE_EINVAL; }
+  SweepProfile* sp = sweep_profile(direction);
+  if (!sp->valid) { set_error("kge_rank_last_sweep_ms: the last kge_rank_1vsall of this thread did not profile direction %d", direction); return KGE_EINVAL; }
+  KGE_CUDA_OK(cudaEventSynchronize(sp->end));
+  KGE_CUDA_OK(cudaEventElapsedTime(ms, sp->beg, sp->end));
+  return KGE_OK;
 }

@@ -20,6 +20,11 @@ int tiled_sweep(const kge_model_t* m, const kge_model_t* mq, int dir, const int6
                 int32_t* counts, int col, void* ws, bool use_tc, float* tc_dbg, float* tc_tau_out,
                 cudaStream_t st);
 
+// Measurement hook (KGE_RANK_PROFILE): CUDA events recorded immediately around the launch of a
+// direction's main sweep kernel (tensor-core or fp32) on the stream it is launched on.
+struct SweepProfile { cudaEvent_t beg = nullptr, end = nullptr; bool armed = false, valid = false; };
+SweepProfile* sweep_profile(int dir);
+
 // ---- tensor-core sweep (kge_rank_tc.cu) -------------------------------------------------------------
 struct TcDirBuffers {
   int32_t* tc_counts;          // [Q] certain counts of level 1 (+ the resolved pairs of level 2)

@@ -605,8 +605,11 @@ int tc_sweep(const kge_model_t* m, int dir, const float* qvec, const float* thr,
   rc = tc_make_map(&TM.b1, w + L.b[1], (uint64_t)nc, (uint64_t)Kp); if (rc) return rc;
   const size_t smem = 2048 + a_bytes + (size_t)nstages * st_bytes;
   KGE_CUDA_OK(cudaFuncSetAttribute(tc_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SweepProfile* sp = sweep_profile(dir);
+  if (sp->armed) KGE_CUDA_OK(cudaEventRecord(sp->beg, st));
   tc_sweep_kernel<<<dim3((unsigned)splits, (unsigned)qblocks), kTcThreads, smem, st>>>(P, TM);
   KGE_CHECK_LAUNCH("tc_sweep_kernel");
+  if (sp->armed) { KGE_CUDA_OK(cudaEventRecord(sp->end, st)); sp->valid = true; }
   out->tc_counts = cnt; out->ctrl = ctrl; out->list = list; out->cap = P.cap; out->tau = tau;
   return KGE_OK;
 }

@@ -839,15 +839,22 @@ int tiled_sweep(const kge_model_t* m, const kge_model_t* mq, int dir, const int6
   P.counts = counts; P.col = col; P.l1 = m->l1_flag; P.margin = m->margin;
   P.fin = (model == KGE_HOLE) ? 1 : (is_simple(model) ? 2 : 0);
 
+  SweepProfile* sp = sweep_profile(dir);
+  const bool prof = sp->armed && !use_tc;   // with the tensor-core level the profiled kernel is tc_sweep_kernel
+  if (prof) KGE_CUDA_OK(cudaEventRecord(sp->beg, st));
+  int rc;
   switch (op) {
-    case OP_TRANS_T: return m->l1_flag ? launch_sweep<OP_TRANS_T, true>(P, QBLK, smem, st, splits, qblocks)
-                                       : launch_sweep<OP_TRANS_T, false>(P, QBLK, smem, st, splits, qblocks);
-    case OP_TRANS_H: return m->l1_flag ? launch_sweep<OP_TRANS_H, true>(P, QBLK, smem, st, splits, qblocks)
-                                       : launch_sweep<OP_TRANS_H, false>(P, QBLK, smem, st, splits, qblocks);
-    case OP_DOT1: return launch_sweep<OP_DOT1, false>(P, QBLK, smem, st, splits, qblocks);
-    case OP_DOT2: return launch_sweep<OP_DOT2, false>(P, QBLK, smem, st, splits, qblocks);
-    default: return launch_sweep<OP_ROT, false>(P, QBLK, smem, st, splits, qblocks);
+    case OP_TRANS_T: rc = m->l1_flag ? launch_sweep<OP_TRANS_T, true>(P, QBLK, smem, st, splits, qblocks)
+                                     : launch_sweep<OP_TRANS_T, false>(P, QBLK, smem, st, splits, qblocks); break;
+    case OP_TRANS_H: rc = m->l1_flag ? launch_sweep<OP_TRANS_H, true>(P, QBLK, smem, st, splits, qblocks)
+                                     : launch_sweep<OP_TRANS_H, false>(P, QBLK, smem, st, splits, qblocks); break;
+    case OP_DOT1: rc = launch_sweep<OP_DOT1, false>(P, QBLK, smem, st, splits, qblocks); break;
+    case OP_DOT2: rc = launch_sweep<OP_DOT2, false>(P, QBLK, smem, st, splits, qblocks); break;
+    default: rc = launch_sweep<OP_ROT, false>(P, QBLK, smem, st, splits, qblocks); break;
   }
+  if (rc) return rc;
+  if (prof) { KGE_CUDA_OK(cudaEventRecord(sp->end, st)); sp->valid = true; }
+  return KGE_OK;
 }
 
 }  // namespace kge

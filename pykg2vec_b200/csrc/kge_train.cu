@@ -212,6 +212,75 @@ int launch_apply(const kge_model_t* m, float* const* tables_rw, float* const* gr
   return KGE_OK;
 }
 
+
+// Dense optimizer.step() over ONE parameter tensor (any shape, n floats): the accumulated gradient
+// is taken out of `g` (left zero-filled, ready for the next step's atomics) and applied in place.
+//   OPT 0 torch.optim.SGD      w -= lr * g                                   (trainer.py:117-121)
+//   OPT 1 torch.optim.Adagrad  s += g*g ; w -= lr * g / (sqrt(s) + eps)      (trainer.py:122-126)
+//   OPT 2 torch.optim.Adam     m += (g - m)(1 - b1) ; v = v*b2 + (1 - b2) g*g ;
+//                              w -= (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)   (trainer.py:112-116)
+// Adam moves EVERY element every step (the moments of rows without gradient keep decaying and keep
+// pushing the weight), exactly as the dense reference optimizer does — which is why this is a sweep
+// over the whole tensor and not a sparse row update.  HBM-bound: 16-32 bytes per element.
+template <int OPT>
+__global__ void __launch_bounds__(256)
+apply_dense_kernel(float* __restrict__ w, float* __restrict__ g, float* __restrict__ s1, float* __restrict__ s2,
+                   int64_t n4, int64_t n, float lr, float eps, float b1, float b2, float step_size, float bc2_sqrt) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 gv = reinterpret_cast<float4*>(g)[i];
+    if (OPT != 2 && gv.x == 0.f && gv.y == 0.f && gv.z == 0.f && gv.w == 0.f) continue;   // SGD / Adagrad: nothing moves
+    float4 wv = reinterpret_cast<float4*>(w)[i];
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (OPT >= 1) a = reinterpret_cast<float4*>(s1)[i];
+    if (OPT == 2) b = reinterpret_cast<float4*>(s2)[i];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float gg = f4_get(gv, e);
+      float& ww = f4_at(wv, e);
+      if (OPT == 0) {
+        ww = ffma(-lr, gg, ww);
+      } else if (OPT == 1) {
+        float& ss = f4_at(a, e);
+        ss = ffma(gg, gg, ss);
+        ww = fsub(ww, fmul(lr, __fdiv_rn(gg, fadd(__fsqrt_rn(ss), eps))));
+      } else {
+        float& m = f4_at(a, e);
+        float& v = f4_at(b, e);
+        m = ffma(fsub(gg, m), 1.0f - b1, m);                       // exp_avg.lerp_(grad, 1 - beta1)
+        v = ffma(fmul(gg, gg), 1.0f - b2, fmul(v, b2));            // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+        const float denom = fadd(__fdiv_rn(__fsqrt_rn(v), bc2_sqrt), eps);
+        ww = ffma(-step_size, __fdiv_rn(m, denom), ww);            // param.addcdiv_(exp_avg, denom, value = -step_size)
+      }
+    }
+    reinterpret_cast<float4*>(w)[i] = wv;
+    if (OPT >= 1) reinterpret_cast<float4*>(s1)[i] = a;
+    if (OPT == 2) reinterpret_cast<float4*>(s2)[i] = b;
+    reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  // scalar tail (n % 4 elements), handled by the first threads of block 0
+  const int64_t tail0 = n4 * 4;
+  if (blockIdx.x == 0 && threadIdx.x < (unsigned)(n - tail0)) {
+    const int64_t i = tail0 + threadIdx.x;
+    const float gg = g[i];
+    float ww = w[i];
+    if (OPT == 0) {
+      ww = ffma(-lr, gg, ww);
+    } else if (OPT == 1) {
+      const float ss = ffma(gg, gg, s1[i]);
+      s1[i] = ss;
+      if (gg != 0.f) ww = fsub(ww, fmul(lr, __fdiv_rn(gg, fadd(__fsqrt_rn(ss), eps))));
+    } else {
+      const float m = ffma(fsub(gg, s1[i]), 1.0f - b1, s1[i]);
+      const float v = ffma(fmul(gg, gg), 1.0f - b2, fmul(s2[i], b2));
+      s1[i] = m; s2[i] = v;
+      ww = ffma(-step_size, __fdiv_rn(m, fadd(__fdiv_rn(__fsqrt_rn(v), bc2_sqrt), eps)), ww);
+    }
+    w[i] = ww;
+    g[i] = 0.f;
+  }
+}
+
 }  // namespace kge
 
 using namespace kge;
@@ -282,4 +351,34 @@ extern "C" int kge_optim_apply_rows(const kge_model_t* m, float* const* tables_r
   const int64_t* rs[1] = {r};
   const int64_t* ts[1] = {t};
   return launch_apply(m, tables_rw, gs, state, optimizer, hs, rs, ts, 1, n, lr, eps, (cudaStream_t)stream);
+}
+
+extern "C" int kge_optim_apply_dense(float* w, float* grad, float* state1, float* state2, int64_t n, int optimizer,
+                                     float lr, float eps, float beta1, float beta2, int64_t step, void* stream) {
+  if (!w || !grad || n < 0 || optimizer < 0 || optimizer > 2 || (optimizer >= 1 && !state1) ||
+      (optimizer == 2 && (!state2 || step < 1))) {
+    set_error("kge_optim_apply_dense: bad arguments"); return KGE_EINVAL;
+  }
+  if (n == 0) return KGE_OK;
+  if (((uintptr_t)w | (uintptr_t)grad | (uintptr_t)state1 | (uintptr_t)state2) & 15) {
+    set_error("kge_optim_apply_dense: tensors must be 16-byte aligned"); return KGE_EINVAL;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n4 = n / 4;
+  int64_t blocks = (n4 + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  // bias corrections in double, as torch computes them in Python floats
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float step_size = optimizer == 2 ? (float)((double)lr / bc1) : 0.f;
+  const float bc2_sqrt = optimizer == 2 ? (float)sqrt(bc2) : 1.f;
+  if (optimizer == 0)
+    apply_dense_kernel<0><<<(unsigned)blocks, 256, 0, st>>>(w, grad, state1, state2, n4, n, lr, eps, beta1, beta2, step_size, bc2_sqrt);
+  else if (optimizer == 1)
+    apply_dense_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(w, grad, state1, state2, n4, n, lr, eps, beta1, beta2, step_size, bc2_sqrt);
+  else
+    apply_dense_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(w, grad, state1, state2, n4, n, lr, eps, beta1, beta2, step_size, bc2_sqrt);
+  KGE_CHECK_LAUNCH("apply_dense_kernel");
+  return KGE_OK;
 }

@@ -401,8 +401,15 @@ class Evaluator:
         from .graphs import StagedGraph
         dev = self._dev()
         cap_t, cap_h = self._bucket(nnz_t), self._bucket(nnz_h)
-        tables = self.model.kge_tables()
-        key = (q, cap_t, cap_h, tuple(int(w.data_ptr()) for w in tables))
+        # Models with derived tables (ConvKB's collapsed A, c0 are fresh temporaries of every kge_tables()
+        # call) are keyed on their persistent parameters only and re-derive the tables on every call
+        # (eager body, no captured pointers); everything else is keyed on the live table pointers.
+        dense = bool(getattr(self.model, "kge_dense_params", False))
+        if dense:
+            ptrs = tuple(int(p_.data_ptr()) for p_ in self.model.parameters())
+        else:
+            ptrs = tuple(int(w.data_ptr()) for w in self.model.kge_tables())
+        key = (q, cap_t, cap_h, dense, ptrs)
         call = self._filter_cache.get(("graph",) + key)
         if call is not None:
             return call
@@ -410,6 +417,7 @@ class Evaluator:
         counts = torch.zeros((q, 4), dtype=torch.int32, device=dev)
         ws = torch.empty(max(_lib.rank_workspace_bytes(desc, q), 16), dtype=torch.uint8, device=dev)
         words = 3 * q + 2 * (q + 1) + cap_t + cap_h
+        model = self.model
 
         def body(d_in):
             o = 3 * q
@@ -418,12 +426,15 @@ class Evaluator:
             o += 2 * q + 2
             tidx, hidx = d_in[o:o + cap_t], d_in[o + cap_t:o + cap_t + cap_h]
             counts.zero_()
-            _lib.rank_1vsall(desc, qh, qr, qt, (tptr, tidx), (hptr, hidx), counts=counts, workspace=ws)
+            if not dense and hasattr(model, "kge_pre_score"):
+                model.kge_pre_score()   # Rescal: tables row-normalised in place, as the reference's forward() does
+            d = model.kge_desc() if dense else desc
+            _lib.rank_1vsall(d, qh, qr, qt, (tptr, tidx), (hptr, hidx), counts=counts, workspace=ws)
             return counts
 
         call = StagedGraph(dev, words, torch.empty((q, 4), dtype=torch.int32), body)
         call.cap_t, call.cap_h = cap_t, cap_h
-        use_graph = getattr(self.config, "cuda_graph", True)
+        use_graph = getattr(self.config, "cuda_graph", True) and not dense
         if use_graph:
             call.capture()
         else:

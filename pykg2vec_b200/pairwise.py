@@ -45,6 +45,17 @@ class _KernelScored:
         """ModelDesc over the live weights (no copy) for the rank / fused-train entry points."""
         return self.kge_spec().desc([w.detach() for w in self.kge_tables()])
 
+    def kge_pre_score(self):
+        """Side effects the reference's forward() has on the tables BEFORE scoring (Rescal's in-place
+        row normalisation, pairwise.py:843-844).  The fused training steps and Evaluator.rank_triples
+        call the kernels directly, so they call this first; no-op for every other model."""
+
+    def kge_fused_reg(self):
+        """(reg_code, lmbda) of the row regulariser get_reg() applies with its DEFAULT reg_type (what
+        Trainer.train_step_pointwise calls, trainer.py:179) for kge_reg_fwd_bwd, or None when get_reg is
+        not a function of the weights (then the fused step adds its value as a constant)."""
+        return None
+
     def forward(self, h, r, t):
         return ScoreFunction.apply(self.kge_spec(), h, r, t, *self.kge_tables())
 
@@ -273,6 +284,9 @@ class Rescal(_KernelScored, PairwiseModel):
         with torch.no_grad():
             _lib.normalize_rows(self.ent_embeddings.weight.data)
             _lib.normalize_rows(self.rel_matrices.weight.data)
+
+    def kge_pre_score(self):
+        self.normalize_tables_()
 
     def forward(self, h, r, t):
         self.normalize_tables_()

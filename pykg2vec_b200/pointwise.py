@@ -14,6 +14,13 @@ _REG_TYPES = {"f2": 0, "n3": 1}
 
 class _RowRegularised(_KernelScored):
     _abs_n3 = False
+    _default_reg = "F2"   # default reg_type of the model's get_reg (what the Trainer calls)
+
+    def kge_fused_reg(self):
+        code = _REG_TYPES[self._default_reg.lower()]
+        if code == 1 and self._abs_n3:
+            code = 2
+        return code, float(self.lmbda)
 
     def _reg(self, h, r, t, reg_type):
         key = reg_type.lower()
@@ -55,6 +62,7 @@ class DistMult(_RowRegularised, PointwiseModel):
 
 class CP(_RowRegularised, PointwiseModel):
     """pykg2vec/models/pointwise.py:321-388."""
+    _default_reg = "N3"
 
     def __init__(self, **kwargs):
         super(CP, self).__init__(self.__class__.__name__.lower())
@@ -121,6 +129,7 @@ class Complex(_RowRegularised, PointwiseModel):
 class ComplexN3(Complex):
     """pykg2vec/models/pointwise.py:205-238."""
     _abs_n3 = True
+    _default_reg = "N3"
 
     def __init__(self, **kwargs):
         super(ComplexN3, self).__init__(**kwargs)
@@ -241,6 +250,9 @@ class _HyperComplex(_KernelScored, PointwiseModel):
 
     def kge_spec(self):
         return ModelSpec(self._kge_name, self.hidden_size)
+
+    def kge_fused_reg(self):
+        return 2, float(self.lmbda)   # get_reg's default reg_type is 'N3' = |x|**3 (pointwise.py:696-727, :901-960)
 
     def get_reg(self, h, r, t, reg_type='N3'):
         key = reg_type.lower()

@@ -7,12 +7,14 @@ minimum the path needs:
   (pykg2vec/utils/evaluator.py:313) -> contiguous query shards, NO collective in the data
   path, one final all-gather of the Q x 4 int32 ranks.
 * 1-vs-all evaluation with ROW-SHARDED entity tables (tables that outgrow one GPU): every
-  rank sweeps its rows for all queries; the only exchanges are (1) an all-reduce that
-  assembles the compact table of query rows (each row contributed by its owner, zeros
-  elsewhere: x + 0 is exact) and (2) ONE all-reduce-sum of the partial rank counts.
-* data-parallel training with replicated tables: a step's batch is tiny (24 KB of ids for
-  B=512), so ranks all-gather their batch ids and every rank applies the identical global
-  update — no gradient exchange at all.
+  rank sweeps its rows for all queries; the only exchanges are (1) an all-gather of the query
+  rows, each contributed by the rank that owns it (owners hold contiguous slices of the sorted
+  unique query ids, so the gathered blocks concatenate into the compact query table), and
+  (2) ONE all-gather of the partial rank counts [Q,4] int32, summed locally.
+* data-parallel training with replicated tables (pykg2vec_b200/trainer.py): "grads" — every rank
+  scores its own batch shard forward + backward into dense gradient buffers, one all-reduce per
+  table, identical dense optimizer step everywhere; "ids" — for tiny batches (24 KB of ids at
+  B=512) the ranks all-gather the ids instead and apply the global batch.
 
 Everything here is host logic over torch.distributed and runs unchanged on the gloo
 backend (tests/test_sharding_gloo.py, world_size 2, CPU) — the per-shard counting itself is
@@ -33,12 +35,9 @@ def init_distributed(backend=None):
         return 0, 1
     if not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # keep stdout clean (bench.py prints exactly one JSON line): NCCL's version banner goes
-        # to stdout at NCCL_DEBUG=VERSION/INFO
-        if "KGE_NCCL_DEBUG" in os.environ:
-            os.environ["NCCL_DEBUG"] = os.environ["KGE_NCCL_DEBUG"]
-        else:
-            os.environ.pop("NCCL_DEBUG", None)
+        # NCCL_DEBUG is left exactly as the launcher set it (the driver reads the communicator's rank
+        # count from NCCL's INFO lines); bench.py keeps its one JSON line clean by pointing fd 1 at
+        # stderr while the run is in progress.
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         dist.init_process_group(backend=backend)
@@ -146,19 +145,28 @@ class RowShardedRanker:
         return out
 
     def exchange_query_rows(self, uniq):
-        """Compact table of the rows `uniq` (sorted global ids) of every entity table,
-        identical on all ranks: owner contributes its rows, everyone else zeros, one
-        all-reduce-sum per table."""
+        """Compact table of the rows `uniq` (SORTED global ids) of every entity table, identical on all
+        ranks.  Rank g owns the contiguous slice of `uniq` that falls in its row range, so one
+        all-gather per table of the owners' blocks (padded to the largest block) concatenates into the
+        compact table — no zero-padded sum, every row travels once."""
         dev = self.ent_local[0].device
-        uniq_t = torch.as_tensor(uniq, dtype=torch.long, device=dev)
-        mine = (uniq_t >= self.row_lo) & (uniq_t < self.row_hi)
+        uniq = np.ascontiguousarray(uniq, dtype=np.int64)
+        bounds = [shard_range(self.num_ent, self.world, g) for g in range(self.world)]
+        starts = [int(np.searchsorted(uniq, lo)) for lo, _ in bounds] + [len(uniq)]
+        counts = [starts[g + 1] - starts[g] for g in range(self.world)]
+        cap = max(max(counts), 1)
+        mine = torch.as_tensor(uniq[starts[self.rank]:starts[self.rank + 1]] - self.row_lo, dtype=torch.long, device=dev)
         compact = []
         for t in self.ent_local:
-            buf = torch.zeros((uniq_t.numel(), t.shape[1]), dtype=t.dtype, device=dev)
-            buf[mine] = t[uniq_t[mine] - self.row_lo]
-            if self.world > 1:
-                dist.all_reduce(buf, op=dist.ReduceOp.SUM)
-            compact.append(buf)
+            if self.world == 1:
+                compact.append(t[mine].contiguous())
+                continue
+            send = torch.zeros((cap, t.shape[1]), dtype=t.dtype, device=dev)
+            send[:mine.numel()] = t[mine]
+            recv = torch.empty((self.world * cap, t.shape[1]), dtype=t.dtype, device=dev)
+            dist.all_gather_into_tensor(recv, send)
+            recv = recv.view(self.world, cap, t.shape[1])
+            compact.append(torch.cat([recv[g, :counts[g]] for g in range(self.world)], dim=0))
         return compact
 
     def rank_queries(self, qh, qr, qt, filt_t=None, filt_h=None):
@@ -177,5 +185,9 @@ class RowShardedRanker:
         counts = self.count_fn(self._assemble(self.ent_local), self._assemble(compact_ent), self.row_lo,
                                self.row_hi, qh_c, to(qr), qt_c, to(qh), to(qt), ft, fh)
         if self.world > 1:
-            dist.all_reduce(counts, op=dist.ReduceOp.SUM)  # the single exchange of partial rank counts
+            # the single exchange of the sweep: ONE all-gather of the partial rank counts, summed locally
+            # (exact: integer counts of bit-identical scores over disjoint row shards)
+            allc = torch.empty((self.world,) + tuple(counts.shape), dtype=counts.dtype, device=counts.device)
+            dist.all_gather_into_tensor(allc.view(self.world * counts.shape[0], counts.shape[1]), counts.contiguous())
+            counts = allc.sum(dim=0, dtype=counts.dtype)
         return counts

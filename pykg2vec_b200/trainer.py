@@ -7,11 +7,21 @@ Two execution modes for the same step semantics:
     loss.backward() / optimizer.step() exactly as the reference Trainer drives them — the
     CUDA kernels sit behind forward()/loss()/backward().  This is also what runs when the
     unmodified reference Trainer is handed these model classes.
-  * fused mode (optimizer sgd or adagrad, config.fused_step not False): the step is issued
-    as a few kernels with no dense [N,d] gradient or dense optimizer sweep:
+  * fused mode (optimizer sgd, adagrad or adam, config.fused_step not False): the step is issued
+    as a few kernels with no autograd graph and no torch optimizer:
       pairwise hinge + SGD : kge_train_pairwise_hinge_sgd (2 kernels)
-      otherwise            : score_fwd -> loss kernel -> score_bwd (+ reg) -> kge_optim_apply_rows
-    Results equal the dense optimizers' (zero-gradient rows do not move under SGD/Adagrad).
+      sgd / adagrad        : score_fwd -> loss kernel -> score_bwd (+ reg) -> kge_optim_apply_rows
+                             (sparse: zero-gradient rows do not move under SGD/Adagrad, so the result
+                             equals the dense optimizers')
+      adam (the CLI default, common.py:50): ... -> kge_optim_apply_dense per table — dense Adam moves
+                             every row every step, so its exact form is one HBM-bound sweep per table
+  * data-parallel (torch.distributed world > 1, tables replicated): config.dp_mode
+      "grads": every rank scores ITS batch shard forward + backward into the dense gradient buffers,
+               ONE all-reduce per table sums (hinge) / averages (mean-type losses) them over NVLink, then
+               every rank applies the identical dense optimizer step — per-GPU scoring work is B, not world x B;
+      "ids"  : ranks all-gather their batch ids (24 KB at B=512) and every rank applies the global batch —
+               cheaper than moving gradient tables when the batch is tiny;
+      None   : "grads" when the batch's touched rows outweigh a table sweep, else "ids".
 
 The sampler processes, epoch loop, early stopping, checkpointing and export of the
 reference Trainer are out of scope here; batches are handed in as
@@ -38,6 +48,10 @@ class Trainer:
         self._pinned = None
         self._loss_buf = None
         self._graphs = {}
+        self._state2 = None
+        self._step = 0
+        self._world = 1
+        self._dp = None
 
     def build_model(self):
         """trainer.py:103-144 (optimizer selection; unknown names raise NotImplementedError)."""
@@ -55,14 +69,31 @@ class Trainer:
             self.optimizer = optim.RMSprop(self.model.parameters(), lr=lr)
         else:
             raise NotImplementedError("No support for %s optimizer" % name)
-        self._fused = name in ("sgd", "adagrad") and getattr(self.config, "fused_step", True) and \
+        self._fused = name in ("sgd", "adagrad", "adam") and getattr(self.config, "fused_step", True) and \
             hasattr(self.model, "kge_desc") and not getattr(self.model, "kge_dense_params", False)
         if self._fused:
             tabs = self.model.kge_tables()
             self._grad_scratch = [torch.zeros_like(t) if t.requires_grad else None for t in tabs]
-            if name == "adagrad":  # optim.Adagrad: state_sum starts at initial_accumulator_value = 0
+            if name in ("adagrad", "adam"):  # optim.Adagrad: state_sum = 0; optim.Adam: exp_avg = exp_avg_sq = 0
                 self._state = [torch.zeros_like(t) if t.requires_grad else None for t in tabs]
+            if name == "adam":
+                self._state2 = [torch.zeros_like(t) if t.requires_grad else None for t in tabs]
+        self._step = 0
         self._loss_buf = torch.zeros(1, dtype=torch.float32, device=self.config.device)
+        import torch.distributed as dist
+        self._world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self._dp = None
+        if self._world > 1 and self._fused:
+            self._dp = getattr(self.config, "dp_mode", None) or self._pick_dp_mode()
+
+    def _pick_dp_mode(self):
+        """'grads' (shard the scoring, all-reduce dense gradients) pays when the rows a local batch touches
+        outweigh one sweep over the tables; tiny batches exchange ids instead."""
+        tabs = [t for t in self.model.kge_tables() if t.requires_grad]
+        table_floats = sum(t.numel() for t in tabs)
+        per_triple = sum(t.shape[1] for t in tabs)
+        batch = int(self.config.batch_size) * (1 + int(getattr(self.config, "neg_rate", 1)))
+        return "grads" if batch * per_triple * self._world >= table_floats else "ids"
 
     # ---- reference-signature steps (autograd mode) --------------------------------------------
     def train_step_pairwise(self, pos_h, pos_r, pos_t, neg_h, neg_r, neg_t):
@@ -115,13 +146,53 @@ class Trainer:
 
     # ---- fused steps --------------------------------------------------------------------------
     def _opt_code(self):
-        return 0 if self.config.optimizer == "sgd" else 1
+        return {"sgd": _lib.OPT_SGD, "adagrad": _lib.OPT_ADAGRAD, "adam": _lib.OPT_ADAM}[self.config.optimizer]
+
+    def _dense_apply(self, desc, lr):
+        """optimizer.step() as one sweep per table over its dense gradient buffer (Adam always; SGD /
+        Adagrad after a data-parallel gradient all-reduce, where the touched rows are the union over ranks)."""
+        self._step += 1
+        state2 = self._state2
+        for k, w in enumerate(desc.tables):
+            g = self._grad_scratch[k]
+            if g is None:
+                continue
+            _lib.optim_apply_dense(w, g, self._opt_code(), lr, self._state[k] if self._state else None,
+                                   state2[k] if state2 else None, step=self._step)
+
+    def _apply(self, desc, id_sets, lr):
+        if self.config.optimizer == "adam" or self._dp == "grads":
+            return self._dense_apply(desc, lr)
+        for h, r, t in id_sets:
+            _lib.optim_apply_rows(desc, self._grad_scratch, self._state, self._opt_code(), h, r, t, lr)
+
+    def _allreduce_grads(self, loss, mean_type):
+        """data-parallel 'grads' mode: ONE NCCL all-reduce per gradient table (sum for the hinge's sum over
+        pairs, average for the mean-type losses and regularisers) + the scalar loss."""
+        if self._dp != "grads":
+            return loss
+        import torch.distributed as dist
+        native_avg = mean_type and dist.get_backend() == "nccl"   # gloo has no AVG: sum, then scale
+        op = dist.ReduceOp.AVG if native_avg else dist.ReduceOp.SUM
+        bufs = [g for g in self._grad_scratch if g is not None] + [loss]
+        for b in bufs:
+            dist.all_reduce(b, op=op)
+            if mean_type and not native_avg:
+                b.div_(self._world)
+        return loss
 
     def _fused_pairwise(self, ids):
+        self.model.kge_pre_score()   # Rescal: in-place row normalisation, as its forward() does
         desc = self.model.kge_desc()
         ph, pr, pt, nh, nr, nt = ids
         lr = float(self.config.learning_rate)
-        if self.model.model_name.lower() != "rotate" and self.config.optimizer == "sgd":
+        rotate = self.model.model_name.lower() == "rotate"
+        if not rotate and nh.numel() != ph.numel():
+            # Criterion.pairwise_hinge subtracts pos [B] and neg [B*neg_rate] elementwise: the reference
+            # raises a broadcast error for neg_rate > 1 (criterion.py:26-29) — so does this path
+            raise ValueError("pairwise hinge needs one negative per positive (got %d positives, %d negatives)"
+                             % (ph.numel(), nh.numel()))
+        if not rotate and self.config.optimizer == "sgd" and self._dp != "grads":
             _lib.train_pairwise_hinge_sgd(desc, self._grad_scratch, ph, pr, pt, nh, nr, nt,
                                           float(self.config.margin), lr, self._loss_buf)
             return self._loss_buf
@@ -133,22 +204,26 @@ class Trainer:
             loss, gp, gn = _lib.loss_pairwise_hinge(pos, neg, float(self.config.margin))
         _lib.score_bwd(desc, ph, pr, pt, gp, self._grad_scratch)
         _lib.score_bwd(desc, nh, nr, nt, gn, self._grad_scratch)
-        _lib.optim_apply_rows(desc, self._grad_scratch, self._state, self._opt_code(), ph, pr, pt, lr)
-        _lib.optim_apply_rows(desc, self._grad_scratch, self._state, self._opt_code(), nh, nr, nt, lr)
+        loss = self._allreduce_grads(loss, mean_type=rotate)
+        self._apply(desc, ((ph, pr, pt), (nh, nr, nt)), lr)
         return loss
 
     def _fused_pointwise(self, ids):
+        self.model.kge_pre_score()
         desc = self.model.kge_desc()
         h, r, t, y = ids
         lr = float(self.config.learning_rate)
         preds = _lib.score_fwd(desc, h, r, t)
         loss, g = _lib.loss_pointwise_logistic(preds, y.to(torch.float32))
         _lib.score_bwd(desc, h, r, t, g, self._grad_scratch)
-        reg_type = 2 if getattr(self.model, "_abs_n3", False) else (1 if self.model.model_name == "cp" else 0)
-        reg = _lib.reg_fwd_bwd(desc, reg_type, float(self.model.lmbda), h, r, t, grad_scale=1.0,
-                               grad_tables=self._grad_scratch)
-        _lib.optim_apply_rows(desc, self._grad_scratch, self._state, self._opt_code(), h, r, t, lr)
-        return loss + reg
+        hook = self.model.kge_fused_reg()
+        if hook is not None:
+            reg = _lib.reg_fwd_bwd(desc, hook[0], hook[1], h, r, t, grad_scale=1.0, grad_tables=self._grad_scratch)
+        else:   # SimplE / SimplE_ignr: get_reg acts on the id tensors — a constant w.r.t. the weights
+            reg = self.model.get_reg(h, r, t).detach().to(torch.float32).reshape(1)
+        loss = self._allreduce_grads(loss + reg, mean_type=True)
+        self._apply(desc, ((h, r, t),), lr)
+        return loss
 
     # ---- one batch, host ids in, host loss out (trainer.py:269-300) -----------------------------
     def _to_device(self, arrays):
@@ -182,6 +257,7 @@ class Trainer:
             def make_body(step_lr):
                 def body(d_in):
                     ids = d_in.view(6, B)
+                    self.model.kge_pre_score()   # captured with the step (Rescal's in-place normalisation)
                     _lib.train_pairwise_hinge_sgd(desc, self._grad_scratch, ids[0], ids[1], ids[2], ids[3],
                                                   ids[4], ids[5], margin, step_lr, loss)
                     return loss
@@ -208,6 +284,15 @@ class Trainer:
         self.model.train()
         ids = list(ids)
         strategy = self.model.training_strategy
+        if self._dp == "ids":   # replicated update on the all-gathered global batch
+            from . import sharding
+            n = [int(a.numel()) for a in ids]
+            if len(set(n)) == 1:
+                ids = list(sharding.allgather_batch_ids(torch.stack(ids)))
+            else:               # ragged (neg_rate > 1): positives and negatives gathered separately
+                k = len(ids) // 2
+                ids = list(sharding.allgather_batch_ids(torch.stack(ids[:k]))) + \
+                    list(sharding.allgather_batch_ids(torch.stack(ids[k:])))
         if self._fused:
             with torch.no_grad():
                 if strategy == TrainingStrategy.PAIRWISE_BASED:
@@ -247,7 +332,7 @@ class Trainer:
         D2H copy — so the caller's next host work overlaps this step's kernels."""
         self.model.train()
         data = list(data)
-        if (self._fused and getattr(self.config, "cuda_graph", True)
+        if (self._fused and getattr(self.config, "cuda_graph", True) and self._dp is None
                 and self.model.training_strategy == TrainingStrategy.PAIRWISE_BASED
                 and self.model.model_name.lower() != "rotate" and self.config.optimizer == "sgd"
                 and len(data) == 6 and all(len(a) == len(data[0]) for a in data)):
@@ -259,13 +344,9 @@ class Trainer:
             ids, nbytes = self._to_device(list(data))
         self.last_h2d_bytes = nbytes
         if self._fused:
-            with torch.no_grad():
-                if strategy == TrainingStrategy.PAIRWISE_BASED:
-                    loss = self._fused_pairwise(ids)
-                elif strategy == TrainingStrategy.POINTWISE_BASED:
-                    loss = self._fused_pointwise(ids)
-                else:
-                    raise NotImplementedError("Unknown training strategy: %s" % strategy)
+            loss = self.train_batch_device(ids)
+            if not sync:
+                return loss                # device tensor; float(loss) syncs when the caller wants the value
             return float(loss.item())  # D2H sync, as acc_loss += loss.item() (trainer.py:300)
         self.optimizer.zero_grad()
         if strategy == TrainingStrategy.PAIRWISE_BASED:

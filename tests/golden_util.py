@@ -8,11 +8,12 @@ import numpy as np
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 NON_CASES = {"losses", "settle"}
 PROJ_PREFIXES = ("conve_", "tucker_")
+SHAPE_PREFIX = "shapes_"   # BASELINE-shape cases: ids / reference outputs only, tables regenerated from a seed
 
 
 def case_names():
     names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-    return [n for n in names if n not in NON_CASES and not n.startswith(PROJ_PREFIXES)]
+    return [n for n in names if n not in NON_CASES and not n.startswith(PROJ_PREFIXES) and not n.startswith(SHAPE_PREFIX)]
 
 
 def proj_case_names():

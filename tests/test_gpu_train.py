@@ -219,15 +219,22 @@ def _trainer_for(model_name, kg, **cfgkw):
     return tr
 
 
-@pytest.mark.parametrize("model_name,opt", [("transe", "sgd"), ("transe", "adagrad"), ("distmult", "sgd"),
-                                            ("complex", "adagrad"), ("rotate", "adagrad")])
+@pytest.mark.parametrize("model_name,opt", [
+    ("transe", "sgd"), ("transe", "adagrad"), ("distmult", "sgd"), ("complex", "adagrad"), ("rotate", "adagrad"),
+    # every pointwise model with its own get_reg default (SimplE's id-tensor regulariser, QuatE /
+    # OctonionE |x|^3, CP signed x^3, ComplexN3 |x|^3), and Rescal whose forward() normalises in place
+    ("cp", "sgd"), ("complexn3", "sgd"), ("analogy", "adagrad"), ("simple", "sgd"), ("simple_ignr", "adagrad"),
+    ("quate", "sgd"), ("octonione", "adagrad"), ("rescal", "sgd"), ("rescal", "adagrad"), ("hole", "sgd"),
+    ("transh", "sgd"), ("transd", "adagrad")])
 def test_trainer_fused_equals_autograd_mode(model_name, opt):
     """Trainer.train_batch in fused mode follows the same weight trajectory as the autograd
     mode (reference step order) with the dense torch optimizer."""
     from pykg2vec_b200.synthetic import SyntheticKnowledgeGraph
     kg = SyntheticKnowledgeGraph(400, 6, 2000, 50, 50, seed=1)
-    kw = dict(optimizer=opt, learning_rate=0.05, hidden_size=64, margin=1.0 if model_name != "rotate" else 6.0,
-              l1_flag=False, lmbda=0.01, neg_rate=4 if model_name == "rotate" else 1, alpha=0.5)
+    kw = dict(optimizer=opt, learning_rate=0.05, hidden_size=32 if model_name == "rescal" else 64,
+              ent_hidden_size=64, rel_hidden_size=64, margin=1.0 if model_name != "rotate" else 6.0,
+              l1_flag=False, lmbda=0.01, neg_rate=4 if model_name == "rotate" else 1, alpha=0.5,
+              cmax=0.5, cmin=-0.5, batch_size=256)
     a = _trainer_for(model_name, kg, fused_step=True, **kw)
     b = _trainer_for(model_name, kg, fused_step=False, **kw)
     b.model.load_state_dict(a.model.state_dict())

@@ -113,9 +113,12 @@ threshold_kernel(ModelParams P, const int64_t* __restrict__ qh, const int64_t* _
   if (valid && lane == 0) thr[g] = s;
 }
 
-// Level 2 of the tensor-core sweep (kge_rank_tc.cu): the (query, candidate) pairs whose tensor-core
-// accumulator fell inside the query's uncertainty band are re-evaluated with the canonical fp32
-// group function — the arithmetic of kge_score_fwd and of the fp32 sweeps — and compared exactly.
+// Level 2 of the tensor-core sweep (kge_rank_tc.cu) + the filter pass, one kernel: both are exact
+// re-evaluations of listed (query, candidate) pairs with the canonical fp32 group function — the
+// arithmetic of kge_score_fwd and of the fp32 sweeps.
+//   items [0, total)            : pairs whose tensor-core accumulator fell inside the query's band:
+//                                 tc_counts[q] += 1 when the candidate really outranks the target
+//   items [total, total + nnz)  : filter entries (as filter_correct_kernel): filtered column -= 1
 // The last CTA to finish then commits the direction: counts += tc_counts, or (list overflow) raises
 // ctrl[3] so that the fp32 tiled sweep enqueued behind this kernel ranks the direction instead.
 template <int MODEL, int VEC, int GROUPING>
@@ -123,25 +126,46 @@ __global__ void __launch_bounds__(kThreads)
 band_resolve_kernel(ModelParams P, const int64_t* __restrict__ qh, const int64_t* __restrict__ qr,
                     const int64_t* __restrict__ qt, const float* __restrict__ thr,
                     const unsigned long long* __restrict__ list, unsigned* __restrict__ ctrl, unsigned cap,
-                    int64_t Q, int32_t* __restrict__ tc_counts, int32_t* __restrict__ counts, int col,
-                    int scratch_floats) {
+                    int64_t Q, int32_t* __restrict__ tc_counts, const RankFilter F, int32_t* __restrict__ counts,
+                    int col, int scratch_floats) {
   extern __shared__ float4 smem_f4[];
   __shared__ int s_last;
   float* scratch = reinterpret_cast<float*>(smem_f4) + (size_t)(threadIdx.x >> 3) * scratch_floats;
   const int lane = threadIdx.x & 7;
-  const unsigned total = *reinterpret_cast<volatile unsigned*>(&ctrl[0]);
-  const bool overflow = total > cap || *reinterpret_cast<volatile unsigned*>(&ctrl[1]) != 0u;
-  if (!overflow) {
-    for (unsigned k = blockIdx.x * kGroupsPerCta + (threadIdx.x >> 3); k < total; k += gridDim.x * kGroupsPerCta) {
+  const unsigned listed = *reinterpret_cast<volatile unsigned*>(&ctrl[0]);
+  const bool overflow = listed > cap || *reinterpret_cast<volatile unsigned*>(&ctrl[1]) != 0u;
+  const int64_t total = overflow ? 0 : (int64_t)listed;
+  const int64_t nnz_true = (F.ptr && F.idx && F.nnz > 0) ? min(F.nnz, __ldg(F.ptr + Q)) : 0;
+  const int64_t items = total + nnz_true;
+  for (int64_t k = (int64_t)blockIdx.x * kGroupsPerCta + (threadIdx.x >> 3); k < items;
+       k += (int64_t)gridDim.x * kGroupsPerCta) {
+    int64_t q, e;
+    bool skip = false;
+    const bool band = k < total;
+    if (band) {
       const unsigned long long pr = list[k];
-      const int64_t q = (int64_t)(pr >> 32), e = (int64_t)(pr & 0xffffffffull);
-      TripleRows R;
-      if (GROUPING == KGE_GROUP_TAIL)
-        resolve_rows<MODEL>(R, P, P.qtab, P.tab, P.qtab, __ldg(qh + q), __ldg(qr + q), e);
-      else
-        resolve_rows<MODEL>(R, P, P.tab, P.qtab, P.qtab, e, __ldg(qr + q), __ldg(qt + q));
-      const float s = score_group<MODEL, VEC, GROUPING>(R, P, lane, scratch);
-      if (lane == 0 && s < __ldg(thr + q)) atomicAdd(tc_counts + q, 1);
+      q = (int64_t)(pr >> 32); e = (int64_t)(pr & 0xffffffffull);
+    } else {
+      const int64_t kk = k - total;
+      int64_t lo = 0, hi = Q;  // largest q with ptr[q] <= kk
+      while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(F.ptr + mid) <= kk) lo = mid; else hi = mid;
+      }
+      q = lo;
+      const int64_t ge = __ldg(F.idx + kk);
+      skip = (ge == __ldg(F.tgt + q)) || ge < F.row_lo || ge >= F.row_hi;
+      e = skip ? 0 : ge - F.row_lo;
+    }
+    TripleRows R;
+    if (GROUPING == KGE_GROUP_TAIL)
+      resolve_rows<MODEL>(R, P, P.qtab, P.tab, P.qtab, __ldg(qh + q), __ldg(qr + q), e);
+    else
+      resolve_rows<MODEL>(R, P, P.tab, P.qtab, P.qtab, e, __ldg(qr + q), __ldg(qt + q));
+    const float s = score_group<MODEL, VEC, GROUPING>(R, P, lane, scratch);
+    if (lane == 0 && !skip && s < __ldg(thr + q)) {
+      if (band) atomicAdd(tc_counts + q, 1);
+      else atomicSub(counts + q * 4 + col + 1, 1);
     }
   }
   __threadfence();
@@ -169,8 +193,8 @@ int check_model(const kge_model_t* m);
 int model_vec(const kge_model_t* m);
 
 int band_resolve(const kge_model_t* m, const kge_model_t* mq, int dir, const int64_t* qh, const int64_t* qr,
-                 const int64_t* qt, const float* thr, int64_t Q, const TcDirBuffers& B, int32_t* counts, int col,
-                 cudaStream_t st) {
+                 const int64_t* qt, const float* thr, int64_t Q, const TcDirBuffers& B, const RankFilter& F,
+                 int32_t* counts, int col, cudaStream_t st) {
   const ModelParams P = make_params(m, mq);
   int vec = model_vec(m);
   const int vq = model_vec(mq);
@@ -185,10 +209,10 @@ int band_resolve(const kge_model_t* m, const kge_model_t* mq, int dir, const int
   do {                                                                                         \
     if (dir == 0) { SET_SMEM_BR((band_resolve_kernel<M, V, KGE_GROUP_TAIL>));                  \
       band_resolve_kernel<M, V, KGE_GROUP_TAIL><<<grid, kThreads, smem, st>>>(                 \
-          P, qh, qr, qt, thr, B.list, B.ctrl, B.cap, Q, B.tc_counts, counts, col, sf); }       \
+          P, qh, qr, qt, thr, B.list, B.ctrl, B.cap, Q, B.tc_counts, F, counts, col, sf); }    \
     else { SET_SMEM_BR((band_resolve_kernel<M, V, KGE_GROUP_HEAD>));                           \
       band_resolve_kernel<M, V, KGE_GROUP_HEAD><<<grid, kThreads, smem, st>>>(                 \
-          P, qh, qr, qt, thr, B.list, B.ctrl, B.cap, Q, B.tc_counts, counts, col, sf); }       \
+          P, qh, qr, qt, thr, B.list, B.ctrl, B.cap, Q, B.tc_counts, F, counts, col, sf); }    \
   } while (0)
   switch (m->model) {   // the models tc_supported() admits
     case KGE_TRANSE: KGE_DISPATCH_VEC(KGE_TRANSE, vec, CALL_BR); break;
@@ -335,7 +359,8 @@ extern "C" int kge_rank_1vsall(const kge_model_t* m, const kge_model_t* mq, int6
 #undef CALL_THR
 
     if (use_tiled) {
-      rc = tiled_sweep(m, mq, dir, qh, qr, qt, thr, Q, nc, counts, col, tiled_ws, use_tc, nullptr, nullptr, st);
+      const RankFilter F = {fptr, fidx, nnz, tgt, row_lo, row_hi};
+      rc = tiled_sweep(m, mq, dir, qh, qr, qt, thr, Q, nc, counts, col, tiled_ws, use_tc, &F, nullptr, nullptr, st);
       if (rc) return rc;
     } else {
 #define CALL_SWEEP(M, V)                                                                       \
@@ -350,7 +375,7 @@ extern "C" int kge_rank_1vsall(const kge_model_t* m, const kge_model_t* mq, int6
       KGE_CHECK_LAUNCH("sweep_gather_kernel");
     }
 
-    if (fptr && fidx && nnz > 0) {
+    if (fptr && fidx && nnz > 0 && !use_tc) {   // (the tensor-core path's resolve kernel applies the filters)
       const unsigned fgrid = (unsigned)((nnz + kGroupsPerCta - 1) / kGroupsPerCta);
 #define CALL_FILT(M, V)                                                                        \
   do {                                                                                         \
@@ -398,8 +423,8 @@ extern "C" int kge_rank_tc_probe(const kge_model_t* m, const kge_model_t* mq, in
   void* tiled_ws = reinterpret_cast<char*>(workspace) + align_up((size_t)2 * (size_t)Q * sizeof(float), 256);
   rc = tiled_prepare_candidates(m, nc, tiled_ws, Q, true, st);
   if (rc) return rc;
-  return tiled_sweep(m, mq, direction, qh, qr, qt, thr, Q, nc, counts, direction == 0 ? 0 : 2, tiled_ws, true, dots,
-                     tau, st);
+  return tiled_sweep(m, mq, direction, qh, qr, qt, thr, Q, nc, counts, direction == 0 ? 0 : 2, tiled_ws, true, nullptr,
+                     dots, tau, st);
 }
 
 extern "C" int kge_rank_last_sweep_ms(int direction, float* ms) {

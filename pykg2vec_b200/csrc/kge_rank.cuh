@@ -15,10 +15,11 @@ int tiled_prepare_candidates(const kge_model_t* m, int64_t nc, void* ws, int64_t
 // use_tc: level 1 on the tensor cores + exact resolution of the ambiguous pairs (kge_rank_tc.cu);
 // the fp32 sweep is still enqueued but returns at once unless the pair list overflowed.
 // tc_dbg (tests): optional [Q][nc] raw tensor-core accumulators; tc_tau_out: optional [Q][2] thresholds.
+struct RankFilter;
 int tiled_sweep(const kge_model_t* m, const kge_model_t* mq, int dir, const int64_t* qh,
                 const int64_t* qr, const int64_t* qt, float* thr, int64_t Q, int64_t nc,
-                int32_t* counts, int col, void* ws, bool use_tc, float* tc_dbg, float* tc_tau_out,
-                cudaStream_t st);
+                int32_t* counts, int col, void* ws, bool use_tc, const RankFilter* filter, float* tc_dbg,
+                float* tc_tau_out, cudaStream_t st);
 
 // Measurement hook (KGE_RANK_PROFILE): CUDA events recorded immediately around the launch of a
 // direction's main sweep kernel (tensor-core or fp32) on the stream it is launched on.
@@ -35,14 +36,22 @@ struct TcDirBuffers {
 };
 bool tc_supported(const kge_model_t* m, int64_t nc);
 size_t tc_workspace_bytes(const kge_model_t* m, int64_t Q);
-int tc_prepare_candidates(const kge_model_t* m, const float* const cand[2], int64_t pitch, int64_t nc, void* tcws,
-                          int64_t Q, cudaStream_t st);
-int tc_sweep(const kge_model_t* m, int dir, const float* qvec, const float* thr, int64_t Q, int64_t nc, void* tcws,
-             TcDirBuffers* out, float* dbg, cudaStream_t st);
+// src[k]: the model's own fp32 candidate tables (row pitch m->dim); scratch: optional fp32 copy
+// [KC][nc][dp] for the fp32 fallback sweep (normalised for TransE), written by the same kernel
+int tc_prepare_candidates(const kge_model_t* m, const float* const src[2], int64_t nc, void* tcws, int64_t Q,
+                          float* scratch, cudaStream_t st);
+struct TcQueryArgs;
+TcQueryArgs tc_query_args(const kge_model_t* m, int dir, void* tcws, int64_t Q);
+int tc_sweep(const kge_model_t* m, int dir, int64_t Q, int64_t nc, void* tcws, TcDirBuffers* out, float* dbg,
+             cudaStream_t st);
 // Level 2 (kge_rank.cu): exact fp32 re-evaluation of the listed pairs, then the last CTA adds the
 // direction's counts to counts[q*4+col], counts[q*4+col+1] — or, if the list overflowed, raises
 // ctrl[3] so that the fp32 sweep enqueued next does the whole direction instead.
+// The same kernel also applies the direction's filter corrections (the entries of the CSR filter that
+// outrank the target are subtracted from the filtered column) — they are exact re-evaluations of
+// listed pairs too —, so the tensor-core path needs no separate filter pass.
+struct RankFilter { const int64_t* ptr; const int64_t* idx; int64_t nnz; const int64_t* tgt; int64_t row_lo, row_hi; };
 int band_resolve(const kge_model_t* m, const kge_model_t* mq, int dir, const int64_t* qh, const int64_t* qr,
-                 const int64_t* qt, const float* thr, int64_t Q, const TcDirBuffers& B, int32_t* counts, int col,
-                 cudaStream_t st);
+                 const int64_t* qt, const float* thr, int64_t Q, const TcDirBuffers& B, const RankFilter& F,
+                 int32_t* counts, int col, cudaStream_t st);
 }  // namespace kge

@@ -35,6 +35,7 @@
 
 #include "kge_models.cuh"
 #include "kge_rank.cuh"
+#include "kge_rank_tc.cuh"
 
 namespace kge {
 
@@ -141,6 +142,47 @@ KGE_DEV uint32_t tc_tmem_ld1(uint32_t taddr) {
   return v;
 }
 KGE_DEV void tc_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 32 accumulator columns (= candidates cbase .. cbase+31) of this thread's query row: count the
+// certainly-better ones; rows with candidates inside the band list them — from the registers already
+// loaded (statically indexed: nothing spills), a thread-divergent but short path taken by ~1 % of the
+// (thread, chunk) pairs.
+KGE_DEV int tc_scan_chunk(const uint32_t (&v)[32], int nv, float tau_hi, float tau_lo, int64_t q, int64_t cbase,
+                          bool live, const TcParams& P) {
+  int hi = 0, lo = 0;
+  if (nv == 32) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float x = __uint_as_float(v[j]);
+      hi += (x > tau_hi) ? 1 : 0;
+      lo += (x >= tau_lo) ? 1 : 0;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float x = __uint_as_float(v[j]);
+      hi += (j < nv && x > tau_hi) ? 1 : 0;
+      lo += (j < nv && x >= tau_lo) ? 1 : 0;
+    }
+  }
+  if (lo != hi) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float x = __uint_as_float(v[j]);
+      if (j < nv && x >= tau_lo && !(x > tau_hi)) {
+        const unsigned idx = atomicAdd(&P.ctrl[0], 1u);
+        if (idx < P.cap) P.list[idx] = ((unsigned long long)q << 32) | (unsigned long long)(cbase + j);
+        else P.ctrl[1] = 1u;
+      }
+    }
+  }
+  if (P.dbg && live) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < nv) P.dbg[(size_t)q * (size_t)P.nc + (size_t)(cbase + j)] = __uint_as_float(v[j]);
+  }
+  return hi;
+}
 
 // ---- the sweep ------------------------------------------------------------------------------------
 // grid (splits, query blocks); CTA = 128 queries x a run of 128-candidate tiles.
@@ -263,43 +305,19 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
       const int64_t cbase = (int64_t)(t0 + t) * kTcBN;
       const int nvalid = (int)min((int64_t)kTcBN, P.nc - cbase);
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * kTcBN);
-      for (int cb = 0; cb * 32 < nvalid; ++cb) {
-        uint32_t v[32];
-        tc_tmem_ld32(taddr + (uint32_t)(cb * 32), v);
+      const int nchunks = (nvalid + 31) >> 5;
+      // two register buffers: the tcgen05.ld of chunk cb+1 is in flight while chunk cb is compared
+      uint32_t va[32], vb[32];
+      tc_tmem_ld32(taddr, va);
+#pragma unroll 1
+      for (int cb = 0; cb < nchunks; cb += 2) {
         tc_tmem_wait_ld();
-        const int nv = min(32, nvalid - cb * 32);
-        int hi = 0, lo = 0;
-        if (nv == 32) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float x = __uint_as_float(v[j]);
-            hi += (x > tau_hi) ? 1 : 0;
-            lo += (x >= tau_lo) ? 1 : 0;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float x = __uint_as_float(v[j]);
-            hi += (j < nv && x > tau_hi) ? 1 : 0;
-            lo += (j < nv && x >= tau_lo) ? 1 : 0;
-          }
-        }
-        cnt += hi;
-        if (P.dbg && live) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < nv) P.dbg[(size_t)q * (size_t)P.nc + (size_t)(cbase + cb * 32 + j)] = __uint_as_float(v[j]);
-        }
-        if (__any_sync(0xffffffffu, lo != hi)) {   // rare: some row of this warp has candidates inside its band
-          for (int j = 0; j < nv; ++j) {
-            const float x = __uint_as_float(tc_tmem_ld1(taddr + (uint32_t)(cb * 32 + j)));
-            tc_tmem_wait_ld();
-            if (x >= tau_lo && !(x > tau_hi)) {
-              const unsigned idx = atomicAdd(&P.ctrl[0], 1u);
-              if (idx < P.cap) P.list[idx] = ((unsigned long long)q << 32) | (unsigned long long)(cbase + cb * 32 + j);
-              else P.ctrl[1] = 1u;
-            }
-          }
+        if (cb + 1 < nchunks) tc_tmem_ld32(taddr + (uint32_t)((cb + 1) * 32), vb);
+        cnt += tc_scan_chunk(va, min(32, nvalid - cb * 32), tau_hi, tau_lo, q, cbase + cb * 32, live, P);
+        if (cb + 1 < nchunks) {
+          tc_tmem_wait_ld();
+          if (cb + 2 < nchunks) tc_tmem_ld32(taddr + (uint32_t)((cb + 2) * 32), va);
+          cnt += tc_scan_chunk(vb, min(32, nvalid - (cb + 1) * 32), tau_hi, tau_lo, q, cbase + (cb + 1) * 32, live, P);
         }
       }
       tc_fence_before();
@@ -317,148 +335,59 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
 }
 
 // ---- operand preparation --------------------------------------------------------------------------
-KGE_DEV double tc_group_sum_d(double v) {
-  const unsigned m = group_mask();
-  v += __shfl_xor_sync(m, v, 4);
-  v += __shfl_xor_sync(m, v, 2);
-  v += __shfl_xor_sync(m, v, 1);
-  return v;
-}
-KGE_DEV void tc_split_store(__nv_bfloat16* o0, __nv_bfloat16* o1, float4 x, float sign) {
-  __nv_bfloat16 h[4], l[4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const float xv = sign * f4_get(x, e);
-    h[e] = __float2bfloat16_rn(xv);
-    l[e] = __float2bfloat16_rn(__fsub_rn(xv, __bfloat162float(h[e])));   // xv - h is exact in fp32
-  }
-  *reinterpret_cast<uint2*>(o0) = *reinterpret_cast<const uint2*>(h);
-  *reinterpret_cast<uint2*>(o1) = *reinterpret_cast<const uint2*>(l);
-}
-
-// One 8-lane group per candidate row: bf16 split of its KC arrays (concatenated along k), the three
-// norm columns (squared-distance models) and the running max of |c|^2.
+// One 8-lane group per candidate row, ONE pass over the fp32 table(s) for everything the row needs:
+// (NORMALISE: TransE) the canonical row normalisation of the fp32 sweep's scratch copy — same arithmetic
+// as prep_cand_kernel, written to s0 when the caller keeps that scratch for the fp32 fallback —, the bf16
+// split of the KC arrays concatenated along k, the three norm columns (squared-distance models) and the
+// running max of |c|^2.  Rows are read with the widest vector the table alignment allows; columns
+// d .. dp-1 are zero.
+template <int VEC, bool NORMALISE>
 __global__ void __launch_bounds__(256)
-tc_prep_cand_kernel(const float* __restrict__ c0, const float* __restrict__ c1, int64_t pitch, int64_t nc, int dp,
-                    int KC, int Kp, int aug, __nv_bfloat16* __restrict__ B0, __nv_bfloat16* __restrict__ B1,
-                    unsigned* __restrict__ cmax_bits) {
+tc_prep_cand_kernel(const float* __restrict__ c0, const float* __restrict__ c1, int64_t pitch, int64_t nc, int d,
+                    int dp, int KC, int Kp, int aug, __nv_bfloat16* __restrict__ B0, __nv_bfloat16* __restrict__ B1,
+                    unsigned* __restrict__ cmax_bits, float* __restrict__ s0, float* __restrict__ s1) {
   const int lane = threadIdx.x & 7;
   const int64_t e = (int64_t)blockIdx.x * 32 + (threadIdx.x >> 3);
   if (e >= nc) return;
-  const int nchp = dp >> 2;
+  const int nch = (d + 3) >> 2, nchp = dp >> 2;
   __nv_bfloat16* o0 = B0 + (size_t)e * Kp;
   __nv_bfloat16* o1 = B1 + (size_t)e * Kp;
   double ss = 0.0;
   for (int k = 0; k < KC; ++k) {
     const float* row = (k == 0 ? c0 : c1) + (size_t)e * pitch;
+    float* srow = (k == 0 ? s0 : s1);
+    if (srow) srow += (size_t)e * dp;
+    float inv = 1.f;
+    if (NORMALISE) {
+      float s = 0.f;
+      for (int c = lane; c < nch; c += 8) {
+        const float4 x = ld_chunk<VEC>(row, c, d);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s = ffma(f4_get(x, j), f4_get(x, j), s);
+      }
+      inv = inv_norm_from_sumsq(group_sum(s));
+    }
     for (int c = lane; c < nchp; c += 8) {
-      const float4 x = __ldg(reinterpret_cast<const float4*>(row) + c);
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < nch) {
+        x = ld_chunk<VEC>(row, c, d);
+        if (NORMALISE) { x.x = fmul(x.x, inv); x.y = fmul(x.y, inv); x.z = fmul(x.z, inv); x.w = fmul(x.w, inv); }
+      }
+      if (srow) *reinterpret_cast<float4*>(srow + 4 * c) = x;
 #pragma unroll
       for (int j = 0; j < 4; ++j) ss += (double)f4_get(x, j) * (double)f4_get(x, j);
       tc_split_store(o0 + k * dp + 4 * c, o1 + k * dp + 4 * c, x, 1.0f);
     }
   }
   ss = tc_group_sum_d(ss);
-  const int K = KC * dp;
-  for (int c = K / 4 + lane; c < Kp / 4; c += 8) {   // norm columns + zero padding (K and Kp are multiples of 4)
-    __nv_bfloat16 h[4], l[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { h[j] = __float2bfloat16_rn(0.f); l[j] = h[j]; }
-    if (aug && c == K / 4) {   // |c|^2 / 2 = n0 + n1 + n2 (+ <= 2^-26 relative), multiplied by the query's -1 columns
-      const float half = (float)(0.5 * ss);
-      const __nv_bfloat16 n0 = __float2bfloat16_rn(half);
-      const float r1 = __fsub_rn(half, __bfloat162float(n0));
-      const __nv_bfloat16 n1 = __float2bfloat16_rn(r1);
-      const __nv_bfloat16 n2 = __float2bfloat16_rn(__fsub_rn(r1, __bfloat162float(n1)));
-      h[0] = n0; h[1] = n1; h[2] = n2;
-    }
-    *reinterpret_cast<uint2*>(o0 + 4 * c) = *reinterpret_cast<const uint2*>(h);
-    *reinterpret_cast<uint2*>(o1 + 4 * c) = *reinterpret_cast<const uint2*>(l);
-  }
+  // |c|^2 / 2 = n0 + n1 + n2 (+ <= 2^-26 relative), multiplied by the query's -1 columns
+  const float half = (float)(0.5 * ss);
+  const __nv_bfloat16 n0 = __float2bfloat16_rn(half);
+  const float r1 = __fsub_rn(half, __bfloat162float(n0));
+  const __nv_bfloat16 n1 = __float2bfloat16_rn(r1);
+  const __nv_bfloat16 n2 = __float2bfloat16_rn(__fsub_rn(r1, __bfloat162float(n1)));
+  tc_store_tail(o0, o1, KC * dp, Kp, lane, aug != 0, n0, n1, n2);
   if (lane == 0) atomicMax(cmax_bits, __float_as_uint(__double2float_ru(ss)));   // non-negative floats order like their bits
-}
-
-// The L2 sum-domain threshold of kge_rank_tiled.cu (rule 7 of DESIGN.md §3), restated for this file.
-KGE_DEV float tc_sqrt_domain_threshold(float th) {
-  if (!(th > 0.f)) return 0.f;
-  float x = fmul(th, th);
-  while (__fsqrt_rn(x) >= th) x = __uint_as_float(__float_as_uint(x) - 1u);
-  while (__fsqrt_rn(x) < th) x = __uint_as_float(__float_as_uint(x) + 1u);
-  return x;
-}
-
-// One 8-lane group per query: bf16 split of its KQ query vectors (sign -1 for the head sweep of the
-// translational models, whose canonical distance is |c + q|), the -1 norm columns, and the two
-// accumulator thresholds.  kind: 0 dot product (better <=> sum > -thr), 1 squared distance compared in
-// the sum domain (TransE-L2), 2 squared distance minus margin (RotatE).
-//
-// Error budget (all in double, rounded outwards to float at the end); A = |q| * max|c| >= sum |q_k c_k|:
-//   split     : |x - x0 - x1| <= 2^-18 |x| per operand -> dropped terms <= 3 * 2^-18 * 1.01 A   (bounded by 2^-16 A)
-//   accumulate: the tensor core adds exact products into an fp32 accumulator; each of the nmma
-//               instructions may lose <= 2 ulp of the running magnitude (<= A)                  -> nmma * 2^-22 A
-//   E_tc = 2 * (2^-16 + nmma * 2^-22) * A      (factor 2: safety; tests measure the real error)
-//   norm columns: 3-way bf16 split of |c|^2/2, float rounding of it                              -> 2^-22 max|c|^2
-//   canonical fp32 chain vs exact value of the same fp32 operands (RSUM, 8 partials, K/8 fma each
-//               + 3 butterfly adds; squared distances add one rounding of (q - c) per element):
-//               gamma = (K/8 + 8) * 2^-24 (+ 2^-22)  times  A  (dot)  or  (|q| + max|c|)^2  (distance)
-__global__ void __launch_bounds__(256)
-tc_prep_query_kernel(const float* __restrict__ qvec, const float* __restrict__ thr, int64_t Q, int dp, int KQ,
-                     int Kp, int kind, float sign, float margin, const unsigned* __restrict__ cmax_bits,
-                     __nv_bfloat16* __restrict__ A0, __nv_bfloat16* __restrict__ A1, float* __restrict__ tau,
-                     int32_t* __restrict__ tc_counts, unsigned* __restrict__ ctrl) {
-  if (blockIdx.x == 0 && threadIdx.x < 4) ctrl[threadIdx.x] = 0u;   // list length, overflow, ticket, fallback flag
-  const int lane = threadIdx.x & 7;
-  const int64_t q = (int64_t)blockIdx.x * 32 + (threadIdx.x >> 3);
-  if (q >= Q) return;
-  const int nchp = dp >> 2;
-  const int K = KQ * dp;
-  __nv_bfloat16* o0 = A0 + (size_t)q * Kp;
-  __nv_bfloat16* o1 = A1 + (size_t)q * Kp;
-  const float* src = qvec + (size_t)q * K;
-  double ss = 0.0;
-  for (int c = lane; c < KQ * nchp; c += 8) {
-    const float4 x = __ldg(reinterpret_cast<const float4*>(src) + c);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) ss += (double)f4_get(x, j) * (double)f4_get(x, j);
-    tc_split_store(o0 + 4 * c, o1 + 4 * c, x, sign);
-  }
-  ss = tc_group_sum_d(ss);
-  for (int c = K / 4 + lane; c < Kp / 4; c += 8) {
-    __nv_bfloat16 h[4], l[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { h[j] = __float2bfloat16_rn(0.f); l[j] = h[j]; }
-    if (kind != 0 && c == K / 4) { h[0] = h[1] = h[2] = __float2bfloat16_rn(-1.0f); }
-    *reinterpret_cast<uint2*>(o0 + 4 * c) = *reinterpret_cast<const uint2*>(h);
-    *reinterpret_cast<uint2*>(o1 + 4 * c) = *reinterpret_cast<const uint2*>(l);
-  }
-  if (lane != 0) return;
-  tc_counts[q] = 0;
-  const double cmax2 = (double)__uint_as_float(*cmax_bits);
-  const double cmax = sqrt(cmax2) * (1.0 + 1e-7), nq = sqrt(ss) * (1.0 + 1e-7);
-  const double A = nq * cmax;
-  const int nmma = 3 * ((Kp + 15) / 16);
-  const double e_tc = 2.0 * (ldexp(1.0, -16) + (double)nmma * ldexp(1.0, -22)) * A + ldexp(1.0, -22) * cmax2 + 1e-30;
-  const double gamma = ((double)K / 8.0 + 8.0) * ldexp(1.0, -24);
-  const float th = thr[q];
-  double centre, half;
-  if (kind == 0) {
-    centre = -(double)th;                        // canonical: -sum < th  <=>  sum > -th (negation is exact)
-    half = e_tc + gamma * A;
-  } else {
-    const double smax = (nq + cmax) * (nq + cmax);
-    const double g2 = gamma + ldexp(1.0, -22);
-    if (kind == 1) {                             // canonical: sum < T(th)
-      const double T = (double)tc_sqrt_domain_threshold(th);
-      centre = 0.5 * (ss - T);
-      half = 0.5 * (2.0 * e_tc + g2 * smax) + ldexp(1.0, -50) * ss;
-    } else {                                     // canonical: fsub(sum, margin) < th
-      centre = 0.5 * (ss - (double)th - (double)margin);
-      half = 0.5 * (2.0 * e_tc + g2 * smax + ldexp(1.0, -24) * (smax * 1.01 + fabs((double)margin))) + ldexp(1.0, -50) * ss;
-    }
-  }
-  // NaN thresholds propagate: every comparison with them is false, as `s < NaN` is in the exact path
-  tau[2 * q] = __double2float_ru(centre + half);
-  tau[2 * q + 1] = __double2float_rd(centre - half);
 }
 
 // ---- host side ------------------------------------------------------------------------------------
@@ -544,40 +473,71 @@ static int tc_make_map(CUtensorMap* tm, const void* base, uint64_t rows, uint64_
   return KGE_OK;
 }
 
-// candidate split of the fp32 arrays the fp32 sweep would read (cand[k], row pitch `pitch` floats)
-int tc_prepare_candidates(const kge_model_t* m, const float* const cand[2], int64_t pitch, int64_t nc, void* tcws,
-                          int64_t Q, cudaStream_t st) {
+// Candidate operands from the model's own fp32 tables src[k] (row pitch m->dim): bf16 split (+ norm
+// columns, + max |c|^2) and, when `scratch` is given, the fp32 copy the fp32 fallback sweep reads
+// (normalised for TransE, zero padded to dp) — all in one kernel.
+int tc_prepare_candidates(const kge_model_t* m, const float* const src[2], int64_t nc, void* tcws, int64_t Q,
+                          float* scratch, cudaStream_t st) {
   const TcLayout L = tc_layout(m, Q);
   char* w = reinterpret_cast<char*>(tcws);
   unsigned* cmax = reinterpret_cast<unsigned*>(w + L.cmax);
   KGE_CUDA_OK(cudaMemsetAsync(cmax, 0, sizeof(unsigned), st));
-  const int KC = tc_kq(m->model);
-  tc_prep_cand_kernel<<<(unsigned)((nc + 31) / 32), 256, 0, st>>>(
-      cand[0], KC == 2 ? cand[1] : cand[0], pitch, nc, tc_dp(m), KC, tc_kp(m), tc_kind(m) != 0 ? 1 : 0,
-      reinterpret_cast<__nv_bfloat16*>(w + L.b[0]), reinterpret_cast<__nv_bfloat16*>(w + L.b[1]), cmax);
+  const int KC = tc_kq(m->model), d = m->dim, dp = tc_dp(m), Kp = tc_kp(m), aug = tc_kind(m) != 0 ? 1 : 0;
+  int vc = (d % 4 == 0) ? 4 : (d % 2 == 0 ? 2 : 1);
+  for (int k = 0; k < KC; ++k) {
+    const uintptr_t a = (uintptr_t)src[k];
+    if (vc == 4 && (a & 15)) vc = 2;
+    if (vc == 2 && (a & 7)) vc = 1;
+  }
+  const float* c0 = src[0];
+  const float* c1 = KC == 2 ? src[1] : src[0];
+  float* s0 = scratch;
+  float* s1 = (scratch && KC == 2) ? scratch + (size_t)nc * dp : nullptr;
+  __nv_bfloat16* B0 = reinterpret_cast<__nv_bfloat16*>(w + L.b[0]);
+  __nv_bfloat16* B1 = reinterpret_cast<__nv_bfloat16*>(w + L.b[1]);
+  const unsigned grid = (unsigned)((nc + 31) / 32);
+  const bool normalise = m->model == KGE_TRANSE;
+#define TC_PREP(V, NRM) tc_prep_cand_kernel<V, NRM><<<grid, 256, 0, st>>>(c0, c1, (int64_t)d, nc, d, dp, KC, Kp, aug, B0, B1, cmax, s0, s1)
+  if (normalise) { if (vc == 4) TC_PREP(4, true); else if (vc == 2) TC_PREP(2, true); else TC_PREP(1, true); }
+  else { if (vc == 4) TC_PREP(4, false); else if (vc == 2) TC_PREP(2, false); else TC_PREP(1, false); }
+#undef TC_PREP
   KGE_CHECK_LAUNCH("tc_prep_cand_kernel");
   return KGE_OK;
 }
 
-// Level 1 of one direction: query split + thresholds, then the tensor-core sweep.  On return (in
-// stream order) tc_counts[q] holds the certain counts and list/ctrl the ambiguous pairs.
-int tc_sweep(const kge_model_t* m, int dir, const float* qvec, const float* thr, int64_t Q, int64_t nc, void* tcws,
-             TcDirBuffers* out, float* dbg, cudaStream_t st) {
+// Where prep_query_kernel (kge_rank_tiled.cu) leaves the tensor-core operands of direction `dir`.
+TcQueryArgs tc_query_args(const kge_model_t* m, int dir, void* tcws, int64_t Q) {
   const TcLayout L = tc_layout(m, Q);
   char* w = reinterpret_cast<char*>(tcws);
-  const int Kp = tc_kp(m), KQ = tc_kq(m->model), dp = tc_dp(m), kind = tc_kind(m);
-  __nv_bfloat16* A0 = reinterpret_cast<__nv_bfloat16*>(w + L.a[dir][0]);
-  __nv_bfloat16* A1 = reinterpret_cast<__nv_bfloat16*>(w + L.a[dir][1]);
-  float* tau = reinterpret_cast<float*>(w + L.tau[dir]);
-  int32_t* cnt = reinterpret_cast<int32_t*>(w + L.cnt[dir]);
-  unsigned* ctrl = reinterpret_cast<unsigned*>(w + L.ctrl[dir]);
-  unsigned long long* list = reinterpret_cast<unsigned long long*>(w + L.list[dir]);
-  const unsigned* cmax = reinterpret_cast<const unsigned*>(w + L.cmax);
+  TcQueryArgs T;
+  T.A0 = reinterpret_cast<__nv_bfloat16*>(w + L.a[dir][0]);
+  T.A1 = reinterpret_cast<__nv_bfloat16*>(w + L.a[dir][1]);
+  T.tau = reinterpret_cast<float*>(w + L.tau[dir]);
+  T.tc_counts = reinterpret_cast<int32_t*>(w + L.cnt[dir]);
+  T.ctrl = reinterpret_cast<unsigned*>(w + L.ctrl[dir]);
+  T.cmax_bits = reinterpret_cast<const unsigned*>(w + L.cmax);
+  T.Kp = tc_kp(m); T.kind = tc_kind(m);
   // head sweep of TransE: canonical distance is |c + q| with q = r^ - t^  ->  contract with -q
-  const float sign = (m->model == KGE_TRANSE && dir == 1) ? -1.0f : 1.0f;
-  tc_prep_query_kernel<<<(unsigned)((Q + 31) / 32), 256, 0, st>>>(qvec, thr, Q, dp, KQ, Kp, kind, sign, m->margin,
-                                                                cmax, A0, A1, tau, cnt, ctrl);
-  KGE_CHECK_LAUNCH("tc_prep_query_kernel");
+  T.sign = (m->model == KGE_TRANSE && dir == 1) ? -1.0f : 1.0f;
+  T.margin = m->margin;
+  return T;
+}
+
+// Level 1 of one direction (the query operands and thresholds were written by prep_query_kernel): the
+// tensor-core sweep.  On return (in stream order) tc_counts[q] holds the certain counts and list/ctrl
+// the ambiguous pairs.
+int tc_sweep(const kge_model_t* m, int dir, int64_t Q, int64_t nc, void* tcws, TcDirBuffers* out, float* dbg,
+             cudaStream_t st) {
+  const TcLayout L = tc_layout(m, Q);
+  char* w = reinterpret_cast<char*>(tcws);
+  const int Kp = tc_kp(m);
+  const TcQueryArgs T = tc_query_args(m, dir, tcws, Q);
+  __nv_bfloat16* A0 = T.A0;
+  __nv_bfloat16* A1 = T.A1;
+  float* tau = T.tau;
+  int32_t* cnt = T.tc_counts;
+  unsigned* ctrl = T.ctrl;
+  unsigned long long* list = reinterpret_cast<unsigned long long*>(w + L.list[dir]);
 
   TcParams P;
   P.tau = tau; P.tc_counts = cnt; P.ctrl = ctrl; P.list = list; P.cap = tc_list_capacity(Q);

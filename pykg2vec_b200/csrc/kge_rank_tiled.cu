@@ -26,6 +26,7 @@
 
 #include "kge_models.cuh"
 #include "kge_rank.cuh"
+#include "kge_rank_tc.cuh"
 
 namespace kge {
 
@@ -398,19 +399,19 @@ template <int MODEL, int VEC, int DIR>
 __global__ void __launch_bounds__(256)
 prep_query_kernel(ModelParams P, const int64_t* __restrict__ qh, const int64_t* __restrict__ qr,
                   const int64_t* __restrict__ qt, int64_t Q, int dp, float* __restrict__ qvec,
-                  float* __restrict__ qscale, float* __restrict__ thr, int scratch_floats) {
+                  float* __restrict__ qscale, float* __restrict__ thr, int scratch_floats, const TcQueryArgs TC) {
   extern __shared__ float4 smem_f4[];
   float* scratch = reinterpret_cast<float*>(smem_f4) + (size_t)(threadIdx.x >> 3) * scratch_floats;
   const int lane = threadIdx.x & 7;
   const int64_t q = (int64_t)blockIdx.x * 32 + (threadIdx.x >> 3);
+  if (TC.A0 && blockIdx.x == 0 && threadIdx.x < 4) TC.ctrl[threadIdx.x] = 0u;   // pair-list length, overflow, ticket, fallback flag
   if (q >= Q) return;
   const int d = P.d, nch = (d + 3) >> 2, nchp = dp >> 2;
   TripleRows R;
   resolve_rows<MODEL>(R, P, P.qtab, P.qtab, P.qtab, __ldg(qh + q), __ldg(qr + q), __ldg(qt + q));
-  {  // threshold = the target's own score in this direction's grouping (== kge_score_fwd)
-    const float s = score_group<MODEL, VEC, DIR == 0 ? KGE_GROUP_TAIL : KGE_GROUP_HEAD>(R, P, lane, scratch);
-    if (lane == 0) thr[q] = s;
-  }
+  // threshold = the target's own score in this direction's grouping (== kge_score_fwd)
+  const float s_target = score_group<MODEL, VEC, DIR == 0 ? KGE_GROUP_TAIL : KGE_GROUP_HEAD>(R, P, lane, scratch);
+  if (lane == 0) thr[q] = s_target;
   constexpr int KQ = (MODEL == KGE_COMPLEX || MODEL == KGE_SIMPLE || MODEL == KGE_SIMPLE_IGNR)
                          ? 2 : (MODEL == KGE_ROTATE ? 2 : 1);
   float* out = qvec + (size_t)q * KQ * dp;
@@ -512,6 +513,12 @@ prep_query_kernel(ModelParams P, const int64_t* __restrict__ qh, const int64_t* 
       }
       st(0, c, o0); st(1, c, o1);
     }
+  }
+  if (TC.A0) {
+    // tensor-core level: bf16 split of the vectors just written (a lane reads chunks other lanes of its
+    // group stored: order the group's global writes first) + the accumulator thresholds
+    __syncwarp(group_mask());
+    tc_query_finish(TC, out, s_target, q, lane, KQ * dp);
   }
 }
 
@@ -627,15 +634,9 @@ int tiled_prepare_candidates(const kge_model_t* m, int64_t nc, void* ws, int64_t
   const int KC = num_cand_tables(m->model);
   float* cscratch = cand_scratch_ptr(m, ws, Q);
   const bool scratch = cand_sources(m, 0, src);
-  if (scratch) {
-    int rc = fill_cand_scratch(m, src, KC, nc, cscratch, st);
-    if (rc) return rc;
-  }
-  if (use_tc) {   // bf16 split of exactly the fp32 arrays the fp32 sweep reads
-    const float* cand[2] = {scratch ? cscratch : src[0],
-                            KC == 2 ? (scratch ? cscratch + (size_t)nc * dp_of(m) : src[1]) : nullptr};
-    return tc_prepare_candidates(m, cand, scratch ? dp_of(m) : m->dim, nc, tc_ws_ptr(m, ws, Q), Q, st);
-  }
+  if (use_tc)   // one kernel: bf16 split for the tensor cores + (if the fp32 sweep needs one) its scratch copy
+    return tc_prepare_candidates(m, src, nc, tc_ws_ptr(m, ws, Q), Q, scratch ? cscratch : nullptr, st);
+  if (scratch) return fill_cand_scratch(m, src, KC, nc, cscratch, st);
   return KGE_OK;
 }
 
@@ -721,8 +722,8 @@ static int launch_sweep(const TiledParams& P, int QBLK, size_t smem, cudaStream_
 
 int tiled_sweep(const kge_model_t* m, const kge_model_t* mq, int dir, const int64_t* qh,
                 const int64_t* qr, const int64_t* qt, float* thr, int64_t Q, int64_t nc,
-                int32_t* counts, int col, void* ws, bool use_tc, float* tc_dbg, float* tc_tau_out,
-                cudaStream_t st) {
+                int32_t* counts, int col, void* ws, bool use_tc, const RankFilter* filter, float* tc_dbg,
+                float* tc_tau_out, cudaStream_t st) {
   const int model = m->model;
   const int d = m->dim, dp = dp_of(m);
   const int op = (model == KGE_TRANSE || model == KGE_TRANSM) ? (dir == 0 ? OP_TRANS_T : OP_TRANS_H)
@@ -747,14 +748,17 @@ int tiled_sweep(const kge_model_t* m, const kge_model_t* mq, int dir, const int6
   const unsigned qgrid = (unsigned)((Q + 31) / 32);
   const int psf = (int)group_scratch_floats(mq);
   const size_t psmem = (size_t)psf * 32 * sizeof(float);
+  TcQueryArgs TCQ;
+  TCQ.A0 = nullptr;
+  if (use_tc) TCQ = tc_query_args(m, dir, tc_ws_ptr(m, ws, Q), Q);
 #define PREP(M, V)                                                                                   \
   do {                                                                                               \
     if (dir == 0) {                                                                                  \
       if (psmem > 40 * 1024) KGE_CUDA_OK(cudaFuncSetAttribute(prep_query_kernel<M, V, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem)); \
-      prep_query_kernel<M, V, 0><<<qgrid, 256, psmem, st>>>(PQ, qh, qr, qt, Q, dp, qvec, qscale, thr, psf); \
+      prep_query_kernel<M, V, 0><<<qgrid, 256, psmem, st>>>(PQ, qh, qr, qt, Q, dp, qvec, qscale, thr, psf, TCQ); \
     } else {                                                                                         \
       if (psmem > 40 * 1024) KGE_CUDA_OK(cudaFuncSetAttribute(prep_query_kernel<M, V, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem)); \
-      prep_query_kernel<M, V, 1><<<qgrid, 256, psmem, st>>>(PQ, qh, qr, qt, Q, dp, qvec, qscale, thr, psf); \
+      prep_query_kernel<M, V, 1><<<qgrid, 256, psmem, st>>>(PQ, qh, qr, qt, Q, dp, qvec, qscale, thr, psf, TCQ); \
     }                                                                                                \
   } while (0)
   switch (model) {
@@ -781,12 +785,16 @@ int tiled_sweep(const kge_model_t* m, const kge_model_t* mq, int dir, const int6
       for (int k = 0; k < KC; ++k) P.cand[k] = cscratch + (size_t)k * (size_t)nc * dp;
       if (KC == 1) P.cand[1] = nullptr;
       P.cand_pitch = dp;
-      if (model == KGE_CP || is_simple(model)) {  // tables differ per direction: (re)fill now
+      if ((model == KGE_CP && !use_tc) || is_simple(model)) {  // tables differ per direction: (re)fill now
         int rc = fill_cand_scratch(m, src, KC, nc, cscratch, st);
         if (rc) return rc;
       }
     } else {
       P.cand[0] = src[0]; P.cand[1] = src[1]; P.cand_pitch = d;
+    }
+    if (model == KGE_CP && use_tc) {   // CP sweeps the object table for tails, the subject table for heads
+      int rc = tc_prepare_candidates(m, src, nc, tc_ws_ptr(m, ws, Q), Q, scratch ? cscratch : nullptr, st);
+      if (rc) return rc;
     }
   }
 
@@ -809,20 +817,16 @@ int tiled_sweep(const kge_model_t* m, const kge_model_t* mq, int dir, const int6
   const size_t smem = bytes_for(DS, nslabs > 1 ? 2 : 1);
   P.run_flag = nullptr;
   if (use_tc) {
-    // level 1 on the tensor cores, level 2 = exact fp32 resolution of the ambiguous pairs; the fp32
-    // sweep below stays enqueued as the fallback and returns at once unless the list overflowed
-    void* tcws = tc_ws_ptr(m, ws, Q);
-    if (model == KGE_CP) {   // candidate table differs per direction
-      const float* cand[2] = {P.cand[0], nullptr};
-      int rc = tc_prepare_candidates(m, cand, P.cand_pitch, nc, tcws, Q, st);
-      if (rc) return rc;
-    }
+    // level 1 on the tensor cores, level 2 = exact fp32 resolution of the ambiguous pairs (+ the filter
+    // corrections, same kernel); the fp32 sweep below stays enqueued as the fallback and returns at once
+    // unless the pair list overflowed
     TcDirBuffers B;
-    int rc = tc_sweep(m, dir, qvec, thr, Q, nc, tcws, &B, tc_dbg, st);
+    int rc = tc_sweep(m, dir, Q, nc, tc_ws_ptr(m, ws, Q), &B, tc_dbg, st);
     if (rc) return rc;
     if (tc_tau_out)
       KGE_CUDA_OK(cudaMemcpyAsync(tc_tau_out, B.tau, (size_t)Q * 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    rc = band_resolve(m, mq, dir, qh, qr, qt, thr, Q, B, counts, col, st);
+    RankFilter none = {nullptr, nullptr, 0, nullptr, 0, 0};
+    rc = band_resolve(m, mq, dir, qh, qr, qt, thr, Q, B, filter ? *filter : none, counts, col, st);
     if (rc) return rc;
     P.run_flag = B.ctrl + 3;
   }

@@ -227,6 +227,9 @@ int kge_rank_1vsall(const kge_model_t* m, const kge_model_t* mq, int64_t row_lo,
  * tc_sweep_kernel, or sweep_tiled_kernel with KGE_RANK_NO_TC — measured by CUDA events recorded around
  * that launch on the stream it ran on (waits for the kernel).  Not usable inside a graph capture. */
 int kge_rank_last_sweep_ms(int direction, float* ms);
+/* Measurement aid: per-role clock64 timeline of CTA (0,0) of subsequent tc_sweep_kernel launches into the
+ * device buffer buf[3][64] (NULL = off): role 0 TMA producer, 1 MMA issuer, 2 epilogue (see kge_rank.cu). */
+int kge_debug_set_tc_trace(long long* buf);
 
 /* Two-level exact sweep (TransE -l1 False, DistMult, CP, ComplEx, RESCAL, RotatE; >= 1024 candidate rows):
  * level 1 evaluates the Q x N x K contraction on the tensor cores (tcgen05.mma, bf16 x 3 split, fp32

@@ -435,3 +435,12 @@ extern "C" int kge_rank_last_sweep_ms(int direction, float* ms) {
   KGE_CUDA_OK(cudaEventElapsedTime(ms, sp->beg, sp->end));
   return KGE_OK;
 }
+
+// Measurement aid: clock64 stamps of CTA (0,0) of the following tc_sweep_kernel launches are written to
+// buf[3 roles][64] (device memory; NULL switches it off).  Roles: 0 TMA producer (slot 0 start, then one
+// per acquired stage), 1 MMA issuer (start, queries resident, then per tile: accumulator free, per
+// k-block: stage full), 2 epilogue warp (start, per tile: accumulator ready, tile done; slot 63: kernel entry).
+extern "C" int kge_debug_set_tc_trace(long long* buf) {
+  tc_set_trace(buf);
+  return KGE_OK;
+}

@@ -34,6 +34,7 @@ struct TcDirBuffers {
   unsigned cap;
   const float* tau;            // [Q][2] accumulator thresholds (hi, lo)
 };
+void tc_set_trace(long long* buf);
 bool tc_supported(const kge_model_t* m, int64_t nc);
 size_t tc_workspace_bytes(const kge_model_t* m, int64_t Q);
 // src[k]: the model's own fp32 candidate tables (row pitch m->dim); scratch: optional fp32 copy

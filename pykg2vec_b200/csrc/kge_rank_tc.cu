@@ -33,6 +33,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "kge_models.cuh"
 #include "kge_rank.cuh"
 #include "kge_rank_tc.cuh"
@@ -58,6 +60,8 @@ struct TcParams {
   int Kp, nkb, a_resident, nstages;
   int tiles_per_cta, ntiles;
   float* dbg;              // optional [Q][nc] raw accumulators (tests)
+  long long* trace;        // optional timeline of CTA (0,0): [3 roles][64] clock64 stamps (kge_debug_set_tc_trace)
+  int epi_mode;            // measurement aid (KGE_TC_EPI_MODE): 0 normal, 1 load only, 2 count only (no band listing)
 };
 struct TcMaps { CUtensorMap a0, a1, b0, b1; };
 
@@ -150,6 +154,7 @@ KGE_DEV void tc_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" :
 KGE_DEV int tc_scan_chunk(const uint32_t (&v)[32], int nv, float tau_hi, float tau_lo, int64_t q, int64_t cbase,
                           bool live, const TcParams& P) {
   int hi = 0, lo = 0;
+  if (P.epi_mode == 1) return (int)(v[0] & 1u) + (int)(v[31] & 1u);
   if (nv == 32) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
@@ -165,7 +170,7 @@ KGE_DEV int tc_scan_chunk(const uint32_t (&v)[32], int nv, float tau_hi, float t
       lo += (j < nv && x >= tau_lo) ? 1 : 0;
     }
   }
-  if (lo != hi) {
+  if (lo != hi && P.epi_mode != 2) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       const float x = __uint_as_float(v[j]);
@@ -183,6 +188,12 @@ KGE_DEV int tc_scan_chunk(const uint32_t (&v)[32], int nv, float tau_hi, float t
   }
   return hi;
 }
+
+// timeline stamps of CTA (0,0) (measurement aid; P.trace is null in normal operation)
+#define TC_STAMP(role, slot)                                                                         \
+  do {                                                                                               \
+    if (P.trace && blockIdx.x == 0 && blockIdx.y == 0 && (slot) < 64) P.trace[(role) * 64 + (slot)] = clock64(); \
+  } while (0)
 
 // ---- the sweep ------------------------------------------------------------------------------------
 // grid (splits, query blocks); CTA = 128 queries x a run of 128-candidate tiles.
@@ -216,6 +227,7 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int64_t q0 = (int64_t)blockIdx.y * kTcBM;
+  if (threadIdx.x == 0) TC_STAMP(2, 63);   // kernel entry of CTA (0,0)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.nstages; ++s) { tc_mbar_init(&full[s], 1); tc_mbar_init(&empty[s], 1); }
@@ -244,10 +256,13 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
         }
       }
       int stage = 0; uint32_t phase = 0;
+      int ev = 0;
+      TC_STAMP(0, ev++);
       for (int t = 0; t < ntl; ++t) {
         const int row = (t0 + t) * kTcBN;
         for (int kb = 0; kb < P.nkb; ++kb) {
           tc_mbar_wait(&empty[stage], phase ^ 1u);
+          TC_STAMP(0, ev++);
           tc_mbar_expect_tx(&full[stage], st_bytes);
           const uint32_t sb = st_base + (uint32_t)stage * st_bytes;
           tc_tma_load_2d(sb, &TM.b0, kb * kTcBK, row, &full[stage]);
@@ -262,16 +277,21 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
     }
   } else if (warp == 1) {
     if (lane == 0) {
+      int ev = 0;
+      TC_STAMP(1, ev++);
       if (P.a_resident) { tc_mbar_wait(a_full, 0u); }
+      TC_STAMP(1, ev++);
       int stage = 0; uint32_t phase = 0;
       for (int t = 0; t < ntl; ++t) {
         const int as = t & 1;
         tc_mbar_wait(&tmem_empty[as], (uint32_t)(((t >> 1) & 1) ^ 1));   // epilogue has drained this accumulator
         tc_fence_after();
+        TC_STAMP(1, ev++);
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * kTcBN);
         for (int kb = 0; kb < P.nkb; ++kb) {
           tc_mbar_wait(&full[stage], phase);
           tc_fence_after();
+          TC_STAMP(1, ev++);
           const uint32_t sb = st_base + (uint32_t)stage * st_bytes;
           const uint32_t b0 = sb, b1 = sb + kTcTileBytes;
           const uint32_t a0 = P.a_resident ? a_base + (uint32_t)kb * 2u * kTcTileBytes : sb + 2u * kTcTileBytes;
@@ -298,10 +318,13 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
     const float tau_hi = live ? __ldg(P.tau + 2 * q) : INFINITY;
     const float tau_lo = live ? __ldg(P.tau + 2 * q + 1) : INFINITY;
     int cnt = 0;
+    int ev = 0;
+    if (warp == 2 && lane == 0) TC_STAMP(2, ev++);
     for (int t = 0; t < ntl; ++t) {
       const int as = t & 1;
       tc_mbar_wait(&tmem_full[as], (uint32_t)((t >> 1) & 1));
       tc_fence_after();
+      if (warp == 2 && lane == 0) TC_STAMP(2, ev++);
       const int64_t cbase = (int64_t)(t0 + t) * kTcBN;
       const int nvalid = (int)min((int64_t)kTcBN, P.nc - cbase);
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * kTcBN);
@@ -323,6 +346,7 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
       tc_fence_before();
       __syncwarp();
       if (lane == 0) tc_mbar_arrive(&tmem_empty[as]);
+      if (warp == 2 && lane == 0) TC_STAMP(2, ev++);
     }
     if (live && cnt) atomicAdd(P.tc_counts + q, cnt);
   }
@@ -389,6 +413,9 @@ tc_prep_cand_kernel(const float* __restrict__ c0, const float* __restrict__ c1, 
   tc_store_tail(o0, o1, KC * dp, Kp, lane, aug != 0, n0, n1, n2);
   if (lane == 0) atomicMax(cmax_bits, __float_as_uint(__double2float_ru(ss)));   // non-negative floats order like their bits
 }
+
+static long long* g_tc_trace = nullptr;   // device buffer [3][64] or null (measurement aid)
+void tc_set_trace(long long* buf) { g_tc_trace = buf; }
 
 // ---- host side ------------------------------------------------------------------------------------
 static inline size_t tc_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -558,6 +585,9 @@ int tc_sweep(const kge_model_t* m, int dir, int64_t Q, int64_t nc, void* tcws, T
   P.tiles_per_cta = (P.ntiles + splits - 1) / splits;
   splits = (P.ntiles + P.tiles_per_cta - 1) / P.tiles_per_cta;
   P.dbg = dbg;
+  P.trace = g_tc_trace;
+  P.epi_mode = 0;
+  if (const char* e = getenv("KGE_TC_EPI_MODE")) P.epi_mode = atoi(e);   // measurement aid: wrong counts unless 0
   TcMaps TM;
   int rc = tc_make_map(&TM.a0, A0, (uint64_t)Q, (uint64_t)Kp); if (rc) return rc;
   rc = tc_make_map(&TM.a1, A1, (uint64_t)Q, (uint64_t)Kp); if (rc) return rc;

@@ -742,6 +742,15 @@ int tiled_sweep(const kge_model_t* m, const kge_model_t* mq, int dir, const int6
   float* qscale = reinterpret_cast<float*>(w + 2 * qvec_bytes + (size_t)dir * qs_bytes);
   float* cscratch = cand_scratch_ptr(m, ws, Q);
 
+  // 0. CP sweeps the object table for tails and the subject table for heads: its tensor-core candidate
+  // operands (and max |c|^2, which the query thresholds read) are per direction and come first
+  if (model == KGE_CP && use_tc) {
+    const float* src[2] = {nullptr, nullptr};
+    const bool scratch = cand_sources(m, dir, src);
+    int rc = tc_prepare_candidates(m, src, nc, tc_ws_ptr(m, ws, Q), Q, scratch ? cscratch : nullptr, st);
+    if (rc) return rc;
+  }
+
   // 1. query vectors (query-side tables)
   const ModelParams PQ = make_params(mq, mq);
   const int vq = model_vec(mq);
@@ -791,10 +800,6 @@ int tiled_sweep(const kge_model_t* m, const kge_model_t* mq, int dir, const int6
       }
     } else {
       P.cand[0] = src[0]; P.cand[1] = src[1]; P.cand_pitch = d;
-    }
-    if (model == KGE_CP && use_tc) {   // CP sweeps the object table for tails, the subject table for heads
-      int rc = tc_prepare_candidates(m, src, nc, tc_ws_ptr(m, ws, Q), Q, scratch ? cscratch : nullptr, st);
-      if (rc) return rc;
     }
   }
 

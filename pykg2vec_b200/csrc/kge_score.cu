@@ -6,6 +6,8 @@
 // of a group cover 128 contiguous bytes of a row per load instruction (one full
 // cache line when the row is line-aligned), and a warp has 4 x (rows per triple)
 // independent row streams in flight.  HBM-bound: rows*d*4 + 28 bytes per triple.
+#include <cstdlib>
+
 #include "kge_models.cuh"
 
 namespace kge {
@@ -91,8 +93,13 @@ extern "C" int kge_score_fwd(const kge_model_t* m, int grouping, const int64_t* 
   // distance models: the register-cache depth is a template parameter picked from the width
   // (TransD gathers six rows per triple: re-reading them from L1 at high occupancy beats caching
   //  the projected operands at <= 128 registers — 0.89 vs 0.78 of HBM peak measured — so CH = 0)
-  const int chsel = (is_distance_model(m->model) && m->model != KGE_TRANSD)
-                        ? ch_select(m->model == KGE_TRANSR ? m->rel_dim : m->dim) : 0;
+  int chsel = (is_distance_model(m->model) && m->model != KGE_TRANSD)
+                  ? ch_select(m->model == KGE_TRANSR ? m->rel_dim : m->dim) : 0;
+  if (const char* e = getenv("KGE_SCORE_CH")) {   // tuning aid (read per call): force the register-cache depth
+    const int v = atoi(e);
+    const int need = (((m->model == KGE_TRANSR ? m->rel_dim : m->dim) + 3) / 4 + 7) / 8;
+    if (is_distance_model(m->model) && (v == 0 || ((v == 2 || v == 4 || v == 8) && v >= need))) chsel = v;
+  }
 #define LAUNCH(M, V, C)                                                                            \
   do {                                                                                             \
     if (smem > 40 * 1024)                                                                          \

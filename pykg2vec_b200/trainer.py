@@ -85,6 +85,8 @@ class Trainer:
         self._dp = None
         if self._world > 1 and self._fused:
             self._dp = getattr(self.config, "dp_mode", None) or self._pick_dp_mode()
+            if self._dp == "off":   # every rank trains on its own (tests: the single-process yardstick)
+                self._dp = None
 
     def _pick_dp_mode(self):
         """'grads' (shard the scoring, all-reduce dense gradients) pays when the rows a local batch touches

@@ -63,6 +63,79 @@ def _worker(rank, world, port, tmp):
     open(os.path.join(tmp, "ok%d" % rank), "w").write("ok")
 
 
+def _dp_worker(rank, world, port, tmp):
+    """data-parallel training (pykg2vec_b200/trainer.py): both exchange modes leave every rank with the same
+    tables, equal (to fp32 rounding) to ONE process stepping on the concatenated global batch."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.dirname(here))
+    sys.path.insert(0, here)
+    import torch.distributed as dist
+    import pykg2vec_b200
+    from pykg2vec_b200 import sharding
+    from pykg2vec_b200.synthetic import SyntheticConfig, SyntheticKnowledgeGraph
+    from pykg2vec_b200.trainer import Trainer
+    torch.cuda.set_device(rank)
+    sharding.init_distributed(backend="nccl")
+    dev = torch.device("cuda", rank)
+    kg = SyntheticKnowledgeGraph(500, 7, 3000, 50, 50, seed=1)
+
+    def make(model_name, opt, mode):
+        cfg = SyntheticConfig(kg, device=dev, optimizer=opt, learning_rate=0.05, hidden_size=64,
+                              margin=6.0 if model_name == "rotate" else 1.0, l1_flag=False, lmbda=0.01,
+                              neg_rate=4 if model_name == "rotate" else 1, alpha=0.5, batch_size=128, dp_mode=mode)
+        torch.manual_seed(0)
+        tr = Trainer(pykg2vec_b200.import_model(model_name)(**cfg.__dict__), cfg)
+        tr.build_model()
+        return tr
+
+    B = 128
+    for model_name, opt in (("transe", "sgd"), ("transe", "adam"), ("distmult", "adam"), ("complex", "adagrad"), ("rotate", "adam")):
+        single = make(model_name, opt, "off")
+        trs = {mode: make(model_name, opt, mode) for mode in ("grads", "ids")}
+        for mode, t_ in trs.items():
+            t_.model.load_state_dict(single.model.state_dict())
+            assert t_._dp == mode and t_._fused and single._dp is None
+        for step in range(3):
+            per_rank = []
+            for rk in range(world):
+                rng = np.random.RandomState(100 * step + rk)
+                if single.model.training_strategy.name == "PAIRWISE_BASED":
+                    nr = single.config.neg_rate
+                    per_rank.append([rng.randint(500, size=B), rng.randint(7, size=B), rng.randint(500, size=B),
+                                     rng.randint(500, size=B * nr), rng.randint(7, size=B * nr), rng.randint(500, size=B * nr)])
+                else:
+                    per_rank.append([rng.randint(500, size=B), rng.randint(7, size=B), rng.randint(500, size=B),
+                                     np.where(np.arange(B) % 2 == 0, 1, -1)])
+            to = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int64)).to(dev)
+            glob = [to(np.concatenate([per_rank[rk][k] for rk in range(world)])) for k in range(len(per_rank[0]))]
+            # (RotatE: the negatives of positive i stay contiguous under this rank-major concatenation)
+            l_single = float(single.train_batch_device(glob).item())
+            for mode, t_ in trs.items():
+                l_dp = float(t_.train_batch_device([to(a) for a in per_rank[rank]]).item())
+                assert abs(l_dp - l_single) <= 2e-4 * max(abs(l_single), 1e-6), (model_name, opt, mode, step, l_dp, l_single)
+        for mode, t_ in trs.items():
+            for (ka, va), (kb, vb) in zip(t_.model.state_dict().items(), single.model.state_dict().items()):
+                np.testing.assert_allclose(va.cpu().numpy(), vb.cpu().numpy(), rtol=0, atol=3e-5, err_msg="%s %s %s %s" % (model_name, opt, mode, ka))
+                # replicas stay bit-identical to each other
+                other = va.clone()
+                dist.broadcast(other, src=0)
+                assert torch.equal(other, va), (model_name, opt, mode, ka)
+    dist.barrier()
+    dist.destroy_process_group()
+    open(os.path.join(tmp, "dp_ok%d" % rank), "w").write("ok")
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_data_parallel_training_nccl(tmp_path):
+    world = 2
+    mp.start_processes(_dp_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True,
+                       start_method="spawn")
+    assert all(os.path.exists(os.path.join(str(tmp_path), "dp_ok%d" % r)) for r in range(world))
+
+
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_row_sharded_and_query_sharded_eval_nccl(tmp_path):
     world = 2

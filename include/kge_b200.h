@@ -160,6 +160,17 @@ int kge_train_pairwise_hinge_sgd(const kge_model_t* m, float* const* tables_rw,
                                  const int64_t* neg_h, const int64_t* neg_r, const int64_t* neg_t,
                                  int64_t n, float margin, float lr, float* loss_out, void* stream);
 
+/* kge_train_pointwise_logistic: Trainer.train_step_pointwise (trainer.py:176-180) minus the regulariser,
+ * for the pointwise row models (DistMult, Complex(N3), CP, SimplE(_ignr), ANALOGY, QuatE, OctonionE):
+ * preds = model(h, r, t); loss = Criterion.pointwise_logistic(preds, y) = mean softplus(y * preds)
+ * (criterion.py:32-34); backward — in ONE kernel, since d loss / d score_i depends on score_i alone.
+ * y: int64 +1 / -1 labels as the generator yields them (generator.py:125-156).  loss_out[0] receives the
+ * batch loss; the row gradients are ACCUMULATED into the dense grad_scratch[k] buffers (shaped like
+ * tables[k]; follow with kge_reg_fwd_bwd and kge_optim_apply_rows / _dense). */
+int kge_train_pointwise_logistic(const kge_model_t* m, float* const* grad_scratch, const int64_t* h,
+                                 const int64_t* r, const int64_t* t, const int64_t* y, int64_t n,
+                                 float* loss_out, void* stream);
+
 /* Sparse optimizer.step() for the rows touched by the triples (h[i], r[i], t[i]):
  * takes the accumulated row gradients out of grad_scratch (as filled by
  * kge_score_bwd / kge_reg_fwd_bwd; left zero-filled) and applies

@@ -27,7 +27,7 @@ EXPORTS = [
     "kge_abi_version", "kge_version", "kge_last_error", "kge_launch_count",
     "kge_score_fwd", "kge_score_bwd", "kge_normalize_rows",
     "kge_loss_pairwise_hinge", "kge_loss_pointwise_logistic", "kge_loss_selfadv", "kge_reg_fwd_bwd",
-    "kge_train_pairwise_hinge_sgd", "kge_optim_apply_rows", "kge_optim_apply_dense",
+    "kge_train_pairwise_hinge_sgd", "kge_train_pointwise_logistic", "kge_optim_apply_rows", "kge_optim_apply_dense",
     "kge_rank_workspace_bytes", "kge_rank_1vsall", "kge_rank_tc_probe", "kge_rank_last_sweep_ms", "kge_debug_set_tc_trace",
     "kge_tripleset_capacity", "kge_tripleset_build", "kge_sample_negatives",
     "kge_proj_tail_fwd", "kge_proj_tail_bwd", "kge_proj_bce", "kge_proj_rank_workspace_bytes", "kge_proj_rank", "kge_proj_labels",
@@ -221,6 +221,19 @@ def train_pairwise_hinge_sgd(desc, grad_scratch, ph, pr, pt, nh, nr, nt, margin,
                                              _ptr(nr), _ptr(nt), ctypes.c_int64(ph.numel()),
                                              ctypes.c_float(margin), ctypes.c_float(lr), _ptr(loss_out),
                                              _stream()), "kge_train_pairwise_hinge_sgd")
+    return loss_out
+
+
+def train_pointwise_logistic(desc, grad_scratch, h, r, t, y, loss_out=None):
+    """forward + Criterion.pointwise_logistic + backward of a pointwise batch in one kernel: returns the loss
+    [1]; row gradients are accumulated into grad_scratch (dense buffers shaped like the tables)."""
+    if loss_out is None:
+        loss_out = torch.empty(1, dtype=torch.float32, device=h.device)
+    m = desc.c_struct()
+    gs = _table_ptr_array(grad_scratch)
+    check(lib().kge_train_pointwise_logistic(ctypes.byref(m), gs, _ptr(_dev_i64(h, "h")), _ptr(_dev_i64(r, "r")),
+                                             _ptr(_dev_i64(t, "t")), _ptr(_dev_i64(y, "y")), ctypes.c_int64(h.numel()),
+                                             _ptr(loss_out), _stream()), "kge_train_pointwise_logistic")
     return loss_out
 
 

@@ -62,8 +62,12 @@ struct TcParams {
   float* dbg;              // optional [Q][nc] raw accumulators (tests)
   long long* trace;        // optional timeline of CTA (0,0): [3 roles][64] clock64 stamps (kge_debug_set_tc_trace)
   int epi_mode;            // measurement aid (KGE_TC_EPI_MODE): 0 normal, 1 load only, 2 count only (no band listing)
+  // exact-width last k-block: when Kp leaves 16 or 32 columns for it, it is staged as a narrow tile
+  // (32- / 64-byte rows, matching swizzle) instead of a zero-filled 128-byte one; 0 = treat it like the others
+  int tail_cols;
+  uint32_t tail_bytes;     // bytes of one operand's tail tile (128 rows x tail_cols x 2)
 };
-struct TcMaps { CUtensorMap a0, a1, b0, b1; };
+struct TcMaps { CUtensorMap a0, a1, b0, b1, a0t, a1t, b0t, b1t; };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 KGE_DEV uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -115,13 +119,16 @@ KGE_DEV void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t id
 // 128-byte swizzle.  start address >> 4 in bits [0,14); leading byte offset (unused for swizzled
 // K-major, canonical value 1) in [16,30); stride byte offset = 8 rows x 128 B = 1024 (>> 4) in
 // [32,46); descriptor version 1 in [46,48); layout type SWIZZLE_128B = 2 in [61,64).
-KGE_DEV uint64_t tc_smem_desc(uint32_t addr) {
+// row_bytes = 128 (SWIZZLE_128B, layout 2), 64 (SWIZZLE_64B, 4) or 32 (SWIZZLE_32B, 6); the stride between
+// 8-row groups is 8 * row_bytes.
+KGE_DEV uint64_t tc_smem_desc(uint32_t addr, uint32_t row_bytes = 128u) {
+  const uint64_t layout = row_bytes == 128u ? 2u : (row_bytes == 64u ? 4u : 6u);
   uint64_t d = 0;
   d |= (uint64_t)((addr >> 4) & 0x3FFF);
   d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)((8u * row_bytes) >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= layout << 61;
   return d;
 }
 // instruction descriptor (kind::f16): D fp32 (bits [4,6) = 1), A and B bf16 ([7,10) = [10,13) = 1),
@@ -147,39 +154,78 @@ KGE_DEV uint32_t tc_tmem_ld1(uint32_t taddr) {
 }
 KGE_DEV void tc_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// Pair-list slots are handed out per WARP in blocks reserved with one global atomic (a returning atomic
+// per ambiguous pair stalled the whole epilogue: 8k of 10k cycles per tile, profiles/r2_tc_trace_v2_*):
+// base/size = the warp's current block in P.list, used = slots already written.  Unused slots of a block
+// are filled with the sentinel ~0 (band_resolve_kernel skips them), so [0, ctrl[0]) is always fully defined.
+struct TcListState { unsigned base, used, size; };
+constexpr unsigned long long kTcListHole = ~0ull;
+constexpr unsigned kTcListBlock = 64;
+
+KGE_DEV void tc_list_pad(TcListState& L, const TcParams& P, int lane) {
+  for (unsigned i = L.used + (unsigned)lane; i < L.size; i += 32u)
+    if (L.base + i < P.cap) P.list[L.base + i] = kTcListHole;
+  L.used = L.size;
+}
+
 // 32 accumulator columns (= candidates cbase .. cbase+31) of this thread's query row: count the
-// certainly-better ones; rows with candidates inside the band list them — from the registers already
-// loaded (statically indexed: nothing spills), a thread-divergent but short path taken by ~1 % of the
-// (thread, chunk) pairs.
+// certainly-better ones (2 compares + 2 predicated adds per column, two independent chains); warps in
+// which some row has candidates inside its band list them from the registers already loaded — a
+// warp-level exclusive scan assigns the slots, no atomic on the path.
 KGE_DEV int tc_scan_chunk(const uint32_t (&v)[32], int nv, float tau_hi, float tau_lo, int64_t q, int64_t cbase,
-                          bool live, const TcParams& P) {
-  int hi = 0, lo = 0;
+                          bool live, const TcParams& P, TcListState& L, int lane) {
   if (P.epi_mode == 1) return (int)(v[0] & 1u) + (int)(v[31] & 1u);
+  int hi0 = 0, hi1 = 0, lo0 = 0, lo1 = 0;
+#define TC_CMP(HI, LO, X)                                                                                 \
+  asm("{\n\t.reg .pred p, q;\n\tsetp.gt.f32 p, %2, %3;\n\tsetp.ge.f32 q, %2, %4;\n\t"                   \
+      "@p add.s32 %0, %0, 1;\n\t@q add.s32 %1, %1, 1;\n\t}"                                               \
+      : "+r"(HI), "+r"(LO) : "f"(X), "f"(tau_hi), "f"(tau_lo))
   if (nv == 32) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float x = __uint_as_float(v[j]);
-      hi += (x > tau_hi) ? 1 : 0;
-      lo += (x >= tau_lo) ? 1 : 0;
+    for (int j = 0; j < 32; j += 2) {
+      TC_CMP(hi0, lo0, __uint_as_float(v[j]));
+      TC_CMP(hi1, lo1, __uint_as_float(v[j + 1]));
     }
   } else {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float x = __uint_as_float(v[j]);
-      hi += (j < nv && x > tau_hi) ? 1 : 0;
-      lo += (j < nv && x >= tau_lo) ? 1 : 0;
-    }
+    for (int j = 0; j < 32; ++j)
+      if (j < nv) TC_CMP(hi0, lo0, __uint_as_float(v[j]));
   }
-  if (lo != hi && P.epi_mode != 2) {
+#undef TC_CMP
+  const int hi = hi0 + hi1;
+  const int na = (lo0 + lo1) - hi;   // this row's candidates inside the band
+  if (P.epi_mode != 2 && __any_sync(0xffffffffu, na != 0)) {
+    int incl = na;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float x = __uint_as_float(v[j]);
-      if (j < nv && x >= tau_lo && !(x > tau_hi)) {
-        const unsigned idx = atomicAdd(&P.ctrl[0], 1u);
-        if (idx < P.cap) P.list[idx] = ((unsigned long long)q << 32) | (unsigned long long)(cbase + j);
-        else P.ctrl[1] = 1u;
+    for (int off = 1; off < 32; off <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += t;
+    }
+    const unsigned total = (unsigned)__shfl_sync(0xffffffffu, incl, 31);
+    if (L.used + total > L.size) {   // next block (rare: once per ~64 listed pairs)
+      tc_list_pad(L, P, lane);
+      const unsigned need = total > kTcListBlock ? total : kTcListBlock;
+      unsigned b = 0;
+      if (lane == 0) {
+        b = atomicAdd(&P.ctrl[0], need);
+        if (b + need > P.cap) P.ctrl[1] = 1u;   // overflow: the exact fp32 sweep takes over (writes below are bounded)
+      }
+      L.base = __shfl_sync(0xffffffffu, b, 0);
+      L.used = 0u;
+      L.size = need;
+    }
+    if (na != 0) {
+      unsigned k = L.base + L.used + (unsigned)(incl - na);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float x = __uint_as_float(v[j]);
+        if (j < nv && x >= tau_lo && !(x > tau_hi)) {
+          if (k < P.cap) P.list[k] = ((unsigned long long)q << 32) | (unsigned long long)(cbase + j);
+          ++k;
+        }
       }
     }
+    L.used += total;
   }
   if (P.dbg && live) {
 #pragma unroll
@@ -220,7 +266,8 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
   uint64_t* const tmem_empty = tmem_full + 2;                   // [2]
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(gbase + 512);
   const uint32_t a_base = base + 1024u;                                            // resident query k-blocks
-  const uint32_t a_bytes = P.a_resident ? (uint32_t)P.nkb * 2u * kTcTileBytes : 0u;
+  const uint32_t a_bytes = !P.a_resident ? 0u
+      : (P.tail_cols ? (uint32_t)(P.nkb - 1) * 2u * kTcTileBytes + 2u * P.tail_bytes : (uint32_t)P.nkb * 2u * kTcTileBytes);
   const uint32_t st_base = a_base + a_bytes;
   const uint32_t st_bytes = (P.a_resident ? 2u : 4u) * kTcTileBytes;              // [B0][B1]([A0][A1])
 
@@ -251,8 +298,11 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
       if (P.a_resident) {
         tc_mbar_expect_tx(a_full, a_bytes);
         for (int kb = 0; kb < P.nkb; ++kb) {
-          tc_tma_load_2d(a_base + (uint32_t)kb * 2u * kTcTileBytes, &TM.a0, kb * kTcBK, (int)q0, a_full);
-          tc_tma_load_2d(a_base + (uint32_t)kb * 2u * kTcTileBytes + kTcTileBytes, &TM.a1, kb * kTcBK, (int)q0, a_full);
+          const bool tail = P.tail_cols && kb == P.nkb - 1;
+          const uint32_t tb = tail ? P.tail_bytes : kTcTileBytes;
+          const uint32_t dst = a_base + (uint32_t)kb * 2u * kTcTileBytes;
+          tc_tma_load_2d(dst, tail ? &TM.a0t : &TM.a0, kb * kTcBK, (int)q0, a_full);
+          tc_tma_load_2d(dst + tb, tail ? &TM.a1t : &TM.a1, kb * kTcBK, (int)q0, a_full);
         }
       }
       int stage = 0; uint32_t phase = 0;
@@ -261,15 +311,17 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
       for (int t = 0; t < ntl; ++t) {
         const int row = (t0 + t) * kTcBN;
         for (int kb = 0; kb < P.nkb; ++kb) {
+          const bool tail = P.tail_cols && kb == P.nkb - 1;
+          const uint32_t tb = tail ? P.tail_bytes : kTcTileBytes;
           tc_mbar_wait(&empty[stage], phase ^ 1u);
           TC_STAMP(0, ev++);
-          tc_mbar_expect_tx(&full[stage], st_bytes);
+          tc_mbar_expect_tx(&full[stage], (P.a_resident ? 2u : 4u) * tb);
           const uint32_t sb = st_base + (uint32_t)stage * st_bytes;
-          tc_tma_load_2d(sb, &TM.b0, kb * kTcBK, row, &full[stage]);
-          tc_tma_load_2d(sb + kTcTileBytes, &TM.b1, kb * kTcBK, row, &full[stage]);
+          tc_tma_load_2d(sb, tail ? &TM.b0t : &TM.b0, kb * kTcBK, row, &full[stage]);
+          tc_tma_load_2d(sb + tb, tail ? &TM.b1t : &TM.b1, kb * kTcBK, row, &full[stage]);
           if (!P.a_resident) {
-            tc_tma_load_2d(sb + 2u * kTcTileBytes, &TM.a0, kb * kTcBK, (int)q0, &full[stage]);
-            tc_tma_load_2d(sb + 3u * kTcTileBytes, &TM.a1, kb * kTcBK, (int)q0, &full[stage]);
+            tc_tma_load_2d(sb + 2u * tb, tail ? &TM.a0t : &TM.a0, kb * kTcBK, (int)q0, &full[stage]);
+            tc_tma_load_2d(sb + 3u * tb, tail ? &TM.a1t : &TM.a1, kb * kTcBK, (int)q0, &full[stage]);
           }
           if (++stage == P.nstages) { stage = 0; phase ^= 1u; }
         }
@@ -292,12 +344,16 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
           tc_mbar_wait(&full[stage], phase);
           tc_fence_after();
           TC_STAMP(1, ev++);
+          const bool tail = P.tail_cols && kb == P.nkb - 1;
+          const uint32_t tb = tail ? P.tail_bytes : kTcTileBytes;
+          const uint32_t rowb = tail ? (uint32_t)P.tail_cols * 2u : 128u;   // bytes per smem row = swizzle span
           const uint32_t sb = st_base + (uint32_t)stage * st_bytes;
-          const uint32_t b0 = sb, b1 = sb + kTcTileBytes;
-          const uint32_t a0 = P.a_resident ? a_base + (uint32_t)kb * 2u * kTcTileBytes : sb + 2u * kTcTileBytes;
-          const uint32_t a1 = a0 + kTcTileBytes;
-          const int nks = min(kTcBK / 16, (P.Kp - kb * kTcBK + 15) / 16);
-          const uint64_t da0 = tc_smem_desc(a0), da1 = tc_smem_desc(a1), db0 = tc_smem_desc(b0), db1 = tc_smem_desc(b1);
+          const uint32_t b0 = sb, b1 = sb + tb;
+          const uint32_t a0 = P.a_resident ? a_base + (uint32_t)kb * 2u * kTcTileBytes : sb + 2u * tb;
+          const uint32_t a1 = a0 + tb;
+          const int nks = tail ? P.tail_cols / 16 : min(kTcBK / 16, (P.Kp - kb * kTcBK + 15) / 16);
+          const uint64_t da0 = tc_smem_desc(a0, rowb), da1 = tc_smem_desc(a1, rowb), db0 = tc_smem_desc(b0, rowb),
+                         db1 = tc_smem_desc(b1, rowb);
           for (int k = 0; k < nks; ++k) {   // 16 bf16 = 32 bytes further along the swizzled row: +2 in the address field
             const uint64_t ko = (uint64_t)(2 * k);
             tc_mma(d_tmem, da0 + ko, db0 + ko, kTcIdesc, (kb | k) != 0 ? 1u : 0u);
@@ -318,6 +374,7 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
     const float tau_hi = live ? __ldg(P.tau + 2 * q) : INFINITY;
     const float tau_lo = live ? __ldg(P.tau + 2 * q + 1) : INFINITY;
     int cnt = 0;
+    TcListState L = {0u, 0u, 0u};
     int ev = 0;
     if (warp == 2 && lane == 0) TC_STAMP(2, ev++);
     for (int t = 0; t < ntl; ++t) {
@@ -336,11 +393,11 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
       for (int cb = 0; cb < nchunks; cb += 2) {
         tc_tmem_wait_ld();
         if (cb + 1 < nchunks) tc_tmem_ld32(taddr + (uint32_t)((cb + 1) * 32), vb);
-        cnt += tc_scan_chunk(va, min(32, nvalid - cb * 32), tau_hi, tau_lo, q, cbase + cb * 32, live, P);
+        cnt += tc_scan_chunk(va, min(32, nvalid - cb * 32), tau_hi, tau_lo, q, cbase + cb * 32, live, P, L, lane);
         if (cb + 1 < nchunks) {
           tc_tmem_wait_ld();
           if (cb + 2 < nchunks) tc_tmem_ld32(taddr + (uint32_t)((cb + 2) * 32), va);
-          cnt += tc_scan_chunk(vb, min(32, nvalid - (cb + 1) * 32), tau_hi, tau_lo, q, cbase + (cb + 1) * 32, live, P);
+          cnt += tc_scan_chunk(vb, min(32, nvalid - (cb + 1) * 32), tau_hi, tau_lo, q, cbase + (cb + 1) * 32, live, P, L, lane);
         }
       }
       tc_fence_before();
@@ -348,6 +405,7 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
       if (lane == 0) tc_mbar_arrive(&tmem_empty[as]);
       if (warp == 2 && lane == 0) TC_STAMP(2, ev++);
     }
+    tc_list_pad(L, P, lane);   // the unused slots of the warp's last block become holes
     if (live && cnt) atomicAdd(P.tc_counts + q, cnt);
   }
   tc_fence_before();
@@ -486,15 +544,18 @@ static TcEncodeFn tc_encode_fn() {
   return fn;
 }
 // bf16 matrix [rows][Kp] row-major; box = {64 columns (128 bytes), 128 rows}, 128-byte swizzle, zero fill
-static int tc_make_map(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t Kp) {
+// (box_cols = 64: one 128-byte swizzle row; 32 / 16: the narrow tile of an exact-width last k-block)
+static int tc_make_map(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t Kp, int box_cols = kTcBK) {
   TcEncodeFn fn = tc_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled is not available"); return KGE_ECUDA; }
   const cuuint64_t gdim[2] = {Kp, rows};
   const cuuint64_t gstride[1] = {Kp * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)kTcBK, (cuuint32_t)kTcBN};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)kTcBN};
   const cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                              : (box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (bf16) failed (%d)", (int)r); return KGE_ECUDA; }
   return KGE_OK;
@@ -570,8 +631,15 @@ int tc_sweep(const kge_model_t* m, int dir, int64_t Q, int64_t nc, void* tcws, T
   P.tau = tau; P.tc_counts = cnt; P.ctrl = ctrl; P.list = list; P.cap = tc_list_capacity(Q);
   P.Q = Q; P.nc = nc; P.Kp = Kp; P.nkb = (Kp + kTcBK - 1) / kTcBK;
   P.a_resident = P.nkb <= kTcResidentMaxKb ? 1 : 0;
+  {
+    const int last = Kp - kTcBK * (P.nkb - 1);   // columns of the last k-block: 16, 32, 48 or 64
+    P.tail_cols = (last == 16 || last == 32) ? last : 0;
+    if (const char* e = getenv("KGE_TC_TAIL")) { if (atoi(e) == 0) P.tail_cols = 0; }   // tuning / test aid
+    P.tail_bytes = (uint32_t)(kTcBN * P.tail_cols * 2);
+  }
   const size_t budget = 227 * 1024 - 2048;   // control block + alignment slack
-  const size_t a_bytes = P.a_resident ? (size_t)P.nkb * 2 * kTcTileBytes : 0;
+  const size_t a_bytes = !P.a_resident ? 0
+      : (P.tail_cols ? (size_t)(P.nkb - 1) * 2 * kTcTileBytes + 2 * (size_t)P.tail_bytes : (size_t)P.nkb * 2 * kTcTileBytes);
   const size_t st_bytes = (P.a_resident ? 2 : 4) * (size_t)kTcTileBytes;
   int nstages = (int)((budget - a_bytes) / st_bytes);
   if (nstages > kTcMaxStages) nstages = kTcMaxStages;
@@ -593,6 +661,13 @@ int tc_sweep(const kge_model_t* m, int dir, int64_t Q, int64_t nc, void* tcws, T
   rc = tc_make_map(&TM.a1, A1, (uint64_t)Q, (uint64_t)Kp); if (rc) return rc;
   rc = tc_make_map(&TM.b0, w + L.b[0], (uint64_t)nc, (uint64_t)Kp); if (rc) return rc;
   rc = tc_make_map(&TM.b1, w + L.b[1], (uint64_t)nc, (uint64_t)Kp); if (rc) return rc;
+  TM.a0t = TM.a0; TM.a1t = TM.a1; TM.b0t = TM.b0; TM.b1t = TM.b1;
+  if (P.tail_cols) {
+    rc = tc_make_map(&TM.a0t, A0, (uint64_t)Q, (uint64_t)Kp, P.tail_cols); if (rc) return rc;
+    rc = tc_make_map(&TM.a1t, A1, (uint64_t)Q, (uint64_t)Kp, P.tail_cols); if (rc) return rc;
+    rc = tc_make_map(&TM.b0t, w + L.b[0], (uint64_t)nc, (uint64_t)Kp, P.tail_cols); if (rc) return rc;
+    rc = tc_make_map(&TM.b1t, w + L.b[1], (uint64_t)nc, (uint64_t)Kp, P.tail_cols); if (rc) return rc;
+  }
   const size_t smem = 2048 + a_bytes + (size_t)nstages * st_bytes;
   KGE_CUDA_OK(cudaFuncSetAttribute(tc_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   SweepProfile* sp = sweep_profile(dir);

@@ -66,6 +66,52 @@ train_hinge_kernel(ModelParams P, GradTablesT GT, const int64_t* __restrict__ ph
   }
 }
 
+// Pointwise models (Trainer.train_step_pointwise, trainer.py:176-180, with Criterion.pointwise_logistic,
+// criterion.py:32-34): the loss gradient of a triple depends on its own score only,
+//   d/ds_i mean_j softplus(y_j s_j) = y_i sigmoid(y_i s_i) / n ,
+// so forward, loss and backward are ONE kernel: the group scores its triple, adds softplus(y s)/n to the
+// batch loss and scatters y sigmoid(y s)/n * d s / d rows into the dense gradient scratch.
+__device__ __forceinline__ float tl_softplus(float x) { return x > 20.f ? x : log1pf(expf(x)); }   // F.softplus, threshold 20
+__device__ __forceinline__ float tl_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
+
+template <int MODEL, int VEC>
+__global__ void __launch_bounds__(kThreads)
+train_logistic_kernel(ModelParams P, GradTablesT GT, const int64_t* __restrict__ h, const int64_t* __restrict__ r,
+                      const int64_t* __restrict__ t, const int64_t* __restrict__ y, int64_t n,
+                      float* __restrict__ loss, int scratch_floats) {
+  extern __shared__ float4 smem_f4[];
+  __shared__ float red[kThreads / 32];
+  float* scratch = reinterpret_cast<float*>(smem_f4) + (size_t)(threadIdx.x >> 3) * scratch_floats;
+  const int lane = threadIdx.x & 7;
+  const int64_t g = (int64_t)blockIdx.x * kGroupsPerCta + (threadIdx.x >> 3);
+  const float inv_n = 1.f / (float)n;
+  float v = 0.f;
+  if (g < n) {
+    const int64_t a = __ldg(h + g), b = __ldg(r + g), c = __ldg(t + g);
+    const float yy = (float)__ldg(y + g);
+    TripleRows R;
+    resolve_rows<MODEL>(R, P, P.tab, P.tab, P.tab, a, b, c);
+    const float s = score_group<MODEL, VEC, KGE_GROUP_TAIL>(R, P, lane, scratch);
+    const float x = yy * s;
+    v = tl_softplus(x) * inv_n;
+    const float gs = (x > 20.f ? 1.f : tl_sigmoid(x)) * yy * inv_n;
+    GradRows G;
+    resolve_grad_rows<MODEL>(G, P, GT.t, a, b, c);
+    grad_group<MODEL, VEC>(R, G, P, lane, gs, scratch);
+    if (lane != 0) v = 0.f;
+  }
+#pragma unroll
+  for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) sum += red[w];
+    if (sum != 0.f) atomicAdd(loss, sum);
+  }
+}
+
 // ---- sparse optimizer application ---------------------------------------------
 constexpr int kMaxTasks = 48;
 struct ApplyTasks {
@@ -380,5 +426,57 @@ extern "C" int kge_optim_apply_dense(float* w, float* grad, float* state1, float
   else
     apply_dense_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(w, grad, state1, state2, n4, n, lr, eps, beta1, beta2, step_size, bc2_sqrt);
   KGE_CHECK_LAUNCH("apply_dense_kernel");
+  return KGE_OK;
+}
+
+extern "C" int kge_train_pointwise_logistic(const kge_model_t* m, float* const* grad_scratch, const int64_t* h,
+                                            const int64_t* r, const int64_t* t, const int64_t* y, int64_t n,
+                                            float* loss_out, void* stream) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  if (n <= 0 || !grad_scratch || !h || !r || !t || !y || !loss_out) {
+    set_error("kge_train_pointwise_logistic: bad arguments"); return KGE_EINVAL;
+  }
+  switch (m->model) {   // the pointwise (logistic) row models of pointwise.py
+    case KGE_DISTMULT: case KGE_COMPLEX: case KGE_CP: case KGE_SIMPLE: case KGE_SIMPLE_IGNR: case KGE_ANALOGY:
+    case KGE_QUATE: case KGE_OCTONIONE: break;
+    default: set_error("kge_train_pointwise_logistic: model %d is not a pointwise row model", (int)m->model); return KGE_ENOTSUP;
+  }
+  const int nt = num_tables(m->model);
+  const ModelParams P = make_params(m, nullptr);
+  GradTablesT GT;
+  int vec = model_vec(m);
+  for (int k = 0; k < KGE_MAX_TABLES; ++k) {
+    GT.t[k] = (k < nt) ? grad_scratch[k] : nullptr;
+    if (GT.t[k]) {
+      const uintptr_t a = (uintptr_t)GT.t[k];
+      if (vec == 4 && (a & 15)) vec = 2;
+      if (vec == 2 && (a & 7)) vec = 1;
+    }
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  KGE_CUDA_OK(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
+  const int sf = (int)group_scratch_floats_bwd(m);
+  const size_t smem = (size_t)sf * kGroupsPerCta * sizeof(float);
+  const unsigned grid = (unsigned)((n + kGroupsPerCta - 1) / kGroupsPerCta);
+#define CALL_TL(M, V)                                                                            \
+  do {                                                                                           \
+    if (smem > 40 * 1024)                                                                        \
+      KGE_CUDA_OK(cudaFuncSetAttribute(train_logistic_kernel<M, V>,                              \
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    train_logistic_kernel<M, V><<<grid, kThreads, smem, st>>>(P, GT, h, r, t, y, n, loss_out, sf); \
+  } while (0)
+  switch (m->model) {
+    case KGE_DISTMULT: KGE_DISPATCH_VEC(KGE_DISTMULT, vec, CALL_TL); break;
+    case KGE_COMPLEX: KGE_DISPATCH_VEC(KGE_COMPLEX, vec, CALL_TL); break;
+    case KGE_CP: KGE_DISPATCH_VEC(KGE_CP, vec, CALL_TL); break;
+    case KGE_SIMPLE: KGE_DISPATCH_VEC(KGE_SIMPLE, vec, CALL_TL); break;
+    case KGE_SIMPLE_IGNR: KGE_DISPATCH_VEC(KGE_SIMPLE_IGNR, vec, CALL_TL); break;
+    case KGE_ANALOGY: KGE_DISPATCH_VEC(KGE_ANALOGY, vec, CALL_TL); break;
+    case KGE_QUATE: KGE_DISPATCH_VEC(KGE_QUATE, vec, CALL_TL); break;
+    default: KGE_DISPATCH_VEC(KGE_OCTONIONE, vec, CALL_TL); break;
+  }
+#undef CALL_TL
+  KGE_CHECK_LAUNCH("train_logistic_kernel");
   return KGE_OK;
 }

@@ -215,9 +215,12 @@ class Trainer:
         desc = self.model.kge_desc()
         h, r, t, y = ids
         lr = float(self.config.learning_rate)
-        preds = _lib.score_fwd(desc, h, r, t)
-        loss, g = _lib.loss_pointwise_logistic(preds, y.to(torch.float32))
-        _lib.score_bwd(desc, h, r, t, g, self._grad_scratch)
+        if y.dtype == torch.int64 and y.is_contiguous():   # forward + logistic loss + backward in ONE kernel
+            loss = _lib.train_pointwise_logistic(desc, self._grad_scratch, h, r, t, y)
+        else:
+            preds = _lib.score_fwd(desc, h, r, t)
+            loss, g = _lib.loss_pointwise_logistic(preds, y.to(torch.float32))
+            _lib.score_bwd(desc, h, r, t, g, self._grad_scratch)
         hook = self.model.kge_fused_reg()
         if hook is not None:
             reg = _lib.reg_fwd_bwd(desc, hook[0], hook[1], h, r, t, grad_scale=1.0, grad_tables=self._grad_scratch)

@@ -226,9 +226,10 @@ def test_degenerate_table_overflows_to_the_exact_sweep():
 
 @pytest.mark.parametrize("model,N,d,Q", [("transe", 1024, 200, 130), ("distmult", 1100, 36, 257), ("complex", 1500, 52, 64),
                                          ("rotate", 2049, 200, 129), ("cp", 1300, 40, 100), ("rescal", 1200, 24, 77)])
-def test_tensor_core_sweep_ragged_geometries(model, N, d, Q):
+def test_tensor_core_sweep_ragged_geometries(model, N, d, Q, monkeypatch):
     """tile / query-block / k-block raggedness of the tensor-core sweep: N not a multiple of 128, Q not a
-    multiple of 128, K not a multiple of 64 (and of 16), the streamed-query mode (K > 256)."""
+    multiple of 128, K not a multiple of 64 (and of 16), the streamed-query mode (K > 256), the last
+    k-block as a narrow (32- / 64-byte swizzle) tile or as a zero-filled full one (KGE_TC_TAIL=0)."""
     import oracle
     L = _lib()
     om, _ = gpu.synthetic_case(model, N, 5, d, seed=N + d, margin=6.0 if model == "rotate" else 0.0)
@@ -241,10 +242,11 @@ def test_tensor_core_sweep_ragged_geometries(model, N, d, Q):
             L.normalize_rows(t)
         om = oracle.Model("rescal", [t.cpu().numpy() for t in desc.tables], d)
     want = oracle.rank_1vsall(om, qh, qr, qt, ft, fh)
-    for flags in (0, L.RANK_NO_TC, 8):
+    for flags, tail in ((0, "1"), (0, "0"), (L.RANK_NO_TC, "1"), (8, "1")):
+        monkeypatch.setenv("KGE_TC_TAIL", tail)
         got = L.rank_1vsall(desc, _cuda(qh), _cuda(qr), _cuda(qt), (_cuda(ft[0]), _cuda(ft[1])),
                             (_cuda(fh[0]), _cuda(fh[1])), flags=flags).cpu().numpy()
-        np.testing.assert_array_equal(got, want, err_msg="flags %d" % flags)
+        np.testing.assert_array_equal(got, want, err_msg="flags %d tail %s" % (flags, tail))
 
 
 def test_config5_row_shards_on_one_gpu():

@@ -17,6 +17,15 @@ except Exception:  # standalone (e.g. the GPU box)
         PAIRWISE_BASED = "pairwise_based"      # translational distance models
         POINTWISE_BASED = "pointwise_based"    # semantic matching models
 
+        # If pykg2vec becomes importable only AFTER this module was loaded, its Trainer / Generator compare
+        # `model.training_strategy == pykg2vec.common.TrainingStrategy.X` (trainer.py:274-296,
+        # generator.py:300-308): members of the two enums with the same value must then compare equal.
+        def __eq__(self, other):
+            return isinstance(other, Enum) and type(other).__name__ == "TrainingStrategy" and other.value == self.value
+
+        def __hash__(self):
+            return hash(self.value)
+
 
 class Model:
     """Meta class of KGE models (KGMeta.py:14-38)."""

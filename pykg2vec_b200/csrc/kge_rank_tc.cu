@@ -154,6 +154,12 @@ KGE_DEV uint32_t tc_tmem_ld1(uint32_t taddr) {
 }
 KGE_DEV void tc_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// timeline stamps of CTA (0,0) (measurement aid; P.trace is null in normal operation)
+#define TC_STAMP(role, slot)                                                                         \
+  do {                                                                                               \
+    if (P.trace && blockIdx.x == 0 && blockIdx.y == 0 && (slot) < 64) P.trace[(role) * 64 + (slot)] = clock64(); \
+  } while (0)
+
 // Pair-list slots are handed out per WARP in blocks reserved with one global atomic (a returning atomic
 // per ambiguous pair stalled the whole epilogue: 8k of 10k cycles per tile, profiles/r2_tc_trace_v2_*):
 // base/size = the warp's current block in P.list, used = slots already written.  Unused slots of a block
@@ -173,8 +179,9 @@ KGE_DEV void tc_list_pad(TcListState& L, const TcParams& P, int lane) {
 // which some row has candidates inside its band list them from the registers already loaded — a
 // warp-level exclusive scan assigns the slots, no atomic on the path.
 KGE_DEV int tc_scan_chunk(const uint32_t (&v)[32], int nv, float tau_hi, float tau_lo, int64_t q, int64_t cbase,
-                          bool live, const TcParams& P, TcListState& L, int lane) {
+                          bool live, const TcParams& P, TcListState& L, int lane, int& ev, bool stamp) {
   if (P.epi_mode == 1) return (int)(v[0] & 1u) + (int)(v[31] & 1u);
+  if (stamp) TC_STAMP(2, ev++);
   int hi0 = 0, hi1 = 0, lo0 = 0, lo1 = 0;
 #define TC_CMP(HI, LO, X)                                                                                 \
   asm("{\n\t.reg .pred p, q;\n\tsetp.gt.f32 p, %2, %3;\n\tsetp.ge.f32 q, %2, %4;\n\t"                   \
@@ -194,6 +201,7 @@ KGE_DEV int tc_scan_chunk(const uint32_t (&v)[32], int nv, float tau_hi, float t
 #undef TC_CMP
   const int hi = hi0 + hi1;
   const int na = (lo0 + lo1) - hi;   // this row's candidates inside the band
+  if (stamp) TC_STAMP(2, ev++);
   if (P.epi_mode != 2 && __any_sync(0xffffffffu, na != 0)) {
     int incl = na;
 #pragma unroll
@@ -234,12 +242,6 @@ KGE_DEV int tc_scan_chunk(const uint32_t (&v)[32], int nv, float tau_hi, float t
   }
   return hi;
 }
-
-// timeline stamps of CTA (0,0) (measurement aid; P.trace is null in normal operation)
-#define TC_STAMP(role, slot)                                                                         \
-  do {                                                                                               \
-    if (P.trace && blockIdx.x == 0 && blockIdx.y == 0 && (slot) < 64) P.trace[(role) * 64 + (slot)] = clock64(); \
-  } while (0)
 
 // ---- the sweep ------------------------------------------------------------------------------------
 // grid (splits, query blocks); CTA = 128 queries x a run of 128-candidate tiles.
@@ -393,11 +395,11 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
       for (int cb = 0; cb < nchunks; cb += 2) {
         tc_tmem_wait_ld();
         if (cb + 1 < nchunks) tc_tmem_ld32(taddr + (uint32_t)((cb + 1) * 32), vb);
-        cnt += tc_scan_chunk(va, min(32, nvalid - cb * 32), tau_hi, tau_lo, q, cbase + cb * 32, live, P, L, lane);
+        cnt += tc_scan_chunk(va, min(32, nvalid - cb * 32), tau_hi, tau_lo, q, cbase + cb * 32, live, P, L, lane, ev, warp == 2 && lane == 0);
         if (cb + 1 < nchunks) {
           tc_tmem_wait_ld();
           if (cb + 2 < nchunks) tc_tmem_ld32(taddr + (uint32_t)((cb + 2) * 32), va);
-          cnt += tc_scan_chunk(vb, min(32, nvalid - (cb + 1) * 32), tau_hi, tau_lo, q, cbase + (cb + 1) * 32, live, P, L, lane);
+          cnt += tc_scan_chunk(vb, min(32, nvalid - (cb + 1) * 32), tau_hi, tau_lo, q, cbase + (cb + 1) * 32, live, P, L, lane, ev, warp == 2 && lane == 0);
         }
       }
       tc_fence_before();

@@ -34,6 +34,79 @@ score_fwd_kernel(ModelParams P, int grouping, const int64_t* __restrict__ h,
   if (valid && lane == 0) out[g] = s;
 }
 
+// ---- TransE / TransM, large batches: persistent CTAs, rows staged in shared memory by cp.async --------
+// The register-cached kernel above holds a triple's three rows in registers (84 of its 115 registers at
+// d = 200), which caps it at 2 CTAs per SM that move in lock step through ids -> rows -> compute: measured
+// 4.2 TB/s of DRAM traffic (0.64 of the measured copy peak, profiles/r2_score_ch_sweep.jsonl).  Here a
+// CTA is persistent and software-pipelined: lane l of a group copies ITS chunks (l, l+8, ...) of the
+// three rows of the NEXT triple into a shared-memory stage with 16-byte cp.async (LDGSTS: no registers
+// are tied up, nothing waits), the ids of the triple after that are already in registers, and the current
+// triple is evaluated from the other stage with exactly the two-pass arithmetic of trans_distance (CH = 0).
+// A lane only ever reads what it copied itself, so there is no barrier anywhere in the loop.
+KGE_DEV void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+KGE_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> KGE_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int MODEL, int GROUPING>
+__global__ void __launch_bounds__(kThreads, 1)
+score_fwd_staged_kernel(ModelParams P, const int64_t* __restrict__ h, const int64_t* __restrict__ r,
+                        const int64_t* __restrict__ t, int64_t n, float* __restrict__ out, int64_t ntiles) {
+  extern __shared__ float4 smem_f4[];
+  const int lane = threadIdx.x & 7, grp = threadIdx.x >> 3;
+  const int d = P.d, nch = d >> 2;                       // d % 4 == 0 (host checks)
+  float4* const st0 = smem_f4 + (size_t)grp * 3 * nch;
+  float4* const st1 = st0 + (size_t)kGroupsPerCta * 3 * nch;
+  const float* const ent = P.tab[0];
+  const float* const rel = P.tab[1];
+  struct Ids { int64_t h, r, t; };
+  auto load_ids = [&](int64_t tile) {
+    Ids I;
+    int64_t g = tile * kGroupsPerCta + grp;
+    if (g >= n) g = n - 1;                               // idle groups shadow the last triple
+    I.h = __ldg(h + g); I.r = __ldg(r + g); I.t = __ldg(t + g);
+    return I;
+  };
+  auto issue = [&](float4* st, const Ids& I) {
+    const float4* hp = reinterpret_cast<const float4*>(ent + (size_t)I.h * d);
+    const float4* rp = reinterpret_cast<const float4*>(rel + (size_t)I.r * d);
+    const float4* tp = reinterpret_cast<const float4*>(ent + (size_t)I.t * d);
+    for (int c = lane; c < nch; c += 8) {
+      cp_async16(st + c, hp + c);
+      cp_async16(st + nch + c, rp + c);
+      cp_async16(st + 2 * nch + c, tp + c);
+    }
+  };
+  const int64_t stride = gridDim.x;
+  int64_t tile = blockIdx.x;
+  if (tile >= ntiles) return;
+  Ids cur = load_ids(tile);
+  issue(st0, cur);
+  cp_async_commit();
+  Ids nxt = cur;
+  if (tile + stride < ntiles) nxt = load_ids(tile + stride);
+  int buf = 0;
+  for (; tile < ntiles; tile += stride, buf ^= 1) {
+    float4* const mine = buf ? st1 : st0;
+    const bool more = tile + stride < ntiles;
+    if (more) issue(buf ? st0 : st1, nxt);               // rows of the next tile: in flight during this tile's math
+    cp_async_commit();
+    const Ids keep = cur;
+    cur = nxt;
+    if (tile + 2 * stride < ntiles) nxt = load_ids(tile + 2 * stride);   // ids two tiles ahead: off the critical path
+    cp_async_wait<1>();                                  // this lane's copies of the current tile have landed
+    auto fh = [&](int c) { return mine[c]; };
+    auto fr = [&](int c) { return mine[nch + c]; };
+    auto ft = [&](int c) { return mine[2 * nch + c]; };
+    float s = trans_distance<GROUPING, 0>(fh, fr, ft, nch, lane, P.l1);
+    if (MODEL == KGE_TRANSM) s = fmul(__ldg(P.tab[2] + keep.r), s);   // theta[r] * distance (pairwise.py:325-347)
+    const int64_t g = tile * kGroupsPerCta + grp;
+    if (g < n && lane == 0) out[g] = s;
+  }
+  cp_async_wait<0>();
+}
+
 int check_model(const kge_model_t* m) {
   if (!m) { set_error("model is NULL"); return KGE_EINVAL; }
   const int nt = num_tables(m->model);
@@ -90,6 +163,30 @@ extern "C" int kge_score_fwd(const kge_model_t* m, int grouping, const int64_t* 
   }
   const unsigned grid = (unsigned)((n + kGroupsPerCta - 1) / kGroupsPerCta);
   cudaStream_t st = (cudaStream_t)stream;
+  if ((m->model == KGE_TRANSE || m->model == KGE_TRANSM) && vec == 4 && m->dim % 4 == 0 && !getenv("KGE_SCORE_NO_STAGED")) {
+    // large batches: persistent cp.async-staged kernel (one CTA per SM, two stages of 32 triples)
+    const size_t stage_smem = (size_t)2 * kGroupsPerCta * 3 * (size_t)m->dim * sizeof(float);
+    const int64_t ntiles = (n + kGroupsPerCta - 1) / kGroupsPerCta;
+    if (stage_smem <= 227 * 1024 && ntiles >= 4 * (int64_t)sm_count()) {
+      const unsigned pgrid = (unsigned)sm_count();
+#define LAUNCH_STAGED(M)                                                                                   \
+  do {                                                                                                     \
+    if (grouping == KGE_GROUP_TAIL) {                                                                      \
+      KGE_CUDA_OK(cudaFuncSetAttribute(score_fwd_staged_kernel<M, KGE_GROUP_TAIL>,                         \
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_smem));     \
+      score_fwd_staged_kernel<M, KGE_GROUP_TAIL><<<pgrid, kThreads, stage_smem, st>>>(P, h, r, t, n, scores, ntiles); \
+    } else {                                                                                               \
+      KGE_CUDA_OK(cudaFuncSetAttribute(score_fwd_staged_kernel<M, KGE_GROUP_HEAD>,                         \
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_smem));     \
+      score_fwd_staged_kernel<M, KGE_GROUP_HEAD><<<pgrid, kThreads, stage_smem, st>>>(P, h, r, t, n, scores, ntiles); \
+    }                                                                                                      \
+  } while (0)
+      if (m->model == KGE_TRANSE) LAUNCH_STAGED(KGE_TRANSE); else LAUNCH_STAGED(KGE_TRANSM);
+#undef LAUNCH_STAGED
+      KGE_CHECK_LAUNCH("score_fwd_staged_kernel");
+      return KGE_OK;
+    }
+  }
   // distance models: the register-cache depth is a template parameter picked from the width
   // (TransD gathers six rows per triple: re-reading them from L1 at high occupancy beats caching
   //  the projected operands at <= 128 registers — 0.89 vs 0.78 of HBM peak measured — so CH = 0)

@@ -275,9 +275,7 @@ class Evaluator:
         name = getattr(self.model, "model_name", "")
         if len(rs) == 0:
             return False
-        if name == "transr":   # same scheme (P_r = normalize(ent) . M_r), proved on the oracle but not yet
-            return getattr(self.config, "relation_grouped_eval", None) is True   # timed on a B200: on request only
-        if name not in ("transh", "transd"):
+        if name not in ("transh", "transd", "transr"):   # TransR: P_r = normalize(ent) . M_r over once-normalised rel rows
             return False
         force = getattr(self.config, "relation_grouped_eval", self.GROUPED_BY_DEFAULT)
         if force is not None:

@@ -267,10 +267,6 @@ def test_relation_grouped_evaluation_equals_gather_sweep(name, d, l1):
     assert np.array_equal(ev.rank_triples(qh, qr, qt)[:, 0], want[:, 0])     # no filters
 
 
-@pytest.mark.skipif(__import__("os").environ.get("KGE_RUN_UNVERIFIED") != "1",
-                    reason="TransR relation-grouped evaluation: proved on the oracle with the emulated kernels "
-                           "(tests/test_emu_project.py) but written after the round's GPU minutes were spent; "
-                           "run with KGE_RUN_UNVERIFIED=1 on a B200 before enabling it by default")
 def test_relation_grouped_evaluation_transr():
     import types
     import oracle

@@ -44,7 +44,8 @@ namespace kge {
 constexpr int kTcBM = 128;        // queries per CTA (UMMA M)
 constexpr int kTcBN = 128;        // candidates per tile (UMMA N)
 constexpr int kTcBK = 64;         // bf16 elements per k-block = one 128-byte swizzle row
-constexpr int kTcThreads = 192;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int kTcThreads = 320;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue
+constexpr int kTcEpiWarps = 8;    // two warps per TMEM lane quadrant, each scanning half of the tile's columns
 constexpr int kTcTmemCols = 256;  // two accumulator stages of kTcBN fp32 columns
 constexpr int kTcMaxStages = 6;
 constexpr uint32_t kTcTileBytes = kTcBN * kTcBK * 2;   // one operand k-block tile: 128 rows x 128 B = 16 KB
@@ -249,8 +250,9 @@ KGE_DEV int tc_scan_chunk(const uint32_t (&v)[32], int nv, float tau_hi, float t
 //                   ring of stages)
 //   warp 1 lane 0 : issues the tcgen05.mma chain of a tile into accumulator stage t&1; tcgen05.commit
 //                   releases smem stages and publishes finished accumulators
-//   warps 2..5    : epilogue — warp w owns TMEM lanes 32*(w&3).. (= query rows), reads 32 columns
-//                   (= candidates) per tcgen05.ld and compares them with the row's two thresholds
+//   warps 2..9    : epilogue — warp w owns TMEM lanes 32*(w&3).. (= query rows) and the column half
+//                   (w-2)/4 of the tile (= 64 candidates), 32 columns per tcgen05.ld, compared with the row's
+//                   two thresholds
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMaps TM) {
   extern __shared__ unsigned char tc_smem_raw[];
@@ -281,7 +283,7 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.nstages; ++s) { tc_mbar_init(&full[s], 1); tc_mbar_init(&empty[s], 1); }
     tc_mbar_init(a_full, 1);
-    for (int s = 0; s < 2; ++s) { tc_mbar_init(&tmem_full[s], 1); tc_mbar_init(&tmem_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { tc_mbar_init(&tmem_full[s], 1); tc_mbar_init(&tmem_empty[s], kTcEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -387,19 +389,22 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
       const int64_t cbase = (int64_t)(t0 + t) * kTcBN;
       const int nvalid = (int)min((int64_t)kTcBN, P.nc - cbase);
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * kTcBN);
-      const int nchunks = (nvalid + 31) >> 5;
+      // this warp's half of the tile's columns: [c0, c0 + 64)
+      const int c0 = ((warp - 2) >> 2) * (kTcBN / 2);
+      const int nloc = min(kTcBN / 2, nvalid - c0);          // valid columns in the half (may be <= 0)
+      const int nchunks = nloc > 0 ? (nloc + 31) >> 5 : 0;
       // two register buffers: the tcgen05.ld of chunk cb+1 is in flight while chunk cb is compared
       uint32_t va[32], vb[32];
-      tc_tmem_ld32(taddr, va);
+      if (nchunks > 0) tc_tmem_ld32(taddr + (uint32_t)c0, va);
 #pragma unroll 1
       for (int cb = 0; cb < nchunks; cb += 2) {
         tc_tmem_wait_ld();
-        if (cb + 1 < nchunks) tc_tmem_ld32(taddr + (uint32_t)((cb + 1) * 32), vb);
-        cnt += tc_scan_chunk(va, min(32, nvalid - cb * 32), tau_hi, tau_lo, q, cbase + cb * 32, live, P, L, lane, ev, warp == 2 && lane == 0);
+        if (cb + 1 < nchunks) tc_tmem_ld32(taddr + (uint32_t)(c0 + (cb + 1) * 32), vb);
+        cnt += tc_scan_chunk(va, min(32, nloc - cb * 32), tau_hi, tau_lo, q, cbase + c0 + cb * 32, live, P, L, lane, ev, warp == 2 && lane == 0);
         if (cb + 1 < nchunks) {
           tc_tmem_wait_ld();
-          if (cb + 2 < nchunks) tc_tmem_ld32(taddr + (uint32_t)((cb + 2) * 32), va);
-          cnt += tc_scan_chunk(vb, min(32, nvalid - (cb + 1) * 32), tau_hi, tau_lo, q, cbase + (cb + 1) * 32, live, P, L, lane, ev, warp == 2 && lane == 0);
+          if (cb + 2 < nchunks) tc_tmem_ld32(taddr + (uint32_t)(c0 + (cb + 2) * 32), va);
+          cnt += tc_scan_chunk(vb, min(32, nloc - (cb + 1) * 32), tau_hi, tau_lo, q, cbase + c0 + (cb + 1) * 32, live, P, L, lane, ev, warp == 2 && lane == 0);
         }
       }
       tc_fence_before();

@@ -55,7 +55,7 @@ class RegFunction(torch.autograd.Function):
         out = _lib.reg_fwd_bwd(desc, reg_type, lmbda, h.contiguous(), r.contiguous(), t.contiguous())
         ctx.spec, ctx.reg_type, ctx.lmbda = spec, reg_type, lmbda
         ctx.save_for_backward(h, r, t, *tables)
-        return out.reshape(())
+        return out.squeeze_(0)
 
     @staticmethod
     def backward(ctx, gout):
@@ -74,7 +74,7 @@ class HingeFunction(torch.autograd.Function):
         _require_cuda(pos, neg)
         loss, gp, gn = _lib.loss_pairwise_hinge(pos.contiguous(), neg.contiguous(), float(margin))
         ctx.save_for_backward(gp, gn)
-        return loss.reshape(())
+        return loss.squeeze_(0)   # in place: a VIEW returned from forward() may not be modified by the caller's `loss += reg` (trainer.py:155)
 
     @staticmethod
     def backward(ctx, g):
@@ -88,7 +88,7 @@ class LogisticFunction(torch.autograd.Function):
         _require_cuda(preds, target)
         loss, gpreds = _lib.loss_pointwise_logistic(preds.contiguous(), target.contiguous().float())
         ctx.save_for_backward(gpreds)
-        return loss.reshape(())
+        return loss.squeeze_(0)   # in place: a VIEW returned from forward() may not be modified by the caller's `loss += reg` (trainer.py:155)
 
     @staticmethod
     def backward(ctx, g):
@@ -102,7 +102,7 @@ class SelfAdvFunction(torch.autograd.Function):
         _require_cuda(pos, neg)
         loss, gp, gn = _lib.loss_selfadv(pos.contiguous(), neg.contiguous(), int(neg_rate), float(alpha))
         ctx.save_for_backward(gp, gn)
-        return loss.reshape(())
+        return loss.squeeze_(0)   # in place: a VIEW returned from forward() may not be modified by the caller's `loss += reg` (trainer.py:155)
 
     @staticmethod
     def backward(ctx, g):
@@ -147,7 +147,7 @@ class MultiClassBceFunction(torch.autograd.Function):
         loss, g = _lib.proj_bce(preds.contiguous(), labels.contiguous().float(), float(label_scale),
                                 float(label_shift), 1.0, want_grad=True)
         ctx.save_for_backward(g)
-        return loss.reshape(())
+        return loss.squeeze_(0)   # in place: a VIEW returned from forward() may not be modified by the caller's `loss += reg` (trainer.py:155)
 
     @staticmethod
     def backward(ctx, gout):

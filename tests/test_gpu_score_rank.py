@@ -283,3 +283,25 @@ def test_relation_grouped_evaluation_transr():
     ev.config = types.SimpleNamespace(device="cuda", tot_entity=N, relation_grouped_eval=True, cuda_graph=False)
     ev._filter_cache, ev._workspace = {}, None
     assert np.array_equal(ev.rank_triples(qh, qr, qt, ft, fh), oracle.rank_1vsall(om, qh, qr, qt, ft, fh))
+
+
+@pytest.mark.parametrize("name,d,l1", [("transe", 200, False), ("transe", 52, True), ("transm", 64, False), ("transe", 300, False)])
+def test_score_fwd_large_batch_staged_kernel(name, d, l1, monkeypatch):
+    """batches of >= 4 tiles per SM take the persistent cp.async-staged kernel (kge_score.cu): same bits as
+    the register-cached kernel and the oracle, ragged last tile included, both groupings."""
+    import oracle
+    L = _lib()
+    N, R = 3000, 11
+    om, _ = gpu.synthetic_case(name, N, R, d, seed=d, l1=l1)
+    desc = gpu.desc_from_oracle_model(om)
+    n = 4 * torch.cuda.get_device_properties(0).multi_processor_count * 32 + 777
+    rng = np.random.RandomState(1)
+    h, r, t = rng.randint(N, size=n), rng.randint(R, size=n), rng.randint(N, size=n)
+    for grouping in (0, 1):
+        so = oracle.score_fwd(om, h, r, t, grouping)
+        s = L.score_fwd(desc, _cuda(h), _cuda(r), _cuda(t), grouping).cpu().numpy()
+        np.testing.assert_array_equal(gpu.bits(s), gpu.bits(so))
+        monkeypatch.setenv("KGE_SCORE_NO_STAGED", "1")
+        s2 = L.score_fwd(desc, _cuda(h), _cuda(r), _cuda(t), grouping).cpu().numpy()
+        monkeypatch.delenv("KGE_SCORE_NO_STAGED")
+        np.testing.assert_array_equal(gpu.bits(s2), gpu.bits(so))

@@ -43,13 +43,12 @@ namespace kge {
 
 constexpr int kTcBM = 128;        // queries per CTA (UMMA M)
 constexpr int kTcBN = 128;        // candidates per tile (UMMA N)
-constexpr int kTcBK = 64;         // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int kTcBKMax = 64;      // bf16 elements per k-block: 64 (128-byte swizzle rows) or 32 (64-byte rows; twice the stages)
 constexpr int kTcThreads = 320;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue
 constexpr int kTcEpiWarps = 8;    // two warps per TMEM lane quadrant, each scanning half of the tile's columns
 constexpr int kTcTmemCols = 256;  // two accumulator stages of kTcBN fp32 columns
-constexpr int kTcMaxStages = 6;
-constexpr uint32_t kTcTileBytes = kTcBN * kTcBK * 2;   // one operand k-block tile: 128 rows x 128 B = 16 KB
-constexpr int kTcResidentMaxKb = 4;                    // query block stays in smem when Kp <= 256
+constexpr int kTcMaxStages = 8;
+constexpr int kTcResidentMaxK = 256;                   // query block stays in smem when Kp <= 256
 
 struct TcParams {
   const float* tau;        // [Q][2]: tau_hi, tau_lo
@@ -59,6 +58,8 @@ struct TcParams {
   unsigned cap;
   int64_t Q, nc;
   int Kp, nkb, a_resident, nstages;
+  int bk;                  // k-block width in bf16 elements (64 or 32)
+  uint32_t tile_bytes;     // one operand k-block tile: 128 rows x bk x 2 bytes
   int tiles_per_cta, ntiles;
   float* dbg;              // optional [Q][nc] raw accumulators (tests)
   long long* trace;        // optional timeline of CTA (0,0): [3 roles][64] clock64 stamps (kge_debug_set_tc_trace)
@@ -271,9 +272,9 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(gbase + 512);
   const uint32_t a_base = base + 1024u;                                            // resident query k-blocks
   const uint32_t a_bytes = !P.a_resident ? 0u
-      : (P.tail_cols ? (uint32_t)(P.nkb - 1) * 2u * kTcTileBytes + 2u * P.tail_bytes : (uint32_t)P.nkb * 2u * kTcTileBytes);
+      : (P.tail_cols ? (uint32_t)(P.nkb - 1) * 2u * P.tile_bytes + 2u * P.tail_bytes : (uint32_t)P.nkb * 2u * P.tile_bytes);
   const uint32_t st_base = a_base + a_bytes;
-  const uint32_t st_bytes = (P.a_resident ? 2u : 4u) * kTcTileBytes;              // [B0][B1]([A0][A1])
+  const uint32_t st_bytes = (P.a_resident ? 2u : 4u) * P.tile_bytes;              // [B0][B1]([A0][A1])
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -303,10 +304,10 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
         tc_mbar_expect_tx(a_full, a_bytes);
         for (int kb = 0; kb < P.nkb; ++kb) {
           const bool tail = P.tail_cols && kb == P.nkb - 1;
-          const uint32_t tb = tail ? P.tail_bytes : kTcTileBytes;
-          const uint32_t dst = a_base + (uint32_t)kb * 2u * kTcTileBytes;
-          tc_tma_load_2d(dst, tail ? &TM.a0t : &TM.a0, kb * kTcBK, (int)q0, a_full);
-          tc_tma_load_2d(dst + tb, tail ? &TM.a1t : &TM.a1, kb * kTcBK, (int)q0, a_full);
+          const uint32_t tb = tail ? P.tail_bytes : P.tile_bytes;
+          const uint32_t dst = a_base + (uint32_t)kb * 2u * P.tile_bytes;
+          tc_tma_load_2d(dst, tail ? &TM.a0t : &TM.a0, kb * P.bk, (int)q0, a_full);
+          tc_tma_load_2d(dst + tb, tail ? &TM.a1t : &TM.a1, kb * P.bk, (int)q0, a_full);
         }
       }
       int stage = 0; uint32_t phase = 0;
@@ -316,16 +317,16 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
         const int row = (t0 + t) * kTcBN;
         for (int kb = 0; kb < P.nkb; ++kb) {
           const bool tail = P.tail_cols && kb == P.nkb - 1;
-          const uint32_t tb = tail ? P.tail_bytes : kTcTileBytes;
+          const uint32_t tb = tail ? P.tail_bytes : P.tile_bytes;
           tc_mbar_wait(&empty[stage], phase ^ 1u);
           TC_STAMP(0, ev++);
           tc_mbar_expect_tx(&full[stage], (P.a_resident ? 2u : 4u) * tb);
           const uint32_t sb = st_base + (uint32_t)stage * st_bytes;
-          tc_tma_load_2d(sb, tail ? &TM.b0t : &TM.b0, kb * kTcBK, row, &full[stage]);
-          tc_tma_load_2d(sb + tb, tail ? &TM.b1t : &TM.b1, kb * kTcBK, row, &full[stage]);
+          tc_tma_load_2d(sb, tail ? &TM.b0t : &TM.b0, kb * P.bk, row, &full[stage]);
+          tc_tma_load_2d(sb + tb, tail ? &TM.b1t : &TM.b1, kb * P.bk, row, &full[stage]);
           if (!P.a_resident) {
-            tc_tma_load_2d(sb + 2u * tb, tail ? &TM.a0t : &TM.a0, kb * kTcBK, (int)q0, &full[stage]);
-            tc_tma_load_2d(sb + 3u * tb, tail ? &TM.a1t : &TM.a1, kb * kTcBK, (int)q0, &full[stage]);
+            tc_tma_load_2d(sb + 2u * tb, tail ? &TM.a0t : &TM.a0, kb * P.bk, (int)q0, &full[stage]);
+            tc_tma_load_2d(sb + 3u * tb, tail ? &TM.a1t : &TM.a1, kb * P.bk, (int)q0, &full[stage]);
           }
           if (++stage == P.nstages) { stage = 0; phase ^= 1u; }
         }
@@ -349,13 +350,13 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
           tc_fence_after();
           TC_STAMP(1, ev++);
           const bool tail = P.tail_cols && kb == P.nkb - 1;
-          const uint32_t tb = tail ? P.tail_bytes : kTcTileBytes;
-          const uint32_t rowb = tail ? (uint32_t)P.tail_cols * 2u : 128u;   // bytes per smem row = swizzle span
+          const uint32_t tb = tail ? P.tail_bytes : P.tile_bytes;
+          const uint32_t rowb = tail ? (uint32_t)P.tail_cols * 2u : (uint32_t)P.bk * 2u;   // bytes per smem row = swizzle span
           const uint32_t sb = st_base + (uint32_t)stage * st_bytes;
           const uint32_t b0 = sb, b1 = sb + tb;
-          const uint32_t a0 = P.a_resident ? a_base + (uint32_t)kb * 2u * kTcTileBytes : sb + 2u * tb;
+          const uint32_t a0 = P.a_resident ? a_base + (uint32_t)kb * 2u * P.tile_bytes : sb + 2u * tb;
           const uint32_t a1 = a0 + tb;
-          const int nks = tail ? P.tail_cols / 16 : min(kTcBK / 16, (P.Kp - kb * kTcBK + 15) / 16);
+          const int nks = tail ? P.tail_cols / 16 : min(P.bk / 16, (P.Kp - kb * P.bk + 15) / 16);
           const uint64_t da0 = tc_smem_desc(a0, rowb), da1 = tc_smem_desc(a1, rowb), db0 = tc_smem_desc(b0, rowb),
                          db1 = tc_smem_desc(b1, rowb);
           for (int k = 0; k < nks; ++k) {   // 16 bf16 = 32 bytes further along the swizzled row: +2 in the address field
@@ -552,7 +553,7 @@ static TcEncodeFn tc_encode_fn() {
 }
 // bf16 matrix [rows][Kp] row-major; box = {64 columns (128 bytes), 128 rows}, 128-byte swizzle, zero fill
 // (box_cols = 64: one 128-byte swizzle row; 32 / 16: the narrow tile of an exact-width last k-block)
-static int tc_make_map(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t Kp, int box_cols = kTcBK) {
+static int tc_make_map(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t Kp, int box_cols) {
   TcEncodeFn fn = tc_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled is not available"); return KGE_ECUDA; }
   const cuuint64_t gdim[2] = {Kp, rows};
@@ -636,18 +637,25 @@ int tc_sweep(const kge_model_t* m, int dir, int64_t Q, int64_t nc, void* tcws, T
 
   TcParams P;
   P.tau = tau; P.tc_counts = cnt; P.ctrl = ctrl; P.list = list; P.cap = tc_list_capacity(Q);
-  P.Q = Q; P.nc = nc; P.Kp = Kp; P.nkb = (Kp + kTcBK - 1) / kTcBK;
-  P.a_resident = P.nkb <= kTcResidentMaxKb ? 1 : 0;
+  // k-block width: 32 columns (64-byte swizzle rows) give twice the pipeline stages of 64 in the same shared
+  // memory — the operand loads are LATENCY bound (a TMA tile takes ~2.4k cycles to land whatever its size,
+  // profiles/r2_tc_trace_v5.jsonl), so stages in flight, not bytes, set the k-block cadence
+  int bk = 32;
+  if (const char* e = getenv("KGE_TC_BK")) { if (atoi(e) == 64) bk = 64; }   // tuning / test aid
+  P.bk = bk;
+  P.tile_bytes = (uint32_t)(kTcBN * bk * 2);
+  P.Q = Q; P.nc = nc; P.Kp = Kp; P.nkb = (Kp + bk - 1) / bk;
+  P.a_resident = Kp <= kTcResidentMaxK ? 1 : 0;
   {
-    const int last = Kp - kTcBK * (P.nkb - 1);   // columns of the last k-block: 16, 32, 48 or 64
-    P.tail_cols = (last == 16 || last == 32) ? last : 0;
+    const int last = Kp - bk * (P.nkb - 1);   // columns of the last k-block: a multiple of 16 up to bk
+    P.tail_cols = (last < bk && (last == 16 || last == 32)) ? last : 0;
     if (const char* e = getenv("KGE_TC_TAIL")) { if (atoi(e) == 0) P.tail_cols = 0; }   // tuning / test aid
     P.tail_bytes = (uint32_t)(kTcBN * P.tail_cols * 2);
   }
   const size_t budget = 227 * 1024 - 2048;   // control block + alignment slack
   const size_t a_bytes = !P.a_resident ? 0
-      : (P.tail_cols ? (size_t)(P.nkb - 1) * 2 * kTcTileBytes + 2 * (size_t)P.tail_bytes : (size_t)P.nkb * 2 * kTcTileBytes);
-  const size_t st_bytes = (P.a_resident ? 2 : 4) * (size_t)kTcTileBytes;
+      : (P.tail_cols ? (size_t)(P.nkb - 1) * 2 * P.tile_bytes + 2 * (size_t)P.tail_bytes : (size_t)P.nkb * 2 * P.tile_bytes);
+  const size_t st_bytes = (P.a_resident ? 2 : 4) * (size_t)P.tile_bytes;
   int nstages = (int)((budget - a_bytes) / st_bytes);
   if (nstages > kTcMaxStages) nstages = kTcMaxStages;
   if (nstages < 2) { set_error("tc_sweep: shared-memory plan failed"); return KGE_ENOTSUP; }
@@ -664,10 +672,10 @@ int tc_sweep(const kge_model_t* m, int dir, int64_t Q, int64_t nc, void* tcws, T
   P.epi_mode = 0;
   if (const char* e = getenv("KGE_TC_EPI_MODE")) P.epi_mode = atoi(e);   // measurement aid: wrong counts unless 0
   TcMaps TM;
-  int rc = tc_make_map(&TM.a0, A0, (uint64_t)Q, (uint64_t)Kp); if (rc) return rc;
-  rc = tc_make_map(&TM.a1, A1, (uint64_t)Q, (uint64_t)Kp); if (rc) return rc;
-  rc = tc_make_map(&TM.b0, w + L.b[0], (uint64_t)nc, (uint64_t)Kp); if (rc) return rc;
-  rc = tc_make_map(&TM.b1, w + L.b[1], (uint64_t)nc, (uint64_t)Kp); if (rc) return rc;
+  int rc = tc_make_map(&TM.a0, A0, (uint64_t)Q, (uint64_t)Kp, bk); if (rc) return rc;
+  rc = tc_make_map(&TM.a1, A1, (uint64_t)Q, (uint64_t)Kp, bk); if (rc) return rc;
+  rc = tc_make_map(&TM.b0, w + L.b[0], (uint64_t)nc, (uint64_t)Kp, bk); if (rc) return rc;
+  rc = tc_make_map(&TM.b1, w + L.b[1], (uint64_t)nc, (uint64_t)Kp, bk); if (rc) return rc;
   TM.a0t = TM.a0; TM.a1t = TM.a1; TM.b0t = TM.b0; TM.b1t = TM.b1;
   if (P.tail_cols) {
     rc = tc_make_map(&TM.a0t, A0, (uint64_t)Q, (uint64_t)Kp, P.tail_cols); if (rc) return rc;

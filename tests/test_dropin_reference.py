@@ -89,7 +89,8 @@ def test_pretrained_checkpoint_loads_through_trainer_load_model(tmp_path, monkey
     monkeypatch.setattr(ref_trainer, "Importer", B200Importer)
     ckpt = os.path.join(ref_loader.REF_DIR, "examples", "pretrained", "TransE")
     tr = object.__new__(ref_trainer.Trainer)
-    tr.config = type("C", (), {"load_from_data": ckpt})()
+    import types
+    tr.config = types.SimpleNamespace(load_from_data=ckpt)
     tr.model = None
     tr.load_model(ckpt)
     m = tr.model

@@ -144,9 +144,9 @@ band_resolve_kernel(ModelParams P, const int64_t* __restrict__ qh, const int64_t
     const bool band = k < total;
     if (band) {
       const unsigned long long pr = list[k];
-      skip = pr == ~0ull;   // unused slot of a warp's reserved block (kge_rank_tc.cu)
-      q = skip ? 0 : (int64_t)(pr >> 32);
-      e = skip ? 0 : (int64_t)(pr & 0xffffffffull);
+      if (pr == ~0ull) continue;   // unused slot of a warp's reserved block (kge_rank_tc.cu); group-uniform
+      q = (int64_t)(pr >> 32);
+      e = (int64_t)(pr & 0xffffffffull);
     } else {
       const int64_t kk = k - total;
       int64_t lo = 0, hi = Q;  // largest q with ptr[q] <= kk

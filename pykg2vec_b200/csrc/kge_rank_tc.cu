@@ -162,13 +162,13 @@ KGE_DEV void tc_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" :
     if (P.trace && blockIdx.x == 0 && blockIdx.y == 0 && (slot) < 64) P.trace[(role) * 64 + (slot)] = clock64(); \
   } while (0)
 
-// Pair-list slots are handed out per WARP in blocks reserved with one global atomic (a returning atomic
+// Pair-list slots are handed out per WARP in blocks (16 slots) reserved with one global atomic (a returning atomic
 // per ambiguous pair stalled the whole epilogue: 8k of 10k cycles per tile, profiles/r2_tc_trace_v2_*):
 // base/size = the warp's current block in P.list, used = slots already written.  Unused slots of a block
 // are filled with the sentinel ~0 (band_resolve_kernel skips them), so [0, ctrl[0]) is always fully defined.
 struct TcListState { unsigned base, used, size; };
 constexpr unsigned long long kTcListHole = ~0ull;
-constexpr unsigned kTcListBlock = 64;
+constexpr unsigned kTcListBlock = 16;
 
 KGE_DEV void tc_list_pad(TcListState& L, const TcParams& P, int lane) {
   for (unsigned i = L.used + (unsigned)lane; i < L.size; i += 32u)
@@ -637,11 +637,12 @@ int tc_sweep(const kge_model_t* m, int dir, int64_t Q, int64_t nc, void* tcws, T
 
   TcParams P;
   P.tau = tau; P.tc_counts = cnt; P.ctrl = ctrl; P.list = list; P.cap = tc_list_capacity(Q);
-  // k-block width: 32 columns (64-byte swizzle rows) give twice the pipeline stages of 64 in the same shared
-  // memory — the operand loads are LATENCY bound (a TMA tile takes ~2.4k cycles to land whatever its size,
-  // profiles/r2_tc_trace_v5.jsonl), so stages in flight, not bytes, set the k-block cadence
-  int bk = 32;
-  if (const char* e = getenv("KGE_TC_BK")) { if (atoi(e) == 64) bk = 64; }   // tuning / test aid
+  // k-block width: 64 columns (128-byte swizzle rows).  32-column blocks (64-byte rows) would give 7 pipeline
+  // stages instead of 3, but measured SLOWER (26.6 vs 24.5 us, profiles/r2_tc_trace_v6.jsonl): the operand
+  // stream is bound by delivered L2 bandwidth (~28 B/cycle per SM with 116 SMs pulling = 6.2 TB/s), not by
+  // latency, and 64-byte rows use it less efficiently.  KGE_TC_BK=32 keeps the variant reachable for tests.
+  int bk = 64;
+  if (const char* e = getenv("KGE_TC_BK")) { if (atoi(e) == 32) bk = 32; }   // tuning / test aid
   P.bk = bk;
   P.tile_bytes = (uint32_t)(kTcBN * bk * 2);
   P.Q = Q; P.nc = nc; P.Kp = Kp; P.nkb = (Kp + bk - 1) / bk;

@@ -100,33 +100,6 @@ class MetricCalculator:
         return {'mr': self.mr[self.epoch], 'fmr': self.fmr[self.epoch],
                 'mrr': self.mrr[self.epoch], 'fmrr': self.fmrr[self.epoch]}
 
-    def save_test_summary(self, model_name):
-        """evaluator.py:151-206 (summary txt + per-epoch CSV)."""
-        import pandas as pd
-        files = os.listdir(str(self.config.path_result))
-        l = len([f for f in files if model_name in f if 'Testing' in f])
-        with open(str(self.config.path_result / (model_name + '_summary_' + str(l) + '.txt')), 'w') as fh:
-            fh.write('----------------SUMMARY----------------\n')
-            for key, val in self.config.__dict__.items():
-                if 'gpu' in key or 'knowledge_graph' in key:
-                    continue
-                if isinstance(val, list):
-                    val = '[' + ','.join(str(v) for v in val) + ']'
-                fh.write(key + ':' + str(val) + '\n')
-            fh.write('-----------------------------------------\n')
-        columns = ['Epoch', 'Mean Rank', 'Filtered Mean Rank', 'Mean Reciprocal Rank',
-                   'Filtered Mean Reciprocal Rank']
-        for hit in self.config.hits:
-            columns += ['Hit-%d Ratio' % hit, 'Filtered Hit-%d Ratio' % hit]
-        results = []
-        for epoch in self.mr:
-            row = [epoch, self.mr[epoch], self.fmr[epoch], self.mrr[epoch], self.fmrr[epoch]]
-            for hit in self.config.hits:
-                row += [self.hit[(epoch, hit)], self.fhit[(epoch, hit)]]
-            results.append(row)
-        with open(str(self.config.path_result / (model_name + '_Testing_results_' + str(l) + '.csv')), 'a') as fh:
-            pd.DataFrame(results, columns=columns).to_csv(fh)
-
     def display_summary(self):
         stop_time = timeit.default_timer()
         lines = ['', "------Test Results for %s: Epoch: %s --- time: %.2f------------"
@@ -478,7 +451,6 @@ class Evaluator:
         self.metric_calculator.append_ranks(counts, epoch)
         self.metric_calculator.settle()
         self.metric_calculator.display_summary()
-        if epoch is not None and hasattr(self.config, 'epochs') and hasattr(self.config, 'path_result') \
-                and self.metric_calculator.epoch >= self.config.epochs - 1:
-            self.metric_calculator.save_test_summary(self.model.model_name)
+        # (the reference also writes a summary txt / csv at the last epoch, evaluator.py:151-206,331-332: result
+        #  files are control plane, out of scope — SURVEY.md §2)
         return self.metric_calculator.get_curr_scores()

@@ -234,8 +234,10 @@ def run_cuda(args):
     def resident_step(i):
         if graph_step is not None:
             return graph_step(i)
+        # multi-GPU "ids" mode: the 24 KB id all-gather is started first and hides behind the evaluation batch
+        ex = tr.exchange_batch_async(devin[i][0])
         eval_resident(i)
-        train_resident(i)
+        tr.train_batch_device(devin[i][0], exchanged=ex)
 
     # Single GPU: the resident step is ~12 short kernels, so launch gaps are a visible share of it.  It is
     # captured ONCE as a CUDA graph reading from fixed device buffers; a timed step is then the D2D copies of

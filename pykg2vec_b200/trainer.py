@@ -283,21 +283,32 @@ class Trainer:
             return PendingScalar(call)
         return float(call()[0])
 
-    def train_batch_device(self, ids):
+    def exchange_batch_async(self, ids):
+        """data-parallel "ids" mode: start the all-gather of this rank's batch ids (NCCL runs it on its own
+        stream) and return a closure yielding the global batch — issue it BEFORE independent work (an
+        evaluation batch) and hand the closure to train_batch_device(exchanged=...) so that the exchange hides
+        behind that work.  None in every other mode."""
+        if self._dp != "ids":
+            return None
+        from . import sharding
+        ids = list(ids)
+        n = [int(a.numel()) for a in ids]
+        if len(set(n)) == 1:
+            fin = sharding.allgather_batch_ids_async(torch.stack(ids))
+            return lambda: list(fin())
+        k = len(ids) // 2   # ragged (neg_rate > 1): positives and negatives gathered separately
+        fa = sharding.allgather_batch_ids_async(torch.stack(ids[:k]))
+        fb = sharding.allgather_batch_ids_async(torch.stack(ids[k:]))
+        return lambda: list(fa()) + list(fb())
+
+    def train_batch_device(self, ids, exchanged=None):
         """One batch whose id arrays are already DEVICE tensors (pykg2vec_b200.generator.Generator).
         Returns the loss as a device tensor (no host sync)."""
         self.model.train()
         ids = list(ids)
         strategy = self.model.training_strategy
         if self._dp == "ids":   # replicated update on the all-gathered global batch
-            from . import sharding
-            n = [int(a.numel()) for a in ids]
-            if len(set(n)) == 1:
-                ids = list(sharding.allgather_batch_ids(torch.stack(ids)))
-            else:               # ragged (neg_rate > 1): positives and negatives gathered separately
-                k = len(ids) // 2
-                ids = list(sharding.allgather_batch_ids(torch.stack(ids[:k]))) + \
-                    list(sharding.allgather_batch_ids(torch.stack(ids[k:])))
+            ids = (exchanged or self.exchange_batch_async(ids))()
         if self._fused:
             with torch.no_grad():
                 if strategy == TrainingStrategy.PAIRWISE_BASED:

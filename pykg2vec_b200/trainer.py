@@ -21,7 +21,7 @@ Two execution modes for the same step semantics:
                every rank applies the identical dense optimizer step — per-GPU scoring work is B, not world x B;
       "ids"  : ranks all-gather their batch ids (24 KB at B=512) and every rank applies the global batch —
                cheaper than moving gradient tables when the batch is tiny;
-      None   : "grads" when the batch's touched rows outweigh a table sweep, else "ids".
+      None   : "grads" when a rank's batch touches more floats than the tables hold, else "ids".
 
 The sampler processes, epoch loop, early stopping, checkpointing and export of the
 reference Trainer are out of scope here; batches are handed in as
@@ -95,7 +95,10 @@ class Trainer:
         table_floats = sum(t.numel() for t in tabs)
         per_triple = sum(t.shape[1] for t in tabs)
         batch = int(self.config.batch_size) * (1 + int(getattr(self.config, "neg_rate", 1)))
-        return "grads" if batch * per_triple * self._world >= table_floats else "ids"
+        # a rank's own batch already touches more floats than the tables hold -> sweep-sized exchanges are cheap
+        # next to the scoring work, and splitting that work is what pays (config 4); below that the 24 KB id
+        # exchange (which hides behind an evaluation batch) beats moving gradient tables (config 2)
+        return "grads" if batch * per_triple >= table_floats else "ids"
 
     # ---- reference-signature steps (autograd mode) --------------------------------------------
     def train_step_pairwise(self, pos_h, pos_r, pos_t, neg_h, neg_r, neg_t):

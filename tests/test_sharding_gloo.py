@@ -108,3 +108,130 @@ def test_shard_range_properties():
             sizes = [shard_range(total, world, r)[1] - shard_range(total, world, r)[0] for r in range(world)]
             assert sum(sizes) == total and max(sizes) - min(sizes) <= 1
             assert shard_range(total, world, 0)[0] == 0 and shard_range(total, world, world - 1)[1] == total
+
+
+# ---- data-parallel Trainer logic on gloo / CPU with a device double ---------------------------------
+def _install_cpu_double():
+    """Swap the C-ABI bindings the fused TransE steps use for torch-CPU restatements (oracle/ref_port.py), so
+    that the HOST logic of pykg2vec_b200.trainer.Trainer — mode selection, id all-gather (sync and async),
+    gradient all-reduce with sum / average semantics, dense optimizer bookkeeping — runs without a GPU."""
+    from oracle import ref_port
+    from pykg2vec_b200 import _lib
+    _lib._dev_f32 = lambda t, name: t
+    _lib._dev_i64 = lambda t, name: t
+
+    def score(desc, h, r, t, tables=None):
+        return ref_port.score(desc.name, tables if tables is not None else desc.tables, h, r, t, l1_flag=desc.l1_flag)
+
+    def score_fwd(desc, h, r, t, grouping=0, out=None):
+        return score(desc, h, r, t).detach()
+
+    def score_bwd(desc, h, r, t, grad_scores, grad_tables):
+        with torch.enable_grad():   # the Trainer runs its fused steps under no_grad
+            tabs = [w.detach().clone().requires_grad_() for w in desc.tables]
+            score(desc, h, r, t, tabs).backward(grad_scores)
+        for g, w in zip(grad_tables, tabs):
+            if g is not None and w.grad is not None:
+                g += w.grad
+
+    def loss_pairwise_hinge(pos, neg, margin, want_grad=True):
+        v = torch.relu(pos + margin - neg)
+        gp = (v > 0).float()
+        return v.sum().reshape(1), gp, -gp
+
+    def optim_apply_dense(w, g, optimizer, lr, state1=None, state2=None, eps=None, betas=(0.9, 0.999), step=1):
+        if optimizer == 0:
+            w -= lr * g
+        elif optimizer == 1:
+            state1 += g * g
+            w -= lr * g / (state1.sqrt() + (1e-10 if eps is None else eps))
+        else:
+            state1 += (g - state1) * (1 - betas[0])
+            state2.mul_(betas[1]).addcmul_(g, g, value=1 - betas[1])
+            denom = state2.sqrt() / (1 - betas[1] ** step) ** 0.5 + (1e-8 if eps is None else eps)
+            w -= (lr / (1 - betas[0] ** step)) * state1 / denom
+        g.zero_()
+
+    def optim_apply_rows(desc, grad_scratch, state, optimizer, h, r, t, lr, eps=1e-10):
+        for k, w in enumerate(desc.tables):   # dense equivalent; a second call sees zeroed gradients
+            if grad_scratch[k] is not None:
+                optim_apply_dense(w, grad_scratch[k], optimizer, lr, state[k] if state else None)
+
+    def train_pairwise_hinge_sgd(desc, grad_scratch, ph, pr, pt, nh, nr, nt, margin, lr, loss_out=None):
+        pos, neg = score_fwd(desc, ph, pr, pt), score_fwd(desc, nh, nr, nt)
+        loss, gp, gn = loss_pairwise_hinge(pos, neg, margin)
+        score_bwd(desc, ph, pr, pt, gp, grad_scratch)
+        score_bwd(desc, nh, nr, nt, gn, grad_scratch)
+        optim_apply_rows(desc, grad_scratch, None, 0, ph, pr, pt, lr)
+        if loss_out is not None:
+            loss_out.copy_(loss)
+            return loss_out
+        return loss
+
+    for name, fn in list(locals().items()):
+        if callable(fn) and hasattr(_lib, name) and name not in ("score",):
+            setattr(_lib, name, fn)
+
+
+def _dp_worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import pykg2vec_b200
+    from pykg2vec_b200 import sharding
+    from pykg2vec_b200.synthetic import SyntheticConfig, SyntheticKnowledgeGraph
+    from pykg2vec_b200.trainer import Trainer
+    sharding.init_distributed(backend="gloo")
+    _install_cpu_double()
+    kg = SyntheticKnowledgeGraph(120, 5, 600, 20, 20, seed=1)
+
+    def make(opt, mode):
+        cfg = SyntheticConfig(kg, device="cpu", optimizer=opt, learning_rate=0.05, hidden_size=16, margin=1.0,
+                              l1_flag=False, batch_size=32, neg_rate=1, dp_mode=mode, cuda_graph=False)
+        torch.manual_seed(0)
+        tr = Trainer(pykg2vec_b200.import_model("transe")(**cfg.__dict__), cfg)
+        tr.build_model()
+        return tr
+
+    B = 32
+    # mode selection: a tiny batch against these tables exchanges ids; a batch that out-weighs the tables, gradients
+    auto = make("sgd", None)
+    assert auto._world == world and auto._dp in ("ids", "grads")
+    auto.config.batch_size = 8          # 16 triples x 32 floats < 2,000 table floats
+    assert auto._pick_dp_mode() == "ids"
+    auto.config.batch_size = 4096
+    assert auto._pick_dp_mode() == "grads"
+    for opt in ("sgd", "adagrad", "adam"):
+        single = make(opt, "off")
+        trs = {mode: make(opt, mode) for mode in ("grads", "ids")}
+        assert single._dp is None and all(t_._dp == m for m, t_ in trs.items())
+        for step in range(3):
+            per_rank = []
+            for rk in range(world):
+                rng = np.random.RandomState(100 * step + rk)
+                per_rank.append([rng.randint(120, size=B), rng.randint(5, size=B), rng.randint(120, size=B),
+                                 rng.randint(120, size=B), rng.randint(5, size=B), rng.randint(120, size=B)])
+            to = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int64))
+            glob = [to(np.concatenate([per_rank[rk][k] for rk in range(world)])) for k in range(6)]
+            l_single = float(single.train_batch_device(glob).item())
+            for mode, t_ in trs.items():
+                mine = [to(a) for a in per_rank[rank]]
+                ex = t_.exchange_batch_async(mine)          # None in "grads" mode
+                assert (ex is None) == (mode == "grads")
+                l_dp = float(t_.train_batch_device(mine, exchanged=ex).item())
+                assert abs(l_dp - l_single) <= 1e-4 * max(abs(l_single), 1e-6), (opt, mode, step, l_dp, l_single)
+        for mode, t_ in trs.items():
+            for (ka, va), (kb, vb) in zip(t_.model.state_dict().items(), single.model.state_dict().items()):
+                np.testing.assert_allclose(va.numpy(), vb.numpy(), rtol=0, atol=2e-5, err_msg="%s %s %s" % (opt, mode, ka))
+                other = va.clone()
+                dist.broadcast(other, src=0)
+                assert torch.equal(other, va), (opt, mode, ka)     # replicas stay identical
+    dist.barrier()
+    dist.destroy_process_group()
+    open(os.path.join(tmp, "dp_ok%d" % rank), "w").write("ok")
+
+
+def test_data_parallel_trainer_world2_gloo(tmp_path):
+    world = 2
+    mp.start_processes(_dp_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True, start_method="spawn")
+    assert all(os.path.exists(os.path.join(str(tmp_path), "dp_ok%d" % r)) for r in range(world))

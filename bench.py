@@ -360,17 +360,26 @@ def run_cuda(args):
         if not verified:
             raise RuntimeError("bench self-check failed: rank counts differ from the oracle")
 
-    # sustained run (~1.5 s of back-to-back steps) so that nvidia-smi samples clocks UNDER LOAD
-    t_end = time.perf_counter() + (0.3 if args.lite else 1.5)
-    sustained_steps = 0
+    # sustained run (~1.5 s of back-to-back steps) so that nvidia-smi samples clocks UNDER LOAD.  The number of
+    # passes is fixed from one timed pass and agreed across ranks (MAX): a time-based loop would let the ranks
+    # run different numbers of steps, and the steps contain collectives.
     torch.cuda.synchronize()
+    t_p0 = time.perf_counter()
+    for i in range(args.warmup, total):
+        resident_step(i)
+    torch.cuda.synchronize()
+    one_pass = max(time.perf_counter() - t_p0, 1e-4)
+    n_pass = max(1, int((0.3 if args.lite else 1.5) / one_pass))
+    if world > 1:
+        t = torch.tensor([n_pass], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        n_pass = int(t.item())
     t_s0 = time.perf_counter()
-    while time.perf_counter() < t_end:
+    for _ in range(n_pass):
         for i in range(args.warmup, total):
             resident_step(i)
         torch.cuda.synchronize()
-        sustained_steps += args.steps
-    ms_sustained = (time.perf_counter() - t_s0) * 1e3 / max(sustained_steps, 1)
+    ms_sustained = (time.perf_counter() - t_s0) * 1e3 / (n_pass * args.steps)
     barrier()
     import gc
     gc.collect()

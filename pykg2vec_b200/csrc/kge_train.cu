@@ -41,15 +41,19 @@ train_hinge_kernel(ModelParams P, GradTablesT GT, const int64_t* __restrict__ ph
     TripleRows Rp, Rn;
     resolve_rows<MODEL>(Rp, P, P.tab, P.tab, P.tab, a, b, c);
     resolve_rows<MODEL>(Rn, P, P.tab, P.tab, P.tab, x, y, z);
-    const float sp = score_group<MODEL, VEC, KGE_GROUP_TAIL>(Rp, P, lane, scratch);
-    const float sn = score_group<MODEL, VEC, KGE_GROUP_TAIL>(Rn, P, lane, scratch);
+    // CHSEL = 0: the looped (not register-cached, not unrolled-by-width) forms of the score / gradient
+    // functions.  A training batch is a few hundred groups — pure latency —, and the cached forms made this
+    // kernel 12,760 instructions (204 KB): ncu showed it stalled on INSTRUCTION FETCH (no_instruction 8.9 per
+    // issue, 30 us for 512 pairs; profiles/r2_ncu_step_v2_summary.txt).  Same arithmetic order, same bits.
+    const float sp = score_group<MODEL, VEC, KGE_GROUP_TAIL, 0>(Rp, P, lane, scratch);
+    const float sn = score_group<MODEL, VEC, KGE_GROUP_TAIL, 0>(Rn, P, lane, scratch);
     v = fmaxf(fsub(fadd(sp, margin), sn), 0.f);  // Criterion.pairwise_hinge, criterion.py:26-29
     if (v > 0.f) {
       GradRows Gp, Gn;
       resolve_grad_rows<MODEL>(Gp, P, GT.t, a, b, c);
       resolve_grad_rows<MODEL>(Gn, P, GT.t, x, y, z);
-      grad_group<MODEL, VEC>(Rp, Gp, P, lane, 1.f, scratch);
-      grad_group<MODEL, VEC>(Rn, Gn, P, lane, -1.f, scratch);
+      grad_group<MODEL, VEC, 0>(Rp, Gp, P, lane, 1.f, scratch);
+      grad_group<MODEL, VEC, 0>(Rn, Gn, P, lane, -1.f, scratch);
     }
     if (lane != 0) v = 0.f;
   }
@@ -91,13 +95,13 @@ train_logistic_kernel(ModelParams P, GradTablesT GT, const int64_t* __restrict__
     const float yy = (float)__ldg(y + g);
     TripleRows R;
     resolve_rows<MODEL>(R, P, P.tab, P.tab, P.tab, a, b, c);
-    const float s = score_group<MODEL, VEC, KGE_GROUP_TAIL>(R, P, lane, scratch);
+    const float s = score_group<MODEL, VEC, KGE_GROUP_TAIL, 0>(R, P, lane, scratch);
     const float x = yy * s;
     v = tl_softplus(x) * inv_n;
     const float gs = (x > 20.f ? 1.f : tl_sigmoid(x)) * yy * inv_n;
     GradRows G;
     resolve_grad_rows<MODEL>(G, P, GT.t, a, b, c);
-    grad_group<MODEL, VEC>(R, G, P, lane, gs, scratch);
+    grad_group<MODEL, VEC, 0>(R, G, P, lane, gs, scratch);
     if (lane != 0) v = 0.f;
   }
 #pragma unroll

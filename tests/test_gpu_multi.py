@@ -119,10 +119,15 @@ def _dp_worker(rank, world, port, tmp):
         for mode, t_ in trs.items():
             for (ka, va), (kb, vb) in zip(t_.model.state_dict().items(), single.model.state_dict().items()):
                 np.testing.assert_allclose(va.cpu().numpy(), vb.cpu().numpy(), rtol=0, atol=3e-5, err_msg="%s %s %s %s" % (model_name, opt, mode, ka))
-                # replicas stay bit-identical to each other
+                # "grads": every rank applies the SAME all-reduced gradient -> replicas stay bit-identical;
+                # "ids": every rank accumulates the global batch itself with float atomics (unordered) -> equal to
+                # rounding only
                 other = va.clone()
                 dist.broadcast(other, src=0)
-                assert torch.equal(other, va), (model_name, opt, mode, ka)
+                if mode == "grads":
+                    assert torch.equal(other, va), (model_name, opt, mode, ka)
+                else:
+                    assert float((other - va).abs().max()) <= 1e-6, (model_name, opt, mode, ka)
     dist.barrier()
     dist.destroy_process_group()
     open(os.path.join(tmp, "dp_ok%d" % rank), "w").write("ok")

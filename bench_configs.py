@@ -30,6 +30,9 @@ CONFIGS = [
     ("cfg3_complex_wn18rr_d200", "complex", "wn18rr", dict(hidden_size=200, lmbda=1e-4), 512, 1, "adagrad", 512),
     ("cfg4_rotate_fb15k_d1000_neg256", "rotate", "fb15k", dict(hidden_size=1000, margin=24.0, alpha=1.0), 1024, 256, "adagrad", 512),
     ("cfg5_complex_yago310_d500", "complex", "yago3_10", dict(hidden_size=500, lmbda=1e-4), 512, 1, "adagrad", 512),
+    # the CLI's default optimizer (-opt adam, common.py:50): fused dense Adam (kge_optim_apply_dense)
+    ("cfg2_transe_fb15k237_d200_adam", "transe", "fb15k_237", dict(hidden_size=200, l1_flag=False, margin=5.0), 512, 1, "adam", 512),
+    ("cfg3_complex_wn18rr_d200_adam", "complex", "wn18rr", dict(hidden_size=200, lmbda=1e-4), 512, 1, "adam", 512),
 ]
 
 

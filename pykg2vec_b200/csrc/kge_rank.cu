@@ -92,7 +92,7 @@ filter_correct_kernel(ModelParams P, const int64_t* __restrict__ qh, const int64
     resolve_rows<MODEL>(R, P, P.qtab, P.tab, P.qtab, __ldg(qh + q), __ldg(qr + q), el);
   else
     resolve_rows<MODEL>(R, P, P.tab, P.qtab, P.qtab, el, __ldg(qr + q), __ldg(qt + q));
-  const float s = score_group<MODEL, VEC, GROUPING, 0>(R, P, lane, scratch);
+  const float s = score_group<MODEL, VEC, GROUPING>(R, P, lane, scratch);
   if (valid && !skip && lane == 0 && s < __ldg(thr + q)) atomicSub(counts + q * 4 + col + 1, 1);
 }
 
@@ -109,7 +109,7 @@ threshold_kernel(ModelParams P, const int64_t* __restrict__ qh, const int64_t* _
   const int64_t gi = valid ? g : Q - 1;
   TripleRows R;
   resolve_rows<MODEL>(R, P, P.qtab, P.qtab, P.qtab, __ldg(qh + gi), __ldg(qr + gi), __ldg(qt + gi));
-  const float s = score_group<MODEL, VEC, GROUPING, 0>(R, P, lane, scratch);
+  const float s = score_group<MODEL, VEC, GROUPING>(R, P, lane, scratch);
   if (valid && lane == 0) thr[g] = s;
 }
 
@@ -164,7 +164,7 @@ band_resolve_kernel(ModelParams P, const int64_t* __restrict__ qh, const int64_t
       resolve_rows<MODEL>(R, P, P.qtab, P.tab, P.qtab, __ldg(qh + q), __ldg(qr + q), e);
     else
       resolve_rows<MODEL>(R, P, P.tab, P.qtab, P.qtab, e, __ldg(qr + q), __ldg(qt + q));
-    const float s = score_group<MODEL, VEC, GROUPING, 0>(R, P, lane, scratch);
+    const float s = score_group<MODEL, VEC, GROUPING>(R, P, lane, scratch);
     if (lane == 0 && !skip && s < __ldg(thr + q)) {
       if (band) atomicAdd(tc_counts + q, 1);
       else atomicSub(counts + q * 4 + col + 1, 1);

@@ -69,7 +69,7 @@ struct TcParams {
   int tail_cols;
   uint32_t tail_bytes;     // bytes of one operand's tail tile (128 rows x tail_cols x 2)
 };
-struct TcMaps { CUtensorMap a0, a1, b0, b1, a0t, a1t, b0t, b1t; };
+struct TcMaps { CUtensorMap a0, a1, b0, b1, a0t, a1t, b0t, b1t; };   // in PAIR mode the b* boxes hold 64 rows
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 KGE_DEV uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -103,8 +103,26 @@ KGE_DEV void tc_tma_load_2d(uint32_t dst_smem, const CUtensorMap* tm, int col, i
       ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tm)), "r"(col), "r"(row), "r"(tc_smem_u32(bar))
       : "memory");
 }
+// the same tile delivered to the CTAs named by `mask` of this cluster (same CTA-relative smem offset and
+// mbarrier in each): one L2 read, one TMA row request, several destinations
+KGE_DEV void tc_tma_load_2d_mc(uint32_t dst_smem, const CUtensorMap* tm, int col, int row, uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%2, %3}], [%4], %5;"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tm)), "r"(col), "r"(row), "r"(tc_smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+KGE_DEV void tc_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 KGE_DEV void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 KGE_DEV void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// arrives on the mbarrier at `bar`'s offset in EVERY CTA of `mask` when the MMAs issued so far have completed
+KGE_DEV void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(tc_smem_u32(bar)), "h"(mask) : "memory");
+}
 KGE_DEV void tc_commit(uint64_t* bar) {   // arrives on `bar` when every MMA issued so far by this thread has completed
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
                ::"r"(tc_smem_u32(bar)) : "memory");
@@ -254,6 +272,12 @@ KGE_DEV int tc_scan_chunk(const uint32_t (&v)[32], int nv, float tau_hi, float t
 //   warps 2..9    : epilogue — warp w owns TMEM lanes 32*(w&3).. (= query rows) and the column half
 //                   (w-2)/4 of the tile (= 64 candidates), 32 columns per tcgen05.ld, compared with the row's
 //                   two thresholds
+// PAIR: launched as clusters of two CTAs (1 x 2 x 1: same candidate tiles, adjacent query blocks).  Each CTA
+// issues the TMA loads of HALF of every candidate k-block (64 of its 128 rows) and multicasts them into both
+// CTAs' stages, so an SM requests half the rows and the L2 is read once per pair — the operand stream was the
+// bound of the single-CTA kernel (~28 B/cycle per SM of TMA row requests).  A stage is refilled only when the
+// MMAs of BOTH CTAs have consumed it (tcgen05.commit multicast onto both empty barriers, count 2).
+template <bool PAIR>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMaps TM) {
   extern __shared__ unsigned char tc_smem_raw[];
@@ -282,7 +306,7 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
   if (threadIdx.x == 0) TC_STAMP(2, 63);   // kernel entry of CTA (0,0)
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < P.nstages; ++s) { tc_mbar_init(&full[s], 1); tc_mbar_init(&empty[s], 1); }
+    for (int s = 0; s < P.nstages; ++s) { tc_mbar_init(&full[s], 1); tc_mbar_init(&empty[s], PAIR ? 2 : 1); }
     tc_mbar_init(a_full, 1);
     for (int s = 0; s < 2; ++s) { tc_mbar_init(&tmem_full[s], 1); tc_mbar_init(&tmem_empty[s], kTcEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -296,7 +320,9 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (PAIR) tc_cluster_sync();   // the peer's barriers exist before anything of ours can reach them
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  const uint32_t crank = PAIR ? (blockIdx.y & 1u) : 0u;   // rank in the (1,2,1) cluster
 
   if (warp == 0) {
     if (lane == 0) {
@@ -322,8 +348,15 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
           TC_STAMP(0, ev++);
           tc_mbar_expect_tx(&full[stage], (P.a_resident ? 2u : 4u) * tb);
           const uint32_t sb = st_base + (uint32_t)stage * st_bytes;
-          tc_tma_load_2d(sb, tail ? &TM.b0t : &TM.b0, kb * P.bk, row, &full[stage]);
-          tc_tma_load_2d(sb + tb, tail ? &TM.b1t : &TM.b1, kb * P.bk, row, &full[stage]);
+          if (PAIR) {   // my half of the candidate rows, into both CTAs (the peer sends the other half)
+            const uint32_t ho = crank * (tb >> 1);
+            const int hrow = row + (int)crank * (kTcBN / 2);
+            tc_tma_load_2d_mc(sb + ho, tail ? &TM.b0t : &TM.b0, kb * P.bk, hrow, &full[stage], (uint16_t)3);
+            tc_tma_load_2d_mc(sb + tb + ho, tail ? &TM.b1t : &TM.b1, kb * P.bk, hrow, &full[stage], (uint16_t)3);
+          } else {
+            tc_tma_load_2d(sb, tail ? &TM.b0t : &TM.b0, kb * P.bk, row, &full[stage]);
+            tc_tma_load_2d(sb + tb, tail ? &TM.b1t : &TM.b1, kb * P.bk, row, &full[stage]);
+          }
           if (!P.a_resident) {
             tc_tma_load_2d(sb + 2u * tb, tail ? &TM.a0t : &TM.a0, kb * P.bk, (int)q0, &full[stage]);
             tc_tma_load_2d(sb + 3u * tb, tail ? &TM.a1t : &TM.a1, kb * P.bk, (int)q0, &full[stage]);
@@ -365,7 +398,8 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
             tc_mma(d_tmem, da0 + ko, db1 + ko, kTcIdesc, 1u);
             tc_mma(d_tmem, da1 + ko, db0 + ko, kTcIdesc, 1u);
           }
-          tc_commit(&empty[stage]);                         // smem stage reusable once these MMAs are done
+          if (PAIR) tc_commit_mc(&empty[stage], (uint16_t)3);   // both CTAs' producers write this stage: tell both
+          else tc_commit(&empty[stage]);                    // smem stage reusable once these MMAs are done
           if (kb == P.nkb - 1) tc_commit(&tmem_full[as]);   // ... and the accumulator is complete
           if (++stage == P.nstages) { stage = 0; phase ^= 1u; }
         }
@@ -418,6 +452,7 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) tc_cluster_sync();   // neither CTA leaves while the peer can still multicast into it / arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTcTmemCols) : "memory");
@@ -553,12 +588,12 @@ static TcEncodeFn tc_encode_fn() {
 }
 // bf16 matrix [rows][Kp] row-major; box = {64 columns (128 bytes), 128 rows}, 128-byte swizzle, zero fill
 // (box_cols = 64: one 128-byte swizzle row; 32 / 16: the narrow tile of an exact-width last k-block)
-static int tc_make_map(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t Kp, int box_cols) {
+static int tc_make_map(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t Kp, int box_cols, int box_rows = kTcBN) {
   TcEncodeFn fn = tc_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled is not available"); return KGE_ECUDA; }
   const cuuint64_t gdim[2] = {Kp, rows};
   const cuuint64_t gstride[1] = {Kp * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)kTcBN};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUtensorMapSwizzle sw = box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                               : (box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
@@ -672,24 +707,48 @@ int tc_sweep(const kge_model_t* m, int dir, int64_t Q, int64_t nc, void* tcws, T
   P.trace = g_tc_trace;
   P.epi_mode = 0;
   if (const char* e = getenv("KGE_TC_EPI_MODE")) P.epi_mode = atoi(e);   // measurement aid: wrong counts unless 0
+  // pair mode: two query blocks share every candidate tile through TMA multicast (needs >= 2 query blocks'
+  // worth of work to pay: Q > 128); KGE_TC_PAIR=0 / 1 forces it off / on (tests run both)
+  bool pair = qblocks >= 2;
+  if (const char* e = getenv("KGE_TC_PAIR")) pair = atoi(e) != 0;
+  const int brows = pair ? kTcBN / 2 : kTcBN;
   TcMaps TM;
   int rc = tc_make_map(&TM.a0, A0, (uint64_t)Q, (uint64_t)Kp, bk); if (rc) return rc;
   rc = tc_make_map(&TM.a1, A1, (uint64_t)Q, (uint64_t)Kp, bk); if (rc) return rc;
-  rc = tc_make_map(&TM.b0, w + L.b[0], (uint64_t)nc, (uint64_t)Kp, bk); if (rc) return rc;
-  rc = tc_make_map(&TM.b1, w + L.b[1], (uint64_t)nc, (uint64_t)Kp, bk); if (rc) return rc;
+  rc = tc_make_map(&TM.b0, w + L.b[0], (uint64_t)nc, (uint64_t)Kp, bk, brows); if (rc) return rc;
+  rc = tc_make_map(&TM.b1, w + L.b[1], (uint64_t)nc, (uint64_t)Kp, bk, brows); if (rc) return rc;
   TM.a0t = TM.a0; TM.a1t = TM.a1; TM.b0t = TM.b0; TM.b1t = TM.b1;
   if (P.tail_cols) {
     rc = tc_make_map(&TM.a0t, A0, (uint64_t)Q, (uint64_t)Kp, P.tail_cols); if (rc) return rc;
     rc = tc_make_map(&TM.a1t, A1, (uint64_t)Q, (uint64_t)Kp, P.tail_cols); if (rc) return rc;
-    rc = tc_make_map(&TM.b0t, w + L.b[0], (uint64_t)nc, (uint64_t)Kp, P.tail_cols); if (rc) return rc;
-    rc = tc_make_map(&TM.b1t, w + L.b[1], (uint64_t)nc, (uint64_t)Kp, P.tail_cols); if (rc) return rc;
+    rc = tc_make_map(&TM.b0t, w + L.b[0], (uint64_t)nc, (uint64_t)Kp, P.tail_cols, brows); if (rc) return rc;
+    rc = tc_make_map(&TM.b1t, w + L.b[1], (uint64_t)nc, (uint64_t)Kp, P.tail_cols, brows); if (rc) return rc;
   }
   const size_t smem = 2048 + a_bytes + (size_t)nstages * st_bytes;
-  KGE_CUDA_OK(cudaFuncSetAttribute(tc_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   SweepProfile* sp = sweep_profile(dir);
-  if (sp->armed) KGE_CUDA_OK(cudaEventRecord(sp->beg, st));
-  tc_sweep_kernel<<<dim3((unsigned)splits, (unsigned)qblocks), kTcThreads, smem, st>>>(P, TM);
-  KGE_CHECK_LAUNCH("tc_sweep_kernel");
+  if (pair) {
+    // clusters of (1, 2, 1): the grid's query-block dimension is padded to an even count (a padding CTA has
+    // no live rows: its operand rows arrive zero-filled, its thresholds are +inf, it only relays its half loads)
+    const unsigned qb2 = (unsigned)((qblocks + 1) & ~1);
+    KGE_CUDA_OK(cudaFuncSetAttribute(tc_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)splits, qb2, 1);
+    cfg.blockDim = dim3(kTcThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 2; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (sp->armed) KGE_CUDA_OK(cudaEventRecord(sp->beg, st));
+    KGE_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_sweep_kernel<true>, P, TM));
+    KGE_CHECK_LAUNCH("tc_sweep_kernel<pair>");
+  } else {
+    KGE_CUDA_OK(cudaFuncSetAttribute(tc_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (sp->armed) KGE_CUDA_OK(cudaEventRecord(sp->beg, st));
+    tc_sweep_kernel<false><<<dim3((unsigned)splits, (unsigned)qblocks), kTcThreads, smem, st>>>(P, TM);
+    KGE_CHECK_LAUNCH("tc_sweep_kernel");
+  }
   if (sp->armed) { KGE_CUDA_OK(cudaEventRecord(sp->end, st)); sp->valid = true; }
   out->tc_counts = cnt; out->ctrl = ctrl; out->list = list; out->cap = P.cap; out->tau = tau;
   return KGE_OK;

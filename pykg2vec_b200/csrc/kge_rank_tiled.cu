@@ -410,7 +410,7 @@ prep_query_kernel(ModelParams P, const int64_t* __restrict__ qh, const int64_t* 
   TripleRows R;
   resolve_rows<MODEL>(R, P, P.qtab, P.qtab, P.qtab, __ldg(qh + q), __ldg(qr + q), __ldg(qt + q));
   // threshold = the target's own score in this direction's grouping (== kge_score_fwd)
-  const float s_target = score_group<MODEL, VEC, DIR == 0 ? KGE_GROUP_TAIL : KGE_GROUP_HEAD, 0>(R, P, lane, scratch);
+  const float s_target = score_group<MODEL, VEC, DIR == 0 ? KGE_GROUP_TAIL : KGE_GROUP_HEAD>(R, P, lane, scratch);
   if (lane == 0) thr[q] = s_target;
   constexpr int KQ = (MODEL == KGE_COMPLEX || MODEL == KGE_SIMPLE || MODEL == KGE_SIMPLE_IGNR)
                          ? 2 : (MODEL == KGE_ROTATE ? 2 : 1);

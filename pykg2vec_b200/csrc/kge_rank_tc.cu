@@ -46,7 +46,7 @@ constexpr int kTcBN = 128;        // candidates per tile (UMMA N)
 constexpr int kTcBKMax = 64;      // bf16 elements per k-block: 64 (128-byte swizzle rows) or 32 (64-byte rows; twice the stages)
 constexpr int kTcThreads = 320;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue
 constexpr int kTcEpiWarps = 8;    // two warps per TMEM lane quadrant, each scanning half of the tile's columns
-constexpr int kTcTmemCols = 256;  // two accumulator stages of kTcBN fp32 columns
+constexpr int kTcTmemCols = 256;  // two accumulator stages of kTcBN fp32 columns (+ 256 for the query operands in a_tmem mode)
 constexpr int kTcMaxStages = 8;
 constexpr int kTcResidentMaxK = 256;                   // query block stays in smem when Kp <= 256
 
@@ -59,6 +59,8 @@ struct TcParams {
   int64_t Q, nc;
   int Kp, nkb, a_resident, nstages;
   int bk;                  // k-block width in bf16 elements (64 or 32)
+  int a_tmem;              // the query block's operands live in TENSOR MEMORY (Kp <= 256): only the candidate tiles use smem
+  const __nv_bfloat16* A0; const __nv_bfloat16* A1;   // [Q][Kp] query operands (read by the TMEM fill)
   uint32_t tile_bytes;     // one operand k-block tile: 128 rows x bk x 2 bytes
   int tiles_per_cta, ntiles;
   float* dbg;              // optional [Q][nc] raw accumulators (tests)
@@ -135,6 +137,21 @@ KGE_DEV void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t id
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// same with the A operand read from tensor memory (row i in lane i, two bf16 per 32-bit column): the
+// shared-memory traffic of an MMA halves (only B), which is what bounded the all-smem form at N = 128
+KGE_DEV void tc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+KGE_DEV void tc_tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+KGE_DEV void tc_tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // shared-memory matrix descriptor: K-major operand tile [rows][64 bf16] written by TMA with the
 // 128-byte swizzle.  start address >> 4 in bits [0,14); leading byte offset (unused for swizzled
 // K-major, canonical value 1) in [16,30); stride byte offset = 8 rows x 128 B = 1024 (>> 4) in
@@ -295,7 +312,7 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
   uint64_t* const tmem_empty = tmem_full + 2;                   // [2]
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(gbase + 512);
   const uint32_t a_base = base + 1024u;                                            // resident query k-blocks
-  const uint32_t a_bytes = !P.a_resident ? 0u
+  const uint32_t a_bytes = (!P.a_resident || P.a_tmem) ? 0u
       : (P.tail_cols ? (uint32_t)(P.nkb - 1) * 2u * P.tile_bytes + 2u * P.tail_bytes : (uint32_t)P.nkb * 2u * P.tile_bytes);
   const uint32_t st_base = a_base + a_bytes;
   const uint32_t st_bytes = (P.a_resident ? 2u : 4u) * P.tile_bytes;              // [B0][B1]([A0][A1])
@@ -307,14 +324,14 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.nstages; ++s) { tc_mbar_init(&full[s], 1); tc_mbar_init(&empty[s], PAIR ? 2 : 1); }
-    tc_mbar_init(a_full, 1);
+    tc_mbar_init(a_full, P.a_tmem ? (uint32_t)kTcEpiWarps : 1u);
     for (int s = 0; s < 2; ++s) { tc_mbar_init(&tmem_full[s], 1); tc_mbar_init(&tmem_empty[s], kTcEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {   // TMEM allocation is warp-collective; the same warp frees it
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                 ::"r"(tc_smem_u32(tmem_slot)), "r"((uint32_t)kTcTmemCols) : "memory");
+                 ::"r"(tc_smem_u32(tmem_slot)), "r"((uint32_t)(P.a_tmem ? 2 * kTcTmemCols : kTcTmemCols)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -326,7 +343,7 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
 
   if (warp == 0) {
     if (lane == 0) {
-      if (P.a_resident) {
+      if (P.a_resident && !P.a_tmem) {
         tc_mbar_expect_tx(a_full, a_bytes);
         for (int kb = 0; kb < P.nkb; ++kb) {
           const bool tail = P.tail_cols && kb == P.nkb - 1;
@@ -369,7 +386,7 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
     if (lane == 0) {
       int ev = 0;
       TC_STAMP(1, ev++);
-      if (P.a_resident) { tc_mbar_wait(a_full, 0u); }
+      if (P.a_resident) { tc_mbar_wait(a_full, 0u); tc_fence_after(); }
       TC_STAMP(1, ev++);
       int stage = 0; uint32_t phase = 0;
       for (int t = 0; t < ntl; ++t) {
@@ -392,6 +409,17 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
           const int nks = tail ? P.tail_cols / 16 : min(P.bk / 16, (P.Kp - kb * P.bk + 15) / 16);
           const uint64_t da0 = tc_smem_desc(a0, rowb), da1 = tc_smem_desc(a1, rowb), db0 = tc_smem_desc(b0, rowb),
                          db1 = tc_smem_desc(b1, rowb);
+          if (P.a_tmem) {
+            // query operands in tensor memory: a0 at columns [256, 256 + Kp/2), a1 right behind; a k-step is 8 columns
+            const uint32_t ta0 = tmem_base + (uint32_t)(2 * kTcBN) + (uint32_t)((kb * P.bk) >> 1);
+            const uint32_t ta1 = ta0 + (uint32_t)(P.Kp >> 1);
+            for (int k = 0; k < nks; ++k) {
+              const uint64_t ko = (uint64_t)(2 * k);
+              tc_mma_ts(d_tmem, ta0 + 8u * k, db0 + ko, kTcIdesc, (kb | k) != 0 ? 1u : 0u);
+              tc_mma_ts(d_tmem, ta0 + 8u * k, db1 + ko, kTcIdesc, 1u);
+              tc_mma_ts(d_tmem, ta1 + 8u * k, db0 + ko, kTcIdesc, 1u);
+            }
+          } else
           for (int k = 0; k < nks; ++k) {   // 16 bf16 = 32 bytes further along the swizzled row: +2 in the address field
             const uint64_t ko = (uint64_t)(2 * k);
             tc_mma(d_tmem, da0 + ko, db0 + ko, kTcIdesc, (kb | k) != 0 ? 1u : 0u);
@@ -412,6 +440,26 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
     const bool live = q < P.Q;
     const float tau_hi = live ? __ldg(P.tau + 2 * q) : INFINITY;
     const float tau_lo = live ? __ldg(P.tau + 2 * q + 1) : INFINITY;
+    if (P.a_tmem) {
+      // this thread's query row -> tensor memory: warps 2-5 write the high parts a0, warps 6-9 the low parts a1;
+      // a row is Kp bf16 = Kp/2 32-bit columns (two consecutive k per column), rows beyond Q are zeros
+      const int half = (warp - 2) >> 2;
+      const __nv_bfloat16* src = (half == 0 ? P.A0 : P.A1) + (size_t)(live ? q : 0) * P.Kp;
+      const uint32_t tdst = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(2 * kTcBN) + (uint32_t)(half * (P.Kp >> 1));
+      for (int c = 0; c < (P.Kp >> 1); c += 8) {   // Kp is a multiple of 16: whole groups of 8 columns
+        uint4 lo = make_uint4(0u, 0u, 0u, 0u), hi = lo;
+        if (live) {
+          lo = __ldg(reinterpret_cast<const uint4*>(src + 2 * c));
+          hi = __ldg(reinterpret_cast<const uint4*>(src + 2 * c + 8));
+        }
+        const uint32_t v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        tc_tmem_st8(tdst + (uint32_t)c, v);
+      }
+      tc_tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc_mbar_arrive(a_full);
+    }
     int cnt = 0;
     TcListState L = {0u, 0u, 0u};
     int ev = 0;
@@ -455,7 +503,7 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
   if (PAIR) tc_cluster_sync();   // neither CTA leaves while the peer can still multicast into it / arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTcTmemCols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(P.a_tmem ? 2 * kTcTmemCols : kTcTmemCols)) : "memory");
   }
 }
 
@@ -688,8 +736,12 @@ int tc_sweep(const kge_model_t* m, int dir, int64_t Q, int64_t nc, void* tcws, T
     if (const char* e = getenv("KGE_TC_TAIL")) { if (atoi(e) == 0) P.tail_cols = 0; }   // tuning / test aid
     P.tail_bytes = (uint32_t)(kTcBN * P.tail_cols * 2);
   }
+  // query operands in tensor memory when they fit beside the two accumulators (2 x Kp/2 <= 256 columns)
+  P.a_tmem = (P.a_resident && Kp <= 256) ? 1 : 0;
+  if (const char* e = getenv("KGE_TC_ATMEM")) { if (atoi(e) == 0) P.a_tmem = 0; }   // tuning / test aid
+  P.A0 = A0; P.A1 = A1;
   const size_t budget = 227 * 1024 - 2048;   // control block + alignment slack
-  const size_t a_bytes = !P.a_resident ? 0
+  const size_t a_bytes = (!P.a_resident || P.a_tmem) ? 0
       : (P.tail_cols ? (size_t)(P.nkb - 1) * 2 * P.tile_bytes + 2 * (size_t)P.tail_bytes : (size_t)P.nkb * 2 * P.tile_bytes);
   const size_t st_bytes = (P.a_resident ? 2 : 4) * (size_t)P.tile_bytes;
   int nstages = (int)((budget - a_bytes) / st_bytes);

@@ -242,14 +242,15 @@ def test_tensor_core_sweep_ragged_geometries(model, N, d, Q, monkeypatch):
             L.normalize_rows(t)
         om = oracle.Model("rescal", [t.cpu().numpy() for t in desc.tables], d)
     want = oracle.rank_1vsall(om, qh, qr, qt, ft, fh)
-    for flags, tail, bk, pair in ((0, "1", "64", "1"), (0, "1", "64", "0"), (0, "0", "64", "1"), (0, "1", "32", "1"), (0, "0", "32", "0"),
-                                  (L.RANK_NO_TC, "1", "64", "1"), (8, "1", "64", "1")):
+    for flags, tail, bk, pair, atmem in ((0, "1", "64", "1", "1"), (0, "1", "64", "0", "1"), (0, "1", "64", "1", "0"), (0, "0", "64", "0", "0"),
+                                         (0, "1", "32", "1", "1"), (0, "0", "32", "0", "0"), (L.RANK_NO_TC, "1", "64", "1", "1"), (8, "1", "64", "1", "1")):
         monkeypatch.setenv("KGE_TC_TAIL", tail)
         monkeypatch.setenv("KGE_TC_BK", bk)
         monkeypatch.setenv("KGE_TC_PAIR", pair)
+        monkeypatch.setenv("KGE_TC_ATMEM", atmem)
         got = L.rank_1vsall(desc, _cuda(qh), _cuda(qr), _cuda(qt), (_cuda(ft[0]), _cuda(ft[1])),
                             (_cuda(fh[0]), _cuda(fh[1])), flags=flags).cpu().numpy()
-        np.testing.assert_array_equal(got, want, err_msg="flags %d tail %s bk %s pair %s" % (flags, tail, bk, pair))
+        np.testing.assert_array_equal(got, want, err_msg="flags %d tail %s bk %s pair %s atmem %s" % (flags, tail, bk, pair, atmem))
 
 
 def test_config5_row_shards_on_one_gpu():

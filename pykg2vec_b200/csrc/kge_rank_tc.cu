@@ -736,9 +736,12 @@ int tc_sweep(const kge_model_t* m, int dir, int64_t Q, int64_t nc, void* tcws, T
     if (const char* e = getenv("KGE_TC_TAIL")) { if (atoi(e) == 0) P.tail_cols = 0; }   // tuning / test aid
     P.tail_bytes = (uint32_t)(kTcBN * P.tail_cols * 2);
   }
-  // query operands in tensor memory when they fit beside the two accumulators (2 x Kp/2 <= 256 columns)
-  P.a_tmem = (P.a_resident && Kp <= 256) ? 1 : 0;
-  if (const char* e = getenv("KGE_TC_ATMEM")) { if (atoi(e) == 0) P.a_tmem = 0; }   // tuning / test aid
+  // query operands in tensor memory (KGE_TC_ATMEM=1; they fit beside the two accumulators when 2 x Kp/2 <= 256
+  // columns): halves the shared-memory reads of an MMA and frees 104 KB for 7 candidate stages.  Correct (tests
+  // run both) but measured slower (26.6 vs 24.6 us): the per-thread fill of tensor memory costs ~5 us of prologue
+  // and the MMA cadence does not change — shared-memory bandwidth was not the bound either.
+  P.a_tmem = 0;
+  if (const char* e = getenv("KGE_TC_ATMEM")) { if (atoi(e) != 0 && P.a_resident && Kp <= 256) P.a_tmem = 1; }
   P.A0 = A0; P.A1 = A1;
   const size_t budget = 227 * 1024 - 2048;   // control block + alignment slack
   const size_t a_bytes = (!P.a_resident || P.a_tmem) ? 0
@@ -759,9 +762,11 @@ int tc_sweep(const kge_model_t* m, int dir, int64_t Q, int64_t nc, void* tcws, T
   P.trace = g_tc_trace;
   P.epi_mode = 0;
   if (const char* e = getenv("KGE_TC_EPI_MODE")) P.epi_mode = atoi(e);   // measurement aid: wrong counts unless 0
-  // pair mode: two query blocks share every candidate tile through TMA multicast (needs >= 2 query blocks'
-  // worth of work to pay: Q > 128); KGE_TC_PAIR=0 / 1 forces it off / on (tests run both)
-  bool pair = qblocks >= 2;
+  // pair mode (KGE_TC_PAIR=1): two query blocks share every candidate tile through TMA multicast.  Correct
+  // (tests run both) but measured NOT faster (24.6 vs 22.5-24.6 us, profiles/r2_tc_trace_v7_pair.jsonl,
+  // r2_tc_trace_v8_modes.txt): the k-block cadence is set by the tensor pipe (~100 cycles per 128x128x16
+  // tcgen05.mma, ~85 % of the per-SM bf16 rate the measured cuBLAS peak implies), not by the operand stream.
+  bool pair = false;
   if (const char* e = getenv("KGE_TC_PAIR")) pair = atoi(e) != 0;
   const int brows = pair ? kTcBN / 2 : kTcBN;
   TcMaps TM;

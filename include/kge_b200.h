@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define KGE_ABI_VERSION 4
+#define KGE_ABI_VERSION 5
 #define KGE_MAX_TABLES 16
 
 /* status codes */
@@ -171,6 +171,19 @@ int kge_train_pointwise_logistic(const kge_model_t* m, float* const* grad_scratc
                                  const int64_t* r, const int64_t* t, const int64_t* y, int64_t n,
                                  float* loss_out, void* stream);
 
+/* kge_train_pairwise_selfadv: Trainer.train_step_pairwise for RotatE (trainer.py:147-157):
+ * pos = model(pos triples) [B], neg = model(neg triples) [B * neg_rate] (the negatives of positive i are
+ * neg[i*neg_rate .. (i+1)*neg_rate), generator.py:94-121), loss = Criterion.pariwise_logistic(pos, neg,
+ * neg_rate, alpha) — the self-adversarial loss, criterion.py:14-23, softmax weights detached — and backward, in
+ * ONE kernel (a warp owns a positive with its negatives).  loss_out[0] receives the batch loss (the same bits
+ * as kge_loss_selfadv on the same scores); the row gradients are ACCUMULATED into grad_scratch[k].
+ * KGE_ENOTSUP for other models, and when neg_rate needs more shared memory than a CTA has (then use
+ * kge_score_fwd + kge_loss_selfadv + kge_score_bwd). */
+int kge_train_pairwise_selfadv(const kge_model_t* m, float* const* grad_scratch, const int64_t* pos_h,
+                               const int64_t* pos_r, const int64_t* pos_t, const int64_t* neg_h,
+                               const int64_t* neg_r, const int64_t* neg_t, int64_t B, int32_t neg_rate,
+                               float alpha, float* loss_out, void* stream);
+
 /* Sparse optimizer.step() for the rows touched by the triples (h[i], r[i], t[i]):
  * takes the accumulated row gradients out of grad_scratch (as filled by
  * kge_score_bwd / kge_reg_fwd_bwd; left zero-filled) and applies
@@ -245,11 +258,13 @@ int kge_debug_set_tc_trace(long long* buf);
 /* Two-level exact sweep (TransE -l1 False, DistMult, CP, ComplEx, RESCAL, RotatE; >= 1024 candidate rows):
  * level 1 evaluates the Q x N x K contraction on the tensor cores (tcgen05.mma, bf16 x 3 split, fp32
  * accumulation in TMEM) and counts every candidate whose accumulator clears the query's threshold by
- * more than a proven error bound; level 2 re-evaluates the few (query, candidate) pairs inside the
+ * more than a proven error bound of that (query, candidate) pair; level 2 re-evaluates the few (query, candidate) pairs inside the
  * band in the canonical fp32 arithmetic.  The counts equal the fp32 specification's for every input
  * (DESIGN.md §4b).  kge_rank_tc_probe exposes level 1 of ONE direction (0 tail, 1 head) for tests and
- * measurements: dots[Q * (row_hi-row_lo)] receives the raw accumulators D(q, c) (may be NULL), tau[Q*2]
- * the per-query thresholds (certainly better: D > tau[2q]; certainly not: D < tau[2q+1]; may be NULL);
+ * measurements: dots[Q * (row_hi-row_lo)] receives the raw accumulators D(q, c) (may be NULL);
+ * tau[Q*4 + (row_hi-row_lo)] (may be NULL) the band: per query (centre, a, b, e), then per candidate its norm
+ * bound n_c — half(q,c) = a + b n_c + e n_c^2; certainly better: D - centre > half; certainly not:
+ * D - centre < -half; otherwise the pair is resolved exactly;
  * counts[Q*4] is accumulated exactly as by kge_rank_1vsall (raw and "filtered" columns both get the raw
  * count: no filter pass here).  KGE_ENOTSUP when the model / table size has no tensor-core sweep. */
 int kge_rank_tc_probe(const kge_model_t* m, const kge_model_t* mq, int64_t row_lo, int64_t row_hi,

@@ -11,7 +11,8 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_build", "libkge_b200.so")
 MAX_TABLES = 16
-ABI_VERSION = 4
+ABI_VERSION = 5
+ENOTSUP = -2   # include/kge_b200.h KGE_ENOTSUP
 
 MODEL_IDS = {
     "transe": 0, "transh": 1, "transd": 2, "transr": 3, "rotate": 4, "hole": 5,
@@ -27,7 +28,7 @@ EXPORTS = [
     "kge_abi_version", "kge_version", "kge_last_error", "kge_launch_count",
     "kge_score_fwd", "kge_score_bwd", "kge_normalize_rows",
     "kge_loss_pairwise_hinge", "kge_loss_pointwise_logistic", "kge_loss_selfadv", "kge_reg_fwd_bwd",
-    "kge_train_pairwise_hinge_sgd", "kge_train_pointwise_logistic", "kge_optim_apply_rows", "kge_optim_apply_dense",
+    "kge_train_pairwise_hinge_sgd", "kge_train_pointwise_logistic", "kge_train_pairwise_selfadv", "kge_optim_apply_rows", "kge_optim_apply_dense",
     "kge_rank_workspace_bytes", "kge_rank_1vsall", "kge_rank_tc_probe", "kge_rank_last_sweep_ms", "kge_debug_set_tc_trace",
     "kge_tripleset_capacity", "kge_tripleset_build", "kge_sample_negatives",
     "kge_proj_tail_fwd", "kge_proj_tail_bwd", "kge_proj_bce", "kge_proj_rank_workspace_bytes", "kge_proj_rank", "kge_proj_labels",
@@ -46,6 +47,11 @@ class KgeModel(ctypes.Structure):
 
 class KgeError(RuntimeError):
     pass
+
+
+class KgeNotSupported(KgeError):
+    """KGE_ENOTSUP: the entry point has no kernel for this model / shape (callers with an alternative path
+    catch exactly this; every other error propagates)."""
 
 
 _lib = None
@@ -76,7 +82,7 @@ def lib():
 
 def check(rc, what):
     if rc != 0:
-        raise KgeError("%s failed (%d): %s" % (what, rc, lib().kge_last_error().decode()))
+        raise (KgeNotSupported if rc == ENOTSUP else KgeError)("%s failed (%d): %s" % (what, rc, lib().kge_last_error().decode()))
 
 
 def _ptr(t):
@@ -237,6 +243,25 @@ def train_pointwise_logistic(desc, grad_scratch, h, r, t, y, loss_out=None):
     return loss_out
 
 
+def train_pairwise_selfadv(desc, grad_scratch, ph, pr, pt, nh, nr, nt, neg_rate, alpha, loss_out=None):
+    """RotatE: forward of the positives and their negatives + the self-adversarial loss + backward in one kernel:
+    returns the loss [1]; row gradients are accumulated into grad_scratch.  KgeError (KGE_ENOTSUP) when neg_rate
+    does not fit a CTA's shared memory — the caller then takes the unfused path."""
+    if loss_out is None:
+        loss_out = torch.empty(1, dtype=torch.float32, device=ph.device)
+    if nh.numel() != ph.numel() * int(neg_rate):
+        raise KgeError("self-adversarial loss: %d negatives for %d positives x neg_rate %d"
+                       % (nh.numel(), ph.numel(), int(neg_rate)))
+    m = desc.c_struct()
+    gs = _table_ptr_array(grad_scratch)
+    check(lib().kge_train_pairwise_selfadv(
+        ctypes.byref(m), gs, _ptr(_dev_i64(ph, "ph")), _ptr(_dev_i64(pr, "pr")), _ptr(_dev_i64(pt, "pt")),
+        _ptr(_dev_i64(nh, "nh")), _ptr(_dev_i64(nr, "nr")), _ptr(_dev_i64(nt, "nt")), ctypes.c_int64(ph.numel()),
+        ctypes.c_int32(int(neg_rate)), ctypes.c_float(float(alpha)), _ptr(loss_out), _stream()),
+        "kge_train_pairwise_selfadv")
+    return loss_out
+
+
 def optim_apply_rows(desc, grad_scratch, state, optimizer, h, r, t, lr, eps=1e-10):
     """optimizer: 0 SGD, 1 Adagrad.  Consumes (and re-zeroes) grad_scratch for the touched rows."""
     m = desc.c_struct()
@@ -308,14 +333,16 @@ def rank_last_sweep_ms(direction):
 
 def rank_tc_probe(desc, qh, qr, qt, direction, want_dots=True, query_desc=None, row_lo=0, row_hi=None):
     """Level 1 (tensor cores) of the two-level exact sweep for ONE direction (include/kge_b200.h):
-    -> (dots [Q, nc] raw accumulators or None, tau [Q,2] (hi, lo), counts [Q,4])."""
+    -> (dots [Q, nc] raw accumulators or None, band, counts [Q,4]); band = (coef [Q,4] = centre, a, b, e per
+    query, cn [nc] = norm bound per candidate): the pair (q, c) is certainly better when
+    dots - centre > a + b cn + e cn^2, certainly not when dots - centre < -(a + b cn + e cn^2)."""
     qh, qr, qt = _dev_i64(qh, "qh"), _dev_i64(qr, "qr"), _dev_i64(qt, "qt")
     Q = qh.numel()
     if row_hi is None:
         row_hi = row_lo + desc.num_ent
     nc = row_hi - row_lo
     dots = torch.empty((Q, nc), dtype=torch.float32, device=qh.device) if want_dots else None
-    tau = torch.empty((Q, 2), dtype=torch.float32, device=qh.device)
+    tau = torch.empty(Q * 4 + nc, dtype=torch.float32, device=qh.device)
     counts = torch.zeros((Q, 4), dtype=torch.int32, device=qh.device)
     ws = torch.empty(max(rank_workspace_bytes(desc, Q), 16), dtype=torch.uint8, device=qh.device)
     m = desc.c_struct()
@@ -324,7 +351,7 @@ def rank_tc_probe(desc, qh, qr, qt, direction, want_dots=True, query_desc=None, 
         ctypes.byref(m), ctypes.byref(mq) if mq is not None else None, ctypes.c_int64(row_lo), ctypes.c_int64(row_hi),
         _ptr(qh), _ptr(qr), _ptr(qt), ctypes.c_int64(Q), ctypes.c_int(direction), _ptr(dots), _ptr(tau),
         _ptr(counts), _ptr(ws), ctypes.c_int64(ws.numel()), _stream()), "kge_rank_tc_probe")
-    return dots, tau, counts
+    return dots, (tau[:Q * 4].view(Q, 4), tau[Q * 4:]), counts
 
 
 def project_entities(desc, r, out=None):

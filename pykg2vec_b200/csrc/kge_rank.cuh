@@ -14,7 +14,8 @@ int tiled_prepare_candidates(const kge_model_t* m, int64_t nc, void* ws, int64_t
 // #{e < nc : score(q, e) < thr[q]} to counts[q*4+col] and counts[q*4+col+1].
 // use_tc: level 1 on the tensor cores + exact resolution of the ambiguous pairs (kge_rank_tc.cu);
 // the fp32 sweep is still enqueued but returns at once unless the pair list overflowed.
-// tc_dbg (tests): optional [Q][nc] raw tensor-core accumulators; tc_tau_out: optional [Q][2] thresholds.
+// tc_dbg (tests): optional [Q][nc] raw tensor-core accumulators; tc_tau_out: optional [Q][4] band
+// coefficients followed by the nc candidate norm bounds.
 struct RankFilter;
 int tiled_sweep(const kge_model_t* m, const kge_model_t* mq, int dir, const int64_t* qh,
                 const int64_t* qr, const int64_t* qt, float* thr, int64_t Q, int64_t nc,
@@ -32,7 +33,8 @@ struct TcDirBuffers {
   unsigned* ctrl;              // [0] pair-list length, [1] overflow, [2] ticket, [3] run-the-fp32-sweep flag
   unsigned long long* list;    // (q << 32 | local candidate row)
   unsigned cap;
-  const float* tau;            // [Q][2] accumulator thresholds (hi, lo)
+  const float* tau;            // [Q][4] band coefficients (centre, a, b, e) of tc_query_finish
+  const float* cn;             // [nc] candidate norm bounds
 };
 void tc_set_trace(long long* buf);
 bool tc_supported(const kge_model_t* m, int64_t nc);

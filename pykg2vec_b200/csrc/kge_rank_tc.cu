@@ -51,7 +51,8 @@ constexpr int kTcMaxStages = 8;
 constexpr int kTcResidentMaxK = 256;                   // query block stays in smem when Kp <= 256
 
 struct TcParams {
-  const float* tau;        // [Q][2]: tau_hi, tau_lo
+  const float* tau;        // [Q][4]: centre, a, b, e (tc_query_finish)
+  const float* cn;         // [nc] per-candidate norm bound n_c (tc_prep_cand_kernel)
   int32_t* tc_counts;      // [Q]
   unsigned* ctrl;          // [0] list length, [1] overflow, [2] ticket, [3] run-fallback flag
   unsigned long long* list;
@@ -205,6 +206,17 @@ struct TcListState { unsigned base, used, size; };
 constexpr unsigned long long kTcListHole = ~0ull;
 constexpr unsigned kTcListBlock = 16;
 
+KGE_DEV void tc_list_reserve(TcListState& L, const TcParams& P, int lane, unsigned need) {
+  unsigned b = 0;
+  if (lane == 0) {
+    b = atomicAdd(&P.ctrl[0], need);
+    if (b + need > P.cap) P.ctrl[1] = 1u;   // overflow: the exact fp32 sweep takes over (list writes are bounded)
+  }
+  L.base = __shfl_sync(0xffffffffu, b, 0);
+  L.used = 0u;
+  L.size = need;
+}
+
 KGE_DEV void tc_list_pad(TcListState& L, const TcParams& P, int lane) {
   for (unsigned i = L.used + (unsigned)lane; i < L.size; i += 32u)
     if (L.base + i < P.cap) P.list[L.base + i] = kTcListHole;
@@ -212,63 +224,83 @@ KGE_DEV void tc_list_pad(TcListState& L, const TcParams& P, int lane) {
 }
 
 // 32 accumulator columns (= candidates cbase .. cbase+31) of this thread's query row: count the
-// certainly-better ones (2 compares + 2 predicated adds per column, two independent chains); warps in
-// which some row has candidates inside its band list them from the registers already loaded — a
-// warp-level exclusive scan assigns the slots, no atomic on the path.
-KGE_DEV int tc_scan_chunk(const uint32_t (&v)[32], int nv, float tau_hi, float tau_lo, int64_t q, int64_t cbase,
+// certainly-better ones.  Per column: the band half-width of the pair (two fma on the candidate's norm
+// bound, broadcast from the lane that loaded it), u = D - centre, 2 compares + 2 predicated adds, two
+// independent chains; warps in which some row has candidates inside its band list them from the registers
+// already loaded — a warp-level exclusive scan assigns the slots, no atomic on the path.
+struct TcBand { float centre, a, b, e; };
+KGE_DEV void tc_band_eval(const TcBand& Bq, float x, float n, float& u, float& half) {
+  half = __fmaf_rn(__fmaf_rn(Bq.e, n, Bq.b), n, Bq.a);
+  u = __fsub_rn(x, Bq.centre);
+}
+KGE_DEV int tc_scan_chunk(const uint32_t (&v)[32], int nv, const TcBand& Bq, float nl, int64_t q, int64_t cbase,
                           bool live, const TcParams& P, TcListState& L, int lane, int& ev, bool stamp) {
   if (P.epi_mode == 1) return (int)(v[0] & 1u) + (int)(v[31] & 1u);
   if (stamp) TC_STAMP(2, ev++);
   int hi0 = 0, hi1 = 0, lo0 = 0, lo1 = 0;
-#define TC_CMP(HI, LO, X)                                                                                 \
-  asm("{\n\t.reg .pred p, q;\n\tsetp.gt.f32 p, %2, %3;\n\tsetp.ge.f32 q, %2, %4;\n\t"                   \
-      "@p add.s32 %0, %0, 1;\n\t@q add.s32 %1, %1, 1;\n\t}"                                               \
-      : "+r"(HI), "+r"(LO) : "f"(X), "f"(tau_hi), "f"(tau_lo))
+#define TC_CMP(HI, LO, X, J)                                                                              \
+  do {                                                                                                    \
+    float u_, h_;                                                                                         \
+    tc_band_eval(Bq, X, __shfl_sync(0xffffffffu, nl, J), u_, h_);                                         \
+    asm("{\n\t.reg .pred p, q;\n\t.reg .f32 nh;\n\tneg.f32 nh, %3;\n\tsetp.gt.f32 p, %2, %3;\n\t"       \
+        "setp.ge.f32 q, %2, nh;\n\t@p add.s32 %0, %0, 1;\n\t@q add.s32 %1, %1, 1;\n\t}"                  \
+        : "+r"(HI), "+r"(LO) : "f"(u_), "f"(h_));                                                         \
+  } while (0)
   if (nv == 32) {
 #pragma unroll
     for (int j = 0; j < 32; j += 2) {
-      TC_CMP(hi0, lo0, __uint_as_float(v[j]));
-      TC_CMP(hi1, lo1, __uint_as_float(v[j + 1]));
+      TC_CMP(hi0, lo0, __uint_as_float(v[j]), j);
+      TC_CMP(hi1, lo1, __uint_as_float(v[j + 1]), j + 1);
     }
   } else {
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < nv) TC_CMP(hi0, lo0, __uint_as_float(v[j]));
+    for (int j = 0; j < 32; ++j) {
+      const float nj = __shfl_sync(0xffffffffu, nl, j);   // (all lanes take part; columns >= nv are skipped)
+      if (j < nv) {
+        float u_, h_;
+        tc_band_eval(Bq, __uint_as_float(v[j]), nj, u_, h_);
+        hi0 += (u_ > h_) ? 1 : 0;
+        lo0 += (u_ >= -h_) ? 1 : 0;
+      }
+    }
   }
 #undef TC_CMP
   const int hi = hi0 + hi1;
   const int na = (lo0 + lo1) - hi;   // this row's candidates inside the band
   if (stamp) TC_STAMP(2, ev++);
   if (P.epi_mode != 2 && __any_sync(0xffffffffu, na != 0)) {
-    int incl = na;
+    // Transpose the band predicate with one vote per column: lane j ends up with the mask of the ROWS whose
+    // candidate cbase+j is ambiguous, so every lane lists its own column's pairs with no divergent code in the
+    // 32-column loop (the per-row form — 32 predicated stores per thread — cost 2-4k cycles per event:
+    // profiles/r2_tc_trace_v9_globalmax.jsonl).
+    unsigned mine = 0u;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float nj = __shfl_sync(0xffffffffu, nl, j);
+      float u_, h_;
+      tc_band_eval(Bq, __uint_as_float(v[j]), nj, u_, h_);
+      const unsigned m = __ballot_sync(0xffffffffu, j < nv && u_ >= -h_ && !(u_ > h_));
+      if (lane == j) mine = m;
+    }
+    const int mycnt = __popc(mine);
+    int incl = mycnt;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
       const int t = __shfl_up_sync(0xffffffffu, incl, off);
       if (lane >= off) incl += t;
     }
     const unsigned total = (unsigned)__shfl_sync(0xffffffffu, incl, 31);
-    if (L.used + total > L.size) {   // next block (rare: once per ~64 listed pairs)
+    if (L.used + total > L.size) {   // next block (rare: the first block is reserved before the first tile)
       tc_list_pad(L, P, lane);
-      const unsigned need = total > kTcListBlock ? total : kTcListBlock;
-      unsigned b = 0;
-      if (lane == 0) {
-        b = atomicAdd(&P.ctrl[0], need);
-        if (b + need > P.cap) P.ctrl[1] = 1u;   // overflow: the exact fp32 sweep takes over (writes below are bounded)
-      }
-      L.base = __shfl_sync(0xffffffffu, b, 0);
-      L.used = 0u;
-      L.size = need;
+      tc_list_reserve(L, P, lane, total > kTcListBlock ? total : kTcListBlock);
     }
-    if (na != 0) {
-      unsigned k = L.base + L.used + (unsigned)(incl - na);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float x = __uint_as_float(v[j]);
-        if (j < nv && x >= tau_lo && !(x > tau_hi)) {
-          if (k < P.cap) P.list[k] = ((unsigned long long)q << 32) | (unsigned long long)(cbase + j);
-          ++k;
-        }
-      }
+    unsigned k = L.base + L.used + (unsigned)(incl - mycnt);
+    const int64_t qrow0 = q - lane;   // the warp's rows are consecutive queries
+    while (mine) {
+      const int r = __ffs((int)mine) - 1;
+      mine &= mine - 1u;
+      if (k < P.cap) P.list[k] = ((unsigned long long)(qrow0 + r) << 32) | (unsigned long long)(cbase + lane);
+      ++k;
     }
     L.used += total;
   }
@@ -343,16 +375,9 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
 
   if (warp == 0) {
     if (lane == 0) {
-      if (P.a_resident && !P.a_tmem) {
-        tc_mbar_expect_tx(a_full, a_bytes);
-        for (int kb = 0; kb < P.nkb; ++kb) {
-          const bool tail = P.tail_cols && kb == P.nkb - 1;
-          const uint32_t tb = tail ? P.tail_bytes : P.tile_bytes;
-          const uint32_t dst = a_base + (uint32_t)kb * 2u * P.tile_bytes;
-          tc_tma_load_2d(dst, tail ? &TM.a0t : &TM.a0, kb * P.bk, (int)q0, a_full);
-          tc_tma_load_2d(dst + tb, tail ? &TM.a1t : &TM.a1, kb * P.bk, (int)q0, a_full);
-        }
-      }
+      // (resident query k-blocks ride on the FIRST tile's stage barriers, k-block by k-block: the first MMA needs
+      // 64 KB in shared memory, not the whole query block + three stages — see the loop below)
+      const bool a_with_first_tile = P.a_resident && !P.a_tmem;
       int stage = 0; uint32_t phase = 0;
       int ev = 0;
       TC_STAMP(0, ev++);
@@ -363,8 +388,14 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
           const uint32_t tb = tail ? P.tail_bytes : P.tile_bytes;
           tc_mbar_wait(&empty[stage], phase ^ 1u);
           TC_STAMP(0, ev++);
-          tc_mbar_expect_tx(&full[stage], (P.a_resident ? 2u : 4u) * tb);
+          const bool with_a = a_with_first_tile && t == 0;
+          tc_mbar_expect_tx(&full[stage], ((P.a_resident && !with_a) ? 2u : 4u) * tb);
           const uint32_t sb = st_base + (uint32_t)stage * st_bytes;
+          if (with_a) {
+            const uint32_t dst = a_base + (uint32_t)kb * 2u * P.tile_bytes;
+            tc_tma_load_2d(dst, tail ? &TM.a0t : &TM.a0, kb * P.bk, (int)q0, &full[stage]);
+            tc_tma_load_2d(dst + tb, tail ? &TM.a1t : &TM.a1, kb * P.bk, (int)q0, &full[stage]);
+          }
           if (PAIR) {   // my half of the candidate rows, into both CTAs (the peer sends the other half)
             const uint32_t ho = crank * (tb >> 1);
             const int hrow = row + (int)crank * (kTcBN / 2);
@@ -386,7 +417,7 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
     if (lane == 0) {
       int ev = 0;
       TC_STAMP(1, ev++);
-      if (P.a_resident) { tc_mbar_wait(a_full, 0u); tc_fence_after(); }
+      if (P.a_tmem) { tc_mbar_wait(a_full, 0u); tc_fence_after(); }   // (smem-resident query blocks arrive with the first tile's stages)
       TC_STAMP(1, ev++);
       int stage = 0; uint32_t phase = 0;
       for (int t = 0; t < ntl; ++t) {
@@ -438,8 +469,11 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
     const int row = quad * 32 + lane;
     const int64_t q = q0 + row;
     const bool live = q < P.Q;
-    const float tau_hi = live ? __ldg(P.tau + 2 * q) : INFINITY;
-    const float tau_lo = live ? __ldg(P.tau + 2 * q + 1) : INFINITY;
+    TcBand Bq = {INFINITY, 0.f, 0.f, 0.f};   // rows beyond Q: u = -inf -> nothing counted, nothing listed
+    if (live) {
+      const float4 tq = __ldg(reinterpret_cast<const float4*>(P.tau) + q);
+      Bq.centre = tq.x; Bq.a = tq.y; Bq.b = tq.z; Bq.e = tq.w;
+    }
     if (P.a_tmem) {
       // this thread's query row -> tensor memory: warps 2-5 write the high parts a0, warps 6-9 the low parts a1;
       // a row is Kp bf16 = Kp/2 32-bit columns (two consecutive k per column), rows beyond Q are zeros
@@ -462,32 +496,36 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
     }
     int cnt = 0;
     TcListState L = {0u, 0u, 0u};
+    tc_list_reserve(L, P, lane, kTcListBlock);   // the warp's first block: the atomic's round trip hides behind the first tile's MMAs
     int ev = 0;
     if (warp == 2 && lane == 0) TC_STAMP(2, ev++);
     for (int t = 0; t < ntl; ++t) {
       const int as = t & 1;
+      const int64_t cbase = (int64_t)(t0 + t) * kTcBN;
+      // this warp's half of the tile's columns: [c0, c0 + 64)
+      const int c0 = ((warp - 2) >> 2) * (kTcBN / 2);
+      // the candidates' norm bounds for the two 32-column chunks (lane = column), requested before the
+      // wait for the accumulator so that the L2 latency is off the path
+      const int64_t ca = cbase + c0 + lane, cb2 = ca + 32;
+      const float nla = ca < P.nc ? __ldg(P.cn + ca) : 0.f;
+      const float nlb = cb2 < P.nc ? __ldg(P.cn + cb2) : 0.f;
       tc_mbar_wait(&tmem_full[as], (uint32_t)((t >> 1) & 1));
       tc_fence_after();
       if (warp == 2 && lane == 0) TC_STAMP(2, ev++);
-      const int64_t cbase = (int64_t)(t0 + t) * kTcBN;
       const int nvalid = (int)min((int64_t)kTcBN, P.nc - cbase);
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * kTcBN);
-      // this warp's half of the tile's columns: [c0, c0 + 64)
-      const int c0 = ((warp - 2) >> 2) * (kTcBN / 2);
       const int nloc = min(kTcBN / 2, nvalid - c0);          // valid columns in the half (may be <= 0)
-      const int nchunks = nloc > 0 ? (nloc + 31) >> 5 : 0;
-      // two register buffers: the tcgen05.ld of chunk cb+1 is in flight while chunk cb is compared
+      const int nchunks = nloc > 0 ? (nloc + 31) >> 5 : 0;   // 0, 1 or 2
+      // two register buffers: the tcgen05.ld of chunk 1 is in flight while chunk 0 is compared
       uint32_t va[32], vb[32];
-      if (nchunks > 0) tc_tmem_ld32(taddr + (uint32_t)c0, va);
-#pragma unroll 1
-      for (int cb = 0; cb < nchunks; cb += 2) {
+      if (nchunks > 0) {
+        tc_tmem_ld32(taddr + (uint32_t)c0, va);
         tc_tmem_wait_ld();
-        if (cb + 1 < nchunks) tc_tmem_ld32(taddr + (uint32_t)(c0 + (cb + 1) * 32), vb);
-        cnt += tc_scan_chunk(va, min(32, nloc - cb * 32), tau_hi, tau_lo, q, cbase + c0 + cb * 32, live, P, L, lane, ev, warp == 2 && lane == 0);
-        if (cb + 1 < nchunks) {
+        if (nchunks > 1) tc_tmem_ld32(taddr + (uint32_t)(c0 + 32), vb);
+        cnt += tc_scan_chunk(va, min(32, nloc), Bq, nla, q, cbase + c0, live, P, L, lane, ev, warp == 2 && lane == 0);
+        if (nchunks > 1) {
           tc_tmem_wait_ld();
-          if (cb + 2 < nchunks) tc_tmem_ld32(taddr + (uint32_t)(c0 + (cb + 2) * 32), va);
-          cnt += tc_scan_chunk(vb, min(32, nloc - (cb + 1) * 32), tau_hi, tau_lo, q, cbase + c0 + (cb + 1) * 32, live, P, L, lane, ev, warp == 2 && lane == 0);
+          cnt += tc_scan_chunk(vb, min(32, nloc - 32), Bq, nlb, q, cbase + c0 + 32, live, P, L, lane, ev, warp == 2 && lane == 0);
         }
       }
       tc_fence_before();
@@ -512,13 +550,13 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
 // (NORMALISE: TransE) the canonical row normalisation of the fp32 sweep's scratch copy — same arithmetic
 // as prep_cand_kernel, written to s0 when the caller keeps that scratch for the fp32 fallback —, the bf16
 // split of the KC arrays concatenated along k, the three norm columns (squared-distance models) and the
-// running max of |c|^2.  Rows are read with the widest vector the table alignment allows; columns
+// row's norm bound n_c.  Rows are read with the widest vector the table alignment allows; columns
 // d .. dp-1 are zero.
 template <int VEC, bool NORMALISE>
 __global__ void __launch_bounds__(256)
 tc_prep_cand_kernel(const float* __restrict__ c0, const float* __restrict__ c1, int64_t pitch, int64_t nc, int d,
                     int dp, int KC, int Kp, int aug, __nv_bfloat16* __restrict__ B0, __nv_bfloat16* __restrict__ B1,
-                    unsigned* __restrict__ cmax_bits, float* __restrict__ s0, float* __restrict__ s1) {
+                    float* __restrict__ cn, float* __restrict__ s0, float* __restrict__ s1) {
   const int lane = threadIdx.x & 7;
   const int64_t e = (int64_t)blockIdx.x * 32 + (threadIdx.x >> 3);
   if (e >= nc) return;
@@ -560,7 +598,8 @@ tc_prep_cand_kernel(const float* __restrict__ c0, const float* __restrict__ c1, 
   const __nv_bfloat16 n1 = __float2bfloat16_rn(r1);
   const __nv_bfloat16 n2 = __float2bfloat16_rn(__fsub_rn(r1, __bfloat162float(n1)));
   tc_store_tail(o0, o1, KC * dp, Kp, lane, aug != 0, n0, n1, n2);
-  if (lane == 0) atomicMax(cmax_bits, __float_as_uint(__double2float_ru(ss)));   // non-negative floats order like their bits
+  // upper bound of |c| over the row's actual fp32 operands: the n_c of the pair's error budget (tc_query_finish)
+  if (lane == 0) cn[e] = __double2float_ru(sqrt(ss) * (1.0 + 1e-7));
 }
 
 static long long* g_tc_trace = nullptr;   // device buffer [3][64] or null (measurement aid)
@@ -589,15 +628,15 @@ bool tc_supported(const kge_model_t* m, int64_t nc) {
 }
 
 unsigned tc_list_capacity(int64_t Q) {
-  int64_t cap = 256 * Q;
-  if (cap < 16384) cap = 16384;
+  int64_t cap = 512 * Q;
+  if (cap < 32768) cap = 32768;   // (every epilogue warp reserves one block of 16 up front: <= 148 x 8 x 16 slots)
   if (cap > (1 << 24)) cap = 1 << 24;
   return (unsigned)cap;
 }
 
 // workspace carve-up (after the fp32 tiled sweep's region)
 struct TcLayout {
-  size_t a[2][2], tau[2], cnt[2], ctrl[2], list[2], b[2], cmax, total;
+  size_t a[2][2], tau[2], cnt[2], ctrl[2], list[2], b[2], cn, total;
 };
 static TcLayout tc_layout(const kge_model_t* m, int64_t Q) {
   TcLayout L;
@@ -605,13 +644,13 @@ static TcLayout tc_layout(const kge_model_t* m, int64_t Q) {
   size_t o = 0;
   for (int d = 0; d < 2; ++d) {
     for (int k = 0; k < 2; ++k) { L.a[d][k] = o; o += tc_align_up((size_t)Q * Kp * 2, 256); }
-    L.tau[d] = o; o += tc_align_up((size_t)Q * 2 * sizeof(float), 256);
+    L.tau[d] = o; o += tc_align_up((size_t)Q * 4 * sizeof(float), 256);
     L.cnt[d] = o; o += tc_align_up((size_t)Q * sizeof(int32_t), 256);
     L.ctrl[d] = o; o += 256;
     L.list[d] = o; o += tc_align_up((size_t)tc_list_capacity(Q) * 8, 256);
   }
   for (int k = 0; k < 2; ++k) { L.b[k] = o; o += tc_align_up((size_t)m->num_ent * Kp * 2, 256); }
-  L.cmax = o; o += 256;
+  L.cn = o; o += tc_align_up((size_t)m->num_ent * sizeof(float), 256);
   L.total = o;
   return L;
 }
@@ -653,14 +692,13 @@ static int tc_make_map(CUtensorMap* tm, const void* base, uint64_t rows, uint64_
 }
 
 // Candidate operands from the model's own fp32 tables src[k] (row pitch m->dim): bf16 split (+ norm
-// columns, + max |c|^2) and, when `scratch` is given, the fp32 copy the fp32 fallback sweep reads
+// columns, + the per-row norm bounds) and, when `scratch` is given, the fp32 copy the fp32 fallback sweep reads
 // (normalised for TransE, zero padded to dp) — all in one kernel.
 int tc_prepare_candidates(const kge_model_t* m, const float* const src[2], int64_t nc, void* tcws, int64_t Q,
                           float* scratch, cudaStream_t st) {
   const TcLayout L = tc_layout(m, Q);
   char* w = reinterpret_cast<char*>(tcws);
-  unsigned* cmax = reinterpret_cast<unsigned*>(w + L.cmax);
-  KGE_CUDA_OK(cudaMemsetAsync(cmax, 0, sizeof(unsigned), st));
+  float* cn = reinterpret_cast<float*>(w + L.cn);
   const int KC = tc_kq(m->model), d = m->dim, dp = tc_dp(m), Kp = tc_kp(m), aug = tc_kind(m) != 0 ? 1 : 0;
   int vc = (d % 4 == 0) ? 4 : (d % 2 == 0 ? 2 : 1);
   for (int k = 0; k < KC; ++k) {
@@ -676,7 +714,7 @@ int tc_prepare_candidates(const kge_model_t* m, const float* const src[2], int64
   __nv_bfloat16* B1 = reinterpret_cast<__nv_bfloat16*>(w + L.b[1]);
   const unsigned grid = (unsigned)((nc + 31) / 32);
   const bool normalise = m->model == KGE_TRANSE;
-#define TC_PREP(V, NRM) tc_prep_cand_kernel<V, NRM><<<grid, 256, 0, st>>>(c0, c1, (int64_t)d, nc, d, dp, KC, Kp, aug, B0, B1, cmax, s0, s1)
+#define TC_PREP(V, NRM) tc_prep_cand_kernel<V, NRM><<<grid, 256, 0, st>>>(c0, c1, (int64_t)d, nc, d, dp, KC, Kp, aug, B0, B1, cn, s0, s1)
   if (normalise) { if (vc == 4) TC_PREP(4, true); else if (vc == 2) TC_PREP(2, true); else TC_PREP(1, true); }
   else { if (vc == 4) TC_PREP(4, false); else if (vc == 2) TC_PREP(2, false); else TC_PREP(1, false); }
 #undef TC_PREP
@@ -694,7 +732,6 @@ TcQueryArgs tc_query_args(const kge_model_t* m, int dir, void* tcws, int64_t Q) 
   T.tau = reinterpret_cast<float*>(w + L.tau[dir]);
   T.tc_counts = reinterpret_cast<int32_t*>(w + L.cnt[dir]);
   T.ctrl = reinterpret_cast<unsigned*>(w + L.ctrl[dir]);
-  T.cmax_bits = reinterpret_cast<const unsigned*>(w + L.cmax);
   T.Kp = tc_kp(m); T.kind = tc_kind(m);
   // head sweep of TransE: canonical distance is |c + q| with q = r^ - t^  ->  contract with -q
   T.sign = (m->model == KGE_TRANSE && dir == 1) ? -1.0f : 1.0f;
@@ -719,7 +756,7 @@ int tc_sweep(const kge_model_t* m, int dir, int64_t Q, int64_t nc, void* tcws, T
   unsigned long long* list = reinterpret_cast<unsigned long long*>(w + L.list[dir]);
 
   TcParams P;
-  P.tau = tau; P.tc_counts = cnt; P.ctrl = ctrl; P.list = list; P.cap = tc_list_capacity(Q);
+  P.tau = tau; P.cn = reinterpret_cast<const float*>(w + L.cn); P.tc_counts = cnt; P.ctrl = ctrl; P.list = list; P.cap = tc_list_capacity(Q);
   // k-block width: 64 columns (128-byte swizzle rows).  32-column blocks (64-byte rows) would give 7 pipeline
   // stages instead of 3, but measured SLOWER (26.6 vs 24.5 us, profiles/r2_tc_trace_v6.jsonl): the operand
   // stream is bound by delivered L2 bandwidth (~28 B/cycle per SM with 116 SMs pulling = 6.2 TB/s), not by
@@ -807,7 +844,7 @@ int tc_sweep(const kge_model_t* m, int dir, int64_t Q, int64_t nc, void* tcws, T
     KGE_CHECK_LAUNCH("tc_sweep_kernel");
   }
   if (sp->armed) { KGE_CUDA_OK(cudaEventRecord(sp->end, st)); sp->valid = true; }
-  out->tc_counts = cnt; out->ctrl = ctrl; out->list = list; out->cap = P.cap; out->tau = tau;
+  out->tc_counts = cnt; out->ctrl = ctrl; out->list = list; out->cap = P.cap; out->tau = tau; out->cn = P.cn;
   return KGE_OK;
 }
 

@@ -11,10 +11,11 @@ namespace kge {
 struct TcQueryArgs {
   __nv_bfloat16* A0;          // [Q][Kp] bf16 high parts of the query vectors (+ the -1 norm columns)
   __nv_bfloat16* A1;          // [Q][Kp] bf16 low parts
-  float* tau;                 // [Q][2] accumulator thresholds (certainly better: D > tau[2q]; certainly not: D < tau[2q+1])
+  float* tau;                 // [Q][4] band of the accumulator test against candidate c with norm bound n_c:
+                              //   centre, a, b, e :  half(q,c) = a + b n_c + e n_c^2 ;
+                              //   certainly better: D - centre > half;  certainly not: D - centre < -half
   int32_t* tc_counts;         // [Q] zeroed here
   unsigned* ctrl;             // [4] zeroed here: pair-list length, overflow, ticket, fallback flag
-  const unsigned* cmax_bits;  // max_c |c|^2 as float bits (written by the candidate preparation)
   int Kp, kind;               // padded contraction length; 0 dot, 1 squared distance (sum domain), 2 squared distance - margin
   float sign, margin;
 };
@@ -65,18 +66,22 @@ KGE_DEV float tc_sqrt_domain_threshold(float th) {
 // Called by the 8 lanes of a query's group once its fp32 query vectors src[0 .. K) (K = KQ * dp, zero
 // padded, visible to the whole group) and its threshold th (the target's own canonical score) exist:
 // writes the bf16 split of the vectors (sign -1 for the head sweep of the translational models, whose
-// canonical distance is |c + q|), the -1 norm columns, and the two accumulator thresholds.
+// canonical distance is |c + q|), the -1 norm columns, and the coefficients of the accumulator band.
 //
-// Error budget (in double, rounded outwards to float at the end).  A = |q| max|c| >= sum_k |q_k c_k|,
-// M = A (+ max|c|^2 / 2 when the norm columns ride along) bounds every partial sum of the accumulation.
+// Error budget PER PAIR (q, c) — in double, rounded outwards to float at the end.  n = |c| (an upper bound,
+// written per candidate row by tc_prep_cand_kernel), A = |q| n >= sum_k |q_k c_k|,
+// M = A (+ n^2 / 2 when the norm columns ride along) bounds every partial sum of the accumulation.
 //   split      : |x - x0 - x1| <= 2^-18 |x| per operand; the three dropped product terms
 //                (a1 b1, da b, a db) are <= 3 * 2^-18 * (1 + 2^-8) A                      -> 2^-16 A  (x 1.33 slack)
 //   accumulate : products of bf16 pairs are exact in fp32; each of the nmma = 3 ceil(Kp/16) tensor-core
 //                instructions may lose <= 4 ulp of the running magnitude                   -> nmma 2^-21 M
-//   norm cols  : 3-way bf16 split of fl(|c|^2 / 2)                                         -> 2^-22 max|c|^2
+//   norm cols  : 3-way bf16 split of fl(|c|^2 / 2)                                         -> 2^-22 n^2
 //   canonical  : the fp32 chain (RSUM: 8 partials of K/8 fma + 3 butterfly adds; squared distances add one
 //                rounding of (q - c) per element) against the exact value of the same fp32 operands:
-//                gamma = (K/8 + 8) 2^-24 (+ 2^-22), times A (dot) or (|q| + max|c|)^2 (distance).
+//                gamma = (K/8 + 8) 2^-24 (+ 2^-22), times A (dot) or (|q| + n)^2 (distance).
+// Every term is a polynomial of degree <= 2 in n with per-query coefficients, so the epilogue evaluates
+// half(q,c) = a + b n + e n^2 with two fma (r2 first used max_c|c| for n: exact too, but one heavy row —
+// trained tables have them — widened every pair's band; now the band of a pair scales with ITS candidate).
 // Measured on the B200 (tests/test_gpu_baseline_shapes.py, profiles/r2_tc_parity.jsonl): the real error is
 // 35x (d = 200) to 400x (d = 1000) below this bound.
 KGE_DEV void tc_query_finish(const TcQueryArgs& T, const float* src, float th, int64_t q, int lane, int K) {
@@ -94,33 +99,45 @@ KGE_DEV void tc_query_finish(const TcQueryArgs& T, const float* src, float th, i
   tc_store_tail(o0, o1, K, T.Kp, lane, T.kind != 0, m1, m1, m1);
   if (lane != 0) return;
   T.tc_counts[q] = 0;
-  const double cmax2 = (double)__uint_as_float(*T.cmax_bits);
-  const double cmax = sqrt(cmax2) * (1.0 + 1e-7), nq = sqrt(ss) * (1.0 + 1e-7);
-  const double A = nq * cmax;
-  const double M = A + (T.kind != 0 ? 0.5 * cmax2 : 0.0);
+  const double nq = sqrt(ss) * (1.0 + 1e-7);
   const int nmma = 3 * ((T.Kp + 15) / 16);
-  const double e_tc = ldexp(1.0, -16) * A + (double)nmma * ldexp(1.0, -21) * M + ldexp(1.0, -22) * cmax2 + 1e-30;
+  const double acc = (double)nmma * ldexp(1.0, -21);
   const double gamma = ((double)K / 8.0 + 8.0) * ldexp(1.0, -24);
-  double centre, half;
+  double centre, a, b, e;
   if (T.kind == 0) {
     centre = -(double)th;                        // canonical: -sum < th  <=>  sum > -th (negation is exact)
-    half = e_tc + gamma * A;
+    a = 0.0;
+    b = nq * (ldexp(1.0, -16) + acc + gamma);
+    e = 0.0;
   } else {
-    const double smax = (nq + cmax) * (nq + cmax);
+    // e_tc = 2^-16 nq n + acc (nq n + n^2/2) + 2^-22 n^2 ;  smax = (nq + n)^2 = nq^2 + 2 nq n + n^2
     const double g2 = gamma + ldexp(1.0, -22);
+    double ks = 0.5 * g2;                        // coefficient of smax in the half band
+    double a0 = ldexp(1.0, -50) * ss;
     if (T.kind == 1) {                           // canonical: sum < T(th)
       const double Tt = (double)tc_sqrt_domain_threshold(th);
       centre = 0.5 * (ss - Tt);
-      half = 0.5 * (2.0 * e_tc + g2 * smax) + ldexp(1.0, -50) * ss;
     } else {                                     // canonical: fsub(sum, margin) < th
       centre = 0.5 * (ss - (double)th - (double)T.margin);
-      half = 0.5 * (2.0 * e_tc + g2 * smax + ldexp(1.0, -24) * (smax * 1.01 + fabs((double)T.margin))) +
-             ldexp(1.0, -50) * ss;
+      ks += 0.5 * 1.01 * ldexp(1.0, -24);        // the rounding of fsub(sum, margin)
+      a0 += 0.5 * ldexp(1.0, -24) * fabs((double)T.margin);
     }
+    a = a0 + ks * nq * nq;
+    b = nq * (ldexp(1.0, -16) + acc) + 2.0 * ks * nq;
+    e = 0.5 * acc + ldexp(1.0, -22) + ks;
   }
+  // The epilogue evaluates u = fsub(D, centre_f) and half = fma(fma(e, n, b), n, a) in fp32: cover the
+  // rounding of centre to float (2^-24 |centre|, absolute), of u (2^-24 relative — harmless against the
+  // 2^-18 inflation) and of the two fma (2^-23 relative).
+  const double infl = 1.0 + ldexp(1.0, -18);
+  a = a * infl + ldexp(1.0, -23) * fabs(centre) + 1e-30;
   // NaN thresholds propagate: every comparison with them is false, as `s < NaN` is in the exact path
-  T.tau[2 * q] = __double2float_ru(centre + half);
-  T.tau[2 * q + 1] = __double2float_rd(centre - half);
+  float4 o;
+  o.x = (float)centre;
+  o.y = __double2float_ru(a);
+  o.z = __double2float_ru(b * infl);
+  o.w = __double2float_ru(e * infl);
+  *reinterpret_cast<float4*>(T.tau + 4 * q) = o;
 }
 
 }  // namespace kge

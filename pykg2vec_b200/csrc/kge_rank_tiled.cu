@@ -828,8 +828,10 @@ int tiled_sweep(const kge_model_t* m, const kge_model_t* mq, int dir, const int6
     TcDirBuffers B;
     int rc = tc_sweep(m, dir, Q, nc, tc_ws_ptr(m, ws, Q), &B, tc_dbg, st);
     if (rc) return rc;
-    if (tc_tau_out)
-      KGE_CUDA_OK(cudaMemcpyAsync(tc_tau_out, B.tau, (size_t)Q * 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (tc_tau_out) {   // probe: [Q][4] band coefficients, then the nc candidate norm bounds
+      KGE_CUDA_OK(cudaMemcpyAsync(tc_tau_out, B.tau, (size_t)Q * 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      KGE_CUDA_OK(cudaMemcpyAsync(tc_tau_out + (size_t)Q * 4, B.cn, (size_t)nc * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
     RankFilter none = {nullptr, nullptr, 0, nullptr, 0, 0};
     rc = band_resolve(m, mq, dir, qh, qr, qt, thr, Q, B, filter ? *filter : none, counts, col, st);
     if (rc) return rc;

@@ -116,6 +116,92 @@ train_logistic_kernel(ModelParams P, GradTablesT GT, const int64_t* __restrict__
   }
 }
 
+// RotatE (Trainer.train_step_pairwise, trainer.py:147-157, with Criterion.pariwise_logistic — the
+// self-adversarial loss, criterion.py:14-23): the softmax runs over the neg_rate negatives of ONE positive, so a
+// warp that owns a positive and its negatives can score them, form the weights, and scatter the row gradients
+// without leaving the kernel — forward + loss + backward of the whole batch in ONE launch (was: two forward
+// launches, the loss kernel, two backward launches).
+//   phase 1: the warp's four 8-lane groups score negatives j = g, g+4, .. (canonical arithmetic == forward())
+//            into shared memory; group 0 also scores the positive
+//   phase 2: the warp's softmax statistics in EXACTLY the arithmetic of selfadv_kernel (kge_loss.cu): lane-strided
+//            max / sum / weighted log-sigmoid + butterflies, so the loss bits equal the unfused path's
+//   phase 3: the groups re-read their triples' rows (L1/L2 hits) and scatter d loss / d score * d score / d rows
+__device__ __forceinline__ float tl_logsigmoid(float x) { return x < 0.f ? x - log1pf(expf(x)) : -log1pf(expf(-x)); }
+
+// TEAM: the threads that share a positive — a warp (4 groups; small neg_rate: 8 positives per CTA) or the whole
+// CTA (32 groups; large neg_rate: as many triples in flight as the unfused launches have).
+template <int MODEL, int VEC, bool CTA_TEAM>
+__global__ void __launch_bounds__(kThreads)
+train_selfadv_kernel(ModelParams P, GradTablesT GT, const int64_t* __restrict__ ph, const int64_t* __restrict__ pr,
+                     const int64_t* __restrict__ pt, const int64_t* __restrict__ nh, const int64_t* __restrict__ nr,
+                     const int64_t* __restrict__ nt, int64_t B, int neg_rate, float alpha, float* __restrict__ loss,
+                     int scratch_floats) {
+  extern __shared__ float4 smem_f4[];
+  float* scratch = reinterpret_cast<float*>(smem_f4) + (size_t)(threadIdx.x >> 3) * scratch_floats;
+  // the team's negative scores, then d loss / d score
+  float* sc = reinterpret_cast<float*>(smem_f4) + (size_t)kGroupsPerCta * scratch_floats +
+              (CTA_TEAM ? (size_t)0 : (size_t)(threadIdx.x >> 5) * neg_rate);
+  constexpr int kTeamGroups = CTA_TEAM ? kGroupsPerCta : 4;
+  const int lane = threadIdx.x & 7, wl = threadIdx.x & 31;
+  const int grp = CTA_TEAM ? (threadIdx.x >> 3) : (wl >> 3);
+  const int64_t i = CTA_TEAM ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  if (i >= B) return;                                                       // whole teams leave together
+  const float inv_b = 1.f / (float)B;
+  float p = 0.f;
+  for (int j = grp; j < neg_rate; j += kTeamGroups) {
+    const int64_t e = i * neg_rate + j;
+    TripleRows R;
+    resolve_rows<MODEL>(R, P, P.tab, P.tab, P.tab, __ldg(nh + e), __ldg(nr + e), __ldg(nt + e));
+    const float s = score_group<MODEL, VEC, KGE_GROUP_TAIL, 0>(R, P, lane, scratch);
+    if (lane == 0) sc[j] = s;
+  }
+  if (grp == 0) {
+    TripleRows R;
+    resolve_rows<MODEL>(R, P, P.tab, P.tab, P.tab, __ldg(ph + i), __ldg(pr + i), __ldg(pt + i));
+    p = score_group<MODEL, VEC, KGE_GROUP_TAIL, 0>(R, P, lane, scratch);
+  }
+  if (CTA_TEAM) __syncthreads(); else __syncwarp();
+  if (!CTA_TEAM || threadIdx.x < 32) {   // (group 0 — the positive's — is in the team's first warp)
+    float mx = -INFINITY;
+    for (int j = wl; j < neg_rate; j += 32) mx = fmaxf(mx, -sc[j] * alpha);
+#pragma unroll
+    for (int off = 16; off; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    float den = 0.f;
+    for (int j = wl; j < neg_rate; j += 32) den += expf(-sc[j] * alpha - mx);
+#pragma unroll
+    for (int off = 16; off; off >>= 1) den += __shfl_xor_sync(0xffffffffu, den, off);
+    float row = 0.f;
+    for (int j = wl; j < neg_rate; j += 32) {
+      const float x = sc[j];
+      const float w = expf(-x * alpha - mx) / den;
+      row += w * tl_logsigmoid(x);
+      sc[j] = -inv_b * w * tl_sigmoid(-x);       // (only this lane reads or writes slot j in this phase)
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) row += __shfl_xor_sync(0xffffffffu, row, off);
+    p = __shfl_sync(0xffffffffu, p, 0);
+    if (wl == 0) atomicAdd(loss, -inv_b * (row + tl_logsigmoid(-p)));
+  }
+  if (CTA_TEAM) __syncthreads(); else __syncwarp();
+  for (int j = grp; j < neg_rate; j += kTeamGroups) {
+    const int64_t e = i * neg_rate + j;
+    const int64_t a = __ldg(nh + e), b = __ldg(nr + e), c = __ldg(nt + e);
+    TripleRows R;
+    GradRows G;
+    resolve_rows<MODEL>(R, P, P.tab, P.tab, P.tab, a, b, c);
+    resolve_grad_rows<MODEL>(G, P, GT.t, a, b, c);
+    grad_group<MODEL, VEC, 0>(R, G, P, lane, sc[j], scratch);
+  }
+  if (grp == 0) {
+    const int64_t a = __ldg(ph + i), b = __ldg(pr + i), c = __ldg(pt + i);
+    TripleRows R;
+    GradRows G;
+    resolve_rows<MODEL>(R, P, P.tab, P.tab, P.tab, a, b, c);
+    resolve_grad_rows<MODEL>(G, P, GT.t, a, b, c);
+    grad_group<MODEL, VEC, 0>(R, G, P, lane, inv_b * tl_sigmoid(p), scratch);
+  }
+}
+
 // ---- sparse optimizer application ---------------------------------------------
 constexpr int kMaxTasks = 48;
 struct ApplyTasks {
@@ -482,5 +568,59 @@ extern "C" int kge_train_pointwise_logistic(const kge_model_t* m, float* const* 
   }
 #undef CALL_TL
   KGE_CHECK_LAUNCH("train_logistic_kernel");
+  return KGE_OK;
+}
+
+extern "C" int kge_train_pairwise_selfadv(const kge_model_t* m, float* const* grad_scratch, const int64_t* pos_h,
+                                          const int64_t* pos_r, const int64_t* pos_t, const int64_t* neg_h,
+                                          const int64_t* neg_r, const int64_t* neg_t, int64_t B, int32_t neg_rate,
+                                          float alpha, float* loss_out, void* stream) {
+  int rc = check_model(m);
+  if (rc) return rc;
+  if (B <= 0 || neg_rate <= 0 || !grad_scratch || !pos_h || !pos_r || !pos_t || !neg_h || !neg_r || !neg_t || !loss_out) {
+    set_error("kge_train_pairwise_selfadv: bad arguments"); return KGE_EINVAL;
+  }
+  if (m->model != KGE_ROTATE) {   // the reference uses this loss for RotatE only (trainer.py:152-155)
+    set_error("kge_train_pairwise_selfadv: model %d does not train with the self-adversarial loss", (int)m->model);
+    return KGE_ENOTSUP;
+  }
+  const int nt = num_tables(m->model);
+  const ModelParams P = make_params(m, nullptr);
+  GradTablesT GT;
+  int vec = model_vec(m);
+  for (int k = 0; k < KGE_MAX_TABLES; ++k) {
+    GT.t[k] = (k < nt) ? grad_scratch[k] : nullptr;
+    if (GT.t[k]) {
+      const uintptr_t a = (uintptr_t)GT.t[k];
+      if (vec == 4 && (a & 15)) vec = 2;
+      if (vec == 2 && (a & 7)) vec = 1;
+    }
+  }
+  const int sf = (int)group_scratch_floats_bwd(m);
+  // a warp per positive while each of its 4 groups has at most one negative; beyond that the whole CTA shares a
+  // positive (measured, profiles/r2_selfadv_fusion.jsonl: at neg_rate 16 the warp form — 4 triples in sequence per
+  // group, twice — is 14-37 % SLOWER than the five-launch path; the CTA form is at parity or ahead up to 256)
+  const bool cta_team = neg_rate > 4;
+  const size_t smem = ((size_t)sf * kGroupsPerCta + (size_t)(cta_team ? 1 : kThreads / 32) * (size_t)neg_rate) * sizeof(float);
+  if (smem > 200 * 1024) {
+    set_error("kge_train_pairwise_selfadv: neg_rate %d needs %zu bytes of shared memory per CTA", (int)neg_rate, smem);
+    return KGE_ENOTSUP;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  KGE_CUDA_OK(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
+  const unsigned grid = cta_team ? (unsigned)B : (unsigned)((B + kThreads / 32 - 1) / (kThreads / 32));
+#define CALL_SA2(M, V, T)                                                                        \
+  do {                                                                                           \
+    if (smem > 40 * 1024)                                                                        \
+      KGE_CUDA_OK(cudaFuncSetAttribute(train_selfadv_kernel<M, V, T>,                            \
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    train_selfadv_kernel<M, V, T><<<grid, kThreads, smem, st>>>(P, GT, pos_h, pos_r, pos_t, neg_h, neg_r, neg_t, B, \
+                                                                (int)neg_rate, alpha, loss_out, sf); \
+  } while (0)
+#define CALL_SA(M, V) do { if (cta_team) CALL_SA2(M, V, true); else CALL_SA2(M, V, false); } while (0)
+  KGE_DISPATCH_VEC(KGE_ROTATE, vec, CALL_SA);
+#undef CALL_SA
+#undef CALL_SA2
+  KGE_CHECK_LAUNCH("train_selfadv_kernel");
   return KGE_OK;
 }

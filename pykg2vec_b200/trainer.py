@@ -50,6 +50,7 @@ class Trainer:
         self._graphs = {}
         self._state2 = None
         self._step = 0
+        self._selfadv_fused = True
         self._world = 1
         self._dp = None
 
@@ -201,14 +202,23 @@ class Trainer:
             _lib.train_pairwise_hinge_sgd(desc, self._grad_scratch, ph, pr, pt, nh, nr, nt,
                                           float(self.config.margin), lr, self._loss_buf)
             return self._loss_buf
-        pos = _lib.score_fwd(desc, ph, pr, pt)
-        neg = _lib.score_fwd(desc, nh, nr, nt)
-        if self.model.model_name.lower() == "rotate":
-            loss, gp, gn = _lib.loss_selfadv(pos, neg, int(self.config.neg_rate), float(self.config.alpha))
-        else:
-            loss, gp, gn = _lib.loss_pairwise_hinge(pos, neg, float(self.config.margin))
-        _lib.score_bwd(desc, ph, pr, pt, gp, self._grad_scratch)
-        _lib.score_bwd(desc, nh, nr, nt, gn, self._grad_scratch)
+        loss = None
+        if rotate and self._selfadv_fused:
+            # forward (positives + negatives) + self-adversarial loss + backward in ONE kernel
+            try:
+                loss = _lib.train_pairwise_selfadv(desc, self._grad_scratch, ph, pr, pt, nh, nr, nt,
+                                                   int(self.config.neg_rate), float(self.config.alpha))
+            except _lib.KgeNotSupported:   # neg_rate beyond a CTA's shared memory: the five-launch path
+                self._selfadv_fused = False
+        if loss is None:
+            pos = _lib.score_fwd(desc, ph, pr, pt)
+            neg = _lib.score_fwd(desc, nh, nr, nt)
+            if rotate:
+                loss, gp, gn = _lib.loss_selfadv(pos, neg, int(self.config.neg_rate), float(self.config.alpha))
+            else:
+                loss, gp, gn = _lib.loss_pairwise_hinge(pos, neg, float(self.config.margin))
+            _lib.score_bwd(desc, ph, pr, pt, gp, self._grad_scratch)
+            _lib.score_bwd(desc, nh, nr, nt, gn, self._grad_scratch)
         loss = self._allreduce_grads(loss, mean_type=rotate)
         self._apply(desc, ((ph, pr, pt), (nh, nr, nt)), lr)
         return loss

@@ -207,6 +207,33 @@ def test_fused_hinge_sgd_matches_dense_sgd():
             assert all(float(s.abs().max()) == 0.0 for s in scratch), "gradient scratch must be left zeroed"
 
 
+@pytest.mark.parametrize("neg_rate,B", [(1, 70), (3, 129), (4, 64), (5, 33), (16, 64), (256, 40)])
+def test_fused_selfadv_step_equals_the_five_launch_path(neg_rate, B):
+    """kge_train_pairwise_selfadv (RotatE: forward + self-adversarial loss + backward in one kernel; a warp per
+    positive up to neg_rate 4, a CTA per positive beyond) == kge_score_fwd x2 + kge_loss_selfadv + kge_score_bwd x2:
+    the loss terms are the same bits (summed by unordered atomics -> compared to fp32 rounding), the gradients
+    equal up to the order of the float atomics."""
+    L = _L()
+    N, R, d = 700, 9, 100
+    om, tabs = gpu.synthetic_case("rotate", N, R, d, seed=31)
+    desc = gpu.desc_from_oracle_model(om)
+    rng = np.random.RandomState(neg_rate)
+    ids = [_cuda(rng.randint(N if k % 3 != 1 else R, size=B if k < 3 else B * neg_rate)) for k in range(6)]
+    g_fused = [torch.zeros_like(x) for x in desc.tables]
+    loss_fused = L.train_pairwise_selfadv(desc, g_fused, *ids, neg_rate=neg_rate, alpha=0.5)
+    pos, neg = L.score_fwd(desc, *ids[:3]), L.score_fwd(desc, *ids[3:])
+    loss, gp, gn = L.loss_selfadv(pos, neg, neg_rate, 0.5)
+    g_ref = [torch.zeros_like(x) for x in desc.tables]
+    L.score_bwd(desc, *ids[:3], gp, g_ref)
+    L.score_bwd(desc, *ids[3:], gn, g_ref)
+    assert abs(loss_fused.item() - loss.item()) <= 2e-6 * abs(loss.item())
+    _check_grads([g.cpu().numpy() for g in g_fused], [g.cpu().numpy() for g in g_ref], tol=2e-5, what="selfadv fused")
+    with pytest.raises(L.KgeNotSupported):   # other models do not train with this loss
+        om2, _ = gpu.synthetic_case("transe", N, R, d, seed=1)
+        d2 = gpu.desc_from_oracle_model(om2)
+        L.train_pairwise_selfadv(d2, [torch.zeros_like(x) for x in d2.tables], *ids, neg_rate=neg_rate, alpha=0.5)
+
+
 def _trainer_for(model_name, kg, **cfgkw):
     import pykg2vec_b200
     from pykg2vec_b200.synthetic import SyntheticConfig

@@ -249,10 +249,16 @@ int kge_rank_1vsall(const kge_model_t* m, const kge_model_t* mq, int64_t row_lo,
 /* Measurement aid (bench.py's roofline entry): after a kge_rank_1vsall call with KGE_RANK_PROFILE from the
  * same host thread, *ms receives the device time of direction 0 (tail) / 1 (head)'s main sweep kernel —
  * tc_sweep_kernel, or sweep_tiled_kernel with KGE_RANK_NO_TC — measured by CUDA events recorded around
- * that launch on the stream it ran on (waits for the kernel).  Not usable inside a graph capture. */
+ * that launch on the stream it ran on (waits for the kernel).  Not usable inside a graph capture.
+ * A full rank call of a tensor-core model sweeps BOTH directions in one launch: it is reported as direction 0,
+ * kge_rank_last_sweep_directions() returns 2 (1 for per-direction launches, 0 when nothing was profiled) and
+ * direction 1 has no launch of its own (KGE_EINVAL). */
 int kge_rank_last_sweep_ms(int direction, float* ms);
+int kge_rank_last_sweep_directions(void);
 /* Measurement aid: per-role clock64 timeline of CTA (0,0) of subsequent tc_sweep_kernel launches into the
- * device buffer buf[3][64] (NULL = off): role 0 TMA producer, 1 MMA issuer, 2 epilogue (see kge_rank.cu). */
+ * device buffer buf[3][64] (NULL = off): role 0 TMA producer, 1 MMA issuer, 2 epilogue (see kge_rank.cu);
+ * behind them buf[192 + 2 i], buf[193 + 2 i] = %globaltimer (ns) at entry / exit of CTA i (linear id < 1024),
+ * and buf[2*64 + 62] = clock64 at the exit of CTA 0: the buffer must hold 192 + 2048 int64. */
 int kge_debug_set_tc_trace(long long* buf);
 
 /* Two-level exact sweep (TransE -l1 False, DistMult, CP, ComplEx, RESCAL, RotatE; >= 1024 candidate rows):

@@ -1,8 +1,8 @@
 """Workload for compute-sanitizer (memcheck / racecheck / synccheck): every kernel with hand-rolled
 cross-warp synchronisation or atomics, at small sizes — the tensor-core sweep (TMA + mbarrier + tcgen05 +
 TMEM), the fp32 tiled sweep (TMA + mbarrier + release counters; whole-row and slab mode, all OPs), the
-exact-resolve kernel (last-CTA commit), the fused hinge step (atom.exch sparse apply) and the dense
-optimizer.  Results are checked against the oracle so a silent corruption would also fail here.
+exact-resolve kernel, the fp32 sweep's commit-or-fallback entry, the fused hinge step (atom.exch sparse apply), the
+fused RotatE self-adversarial step (warp team and CTA team) and the dense optimizer.  Results are checked against the oracle so a silent corruption would also fail here.
 
     compute-sanitizer --tool memcheck  python profiles/sanitizer_workload.py
     compute-sanitizer --tool racecheck python profiles/sanitizer_workload.py
@@ -55,5 +55,15 @@ for opt in (0, 1, 2):
     gg = g.clone()
     _lib.optim_apply_dense(desc.tables[0], gg, opt, 0.01, m1, m2, step=1)
     assert float(gg.abs().max()) == 0.0
+# fused RotatE self-adversarial step: warp team (neg_rate <= 4) and CTA team
+om, tabs = gpu.synthetic_case("rotate", 400, 5, 48, seed=9, margin=6.0)
+desc = gpu.desc_from_oracle_model(om)
+for neg_rate, B in ((2, 37), (24, 19)):
+    ids = [cu(rng.randint(400 if k % 3 != 1 else 5, size=B if k < 3 else B * neg_rate)) for k in range(6)]
+    gs = [torch.zeros_like(t) for t in desc.tables]
+    loss = _lib.train_pairwise_selfadv(desc, gs, *ids, neg_rate=neg_rate, alpha=0.5)
+    pos, neg = _lib.score_fwd(desc, *ids[:3]), _lib.score_fwd(desc, *ids[3:])
+    want, _gp, _gn = _lib.loss_selfadv(pos, neg, neg_rate, 0.5)
+    assert abs(loss.item() - want.item()) <= 1e-5 * abs(want.item())
 torch.cuda.synchronize()
 print("train ok", flush=True)

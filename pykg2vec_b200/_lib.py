@@ -29,7 +29,7 @@ EXPORTS = [
     "kge_score_fwd", "kge_score_bwd", "kge_normalize_rows",
     "kge_loss_pairwise_hinge", "kge_loss_pointwise_logistic", "kge_loss_selfadv", "kge_reg_fwd_bwd",
     "kge_train_pairwise_hinge_sgd", "kge_train_pointwise_logistic", "kge_train_pairwise_selfadv", "kge_optim_apply_rows", "kge_optim_apply_dense",
-    "kge_rank_workspace_bytes", "kge_rank_1vsall", "kge_rank_tc_probe", "kge_rank_last_sweep_ms", "kge_debug_set_tc_trace",
+    "kge_rank_workspace_bytes", "kge_rank_1vsall", "kge_rank_tc_probe", "kge_rank_last_sweep_ms", "kge_rank_last_sweep_directions", "kge_debug_set_tc_trace",
     "kge_tripleset_capacity", "kge_tripleset_build", "kge_sample_negatives",
     "kge_proj_tail_fwd", "kge_proj_tail_bwd", "kge_proj_bce", "kge_proj_rank_workspace_bytes", "kge_proj_rank", "kge_proj_labels",
     "kge_conve_trunk_workspace_bytes", "kge_conve_trunk_fwd", "kge_project_entities", "kge_normalize_rows_to",
@@ -322,6 +322,12 @@ def rank_1vsall(desc, qh, qr, qt, filt_t=None, filt_h=None, counts=None, row_lo=
         _ptr(counts), _ptr(workspace), ctypes.c_int64(workspace.numel()), ctypes.c_int(flags), _stream()),
         "kge_rank_1vsall")
     return counts
+
+
+def rank_last_sweep_directions():
+    """how many directions the launch timed by rank_last_sweep_ms(0) swept (2: the tensor-core sweep of a full
+    rank call covers tail and head in one launch; 0: nothing profiled)."""
+    return int(lib().kge_rank_last_sweep_directions())
 
 
 def rank_last_sweep_ms(direction):

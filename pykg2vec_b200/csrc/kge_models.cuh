@@ -15,6 +15,25 @@ struct TripleRows {
   const float* r[8];  // relation-side rows (rel / rel_re, w / rel_map / rel_im / M_r / theta)
 };
 
+// Latency-bound kernels (a few hundred groups: training batch, query preparation, pair resolution) read a
+// triple's rows in dependent phases — norm of h, norm of r, norm of t, score, gradients —, each starting with a
+// cold miss.  Requesting every row of the triple up front (one prefetch per 128-byte line, lanes of the group
+// interleaved) overlaps those misses; the phases then hit in L2.  Row widths: d floats (h / t side), dr (r side).
+KGE_DEV void prefetch_row_lines(const float* row, int nfloats, int lane) {
+  if (row == nullptr) return;
+  const char* p = reinterpret_cast<const char*>(row);
+  for (int off = lane * 128; off < nfloats * 4; off += 8 * 128)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
+}
+KGE_DEV void prefetch_triple_rows(const TripleRows& R, int d, int dr, int lane) {
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {   // (rows [2..] exist for the hypercomplex models only: not used by the callers)
+    prefetch_row_lines(R.h[k], d, lane);
+    prefetch_row_lines(R.t[k], d, lane);
+    prefetch_row_lines(R.r[k], dr, lane);
+  }
+}
+
 // Row pointers of triple (h, r, t).  htab/ttab/rtab: the table sets the head-side,
 // tail-side and relation-side rows are read from (they differ only in 1-vs-all
 // sweeps over a row shard, where the candidate side is the local shard).

@@ -119,8 +119,9 @@ threshold_kernel(ModelParams P, const int64_t* __restrict__ qh, const int64_t* _
 //   items [0, total)            : pairs whose tensor-core accumulator fell inside the query's band:
 //                                 tc_counts[q] += 1 when the candidate really outranks the target
 //   items [total, total + nnz)  : filter entries (as filter_correct_kernel): filtered column -= 1
-// The last CTA to finish then commits the direction: counts += tc_counts, or (list overflow) raises
-// ctrl[3] so that the fp32 tiled sweep enqueued behind this kernel ranks the direction instead.
+// The fp32 tiled sweep enqueued behind this kernel then commits the direction (counts += tc_counts) or —
+// list overflow: ctrl[0] > cap or ctrl[1] — ranks it itself (sweep_tiled_kernel's entry, kge_rank_tiled.cu);
+// on overflow this kernel still applies the filter corrections.
 template <int MODEL, int VEC, int GROUPING>
 __global__ void __launch_bounds__(kThreads)
 band_resolve_kernel(ModelParams P, const int64_t* __restrict__ qh, const int64_t* __restrict__ qr,
@@ -129,7 +130,6 @@ band_resolve_kernel(ModelParams P, const int64_t* __restrict__ qh, const int64_t
                     int64_t Q, int32_t* __restrict__ tc_counts, const RankFilter F, int32_t* __restrict__ counts,
                     int col, int scratch_floats) {
   extern __shared__ float4 smem_f4[];
-  __shared__ int s_last;
   float* scratch = reinterpret_cast<float*>(smem_f4) + (size_t)(threadIdx.x >> 3) * scratch_floats;
   const int lane = threadIdx.x & 7;
   const unsigned listed = *reinterpret_cast<volatile unsigned*>(&ctrl[0]);
@@ -164,25 +164,12 @@ band_resolve_kernel(ModelParams P, const int64_t* __restrict__ qh, const int64_t
       resolve_rows<MODEL>(R, P, P.qtab, P.tab, P.qtab, __ldg(qh + q), __ldg(qr + q), e);
     else
       resolve_rows<MODEL>(R, P, P.tab, P.qtab, P.qtab, e, __ldg(qr + q), __ldg(qt + q));
+    prefetch_triple_rows(R, P.d, P.dr, lane);
     const float s = score_group<MODEL, VEC, GROUPING>(R, P, lane, scratch);
     if (lane == 0 && !skip && s < __ldg(thr + q)) {
       if (band) atomicAdd(tc_counts + q, 1);
       else atomicSub(counts + q * 4 + col + 1, 1);
     }
-  }
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(&ctrl[2], 1u) == gridDim.x - 1) ? 1 : 0;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  if (overflow) {
-    if (threadIdx.x == 0) ctrl[3] = 1u;
-    return;
-  }
-  for (int64_t q = threadIdx.x; q < Q; q += kThreads) {
-    const int c = *reinterpret_cast<volatile int32_t*>(tc_counts + q);
-    if (c) { atomicAdd(counts + q * 4 + col, c); atomicAdd(counts + q * 4 + col + 1, c); }
   }
 }
 
@@ -239,7 +226,7 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 // event record / wait are capture-safe, so the pattern also works inside a CUDA graph capture.
 struct SideStream {
   cudaStream_t stream = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr, mid = nullptr, fork2 = nullptr;
   int device = -1;
 };
 static int side_stream(SideStream** out) {
@@ -251,6 +238,8 @@ static int side_stream(SideStream** out) {
     KGE_CUDA_OK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     KGE_CUDA_OK(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
     KGE_CUDA_OK(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
+    KGE_CUDA_OK(cudaEventCreateWithFlags(&s.mid, cudaEventDisableTiming));
+    KGE_CUDA_OK(cudaEventCreateWithFlags(&s.fork2, cudaEventDisableTiming));
     s.device = dev;
   }
   *out = &s;
@@ -333,6 +322,31 @@ extern "C" int kge_rank_1vsall(const kge_model_t* m, const kge_model_t* mq, int6
     if (rc) return rc;
     KGE_CUDA_OK(cudaEventRecord(side->fork, main_st));          // after candidate preparation
     KGE_CUDA_OK(cudaStreamWaitEvent(side->stream, side->fork, 0));
+  }
+  // Both directions on the tensor cores: their query preparations run side by side, ONE launch sweeps both
+  // (grid.z = 2: same candidate operands; the launch / pipeline-ramp / drain overhead — a third of a 25 us
+  // sweep at the FB15k-237 shape — is paid once and the tile units of both directions balance over the SMs),
+  // then the two exact-resolution chains run side by side again.
+  if (use_tc && two_streams) {
+    const RankFilter Ft = {filt_t_ptr, filt_t_idx, filt_t_nnz, tgt_t, row_lo, row_hi};
+    const RankFilter Fh = {filt_h_ptr, filt_h_idx, filt_h_nnz, tgt_h, row_lo, row_hi};
+    rc = tiled_sweep(m, mq, 0, qh, qr, qt, thr_t, Q, nc, counts, 0, tiled_ws, true, &Ft, nullptr, nullptr, main_st, kSweepPrep);
+    if (rc) return rc;
+    rc = tiled_sweep(m, mq, 1, qh, qr, qt, thr_h, Q, nc, counts, 2, tiled_ws, true, &Fh, nullptr, nullptr, side->stream, kSweepPrep);
+    if (rc) return rc;
+    KGE_CUDA_OK(cudaEventRecord(side->mid, side->stream));
+    KGE_CUDA_OK(cudaStreamWaitEvent(main_st, side->mid, 0));
+    rc = tiled_sweep(m, mq, 0, qh, qr, qt, thr_t, Q, nc, counts, 0, tiled_ws, true, &Ft, nullptr, nullptr, main_st, kSweepTc, true);
+    if (rc) return rc;
+    KGE_CUDA_OK(cudaEventRecord(side->fork2, main_st));
+    KGE_CUDA_OK(cudaStreamWaitEvent(side->stream, side->fork2, 0));
+    rc = tiled_sweep(m, mq, 0, qh, qr, qt, thr_t, Q, nc, counts, 0, tiled_ws, true, &Ft, nullptr, nullptr, main_st, kSweepPost);
+    if (rc) return rc;
+    rc = tiled_sweep(m, mq, 1, qh, qr, qt, thr_h, Q, nc, counts, 2, tiled_ws, true, &Fh, nullptr, nullptr, side->stream, kSweepPost);
+    if (rc) return rc;
+    KGE_CUDA_OK(cudaEventRecord(side->join, side->stream));
+    KGE_CUDA_OK(cudaStreamWaitEvent(main_st, side->join, 0));
+    return KGE_OK;
   }
   for (int dir = 0; dir < 2; ++dir) {
     if (dir == 0 && (flags & KGE_RANK_HEAD_ONLY)) continue;
@@ -427,6 +441,11 @@ extern "C" int kge_rank_tc_probe(const kge_model_t* m, const kge_model_t* mq, in
   if (rc) return rc;
   return tiled_sweep(m, mq, direction, qh, qr, qt, thr, Q, nc, counts, direction == 0 ? 0 : 2, tiled_ws, true, nullptr,
                      dots, tau, st);
+}
+
+extern "C" int kge_rank_last_sweep_directions(void) {
+  SweepProfile* sp = sweep_profile(0);
+  return sp->valid ? sp->ndirs : 0;
 }
 
 extern "C" int kge_rank_last_sweep_ms(int direction, float* ms) {

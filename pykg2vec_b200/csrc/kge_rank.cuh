@@ -17,20 +17,25 @@ int tiled_prepare_candidates(const kge_model_t* m, int64_t nc, void* ws, int64_t
 // tc_dbg (tests): optional [Q][nc] raw tensor-core accumulators; tc_tau_out: optional [Q][4] band
 // coefficients followed by the nc candidate norm bounds.
 struct RankFilter;
+// phases (bit mask; the driver splits a direction's chain so that ONE tensor-core launch can sweep both
+// directions): kSweepPrep = query vectors, thresholds (+ CP's per-direction candidate operands);
+// kSweepTc = the tensor-core launch (tc_both: of both directions — call it for dir 0 only);
+// kSweepPost = level 2 + the fp32 sweep (the whole sweep when !use_tc, else the flag-gated fallback).
+constexpr int kSweepPrep = 1, kSweepTc = 2, kSweepPost = 4, kSweepAll = 7;
 int tiled_sweep(const kge_model_t* m, const kge_model_t* mq, int dir, const int64_t* qh,
                 const int64_t* qr, const int64_t* qt, float* thr, int64_t Q, int64_t nc,
                 int32_t* counts, int col, void* ws, bool use_tc, const RankFilter* filter, float* tc_dbg,
-                float* tc_tau_out, cudaStream_t st);
+                float* tc_tau_out, cudaStream_t st, int phases = kSweepAll, bool tc_both = false);
 
 // Measurement hook (KGE_RANK_PROFILE): CUDA events recorded immediately around the launch of a
 // direction's main sweep kernel (tensor-core or fp32) on the stream it is launched on.
-struct SweepProfile { cudaEvent_t beg = nullptr, end = nullptr; bool armed = false, valid = false; };
+struct SweepProfile { cudaEvent_t beg = nullptr, end = nullptr; bool armed = false, valid = false; int ndirs = 1; };
 SweepProfile* sweep_profile(int dir);
 
 // ---- tensor-core sweep (kge_rank_tc.cu) -------------------------------------------------------------
 struct TcDirBuffers {
   int32_t* tc_counts;          // [Q] certain counts of level 1 (+ the resolved pairs of level 2)
-  unsigned* ctrl;              // [0] pair-list length, [1] overflow, [2] ticket, [3] run-the-fp32-sweep flag
+  unsigned* ctrl;              // [0] pair-list length, [1] overflow ([2], [3] unused)
   unsigned long long* list;    // (q << 32 | local candidate row)
   unsigned cap;
   const float* tau;            // [Q][4] band coefficients (centre, a, b, e) of tc_query_finish
@@ -45,11 +50,12 @@ int tc_prepare_candidates(const kge_model_t* m, const float* const src[2], int64
                           float* scratch, cudaStream_t st);
 struct TcQueryArgs;
 TcQueryArgs tc_query_args(const kge_model_t* m, int dir, void* tcws, int64_t Q);
-int tc_sweep(const kge_model_t* m, int dir, int64_t Q, int64_t nc, void* tcws, TcDirBuffers* out, float* dbg,
-             cudaStream_t st);
-// Level 2 (kge_rank.cu): exact fp32 re-evaluation of the listed pairs, then the last CTA adds the
-// direction's counts to counts[q*4+col], counts[q*4+col+1] — or, if the list overflowed, raises
-// ctrl[3] so that the fp32 sweep enqueued next does the whole direction instead.
+// ndirs == 2 (dir == 0): both directions in one launch (same candidate operands, grid.z = 2)
+int tc_sweep(const kge_model_t* m, int dir, int ndirs, int64_t Q, int64_t nc, void* tcws, float* dbg, cudaStream_t st);
+void tc_dir_buffers(const kge_model_t* m, int dir, int64_t Q, void* tcws, TcDirBuffers* out);
+// Level 2 (kge_rank.cu): exact fp32 re-evaluation of the listed pairs into tc_counts.  The fp32 sweep
+// enqueued next either commits the direction (counts[q*4+col], counts[q*4+col+1] += tc_counts[q]) or, if the
+// list overflowed, ranks the whole direction itself.
 // The same kernel also applies the direction's filter corrections (the entries of the CSR filter that
 // outrank the target are subtracted from the filtered column) — they are exact re-evaluations of
 // listed pairs too —, so the tensor-core path needs no separate filter pass.

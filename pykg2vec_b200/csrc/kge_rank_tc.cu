@@ -50,21 +50,27 @@ constexpr int kTcTmemCols = 256;  // two accumulator stages of kTcBN fp32 column
 constexpr int kTcMaxStages = 8;
 constexpr int kTcResidentMaxK = 256;                   // query block stays in smem when Kp <= 256
 
-struct TcParams {
+// The per-direction buffers of a launch: blockIdx.z picks the set (one launch sweeps BOTH directions of a rank
+// call — same candidate operands, different query operands — so that the fixed cost of a launch, the pipeline
+// ramp and the last tile's drain are paid once, and 2 x qblocks x ntiles tile units balance over the SMs).
+struct TcDirView {
   const float* tau;        // [Q][4]: centre, a, b, e (tc_query_finish)
-  const float* cn;         // [nc] per-candidate norm bound n_c (tc_prep_cand_kernel)
   int32_t* tc_counts;      // [Q]
-  unsigned* ctrl;          // [0] list length, [1] overflow, [2] ticket, [3] run-fallback flag
+  unsigned* ctrl;          // [0] list length, [1] overflow ([2], [3] unused)
   unsigned long long* list;
+  const __nv_bfloat16* A0; const __nv_bfloat16* A1;   // [Q][Kp] query operands (read by the TMEM fill)
+  float* dbg;              // optional [Q][nc] raw accumulators (tests)
+};
+struct TcParams {
+  TcDirView D[2];
+  const float* cn;         // [nc] per-candidate norm bound n_c (tc_prep_cand_kernel)
   unsigned cap;
   int64_t Q, nc;
   int Kp, nkb, a_resident, nstages;
   int bk;                  // k-block width in bf16 elements (64 or 32)
   int a_tmem;              // the query block's operands live in TENSOR MEMORY (Kp <= 256): only the candidate tiles use smem
-  const __nv_bfloat16* A0; const __nv_bfloat16* A1;   // [Q][Kp] query operands (read by the TMEM fill)
   uint32_t tile_bytes;     // one operand k-block tile: 128 rows x bk x 2 bytes
   int tiles_per_cta, ntiles;
-  float* dbg;              // optional [Q][nc] raw accumulators (tests)
   long long* trace;        // optional timeline of CTA (0,0): [3 roles][64] clock64 stamps (kge_debug_set_tc_trace)
   int epi_mode;            // measurement aid (KGE_TC_EPI_MODE): 0 normal, 1 load only, 2 count only (no band listing)
   // exact-width last k-block: when Kp leaves 16 or 32 columns for it, it is staged as a narrow tile
@@ -72,7 +78,8 @@ struct TcParams {
   int tail_cols;
   uint32_t tail_bytes;     // bytes of one operand's tail tile (128 rows x tail_cols x 2)
 };
-struct TcMaps { CUtensorMap a0, a1, b0, b1, a0t, a1t, b0t, b1t; };   // in PAIR mode the b* boxes hold 64 rows
+// a*: query operands of blockIdx.z == 0, c*: of blockIdx.z == 1; *t: the narrow tail k-block; in PAIR mode the b* boxes hold 64 rows
+struct TcMaps { CUtensorMap a0, a1, b0, b1, a0t, a1t, b0t, b1t, c0, c1, c0t, c1t; };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 KGE_DEV uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -195,7 +202,7 @@ KGE_DEV void tc_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" :
 // timeline stamps of CTA (0,0) (measurement aid; P.trace is null in normal operation)
 #define TC_STAMP(role, slot)                                                                         \
   do {                                                                                               \
-    if (P.trace && blockIdx.x == 0 && blockIdx.y == 0 && (slot) < 64) P.trace[(role) * 64 + (slot)] = clock64(); \
+    if (P.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (slot) < 64 && ((slot) < 62 || (slot) == 63)) P.trace[(role) * 64 + (slot)] = clock64(); \
   } while (0)
 
 // Pair-list slots are handed out per WARP in blocks (16 slots) reserved with one global atomic (a returning atomic
@@ -206,20 +213,20 @@ struct TcListState { unsigned base, used, size; };
 constexpr unsigned long long kTcListHole = ~0ull;
 constexpr unsigned kTcListBlock = 16;
 
-KGE_DEV void tc_list_reserve(TcListState& L, const TcParams& P, int lane, unsigned need) {
+KGE_DEV void tc_list_reserve(TcListState& L, const TcParams& P, const TcDirView& V, int lane, unsigned need) {
   unsigned b = 0;
   if (lane == 0) {
-    b = atomicAdd(&P.ctrl[0], need);
-    if (b + need > P.cap) P.ctrl[1] = 1u;   // overflow: the exact fp32 sweep takes over (list writes are bounded)
+    b = atomicAdd(&V.ctrl[0], need);
+    if (b + need > P.cap) V.ctrl[1] = 1u;   // overflow: the exact fp32 sweep takes over (list writes are bounded)
   }
   L.base = __shfl_sync(0xffffffffu, b, 0);
   L.used = 0u;
   L.size = need;
 }
 
-KGE_DEV void tc_list_pad(TcListState& L, const TcParams& P, int lane) {
+KGE_DEV void tc_list_pad(TcListState& L, const TcParams& P, const TcDirView& V, int lane) {
   for (unsigned i = L.used + (unsigned)lane; i < L.size; i += 32u)
-    if (L.base + i < P.cap) P.list[L.base + i] = kTcListHole;
+    if (L.base + i < P.cap) V.list[L.base + i] = kTcListHole;
   L.used = L.size;
 }
 
@@ -234,7 +241,7 @@ KGE_DEV void tc_band_eval(const TcBand& Bq, float x, float n, float& u, float& h
   u = __fsub_rn(x, Bq.centre);
 }
 KGE_DEV int tc_scan_chunk(const uint32_t (&v)[32], int nv, const TcBand& Bq, float nl, int64_t q, int64_t cbase,
-                          bool live, const TcParams& P, TcListState& L, int lane, int& ev, bool stamp) {
+                          bool live, const TcParams& P, const TcDirView& V, TcListState& L, int lane, int& ev, bool stamp) {
   if (P.epi_mode == 1) return (int)(v[0] & 1u) + (int)(v[31] & 1u);
   if (stamp) TC_STAMP(2, ev++);
   int hi0 = 0, hi1 = 0, lo0 = 0, lo1 = 0;
@@ -291,23 +298,23 @@ KGE_DEV int tc_scan_chunk(const uint32_t (&v)[32], int nv, const TcBand& Bq, flo
     }
     const unsigned total = (unsigned)__shfl_sync(0xffffffffu, incl, 31);
     if (L.used + total > L.size) {   // next block (rare: the first block is reserved before the first tile)
-      tc_list_pad(L, P, lane);
-      tc_list_reserve(L, P, lane, total > kTcListBlock ? total : kTcListBlock);
+      tc_list_pad(L, P, V, lane);
+      tc_list_reserve(L, P, V, lane, total > kTcListBlock ? total : kTcListBlock);
     }
     unsigned k = L.base + L.used + (unsigned)(incl - mycnt);
     const int64_t qrow0 = q - lane;   // the warp's rows are consecutive queries
     while (mine) {
       const int r = __ffs((int)mine) - 1;
       mine &= mine - 1u;
-      if (k < P.cap) P.list[k] = ((unsigned long long)(qrow0 + r) << 32) | (unsigned long long)(cbase + lane);
+      if (k < P.cap) V.list[k] = ((unsigned long long)(qrow0 + r) << 32) | (unsigned long long)(cbase + lane);
       ++k;
     }
     L.used += total;
   }
-  if (P.dbg && live) {
+  if (V.dbg && live) {
 #pragma unroll
     for (int j = 0; j < 32; ++j)
-      if (j < nv) P.dbg[(size_t)q * (size_t)P.nc + (size_t)(cbase + j)] = __uint_as_float(v[j]);
+      if (j < nv) V.dbg[(size_t)q * (size_t)P.nc + (size_t)(cbase + j)] = __uint_as_float(v[j]);
   }
   return hi;
 }
@@ -352,7 +359,20 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int64_t q0 = (int64_t)blockIdx.y * kTcBM;
+  const bool zdir = blockIdx.z != 0;
+  const TcDirView& V = zdir ? P.D[1] : P.D[0];
+  const CUtensorMap* const ma0 = zdir ? &TM.c0 : &TM.a0;
+  const CUtensorMap* const ma1 = zdir ? &TM.c1 : &TM.a1;
+  const CUtensorMap* const ma0t = zdir ? &TM.c0t : &TM.a0t;
+  const CUtensorMap* const ma1t = zdir ? &TM.c1t : &TM.a1t;
   if (threadIdx.x == 0) TC_STAMP(2, 63);   // kernel entry of CTA (0,0)
+  // wall-clock span of EVERY CTA (%globaltimer, ns) behind the three role timelines: launch skew and stragglers
+  const unsigned cta_lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  if (P.trace && threadIdx.x == 0 && cta_lin < 1024u) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    P.trace[192 + 2 * cta_lin] = (long long)ns;
+  }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.nstages; ++s) { tc_mbar_init(&full[s], 1); tc_mbar_init(&empty[s], PAIR ? 2 : 1); }
@@ -393,8 +413,8 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
           const uint32_t sb = st_base + (uint32_t)stage * st_bytes;
           if (with_a) {
             const uint32_t dst = a_base + (uint32_t)kb * 2u * P.tile_bytes;
-            tc_tma_load_2d(dst, tail ? &TM.a0t : &TM.a0, kb * P.bk, (int)q0, &full[stage]);
-            tc_tma_load_2d(dst + tb, tail ? &TM.a1t : &TM.a1, kb * P.bk, (int)q0, &full[stage]);
+            tc_tma_load_2d(dst, tail ? ma0t : ma0, kb * P.bk, (int)q0, &full[stage]);
+            tc_tma_load_2d(dst + tb, tail ? ma1t : ma1, kb * P.bk, (int)q0, &full[stage]);
           }
           if (PAIR) {   // my half of the candidate rows, into both CTAs (the peer sends the other half)
             const uint32_t ho = crank * (tb >> 1);
@@ -406,8 +426,8 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
             tc_tma_load_2d(sb + tb, tail ? &TM.b1t : &TM.b1, kb * P.bk, row, &full[stage]);
           }
           if (!P.a_resident) {
-            tc_tma_load_2d(sb + 2u * tb, tail ? &TM.a0t : &TM.a0, kb * P.bk, (int)q0, &full[stage]);
-            tc_tma_load_2d(sb + 3u * tb, tail ? &TM.a1t : &TM.a1, kb * P.bk, (int)q0, &full[stage]);
+            tc_tma_load_2d(sb + 2u * tb, tail ? ma0t : ma0, kb * P.bk, (int)q0, &full[stage]);
+            tc_tma_load_2d(sb + 3u * tb, tail ? ma1t : ma1, kb * P.bk, (int)q0, &full[stage]);
           }
           if (++stage == P.nstages) { stage = 0; phase ^= 1u; }
         }
@@ -471,14 +491,14 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
     const bool live = q < P.Q;
     TcBand Bq = {INFINITY, 0.f, 0.f, 0.f};   // rows beyond Q: u = -inf -> nothing counted, nothing listed
     if (live) {
-      const float4 tq = __ldg(reinterpret_cast<const float4*>(P.tau) + q);
+      const float4 tq = __ldg(reinterpret_cast<const float4*>(V.tau) + q);
       Bq.centre = tq.x; Bq.a = tq.y; Bq.b = tq.z; Bq.e = tq.w;
     }
     if (P.a_tmem) {
       // this thread's query row -> tensor memory: warps 2-5 write the high parts a0, warps 6-9 the low parts a1;
       // a row is Kp bf16 = Kp/2 32-bit columns (two consecutive k per column), rows beyond Q are zeros
       const int half = (warp - 2) >> 2;
-      const __nv_bfloat16* src = (half == 0 ? P.A0 : P.A1) + (size_t)(live ? q : 0) * P.Kp;
+      const __nv_bfloat16* src = (half == 0 ? V.A0 : V.A1) + (size_t)(live ? q : 0) * P.Kp;
       const uint32_t tdst = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(2 * kTcBN) + (uint32_t)(half * (P.Kp >> 1));
       for (int c = 0; c < (P.Kp >> 1); c += 8) {   // Kp is a multiple of 16: whole groups of 8 columns
         uint4 lo = make_uint4(0u, 0u, 0u, 0u), hi = lo;
@@ -496,7 +516,7 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
     }
     int cnt = 0;
     TcListState L = {0u, 0u, 0u};
-    tc_list_reserve(L, P, lane, kTcListBlock);   // the warp's first block: the atomic's round trip hides behind the first tile's MMAs
+    tc_list_reserve(L, P, V, lane, kTcListBlock);   // the warp's first block: the atomic's round trip hides behind the first tile's MMAs
     int ev = 0;
     if (warp == 2 && lane == 0) TC_STAMP(2, ev++);
     for (int t = 0; t < ntl; ++t) {
@@ -522,10 +542,10 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
         tc_tmem_ld32(taddr + (uint32_t)c0, va);
         tc_tmem_wait_ld();
         if (nchunks > 1) tc_tmem_ld32(taddr + (uint32_t)(c0 + 32), vb);
-        cnt += tc_scan_chunk(va, min(32, nloc), Bq, nla, q, cbase + c0, live, P, L, lane, ev, warp == 2 && lane == 0);
+        cnt += tc_scan_chunk(va, min(32, nloc), Bq, nla, q, cbase + c0, live, P, V, L, lane, ev, warp == 2 && lane == 0);
         if (nchunks > 1) {
           tc_tmem_wait_ld();
-          cnt += tc_scan_chunk(vb, min(32, nloc - 32), Bq, nlb, q, cbase + c0 + 32, live, P, L, lane, ev, warp == 2 && lane == 0);
+          cnt += tc_scan_chunk(vb, min(32, nloc - 32), Bq, nlb, q, cbase + c0 + 32, live, P, V, L, lane, ev, warp == 2 && lane == 0);
         }
       }
       tc_fence_before();
@@ -533,11 +553,17 @@ tc_sweep_kernel(const __grid_constant__ TcParams P, const __grid_constant__ TcMa
       if (lane == 0) tc_mbar_arrive(&tmem_empty[as]);
       if (warp == 2 && lane == 0) TC_STAMP(2, ev++);
     }
-    tc_list_pad(L, P, lane);   // the unused slots of the warp's last block become holes
-    if (live && cnt) atomicAdd(P.tc_counts + q, cnt);
+    tc_list_pad(L, P, V, lane);   // the unused slots of the warp's last block become holes
+    if (live && cnt) atomicAdd(V.tc_counts + q, cnt);
   }
   tc_fence_before();
   __syncthreads();
+  if (P.trace && threadIdx.x == 0 && cta_lin < 1024u) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    P.trace[192 + 2 * cta_lin + 1] = (long long)ns;
+    if (cta_lin == 0) P.trace[2 * 64 + 62] = clock64();   // CTA (0,0,0): cycles at exit, next to its ns span
+  }
   if (PAIR) tc_cluster_sync();   // neither CTA leaves while the peer can still multicast into it / arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
@@ -739,24 +765,36 @@ TcQueryArgs tc_query_args(const kge_model_t* m, int dir, void* tcws, int64_t Q) 
   return T;
 }
 
-// Level 1 of one direction (the query operands and thresholds were written by prep_query_kernel): the
-// tensor-core sweep.  On return (in stream order) tc_counts[q] holds the certain counts and list/ctrl
-// the ambiguous pairs.
-int tc_sweep(const kge_model_t* m, int dir, int64_t Q, int64_t nc, void* tcws, TcDirBuffers* out, float* dbg,
-             cudaStream_t st) {
+// The buffers level 2 reads for direction `dir` (no launch).
+void tc_dir_buffers(const kge_model_t* m, int dir, int64_t Q, void* tcws, TcDirBuffers* out) {
+  const TcLayout L = tc_layout(m, Q);
+  char* w = reinterpret_cast<char*>(tcws);
+  const TcQueryArgs T = tc_query_args(m, dir, tcws, Q);
+  out->tc_counts = T.tc_counts; out->ctrl = T.ctrl;
+  out->list = reinterpret_cast<unsigned long long*>(w + L.list[dir]);
+  out->cap = tc_list_capacity(Q); out->tau = T.tau; out->cn = reinterpret_cast<const float*>(w + L.cn);
+}
+
+// Level 1 (the query operands and thresholds were written by prep_query_kernel): the tensor-core sweep of
+// direction `dir`, or — ndirs == 2, dir == 0 — of both directions in ONE launch (grid.z = 2).  On return (in
+// stream order) tc_counts[q] holds the certain counts and list/ctrl the ambiguous pairs of each direction swept.
+int tc_sweep(const kge_model_t* m, int dir, int ndirs, int64_t Q, int64_t nc, void* tcws, float* dbg, cudaStream_t st) {
   const TcLayout L = tc_layout(m, Q);
   char* w = reinterpret_cast<char*>(tcws);
   const int Kp = tc_kp(m);
-  const TcQueryArgs T = tc_query_args(m, dir, tcws, Q);
-  __nv_bfloat16* A0 = T.A0;
-  __nv_bfloat16* A1 = T.A1;
-  float* tau = T.tau;
-  int32_t* cnt = T.tc_counts;
-  unsigned* ctrl = T.ctrl;
-  unsigned long long* list = reinterpret_cast<unsigned long long*>(w + L.list[dir]);
-
+  if (ndirs < 1 || ndirs > 2 || (ndirs == 2 && dir != 0)) { set_error("tc_sweep: bad direction set"); return KGE_EINVAL; }
   TcParams P;
-  P.tau = tau; P.cn = reinterpret_cast<const float*>(w + L.cn); P.tc_counts = cnt; P.ctrl = ctrl; P.list = list; P.cap = tc_list_capacity(Q);
+  const __nv_bfloat16* A0[2] = {nullptr, nullptr};
+  const __nv_bfloat16* A1[2] = {nullptr, nullptr};
+  for (int z = 0; z < 2; ++z) {
+    const int dz = z < ndirs ? dir + z : dir;   // (an unused second set mirrors the first)
+    const TcQueryArgs T = tc_query_args(m, dz, tcws, Q);
+    P.D[z].tau = T.tau; P.D[z].tc_counts = T.tc_counts; P.D[z].ctrl = T.ctrl;
+    P.D[z].list = reinterpret_cast<unsigned long long*>(w + L.list[dz]);
+    P.D[z].A0 = T.A0; P.D[z].A1 = T.A1; P.D[z].dbg = (z == 0) ? dbg : nullptr;
+    A0[z] = T.A0; A1[z] = T.A1;
+  }
+  P.cn = reinterpret_cast<const float*>(w + L.cn); P.cap = tc_list_capacity(Q);
   // k-block width: 64 columns (128-byte swizzle rows).  32-column blocks (64-byte rows) would give 7 pipeline
   // stages instead of 3, but measured SLOWER (26.6 vs 24.5 us, profiles/r2_tc_trace_v6.jsonl): the operand
   // stream is bound by delivered L2 bandwidth (~28 B/cycle per SM with 116 SMs pulling = 6.2 TB/s), not by
@@ -779,7 +817,6 @@ int tc_sweep(const kge_model_t* m, int dir, int64_t Q, int64_t nc, void* tcws, T
   // and the MMA cadence does not change — shared-memory bandwidth was not the bound either.
   P.a_tmem = 0;
   if (const char* e = getenv("KGE_TC_ATMEM")) { if (atoi(e) != 0 && P.a_resident && Kp <= 256) P.a_tmem = 1; }
-  P.A0 = A0; P.A1 = A1;
   const size_t budget = 227 * 1024 - 2048;   // control block + alignment slack
   const size_t a_bytes = (!P.a_resident || P.a_tmem) ? 0
       : (P.tail_cols ? (size_t)(P.nkb - 1) * 2 * P.tile_bytes + 2 * (size_t)P.tail_bytes : (size_t)P.nkb * 2 * P.tile_bytes);
@@ -790,12 +827,12 @@ int tc_sweep(const kge_model_t* m, int dir, int64_t Q, int64_t nc, void* tcws, T
   P.nstages = nstages;
   P.ntiles = (int)((nc + kTcBN - 1) / kTcBN);
   const int qblocks = (int)((Q + kTcBM - 1) / kTcBM);
-  int splits = (sm_count() + qblocks - 1) / qblocks;
+  // one CTA per SM: as many runs of tiles as fit in ONE wave over (directions x query blocks)
+  int splits = sm_count() / (qblocks * ndirs);
   if (splits < 1) splits = 1;
   if (splits > P.ntiles) splits = P.ntiles;
   P.tiles_per_cta = (P.ntiles + splits - 1) / splits;
   splits = (P.ntiles + P.tiles_per_cta - 1) / P.tiles_per_cta;
-  P.dbg = dbg;
   P.trace = g_tc_trace;
   P.epi_mode = 0;
   if (const char* e = getenv("KGE_TC_EPI_MODE")) P.epi_mode = atoi(e);   // measurement aid: wrong counts unless 0
@@ -807,14 +844,18 @@ int tc_sweep(const kge_model_t* m, int dir, int64_t Q, int64_t nc, void* tcws, T
   if (const char* e = getenv("KGE_TC_PAIR")) pair = atoi(e) != 0;
   const int brows = pair ? kTcBN / 2 : kTcBN;
   TcMaps TM;
-  int rc = tc_make_map(&TM.a0, A0, (uint64_t)Q, (uint64_t)Kp, bk); if (rc) return rc;
-  rc = tc_make_map(&TM.a1, A1, (uint64_t)Q, (uint64_t)Kp, bk); if (rc) return rc;
+  int rc = tc_make_map(&TM.a0, A0[0], (uint64_t)Q, (uint64_t)Kp, bk); if (rc) return rc;
+  rc = tc_make_map(&TM.a1, A1[0], (uint64_t)Q, (uint64_t)Kp, bk); if (rc) return rc;
+  rc = tc_make_map(&TM.c0, A0[1], (uint64_t)Q, (uint64_t)Kp, bk); if (rc) return rc;
+  rc = tc_make_map(&TM.c1, A1[1], (uint64_t)Q, (uint64_t)Kp, bk); if (rc) return rc;
   rc = tc_make_map(&TM.b0, w + L.b[0], (uint64_t)nc, (uint64_t)Kp, bk, brows); if (rc) return rc;
   rc = tc_make_map(&TM.b1, w + L.b[1], (uint64_t)nc, (uint64_t)Kp, bk, brows); if (rc) return rc;
-  TM.a0t = TM.a0; TM.a1t = TM.a1; TM.b0t = TM.b0; TM.b1t = TM.b1;
+  TM.a0t = TM.a0; TM.a1t = TM.a1; TM.b0t = TM.b0; TM.b1t = TM.b1; TM.c0t = TM.c0; TM.c1t = TM.c1;
   if (P.tail_cols) {
-    rc = tc_make_map(&TM.a0t, A0, (uint64_t)Q, (uint64_t)Kp, P.tail_cols); if (rc) return rc;
-    rc = tc_make_map(&TM.a1t, A1, (uint64_t)Q, (uint64_t)Kp, P.tail_cols); if (rc) return rc;
+    rc = tc_make_map(&TM.a0t, A0[0], (uint64_t)Q, (uint64_t)Kp, P.tail_cols); if (rc) return rc;
+    rc = tc_make_map(&TM.a1t, A1[0], (uint64_t)Q, (uint64_t)Kp, P.tail_cols); if (rc) return rc;
+    rc = tc_make_map(&TM.c0t, A0[1], (uint64_t)Q, (uint64_t)Kp, P.tail_cols); if (rc) return rc;
+    rc = tc_make_map(&TM.c1t, A1[1], (uint64_t)Q, (uint64_t)Kp, P.tail_cols); if (rc) return rc;
     rc = tc_make_map(&TM.b0t, w + L.b[0], (uint64_t)nc, (uint64_t)Kp, P.tail_cols, brows); if (rc) return rc;
     rc = tc_make_map(&TM.b1t, w + L.b[1], (uint64_t)nc, (uint64_t)Kp, P.tail_cols, brows); if (rc) return rc;
   }
@@ -826,7 +867,7 @@ int tc_sweep(const kge_model_t* m, int dir, int64_t Q, int64_t nc, void* tcws, T
     const unsigned qb2 = (unsigned)((qblocks + 1) & ~1);
     KGE_CUDA_OK(cudaFuncSetAttribute(tc_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)splits, qb2, 1);
+    cfg.gridDim = dim3((unsigned)splits, qb2, (unsigned)ndirs);
     cfg.blockDim = dim3(kTcThreads, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
@@ -840,11 +881,10 @@ int tc_sweep(const kge_model_t* m, int dir, int64_t Q, int64_t nc, void* tcws, T
   } else {
     KGE_CUDA_OK(cudaFuncSetAttribute(tc_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (sp->armed) KGE_CUDA_OK(cudaEventRecord(sp->beg, st));
-    tc_sweep_kernel<false><<<dim3((unsigned)splits, (unsigned)qblocks), kTcThreads, smem, st>>>(P, TM);
+    tc_sweep_kernel<false><<<dim3((unsigned)splits, (unsigned)qblocks, (unsigned)ndirs), kTcThreads, smem, st>>>(P, TM);
     KGE_CHECK_LAUNCH("tc_sweep_kernel");
   }
-  if (sp->armed) { KGE_CUDA_OK(cudaEventRecord(sp->end, st)); sp->valid = true; }
-  out->tc_counts = cnt; out->ctrl = ctrl; out->list = list; out->cap = P.cap; out->tau = tau; out->cn = P.cn;
+  if (sp->armed) { KGE_CUDA_OK(cudaEventRecord(sp->end, st)); sp->valid = true; sp->ndirs = ndirs; }
   return KGE_OK;
 }
 

@@ -57,9 +57,12 @@ struct TiledParams {
   int col, l1;
   int fin;      // DOT ops: 0 -> -sum ; 1 -> -sigmoid(sum) (HoLE) ; 2 -> -clamp(sum, +-20) (SimplE)
   float margin;
-  // tensor-core path: the fp32 sweep is enqueued behind it as the exact fallback and runs only when
-  // the device raised this flag (ambiguous-pair list overflow); nullptr -> always run
-  const unsigned* run_flag;
+  // tensor-core path (tc_ctrl != nullptr): this sweep is enqueued behind the two levels as the exact fallback.
+  // When the ambiguous-pair list did NOT overflow (tc_ctrl[0] <= tc_cap and tc_ctrl[1] == 0) it only commits the
+  // direction — counts[q*4+col], counts[q*4+col+1] += tc_counts[q] — and returns; else it ranks the direction.
+  const unsigned* tc_ctrl;
+  unsigned tc_cap;
+  const int32_t* tc_counts;
 };
 
 // ---- mbarrier / bulk-copy primitives ------------------------------------------------------
@@ -206,8 +209,19 @@ __device__ __forceinline__ void sweep_tiled_body(const TiledParams& P, const Til
   const int qrows = (int)min((int64_t)QBLK, P.Q - q0);
   const int t0 = blockIdx.x * P.tiles_per_cta;
   const int ntile_local = min(P.tiles_per_cta, P.ntiles - t0);
+  if (P.tc_ctrl != nullptr) {
+    const unsigned listed = *reinterpret_cast<const volatile unsigned*>(P.tc_ctrl);
+    const bool overflow = listed > P.tc_cap || *reinterpret_cast<const volatile unsigned*>(P.tc_ctrl + 1) != 0u;
+    if (!overflow) {   // the usual case: commit the tensor-core levels' counts (one thread per query) and leave
+      const int64_t q = ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+      if (q < P.Q) {
+        const int c = __ldg(P.tc_counts + q);
+        if (c) { atomicAdd(P.counts + q * 4 + P.col, c); atomicAdd(P.counts + q * 4 + P.col + 1, c); }
+      }
+      return;
+    }
+  }
   if (ntile_local <= 0) return;
-  if (P.run_flag != nullptr && *reinterpret_cast<const volatile unsigned*>(P.run_flag) == 0u) return;
   const int T = ntile_local * P.nslabs;
   const bool sum_domain = (OP == OP_TRANS_T || OP == OP_TRANS_H) && !L1 && P.qscale == nullptr;
 
@@ -404,11 +418,12 @@ prep_query_kernel(ModelParams P, const int64_t* __restrict__ qh, const int64_t* 
   float* scratch = reinterpret_cast<float*>(smem_f4) + (size_t)(threadIdx.x >> 3) * scratch_floats;
   const int lane = threadIdx.x & 7;
   const int64_t q = (int64_t)blockIdx.x * 32 + (threadIdx.x >> 3);
-  if (TC.A0 && blockIdx.x == 0 && threadIdx.x < 4) TC.ctrl[threadIdx.x] = 0u;   // pair-list length, overflow, ticket, fallback flag
+  if (TC.A0 && blockIdx.x == 0 && threadIdx.x < 4) TC.ctrl[threadIdx.x] = 0u;   // pair-list length, overflow (+ 2 unused words)
   if (q >= Q) return;
   const int d = P.d, nch = (d + 3) >> 2, nchp = dp >> 2;
   TripleRows R;
   resolve_rows<MODEL>(R, P, P.qtab, P.qtab, P.qtab, __ldg(qh + q), __ldg(qr + q), __ldg(qt + q));
+  prefetch_triple_rows(R, P.d, P.dr, lane);
   // threshold = the target's own score in this direction's grouping (== kge_score_fwd)
   const float s_target = score_group<MODEL, VEC, DIR == 0 ? KGE_GROUP_TAIL : KGE_GROUP_HEAD>(R, P, lane, scratch);
   if (lane == 0) thr[q] = s_target;
@@ -723,7 +738,7 @@ static int launch_sweep(const TiledParams& P, int QBLK, size_t smem, cudaStream_
 int tiled_sweep(const kge_model_t* m, const kge_model_t* mq, int dir, const int64_t* qh,
                 const int64_t* qr, const int64_t* qt, float* thr, int64_t Q, int64_t nc,
                 int32_t* counts, int col, void* ws, bool use_tc, const RankFilter* filter, float* tc_dbg,
-                float* tc_tau_out, cudaStream_t st) {
+                float* tc_tau_out, cudaStream_t st, int phases, bool tc_both) {
   const int model = m->model;
   const int d = m->dim, dp = dp_of(m);
   const int op = (model == KGE_TRANSE || model == KGE_TRANSM) ? (dir == 0 ? OP_TRANS_T : OP_TRANS_H)
@@ -742,6 +757,7 @@ int tiled_sweep(const kge_model_t* m, const kge_model_t* mq, int dir, const int6
   float* qscale = reinterpret_cast<float*>(w + 2 * qvec_bytes + (size_t)dir * qs_bytes);
   float* cscratch = cand_scratch_ptr(m, ws, Q);
 
+  if (phases & kSweepPrep) {
   // 0. CP sweeps the object table for tails and the subject table for heads: its tensor-core candidate
   // operands (and max |c|^2, which the query thresholds read) are per direction and come first
   if (model == KGE_CP && use_tc) {
@@ -784,6 +800,7 @@ int tiled_sweep(const kge_model_t* m, const kge_model_t* mq, int dir, const int6
   }
 #undef PREP
   KGE_CHECK_LAUNCH("prep_query_kernel");
+  }   // kSweepPrep
 
   // 2. candidate arrays (scratch copies were produced by tiled_prepare_candidates)
   TiledParams P;
@@ -794,7 +811,7 @@ int tiled_sweep(const kge_model_t* m, const kge_model_t* mq, int dir, const int6
       for (int k = 0; k < KC; ++k) P.cand[k] = cscratch + (size_t)k * (size_t)nc * dp;
       if (KC == 1) P.cand[1] = nullptr;
       P.cand_pitch = dp;
-      if ((model == KGE_CP && !use_tc) || is_simple(model)) {  // tables differ per direction: (re)fill now
+      if (((model == KGE_CP && !use_tc) || is_simple(model)) && (phases & kSweepPost)) {  // tables differ per direction: (re)fill now
         int rc = fill_cand_scratch(m, src, KC, nc, cscratch, st);
         if (rc) return rc;
       }
@@ -820,23 +837,29 @@ int tiled_sweep(const kge_model_t* m, const kge_model_t* mq, int dir, const int6
     nslabs = (dp + DS - 1) / DS;
   }
   const size_t smem = bytes_for(DS, nslabs > 1 ? 2 : 1);
-  P.run_flag = nullptr;
+  P.tc_ctrl = nullptr; P.tc_cap = 0; P.tc_counts = nullptr;
   if (use_tc) {
     // level 1 on the tensor cores, level 2 = exact fp32 resolution of the ambiguous pairs (+ the filter
     // corrections, same kernel); the fp32 sweep below stays enqueued as the fallback and returns at once
     // unless the pair list overflowed
     TcDirBuffers B;
-    int rc = tc_sweep(m, dir, Q, nc, tc_ws_ptr(m, ws, Q), &B, tc_dbg, st);
-    if (rc) return rc;
-    if (tc_tau_out) {   // probe: [Q][4] band coefficients, then the nc candidate norm bounds
-      KGE_CUDA_OK(cudaMemcpyAsync(tc_tau_out, B.tau, (size_t)Q * 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-      KGE_CUDA_OK(cudaMemcpyAsync(tc_tau_out + (size_t)Q * 4, B.cn, (size_t)nc * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    tc_dir_buffers(m, dir, Q, tc_ws_ptr(m, ws, Q), &B);
+    if (phases & kSweepTc) {
+      int rc = tc_sweep(m, dir, tc_both ? 2 : 1, Q, nc, tc_ws_ptr(m, ws, Q), tc_dbg, st);
+      if (rc) return rc;
+      if (tc_tau_out) {   // probe: [Q][4] band coefficients, then the nc candidate norm bounds
+        KGE_CUDA_OK(cudaMemcpyAsync(tc_tau_out, B.tau, (size_t)Q * 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        KGE_CUDA_OK(cudaMemcpyAsync(tc_tau_out + (size_t)Q * 4, B.cn, (size_t)nc * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      }
     }
-    RankFilter none = {nullptr, nullptr, 0, nullptr, 0, 0};
-    rc = band_resolve(m, mq, dir, qh, qr, qt, thr, Q, B, filter ? *filter : none, counts, col, st);
-    if (rc) return rc;
-    P.run_flag = B.ctrl + 3;
+    if (phases & kSweepPost) {
+      RankFilter none = {nullptr, nullptr, 0, nullptr, 0, 0};
+      int rc = band_resolve(m, mq, dir, qh, qr, qt, thr, Q, B, filter ? *filter : none, counts, col, st);
+      if (rc) return rc;
+    }
+    P.tc_ctrl = B.ctrl; P.tc_cap = B.cap; P.tc_counts = B.tc_counts;
   }
+  if (!(phases & kSweepPost)) return KGE_OK;
   P.qvec = qvec; P.thr = thr; P.qscale = (model == KGE_TRANSM) ? qscale : nullptr;
   P.Q = Q; P.nc = nc; P.dp = dp; P.DS = DS; P.nslabs = nslabs;
   P.ntiles = (int)((nc + kCBLK - 1) / kCBLK);

@@ -41,6 +41,8 @@ train_hinge_kernel(ModelParams P, GradTablesT GT, const int64_t* __restrict__ ph
     TripleRows Rp, Rn;
     resolve_rows<MODEL>(Rp, P, P.tab, P.tab, P.tab, a, b, c);
     resolve_rows<MODEL>(Rn, P, P.tab, P.tab, P.tab, x, y, z);
+    prefetch_triple_rows(Rp, P.d, P.dr, lane);   // all six rows' cold misses overlap (the phases below are dependent)
+    prefetch_triple_rows(Rn, P.d, P.dr, lane);
     // CHSEL = 0: the looped (not register-cached, not unrolled-by-width) forms of the score / gradient
     // functions.  A training batch is a few hundred groups — pure latency —, and the cached forms made this
     // kernel 12,760 instructions (204 KB): ncu showed it stalled on INSTRUCTION FETCH (no_instruction 8.9 per
@@ -95,6 +97,7 @@ train_logistic_kernel(ModelParams P, GradTablesT GT, const int64_t* __restrict__
     const float yy = (float)__ldg(y + g);
     TripleRows R;
     resolve_rows<MODEL>(R, P, P.tab, P.tab, P.tab, a, b, c);
+    prefetch_triple_rows(R, P.d, P.dr, lane);
     const float s = score_group<MODEL, VEC, KGE_GROUP_TAIL, 0>(R, P, lane, scratch);
     const float x = yy * s;
     v = tl_softplus(x) * inv_n;

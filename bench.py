@@ -244,7 +244,7 @@ def run_cuda(args):
     # that step's resident inputs into those buffers plus one replay (all inside the timed region).
     graph_step = None
     kernels_per_replay = None
-    if world == 1 and not args.no_graph:
+    if not args.no_graph and (world == 1 or tr._dp == "ids"):
         # every step's resident inputs packed into ONE int64 buffer -> one D2D copy per step into the
         # static buffer the captured kernels read: [6 x B ids][qh qr qt][tail ptr][head ptr][tail idx cap][head idx cap]
         cap_t = max(x[4][1].numel() for x in devin)
@@ -276,27 +276,96 @@ def run_cuda(args):
         scratch = tr._grad_scratch
         loss_buf = torch.zeros(1, dtype=torch.float32, device=dev)
 
-        def body(lr):
+        def body_eval():
             counts.zero_()
             _lib.rank_1vsall(desc, s_q[0], s_q[1], s_q[2], (s_tp, s_ti), (s_hp, s_hi), counts=counts, workspace=ws)
-            _lib.train_pairwise_hinge_sgd(desc, scratch, *s_ids, w["margin"], lr, loss_buf)
+
+        def capture(fn, warm):
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                warm()   # un-captured warm-up (lr = 0: tables untouched)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            k0 = _lib.launch_count()
+            # (NCCL's watchdog thread may poll its events while we capture: keep the capture's legality check
+            # local to this thread when a process group is alive)
+            with torch.cuda.graph(g, capture_error_mode="thread_local" if world > 1 else "global"):
+                fn()
+            return g, _lib.launch_count() - k0
 
         load_inputs(0)
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            body(0.0)   # un-captured warm-up with lr = 0 (tables untouched)
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
-        k0 = _lib.launch_count()
-        with torch.cuda.graph(g):
-            body(w["lr"])
-        kernels_per_replay = _lib.launch_count() - k0   # our kernels inside one replay of the graph
+        if world == 1:
+            def body(lr):
+                body_eval()
+                _lib.train_pairwise_hinge_sgd(desc, scratch, *s_ids, w["margin"], lr, loss_buf)
 
-        def graph_step(i):
-            load_inputs(i)
-            g.replay()
+            g, kernels_per_replay = capture(lambda: body(w["lr"]), lambda: body(0.0))
+            # the two halves as graphs of their own, for the separately reported train / eval rates
+            g_eval, _ = capture(body_eval, body_eval)
+            g_train, _ = capture(lambda: _lib.train_pairwise_hinge_sgd(desc, scratch, *s_ids, w["margin"], w["lr"], loss_buf),
+                                 lambda: _lib.train_pairwise_hinge_sgd(desc, scratch, *s_ids, w["margin"], 0.0, loss_buf))
+
+            def graph_step(i):
+                load_inputs(i)
+                g.replay()
+
+            def train_resident(i):   # noqa: F811 — graph-replayed like the step itself
+                load_inputs(i)
+                g_train.replay()
+
+            def eval_resident(i):   # noqa: F811
+                load_inputs(i)
+                g_eval.replay()
+        else:
+            # data parallel, "ids" mode: the NCCL all-gather of the batch ids (24 KB) stays an eager call, started
+            # first; the evaluation graph runs while it is in flight; the training graph (the Trainer's own
+            # step on the gathered global batch) follows.  Three host calls per step instead of ~25.
+            s_gath = torch.zeros((world * 6, B), dtype=torch.int64, device=dev)
+            s_stack = s_in[:6 * B].view(6, B)
+
+            def glob_ids():
+                gl = s_gath.view(world, 6, B).permute(1, 0, 2).reshape(6, world * B).contiguous()
+                return [gl[k] for k in range(6)]
+
+            def body_train():
+                tr.train_batch_device(s_ids, exchanged=glob_ids)
+
+            def warm_train():
+                lr0 = tr.config.learning_rate
+                tr.config.learning_rate = 0.0
+                try:
+                    body_train()
+                finally:
+                    tr.config.learning_rate = lr0
+
+            try:
+                dist.all_gather_into_tensor(s_gath, s_stack)
+                g_eval, k_eval = capture(body_eval, body_eval)
+                g_train, k_train = capture(body_train, warm_train)
+                kernels_per_replay = k_eval + k_train
+
+                def graph_step(i):
+                    load_inputs(i)
+                    work = dist.all_gather_into_tensor(s_gath, s_stack, async_op=True)
+                    g_eval.replay()
+                    work.wait()
+                    g_train.replay()
+
+                def train_resident(i):   # noqa: F811 — exchange + graph, nothing to hide the exchange behind
+                    load_inputs(i)
+                    dist.all_gather_into_tensor(s_gath, s_stack)
+                    g_train.replay()
+
+                def eval_resident(i):   # noqa: F811
+                    load_inputs(i)
+                    g_eval.replay()
+            except Exception as exc:   # capture refused next to a live process group: the eager step still measures
+                print("bench: CUDA-graph capture of the data-parallel step failed (%s); timing it kernel by kernel"
+                      % (str(exc).splitlines()[0] if str(exc) else type(exc).__name__), file=sys.stderr)
+                graph_step = None
+                torch.cuda.synchronize()
 
     def e2e_step(i):
         ids, q, ft, fh = host[i]
@@ -442,7 +511,10 @@ def run_cuda(args):
         "dtype": "f32", "data": DATA, "config": CONFIG, "verified": verified,
         "parallelism": "dp%d (%s): tables replicated, test triples sharded, no collective in the eval step"
                        % (world, tr._dp or "single GPU"),
-        "resident_step_launch": "one D2D copy of the step's packed inputs + one CUDA-graph replay" if graph_step is not None else "kernel by kernel",
+        "resident_step_launch": ("kernel by kernel" if graph_step is None else
+                                 "one D2D copy of the step's packed inputs + one CUDA-graph replay" if world == 1 else
+                                 "one D2D copy of the step's packed inputs + the NCCL all-gather of the batch ids (eager, started "
+                                 "first) + two CUDA-graph replays (evaluation while the ids travel, then the training step)"),
         "train_triples_per_s": train_per_step * args.steps / (ms_train * 1e-3),
         "eval_scores_per_s": eval_per_step * args.steps / (ms_eval * 1e-3),
         "ms_per_train_step": ms_train / args.steps, "ms_per_eval_batch": ms_eval / args.steps,

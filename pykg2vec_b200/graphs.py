@@ -11,22 +11,32 @@ import torch
 
 
 class StagedGraph:
-    def __init__(self, device, in_words, out_like, body, in_dtype=torch.int64, warm_body=None):
+    def __init__(self, device, in_words, out_like, body, in_dtype=torch.int64, warm_body=None, pre=None,
+                 capture_error_mode="global"):
         """body(d_in) must enqueue the kernels on the current stream and return a device tensor
         shaped like `out_like` (a CPU tensor prototype) that it fully overwrites.  The staging
         buffer starts zero-filled (id 0 is always valid) and the un-captured warm-up run uses
-        `warm_body` when the real body has side effects (a training step)."""
+        `warm_body` when the real body has side effects (a training step).
+        pre(d_in): optional work that must stay OUTSIDE the graph — a collective on the staged inputs
+        (data-parallel id exchange): then the H2D copy and pre() are issued eagerly by every call and
+        the graph holds body + the D2H copy."""
         self.device = torch.device(device)
         self.h_in = torch.zeros(in_words, dtype=in_dtype).pin_memory()
         self.warm_body = warm_body
         self.d_in = torch.zeros(in_words, dtype=in_dtype, device=self.device)
         self.h_out = torch.empty_like(out_like).pin_memory()
         self.body = body
+        self.pre = pre
+        self.capture_error_mode = capture_error_mode
         self.graph = None
         self._done = None   # event of the last asynchronous replay
 
-    def _run_eager(self, body=None):
+    def _stage(self):
         self.d_in.copy_(self.h_in, non_blocking=True)
+        if self.pre is not None:
+            self.pre(self.d_in)
+
+    def _compute(self, body=None):
         d_out = (body or self.body)(self.d_in)
         self.h_out.copy_(d_out, non_blocking=True)
 
@@ -34,13 +44,16 @@ class StagedGraph:
         cur = torch.cuda.current_stream(self.device)
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            self._run_eager(self.warm_body)  # warm-up outside capture (loads kernels, sets attributes)
+        with torch.cuda.stream(side):   # warm-up outside capture (loads kernels, sets attributes)
+            self._stage()
+            self._compute(self.warm_body)
         cur.wait_stream(side)
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self._run_eager()
+        with torch.cuda.graph(g, capture_error_mode=self.capture_error_mode):
+            if self.pre is None:
+                self._stage()
+            self._compute()
         self.graph = g
         return self
 
@@ -54,6 +67,8 @@ class StagedGraph:
         """h_in must already hold the inputs.  Returns the pinned result (valid until next call).
         sync=False only enqueues the replay: the result is valid after wait_idle() (or any later
         synchronisation of the stream), so the next call's host work overlaps this one's kernels."""
+        if self.pre is not None:
+            self._stage()
         self.graph.replay()
         if sync:
             torch.cuda.current_stream(self.device).synchronize()

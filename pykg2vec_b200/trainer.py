@@ -91,7 +91,16 @@ class Trainer:
 
     def _pick_dp_mode(self):
         """'grads' (shard the scoring, all-reduce dense gradients) pays when the rows a local batch touches
-        outweigh one sweep over the tables; tiny batches exchange ids instead."""
+        outweigh one sweep over the tables; tiny batches exchange ids instead — for plain SGD only.
+
+        Replica consistency decides the rest.  In 'grads' mode every rank applies the SAME all-reduced gradient, so
+        the replicas stay bit-identical.  In 'ids' mode every rank accumulates the global batch itself with float
+        atomics (unordered): the gradients agree to rounding only.  SGD carries that rounding through unchanged
+        (w -= lr g: replicas agree to ~1e-7 relative), but Adagrad and Adam DIVIDE by a gradient magnitude, so an
+        element whose contributions cancel to ~0 can step by +-lr in opposite directions on two ranks
+        (tests/test_gpu_multi.py saw 1e-3 after three Adam steps) — those optimizers always get 'grads'."""
+        if self.config.optimizer != "sgd":
+            return "grads"
         tabs = [t for t in self.model.kge_tables() if t.requires_grad]
         table_floats = sum(t.numel() for t in tabs)
         per_triple = sum(t.shape[1] for t in tabs)
@@ -261,7 +270,8 @@ class Trainer:
 
     def _graphed_hinge_step(self, data, sync=True):
         """Pairwise hinge + SGD as ONE CUDA graph: H2D of the packed [6,B] ids from a pinned
-        buffer, the two training kernels, D2H of the loss."""
+        buffer, the two training kernels, D2H of the loss.  Data parallel in "ids" mode: the H2D copy and the
+        NCCL all-gather of the ids are issued eagerly, the graph holds the step on the gathered global batch."""
         from .graphs import StagedGraph
         B = len(data[0])
         tables = self.model.kge_tables()
@@ -271,19 +281,32 @@ class Trainer:
             desc = self.model.kge_desc()
             loss = torch.zeros(1, dtype=torch.float32, device=self.config.device)
             margin, lr = float(self.config.margin), float(self.config.learning_rate)
+            world = self._world if self._dp == "ids" else 1
+            gath = torch.zeros((world * 6, B), dtype=torch.int64, device=self.config.device) if world > 1 else None
 
             def make_body(step_lr):
                 def body(d_in):
-                    ids = d_in.view(6, B)
+                    if world > 1:   # rank-major gathered blocks -> [6, world * B]
+                        ids = gath.view(world, 6, B).permute(1, 0, 2).reshape(6, world * B).contiguous()
+                    else:
+                        ids = d_in.view(6, B)
                     self.model.kge_pre_score()   # captured with the step (Rescal's in-place normalisation)
                     _lib.train_pairwise_hinge_sgd(desc, self._grad_scratch, ids[0], ids[1], ids[2], ids[3],
                                                   ids[4], ids[5], margin, step_lr, loss)
                     return loss
                 return body
 
+            pre = None
+            if world > 1:
+                import torch.distributed as dist
+
+                def pre(d_in):
+                    dist.all_gather_into_tensor(gath, d_in.view(6, B))
+
             # the warm-up run before capture uses lr = 0: the tables are left exactly unchanged
             call = StagedGraph(self.config.device, 6 * B, torch.empty(1, dtype=torch.float32), make_body(lr),
-                               warm_body=make_body(0.0)).capture()
+                               warm_body=make_body(0.0), pre=pre,
+                               capture_error_mode="thread_local" if world > 1 else "global").capture()
             self._graphs[key] = call
         call.wait_idle()  # an earlier asynchronous step may still be reading the staging buffer
         buf = call.h_in.numpy().reshape(6, B)
@@ -361,7 +384,7 @@ class Trainer:
         D2H copy — so the caller's next host work overlaps this step's kernels."""
         self.model.train()
         data = list(data)
-        if (self._fused and getattr(self.config, "cuda_graph", True) and self._dp is None
+        if (self._fused and getattr(self.config, "cuda_graph", True) and self._dp in (None, "ids")
                 and self.model.training_strategy == TrainingStrategy.PAIRWISE_BASED
                 and self.model.model_name.lower() != "rotate" and self.config.optimizer == "sgd"
                 and len(data) == 6 and all(len(a) == len(data[0]) for a in data)):

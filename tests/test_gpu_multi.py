@@ -118,16 +118,47 @@ def _dp_worker(rank, world, port, tmp):
                 assert abs(l_dp - l_single) <= 2e-4 * max(abs(l_single), 1e-6), (model_name, opt, mode, step, l_dp, l_single)
         for mode, t_ in trs.items():
             for (ka, va), (kb, vb) in zip(t_.model.state_dict().items(), single.model.state_dict().items()):
-                np.testing.assert_allclose(va.cpu().numpy(), vb.cpu().numpy(), rtol=0, atol=3e-5, err_msg="%s %s %s %s" % (model_name, opt, mode, ka))
+                d1 = (va - vb).abs()
+                if opt == "sgd":
+                    assert float(d1.max()) <= 3e-5, (model_name, opt, mode, ka, float(d1.max()))
+                else:   # (see below: a cancelling gradient element may flip a +-lr step under Adagrad / Adam)
+                    assert float((d1 > 3e-5).float().mean()) <= 1e-3, (model_name, opt, mode, ka)
                 # "grads": every rank applies the SAME all-reduced gradient -> replicas stay bit-identical;
-                # "ids": every rank accumulates the global batch itself with float atomics (unordered) -> equal to
-                # rounding only
+                # "ids": every rank accumulates the global batch itself with float atomics (unordered): the
+                # gradients agree to rounding.  SGD carries the rounding through (replicas within 1e-6); Adagrad /
+                # Adam divide by a gradient magnitude, so an element whose contributions cancel can step by ~lr in
+                # opposite directions — which is why Trainer._pick_dp_mode never picks "ids" for them; forced here,
+                # all but a handful of elements must still agree
                 other = va.clone()
                 dist.broadcast(other, src=0)
+                diff = (other - va).abs()
                 if mode == "grads":
                     assert torch.equal(other, va), (model_name, opt, mode, ka)
+                elif opt == "sgd":
+                    assert float(diff.max()) <= 1e-6, (model_name, opt, mode, ka)
                 else:
-                    assert float((other - va).abs().max()) <= 1e-6, (model_name, opt, mode, ka)
+                    assert float((diff > 1e-6).float().mean()) <= 1e-3, (model_name, opt, mode, ka)
+                    assert float(diff.max()) <= 3 * 2 * 0.05 + 1e-6, (model_name, opt, mode, ka)   # 3 steps of +-lr
+        if opt != "sgd":   # left to itself the trainer keeps replicas bit-identical for these optimizers
+            assert make(model_name, opt, None)._dp == "grads", (model_name, opt)
+    # host API (Trainer.train_batch: pinned H2D, graph replay, D2H of the loss) in "ids" mode: the H2D copy and
+    # the id all-gather are eager, the step on the gathered batch is a CUDA graph — same tables as one process
+    # stepping on the concatenated batch through ITS graph
+    single = make("transe", "sgd", "off")
+    dp = make("transe", "sgd", "ids")
+    dp.model.load_state_dict(single.model.state_dict())
+    for step in range(4):
+        per_rank = []
+        for rk in range(world):
+            rng = np.random.RandomState(7000 + 10 * step + rk)
+            per_rank.append([rng.randint(500 if k % 3 != 1 else 7, size=B) for k in range(6)])
+        glob = [np.concatenate([per_rank[rk][k] for rk in range(world)]) for k in range(6)]
+        l_single = single.train_batch(glob)
+        l_dp = float(dp.train_batch(per_rank[rank], sync=(step % 2 == 0)))
+        assert abs(l_dp - l_single) <= 2e-4 * max(abs(l_single), 1e-6), (step, l_dp, l_single)
+    assert any(len(k) == 2 for k in dp._graphs), "the data-parallel host step must be graph-staged"
+    for (ka, va), (kb, vb) in zip(dp.model.state_dict().items(), single.model.state_dict().items()):
+        assert float((va - vb).abs().max()) <= 3e-5, ka
     dist.barrier()
     dist.destroy_process_group()
     open(os.path.join(tmp, "dp_ok%d" % rank), "w").write("ok")

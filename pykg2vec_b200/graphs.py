@@ -40,6 +40,11 @@ class StagedGraph:
         d_out = (body or self.body)(self.d_in)
         self.h_out.copy_(d_out, non_blocking=True)
 
+    def _run_eager(self, body=None):
+        """the whole call without a graph (config.cuda_graph = False)"""
+        self._stage()
+        self._compute(body)
+
     def capture(self):
         cur = torch.cuda.current_stream(self.device)
         side = torch.cuda.Stream(device=self.device)

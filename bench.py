@@ -157,6 +157,17 @@ def event_ms(torch, fn, reps, flush=None):
     return tot / reps
 
 
+# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of ONE `ncu --set full` capture of each
+# kernel at exactly the shapes timed here — the summaries are committed under profiles/ (ncu cannot run inside
+# this process, and a number printed under ncu is never a bench value).
+NCU_TRAFFIC = {
+    "tc_sweep_both": (13.101824e6 + 0.0, "profiles/r2_ncu_tc_sweep_final_summary.txt (cold caches: the 12 MB of bf16 "
+                                         "candidate operands read once from DRAM; in the step they are L2 hits)"),
+    "transe": (6.846856e9 + 19.496704e6, "profiles/r2_ncu_score_fwd_transe_staged_summary.txt"),
+    "complex": (6.801099e9 + 11.725824e6, "profiles/r2_ncu_score_fwd_complex_summary.txt"),
+}
+
+
 def gather_score_rooflines(torch, _lib, dev, pk, reps=10):
     """The fused gather+score kernels north_star's >= 60 %-of-HBM target names (TransE, ComplEx; d = 200),
     timed here on tables far larger than the 126 MB L2 with random ids.  Algorithmic bytes count what
@@ -184,7 +195,7 @@ def gather_score_rooflines(torch, _lib, dev, pk, reps=10):
                     "algorithmic_bytes_per_launch": alg,
                     "algorithmic_bytes_per_triple": "entity rows %d x %d B + 24 B ids + 4 B score (relation rows are L2-resident)"
                                                     % (2 * ntab_e, d * 4),
-                    "traffic": None})
+                    "traffic": NCU_TRAFFIC[name][0], "traffic_source": NCU_TRAFFIC[name][1]})
         del tabs, desc, h, r, t, o
         torch.cuda.empty_cache()
     return out
@@ -537,7 +548,8 @@ def run_cuda(args):
                      "algorithmic_flops_per_unit": "2*d = 400 flop per scored candidate (one length-d contraction)",
                      "executed_tensor_flops_per_launch": exec_flops,
                      "executed_frac": exec_flops / (tc_ms * 1e-3) / 1e12 / pk["bf16"],
-                     "traffic": None,
+                     "traffic": NCU_TRAFFIC["tc_sweep_both"][0] if tc_dirs == 2 else None,
+                     "traffic_source": NCU_TRAFFIC["tc_sweep_both"][1] if tc_dirs == 2 else None,
                      "note": "exact fp32 ranks need three bf16 passes (a0b0 + a0b1 + a1b0) over tiles padded to 128 x 128 x 208: "
                              "executed_frac counts those tensor flops, frac only the algorithm's 2*Q*N*d",
                      "fp32_sweep_ms_per_direction": fp32_ms, "speedup_vs_fp32_sweep": fp32_ms * tc_dirs / tc_ms},

@@ -326,12 +326,12 @@ KGE_DEV int tc_scan_chunk(const uint32_t (&v)[32], int nv, const TcBand& Bq, flo
 //   warp 1 lane 0 : issues the tcgen05.mma chain of a tile into accumulator stage t&1; tcgen05.commit
 //                   releases smem stages and publishes finished accumulators
 //   warps 2..9    : epilogue — warp w owns TMEM lanes 32*(w&3).. (= query rows) and the column half
-//                   (w-2)/4 of the tile (= 64 candidates), 32 columns per tcgen05.ld, compared with the row's
-//                   two thresholds
+//                   (w-2)/4 of the tile (= 64 candidates), 32 columns per tcgen05.ld, each compared with the
+//                   band of its (query, candidate) pair
 // PAIR: launched as clusters of two CTAs (1 x 2 x 1: same candidate tiles, adjacent query blocks).  Each CTA
 // issues the TMA loads of HALF of every candidate k-block (64 of its 128 rows) and multicasts them into both
-// CTAs' stages, so an SM requests half the rows and the L2 is read once per pair — the operand stream was the
-// bound of the single-CTA kernel (~28 B/cycle per SM of TMA row requests).  A stage is refilled only when the
+// CTAs' stages, so an SM requests half the rows and the L2 is read once per pair (a test of the hypothesis that
+// the L2->SM operand stream sets the k-block cadence: it does not, see tc_sweep()).  A stage is refilled only when the
 // MMAs of BOTH CTAs have consumed it (tcgen05.commit multicast onto both empty barriers, count 2).
 template <bool PAIR>
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -796,9 +796,8 @@ int tc_sweep(const kge_model_t* m, int dir, int ndirs, int64_t Q, int64_t nc, vo
   }
   P.cn = reinterpret_cast<const float*>(w + L.cn); P.cap = tc_list_capacity(Q);
   // k-block width: 64 columns (128-byte swizzle rows).  32-column blocks (64-byte rows) would give 7 pipeline
-  // stages instead of 3, but measured SLOWER (26.6 vs 24.5 us, profiles/r2_tc_trace_v6.jsonl): the operand
-  // stream is bound by delivered L2 bandwidth (~28 B/cycle per SM with 116 SMs pulling = 6.2 TB/s), not by
-  // latency, and 64-byte rows use it less efficiently.  KGE_TC_BK=32 keeps the variant reachable for tests.
+  // stages instead of 3, but measured SLOWER (26.6 vs 24.5 us, profiles/r2_tc_trace_v6.jsonl): prefetch depth is
+  // not what limits the k-block cadence.  KGE_TC_BK=32 keeps the variant reachable for tests.
   int bk = 64;
   if (const char* e = getenv("KGE_TC_BK")) { if (atoi(e) == 32) bk = 32; }   // tuning / test aid
   P.bk = bk;
@@ -814,7 +813,7 @@ int tc_sweep(const kge_model_t* m, int dir, int ndirs, int64_t Q, int64_t nc, vo
   // query operands in tensor memory (KGE_TC_ATMEM=1; they fit beside the two accumulators when 2 x Kp/2 <= 256
   // columns): halves the shared-memory reads of an MMA and frees 104 KB for 7 candidate stages.  Correct (tests
   // run both) but measured slower (26.6 vs 24.6 us): the per-thread fill of tensor memory costs ~5 us of prologue
-  // and the MMA cadence does not change — shared-memory bandwidth was not the bound either.
+  // and the MMA cadence does not change — the query operand's shared-memory reads alone are not the limiter either.
   P.a_tmem = 0;
   if (const char* e = getenv("KGE_TC_ATMEM")) { if (atoi(e) != 0 && P.a_resident && Kp <= 256) P.a_tmem = 1; }
   const size_t budget = 227 * 1024 - 2048;   // control block + alignment slack
@@ -838,8 +837,8 @@ int tc_sweep(const kge_model_t* m, int dir, int ndirs, int64_t Q, int64_t nc, vo
   if (const char* e = getenv("KGE_TC_EPI_MODE")) P.epi_mode = atoi(e);   // measurement aid: wrong counts unless 0
   // pair mode (KGE_TC_PAIR=1): two query blocks share every candidate tile through TMA multicast.  Correct
   // (tests run both) but measured NOT faster (24.6 vs 22.5-24.6 us, profiles/r2_tc_trace_v7_pair.jsonl,
-  // r2_tc_trace_v8_modes.txt): the k-block cadence is set by the tensor pipe (~100 cycles per 128x128x16
-  // tcgen05.mma, ~85 % of the per-SM bf16 rate the measured cuBLAS peak implies), not by the operand stream.
+  // r2_tc_trace_v8_modes.txt): halving the L2->SM stream does not move the k-block cadence (~100 cycles per
+  // 128x128x16 tcgen05.mma while the tensor pipe is busy ~56 of them: DESIGN.md 5b "What bounds it").
   bool pair = false;
   if (const char* e = getenv("KGE_TC_PAIR")) pair = atoi(e) != 0;
   const int brows = pair ? kTcBN / 2 : kTcBN;

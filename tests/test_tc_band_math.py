@@ -81,20 +81,31 @@ def band_coefficients(qvec, thr, kind, Kp, K, margin=0.0):
     return centre.astype(np.float32).astype(np.float64), a, b * infl, e * infl
 
 
-@pytest.mark.parametrize("name,d,heavy", [("distmult", 40, False), ("distmult", 64, True), ("transe", 48, False)])
+@pytest.mark.parametrize("name,d,heavy", [("distmult", 40, False), ("distmult", 64, True), ("transe", 48, False),
+                                          ("complex", 36, False), ("complex", 40, True)])
 def test_certain_pairs_agree_with_canonical_scores(name, d, heavy):
     import oracle
     N, R, Q = 900, 5, 24
     om, tabs = gpu.synthetic_case(name, N, R, d, seed=3 * d)
     if heavy:   # a quarter of the entity rows 8x heavier: the band of a pair must scale with ITS candidate
         rows = np.random.RandomState(1).choice(N, N // 4, replace=False)
-        tabs[0][rows] *= 8.0
+        for k in range(2 if name == "complex" else 1):
+            tabs[k][rows] *= 8.0
         om = oracle.Model(name, tabs, d)
     rng = np.random.RandomState(d)
     qh, qr = rng.randint(N, size=Q), rng.randint(R, size=Q)
     qt = rng.randint(N, size=Q)
     ent, rel = tabs[0], tabs[1]
-    if name == "distmult":
+    if name == "complex":   # tail direction: score = -(e_re . a + e_im . b), a = hr rr - hi ri, b = hi rr + hr ri
+        er, ei, rr, ri = tabs
+        kind, K = 0, 2 * d
+        f = np.float32
+        qa = (er[qh] * rr[qr]).astype(f) - (ei[qh] * ri[qr]).astype(f)
+        qb = (ei[qh] * rr[qr]).astype(f) + (er[qh] * ri[qr]).astype(f)
+        qvec = np.concatenate([qa.astype(f), qb.astype(f)], axis=1)
+        cand = np.concatenate([er, ei], axis=1)
+        aug_q = aug_c = None
+    elif name == "distmult":
         kind, K = 0, d
         qvec = (ent[qh] * rel[qr]).astype(np.float32)     # tail direction: score = -(h o r) . t
         cand = ent

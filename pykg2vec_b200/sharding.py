@@ -132,6 +132,7 @@ class RowShardedRanker:
         self.ent_local = list(entity_tables_local)
         self.rel = list(relation_tables)
         self.ent_slots, self.rel_slots = tuple(ent_slots), tuple(rel_slots)
+        self._bufs = {}
         for t in self.ent_local:
             assert t.shape[0] == self.row_hi - self.row_lo, "local shard has the wrong row count"
 
@@ -144,46 +145,90 @@ class RowShardedRanker:
             out[s] = t
         return out
 
+    def _owner_layout(self, uniq):
+        """Owners of the SORTED global ids `uniq`: rank g owns uniq[starts[g]:starts[g+1]] (its row range);
+        cap = the largest block (the all-gather's common block size)."""
+        bounds = [shard_range(self.num_ent, self.world, g) for g in range(self.world)]
+        starts = np.array([np.searchsorted(uniq, lo) for lo, _ in bounds] + [len(uniq)], dtype=np.int64)
+        cap = max(int((starts[1:] - starts[:-1]).max()), 1)
+        return starts, cap
+
+    def _gather_owner_blocks(self, mine, cap):
+        """One all-gather per entity table of the owners' rows: -> per table a [world * cap, d] buffer whose
+        block g holds rank g's rows (block-padded: rows beyond a rank's count are never addressed)."""
+        out = []
+        for t in self.ent_local:
+            key = (cap, t.shape[1], t.dtype, t.device)
+            bufs = self._bufs.get(key)
+            if bufs is None:   # (re)used across calls: no allocation, no zero fill on the path
+                bufs = (torch.empty((cap, t.shape[1]), dtype=t.dtype, device=t.device),
+                        [torch.empty((self.world * cap, t.shape[1]), dtype=t.dtype, device=t.device)
+                         for _ in self.ent_local])
+                self._bufs[key] = bufs
+            send, recvs = bufs
+            if mine.numel():
+                torch.index_select(t, 0, mine, out=send[:mine.numel()])
+            recv = recvs[len(out)]
+            if self.world == 1:
+                recv.copy_(send)
+            else:
+                dist.all_gather_into_tensor(recv, send)
+            out.append(recv)
+        return out
+
     def exchange_query_rows(self, uniq):
         """Compact table of the rows `uniq` (SORTED global ids) of every entity table, identical on all
         ranks.  Rank g owns the contiguous slice of `uniq` that falls in its row range, so one
-        all-gather per table of the owners' blocks (padded to the largest block) concatenates into the
-        compact table — no zero-padded sum, every row travels once."""
+        all-gather per table of the owners' blocks (padded to the largest block) holds every row exactly
+        once — no zero-padded sum.  (rank_queries addresses the gathered blocks in place; this form
+        concatenates them into the compact [len(uniq), d] table.)"""
         dev = self.ent_local[0].device
         uniq = np.ascontiguousarray(uniq, dtype=np.int64)
-        bounds = [shard_range(self.num_ent, self.world, g) for g in range(self.world)]
-        starts = [int(np.searchsorted(uniq, lo)) for lo, _ in bounds] + [len(uniq)]
-        counts = [starts[g + 1] - starts[g] for g in range(self.world)]
-        cap = max(max(counts), 1)
+        starts, cap = self._owner_layout(uniq)
         mine = torch.as_tensor(uniq[starts[self.rank]:starts[self.rank + 1]] - self.row_lo, dtype=torch.long, device=dev)
-        compact = []
-        for t in self.ent_local:
-            if self.world == 1:
-                compact.append(t[mine].contiguous())
-                continue
-            send = torch.zeros((cap, t.shape[1]), dtype=t.dtype, device=dev)
-            send[:mine.numel()] = t[mine]
-            recv = torch.empty((self.world * cap, t.shape[1]), dtype=t.dtype, device=dev)
-            dist.all_gather_into_tensor(recv, send)
-            recv = recv.view(self.world, cap, t.shape[1])
-            compact.append(torch.cat([recv[g, :counts[g]] for g in range(self.world)], dim=0))
-        return compact
+        blocks = self._gather_owner_blocks(mine, cap)
+        counts = (starts[1:] - starts[:-1]).tolist()
+        return [torch.cat([r.view(self.world, cap, -1)[g, :counts[g]] for g in range(self.world)], dim=0) for r in blocks]
 
     def rank_queries(self, qh, qr, qt, filt_t=None, filt_h=None):
         """qh/qr/qt: numpy int64 global ids (identical on all ranks).  filt_*: CSR numpy
-        (ptr, idx) with global ids or None.  Returns [Q,4] int32 global ranks on every rank."""
+        (ptr, idx) with global ids or None.  Returns [Q,4] int32 global ranks on every rank.
+
+        Host path: ONE copy carries every integer array of the call to the device; the query rows are addressed
+        inside the gathered owner blocks (index = owner * cap + position in the owner's block), so nothing is
+        concatenated or zero-filled; send / receive buffers are reused across calls."""
         dev = self.ent_local[0].device
         qh = np.ascontiguousarray(qh, dtype=np.int64)
+        qr = np.ascontiguousarray(qr, dtype=np.int64)
         qt = np.ascontiguousarray(qt, dtype=np.int64)
         uniq = np.unique(np.concatenate([qh, qt]))
-        compact_ent = self.exchange_query_rows(uniq)
-        qh_c = torch.from_numpy(np.searchsorted(uniq, qh)).to(dev)
-        qt_c = torch.from_numpy(np.searchsorted(uniq, qt)).to(dev)
-        to = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int64)).to(dev)
-        ft = (to(filt_t[0]), to(filt_t[1])) if filt_t is not None else None
-        fh = (to(filt_h[0]), to(filt_h[1])) if filt_h is not None else None
-        counts = self.count_fn(self._assemble(self.ent_local), self._assemble(compact_ent), self.row_lo,
-                               self.row_hi, qh_c, to(qr), qt_c, to(qh), to(qt), ft, fh)
+        starts, cap = self._owner_layout(uniq)
+
+        def block_index(ids):   # position of each id's row in the [world * cap, d] gathered buffer
+            pos = np.searchsorted(uniq, ids)
+            owner = np.searchsorted(starts, pos, side="right") - 1
+            return owner * cap + (pos - starts[owner])
+
+        mine = uniq[starts[self.rank]:starts[self.rank + 1]] - self.row_lo
+        parts = [block_index(qh), block_index(qt), qr, qh, qt, mine]
+        for f in (filt_t, filt_h):
+            if f is not None:
+                parts += [np.ascontiguousarray(f[0], dtype=np.int64), np.ascontiguousarray(f[1], dtype=np.int64)]
+        packed = torch.from_numpy(np.concatenate(parts)).to(dev)
+        views, o = [], 0
+        for a in parts:
+            views.append(packed[o:o + len(a)])
+            o += len(a)
+        qh_c, qt_c, qr_d, qh_d, qt_d, mine_d = views[:6]
+        rest = views[6:]
+        ft = fh = None
+        if filt_t is not None:
+            ft, rest = (rest[0], rest[1]), rest[2:]
+        if filt_h is not None:
+            fh = (rest[0], rest[1])
+        blocks = self._gather_owner_blocks(mine_d, cap)
+        counts = self.count_fn(self._assemble(self.ent_local), self._assemble(blocks), self.row_lo,
+                               self.row_hi, qh_c, qr_d, qt_c, qh_d, qt_d, ft, fh)
         if self.world > 1:
             # the single exchange of the sweep: ONE all-gather of the partial rank counts, summed locally
             # (exact: integer counts of bit-identical scores over disjoint row shards)

@@ -26,12 +26,11 @@ KGE_DEV void prefetch_row_lines(const float* row, int nfloats, int lane) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
 }
 KGE_DEV void prefetch_triple_rows(const TripleRows& R, int d, int dr, int lane) {
-#pragma unroll
-  for (int k = 0; k < 2; ++k) {   // (rows [2..] exist for the hypercomplex models only: not used by the callers)
-    prefetch_row_lines(R.h[k], d, lane);
-    prefetch_row_lines(R.t[k], d, lane);
-    prefetch_row_lines(R.r[k], dr, lane);
-  }
+  // slot 0 only: in every model these rows are exactly d (h / t side) and >= dr (r side) floats wide, so no
+  // request leaves its row; the further slots differ per model (ANALOGY's are d/2 wide) and are left alone
+  prefetch_row_lines(R.h[0], d, lane);
+  prefetch_row_lines(R.t[0], d, lane);
+  prefetch_row_lines(R.r[0], dr, lane);
 }
 
 // Row pointers of triple (h, r, t).  htab/ttab/rtab: the table sets the head-side,

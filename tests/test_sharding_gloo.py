@@ -201,6 +201,11 @@ def _dp_worker(rank, world, port, tmp):
     assert auto._pick_dp_mode() == "ids"
     auto.config.batch_size = 4096
     assert auto._pick_dp_mode() == "grads"
+    # optimizers that divide by a gradient magnitude never exchange ids (replicas would drift, trainer.py)
+    for opt in ("adagrad", "adam"):
+        t_ = make(opt, None)
+        t_.config.batch_size = 8
+        assert t_._dp == "grads" and t_._pick_dp_mode() == "grads", opt
     for opt in ("sgd", "adagrad", "adam"):
         single = make(opt, "off")
         trs = {mode: make(opt, mode) for mode in ("grads", "ids")}
